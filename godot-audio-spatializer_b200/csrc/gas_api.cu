@@ -1,0 +1,716 @@
+// gas_api.cu — the C ABI (include/gas.h): context, device memory, stream ordering, validation.
+// Host code only; every data-path operation is a kernel launched from the other .cu files.
+// There is no CPU implementation of anything here: without a CUDA device gas_create fails.
+#include "gas_internal.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+static thread_local std::string g_create_error;
+
+int gas_fail(gas_ctx *ctx, int status, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (ctx) {
+		ctx->err = buf;
+	} else {
+		g_create_error = buf;
+	}
+	return status;
+}
+
+namespace {
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t n) {
+	cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+	if (e == cudaSuccess) {
+		e = cudaMemset(*p, 0, n * sizeof(T));
+	}
+	return e;
+}
+
+void refresh_globals(gas_ctx *ctx) {
+	ctx->g.speaker_mode = ctx->cfg.speaker_mode;
+	ctx->g.channels = ctx->cfg.speaker_mode + 1;
+	ctx->g.num_buses = ctx->cfg.num_buses;
+	ctx->g.mix_rate = ctx->cfg.mix_rate;
+	ctx->g.global_panning = ctx->cfg.global_panning_strength;
+	ctx->g.max_instances = ctx->cfg.max_instances;
+	ctx->g.max_voices = ctx->cfg.max_voices;
+	ctx->g.max_spatializers = ctx->cfg.max_spatializers;
+}
+
+// Stream ordering between the gain side and the mix side (the reference's physics / audio threads):
+// the tiny per-block prologue is the only mix-side kernel that reads instance tables, so gain-side work
+// waits for the last prologue and the next prologue waits for the last gain-side work.
+int gain_side_begin(gas_ctx *ctx) {
+	if (ctx->prologue_pending) {
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_gain, ctx->ev_prologue_done, 0));
+	}
+	return GAS_OK;
+}
+int gain_side_end(gas_ctx *ctx) {
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_gain_done, ctx->s_gain));
+	ctx->gain_pending = true;
+	return GAS_OK;
+}
+
+bool ids_valid(const int32_t *ids, int n, int limit) {
+	for (int i = 0; i < n; i++) {
+		if (ids[i] < 0 || ids[i] >= limit) {
+			return false;
+		}
+	}
+	return true;
+}
+
+bool spat_valid(const gas_spatializer *s) { // reference audio_spatializer_3d.cpp:670-672,695-697,728-730,737-739,758-760
+	if (s->kind != GAS_SPATIALIZER_3D && s->kind != GAS_SPATIALIZER_EFFECT) {
+		return false;
+	}
+	if (!(s->max_distance >= 0.0f)) {
+		return false;
+	}
+	if (!(s->emission_angle >= 0.f && s->emission_angle <= 90.f)) {
+		return false;
+	}
+	if (s->attenuation_model < 0 || s->attenuation_model >= 4) {
+		return false;
+	}
+	if (!(s->panning_strength >= 0.f)) {
+		return false;
+	}
+	if (!(s->doppler_speed_of_sound > 0.f)) {
+		return false;
+	}
+	if (s->chain.n_effects < 0 || s->chain.n_effects > GAS_MAX_EFFECTS) {
+		return false;
+	}
+	return true;
+}
+
+int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_frame *d_src, int src_stride, int frames,
+		gas_frame *d_bus, gas_frame *d_peaks) {
+	if (ctx->gain_pending) {
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
+	}
+	GAS_CUDA(ctx, launch_prologue(ctx, n_voices, d_voices, frames, d_bus, d_peaks, ctx->s_mix));
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix));
+	ctx->prologue_pending = true;
+	if (n_voices > 0) {
+		GAS_CUDA(ctx, launch_mix_stream(ctx, d_src, src_stride, frames, d_bus, ctx->s_mix));
+		GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_mix));
+	}
+	return GAS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int gas_abi_version(void) { return GAS_ABI_VERSION; }
+
+size_t gas_abi_sizeof(int32_t id) {
+	switch (id) {
+		case GAS_STRUCT_FRAME: return sizeof(gas_frame);
+		case GAS_STRUCT_EFFECT: return sizeof(gas_effect);
+		case GAS_STRUCT_EFFECT_CHAIN: return sizeof(gas_effect_chain);
+		case GAS_STRUCT_SPATIALIZER: return sizeof(gas_spatializer);
+		case GAS_STRUCT_LISTENER: return sizeof(gas_listener);
+		case GAS_STRUCT_AREA: return sizeof(gas_area);
+		case GAS_STRUCT_EMITTER: return sizeof(gas_emitter);
+		case GAS_STRUCT_PARAMS: return sizeof(gas_params);
+		case GAS_STRUCT_VOICE: return sizeof(gas_voice);
+		case GAS_STRUCT_PROCESSOR_STATE: return sizeof(gas_processor_state);
+		case GAS_STRUCT_VOICE_STATE: return sizeof(gas_voice_state);
+		case GAS_STRUCT_CONFIG: return sizeof(gas_config);
+		default: return 0;
+	}
+}
+
+void gas_config_defaults(gas_config *c) {
+	if (!c) {
+		return;
+	}
+	c->device = 0;
+	c->max_instances = 1024;
+	c->max_voices = 1024;
+	c->max_frames = 512; // upstream AudioServer buffer size
+	c->max_spatializers = 16;
+	c->num_buses = 2;
+	c->speaker_mode = GAS_SPEAKER_MODE_STEREO;
+	c->mix_rate = 44100.0f;
+	c->global_panning_strength = 0.5f;
+}
+
+void gas_spatializer_defaults(gas_spatializer *s) { // reference audio_spatializer_3d.h:171-188
+	if (!s) {
+		return;
+	}
+	memset(s, 0, sizeof(*s));
+	s->kind = GAS_SPATIALIZER_3D;
+	s->attenuation_model = GAS_ATTENUATION_INVERSE_DISTANCE;
+	s->unit_size = 10.0f;
+	s->max_distance = 0.0f;
+	s->panning_strength = 1.0f;
+	s->area_mask = 1;
+	s->emission_angle_enabled = 0;
+	s->emission_angle = 45.0f;
+	s->emission_angle_filter_attenuation_db = -12.0f;
+	s->attenuation_filter_cutoff_hz = 5000.0f;
+	s->attenuation_filter_db = -24.0f;
+	s->doppler_tracking = GAS_DOPPLER_TRACKING_DISABLED;
+	s->doppler_speed_of_sound = 343.0f;
+	s->mix_channel_mode = 0;
+	s->effect_gain_binding = -1;
+}
+
+const char *gas_last_error(const gas_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gas_create(const gas_config *cfg, gas_ctx **out) {
+	if (out) {
+		*out = nullptr;
+	}
+	if (!cfg || !out) {
+		return gas_fail(nullptr, GAS_ERR_INVALID, "gas_create: null argument");
+	}
+	if (cfg->max_instances <= 0 || cfg->max_voices <= 0 || cfg->max_frames < 2 || (cfg->max_frames & 1) || cfg->max_spatializers <= 0 ||
+			cfg->num_buses < 1 || cfg->num_buses > GAS_MAX_BUSES || cfg->speaker_mode < 0 || cfg->speaker_mode > 3 || !(cfg->mix_rate > 0.f)) {
+		return gas_fail(nullptr, GAS_ERR_INVALID, "gas_create: invalid configuration");
+	}
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev <= 0) {
+		return gas_fail(nullptr, GAS_ERR_NO_DEVICE, "gas_create: no CUDA device (%s); this library has no CPU fallback",
+				e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+	}
+	if (cfg->device < 0 || cfg->device >= ndev) {
+		return gas_fail(nullptr, GAS_ERR_INVALID, "gas_create: device %d out of range (%d devices)", cfg->device, ndev);
+	}
+	cudaDeviceProp prop;
+	e = cudaGetDeviceProperties(&prop, cfg->device);
+	if (e != cudaSuccess) {
+		return gas_fail(nullptr, GAS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+	}
+	if (prop.major != 10) {
+		return gas_fail(nullptr, GAS_ERR_NO_DEVICE, "gas_create: device %d is sm_%d%d; the kernels are built for sm_100a only", cfg->device,
+				prop.major, prop.minor);
+	}
+	e = cudaSetDevice(cfg->device);
+	if (e != cudaSuccess) {
+		return gas_fail(nullptr, GAS_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+	}
+	gas_ctx *ctx = new (std::nothrow) gas_ctx();
+	if (!ctx) {
+		return gas_fail(nullptr, GAS_ERR_NOMEM, "gas_create: out of host memory");
+	}
+	ctx->cfg = *cfg;
+	ctx->device = cfg->device;
+	ctx->num_sms = prop.multiProcessorCount;
+	ctx->l2_bytes = prop.l2CacheSize;
+	refresh_globals(ctx);
+
+	const size_t I = cfg->max_instances, V = cfg->max_voices, F = cfg->max_frames;
+	const size_t nscratch_ids = (I > V ? I : V);
+	ctx->max_areas = 1024;
+	ctx->scratch_bytes = V * sizeof(gas_voice_state);
+	if (ctx->scratch_bytes < I * sizeof(gas_params)) {
+		ctx->scratch_bytes = I * sizeof(gas_params);
+	}
+	bool ok = true;
+#define ALLOC(ptr, n) ok = ok && (dev_alloc(&(ptr), (n)) == cudaSuccess)
+	ALLOC(ctx->t.spat, (size_t)cfg->max_spatializers);
+	ALLOC(ctx->t.inst_spat, I);
+	ALLOC(ctx->t.inst_params, I);
+	ALLOC(ctx->t.inst_was_further, I);
+	ALLOC(ctx->t.inst_active, I);
+	ALLOC(ctx->t.inst_cur, I);
+	ALLOC(ctx->t.inst_prev, I);
+	ALLOC(ctx->t.inst_fx, I);
+	ALLOC(ctx->t.inst_sends, I);
+	ALLOC(ctx->t.vs_prev, V * 8);
+	ALLOC(ctx->t.vs_proc, V * 8);
+	ALLOC(ctx->t.vs_fx, V * (size_t)(GAS_MAX_EFFECTS * 2 * GAS_MAX_FILTER_STAGES * 4));
+	ALLOC(ctx->plan.cls, (size_t)GAS_MAX_CLASSES);
+	ALLOC(ctx->plan.n_cls, (size_t)1);
+	ALLOC(ctx->plan.overflow, (size_t)1);
+	ALLOC(ctx->plan.k2_src, (size_t)GAS_MAX_CLASSES * V);
+	ALLOC(ctx->plan.k2_rows, (size_t)GAS_MAX_CLASSES * V * GAS_K2_ROW_FLOATS + 64);
+	ALLOC(ctx->plan.k3_list, (size_t)GAS_MAX_CLASSES * V);
+	ALLOC(ctx->plan.rec, V);
+	ALLOC(ctx->d_voices, V);
+	ALLOC(ctx->d_src, V * F);
+	ALLOC(ctx->d_bus, (size_t)GAS_MAX_BUSES * GAS_MAX_CHANNELS_PER_BUS * F);
+	ALLOC(ctx->d_peaks, V);
+	ALLOC(ctx->d_emitters, I);
+	ALLOC(ctx->d_listeners, (size_t)GAS_MAX_LISTENERS);
+	ALLOC(ctx->d_areas, (size_t)ctx->max_areas);
+	ALLOC(ctx->d_params_out, I);
+	ALLOC(ctx->d_ids, nscratch_ids);
+	ALLOC(ctx->d_ids2, nscratch_ids);
+	{
+		unsigned char *p = nullptr;
+		ok = ok && (dev_alloc(&p, ctx->scratch_bytes) == cudaSuccess);
+		ctx->d_scratch = p;
+	}
+#undef ALLOC
+	ok = ok && cudaStreamCreateWithFlags(&ctx->s_mix, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&ctx->s_gain, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_gain_done, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_prologue_done, cudaEventDisableTiming) == cudaSuccess;
+	if (ok) {
+		ok = launch_defaults(ctx, ctx->s_gain) == cudaSuccess && cudaStreamSynchronize(ctx->s_gain) == cudaSuccess;
+	}
+	if (!ok) {
+		cudaError_t le = cudaGetLastError();
+		int st = gas_fail(nullptr, le == cudaErrorMemoryAllocation ? GAS_ERR_NOMEM : GAS_ERR_CUDA, "gas_create: device setup failed (%s)",
+				cudaGetErrorString(le));
+		gas_destroy(ctx);
+		return st;
+	}
+	*out = ctx;
+	return GAS_OK;
+}
+
+void gas_destroy(gas_ctx *ctx) {
+	if (!ctx) {
+		return;
+	}
+	cudaSetDevice(ctx->device);
+	if (ctx->s_mix) {
+		cudaStreamSynchronize(ctx->s_mix);
+	}
+	if (ctx->s_gain) {
+		cudaStreamSynchronize(ctx->s_gain);
+	}
+	gas_comm_close(ctx);
+	void *ptrs[] = { ctx->t.spat, ctx->t.inst_spat, ctx->t.inst_params, ctx->t.inst_was_further, ctx->t.inst_active, ctx->t.inst_cur,
+		ctx->t.inst_prev, ctx->t.inst_fx, ctx->t.inst_sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls, ctx->plan.n_cls,
+		ctx->plan.overflow, ctx->plan.k2_src, ctx->plan.k2_rows, ctx->plan.k3_list, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
+		ctx->d_peaks, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
+		ctx->d_exchange };
+	for (void *p : ptrs) {
+		if (p) {
+			cudaFree(p);
+		}
+	}
+	if (ctx->ev_gain_done) {
+		cudaEventDestroy(ctx->ev_gain_done);
+	}
+	if (ctx->ev_prologue_done) {
+		cudaEventDestroy(ctx->ev_prologue_done);
+	}
+	if (ctx->s_mix) {
+		cudaStreamDestroy(ctx->s_mix);
+	}
+	if (ctx->s_gain) {
+		cudaStreamDestroy(ctx->s_gain);
+	}
+	delete ctx;
+}
+
+#define ENTER(ctx)                                                          \
+	if (!(ctx)) {                                                           \
+		return gas_fail(nullptr, GAS_ERR_INVALID, "%s: null context", __func__); \
+	}                                                                       \
+	std::lock_guard<std::mutex> _lk((ctx)->mu);                             \
+	GAS_CUDA(ctx, cudaSetDevice((ctx)->device))
+
+int gas_set_speaker_mode(gas_ctx *ctx, int32_t mode) {
+	ENTER(ctx);
+	if (mode < 0 || mode > 3) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_set_speaker_mode: mode %d out of range", mode);
+	}
+	ctx->cfg.speaker_mode = mode;
+	refresh_globals(ctx);
+	return GAS_OK;
+}
+
+int gas_set_mix_rate(gas_ctx *ctx, float hz) {
+	ENTER(ctx);
+	if (!(hz > 0.f)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_set_mix_rate: rate must be positive");
+	}
+	ctx->cfg.mix_rate = hz;
+	refresh_globals(ctx);
+	return GAS_OK;
+}
+
+int gas_set_global_panning_strength(gas_ctx *ctx, float s) {
+	ENTER(ctx);
+	ctx->cfg.global_panning_strength = s;
+	refresh_globals(ctx);
+	return GAS_OK;
+}
+
+int gas_get_channel_count(const gas_ctx *ctx) { return ctx ? ctx->cfg.speaker_mode + 1 : 0; }
+
+int gas_spatializer_set(gas_ctx *ctx, int32_t slot, const gas_spatializer *s) {
+	ENTER(ctx);
+	if (slot < 0 || slot >= ctx->cfg.max_spatializers || !s) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_spatializer_set: bad slot or null");
+	}
+	if (!spat_valid(s)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_spatializer_set: property out of range (max_distance>=0, emission_angle in [0,90], attenuation_model<4, panning_strength>=0, doppler_speed_of_sound>0)");
+	}
+	int st = gain_side_begin(ctx);
+	if (st) {
+		return st;
+	}
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->t.spat + slot, s, sizeof(*s), cudaMemcpyHostToDevice, ctx->s_gain));
+	return gain_side_end(ctx);
+}
+
+int gas_instance_init(gas_ctx *ctx, int32_t n, const int32_t *instances, const int32_t *spatializers) {
+	ENTER(ctx);
+	if (n < 0 || n > ctx->cfg.max_instances || (n > 0 && (!instances || !spatializers)) || !ids_valid(instances, n, ctx->cfg.max_instances) ||
+			!ids_valid(spatializers, n, ctx->cfg.max_spatializers)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_instance_init: bad instance or spatializer slot");
+	}
+	int st = gain_side_begin(ctx);
+	if (st) {
+		return st;
+	}
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, instances, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_gain));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids2, spatializers, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_gain));
+	GAS_CUDA(ctx, launch_instance_init(ctx, n, ctx->d_ids, ctx->d_ids2, ctx->s_gain));
+	for (int i = 0; i < n; i++) {
+		if (instances[i] + 1 > ctx->inst_hwm) {
+			ctx->inst_hwm = instances[i] + 1;
+		}
+	}
+	return gain_side_end(ctx);
+}
+
+static int instance_list_op(gas_ctx *ctx, int32_t n, const int32_t *instances, bool start, const char *who) {
+	if (n < 0 || n > ctx->cfg.max_instances || (n > 0 && !instances) || !ids_valid(instances, n, ctx->cfg.max_instances)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "%s: bad instance slot", who);
+	}
+	int st = gain_side_begin(ctx);
+	if (st) {
+		return st;
+	}
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, instances, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_gain));
+	if (start) {
+		GAS_CUDA(ctx, launch_instance_start(ctx, n, ctx->d_ids, ctx->s_gain));
+		for (int i = 0; i < n; i++) {
+			if (instances[i] + 1 > ctx->inst_hwm) {
+				ctx->inst_hwm = instances[i] + 1;
+			}
+		}
+	} else {
+		GAS_CUDA(ctx, launch_instance_stop(ctx, n, ctx->d_ids, ctx->s_gain));
+	}
+	return gain_side_end(ctx);
+}
+
+int gas_instance_start(gas_ctx *ctx, int32_t n, const int32_t *instances) {
+	ENTER(ctx);
+	return instance_list_op(ctx, n, instances, true, "gas_instance_start");
+}
+
+int gas_instance_stop(gas_ctx *ctx, int32_t n, const int32_t *instances) {
+	ENTER(ctx);
+	return instance_list_op(ctx, n, instances, false, "gas_instance_stop");
+}
+
+int gas_voice_init(gas_ctx *ctx, int32_t n, const int32_t *voices) {
+	ENTER(ctx);
+	if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && !voices) || !ids_valid(voices, n, ctx->cfg.max_voices)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_init: bad voice slot");
+	}
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, launch_voice_init(ctx, n, ctx->d_ids, ctx->s_mix));
+	return GAS_OK;
+}
+
+static int gain_common(gas_ctx *ctx, int32_t n, const gas_emitter *d_em, int32_t n_listeners, const gas_listener *listeners, int32_t n_areas,
+		const gas_area *areas, gas_params *d_out) {
+	if (n_listeners < 0 || n_listeners > GAS_MAX_LISTENERS || (n_listeners > 0 && !listeners)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute: 0..%d listeners", GAS_MAX_LISTENERS);
+	}
+	if (n_areas < 0 || n_areas > ctx->max_areas || (n_areas > 0 && !areas)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute: 0..%d areas", ctx->max_areas);
+	}
+	if (n_listeners > 0) {
+		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_listeners, listeners, n_listeners * sizeof(gas_listener), cudaMemcpyHostToDevice, ctx->s_gain));
+	}
+	if (n_areas > 0) {
+		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_areas, areas, n_areas * sizeof(gas_area), cudaMemcpyHostToDevice, ctx->s_gain));
+	}
+	GAS_CUDA(ctx, launch_gain(ctx, n, d_em, n_listeners, ctx->d_listeners, ctx->d_areas, d_out, ctx->s_gain));
+	return GAS_OK;
+}
+
+int gas_gain_compute(gas_ctx *ctx, int32_t n, const gas_emitter *emitters, int32_t n_listeners, const gas_listener *listeners,
+		int32_t n_areas, const gas_area *areas, gas_params *out_params) {
+	{
+		ENTER(ctx);
+		if (n < 0 || n > ctx->cfg.max_instances || (n > 0 && !emitters)) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute: 0..max_instances emitters");
+		}
+		for (int i = 0; i < n; i++) {
+			const gas_emitter &e = emitters[i];
+			if (e.instance < 0 || e.instance >= ctx->cfg.max_instances || e.spatializer < 0 || e.spatializer >= ctx->cfg.max_spatializers ||
+					e.area >= n_areas) {
+				return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute: emitter %d references a bad instance/spatializer/area", i);
+			}
+		}
+		int st = gain_side_begin(ctx);
+		if (st) {
+			return st;
+		}
+		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_emitters, emitters, n * sizeof(gas_emitter), cudaMemcpyHostToDevice, ctx->s_gain));
+		st = gain_common(ctx, n, ctx->d_emitters, n_listeners, listeners, n_areas, areas, out_params ? ctx->d_params_out : nullptr);
+		if (st) {
+			return st;
+		}
+		if (out_params && n > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(out_params, ctx->d_params_out, n * sizeof(gas_params), cudaMemcpyDeviceToHost, ctx->s_gain));
+		}
+		st = gain_side_end(ctx);
+		if (st) {
+			return st;
+		}
+	}
+	if (out_params) {
+		GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_gain));
+	}
+	return GAS_OK;
+}
+
+int gas_gain_compute_device(gas_ctx *ctx, int32_t n, const gas_emitter *d_emitters, int32_t n_listeners, const gas_listener *listeners,
+		int32_t n_areas, const gas_area *areas, gas_params *d_out_params) {
+	ENTER(ctx);
+	if (n < 0 || n > ctx->cfg.max_instances || (n > 0 && !d_emitters)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute_device: 0..max_instances emitters");
+	}
+	int st = gain_side_begin(ctx);
+	if (st) {
+		return st;
+	}
+	st = gain_common(ctx, n, d_emitters, n_listeners, listeners, n_areas, areas, d_out_params);
+	if (st) {
+		return st;
+	}
+	return gain_side_end(ctx);
+}
+
+int gas_params_set(gas_ctx *ctx, int32_t n, const int32_t *instances, const gas_params *params) {
+	ENTER(ctx);
+	if (n < 0 || n > ctx->cfg.max_instances || (n > 0 && (!instances || !params)) || !ids_valid(instances, n, ctx->cfg.max_instances)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_params_set: bad instance slot");
+	}
+	for (int i = 0; i < n; i++) {
+		if (params[i].n_bus < 0 || params[i].n_bus > GAS_MAX_BUSES_PER_PLAYBACK) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_params_set: n_bus must be 0..%d", GAS_MAX_BUSES_PER_PLAYBACK);
+		}
+	}
+	int st = gain_side_begin(ctx);
+	if (st) {
+		return st;
+	}
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, instances, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_gain));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, params, n * sizeof(gas_params), cudaMemcpyHostToDevice, ctx->s_gain));
+	GAS_CUDA(ctx, launch_params_set(ctx, n, ctx->d_ids, (const gas_params *)ctx->d_scratch, ctx->s_gain));
+	return gain_side_end(ctx);
+}
+
+int gas_params_get(gas_ctx *ctx, int32_t n, const int32_t *instances, gas_params *out) {
+	{
+		ENTER(ctx);
+		if (n < 0 || n > ctx->cfg.max_instances || (n > 0 && (!instances || !out)) || !ids_valid(instances, n, ctx->cfg.max_instances)) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_params_get: bad instance slot");
+		}
+		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, instances, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_gain));
+		GAS_CUDA(ctx, launch_params_get(ctx, n, ctx->d_ids, (gas_params *)ctx->d_scratch, ctx->s_gain));
+		if (n > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scratch, n * sizeof(gas_params), cudaMemcpyDeviceToHost, ctx->s_gain));
+		}
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_gain));
+	return GAS_OK;
+}
+
+int gas_effect_params_set(gas_ctx *ctx, int32_t n, const int32_t *instances, const gas_effect_chain *chains) {
+	ENTER(ctx);
+	if (n < 0 || n > ctx->cfg.max_instances || (n > 0 && (!instances || !chains)) || !ids_valid(instances, n, ctx->cfg.max_instances)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_effect_params_set: bad instance slot");
+	}
+	for (int i = 0; i < n; i++) {
+		if (chains[i].n_effects < 0 || chains[i].n_effects > GAS_MAX_EFFECTS) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_effect_params_set: n_effects must be 0..%d", GAS_MAX_EFFECTS);
+		}
+	}
+	int st = gain_side_begin(ctx);
+	if (st) {
+		return st;
+	}
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, instances, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_gain));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, chains, n * sizeof(gas_effect_chain), cudaMemcpyHostToDevice, ctx->s_gain));
+	GAS_CUDA(ctx, launch_fx_set(ctx, n, ctx->d_ids, (const gas_effect_chain *)ctx->d_scratch, ctx->s_gain));
+	return gain_side_end(ctx);
+}
+
+int gas_mix_block(gas_ctx *ctx, int32_t n_voices, const gas_voice *voices, const gas_frame *src, int32_t src_rows, int32_t frames,
+		gas_frame *bus_out, gas_frame *peaks) {
+	{
+		ENTER(ctx);
+		if (n_voices < 0 || n_voices > ctx->cfg.max_voices || (n_voices > 0 && !voices)) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block: 0..max_voices voices");
+		}
+		if (frames < 2 || (frames & 1) || frames > ctx->cfg.max_frames) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block: frames must be even and in [2, max_frames]");
+		}
+		if (src_rows < 0 || src_rows > ctx->cfg.max_voices || (src_rows > 0 && !src)) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block: 0..max_voices source rows");
+		}
+		for (int i = 0; i < n_voices; i++) {
+			const gas_voice &v = voices[i];
+			if (v.voice < 0 || v.voice >= ctx->cfg.max_voices || v.instance < 0 || v.instance >= ctx->cfg.max_instances || v.src_row >= src_rows) {
+				return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block: voice %d references a bad voice/instance slot or source row", i);
+			}
+		}
+		if (n_voices > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_voices, voices, n_voices * sizeof(gas_voice), cudaMemcpyHostToDevice, ctx->s_mix));
+		}
+		if (src_rows > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_src, src, (size_t)src_rows * frames * sizeof(gas_frame), cudaMemcpyHostToDevice, ctx->s_mix));
+		}
+		int st = mix_core(ctx, n_voices, ctx->d_voices, ctx->d_src, frames, frames, ctx->d_bus, peaks ? ctx->d_peaks : nullptr);
+		if (st) {
+			return st;
+		}
+		if (bus_out) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(bus_out, ctx->d_bus, (size_t)ctx->cfg.num_buses * (ctx->cfg.speaker_mode + 1) * frames * sizeof(gas_frame),
+					cudaMemcpyDeviceToHost, ctx->s_mix));
+		}
+		if (peaks && n_voices > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(peaks, ctx->d_peaks, n_voices * sizeof(gas_frame), cudaMemcpyDeviceToHost, ctx->s_mix));
+		}
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	return GAS_OK;
+}
+
+int gas_mix_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices, const gas_frame *d_src, int32_t src_rows,
+		int32_t src_row_stride, int32_t frames, gas_frame *d_bus_out, gas_frame *d_peaks) {
+	ENTER(ctx);
+	(void)src_rows;
+	if (n_voices < 0 || n_voices > ctx->cfg.max_voices || (n_voices > 0 && (!d_voices || !d_src)) || !d_bus_out) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_device: bad voice count or null pointer");
+	}
+	if (frames < 2 || (frames & 1) || frames > ctx->cfg.max_frames || src_row_stride < frames || (src_row_stride & 1)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_device: frames/stride must be even, frames <= max_frames, stride >= frames");
+	}
+	if (((uintptr_t)d_src & 15u) || ((uintptr_t)d_bus_out & 15u)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_device: source and bus buffers must be 16-byte aligned");
+	}
+	return mix_core(ctx, n_voices, d_voices, d_src, src_row_stride, frames, d_bus_out, d_peaks);
+}
+
+int gas_sync(gas_ctx *ctx) {
+	if (!ctx) {
+		return gas_fail(nullptr, GAS_ERR_INVALID, "gas_sync: null context");
+	}
+	GAS_CUDA(ctx, cudaSetDevice(ctx->device));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_gain));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	return GAS_OK;
+}
+
+void *gas_mix_stream(gas_ctx *ctx) { return ctx ? (void *)ctx->s_mix : nullptr; }
+void *gas_gain_stream(gas_ctx *ctx) { return ctx ? (void *)ctx->s_gain : nullptr; }
+uint64_t gas_kernel_launches(const gas_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int gas_voice_state_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_voice_state *out) {
+	{
+		ENTER(ctx);
+		if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && (!voices || !out)) || !ids_valid(voices, n, ctx->cfg.max_voices)) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_state_export: bad voice slot");
+		}
+		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+		GAS_CUDA(ctx, launch_state_export(ctx, n, ctx->d_ids, (gas_voice_state *)ctx->d_scratch, ctx->s_mix));
+		if (n > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scratch, n * sizeof(gas_voice_state), cudaMemcpyDeviceToHost, ctx->s_mix));
+		}
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	return GAS_OK;
+}
+
+int gas_voice_state_import(gas_ctx *ctx, int32_t n, const int32_t *voices, const gas_voice_state *in) {
+	ENTER(ctx);
+	if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && (!voices || !in)) || !ids_valid(voices, n, ctx->cfg.max_voices)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_state_import: bad voice slot");
+	}
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, in, n * sizeof(gas_voice_state), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, launch_state_import(ctx, n, ctx->d_ids, (const gas_voice_state *)ctx->d_scratch, ctx->s_mix));
+	return GAS_OK;
+}
+
+// ---- multi-GPU exchange (round 1: handles only; the fused peer epilogue lands with the N>1 work) ----------
+int gas_comm_export(gas_ctx *ctx, void *handle_out, size_t handle_bytes) {
+	ENTER(ctx);
+	if (!handle_out || handle_bytes < sizeof(cudaIpcMemHandle_t)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_comm_export: handle buffer must hold %zu bytes", sizeof(cudaIpcMemHandle_t));
+	}
+	if (!ctx->d_exchange) {
+		const size_t n = (size_t)8 * GAS_MAX_BUSES * GAS_MAX_CHANNELS_PER_BUS * ctx->cfg.max_frames;
+		GAS_CUDA(ctx, cudaMalloc((void **)&ctx->d_exchange, n * sizeof(gas_frame)));
+		GAS_CUDA(ctx, cudaMemset(ctx->d_exchange, 0, n * sizeof(gas_frame)));
+	}
+	cudaIpcMemHandle_t h;
+	GAS_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->d_exchange));
+	memcpy(handle_out, &h, sizeof(h));
+	return GAS_OK;
+}
+
+int gas_comm_open(gas_ctx *ctx, int32_t rank, int32_t n_ranks, const void *handles, size_t handle_bytes) {
+	ENTER(ctx);
+	if (n_ranks < 1 || n_ranks > 8 || rank < 0 || rank >= n_ranks || !handles || handle_bytes < sizeof(cudaIpcMemHandle_t)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_comm_open: 1..8 ranks, one %zu-byte handle per rank", sizeof(cudaIpcMemHandle_t));
+	}
+	if (!ctx->d_exchange) {
+		return gas_fail(ctx, GAS_ERR_STATE, "gas_comm_open: call gas_comm_export first");
+	}
+	for (int r = 0; r < n_ranks; r++) {
+		if (r == rank) {
+			ctx->peer_exchange[r] = ctx->d_exchange;
+			continue;
+		}
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const unsigned char *)handles + (size_t)r * handle_bytes, sizeof(h));
+		void *p = nullptr;
+		GAS_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		ctx->peer_exchange[r] = (gas_frame *)p;
+	}
+	ctx->comm_rank = rank;
+	ctx->comm_ranks = n_ranks;
+	return GAS_OK;
+}
+
+int gas_comm_close(gas_ctx *ctx) {
+	if (!ctx) {
+		return GAS_OK;
+	}
+	for (int r = 0; r < 8; r++) {
+		if (ctx->peer_exchange[r] && ctx->peer_exchange[r] != ctx->d_exchange) {
+			cudaIpcCloseMemHandle(ctx->peer_exchange[r]);
+		}
+		ctx->peer_exchange[r] = nullptr;
+	}
+	ctx->comm_ranks = 1;
+	ctx->comm_rank = 0;
+	return GAS_OK;
+}
+
+} // extern "C"

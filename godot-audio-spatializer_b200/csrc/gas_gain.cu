@@ -1,0 +1,539 @@
+// gas_gain.cu — K1: batched AudioSpatializerInstance3D::calculate_spatialization
+// (reference audio_spatializer_3d.cpp:277-489) + update_spatializer_parameters / get_bus_map
+// (reference audio_spatializer.cpp:258-324), one thread per emitter.
+//
+// Compiled with -fmad=false: the reference mixes float storage with double intermediates (SURVEY Q3,
+// Q8, Q10) and the gains must come out the way a scalar x86-64 build produces them, so no contraction.
+// float transcendentals are evaluated in double and narrowed, which is correctly rounded in practice
+// and therefore agrees with a correctly-rounded libm.  V is small here; cost is irrelevant.
+#include "gas_internal.h"
+
+#define CMP_EPSILON 0.00001
+
+namespace {
+
+struct V3 {
+	float x, y, z;
+};
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float len3(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
+__device__ __forceinline__ V3 sub3(V3 a, V3 b) { return V3{ a.x - b.x, a.y - b.y, a.z - b.z }; }
+__device__ __forceinline__ V3 mul3(V3 a, float s) { return V3{ a.x * s, a.y * s, a.z * s }; }
+__device__ __forceinline__ V3 norm3(V3 a) { // upstream Vector3::normalized
+	float l2 = a.x * a.x + a.y * a.y + a.z * a.z;
+	if (l2 == 0.0f) {
+		return V3{ 0.f, 0.f, 0.f };
+	}
+	float l = sqrtf(l2);
+	return V3{ a.x / l, a.y / l, a.z / l };
+}
+
+struct Xf { // upstream Transform3D: Basis rows + origin
+	float m[3][3];
+	V3 o;
+};
+__device__ __forceinline__ V3 col(const Xf &t, int c) { return V3{ t.m[0][c], t.m[1][c], t.m[2][c] }; }
+__device__ __forceinline__ void set_col(Xf &t, int c, V3 v) {
+	t.m[0][c] = v.x;
+	t.m[1][c] = v.y;
+	t.m[2][c] = v.z;
+}
+__device__ void orthonormalize(Xf &t) { // upstream Basis::orthonormalize (Gram-Schmidt)
+	V3 x = col(t, 0), y = col(t, 1), z = col(t, 2);
+	x = norm3(x);
+	y = sub3(y, mul3(x, dot3(x, y)));
+	y = norm3(y);
+	z = sub3(sub3(z, mul3(x, dot3(x, z))), mul3(y, dot3(y, z)));
+	z = norm3(z);
+	set_col(t, 0, x);
+	set_col(t, 1, y);
+	set_col(t, 2, z);
+}
+__device__ __forceinline__ V3 bxform(const Xf &t, V3 v) {
+	return V3{ t.m[0][0] * v.x + t.m[0][1] * v.y + t.m[0][2] * v.z,
+		t.m[1][0] * v.x + t.m[1][1] * v.y + t.m[1][2] * v.z,
+		t.m[2][0] * v.x + t.m[2][1] * v.y + t.m[2][2] * v.z };
+}
+__device__ __forceinline__ V3 bxform_inv(const Xf &t, V3 v) {
+	return V3{ t.m[0][0] * v.x + t.m[1][0] * v.y + t.m[2][0] * v.z,
+		t.m[0][1] * v.x + t.m[1][1] * v.y + t.m[2][1] * v.z,
+		t.m[0][2] * v.x + t.m[1][2] * v.y + t.m[2][2] * v.z };
+}
+__device__ void affine_invert(Xf &t) { // upstream Transform3D::affine_invert
+#define CF(r1, c1, r2, c2) (t.m[r1][c1] * t.m[r2][c2] - t.m[r1][c2] * t.m[r2][c1])
+	float co0 = CF(1, 1, 2, 2), co1 = CF(1, 2, 2, 0), co2 = CF(1, 0, 2, 1);
+	float det = t.m[0][0] * co0 + t.m[0][1] * co1 + t.m[0][2] * co2;
+	float s = 1.0f / det;
+	float n[3][3];
+	n[0][0] = co0 * s;
+	n[0][1] = CF(0, 2, 2, 1) * s;
+	n[0][2] = CF(0, 1, 1, 2) * s;
+	n[1][0] = co1 * s;
+	n[1][1] = CF(0, 0, 2, 2) * s;
+	n[1][2] = CF(0, 2, 1, 0) * s;
+	n[2][0] = co2 * s;
+	n[2][1] = CF(0, 1, 2, 0) * s;
+	n[2][2] = CF(0, 0, 1, 1) * s;
+#undef CF
+	for (int i = 0; i < 3; i++) {
+		for (int j = 0; j < 3; j++) {
+			t.m[i][j] = n[i][j];
+		}
+	}
+	t.o = bxform(t, V3{ -t.o.x, -t.o.y, -t.o.z });
+}
+__device__ __forceinline__ V3 xform(const Xf &t, V3 v) {
+	V3 r = bxform(t, v);
+	return V3{ r.x + t.o.x, r.y + t.o.y, r.z + t.o.z };
+}
+__device__ Xf load_xf(const gas_listener &l) {
+	Xf t;
+	for (int i = 0; i < 3; i++) {
+		for (int j = 0; j < 3; j++) {
+			t.m[i][j] = l.basis[i * 3 + j];
+		}
+	}
+	t.o = V3{ l.origin[0], l.origin[1], l.origin[2] };
+	return t;
+}
+
+// upstream Math::db_to_linear(float) / linear_to_db(double)
+__device__ __forceinline__ float db_to_linear_f(float db) {
+	float a = db * (float)0.11512925464970228420089957273422;
+	return (float)exp((double)a);
+}
+__device__ __forceinline__ double linear_to_db_d(double lin) { return log(lin) * 8.6858896380650365530225783783321; }
+
+// reference audio_spatializer_3d.cpp:123-151
+__device__ float attenuation_db(const gas_spatializer &s, float volume_db, float max_db, float dist) {
+	float att = 0.f;
+	switch (s.attenuation_model) {
+		case GAS_ATTENUATION_INVERSE_DISTANCE:
+			att = (float)linear_to_db_d(1.0 / ((double)(dist / s.unit_size) + CMP_EPSILON));
+			break;
+		case GAS_ATTENUATION_INVERSE_SQUARE_DISTANCE: {
+			float d = dist / s.unit_size;
+			d *= d;
+			att = (float)linear_to_db_d(1.0 / ((double)d + CMP_EPSILON));
+		} break;
+		case GAS_ATTENUATION_LOGARITHMIC:
+			att = (float)(-20.0 * log((double)(dist / s.unit_size) + CMP_EPSILON));
+			break;
+		default:
+			break;
+	}
+	att += volume_db;
+	if (att > max_db) {
+		att = max_db;
+	}
+	return att;
+}
+
+// SPCAP speaker set (reference audio_spatializer_3d.cpp:47-55), normalised in float exactly as
+// Vector3(-1,0,-1).normalized() does: x / sqrtf(2.f).
+__device__ __forceinline__ V3 spcap_dir(int i) {
+	V3 raw;
+	switch (i) {
+		case 0: raw = V3{ -1.f, 0.f, -1.f }; break;
+		case 1: raw = V3{ 1.f, 0.f, -1.f }; break;
+		case 2: raw = V3{ 0.f, 0.f, -1.f }; break;
+		case 3: raw = V3{ -1.f, 0.f, 1.f }; break;
+		case 4: raw = V3{ 1.f, 0.f, 1.f }; break;
+		case 5: raw = V3{ -1.f, 0.f, 0.f }; break;
+		default: raw = V3{ 1.f, 0.f, 0.f }; break;
+	}
+	return norm3(raw);
+}
+
+// reference audio_spatializer_3d.cpp:57-98 + :903-938
+__device__ void output_vol_surround(int speaker_mode, V3 src, float tightness, float out[4][2]) {
+	int count = speaker_mode == GAS_SPEAKER_SURROUND_31 ? 3 : (speaker_mode == GAS_SPEAKER_SURROUND_51 ? 5 : (speaker_mode == GAS_SPEAKER_SURROUND_71 ? 7 : 2));
+	V3 d[7];
+	float eff[7], sq[7], vol[7];
+	for (int i = 0; i < 7; i++) {
+		d[i] = spcap_dir(i);
+		eff[i] = 0.f;
+		vol[i] = 0.f;
+	}
+	for (int i = 0; i < count; i++) { // :911-915, float accumulator += double term
+		for (int j = 0; j < count; j++) {
+			eff[i] = (float)((double)eff[i] + 0.5 * (1.0 + (double)dot3(d[i], d[j])));
+		}
+	}
+	float sum = 0.f;
+	for (int i = 0; i < count; i++) { // :929-933
+		float g = (float)(0.5 * pow(1.0 + (double)dot3(d[i], src), (double)tightness) / (double)eff[i]);
+		sq[i] = g * g;
+		sum += sq[i];
+	}
+	for (int i = 0; i < count; i++) { // :935-937
+		vol[i] = sqrtf(sq[i] / sum);
+	}
+	switch (speaker_mode) {
+		case GAS_SPEAKER_SURROUND_71:
+			out[3][0] = vol[5];
+			out[3][1] = vol[6];
+		case GAS_SPEAKER_SURROUND_51:
+			out[2][0] = vol[3];
+			out[2][1] = vol[4];
+		case GAS_SPEAKER_SURROUND_31:
+			out[1][0] = vol[2];
+			out[1][1] = 1.0f; // LFE — always full power (Q9)
+		default:
+			out[0][0] = vol[0];
+			out[0][1] = vol[1];
+	}
+}
+
+// reference audio_spatializer_3d.cpp:103-110
+__device__ void output_vol_stereo(V3 dir, float pan_strength, float out[4][2]) {
+	double flatrad = sqrt((double)(dir.x * dir.x + dir.z * dir.z));
+	double g = (1.0 - (double)pan_strength) * (1.0 - (double)pan_strength);
+	g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
+	double f = (1.0 - g) / (1.0 + g);
+	double cosx = (double)dir.x / (flatrad == 0.0 ? 1.0 : flatrad);
+	cosx = cosx < -1.0 ? -1.0 : (cosx > 1.0 ? 1.0 : cosx);
+	double fcosx = cosx * f;
+	out[0][0] = (float)sqrt((-fcosx + 1.0) / 2.0);
+	out[0][1] = (float)sqrt((fcosx + 1.0) / 2.0);
+}
+
+// reference audio_spatializer_3d.cpp:112-121
+__device__ void output_vol(const GlobalCfg &g, const gas_spatializer &s, V3 dir, float out[4][2]) {
+	if (g.speaker_mode == GAS_SPEAKER_MODE_STEREO) {
+		output_vol_stereo(dir, g.global_panning * s.panning_strength, out);
+	} else {
+		float tightness = g.global_panning * 2.0f;
+		tightness *= s.panning_strength;
+		output_vol_surround(g.speaker_mode, dir, tightness, out);
+	}
+}
+
+__device__ __forceinline__ float lerpf(float a, float b, float w) { return a + (b - a) * w; }
+
+// reference audio_spatializer_3d.cpp:154-197
+__device__ void reverb_vol(const GlobalCfg &g, const gas_spatializer &s, const gas_emitter &e, const gas_area &a,
+		V3 listener_area_pos, const float direct[4][2], float rev[4][2]) {
+	for (int i = 0; i < 4; i++) {
+		rev[i][0] = rev[i][1] = 0.f;
+	}
+	float uniformity = a.reverb_uniformity;
+	float area_send = a.reverb_amount;
+	int chan = g.channels;
+	if (uniformity > 0.0f) {
+		float distance = len3(listener_area_pos);
+		float attenuation = db_to_linear_f(attenuation_db(s, e.volume_db, e.max_db, distance));
+		const float center_val[4] = { 0.5f, 0.25f, 0.16666f, 0.125f };
+		float cv = center_val[chan - 1];
+		if (attenuation < 1.0f) {
+			V3 rp = listener_area_pos;
+			rp.y = 0.f;
+			rp = norm3(rp);
+			output_vol(g, s, rp, rev);
+			for (int i = 0; i < chan; i++) {
+				rev[i][0] = lerpf(rev[i][0], cv, attenuation);
+				rev[i][1] = lerpf(rev[i][1], cv, attenuation);
+			}
+		} else {
+			for (int i = 0; i < chan; i++) {
+				rev[i][0] = rev[i][1] = cv;
+			}
+		}
+		for (int i = 0; i < chan; i++) {
+			rev[i][0] = lerpf(direct[i][0], rev[i][0] * attenuation, uniformity);
+			rev[i][1] = lerpf(direct[i][1], rev[i][1] * attenuation, uniformity);
+			rev[i][0] *= area_send;
+			rev[i][1] *= area_send;
+		}
+	} else {
+		for (int i = 0; i < 4; i++) {
+			rev[i][0] = direct[i][0] * area_send;
+			rev[i][1] = direct[i][1] * area_send;
+		}
+	}
+}
+
+__device__ __forceinline__ int resolve_bus(const GlobalCfg &g, int bus) { // audio_stream_player_spatial.cpp:405-413
+	return (bus >= 0 && bus < g.num_buses) ? bus : 0;
+}
+
+__device__ void add_bus_volume(gas_params &p, int bus, const float vol[4][2]) { // spatializer_parameters.cpp:35-38
+	int slot = -1;
+	for (int i = 0; i < p.n_bus; i++) {
+		if (p.bus[i] == bus) {
+			slot = i;
+		}
+	}
+	if (slot < 0) {
+		if (p.n_bus >= GAS_MAX_BUSES_PER_PLAYBACK) {
+			return;
+		}
+		slot = p.n_bus++;
+		p.bus[slot] = bus;
+	}
+	for (int c = 0; c < 4; c++) {
+		p.bus_volumes[slot][c][0] = vol[c][0];
+		p.bus_volumes[slot][c][1] = vol[c][1];
+	}
+}
+
+// AudioSpatializerInstance::get_bus_map for all proxy channels at once (audio_spatializer.cpp:274-324):
+// Mode B proxies normalise by the mix volume and mask to their own pair; Mode A sends mix_volumes to
+// every bus (Q15).
+__device__ void push_bus_map(const gas_params &p, bool mix_channels, BusDetails &d) {
+	int n = p.n_bus < GAS_MAX_BUSES_PER_PLAYBACK ? p.n_bus : GAS_MAX_BUSES_PER_PLAYBACK;
+	d.n = n;
+	for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+		d.bus[k] = k < n ? p.bus[k] : 0;
+		for (int c = 0; c < 4; c++) {
+			float l = 0.f, r = 0.f;
+			if (k < n) {
+				if (mix_channels) {
+					if (p.mix_volumes[c][0] > 0.0f) {
+						l = p.bus_volumes[k][c][0] / p.mix_volumes[c][0];
+					}
+					if (p.mix_volumes[c][1] > 0.0f) {
+						r = p.bus_volumes[k][c][1] / p.mix_volumes[c][1];
+					}
+				} else {
+					l = p.mix_volumes[c][0];
+					r = p.mix_volumes[c][1];
+				}
+			}
+			d.vol[k][c][0] = l;
+			d.vol[k][c][1] = r;
+		}
+	}
+}
+
+__device__ __forceinline__ bool inst_mix_channels(const DevTables &t, int q) {
+	const gas_spatializer &s = t.spat[t.inst_spat[q]];
+	return s.kind == GAS_SPATIALIZER_3D && s.mix_channel_mode != 0;
+}
+
+// set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272)
+__device__ void commit_params(const DevTables &t, int q, const gas_params &p) {
+	t.inst_params[q] = p;
+	if (p.update_parameters && t.inst_active[q]) {
+		push_bus_map(p, inst_mix_channels(t, q), t.inst_cur[q]);
+	}
+}
+
+__global__ void __launch_bounds__(128) k_gain(DevTables t, GlobalCfg g, int n, const gas_emitter *__restrict__ emitters,
+		int n_listeners, const gas_listener *__restrict__ listeners, const gas_area *__restrict__ areas, gas_params *__restrict__ out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) {
+		return;
+	}
+	const gas_emitter e = emitters[i];
+	const gas_spatializer s = t.spat[e.spatializer];
+	const bool has_area = e.area >= 0;
+	gas_area a;
+	if (has_area) {
+		a = areas[e.area];
+	}
+	gas_params prm;
+	for (int c = 0; c < 4; c++) {
+		prm.mix_volumes[c][0] = prm.mix_volumes[c][1] = 0.f;
+	}
+	prm.pitch_scale = 1.0f;
+	prm.linear_attenuation = 0.0f;
+	prm.attenuation_filter_cutoff_hz = 5000.0f;
+	prm.update_parameters = 0;
+	prm.n_bus = 0;
+	for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+		prm.bus[k] = 0;
+		for (int c = 0; c < 4; c++) {
+			prm.bus_volumes[k][c][0] = prm.bus_volumes[k][c][1] = 0.f;
+		}
+	}
+
+	const V3 global_pos{ e.origin[0], e.origin[1], e.origin[2] };
+	V3 linear_velocity{ 0.f, 0.f, 0.f };
+	const bool doppler = s.doppler_tracking != GAS_DOPPLER_TRACKING_DISABLED;
+	if (doppler) { // :297-299
+		linear_velocity = V3{ e.velocity[0], e.velocity[1], e.velocity[2] };
+	}
+	float log_pitch_scale = 0.f, log_pitch_weight = 0.f;
+	float output_volume[4][2], reverb_volume[4][2], tmp_volume[4][2], tmp_reverb[4][2];
+	for (int c = 0; c < 4; c++) {
+		output_volume[c][0] = output_volume[c][1] = 0.f;
+		reverb_volume[c][0] = reverb_volume[c][1] = 0.f;
+	}
+	bool in_range_any = false;
+	const bool area_reverb_uniform = has_area && a.use_reverb && a.reverb_uniformity > 0.0f;
+
+	for (int li = 0; li < n_listeners; li++) { // :323
+		const gas_listener L = listeners[li];
+		const Xf lt = load_xf(L);
+		Xf inv = lt;
+		orthonormalize(inv);
+		affine_invert(inv);
+		const V3 local_pos = xform(inv, global_pos); // :342
+		const float dist = len3(local_pos);          // :344
+		V3 listener_area_pos{ 0.f, 0.f, 0.f };
+		if (area_reverb_uniform) { // :350-353 (plain affine inverse, not orthonormalised)
+			Xf inv2 = lt;
+			affine_invert(inv2);
+			listener_area_pos = xform(inv2, V3{ a.closest_point[li][0], a.closest_point[li][1], a.closest_point[li][2] });
+		}
+		float multiplier = db_to_linear_f(attenuation_db(s, e.volume_db, e.max_db, dist)); // :359
+		if (s.max_distance > 0.f) { // :361-373
+			float total_max = s.max_distance;
+			if (area_reverb_uniform) {
+				float lap = len3(listener_area_pos);
+				total_max = total_max > lap ? total_max : lap;
+			}
+			if (dist > total_max || total_max > s.max_distance) {
+				continue;
+			}
+			double m = 1.0 - (double)(dist / s.max_distance);
+			m = 0.0 > m ? 0.0 : m;
+			multiplier = (float)((double)multiplier * m);
+		}
+		in_range_any = true;
+
+		double mm = 1.0 < (double)multiplier ? 1.0 : (double)multiplier;
+		float db_att = (float)((1.0 - mm) * (double)s.attenuation_filter_db); // :376
+		if (s.emission_angle_enabled) { // :378-385
+			V3 listenertopos = sub3(global_pos, V3{ L.origin[0], L.origin[1], L.origin[2] });
+			float c = dot3(norm3(listenertopos), norm3(V3{ e.basis_z[0], e.basis_z[1], e.basis_z[2] }));
+			float ac = c < -1.0f ? (float)3.14159265358979323846 : (c > 1.0f ? 0.0f : (float)acos((double)c));
+			float angle = ac * (float)(180.0 / 3.14159265358979323846);
+			if (angle > s.emission_angle) {
+				db_att -= -s.emission_angle_filter_attenuation_db;
+			}
+		}
+		prm.linear_attenuation = db_to_linear_f(db_att); // :387, last listener wins (Q6)
+		prm.attenuation_filter_cutoff_hz = s.attenuation_filter_cutoff_hz;
+
+		for (int c = 0; c < 4; c++) {
+			tmp_volume[c][0] = tmp_volume[c][1] = 0.f;
+		}
+		output_vol(g, s, local_pos, tmp_volume); // :391 — un-normalised direction (Q1)
+		for (int c = 0; c < 4; c++) {            // :393-396
+			tmp_volume[c][0] = multiplier * tmp_volume[c][0];
+			tmp_volume[c][1] = multiplier * tmp_volume[c][1];
+			output_volume[c][0] = output_volume[c][0] > tmp_volume[c][0] ? output_volume[c][0] : tmp_volume[c][0];
+			output_volume[c][1] = output_volume[c][1] > tmp_volume[c][1] ? output_volume[c][1] : tmp_volume[c][1];
+		}
+		if (has_area && a.use_reverb) { // :399-402
+			reverb_vol(g, s, e, a, listener_area_pos, tmp_volume, tmp_reverb);
+			for (int c = 0; c < 4; c++) {
+				reverb_volume[c][0] = reverb_volume[c][0] > tmp_reverb[c][0] ? reverb_volume[c][0] : tmp_reverb[c][0];
+				reverb_volume[c][1] = reverb_volume[c][1] > tmp_reverb[c][1] ? reverb_volume[c][1] : tmp_reverb[c][1];
+			}
+		}
+		if (doppler) { // :405-427
+			Xf on = lt;
+			orthonormalize(on);
+			V3 local_velocity = bxform_inv(on, sub3(linear_velocity, V3{ L.velocity[0], L.velocity[1], L.velocity[2] }));
+			if (!(local_velocity.x == 0.f && local_velocity.y == 0.f && local_velocity.z == 0.f)) {
+				float approaching = dot3(norm3(local_pos), norm3(local_velocity));
+				float velocity = len3(local_velocity);
+				float dps = e.pitch_scale * s.doppler_speed_of_sound / (s.doppler_speed_of_sound + velocity * approaching);
+				dps = (double)dps < 0.125 ? 0.125f : ((double)dps > 8.0 ? 8.0f : dps);
+				float weight = 0.f;
+				for (int c = 0; c < 4; c++) {
+					weight = weight > tmp_volume[c][0] ? weight : tmp_volume[c][0];
+					weight = weight > tmp_volume[c][1] ? weight : tmp_volume[c][1];
+				}
+				log_pitch_scale += weight * (float)log2((double)dps);
+				log_pitch_weight += weight;
+			}
+		}
+	}
+	if (log_pitch_weight > 0.f) { // :430-434
+		prm.pitch_scale = (float)pow(2.0, (double)(log_pitch_scale / log_pitch_weight));
+	} else {
+		prm.pitch_scale = e.pitch_scale;
+	}
+	if (in_range_any) { // :437-461
+		if (has_area) {
+			add_bus_volume(prm, resolve_bus(g, a.override_bus ? a.bus : e.bus), output_volume);
+			if (a.use_reverb) {
+				add_bus_volume(prm, resolve_bus(g, a.reverb_bus), reverb_volume);
+			}
+		} else {
+			add_bus_volume(prm, resolve_bus(g, e.bus), output_volume);
+		}
+	}
+	for (int c = 0; c < 4; c++) { // :463
+		prm.mix_volumes[c][0] = output_volume[c][0];
+		prm.mix_volumes[c][1] = output_volume[c][1];
+	}
+	const int q = e.instance;
+	const bool was_further = t.inst_was_further[q] != 0;
+	const bool skip = !in_range_any && was_further; // :466-467
+	t.inst_was_further[q] = in_range_any ? 0 : 1;
+	if (!skip) {
+		prm.update_parameters = 1;
+	}
+	commit_params(t, q, prm);
+	if (out) {
+		out[i] = prm;
+	}
+}
+
+__global__ void __launch_bounds__(128) k_params_set(DevTables t, GlobalCfg g, int n, const int32_t *__restrict__ ids, const gas_params *__restrict__ params) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) {
+		return;
+	}
+	gas_params p = params[i];
+	for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+		p.bus[k] = resolve_bus(g, p.bus[k]);
+	}
+	commit_params(t, ids[i], p);
+}
+
+// proxies (re)registered: current details from the current parameters, previous details empty
+// (reference audio_spatializer.cpp:75-95, upstream AudioServer::start_playback_stream)
+__global__ void __launch_bounds__(128) k_instance_start(DevTables t, int n, const int32_t *__restrict__ ids) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) {
+		return;
+	}
+	int q = ids[i];
+	t.inst_active[q] = 1;
+	BusDetails z;
+	z.n = 0;
+	for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+		z.bus[k] = 0;
+		for (int c = 0; c < 4; c++) {
+			z.vol[k][c][0] = z.vol[k][c][1] = 0.f;
+		}
+	}
+	t.inst_prev[q] = z;
+	push_bus_map(t.inst_params[q], inst_mix_channels(t, q), t.inst_cur[q]);
+}
+
+} // namespace
+
+cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_listeners, const gas_listener *d_l,
+		const gas_area *d_areas, gas_params *d_out, cudaStream_t st) {
+	if (n <= 0) {
+		return cudaSuccess;
+	}
+	k_gain<<<(n + 127) / 128, 128, 0, st>>>(ctx->t, ctx->g, n, d_em, n_listeners, d_l, d_areas, d_out);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_params_set(gas_ctx *ctx, int n, const int32_t *d_ids, const gas_params *d_params, cudaStream_t st) {
+	if (n <= 0) {
+		return cudaSuccess;
+	}
+	k_params_set<<<(n + 127) / 128, 128, 0, st>>>(ctx->t, ctx->g, n, d_ids, d_params);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_instance_start(gas_ctx *ctx, int n, const int32_t *d_ids, cudaStream_t st) {
+	if (n <= 0) {
+		return cudaSuccess;
+	}
+	k_instance_start<<<(n + 127) / 128, 128, 0, st>>>(ctx->t, n, d_ids);
+	ctx->launches++;
+	return cudaGetLastError();
+}

@@ -1,0 +1,422 @@
+// gas_mix_stream.cu — K2: the streaming mix kernel (sm_100a).
+//
+// For every voice whose block needs no per-sample recurrence (no attenuation filter, no effect chain)
+// the reference's per-voice work (mix_channel ramp, reference audio_spatializer_3d.cpp:600-604, the
+// += into the instance mix buffer, audio_spatializer.cpp:433-434, and the AudioServer ramped bus
+// accumulate, upstream _mix_step_for_channel) collapses to
+//       bus[b][c][i] += (A + B t + C t^2) * x_v[i],   t = i / F
+// with the polynomial rows prepared by the prologue.  Summed over voices this is a skinny fp32
+// contraction  Out[rows, F] = W[rows, V] . X[V, F]  followed by the evaluation in t — HBM-bound: every
+// source frame (8 bytes) is read exactly once and feeds 2*rows FMAs.
+//
+// Structure: persistent, one CTA per SM, warp-specialised.
+//   warp 8      producer: streams voice rows HBM -> shared memory with 1-D bulk async copies (TMA engine,
+//               cp.async.bulk + mbarrier complete_tx) through a ring of stages; rows are gathered by
+//               the class lists, so voices need not be contiguous in memory.
+//   warps 0-7   consumers: each thread owns 2 frames of the tile and keeps rows x 2 (L,R) accumulators in
+//               registers; weights are broadcast from shared memory; the FMAs are packed FFMA2
+//               (fma.rn.f32x2: one instruction per (L,R) pair).
+// A CTA owns a contiguous range of (class, frame tile, voice batch) units; when the class or tile
+// changes it evaluates the polynomial and adds its partial sums into the bus buffers with vector
+// reductions (red.global.add.v4.f32).  No per-voice state is written here.
+#include "gas_internal.h"
+
+#ifndef GAS_USE_FFMA2
+#define GAS_USE_FFMA2 1
+#endif
+
+namespace {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = kConsumerThreads + 32;
+constexpr int kTileFrames = 512;       // frames per tile: 2 per consumer thread
+constexpr int kMaxPairs = GAS_K2_MAX_ROWS * GAS_MAX_CHANNELS_PER_BUS; // 24 (L,R) weight pairs per voice
+constexpr int kMaxStages = 8;
+
+struct StreamCfg {
+	int frames;        // F
+	int src_stride;    // frames between consecutive source rows
+	int tile_frames;   // min(F, 512)
+	int n_tiles;       // ceil(F / 512)
+	int slots;         // tile_frames / 2
+	int groups;        // voice groups working side by side inside a stage
+	int vb;            // voices per stage
+	int stages;
+	int x_bytes;       // per stage
+	int w_bytes;       // per stage
+	int stage_bytes;
+};
+
+// ---- PTX helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	uint32_t ok = 0;
+	do {
+		asm volatile(
+				"{\n"
+				".reg .pred p;\n"
+				"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+				"selp.u32 %0, 1, 0, p;\n"
+				"}\n"
+				: "=r"(ok)
+				: "r"(smem_u32(bar)), "r"(parity)
+				: "memory");
+	} while (!ok);
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+			"l"(src), "r"(bytes), "r"(smem_u32(bar))
+			: "memory");
+}
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// packed (L,R) FMA: acc += w * x on both halves with one instruction (SASS: FFMA2)
+__device__ __forceinline__ void fma2(float2 &acc, const float2 w, const float2 x) {
+#if GAS_USE_FFMA2
+	asm("{\n"
+		".reg .b64 a, ww, xx;\n"
+		"mov.b64 a, {%0, %1};\n"
+		"mov.b64 ww, {%2, %3};\n"
+		"mov.b64 xx, {%4, %5};\n"
+		"fma.rn.f32x2 a, ww, xx, a;\n"
+		"mov.b64 {%0, %1}, a;\n"
+		"}\n"
+		: "+f"(acc.x), "+f"(acc.y)
+		: "f"(w.x), "f"(w.y), "f"(x.x), "f"(x.y));
+#else
+	acc.x = fmaf(w.x, x.x, acc.x);
+	acc.y = fmaf(w.y, x.y, acc.y);
+#endif
+}
+
+// ---- unit iterator: (class, frame tile, voice batch), identical in every role -------------------------
+struct UnitIter {
+	int cid, tile, batch, nb; // nb: batches of the current class
+	int remaining;
+};
+
+__device__ void unit_iter_init(UnitIter &it, const ClassInfo *cls, const StreamCfg &cf, int cta, int n_cta) {
+	int total = 0;
+	for (int c = 0; c < GAS_MAX_CLASSES; c++) {
+		if (cls[c].key != 0ULL && cls[c].path == PATH_STREAM) {
+			total += ((cls[c].count + cf.vb - 1) / cf.vb) * cf.n_tiles;
+		}
+	}
+	const long long lo = (long long)total * cta / n_cta;
+	const long long hi = (long long)total * (cta + 1) / n_cta;
+	it.remaining = (int)(hi - lo);
+	it.cid = GAS_MAX_CLASSES;
+	it.tile = it.batch = it.nb = 0;
+	int skip = (int)lo;
+	for (int c = 0; c < GAS_MAX_CLASSES && it.remaining > 0; c++) {
+		if (cls[c].key == 0ULL || cls[c].path != PATH_STREAM) {
+			continue;
+		}
+		int nb = (cls[c].count + cf.vb - 1) / cf.vb;
+		int u = nb * cf.n_tiles;
+		if (skip >= u) {
+			skip -= u;
+			continue;
+		}
+		it.cid = c;
+		it.nb = nb;
+		it.tile = skip / nb;
+		it.batch = skip % nb;
+		break;
+	}
+}
+
+__device__ __forceinline__ void unit_iter_next(UnitIter &it, const ClassInfo *cls, const StreamCfg &cf) {
+	it.remaining--;
+	if (it.remaining <= 0) {
+		return;
+	}
+	if (++it.batch < it.nb) {
+		return;
+	}
+	it.batch = 0;
+	if (++it.tile < cf.n_tiles) {
+		return;
+	}
+	it.tile = 0;
+	for (int c = it.cid + 1; c < GAS_MAX_CLASSES; c++) {
+		if (cls[c].key != 0ULL && cls[c].path == PATH_STREAM && cls[c].count > 0) {
+			it.cid = c;
+			it.nb = (cls[c].count + cf.vb - 1) / cf.vb;
+			return;
+		}
+	}
+	it.remaining = 0;
+}
+
+struct ConsumerCtx {
+	const unsigned char *smem;
+	uint64_t *full;
+	uint64_t *empty;
+	const ClassInfo *cls;
+	int C, lane, slot, group;
+	bool worker;
+	int stage;
+	uint32_t phase;
+};
+
+// One run = every consecutive unit of this CTA that shares (class, tile).  NP = (L,R) weight pairs per
+// voice = rows * pairs.  The accumulators live in registers for the whole run; at its end the polynomial
+// is evaluated in t and the partial sums are added to the bus buffers.
+template <int NP>
+__device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, const StreamCfg &cf, float *__restrict__ bus) {
+	float2 acc[NP][2];
+#pragma unroll
+	for (int p = 0; p < NP; p++) {
+		acc[p][0] = make_float2(0.f, 0.f);
+		acc[p][1] = make_float2(0.f, 0.f);
+	}
+	const int cid = it.cid, tile = it.tile;
+	const ClassInfo &ci = cc.cls[cid];
+	const int tile_w = min(cf.tile_frames, cf.frames - tile * kTileFrames);
+	const int row_bytes = tile_w * 8;
+	const bool mine = cc.worker && cc.slot * 2 < tile_w;
+	do {
+		const int v0 = it.batch * cf.vb;
+		const int nv = min(cf.vb, ci.count - v0);
+		const unsigned char *sx = cc.smem + (size_t)cc.stage * cf.stage_bytes;
+		const unsigned char *sw = sx + cf.x_bytes;
+		mbar_wait(&cc.full[cc.stage], cc.phase);
+		if (mine) {
+			for (int v = cc.group; v < nv; v += cf.groups) {
+				const float4 x = *reinterpret_cast<const float4 *>(sx + (size_t)v * row_bytes + cc.slot * 16);
+				const float2 x0 = make_float2(x.x, x.y), x1 = make_float2(x.z, x.w);
+				const unsigned char *wv = sw + v * (NP * 8);
+				if (NP % 2 == 0) { // per-voice weight block is a multiple of 16 bytes: 128-bit broadcast loads
+#pragma unroll
+					for (int p = 0; p < NP; p += 2) {
+						const float4 w = *reinterpret_cast<const float4 *>(wv + p * 8);
+						const float2 wa = make_float2(w.x, w.y), wb = make_float2(w.z, w.w);
+						fma2(acc[p][0], wa, x0);
+						fma2(acc[p][1], wa, x1);
+						fma2(acc[p + 1][0], wb, x0);
+						fma2(acc[p + 1][1], wb, x1);
+					}
+				} else {
+#pragma unroll
+					for (int p = 0; p < NP; p++) {
+						const float2 wa = *reinterpret_cast<const float2 *>(wv + p * 8);
+						fma2(acc[p][0], wa, x0);
+						fma2(acc[p][1], wa, x1);
+					}
+				}
+			}
+		}
+		__syncwarp();
+		if (cc.lane == 0) {
+			mbar_arrive(&cc.empty[cc.stage]);
+		}
+		if (++cc.stage == cf.stages) {
+			cc.stage = 0;
+			cc.phase ^= 1u;
+		}
+		unit_iter_next(it, cc.cls, cf);
+	} while (it.remaining > 0 && it.cid == cid && it.tile == tile);
+
+	if (!mine) {
+		return;
+	}
+	// ---- flush: bus[b][c][i] += A + B t (+ C t^2), rows ordered [group][poly][pair] --------------------
+	const int C = cc.C, F = cf.frames;
+	const int frame0 = tile * kTileFrames + cc.slot * 2;
+	const float t0 = (float)frame0 / (float)F;
+	const float t1 = (float)(frame0 + 1) / (float)F;
+	const bool lin = (ci.flags & CLS_LIN) != 0;
+	const bool shared = (ci.flags & CLS_SHARED) != 0;
+	const int P = lin ? 2 : 3;
+	const int G = NP / (P * C); // row groups
+	uint32_t rest = ci.mask;
+	for (int k = 0; k < G; k++) {
+		const int b_own = __ffs(rest) - 1; // k-th bus of the mask (sends ascend by bus)
+		rest &= rest - 1;
+		for (int c = 0; c < C; c++) {
+			const int pa = (k * P + 0) * C + c, pb = (k * P + 1) * C + c, pc = (k * P + 2) * C + c;
+			float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0, c0 = a0, c1 = a0;
+#pragma unroll
+			for (int p = 0; p < NP; p++) { // static indexing only: the accumulators must stay in registers
+				if (p == pa) {
+					a0 = acc[p][0];
+					a1 = acc[p][1];
+				}
+				if (p == pb) {
+					b0 = acc[p][0];
+					b1 = acc[p][1];
+				}
+				if (!lin && p == pc) {
+					c0 = acc[p][0];
+					c1 = acc[p][1];
+				}
+			}
+			float2 v0, v1;
+			v0.x = fmaf(t0, fmaf(t0, c0.x, b0.x), a0.x);
+			v0.y = fmaf(t0, fmaf(t0, c0.y, b0.y), a0.y);
+			v1.x = fmaf(t1, fmaf(t1, c1.x, b1.x), a1.x);
+			v1.y = fmaf(t1, fmaf(t1, c1.y, b1.y), a1.y);
+			if (shared) { // one row group fanned out to every bus of the mask
+				uint32_t m = ci.mask;
+				while (m) {
+					const int b = __ffs(m) - 1;
+					m &= m - 1;
+					red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, v0.x, v0.y, v1.x, v1.y);
+				}
+			} else {
+				red_add_v4(bus + ((size_t)(b_own * C + c) * F + frame0) * 2, v0.x, v0.y, v1.x, v1.y);
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, GlobalCfg g, StreamCfg cf,
+		const gas_frame *__restrict__ src, float *__restrict__ bus) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
+	__shared__ __align__(8) uint64_t s_full[kMaxStages];
+	__shared__ __align__(8) uint64_t s_empty[kMaxStages];
+
+	const int tid = threadIdx.x;
+	const int warp = tid >> 5, lane = tid & 31;
+	const int C = g.channels;
+	const int maxv = g.max_voices;
+
+	if (tid < GAS_MAX_CLASSES) {
+		s_cls[tid] = plan.cls[tid];
+	}
+	if (tid == 0) {
+		for (int s = 0; s < cf.stages; s++) {
+			mbar_init(&s_full[s], 1);
+			mbar_init(&s_empty[s], kConsumerWarps);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	UnitIter it;
+	unit_iter_init(it, s_cls, cf, blockIdx.x, gridDim.x);
+	if (it.remaining <= 0) {
+		return;
+	}
+
+	if (warp == kConsumerWarps) {
+		// ===== producer =====
+		int stage = 0;
+		uint32_t phase = 0;
+		while (it.remaining > 0) {
+			const ClassInfo &ci = s_cls[it.cid];
+			const int v0 = it.batch * cf.vb;
+			const int nv = min(cf.vb, ci.count - v0);
+			const int tile_w = min(cf.tile_frames, cf.frames - it.tile * kTileFrames); // frames in this tile
+			const uint32_t row_bytes = (uint32_t)tile_w * 8u;
+			const int nf = ci.n_rows * C * 2; // floats of weights per voice
+			const uint32_t w_bytes = ((uint32_t)(nv * nf * 4) + 15u) & ~15u;
+			unsigned char *sx = smem + (size_t)stage * cf.stage_bytes;
+			unsigned char *sw = sx + cf.x_bytes;
+			mbar_wait(&s_empty[stage], phase ^ 1u);
+			if (lane == 0) {
+				mbar_arrive_expect_tx(&s_full[stage], row_bytes * (uint32_t)nv + w_bytes);
+				bulk_g2s(sw, plan.k2_rows + (size_t)it.cid * maxv * GAS_K2_ROW_FLOATS + (size_t)v0 * nf, w_bytes, &s_full[stage]);
+			}
+			__syncwarp();
+			for (int v = lane; v < nv; v += 32) {
+				const int row = plan.k2_src[(size_t)it.cid * maxv + v0 + v];
+				bulk_g2s(sx + (size_t)v * row_bytes, src + (size_t)row * cf.src_stride + (size_t)it.tile * kTileFrames, row_bytes, &s_full[stage]);
+			}
+			if (++stage == cf.stages) {
+				stage = 0;
+				phase ^= 1u;
+			}
+			unit_iter_next(it, s_cls, cf);
+		}
+	} else {
+		// ===== consumers =====
+		ConsumerCtx cc;
+		cc.smem = smem;
+		cc.full = s_full;
+		cc.empty = s_empty;
+		cc.cls = s_cls;
+		cc.C = C;
+		cc.lane = lane;
+		cc.slot = tid % cf.slots;
+		cc.group = tid / cf.slots;
+		cc.worker = cc.group < cf.groups;
+		cc.stage = 0;
+		cc.phase = 0;
+		while (it.remaining > 0) {
+			const int np = s_cls[it.cid].n_rows * C;
+			switch (np) {
+				case 2: consumer_run<2>(it, cc, cf, bus); break;
+				case 3: consumer_run<3>(it, cc, cf, bus); break;
+				case 4: consumer_run<4>(it, cc, cf, bus); break;
+				case 6: consumer_run<6>(it, cc, cf, bus); break;
+				case 8: consumer_run<8>(it, cc, cf, bus); break;
+				case 9: consumer_run<9>(it, cc, cf, bus); break;
+				case 12: consumer_run<12>(it, cc, cf, bus); break;
+				case 16: consumer_run<16>(it, cc, cf, bus); break;
+				case 18: consumer_run<18>(it, cc, cf, bus); break;
+				case 24: consumer_run<24>(it, cc, cf, bus); break;
+				default: // cannot happen (rows in {2,3,4,6} x pairs in {1..4}); drain so the producer never stalls
+					consumer_run<1>(it, cc, cf, bus);
+					break;
+			}
+		}
+	}
+}
+
+} // namespace
+
+static StreamCfg make_cfg(int frames, int src_stride, int smem_limit) {
+	StreamCfg cf{};
+	cf.frames = frames;
+	cf.src_stride = src_stride;
+	cf.tile_frames = frames < kTileFrames ? frames : kTileFrames;
+	cf.n_tiles = (frames + kTileFrames - 1) / kTileFrames;
+	cf.slots = cf.tile_frames / 2;
+	cf.groups = kConsumerThreads / cf.slots;
+	if (cf.groups < 1) {
+		cf.groups = 1;
+	}
+	int vb = 32768 / (cf.tile_frames * 8);
+	vb = vb < 8 ? 8 : (vb > 32 ? 32 : vb);
+	cf.vb = vb;
+	cf.x_bytes = vb * cf.tile_frames * 8;
+	cf.w_bytes = (vb * kMaxPairs * 8 + 127) & ~127;
+	cf.stage_bytes = cf.x_bytes + cf.w_bytes;
+	int stages = smem_limit / cf.stage_bytes;
+	cf.stages = stages > kMaxStages ? kMaxStages : stages;
+	return cf;
+}
+
+cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, cudaStream_t st) {
+	static const int kSmemLimit = 208 * 1024;
+	StreamCfg cf = make_cfg(frames, src_stride, kSmemLimit);
+	if (cf.stages < 2) {
+		return cudaErrorInvalidConfiguration;
+	}
+	const size_t smem = (size_t)cf.stages * cf.stage_bytes;
+	if (!ctx->k2_smem_attr_set) {
+		cudaError_t e = cudaFuncSetAttribute(k_mix_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+		if (e != cudaSuccess) {
+			return e;
+		}
+		ctx->k2_smem_attr_set = true;
+	}
+	k_mix_stream<<<ctx->num_sms, kThreads, smem, st>>>(ctx->plan, ctx->g, cf, d_src, (float *)d_bus);
+	ctx->launches++;
+	return cudaGetLastError();
+}

@@ -1,0 +1,412 @@
+// gas_mix_voice.cu — K3: the voice-parallel mix kernel (sm_100a).
+//
+// Voices whose block contains a per-sample recurrence — the attenuation high-shelf biquad of
+// process_frames / mix_channel (reference audio_spatializer_3d.cpp:503-529, :568-597, upstream
+// AudioFilterSW::Processor) or an AudioSpatializerEffect filter chain (reference
+// audio_spatializer_effect.cpp:33-77) — and voices that must report a block peak
+// (reference audio_spatializer.cpp:419-461) run here: one lane per voice, serial in time, filter state in
+// registers for the whole block, 32 voices of one class per warp.  After the per-voice work the
+// AudioServer ramp (upstream _mix_step_for_channel) is applied per lane and the 32 voices are summed
+// with a transposing warp-shuffle reduction; each lane ends up owning one (send, pair, frame, side)
+// element which it adds to the bus buffer.
+//
+// Sends are processed two at a time; a voice with more than two sends (bus transitions) is run in
+// several passes from the same initial state — every pass recomputes bit-identical samples, only the
+// last one stores state and peaks.
+#include "gas_internal.h"
+
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct Biquad {
+	float ha1, ha2, hb1, hb2;
+};
+
+// upstream AudioFilterSW::Processor::process_one: y = x*b0 + hb1*b1 + hb2*b2 + ha1*a1 + ha2*a2
+__device__ __forceinline__ float biquad_step(Biquad &h, float x, float b0, float b1, float b2, float a1, float a2) {
+	float y = x * b0 + h.hb1 * b1 + h.hb2 * b2 + h.ha1 * a1 + h.ha2 * a2;
+	h.ha2 = h.ha1;
+	h.hb2 = h.hb1;
+	h.hb1 = x;
+	h.ha1 = y;
+	return y;
+}
+
+// Transposing reduction: NV (power of two <= 32) per-lane values are summed over the 32 lanes; on
+// return v[0] of lane l holds the total of element l >> (5 - log2 NV).
+template <int NV>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane) {
+	int m = 16;
+#pragma unroll
+	for (int w = NV / 2; w >= 1; w >>= 1) {
+		const bool upper = (lane & m) != 0;
+#pragma unroll
+		for (int i = 0; i < w; i++) {
+			const float send = upper ? v[i] : v[i + w];
+			const float keep = upper ? v[i + w] : v[i];
+			v[i] = keep + __shfl_xor_sync(kFull, send, m);
+		}
+		m >>= 1;
+	}
+#pragma unroll
+	for (; m >= 1; m >>= 1) {
+		v[0] += __shfl_xor_sync(kFull, v[0], m);
+	}
+	return v[0];
+}
+
+template <int N>
+struct Pow2Ceil {
+	static constexpr int value = N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : 32));
+};
+
+struct ChunkArgs {
+	const VoiceRec *rec;
+	const int32_t *list;  // class list (call-order indices)
+	int count;            // voices in the class
+	int chunk;            // which 32-voice chunk
+	uint32_t cls_flags;
+	uint32_t mask;
+	int n_send;
+};
+
+// One pass of one 32-voice chunk.  MODE: MODE_A / MODE_B / MODE_E.  C: channel pairs.  NS: sends handled
+// in this pass (1 or 2).  `emit` false => NS == 1 with no bus output (state/peak only).
+template <int MODE, int C, int NS>
+__device__ void voice_pass(const DevTables &t, const GlobalCfg &g, const ChunkArgs &a, int send0, bool emit, bool last_pass,
+		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks) {
+	const int lane = threadIdx.x & 31;
+	const int pos = a.chunk * 32 + lane;
+	const bool active = pos < a.count;
+	const int j = active ? a.list[pos] : -1;
+	constexpr int NY = (MODE == MODE_B) ? C : 1; // distinct processed streams per voice (pairs)
+	constexpr int NPROC = NY * 2;
+
+	VoiceRec r;
+	if (active) {
+		r = a.rec[j];
+	} else {
+		r.voice = 0;
+		r.instance = 0;
+		r.src_row = -1;
+		r.flags = 0;
+		r.n_fx = 0;
+		for (int c = 0; c < 4; c++) {
+			r.m_prev[c][0] = r.m_prev[c][1] = r.m_new[c][0] = r.m_new[c][1] = 0.f;
+		}
+		for (int k = 0; k < 5; k++) {
+			r.target[k] = 0.f;
+		}
+	}
+	const bool filt = (a.cls_flags & CLS_FILT) != 0;
+	const bool want_peak = active && (r.flags & GAS_VOICE_WANT_PEAK);
+
+	// AudioServer ramps of the sends handled in this pass
+	float np[NS][C][2], nn[NS][C][2];
+	int bus_of[NS];
+	{
+		const InstSends *snd = &t.inst_sends[r.instance];
+		uint32_t m = a.mask;
+		for (int s = 0; s < send0; s++) {
+			m &= m - 1;
+		}
+#pragma unroll
+		for (int s = 0; s < NS; s++) {
+			bus_of[s] = m ? (__ffs(m) - 1) : 0;
+			m &= m - 1;
+#pragma unroll
+			for (int c = 0; c < C; c++) {
+				const bool ok = active && emit && (send0 + s) < a.n_send;
+				np[s][c][0] = ok ? snd->vp[send0 + s][c][0] : 0.f;
+				np[s][c][1] = ok ? snd->vp[send0 + s][c][1] : 0.f;
+				nn[s][c][0] = ok ? snd->vn[send0 + s][c][0] : 0.f;
+				nn[s][c][1] = ok ? snd->vn[send0 + s][c][1] : 0.f;
+			}
+		}
+	}
+
+	// ---- filter state -------------------------------------------------------------------------------
+	// MODE_A/B: interpolated high-shelf processors (pair*2 + side), MODE_E: constant-coefficient chain.
+	Biquad h[NPROC];
+	float cf[NPROC][5], inc[NPROC][5];
+	gas_processor_state *ps = t.vs_proc + (size_t)r.voice * 8;
+	if (MODE != MODE_E) {
+#pragma unroll
+		for (int k = 0; k < NPROC; k++) {
+			const int pair = k >> 1;
+			gas_processor_state st{};
+			if (active && filt) {
+				st = ps[k];
+			}
+			const bool clear = (r.flags >> (8 + pair)) & 1u; // is_just_started => clear history (:518-521, :583-586)
+			h[k].ha1 = clear ? 0.f : st.ha1;
+			h[k].ha2 = clear ? 0.f : st.ha2;
+			h[k].hb1 = clear ? 0.f : st.hb1;
+			h[k].hb2 = clear ? 0.f : st.hb2;
+			cf[k][0] = st.b0;
+			cf[k][1] = st.b1;
+			cf[k][2] = st.b2;
+			cf[k][3] = st.a1;
+			cf[k][4] = st.a2;
+#pragma unroll
+			for (int q = 0; q < 5; q++) { // update_coeffs(F): per-sample increment towards the target
+				inc[k][q] = (r.target[q] - cf[k][q]) / (float)F;
+			}
+		}
+	}
+	// effect chain history lives in local memory (dynamic structure); [effect][side][stage]{ha1,ha2,hb1,hb2}
+	float fxh[GAS_MAX_EFFECTS][2][GAS_MAX_FILTER_STAGES][4];
+	float *fxs = t.vs_fx + (size_t)r.voice * (GAS_MAX_EFFECTS * 2 * GAS_MAX_FILTER_STAGES * 4);
+	if (MODE == MODE_E) {
+		for (int e = 0; e < GAS_MAX_EFFECTS; e++) {
+			for (int s = 0; s < 2; s++) {
+				for (int q = 0; q < GAS_MAX_FILTER_STAGES; q++) {
+					for (int k = 0; k < 4; k++) {
+						fxh[e][s][q][k] = (active && e < r.n_fx) ? fxs[((e * 2 + s) * GAS_MAX_FILTER_STAGES + q) * 4 + k] : 0.f;
+					}
+				}
+			}
+		}
+	}
+
+	float pk_l = 0.f, pk_r = 0.f;
+	const float4 *row = (active && r.src_row >= 0) ? reinterpret_cast<const float4 *>(src + (size_t)r.src_row * src_stride) : nullptr;
+	const float invF = 1.0f; // t is computed as (float)i / F exactly like the reference
+	(void)invF;
+
+	constexpr int NVRAW = NS * C * 4;            // values per 2-frame group
+	constexpr int NV = Pow2Ceil<NVRAW>::value;
+	const int shift = (NV == 32) ? 0 : (NV == 16 ? 1 : (NV == 8 ? 2 : 3));
+
+	for (int i0 = 0; i0 < F; i0 += 8) { // 8 frames (64 bytes of this voice's row) per trip
+		float4 xb[4];
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			xb[u] = (row && (i0 + 2 * u) < F) ? __ldg(row + (i0 >> 1) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const int ia = i0 + 2 * u;
+			if (ia >= F) {
+				break;
+			}
+			float v[NV];
+#pragma unroll
+			for (int k = 0; k < NV; k++) {
+				v[k] = 0.f;
+			}
+#pragma unroll
+			for (int f = 0; f < 2; f++) {
+				const int i = ia + f;
+				const float tt = (float)i / (float)F;   // :591
+				const float omt = 1.0f - tt;
+				const float xl = f == 0 ? xb[u].x : xb[u].z;
+				const float xr = f == 0 ? xb[u].y : xb[u].w;
+				float y[NY][2];
+				if (MODE == MODE_B) {
+#pragma unroll
+					for (int c = 0; c < C; c++) {
+						const float vl = r.m_new[c][0] * tt + omt * r.m_prev[c][0]; // :592
+						const float vr = r.m_new[c][1] * tt + omt * r.m_prev[c][1];
+						float ml = vl * xl, mr = vr * xr;                         // :593
+						if (filt) {
+							const int kl = c * 2, kr = c * 2 + 1;
+							ml = biquad_step(h[kl], ml, cf[kl][0], cf[kl][1], cf[kl][2], cf[kl][3], cf[kl][4]); // :594
+							mr = biquad_step(h[kr], mr, cf[kr][0], cf[kr][1], cf[kr][2], cf[kr][3], cf[kr][4]); // :595
+#pragma unroll
+							for (int q = 0; q < 5; q++) { // process_one_interp: coeffs += incr
+								cf[kl][q] += inc[kl][q];
+								cf[kr][q] += inc[kr][q];
+							}
+						}
+						y[c][0] = ml;
+						y[c][1] = mr;
+					}
+				} else if (MODE == MODE_A) {
+					float ml = xl, mr = xr;
+					if (filt) { // :524-529
+						ml = biquad_step(h[0], ml, cf[0][0], cf[0][1], cf[0][2], cf[0][3], cf[0][4]);
+						mr = biquad_step(h[1], mr, cf[1][0], cf[1][1], cf[1][2], cf[1][3], cf[1][4]);
+#pragma unroll
+						for (int q = 0; q < 5; q++) {
+							cf[0][q] += inc[0][q];
+							cf[1][q] += inc[1][q];
+						}
+					}
+					y[0][0] = ml;
+					y[0][1] = mr;
+				} else { // MODE_E: cascaded constant-coefficient biquads per effect, left then right
+					float ml = xl, mr = xr;
+					for (int e = 0; e < r.n_fx; e++) {
+						const float b0 = r.fx_coef[e][0], b1 = r.fx_coef[e][1], b2 = r.fx_coef[e][2], a1 = r.fx_coef[e][3], a2 = r.fx_coef[e][4];
+						for (int q = 0; q < r.fx_stages[e]; q++) {
+							float *hl = fxh[e][0][q], *hr = fxh[e][1][q];
+							float pl = ml, pr = mr;
+							ml = ml * b0 + hl[2] * b1 + hl[3] * b2 + hl[0] * a1 + hl[1] * a2;
+							mr = mr * b0 + hr[2] * b1 + hr[3] * b2 + hr[0] * a1 + hr[1] * a2;
+							hl[1] = hl[0];
+							hl[3] = hl[2];
+							hl[2] = pl;
+							hl[0] = ml;
+							hr[1] = hr[0];
+							hr[3] = hr[2];
+							hr[2] = pr;
+							hr[0] = mr;
+						}
+					}
+					y[0][0] = ml;
+					y[0][1] = mr;
+				}
+				// block peak over all processed streams (audio_spatializer.cpp:436-443, :453-460)
+#pragma unroll
+				for (int c = 0; c < NY; c++) {
+					pk_l = fmaxf(pk_l, fabsf(y[c][0]));
+					pk_r = fmaxf(pk_r, fabsf(y[c][1]));
+				}
+				// AudioServer ramp per send / pair / side (upstream _mix_step_for_channel)
+#pragma unroll
+				for (int s = 0; s < NS; s++) {
+#pragma unroll
+					for (int c = 0; c < C; c++) {
+						const int yc = (MODE == MODE_B) ? c : 0;
+						const float wl = nn[s][c][0] * tt + omt * np[s][c][0];
+						const float wr = nn[s][c][1] * tt + omt * np[s][c][1];
+						v[((s * C + c) * 2 + f) * 2 + 0] = wl * y[yc][0];
+						v[((s * C + c) * 2 + f) * 2 + 1] = wr * y[yc][1];
+					}
+				}
+			}
+			if (emit) {
+				const float tot = warp_transpose_reduce<NV>(v, lane);
+				const int idx = lane >> shift;
+				const bool owner = (lane & ((1 << shift) - 1)) == 0 && idx < NVRAW;
+				if (owner) {
+					const int side = idx & 1, f = (idx >> 1) & 1, sc = idx >> 2;
+					const int c = sc % C, s = sc / C;
+					atomicAdd(bus + ((size_t)(bus_of[s] * C + c) * F + ia + f) * 2 + side, tot);
+				}
+			}
+		}
+	}
+
+	if (last_pass && active) {
+		if (MODE != MODE_E && filt) {
+#pragma unroll
+			for (int k = 0; k < NPROC; k++) {
+				gas_processor_state st;
+				st.b0 = cf[k][0];
+				st.b1 = cf[k][1];
+				st.b2 = cf[k][2];
+				st.a1 = cf[k][3];
+				st.a2 = cf[k][4];
+				st.ha1 = h[k].ha1;
+				st.ha2 = h[k].ha2;
+				st.hb1 = h[k].hb1;
+				st.hb2 = h[k].hb2;
+				ps[k] = st;
+			}
+		}
+		if (MODE == MODE_E) {
+			for (int e = 0; e < r.n_fx; e++) {
+				for (int s = 0; s < 2; s++) {
+					for (int q = 0; q < GAS_MAX_FILTER_STAGES; q++) {
+						for (int k = 0; k < 4; k++) {
+							fxs[((e * 2 + s) * GAS_MAX_FILTER_STAGES + q) * 4 + k] = fxh[e][s][q][k];
+						}
+					}
+				}
+			}
+		}
+		if (want_peak && peaks) {
+			peaks[j] = make_float2(pk_l, pk_r);
+		}
+	}
+}
+
+template <int MODE, int C>
+__device__ void voice_chunk(const DevTables &t, const GlobalCfg &g, const ChunkArgs &a, const gas_frame *__restrict__ src, int src_stride,
+		int F, float *__restrict__ bus, float2 *__restrict__ peaks) {
+	const int n = a.n_send;
+	if (n == 0) {
+		voice_pass<MODE, C, 1>(t, g, a, 0, false, true, src, src_stride, F, bus, peaks);
+		return;
+	}
+	for (int s0 = 0; s0 < n; s0 += 2) {
+		const bool last = s0 + 2 >= n;
+		if (n - s0 >= 2) {
+			voice_pass<MODE, C, 2>(t, g, a, s0, true, last, src, src_stride, F, bus, peaks);
+		} else {
+			voice_pass<MODE, C, 1>(t, g, a, s0, true, last, src, src_stride, F, bus, peaks);
+		}
+	}
+}
+
+template <int C>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_mix_voice(DevTables t, GlobalCfg g, BlockPlan plan,
+		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks) {
+	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
+	if (threadIdx.x < GAS_MAX_CLASSES) {
+		s_cls[threadIdx.x] = plan.cls[threadIdx.x];
+	}
+	__syncthreads();
+	const int warp_global = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+	const int n_warps = gridDim.x * kWarpsPerCta;
+	// units: 32-voice chunks of every PATH_VOICE class, dealt round-robin to warps
+	int unit = 0;
+	for (int c = 0; c < GAS_MAX_CLASSES; c++) {
+		const ClassInfo &ci = s_cls[c];
+		if (ci.key == 0ULL || ci.path != PATH_VOICE) {
+			continue;
+		}
+		const int chunks = (ci.count + 31) / 32;
+		for (int k = 0; k < chunks; k++, unit++) {
+			if (unit % n_warps != warp_global) {
+				continue;
+			}
+			ChunkArgs a;
+			a.rec = plan.rec;
+			a.list = plan.k3_list + (size_t)c * g.max_voices;
+			a.count = ci.count;
+			a.chunk = k;
+			a.cls_flags = ci.flags;
+			a.mask = ci.mask;
+			a.n_send = ci.n_send;
+			switch (ci.mode) {
+				case MODE_A:
+					voice_chunk<MODE_A, C>(t, g, a, src, src_stride, F, bus, peaks);
+					break;
+				case MODE_B:
+					voice_chunk<MODE_B, C>(t, g, a, src, src_stride, F, bus, peaks);
+					break;
+				default:
+					voice_chunk<MODE_E, C>(t, g, a, src, src_stride, F, bus, peaks);
+					break;
+			}
+		}
+	}
+}
+
+} // namespace
+
+cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus,
+		gas_frame *d_peaks, cudaStream_t st) {
+	const int grid = ctx->num_sms * 4;
+	switch (ctx->g.channels) {
+		case 1:
+			k_mix_voice<1><<<grid, kWarpsPerCta * 32, 0, st>>>(ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks);
+			break;
+		case 2:
+			k_mix_voice<2><<<grid, kWarpsPerCta * 32, 0, st>>>(ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks);
+			break;
+		case 3:
+			k_mix_voice<3><<<grid, kWarpsPerCta * 32, 0, st>>>(ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks);
+			break;
+		default:
+			k_mix_voice<4><<<grid, kWarpsPerCta * 32, 0, st>>>(ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks);
+			break;
+	}
+	ctx->launches++;
+	return cudaGetLastError();
+}

@@ -1,0 +1,222 @@
+"""Mixer — thin numpy-facing wrapper of the C ABI (one gas_ctx).
+
+Method names follow include/gas.h one to one; each docstring names the reference interface the call
+replaces.  Array arguments are numpy structured arrays with the dtypes of ``abi`` (or anything
+convertible); device-side variants take raw device pointers (e.g. ``tensor.data_ptr()``).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .lib import check, load
+
+
+def _arr(x, dtype):
+    a = np.ascontiguousarray(np.asarray(x, dtype=dtype))
+    return a
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)
+
+
+class Mixer:
+    def __init__(self, **config):
+        """gas_create.  Keyword arguments override abi.config_defaults()."""
+        self._lib = load()
+        self.config = abi.config_defaults(**config)
+        self._ctx = C.c_void_p()
+        st = self._lib.gas_create(_ptr(self.config.reshape(1)), C.byref(self._ctx))
+        if st != 0:
+            msg = self._lib.gas_last_error(None)
+            from .lib import GasError
+            raise GasError(st, msg.decode() if msg else "")
+
+    # ---- lifetime -----------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.gas_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def channels(self):
+        return int(self._lib.gas_get_channel_count(self._ctx))
+
+    @property
+    def num_buses(self):
+        return int(self.config["num_buses"])
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.gas_kernel_launches(self._ctx))
+
+    @property
+    def mix_stream(self):
+        return self._lib.gas_mix_stream(self._ctx)
+
+    @property
+    def gain_stream(self):
+        return self._lib.gas_gain_stream(self._ctx)
+
+    def _ck(self, st):
+        check(st, self._ctx)
+
+    # ---- globals (AudioServer::get_speaker_mode / get_mix_rate, 3d_panning_strength) -----------------
+    def set_speaker_mode(self, mode):
+        self._ck(self._lib.gas_set_speaker_mode(self._ctx, int(mode)))
+        self.config["speaker_mode"] = mode
+
+    def set_mix_rate(self, hz):
+        self._ck(self._lib.gas_set_mix_rate(self._ctx, float(hz)))
+        self.config["mix_rate"] = hz
+
+    def set_global_panning_strength(self, s):
+        self._ck(self._lib.gas_set_global_panning_strength(self._ctx, float(s)))
+        self.config["global_panning_strength"] = s
+
+    # ---- resources / slots ----------------------------------------------------------------------------
+    def spatializer_set(self, slot, spat):
+        """AudioSpatializer3D property setters with their validation (audio_spatializer_3d.cpp:654-765)."""
+        s = _arr(spat, abi.spatializer).reshape(1)
+        self._ck(self._lib.gas_spatializer_set(self._ctx, int(slot), _ptr(s)))
+
+    def instance_init(self, instances, spatializers):
+        """AudioSpatializer::instantiate (audio_spatializer_3d.cpp:645-652)."""
+        i = _arr(instances, np.int32)
+        s = np.broadcast_to(_arr(spatializers, np.int32), i.shape).copy()
+        self._ck(self._lib.gas_instance_init(self._ctx, i.size, _ptr(i), _ptr(s)))
+
+    def instance_start(self, instances):
+        """Proxy playbacks registered with AudioServer (audio_spatializer.cpp:75-95)."""
+        i = _arr(instances, np.int32)
+        self._ck(self._lib.gas_instance_start(self._ctx, i.size, _ptr(i)))
+
+    def instance_stop(self, instances):
+        i = _arr(instances, np.int32)
+        self._ck(self._lib.gas_instance_stop(self._ctx, i.size, _ptr(i)))
+
+    def voice_init(self, voices):
+        """instantiate_playback_data (audio_spatializer_3d.cpp:200-204)."""
+        v = _arr(voices, np.int32)
+        self._ck(self._lib.gas_voice_init(self._ctx, v.size, _ptr(v)))
+
+    # ---- gain side --------------------------------------------------------------------------------------
+    def gain_compute(self, emitters, listeners, areas=None, want_params=True):
+        """Batched calculate_spatialization + update_spatializer_parameters
+        (audio_spatializer_3d.cpp:277-489, audio_spatializer.cpp:258-272)."""
+        e = _arr(emitters, abi.emitter).reshape(-1)
+        l = _arr(listeners, abi.listener).reshape(-1)
+        a = _arr(areas, abi.area).reshape(-1) if areas is not None else None
+        out = np.zeros(e.size, dtype=abi.params) if want_params else None
+        self._ck(self._lib.gas_gain_compute(self._ctx, e.size, _ptr(e), l.size, _ptr(l),
+                                            0 if a is None else a.size, _ptr(a), _ptr(out)))
+        return out
+
+    def gain_compute_device(self, n, d_emitters, listeners, areas=None, d_out_params=0):
+        l = _arr(listeners, abi.listener).reshape(-1)
+        a = _arr(areas, abi.area).reshape(-1) if areas is not None else None
+        self._ck(self._lib.gas_gain_compute_device(self._ctx, int(n), C.c_void_p(d_emitters), l.size, _ptr(l),
+                                                   0 if a is None else a.size, _ptr(a), C.c_void_p(d_out_params)))
+
+    def params_set(self, instances, params):
+        """set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272, :558-564)."""
+        i = _arr(instances, np.int32)
+        p = _arr(params, abi.params).reshape(-1)
+        if p.size != i.size:
+            raise ValueError("one gas_params per instance")
+        self._ck(self._lib.gas_params_set(self._ctx, i.size, _ptr(i), _ptr(p)))
+
+    def params_get(self, instances):
+        i = _arr(instances, np.int32)
+        out = np.zeros(i.size, dtype=abi.params)
+        self._ck(self._lib.gas_params_get(self._ctx, i.size, _ptr(i), _ptr(out)))
+        return out
+
+    def effect_params_set(self, instances, chains):
+        """What a _process_effects override writes into its effects (audio_spatializer_effect.cpp:39)."""
+        i = _arr(instances, np.int32)
+        c = _arr(chains, abi.effect_chain).reshape(-1)
+        if c.size != i.size:
+            raise ValueError("one gas_effect_chain per instance")
+        self._ck(self._lib.gas_effect_params_set(self._ctx, i.size, _ptr(i), _ptr(c)))
+
+    # ---- mix side -----------------------------------------------------------------------------------------
+    def mix_block(self, voices, src, frames=None, want_peaks=True):
+        """Batched _mix_from_playback_list + AudioServer bus accumulate (audio_spatializer.cpp:326-471).
+
+        src: float32 [rows, frames, 2] (or abi.frame [rows, frames]).  Returns (bus, peaks) with
+        bus float32 [num_buses, channels, frames, 2] and peaks float32 [n_voices, 2] (or None)."""
+        v = _arr(voices, abi.voice).reshape(-1)
+        s = np.asarray(src)
+        if s.dtype == abi.frame:
+            s = s.view(np.float32).reshape(s.shape + (2,))
+        s = np.ascontiguousarray(s, dtype=np.float32)
+        if s.size == 0:
+            rows = 0
+            if frames is None:
+                raise ValueError("frames is required without source rows")
+        else:
+            if s.ndim != 3 or s.shape[2] != 2:
+                raise ValueError("src must be [rows, frames, 2]")
+            rows = s.shape[0]
+            if frames is None:
+                frames = s.shape[1]
+            elif frames != s.shape[1]:
+                raise ValueError("src row length must equal frames")
+        bus = np.empty((self.num_buses, self.channels, frames, 2), dtype=np.float32)
+        peaks = np.zeros((v.size, 2), dtype=np.float32) if want_peaks else None
+        self._ck(self._lib.gas_mix_block(self._ctx, v.size, _ptr(v), _ptr(s), rows, int(frames), _ptr(bus), _ptr(peaks)))
+        return bus, peaks
+
+    def mix_block_host_ptr(self, n_voices, voices_ptr, src_ptr, src_rows, frames, bus_ptr, peaks_ptr=0):
+        """gas_mix_block with caller-owned (e.g. pinned) host buffers given as raw addresses."""
+        self._ck(self._lib.gas_mix_block(self._ctx, int(n_voices), C.c_void_p(voices_ptr), C.c_void_p(src_ptr), int(src_rows),
+                                         int(frames), C.c_void_p(bus_ptr), C.c_void_p(peaks_ptr)))
+
+    def mix_block_device(self, n_voices, d_voices, d_src, src_rows, src_row_stride, frames, d_bus_out, d_peaks=0):
+        """gas_mix_block_device: asynchronous on the mix stream, everything device-resident."""
+        self._ck(self._lib.gas_mix_block_device(self._ctx, int(n_voices), C.c_void_p(d_voices), C.c_void_p(d_src), int(src_rows),
+                                                int(src_row_stride), int(frames), C.c_void_p(d_bus_out), C.c_void_p(d_peaks)))
+
+    def sync(self):
+        self._ck(self._lib.gas_sync(self._ctx))
+
+    # ---- persistent state ------------------------------------------------------------------------------------
+    def voice_state_export(self, voices):
+        v = _arr(voices, np.int32)
+        out = np.zeros(v.size, dtype=abi.voice_state)
+        self._ck(self._lib.gas_voice_state_export(self._ctx, v.size, _ptr(v), _ptr(out)))
+        return out
+
+    def voice_state_import(self, voices, states):
+        v = _arr(voices, np.int32)
+        s = _arr(states, abi.voice_state).reshape(-1)
+        if s.size != v.size:
+            raise ValueError("one gas_voice_state per voice")
+        self._ck(self._lib.gas_voice_state_import(self._ctx, v.size, _ptr(v), _ptr(s)))
+
+    # ---- multi-GPU exchange -----------------------------------------------------------------------------------
+    def comm_export(self):
+        buf = (C.c_ubyte * 64)()
+        self._ck(self._lib.gas_comm_export(self._ctx, buf, 64))
+        return bytes(buf)
+
+    def comm_open(self, rank, handles):
+        blob = b"".join(handles)
+        self._ck(self._lib.gas_comm_open(self._ctx, int(rank), len(handles), blob, 64))
+
+    def comm_close(self):
+        self._ck(self._lib.gas_comm_close(self._ctx))

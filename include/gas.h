@@ -1,0 +1,355 @@
+/*
+ * gas.h — C ABI of the B200-native batched spatial-audio mixer ("gas" = godot audio spatializer).
+ *
+ * This is the drop-in boundary for the data-parallel hot path of BuzzLord/godot-audio-spatializer:
+ * per-instance gain computation + per-voice volume-ramped / filtered mixing of AudioFrame buffers into
+ * bus channel buffers.  The reference has no C ABI; the closest thing is the raw-pointer GDExtension
+ * virtuals on AudioSpatializerInstance (reference audio_spatializer.h:103-112, :144-150).  Every entry
+ * point below names the reference interface it replaces.  Plain C types only: no torch, no C++.
+ *
+ * Vocabulary (same as the reference):
+ *   instance  = one AudioSpatializerInstance (one per AudioStreamPlayerSpatial).  Owns the
+ *               SpatializerParameters of the current physics tick and the AudioServer-side bus
+ *               volume state of its proxy playbacks.
+ *   voice     = one SpatialPlaybackListNode (audio_spatializer.h:55-66): one live playback of an
+ *               instance.  Owns SpatializerPlaybackData (prev mix volumes, filter processors).
+ *   pair      = one stereo channel pair of a bus (0 front L/R, 1 centre/LFE, 2 rear L/R, 3 side L/R).
+ *   bus       = AudioServer bus, addressed by index (0 = Master).  Unknown index => Master, like
+ *               AudioStreamPlayerSpatial::get_bus (audio_stream_player_spatial.cpp:405-413).
+ *
+ * Error convention: every call returns a gas_status (0 = OK).  Nothing throws, nothing aborts; on an
+ * invalid argument the context is left untouched (reference: ERR_FAIL_* macros, e.g.
+ * audio_spatializer_3d.cpp:670-672, spatializer_parameters.cpp:35-47).  gas_last_error() returns the
+ * message of the last failing call.  There is NO CPU fallback: without a CUDA device gas_create fails.
+ *
+ * Threading (reference audio_spatializer.h:135-139, README.md:26,32,51): gas_gain_compute /
+ * gas_params_set / gas_effect_params_set may be called from a "physics" thread while one "audio"
+ * thread calls gas_mix_block*; parameter hand-off is double-buffered inside the context and swapped
+ * under a mutex (reference audio_spatializer.cpp:558-574).  gas_mix_block* is single-caller.
+ */
+#ifndef GAS_H
+#define GAS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define GAS_API __declspec(dllexport)
+#else
+#define GAS_API __attribute__((visibility("default")))
+#endif
+
+/* ---- limits (reference audio_spatializer.h:47-52) ---------------------------------------------- */
+#define GAS_MAX_CHANNELS_PER_BUS 4
+#define GAS_LOOKAHEAD_BUFFER_SIZE 64
+#define GAS_MAX_BUSES_PER_PLAYBACK 6
+#define GAS_MAX_LISTENERS 8
+#define GAS_MAX_EFFECTS 4        /* AudioEffectFilter instances per AudioSpatializerEffect chain */
+#define GAS_MAX_FILTER_STAGES 4  /* AudioEffectFilter FILTER_6DB..FILTER_24DB */
+#define GAS_MAX_BUSES 16         /* bus indices a context can mix into */
+#define GAS_ABI_VERSION 1
+
+typedef enum gas_status {
+	GAS_OK = 0,
+	GAS_ERR_INVALID = 1, /* bad argument; context untouched */
+	GAS_ERR_CUDA = 2,    /* CUDA runtime/driver error; message has the CUDA string */
+	GAS_ERR_NOMEM = 3,
+	GAS_ERR_STATE = 4,   /* call not valid in the current state (e.g. comm not initialised) */
+	GAS_ERR_NCCL = 5,
+	GAS_ERR_NO_DEVICE = 6 /* no usable sm_100 device: there is no CPU fallback */
+} gas_status;
+
+/* AudioFrame (upstream servers/audio/audio_frame.h): 2 x fp32, 8 bytes. */
+typedef struct gas_frame {
+	float l, r;
+} gas_frame;
+
+/* AudioServer::SpeakerMode; channel pair count = mode + 1 (AudioServer::get_channel_count). */
+typedef enum gas_speaker_mode {
+	GAS_SPEAKER_MODE_STEREO = 0,
+	GAS_SPEAKER_SURROUND_31 = 1,
+	GAS_SPEAKER_SURROUND_51 = 2,
+	GAS_SPEAKER_SURROUND_71 = 3
+} gas_speaker_mode;
+
+/* AudioSpatializer3D::AttenuationModel (audio_spatializer_3d.h:157-162). */
+typedef enum gas_attenuation_model {
+	GAS_ATTENUATION_INVERSE_DISTANCE = 0,
+	GAS_ATTENUATION_INVERSE_SQUARE_DISTANCE = 1,
+	GAS_ATTENUATION_LOGARITHMIC = 2,
+	GAS_ATTENUATION_DISABLED = 3
+} gas_attenuation_model;
+
+/* AudioSpatializer3D::DopplerTracking (audio_spatializer_3d.h:164-168). */
+typedef enum gas_doppler_tracking {
+	GAS_DOPPLER_TRACKING_DISABLED = 0,
+	GAS_DOPPLER_TRACKING_IDLE_STEP = 1,
+	GAS_DOPPLER_TRACKING_PHYSICS_STEP = 2
+} gas_doppler_tracking;
+
+typedef enum gas_spatializer_kind {
+	GAS_SPATIALIZER_3D = 0,    /* AudioSpatializer3D (audio_spatializer_3d.h:153-241) */
+	GAS_SPATIALIZER_EFFECT = 1 /* AudioSpatializerEffect (audio_spatializer_effect.h:83-96), filter-chain subset */
+} gas_spatializer_kind;
+
+/* upstream AudioFilterSW::Mode (servers/audio/audio_filter_sw.h). */
+typedef enum gas_filter_mode {
+	GAS_FILTER_BANDPASS = 0,
+	GAS_FILTER_HIGHPASS = 1,
+	GAS_FILTER_LOWPASS = 2,
+	GAS_FILTER_NOTCH = 3,
+	GAS_FILTER_PEAK = 4,
+	GAS_FILTER_BANDLIMIT = 5,
+	GAS_FILTER_LOWSHELF = 6,
+	GAS_FILTER_HIGHSHELF = 7
+} gas_filter_mode;
+
+/* One AudioEffectFilter of an AudioSpatializerEffect chain (upstream AudioEffectFilter properties;
+ * example gd_spatializer.gd:14-19).  `stages` = int(db)+1, 1..4. */
+typedef struct gas_effect {
+	int32_t mode; /* gas_filter_mode */
+	float cutoff_hz;
+	float resonance;
+	float gain;
+	int32_t stages;
+} gas_effect;
+
+typedef struct gas_effect_chain {
+	int32_t n_effects; /* 0..GAS_MAX_EFFECTS; 0 => process_frames is a copy (audio_spatializer_effect.cpp:41-46) */
+	gas_effect effects[GAS_MAX_EFFECTS];
+} gas_effect_chain;
+
+/* AudioSpatializer3D resource properties (audio_spatializer_3d.h:171-188), plus the effect chain of an
+ * AudioSpatializerEffect.  Defaults: see gas_spatializer_defaults(). */
+typedef struct gas_spatializer {
+	int32_t kind;              /* gas_spatializer_kind */
+	int32_t attenuation_model; /* gas_attenuation_model */
+	float unit_size;
+	float max_distance;
+	float panning_strength;
+	uint32_t area_mask; /* carried, unused on device (physics query is the caller's) */
+	int32_t emission_angle_enabled;
+	float emission_angle; /* degrees, [0, 90] */
+	float emission_angle_filter_attenuation_db;
+	float attenuation_filter_cutoff_hz;
+	float attenuation_filter_db;
+	int32_t doppler_tracking; /* gas_doppler_tracking */
+	float doppler_speed_of_sound;
+	int32_t mix_channel_mode; /* 0 = Mode A (_process_frames), 1 = Mode B (_mix_channel); EFFECT is always 0 */
+	/* EFFECT kind only: effect whose `gain` is bound to SpatializerParameters3D::linear_attenuation each
+	 * block, as the example's _process_effects does (gd_spatializer_instance.gd:125-127); -1 = none. */
+	int32_t effect_gain_binding;
+	gas_effect_chain chain;
+} gas_spatializer;
+
+/* Listener = Camera3D / AudioListener3D global transform + doppler velocity
+ * (audio_spatializer_3d.cpp:335-344, :408-412).  basis is row-major rows[3][3] like Godot's Basis. */
+typedef struct gas_listener {
+	float basis[9];
+	float origin[3];
+	float velocity[3];
+} gas_listener;
+
+/* Result of the physics-side Area3D query for one emitter (audio_spatializer_3d.cpp:206-245, :346-354).
+ * closest_point[l] = PhysicsDirectSpaceState3D::get_closest_point_to_object_volume(area, listener l origin). */
+typedef struct gas_area {
+	int32_t override_bus; /* Area3D::is_overriding_audio_bus */
+	int32_t bus;          /* Area3D::get_audio_bus_name, as bus index */
+	int32_t use_reverb;   /* Area3D::is_using_reverb_bus */
+	int32_t reverb_bus;   /* Area3D::get_reverb_bus_name, as bus index */
+	float reverb_amount;
+	float reverb_uniformity;
+	float closest_point[GAS_MAX_LISTENERS][3];
+} gas_area;
+
+/* Per-instance inputs of calculate_spatialization (audio_spatializer_3d.cpp:277-489): what the
+ * reference reads from get_audio_player() and the scene. */
+typedef struct gas_emitter {
+	int32_t instance;    /* instance slot the result is stored for */
+	int32_t spatializer; /* gas_spatializer slot (the shared resource) */
+	int32_t area;        /* index into the areas array, -1 = none */
+	int32_t bus;         /* AudioStreamPlayerSpatial::get_bus as index (out of range => 0 = Master) */
+	float origin[3];     /* get_global_transform().origin */
+	float basis_z[3];    /* get_global_transform().basis.get_column(2) (emission direction is -Z) */
+	float velocity[3];   /* VelocityTracker3D::get_tracked_linear_velocity */
+	float volume_db;
+	float max_db;
+	float pitch_scale;
+} gas_emitter;
+
+/* SpatializerParameters + SpatializerParameters3D (spatializer_parameters.h:39-67,
+ * audio_spatializer_3d.h:61-83) as one POD record.  bus/bus_volumes keep Dictionary insertion order. */
+typedef struct gas_params {
+	float mix_volumes[GAS_MAX_CHANNELS_PER_BUS][2];
+	float pitch_scale;
+	float linear_attenuation;            /* aka high-shelf gain */
+	float attenuation_filter_cutoff_hz;
+	int32_t update_parameters;
+	int32_t n_bus;                       /* 0..GAS_MAX_BUSES_PER_PLAYBACK */
+	int32_t bus[GAS_MAX_BUSES_PER_PLAYBACK];
+	float bus_volumes[GAS_MAX_BUSES_PER_PLAYBACK][GAS_MAX_CHANNELS_PER_BUS][2];
+} gas_params;
+
+/* One voice of a mix block. */
+#define GAS_VOICE_WANT_PEAK 1u /* compute this voice's block peak (reference computes it always,
+                                  audio_spatializer.cpp:419-461, but only reads it when !has_frames, :464) */
+typedef struct gas_voice {
+	int32_t voice;    /* playback-data slot */
+	int32_t instance; /* owning instance slot */
+	int32_t src_row;  /* row of `src` holding this voice's frames; -1 = silence (the reference's
+	                     zero-filled playback_buffer once has_frames is clear, audio_spatializer.cpp:405-408) */
+	uint32_t flags;
+} gas_voice;
+
+/* upstream AudioFilterSW::Processor persistent state. */
+typedef struct gas_processor_state {
+	float b0, b1, b2, a1, a2; /* current (interpolating) coefficients; a1/a2 stored negated */
+	float ha1, ha2, hb1, hb2; /* history */
+} gas_processor_state;
+
+/* SpatializerPlaybackData3D (audio_spatializer_3d.h:85-99) + effect-chain histories
+ * (SpatializerPlaybackDataEffect's AudioEffectFilterInstance::filter_process[2][4]). */
+typedef struct gas_voice_state {
+	float prev_mix_volumes[GAS_MAX_CHANNELS_PER_BUS][2];
+	gas_processor_state filter_processors[2 * GAS_MAX_CHANNELS_PER_BUS]; /* index pair*2 + (left?0:1), :887-894 */
+	float effect_history[GAS_MAX_EFFECTS][2][GAS_MAX_FILTER_STAGES][4];  /* [effect][l/r][stage]{ha1,ha2,hb1,hb2} */
+} gas_voice_state;
+
+typedef struct gas_config {
+	int32_t device; /* CUDA ordinal */
+	int32_t max_instances;
+	int32_t max_voices;
+	int32_t max_frames;       /* largest block size (frames) */
+	int32_t max_spatializers; /* gas_spatializer slots */
+	int32_t num_buses;        /* 1..GAS_MAX_BUSES */
+	int32_t speaker_mode;     /* gas_speaker_mode */
+	float mix_rate;           /* AudioServer::get_mix_rate */
+	float global_panning_strength; /* project setting audio/general/3d_panning_strength (audio_spatializer_3d.cpp:633) */
+} gas_config;
+
+typedef struct gas_ctx gas_ctx;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+GAS_API int gas_abi_version(void);
+/* sizeof() of the records above as compiled into the library, so a foreign-language binding can check
+ * its own layout before the first call.  Returns 0 for an unknown id. */
+typedef enum gas_struct_id {
+	GAS_STRUCT_FRAME = 0,
+	GAS_STRUCT_EFFECT = 1,
+	GAS_STRUCT_EFFECT_CHAIN = 2,
+	GAS_STRUCT_SPATIALIZER = 3,
+	GAS_STRUCT_LISTENER = 4,
+	GAS_STRUCT_AREA = 5,
+	GAS_STRUCT_EMITTER = 6,
+	GAS_STRUCT_PARAMS = 7,
+	GAS_STRUCT_VOICE = 8,
+	GAS_STRUCT_PROCESSOR_STATE = 9,
+	GAS_STRUCT_VOICE_STATE = 10,
+	GAS_STRUCT_CONFIG = 11
+} gas_struct_id;
+GAS_API size_t gas_abi_sizeof(int32_t struct_id);
+GAS_API void gas_config_defaults(gas_config *cfg);
+/* Replaces module registration + AudioServer globals the path reads (register_types.cpp:40-60). */
+GAS_API int gas_create(const gas_config *cfg, gas_ctx **out_ctx);
+GAS_API void gas_destroy(gas_ctx *ctx);
+/* Message of the last failing call on ctx (or of the last failing gas_create when ctx == NULL). */
+GAS_API const char *gas_last_error(const gas_ctx *ctx);
+/* AudioServer::get_speaker_mode / get_mix_rate / project setting, changed at run time. */
+GAS_API int gas_set_speaker_mode(gas_ctx *ctx, int32_t speaker_mode);
+GAS_API int gas_set_mix_rate(gas_ctx *ctx, float mix_rate);
+GAS_API int gas_set_global_panning_strength(gas_ctx *ctx, float strength);
+GAS_API int gas_get_channel_count(const gas_ctx *ctx);
+
+/* ---- resources / slots -------------------------------------------------------------------------- */
+/* AudioSpatializer3D defaults (audio_spatializer_3d.h:171-188). */
+GAS_API void gas_spatializer_defaults(gas_spatializer *s);
+/* AudioSpatializer3D setters with their validation (audio_spatializer_3d.cpp:654-765): max_distance>=0,
+ * emission_angle in [0,90], attenuation_model<4, panning_strength>=0, doppler_speed_of_sound>0. */
+GAS_API int gas_spatializer_set(gas_ctx *ctx, int32_t slot, const gas_spatializer *s);
+/* AudioSpatializer::instantiate (audio_spatializer_3d.cpp:645-652): binds instances to a spatializer
+ * slot and resets all per-instance state (parameters, was_further_than_max_distance_last_frame,
+ * AudioServer-side bus details). */
+GAS_API int gas_instance_init(gas_ctx *ctx, int32_t n, const int32_t *instances, const int32_t *spatializers);
+/* First voice of an inactive instance: the proxy playbacks are (re)registered with AudioServer using
+ * get_bus_map(current parameters); previous bus details start empty => fade-in
+ * (audio_spatializer.cpp:75-95; upstream AudioServer::start_playback_stream). */
+GAS_API int gas_instance_start(gas_ctx *ctx, int32_t n, const int32_t *instances);
+/* AudioSpatializerInstance::_manage_playback_state stopping the proxies (audio_spatializer.cpp:484-491). */
+GAS_API int gas_instance_stop(gas_ctx *ctx, int32_t n, const int32_t *instances);
+/* instantiate_playback_data (audio_spatializer_3d.cpp:200-204, audio_spatializer_effect.cpp:79-88): zero state. */
+GAS_API int gas_voice_init(gas_ctx *ctx, int32_t n, const int32_t *voices);
+
+/* ---- gain side (physics thread) ----------------------------------------------------------------- */
+/* Batched AudioSpatializerInstance3D::calculate_spatialization + update_spatializer_parameters
+ * (audio_spatializer_3d.cpp:277-489, audio_spatializer.cpp:258-272): for every emitter, computes the
+ * SpatializerParameters3D of its instance on the GPU, stores them as the instance's current
+ * parameters and, when update_parameters is set, pushes get_bus_map() to the AudioServer-side state
+ * (audio_spatializer.cpp:274-324).  `areas` may be NULL when no emitter references one.
+ * out_params (optional, host, n entries) receives a copy of the computed parameters. */
+GAS_API int gas_gain_compute(gas_ctx *ctx, int32_t n, const gas_emitter *emitters,
+		int32_t n_listeners, const gas_listener *listeners,
+		int32_t n_areas, const gas_area *areas, gas_params *out_params);
+/* Same with device-resident emitters (listeners/areas are small and stay host pointers); asynchronous
+ * on the context's gain stream. */
+GAS_API int gas_gain_compute_device(gas_ctx *ctx, int32_t n, const gas_emitter *d_emitters,
+		int32_t n_listeners, const gas_listener *listeners,
+		int32_t n_areas, const gas_area *areas, gas_params *d_out_params);
+/* Hand-off of parameters computed elsewhere (a custom _calculate_spatialization): the batched
+ * set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272, :558-564).  Validation:
+ * n_bus <= 6 (spatializer_parameters.cpp:35-47 sizes are fixed by the struct). */
+GAS_API int gas_params_set(gas_ctx *ctx, int32_t n, const int32_t *instances, const gas_params *params);
+GAS_API int gas_params_get(gas_ctx *ctx, int32_t n, const int32_t *instances, gas_params *out_params);
+/* Per-instance effect parameters for the next blocks: what a _process_effects override would write
+ * into its AudioEffectFilter resources (audio_spatializer_effect.cpp:39, :90-92). */
+GAS_API int gas_effect_params_set(gas_ctx *ctx, int32_t n, const int32_t *instances, const gas_effect_chain *chains);
+
+/* ---- mix side (audio thread) -------------------------------------------------------------------- */
+/* One mix block for all voices of all instances: batched
+ * AudioSpatializerInstance::_mix_from_playback_list (audio_spatializer.cpp:326-471) calling
+ * process_frames (audio_spatializer_3d.cpp:491-552, audio_spatializer_effect.cpp:33-77) or mix_channel
+ * (audio_spatializer_3d.cpp:554-609) per voice, followed by the AudioServer bus accumulate of the
+ * proxy playbacks (upstream AudioServer::_mix_step_for_channel, fed by audio_spatializer.cpp:93,269).
+ *   voices   n_voices descriptors (host); a voice slot may appear at most once per block.
+ *   src      src_rows x frames AudioFrames (host): the post-lookahead playback buffers
+ *            (audio_spatializer.cpp:367-408), row r used by voices with src_row == r.
+ *   frames   block size, even, <= max_frames.
+ *   bus_out  host, [num_buses][channel_count][frames] AudioFrames, fully overwritten.
+ *   peaks    optional host, n_voices entries: per-voice block peak (max |sample| over pairs, l/r
+ *            separately), valid for voices flagged GAS_VOICE_WANT_PEAK, else {0,0}.
+ * Synchronous: returns after bus_out/peaks are written. */
+GAS_API int gas_mix_block(gas_ctx *ctx, int32_t n_voices, const gas_voice *voices,
+		const gas_frame *src, int32_t src_rows, int32_t frames,
+		gas_frame *bus_out, gas_frame *peaks);
+/* Same with everything device-resident; asynchronous on the context's mix stream.  d_bus_out is
+ * overwritten; d_peaks may be NULL.  src_row_stride in frames (>= frames, even). */
+GAS_API int gas_mix_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices,
+		const gas_frame *d_src, int32_t src_rows, int32_t src_row_stride, int32_t frames,
+		gas_frame *d_bus_out, gas_frame *d_peaks);
+GAS_API int gas_sync(gas_ctx *ctx);
+/* cudaStream_t of the mix / gain streams as void*, for callers that enqueue their own work
+ * (collectives, copies) in order with the mixer. */
+GAS_API void *gas_mix_stream(gas_ctx *ctx);
+GAS_API void *gas_gain_stream(gas_ctx *ctx);
+/* Number of kernels this library has launched on ctx since creation (evidence for bench.py). */
+GAS_API uint64_t gas_kernel_launches(const gas_ctx *ctx);
+
+/* ---- persistent state (checkpoint / re-sharding; no reference analogue) ------------- */
+GAS_API int gas_voice_state_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_voice_state *out);
+GAS_API int gas_voice_state_import(gas_ctx *ctx, int32_t n, const int32_t *voices, const gas_voice_state *in);
+
+/* ---- multi-GPU: voices sharded over ranks, partial bus buffers summed ---------------------------- */
+/* Peer-memory reduce: every rank exports an IPC handle of its partial-bus exchange buffer; rank r
+ * opens the others and the mix epilogue pushes partial sums straight into the root's buffer over
+ * NVLink.  handle_out: 64 bytes (cudaIpcMemHandle_t). */
+GAS_API int gas_comm_export(gas_ctx *ctx, void *handle_out, size_t handle_bytes);
+GAS_API int gas_comm_open(gas_ctx *ctx, int32_t rank, int32_t n_ranks, const void *handles, size_t handle_bytes);
+GAS_API int gas_comm_close(gas_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAS_H */

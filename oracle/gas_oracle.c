@@ -1,0 +1,1354 @@
+/*
+ * gas_oracle.c — CPU oracle (scalar C restatement of the reference hot path).
+ * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED — see gas_oracle.h.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp (no -ffast-math): Godot's release optimisation level
+ * without FMA contraction, so every float operation below rounds where the reference's does on a
+ * baseline x86-64 build.
+ */
+#include "gas_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define CMP_EPSILON 0.00001 /* upstream core/math/math_defs.h (double literal) */
+
+/* ---------------------------------------------------------------------------------------------
+ * upstream Math::* (core/math/math_funcs.h), SURVEY Appendix A
+ * ------------------------------------------------------------------------------------------- */
+float orc_db_to_linear_f(float db) {
+	return expf(db * (float)0.11512925464970228420089957273422);
+}
+double orc_db_to_linear_d(double db) {
+	return exp(db * 0.11512925464970228420089957273422);
+}
+float orc_linear_to_db_f(float lin) {
+	return logf(lin) * (float)8.6858896380650365530225783783321;
+}
+double orc_linear_to_db_d(double lin) {
+	return log(lin) * 8.6858896380650365530225783783321;
+}
+
+/* upstream Vector3 (real_t = float) */
+typedef struct v3 {
+	float x, y, z;
+} v3;
+static inline float v3_dot(v3 a, v3 b) {
+	return a.x * b.x + a.y * b.y + a.z * b.z;
+}
+static inline float v3_length(v3 a) {
+	return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+}
+static inline v3 v3_normalized(v3 a) {
+	float lengthsq = a.x * a.x + a.y * a.y + a.z * a.z;
+	if (lengthsq == 0) {
+		v3 z = { 0, 0, 0 };
+		return z;
+	}
+	float length = sqrtf(lengthsq);
+	v3 r = { a.x / length, a.y / length, a.z / length };
+	return r;
+}
+static inline v3 v3_sub(v3 a, v3 b) {
+	v3 r = { a.x - b.x, a.y - b.y, a.z - b.z };
+	return r;
+}
+static inline v3 v3_scale(v3 a, float s) {
+	v3 r = { a.x * s, a.y * s, a.z * s };
+	return r;
+}
+
+/* upstream Basis (rows[3]) / Transform3D */
+typedef struct xf3 {
+	float m[3][3];
+	v3 o;
+} xf3;
+static v3 xf_col(const xf3 *t, int c) {
+	v3 r = { t->m[0][c], t->m[1][c], t->m[2][c] };
+	return r;
+}
+static void xf_set_col(xf3 *t, int c, v3 v) {
+	t->m[0][c] = v.x;
+	t->m[1][c] = v.y;
+	t->m[2][c] = v.z;
+}
+/* Basis::orthonormalize (Gram-Schmidt) */
+static void xf_orthonormalize(xf3 *t) {
+	v3 x = xf_col(t, 0), y = xf_col(t, 1), z = xf_col(t, 2);
+	x = v3_normalized(x);
+	y = v3_sub(y, v3_scale(x, v3_dot(x, y)));
+	y = v3_normalized(y);
+	z = v3_sub(v3_sub(z, v3_scale(x, v3_dot(x, z))), v3_scale(y, v3_dot(y, z)));
+	z = v3_normalized(z);
+	xf_set_col(t, 0, x);
+	xf_set_col(t, 1, y);
+	xf_set_col(t, 2, z);
+}
+static inline v3 basis_xform(const xf3 *t, v3 v) {
+	v3 r = { t->m[0][0] * v.x + t->m[0][1] * v.y + t->m[0][2] * v.z,
+		t->m[1][0] * v.x + t->m[1][1] * v.y + t->m[1][2] * v.z,
+		t->m[2][0] * v.x + t->m[2][1] * v.y + t->m[2][2] * v.z };
+	return r;
+}
+/* Basis::xform_inv: transposed multiply */
+static inline v3 basis_xform_inv(const xf3 *t, v3 v) {
+	v3 r = { t->m[0][0] * v.x + t->m[1][0] * v.y + t->m[2][0] * v.z,
+		t->m[0][1] * v.x + t->m[1][1] * v.y + t->m[2][1] * v.z,
+		t->m[0][2] * v.x + t->m[1][2] * v.y + t->m[2][2] * v.z };
+	return r;
+}
+/* Transform3D::affine_invert: Basis::invert (cofactors) then origin = basis.xform(-origin) */
+static void xf_affine_invert(xf3 *t) {
+#define COFAC(r1, c1, r2, c2) (t->m[r1][c1] * t->m[r2][c2] - t->m[r1][c2] * t->m[r2][c1])
+	float co[3] = { COFAC(1, 1, 2, 2), COFAC(1, 2, 2, 0), COFAC(1, 0, 2, 1) };
+	float det = t->m[0][0] * co[0] + t->m[0][1] * co[1] + t->m[0][2] * co[2];
+	float s = 1.0f / det;
+	float n[3][3] = {
+		{ co[0] * s, COFAC(0, 2, 2, 1) * s, COFAC(0, 1, 1, 2) * s },
+		{ co[1] * s, COFAC(0, 0, 2, 2) * s, COFAC(0, 2, 1, 0) * s },
+		{ co[2] * s, COFAC(0, 1, 2, 0) * s, COFAC(0, 0, 1, 1) * s },
+	};
+#undef COFAC
+	memcpy(t->m, n, sizeof(n));
+	v3 neg = { -t->o.x, -t->o.y, -t->o.z };
+	t->o = basis_xform(t, neg);
+}
+static inline v3 xf_xform(const xf3 *t, v3 v) {
+	v3 r = basis_xform(t, v);
+	r.x += t->o.x;
+	r.y += t->o.y;
+	r.z += t->o.z;
+	return r;
+}
+static xf3 xf_from_listener(const gas_listener *l) {
+	xf3 t;
+	memcpy(t.m, l->basis, sizeof(t.m));
+	t.o.x = l->origin[0];
+	t.o.y = l->origin[1];
+	t.o.z = l->origin[2];
+	return t;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * SPCAP — audio_spatializer_3d.cpp:47-55 (speaker directions), :903-916, :926-938
+ * ------------------------------------------------------------------------------------------- */
+static void spcap_dirs(v3 d[7]) {
+	static const float raw[7][3] = {
+		{ -1, 0, -1 }, { 1, 0, -1 }, { 0, 0, -1 }, { -1, 0, 1 }, { 1, 0, 1 }, { -1, 0, 0 }, { 1, 0, 0 }
+	};
+	for (int i = 0; i < 7; i++) {
+		v3 v = { raw[i][0], raw[i][1], raw[i][2] };
+		d[i] = v3_normalized(v);
+	}
+}
+
+void orc_spcap_effective_speakers(int speaker_count, float eff[7]) {
+	v3 d[7];
+	spcap_dirs(d);
+	for (int i = 0; i < 7; i++) {
+		eff[i] = 0.0f;
+	}
+	for (int i = 0; i < speaker_count; i++) { /* :911-915 — float += double, narrowed every iteration */
+		for (int j = 0; j < speaker_count; j++) {
+			eff[i] = (float)((double)eff[i] + 0.5 * (1.0 + (double)v3_dot(d[i], d[j])));
+		}
+	}
+}
+
+void orc_spcap_calculate(int speaker_count, const float dir[3], float tightness, float volumes[7]) {
+	v3 d[7];
+	float eff[7];
+	float sq[7];
+	spcap_dirs(d);
+	orc_spcap_effective_speakers(speaker_count, eff);
+	v3 src = { dir[0], dir[1], dir[2] };
+	float sum_squared_gains = 0.0f;
+	for (int i = 0; i < speaker_count; i++) { /* :929-933 */
+		float initial_gain = (float)(0.5 * pow(1.0 + (double)v3_dot(d[i], src), (double)tightness) / (double)eff[i]);
+		sq[i] = initial_gain * initial_gain;
+		sum_squared_gains += sq[i];
+	}
+	for (int i = 0; i < speaker_count; i++) { /* :935-937 */
+		volumes[i] = sqrtf(sq[i] / sum_squared_gains);
+	}
+}
+
+/* audio_spatializer_3d.cpp:57-98 */
+void orc_calc_output_vol_surround(int speaker_mode, const float dir[3], float tightness, float out[4][2]) {
+	int speaker_count = 0;
+	switch (speaker_mode) {
+		case GAS_SPEAKER_MODE_STEREO:
+			speaker_count = 2;
+			break;
+		case GAS_SPEAKER_SURROUND_31:
+			speaker_count = 3;
+			break;
+		case GAS_SPEAKER_SURROUND_51:
+			speaker_count = 5;
+			break;
+		case GAS_SPEAKER_SURROUND_71:
+			speaker_count = 7;
+			break;
+	}
+	float volumes[7] = { 0 };
+	orc_spcap_calculate(speaker_count, dir, tightness, volumes);
+	switch (speaker_mode) {
+		case GAS_SPEAKER_SURROUND_71:
+			out[3][0] = volumes[5];
+			out[3][1] = volumes[6];
+			/* fallthrough */
+		case GAS_SPEAKER_SURROUND_51:
+			out[2][0] = volumes[3];
+			out[2][1] = volumes[4];
+			/* fallthrough */
+		case GAS_SPEAKER_SURROUND_31:
+			out[1][0] = volumes[2];
+			out[1][1] = 1.0f; /* LFE - always full power */
+			/* fallthrough */
+		case GAS_SPEAKER_MODE_STEREO:
+			out[0][0] = volumes[0];
+			out[0][1] = volumes[1];
+			break;
+	}
+}
+
+/* audio_spatializer_3d.cpp:103-110 */
+void orc_calc_output_vol_stereo(const float dir[3], float pan_strength, float out[4][2]) {
+	double flatrad = sqrt((double)(dir[0] * dir[0] + dir[2] * dir[2]));
+	double g = (1.0 - pan_strength) * (1.0 - pan_strength);
+	g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
+	double f = (1.0 - g) / (1.0 + g);
+	double cosx = dir[0] / (flatrad == 0.0 ? 1.0 : flatrad);
+	cosx = cosx < -1.0 ? -1.0 : (cosx > 1.0 ? 1.0 : cosx);
+	double fcosx = cosx * f;
+	out[0][0] = (float)sqrt((-fcosx + 1.0) / 2.0);
+	out[0][1] = (float)sqrt((fcosx + 1.0) / 2.0);
+}
+
+/* audio_spatializer_3d.cpp:112-121 */
+void orc_calc_output_vol(int speaker_mode, float global_panning, float panning_strength, const float dir[3], float out[4][2]) {
+	if (speaker_mode == GAS_SPEAKER_MODE_STEREO) {
+		orc_calc_output_vol_stereo(dir, global_panning * panning_strength, out);
+	} else {
+		float tightness = global_panning * 2.0f;
+		tightness *= panning_strength;
+		orc_calc_output_vol_surround(speaker_mode, dir, tightness, out);
+	}
+}
+
+/* audio_spatializer_3d.cpp:123-151 */
+float orc_get_attenuation_db(const gas_spatializer *s, float volume_db, float max_db, float p_distance) {
+	float att = 0;
+	switch (s->attenuation_model) {
+		case GAS_ATTENUATION_INVERSE_DISTANCE: {
+			att = (float)orc_linear_to_db_d(1.0 / ((p_distance / s->unit_size) + CMP_EPSILON));
+		} break;
+		case GAS_ATTENUATION_INVERSE_SQUARE_DISTANCE: {
+			float d = (p_distance / s->unit_size);
+			d *= d;
+			att = (float)orc_linear_to_db_d(1.0 / (d + CMP_EPSILON));
+		} break;
+		case GAS_ATTENUATION_LOGARITHMIC: {
+			att = (float)(-20 * log(p_distance / s->unit_size + CMP_EPSILON));
+		} break;
+		case GAS_ATTENUATION_DISABLED:
+			break;
+		default:
+			break;
+	}
+	att += volume_db;
+	if (att > max_db) {
+		att = max_db;
+	}
+	return att;
+}
+
+static inline float lerpf(float from, float to, float w) { /* upstream Math::lerp */
+	return from + (to - from) * w;
+}
+
+/* audio_spatializer_3d.cpp:154-197 */
+static void calc_reverb_vol(const gas_config *cfg, const gas_spatializer *s, const gas_emitter *e, const gas_area *area,
+		v3 listener_area_pos, float direct[4][2], float reverb[4][2]) {
+	memset(reverb, 0, sizeof(float) * 8);
+	float uniformity = area->reverb_uniformity;
+	float area_send = area->reverb_amount;
+	int chan_count = cfg->speaker_mode + 1;
+	if (uniformity > 0.0) {
+		float distance = v3_length(listener_area_pos);
+		float attenuation = orc_db_to_linear_f(orc_get_attenuation_db(s, e->volume_db, e->max_db, distance));
+		const float center_val[4] = { 0.5f, 0.25f, 0.16666f, 0.125f };
+		float cv = center_val[chan_count - 1];
+		if (attenuation < 1.0) {
+			v3 rev_pos = listener_area_pos;
+			rev_pos.y = 0;
+			rev_pos = v3_normalized(rev_pos);
+			float rp[3] = { rev_pos.x, rev_pos.y, rev_pos.z };
+			orc_calc_output_vol(cfg->speaker_mode, cfg->global_panning_strength, s->panning_strength, rp, reverb);
+			for (int i = 0; i < chan_count; i++) {
+				reverb[i][0] = lerpf(reverb[i][0], cv, attenuation);
+				reverb[i][1] = lerpf(reverb[i][1], cv, attenuation);
+			}
+		} else {
+			for (int i = 0; i < chan_count; i++) {
+				reverb[i][0] = cv;
+				reverb[i][1] = cv;
+			}
+		}
+		for (int i = 0; i < chan_count; i++) {
+			reverb[i][0] = lerpf(direct[i][0], reverb[i][0] * attenuation, uniformity);
+			reverb[i][1] = lerpf(direct[i][1], reverb[i][1] * attenuation, uniformity);
+			reverb[i][0] *= area_send;
+			reverb[i][1] *= area_send;
+		}
+	} else {
+		for (int i = 0; i < 4; i++) {
+			reverb[i][0] = direct[i][0] * area_send;
+			reverb[i][1] = direct[i][1] * area_send;
+		}
+	}
+}
+
+/* SpatializerParameters::add_bus_volume: Dictionary assignment keeps the first insertion position */
+static void params_add_bus_volume(gas_params *p, int bus, float vol[4][2]) {
+	for (int i = 0; i < p->n_bus; i++) {
+		if (p->bus[i] == bus) {
+			memcpy(p->bus_volumes[i], vol, sizeof(float) * 8);
+			return;
+		}
+	}
+	if (p->n_bus >= GAS_MAX_BUSES_PER_PLAYBACK) {
+		return;
+	}
+	p->bus[p->n_bus] = bus;
+	memcpy(p->bus_volumes[p->n_bus], vol, sizeof(float) * 8);
+	p->n_bus++;
+}
+
+static int resolve_bus(const gas_config *cfg, int bus) { /* audio_stream_player_spatial.cpp:405-413 */
+	return (bus >= 0 && bus < cfg->num_buses) ? bus : 0;
+}
+
+/* AudioSpatializerInstance3D::calculate_spatialization, audio_spatializer_3d.cpp:277-489, minus the
+ * scene / physics look-ups whose results arrive in gas_emitter / gas_listener / gas_area. */
+void orc_calculate_spatialization(const gas_config *cfg, const gas_spatializer *s, const gas_emitter *e,
+		int n_listeners, const gas_listener *listeners, const gas_area *area, int *was_further, gas_params *out) {
+	gas_params prm;
+	memset(&prm, 0, sizeof(prm));
+	prm.pitch_scale = 1.0f;                      /* spatializer_parameters.h:48 */
+	prm.linear_attenuation = 0.0f;               /* audio_spatializer_3d.h:67 */
+	prm.attenuation_filter_cutoff_hz = 5000.0f;  /* audio_spatializer_3d.h:68 */
+
+	v3 global_pos = { e->origin[0], e->origin[1], e->origin[2] };
+	v3 linear_velocity = { 0, 0, 0 };
+	if (s->doppler_tracking != GAS_DOPPLER_TRACKING_DISABLED) { /* :297-299 */
+		linear_velocity.x = e->velocity[0];
+		linear_velocity.y = e->velocity[1];
+		linear_velocity.z = e->velocity[2];
+	}
+	float log_pitch_scale = 0.0f;
+	float log_pitch_weight = 0.0f;
+	float output_volume[4][2] = { { 0 } };
+	float reverb_volume[4][2] = { { 0 } };
+	float tmp_volume[4][2];
+	float tmp_reverb[4][2];
+	int has_any_listener_in_range = 0;
+	const int area_reverb_uniform = area && area->use_reverb && area->reverb_uniformity > 0;
+
+	for (int li = 0; li < n_listeners; li++) { /* :323 */
+		const gas_listener *L = &listeners[li];
+		xf3 lt = xf_from_listener(L);
+		xf3 inv = lt;
+		xf_orthonormalize(&inv);
+		xf_affine_invert(&inv);
+		const v3 local_pos = xf_xform(&inv, global_pos); /* :342 */
+		const float dist = v3_length(local_pos);        /* :344 */
+
+		v3 listener_area_pos = { 0, 0, 0 };
+		if (area_reverb_uniform) { /* :350-353 — NOT orthonormalized */
+			v3 area_sound_pos = { area->closest_point[li][0], area->closest_point[li][1], area->closest_point[li][2] };
+			xf3 inv2 = lt;
+			xf_affine_invert(&inv2);
+			listener_area_pos = xf_xform(&inv2, area_sound_pos);
+		}
+
+		float multiplier = orc_db_to_linear_f(orc_get_attenuation_db(s, e->volume_db, e->max_db, dist)); /* :359 */
+		if (s->max_distance > 0) { /* :361-373 */
+			float total_max = s->max_distance;
+			if (area_reverb_uniform) {
+				float lap = v3_length(listener_area_pos);
+				total_max = total_max > lap ? total_max : lap;
+			}
+			if (dist > total_max || total_max > s->max_distance) {
+				continue;
+			}
+			double m = 1.0 - (dist / s->max_distance);
+			m = 0 > m ? 0 : m;
+			multiplier = (float)((double)multiplier * m);
+		}
+		has_any_listener_in_range = 1;
+
+		double mm = 1.0 < (double)multiplier ? 1.0 : (double)multiplier;
+		float db_att = (float)((1.0 - mm) * (double)s->attenuation_filter_db); /* :376 */
+
+		if (s->emission_angle_enabled) { /* :378-385 */
+			v3 lo = { L->origin[0], L->origin[1], L->origin[2] };
+			v3 listenertopos = v3_sub(global_pos, lo);
+			v3 bz = { e->basis_z[0], e->basis_z[1], e->basis_z[2] };
+			float c = v3_dot(v3_normalized(listenertopos), v3_normalized(bz));
+			float ac = c < -1.0f ? (float)3.14159265358979323846 : (c > 1.0f ? 0.0f : acosf(c)); /* upstream Math::acos clamps */
+			float angle = ac * (float)(180.0 / 3.14159265358979323846);
+			if (angle > s->emission_angle) {
+				db_att -= -s->emission_angle_filter_attenuation_db;
+			}
+		}
+		prm.linear_attenuation = orc_db_to_linear_f(db_att);                  /* :387 — last listener wins */
+		prm.attenuation_filter_cutoff_hz = s->attenuation_filter_cutoff_hz; /* :388 */
+
+		memset(tmp_volume, 0, sizeof(tmp_volume)); /* :390 */
+		float lp[3] = { local_pos.x, local_pos.y, local_pos.z };
+		orc_calc_output_vol(cfg->speaker_mode, cfg->global_panning_strength, s->panning_strength, lp, tmp_volume); /* :391 — NOT normalised (Q1) */
+		for (int k = 0; k < 4; k++) { /* :393-396 */
+			tmp_volume[k][0] = multiplier * tmp_volume[k][0];
+			tmp_volume[k][1] = multiplier * tmp_volume[k][1];
+			output_volume[k][0] = output_volume[k][0] > tmp_volume[k][0] ? output_volume[k][0] : tmp_volume[k][0];
+			output_volume[k][1] = output_volume[k][1] > tmp_volume[k][1] ? output_volume[k][1] : tmp_volume[k][1];
+		}
+		if (area && area->use_reverb) { /* :399-402 */
+			calc_reverb_vol(cfg, s, e, area, listener_area_pos, tmp_volume, tmp_reverb);
+			for (int k = 0; k < 4; k++) {
+				reverb_volume[k][0] = reverb_volume[k][0] > tmp_reverb[k][0] ? reverb_volume[k][0] : tmp_reverb[k][0];
+				reverb_volume[k][1] = reverb_volume[k][1] > tmp_reverb[k][1] ? reverb_volume[k][1] : tmp_reverb[k][1];
+			}
+		}
+		if (s->doppler_tracking != GAS_DOPPLER_TRACKING_DISABLED) { /* :405-427 */
+			v3 lv = { L->velocity[0], L->velocity[1], L->velocity[2] };
+			xf3 on = lt;
+			xf_orthonormalize(&on);
+			v3 local_velocity = basis_xform_inv(&on, v3_sub(linear_velocity, lv));
+			if (!(local_velocity.x == 0 && local_velocity.y == 0 && local_velocity.z == 0)) {
+				float approaching = v3_dot(v3_normalized(local_pos), v3_normalized(local_velocity));
+				float velocity = v3_length(local_velocity);
+				float dps = e->pitch_scale * s->doppler_speed_of_sound / (s->doppler_speed_of_sound + velocity * approaching);
+				dps = (double)dps < (1 / 8.0) ? (float)(1 / 8.0) : ((double)dps > 8.0 ? 8.0f : dps);
+				float weight = 0.0f; /* _get_max_volume, :268-275 */
+				for (int k = 0; k < 4; k++) {
+					weight = weight > tmp_volume[k][0] ? weight : tmp_volume[k][0];
+					weight = weight > tmp_volume[k][1] ? weight : tmp_volume[k][1];
+				}
+				log_pitch_scale += weight * log2f(dps);
+				log_pitch_weight += weight;
+			}
+		}
+	}
+
+	if (log_pitch_weight > 0) { /* :430-434 */
+		prm.pitch_scale = powf(2.0f, log_pitch_scale / log_pitch_weight);
+	} else {
+		prm.pitch_scale = e->pitch_scale;
+	}
+
+	if (has_any_listener_in_range) { /* :437-461 */
+		if (area) {
+			if (area->override_bus) {
+				params_add_bus_volume(&prm, resolve_bus(cfg, area->bus), output_volume);
+			} else {
+				params_add_bus_volume(&prm, resolve_bus(cfg, e->bus), output_volume);
+			}
+			if (area->use_reverb) {
+				params_add_bus_volume(&prm, resolve_bus(cfg, area->reverb_bus), reverb_volume);
+			}
+		} else {
+			params_add_bus_volume(&prm, resolve_bus(cfg, e->bus), output_volume);
+		}
+	}
+	memcpy(prm.mix_volumes, output_volume, sizeof(output_volume)); /* :463 */
+
+	const int skip_setting_volumes = !has_any_listener_in_range && *was_further; /* :466 */
+	*was_further = !has_any_listener_in_range;                                  /* :467 */
+	if (!skip_setting_volumes) {
+		prm.update_parameters = 1; /* :471 */
+	}
+	*out = prm;
+}
+
+/* AudioSpatializerInstance::get_bus_map, audio_spatializer.cpp:274-324 */
+int orc_get_bus_map(const gas_params *p, int mix_channels, int channel, int out_bus[6], float out_vol[6][4][2]) {
+	int idx = 0;
+	if (channel < 0 || channel >= GAS_MAX_CHANNELS_PER_BUS) {
+		return 0;
+	}
+	for (int k = 0; k < p->n_bus; k++) {
+		if (idx >= GAS_MAX_BUSES_PER_PLAYBACK) {
+			break;
+		}
+		out_bus[idx] = p->bus[k];
+		for (int c = 0; c < GAS_MAX_CHANNELS_PER_BUS; c++) {
+			if (mix_channels) {
+				float left = 0.0f, right = 0.0f;
+				if (c == channel) {
+					if (p->mix_volumes[c][0] > 0.0) {
+						left = p->bus_volumes[k][c][0] / p->mix_volumes[c][0];
+					}
+					if (p->mix_volumes[c][1] > 0.0) {
+						right = p->bus_volumes[k][c][1] / p->mix_volumes[c][1];
+					}
+				}
+				out_vol[idx][c][0] = left;
+				out_vol[idx][c][1] = right;
+			} else {
+				out_vol[idx][c][0] = p->mix_volumes[c][0]; /* Q15: mix volumes to every bus */
+				out_vol[idx][c][1] = p->mix_volumes[c][1];
+			}
+		}
+		idx++;
+	}
+	return idx;
+}
+
+/* upstream AudioFilterSW::prepare_coefficients: all arithmetic in double, each
+ * coefficient narrowed to float when stored and again after the division by a0. */
+void orc_filter_prepare_coefficients(int mode, float cutoff, float resonance, float gain, int stages, float sampling_rate, float out[5]) {
+	int sr_limit = (int)((sampling_rate / 2) + 512);
+	double final_cutoff = (cutoff > sr_limit) ? sr_limit : cutoff;
+	if (final_cutoff < 1) {
+		final_cutoff = 1;
+	}
+	const double TAU = 6.2831853071795864769252867666;
+	double omega = TAU * final_cutoff / sampling_rate;
+	double sin_v = sin(omega);
+	double cos_v = cos(omega);
+	double Q = resonance;
+	if (Q <= 0.0) {
+		Q = 0.0001;
+	}
+	if (mode == GAS_FILTER_BANDPASS) {
+		Q *= 2.0;
+	} else if (mode == GAS_FILTER_PEAK) {
+		Q *= 3.0;
+	}
+	double tmpgain = gain;
+	if (tmpgain < 0.001) {
+		tmpgain = 0.001;
+	}
+	if (stages > 1) {
+		Q = (Q > 1.0 ? pow(Q, 1.0 / stages) : Q);
+		tmpgain = pow(tmpgain, 1.0 / (stages + 1));
+	}
+	double alpha = sin_v / (2 * Q);
+	double a0 = 1.0 + alpha;
+	float b0 = 0, b1 = 0, b2 = 0, a1 = 0, a2 = 0;
+	switch (mode) {
+		case GAS_FILTER_LOWPASS: {
+			b0 = (float)((1.0 - cos_v) / 2.0);
+			b1 = (float)(1.0 - cos_v);
+			b2 = (float)((1.0 - cos_v) / 2.0);
+			a1 = (float)(-2.0 * cos_v);
+			a2 = (float)(1.0 - alpha);
+		} break;
+		case GAS_FILTER_HIGHPASS: {
+			b0 = (float)((1.0 + cos_v) / 2.0);
+			b1 = (float)(-(1.0 + cos_v));
+			b2 = (float)((1.0 + cos_v) / 2.0);
+			a1 = (float)(-2.0 * cos_v);
+			a2 = (float)(1.0 - alpha);
+		} break;
+		case GAS_FILTER_BANDPASS: {
+			b0 = (float)(alpha * sqrt(Q + 1));
+			b1 = 0.0f;
+			b2 = (float)(-alpha * sqrt(Q + 1));
+			a1 = (float)(-2.0 * cos_v);
+			a2 = (float)(1.0 - alpha);
+		} break;
+		case GAS_FILTER_NOTCH: {
+			b0 = 1.0f;
+			b1 = (float)(-2.0 * cos_v);
+			b2 = 1.0f;
+			a1 = (float)(-2.0 * cos_v);
+			a2 = (float)(1.0 - alpha);
+		} break;
+		case GAS_FILTER_PEAK: {
+			b0 = (float)(1.0 + alpha * tmpgain);
+			b1 = (float)(-2.0 * cos_v);
+			b2 = (float)(1.0 - alpha * tmpgain);
+			a1 = (float)(-2 * cos_v);
+			a2 = (float)(1 - alpha / tmpgain);
+		} break;
+		case GAS_FILTER_BANDLIMIT: {
+			double hicutoff = resonance;
+			double centercutoff = (cutoff + resonance) / 2.0;
+			double bandwidth = (log(centercutoff) - log(hicutoff)) / log((double)2);
+			omega = TAU * centercutoff / sampling_rate;
+			alpha = sin(omega) * sinh(log((double)2) / 2 * bandwidth * omega / sin(omega));
+			a0 = 1 + alpha;
+			b0 = (float)alpha;
+			b1 = 0;
+			b2 = (float)-alpha;
+			a1 = (float)(-2 * cos(omega));
+			a2 = (float)(1 - alpha);
+		} break;
+		case GAS_FILTER_LOWSHELF: {
+			double tmpq = sqrt(Q);
+			if (tmpq <= 0) {
+				tmpq = 0.001;
+			}
+			double beta = sqrt(tmpgain) / tmpq;
+			a0 = (tmpgain + 1.0) + (tmpgain - 1.0) * cos_v + beta * sin_v;
+			b0 = (float)(tmpgain * ((tmpgain + 1.0) - (tmpgain - 1.0) * cos_v + beta * sin_v));
+			b1 = (float)(2.0 * tmpgain * ((tmpgain - 1.0) - (tmpgain + 1.0) * cos_v));
+			b2 = (float)(tmpgain * ((tmpgain + 1.0) - (tmpgain - 1.0) * cos_v - beta * sin_v));
+			a1 = (float)(-2.0 * ((tmpgain - 1.0) + (tmpgain + 1.0) * cos_v));
+			a2 = (float)((tmpgain + 1.0) + (tmpgain - 1.0) * cos_v - beta * sin_v);
+		} break;
+		case GAS_FILTER_HIGHSHELF:
+		default: {
+			double tmpq = sqrt(Q);
+			if (tmpq <= 0) {
+				tmpq = 0.001;
+			}
+			double beta = sqrt(tmpgain) / tmpq;
+			a0 = (tmpgain + 1.0) - (tmpgain - 1.0) * cos_v + beta * sin_v;
+			b0 = (float)(tmpgain * ((tmpgain + 1.0) + (tmpgain - 1.0) * cos_v + beta * sin_v));
+			b1 = (float)(-2.0 * tmpgain * ((tmpgain - 1.0) + (tmpgain + 1.0) * cos_v));
+			b2 = (float)(tmpgain * ((tmpgain + 1.0) + (tmpgain - 1.0) * cos_v - beta * sin_v));
+			a1 = (float)(2.0 * ((tmpgain - 1.0) - (tmpgain + 1.0) * cos_v));
+			a2 = (float)((tmpgain + 1.0) - (tmpgain - 1.0) * cos_v - beta * sin_v);
+		} break;
+	}
+	out[0] = (float)((double)b0 / a0);
+	out[1] = (float)((double)b1 / a0);
+	out[2] = (float)((double)b2 / a0);
+	out[3] = (float)((double)a1 / (0.0 - a0));
+	out[4] = (float)((double)a2 / (0.0 - a0));
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * per-voice mix functions, float32 (reference arithmetic) and float64 (shadow)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct proc64 {
+	double b0, b1, b2, a1, a2, ha1, ha2, hb1, hb2;
+} proc64;
+typedef struct vstate64 {
+	double prev_mix_volumes[GAS_MAX_CHANNELS_PER_BUS][2];
+	proc64 filter_processors[2 * GAS_MAX_CHANNELS_PER_BUS];
+	double effect_history[GAS_MAX_EFFECTS][2][GAS_MAX_FILTER_STAGES][4];
+} vstate64;
+typedef struct frame64 {
+	double l, r;
+} frame64;
+
+#define REAL float
+#define SUF(n) n##_f32
+#define PROC gas_processor_state
+#define VSTATE gas_voice_state
+#define FRAME gas_frame
+#include "gas_oracle_mix.inc"
+#undef REAL
+#undef SUF
+#undef PROC
+#undef VSTATE
+#undef FRAME
+
+#define REAL double
+#define SUF(n) n##_f64
+#define PROC proc64
+#define VSTATE vstate64
+#define FRAME frame64
+#include "gas_oracle_mix.inc"
+#undef REAL
+#undef SUF
+#undef PROC
+#undef VSTATE
+#undef FRAME
+
+void orc_process_frames_3d(const gas_params *p, gas_voice_state *st, float mix_rate, gas_frame *out, const gas_frame *src, int frames) {
+	process_frames_3d_f32(p, st, mix_rate, out, src, frames);
+}
+void orc_mix_channel_3d(const gas_params *p, gas_voice_state *st, float mix_rate, int channel, gas_frame *out, const gas_frame *src, int frames) {
+	mix_channel_3d_f32(p, st, mix_rate, channel, out, src, frames);
+}
+void orc_process_frames_effect(const gas_effect_chain *chain, gas_voice_state *st, float mix_rate, gas_frame *out, const gas_frame *src, int frames) {
+	process_frames_effect_f32(chain, st, mix_rate, out, src, frames);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * world
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bus_details { /* upstream AudioStreamPlaybackBusDetails, shared by an instance's proxies */
+	int n;
+	int bus[GAS_MAX_BUSES_PER_PLAYBACK];
+	float vol[GAS_MAX_BUSES_PER_PLAYBACK][GAS_MAX_CHANNELS_PER_BUS][2];
+} bus_details;
+
+typedef struct orc_instance {
+	int spatializer;
+	gas_params params;
+	int was_further;
+	int active; /* playback_active: proxies registered with AudioServer */
+	bus_details cur, prev;
+	gas_effect_chain fx;
+} orc_instance;
+
+struct orc_world {
+	gas_config cfg;
+	gas_spatializer *spat;
+	orc_instance *inst;
+	gas_voice_state *vs;
+	vstate64 *vs64;
+	double last_mix_s, last_gain_s;
+};
+
+static double now_s(void) {
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void spat_defaults(gas_spatializer *s) { /* audio_spatializer_3d.h:171-188 */
+	memset(s, 0, sizeof(*s));
+	s->kind = GAS_SPATIALIZER_3D;
+	s->attenuation_model = GAS_ATTENUATION_INVERSE_DISTANCE;
+	s->unit_size = 10.0f;
+	s->max_distance = 0.0f;
+	s->panning_strength = 1.0f;
+	s->area_mask = 1;
+	s->emission_angle_enabled = 0;
+	s->emission_angle = 45.0f;
+	s->emission_angle_filter_attenuation_db = -12.0f;
+	s->attenuation_filter_cutoff_hz = 5000.0f;
+	s->attenuation_filter_db = -24.0f;
+	s->doppler_tracking = GAS_DOPPLER_TRACKING_DISABLED;
+	s->doppler_speed_of_sound = 343.0f;
+	s->mix_channel_mode = 0;
+	s->effect_gain_binding = -1;
+}
+
+static void params_defaults(gas_params *p) {
+	memset(p, 0, sizeof(*p));
+	p->pitch_scale = 1.0f;
+	p->attenuation_filter_cutoff_hz = 5000.0f;
+}
+
+orc_world *orc_create(const gas_config *cfg) {
+	if (!cfg || cfg->max_instances <= 0 || cfg->max_voices <= 0 || cfg->max_spatializers <= 0 ||
+			cfg->num_buses < 1 || cfg->num_buses > GAS_MAX_BUSES || cfg->speaker_mode < 0 || cfg->speaker_mode > 3) {
+		return NULL;
+	}
+	orc_world *w = (orc_world *)calloc(1, sizeof(orc_world));
+	w->cfg = *cfg;
+	w->spat = (gas_spatializer *)calloc(cfg->max_spatializers, sizeof(gas_spatializer));
+	w->inst = (orc_instance *)calloc(cfg->max_instances, sizeof(orc_instance));
+	w->vs = (gas_voice_state *)calloc(cfg->max_voices, sizeof(gas_voice_state));
+	w->vs64 = (vstate64 *)calloc(cfg->max_voices, sizeof(vstate64));
+	for (int i = 0; i < cfg->max_spatializers; i++) {
+		spat_defaults(&w->spat[i]);
+	}
+	for (int i = 0; i < cfg->max_instances; i++) {
+		params_defaults(&w->inst[i].params);
+	}
+	return w;
+}
+
+void orc_destroy(orc_world *w) {
+	if (!w) {
+		return;
+	}
+	free(w->spat);
+	free(w->inst);
+	free(w->vs);
+	free(w->vs64);
+	free(w);
+}
+
+int orc_set_speaker_mode(orc_world *w, int mode) {
+	if (mode < 0 || mode > 3) {
+		return GAS_ERR_INVALID;
+	}
+	w->cfg.speaker_mode = mode;
+	return GAS_OK;
+}
+int orc_set_mix_rate(orc_world *w, float hz) {
+	if (!(hz > 0)) {
+		return GAS_ERR_INVALID;
+	}
+	w->cfg.mix_rate = hz;
+	return GAS_OK;
+}
+int orc_set_global_panning_strength(orc_world *w, float s) {
+	w->cfg.global_panning_strength = s;
+	return GAS_OK;
+}
+
+static int spat_valid(const gas_spatializer *s) { /* audio_spatializer_3d.cpp:670-672,695-697,728-730,737-739,758-760 */
+	if (s->kind != GAS_SPATIALIZER_3D && s->kind != GAS_SPATIALIZER_EFFECT) {
+		return 0;
+	}
+	if (s->max_distance < 0.0) {
+		return 0;
+	}
+	if (s->emission_angle < 0 || s->emission_angle > 90) {
+		return 0;
+	}
+	if (s->attenuation_model < 0 || s->attenuation_model >= 4) {
+		return 0;
+	}
+	if (s->panning_strength < 0) {
+		return 0;
+	}
+	if (s->doppler_speed_of_sound <= 0) {
+		return 0;
+	}
+	if (s->chain.n_effects < 0 || s->chain.n_effects > GAS_MAX_EFFECTS) {
+		return 0;
+	}
+	return 1;
+}
+
+int orc_spatializer_set(orc_world *w, int slot, const gas_spatializer *s) {
+	if (slot < 0 || slot >= w->cfg.max_spatializers || !s || !spat_valid(s)) {
+		return GAS_ERR_INVALID;
+	}
+	w->spat[slot] = *s;
+	return GAS_OK;
+}
+
+static int inst_mix_channels(const orc_world *w, const orc_instance *q) {
+	const gas_spatializer *s = &w->spat[q->spatializer];
+	return s->kind == GAS_SPATIALIZER_3D && s->mix_channel_mode;
+}
+
+/* get_bus_map for every proxy channel folded into one table: entry [bus][c] is what proxy c (Mode B)
+ * or the single proxy (Mode A) sends to pair c of that bus (audio_spatializer.cpp:266-270, :295-319). */
+static void inst_push_bus_map(const orc_world *w, orc_instance *q) {
+	int mc = inst_mix_channels(w, q);
+	bus_details d;
+	memset(&d, 0, sizeof(d));
+	if (mc) {
+		for (int c = 0; c < GAS_MAX_CHANNELS_PER_BUS; c++) {
+			int bus[6];
+			float vol[6][4][2];
+			int n = orc_get_bus_map(&q->params, 1, c, bus, vol);
+			d.n = n;
+			for (int k = 0; k < n; k++) {
+				d.bus[k] = bus[k];
+				d.vol[k][c][0] = vol[k][c][0];
+				d.vol[k][c][1] = vol[k][c][1];
+			}
+		}
+	} else {
+		int bus[6];
+		float vol[6][4][2];
+		int n = orc_get_bus_map(&q->params, 0, 0, bus, vol);
+		d.n = n;
+		for (int k = 0; k < n; k++) {
+			d.bus[k] = bus[k];
+			memcpy(d.vol[k], vol[k], sizeof(float) * 8);
+		}
+	}
+	q->cur = d;
+}
+
+int orc_instance_init(orc_world *w, int n, const int32_t *instances, const int32_t *spatializers) {
+	for (int i = 0; i < n; i++) {
+		if (instances[i] < 0 || instances[i] >= w->cfg.max_instances || spatializers[i] < 0 || spatializers[i] >= w->cfg.max_spatializers) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		orc_instance *q = &w->inst[instances[i]];
+		memset(q, 0, sizeof(*q));
+		q->spatializer = spatializers[i];
+		params_defaults(&q->params);
+		q->fx = w->spat[q->spatializer].chain;
+	}
+	return GAS_OK;
+}
+
+int orc_instance_start(orc_world *w, int n, const int32_t *instances) {
+	for (int i = 0; i < n; i++) {
+		if (instances[i] < 0 || instances[i] >= w->cfg.max_instances) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		orc_instance *q = &w->inst[instances[i]];
+		q->active = 1;
+		memset(&q->prev, 0, sizeof(q->prev));
+		inst_push_bus_map(w, q);
+	}
+	return GAS_OK;
+}
+
+int orc_instance_stop(orc_world *w, int n, const int32_t *instances) {
+	for (int i = 0; i < n; i++) {
+		if (instances[i] < 0 || instances[i] >= w->cfg.max_instances) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		w->inst[instances[i]].active = 0;
+	}
+	return GAS_OK;
+}
+
+int orc_voice_init(orc_world *w, int n, const int32_t *voices) {
+	for (int i = 0; i < n; i++) {
+		if (voices[i] < 0 || voices[i] >= w->cfg.max_voices) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		memset(&w->vs[voices[i]], 0, sizeof(gas_voice_state));
+		memset(&w->vs64[voices[i]], 0, sizeof(vstate64));
+	}
+	return GAS_OK;
+}
+
+static void inst_set_params(orc_world *w, orc_instance *q, const gas_params *p) {
+	q->params = *p; /* set_spatializer_parameters, audio_spatializer.cpp:263 */
+	if (p->update_parameters && q->active) { /* :265-271 (spatial_playbacks is empty while inactive) */
+		inst_push_bus_map(w, q);
+	}
+}
+
+int orc_gain_compute(orc_world *w, int n, const gas_emitter *emitters, int n_listeners, const gas_listener *listeners,
+		int n_areas, const gas_area *areas, gas_params *out_params) {
+	if (n < 0 || n_listeners < 0 || n_listeners > GAS_MAX_LISTENERS) {
+		return GAS_ERR_INVALID;
+	}
+	for (int i = 0; i < n; i++) {
+		const gas_emitter *e = &emitters[i];
+		if (e->instance < 0 || e->instance >= w->cfg.max_instances || e->spatializer < 0 || e->spatializer >= w->cfg.max_spatializers ||
+				e->area >= n_areas) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	double t0 = now_s();
+	for (int i = 0; i < n; i++) {
+		const gas_emitter *e = &emitters[i];
+		orc_instance *q = &w->inst[e->instance];
+		gas_params p;
+		orc_calculate_spatialization(&w->cfg, &w->spat[e->spatializer], e, n_listeners, listeners,
+				e->area >= 0 ? &areas[e->area] : NULL, &q->was_further, &p);
+		inst_set_params(w, q, &p);
+		if (out_params) {
+			out_params[i] = p;
+		}
+	}
+	w->last_gain_s = now_s() - t0;
+	return GAS_OK;
+}
+
+int orc_params_set(orc_world *w, int n, const int32_t *instances, const gas_params *params) {
+	for (int i = 0; i < n; i++) {
+		if (instances[i] < 0 || instances[i] >= w->cfg.max_instances || params[i].n_bus < 0 || params[i].n_bus > GAS_MAX_BUSES_PER_PLAYBACK) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		gas_params p = params[i];
+		for (int k = 0; k < p.n_bus; k++) {
+			p.bus[k] = resolve_bus(&w->cfg, p.bus[k]);
+		}
+		inst_set_params(w, &w->inst[instances[i]], &p);
+	}
+	return GAS_OK;
+}
+
+int orc_params_get(orc_world *w, int n, const int32_t *instances, gas_params *out) {
+	for (int i = 0; i < n; i++) {
+		if (instances[i] < 0 || instances[i] >= w->cfg.max_instances) {
+			return GAS_ERR_INVALID;
+		}
+		out[i] = w->inst[instances[i]].params;
+	}
+	return GAS_OK;
+}
+
+int orc_effect_params_set(orc_world *w, int n, const int32_t *instances, const gas_effect_chain *chains) {
+	for (int i = 0; i < n; i++) {
+		if (instances[i] < 0 || instances[i] >= w->cfg.max_instances || chains[i].n_effects < 0 || chains[i].n_effects > GAS_MAX_EFFECTS) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		w->inst[instances[i]].fx = chains[i];
+	}
+	return GAS_OK;
+}
+
+/* One instance: AudioSpatializerInstance::_mix_from_playback_list (audio_spatializer.cpp:326-471) over
+ * the voices idx[0..nv) followed by the AudioServer step of its proxies into `bus` (and `bus64`). */
+typedef struct scratch {
+	gas_frame *zero, *process, *temp, *mix[GAS_MAX_CHANNELS_PER_BUS];
+	frame64 *src64, *process64, *temp64, *mix64[GAS_MAX_CHANNELS_PER_BUS];
+} scratch;
+
+static void scratch_alloc(scratch *s, int frames, int want64) {
+	memset(s, 0, sizeof(*s));
+	s->zero = (gas_frame *)calloc(frames, sizeof(gas_frame));
+	s->process = (gas_frame *)calloc(frames, sizeof(gas_frame));
+	s->temp = (gas_frame *)calloc(frames, sizeof(gas_frame));
+	for (int c = 0; c < GAS_MAX_CHANNELS_PER_BUS; c++) {
+		s->mix[c] = (gas_frame *)calloc(frames, sizeof(gas_frame));
+	}
+	if (want64) {
+		s->src64 = (frame64 *)calloc(frames, sizeof(frame64));
+		s->process64 = (frame64 *)calloc(frames, sizeof(frame64));
+		s->temp64 = (frame64 *)calloc(frames, sizeof(frame64));
+		for (int c = 0; c < GAS_MAX_CHANNELS_PER_BUS; c++) {
+			s->mix64[c] = (frame64 *)calloc(frames, sizeof(frame64));
+		}
+	}
+}
+static void scratch_free(scratch *s) {
+	free(s->zero);
+	free(s->process);
+	free(s->temp);
+	free(s->src64);
+	free(s->process64);
+	free(s->temp64);
+	for (int c = 0; c < GAS_MAX_CHANNELS_PER_BUS; c++) {
+		free(s->mix[c]);
+		free(s->mix64[c]);
+	}
+}
+
+static int details_find(const bus_details *d, int bus) {
+	for (int k = 0; k < d->n; k++) {
+		if (d->bus[k] == bus) {
+			return k;
+		}
+	}
+	return -1;
+}
+
+static void mix_instance(orc_world *w, int qi, const gas_voice *voices, const int *idx, int nv, const gas_frame *src, int frames,
+		gas_frame *bus, gas_frame *peaks, double *bus64, scratch *sc) {
+	orc_instance *q = &w->inst[qi];
+	const gas_spatializer *sp = &w->spat[q->spatializer];
+	const int channels = w->cfg.speaker_mode + 1;
+	const int mix_channels = inst_mix_channels(w, q);                    /* should_mix_channels */
+	const int count = mix_channels ? channels : 1;                       /* init_channels_and_buffers, audio_spatializer.cpp:172-179 */
+	const float mix_rate = w->cfg.mix_rate;
+	const gas_params *prm = &q->params;                                  /* :328 */
+	gas_effect_chain fx = q->fx;
+	if (sp->kind == GAS_SPATIALIZER_EFFECT && sp->effect_gain_binding >= 0 && sp->effect_gain_binding < fx.n_effects) {
+		fx.effects[sp->effect_gain_binding].gain = prm->linear_attenuation; /* example _process_effects, gd_spatializer_instance.gd:125-127 */
+	}
+
+	for (int c = 0; c < count; c++) { /* :335-343 */
+		memset(sc->mix[c], 0, sizeof(gas_frame) * frames);
+		if (bus64) {
+			memset(sc->mix64[c], 0, sizeof(frame64) * frames);
+		}
+	}
+	for (int j = 0; j < nv; j++) { /* :353 */
+		const gas_voice *v = &voices[idx[j]];
+		gas_voice_state *st = &w->vs[v->voice];
+		vstate64 *st64 = &w->vs64[v->voice];
+		const gas_frame *buf = v->src_row >= 0 ? src + (size_t)v->src_row * frames : sc->zero; /* :367-408 done by the caller */
+		if (bus64) {
+			for (int i = 0; i < frames; i++) {
+				sc->src64[i].l = buf[i].l;
+				sc->src64[i].r = buf[i].r;
+			}
+		}
+		const gas_frame *processed = buf;
+		const frame64 *processed64 = sc->src64;
+		if (!mix_channels) { /* should_process_frames: Mode A and Effect, :411-417 */
+			if (sp->kind == GAS_SPATIALIZER_EFFECT) {
+				process_frames_effect_f32(&fx, st, mix_rate, sc->process, buf, frames);
+				if (bus64) {
+					process_frames_effect_f64(&fx, st64, mix_rate, sc->process64, sc->src64, frames);
+				}
+			} else {
+				process_frames_3d_f32(prm, st, mix_rate, sc->process, buf, frames);
+				if (bus64) {
+					process_frames_3d_f64(prm, st64, mix_rate, sc->process64, sc->src64, frames);
+				}
+			}
+			processed = sc->process;
+			processed64 = sc->process64;
+		}
+		gas_frame peak = { 0, 0 }; /* :419 */
+		if (mix_channels) {        /* :421-445 */
+			for (int c = 0; c < channels; c++) {
+				mix_channel_3d_f32(prm, st, mix_rate, c, sc->temp, processed, frames);
+				gas_frame *cb = sc->mix[c];
+				for (int i = 0; i < frames; i++) {
+					cb[i].l += sc->temp[i].l;
+					cb[i].r += sc->temp[i].r;
+					float l = fabsf(sc->temp[i].l);
+					if (l > peak.l) {
+						peak.l = l;
+					}
+					float r = fabsf(sc->temp[i].r);
+					if (r > peak.r) {
+						peak.r = r;
+					}
+				}
+				if (bus64) {
+					mix_channel_3d_f64(prm, st64, mix_rate, c, sc->temp64, processed64, frames);
+					for (int i = 0; i < frames; i++) {
+						sc->mix64[c][i].l += sc->temp64[i].l;
+						sc->mix64[c][i].r += sc->temp64[i].r;
+					}
+				}
+			}
+		} else { /* :446-462 */
+			gas_frame *ob = sc->mix[0];
+			for (int i = 0; i < frames; i++) {
+				ob[i].l += processed[i].l;
+				ob[i].r += processed[i].r;
+				float l = fabsf(processed[i].l);
+				if (l > peak.l) {
+					peak.l = l;
+				}
+				float r = fabsf(processed[i].r);
+				if (r > peak.r) {
+					peak.r = r;
+				}
+			}
+			if (bus64) {
+				for (int i = 0; i < frames; i++) {
+					sc->mix64[0][i].l += processed64[i].l;
+					sc->mix64[0][i].r += processed64[i].r;
+				}
+			}
+		}
+		if (peaks) {
+			peaks[idx[j]] = peak;
+		}
+	}
+
+	/* upstream AudioServer::_mix_step for this instance's proxy playbacks: every
+	 * active bus slot is mixed with the previous volume looked up by bus (absent => 0 => fade-in), buses
+	 * only present in the previous details are mixed once more towards 0, then prev <- cur. */
+	if (bus) {
+		for (int k = 0; k < q->cur.n; k++) {
+			int b = resolve_bus(&w->cfg, q->cur.bus[k]);
+			int pk = details_find(&q->prev, q->cur.bus[k]);
+			for (int c = 0; c < channels; c++) {
+				float ps[2] = { 0, 0 };
+				if (pk >= 0) {
+					ps[0] = q->prev.vol[pk][c][0];
+					ps[1] = q->prev.vol[pk][c][1];
+				}
+				const int sc_idx = mix_channels ? c : 0;
+				server_mix_step_for_channel_f32(bus + ((size_t)b * channels + c) * frames, sc->mix[sc_idx], ps[0], ps[1],
+						q->cur.vol[k][c][0], q->cur.vol[k][c][1], frames);
+				if (bus64) {
+					server_mix_step_for_channel_f64((frame64 *)bus64 + ((size_t)b * channels + c) * frames, sc->mix64[sc_idx], ps[0], ps[1],
+							q->cur.vol[k][c][0], q->cur.vol[k][c][1], frames);
+				}
+			}
+		}
+		for (int pk = 0; pk < q->prev.n; pk++) {
+			if (details_find(&q->cur, q->prev.bus[pk]) >= 0) {
+				continue;
+			}
+			int b = resolve_bus(&w->cfg, q->prev.bus[pk]);
+			for (int c = 0; c < channels; c++) {
+				const int sc_idx = mix_channels ? c : 0;
+				server_mix_step_for_channel_f32(bus + ((size_t)b * channels + c) * frames, sc->mix[sc_idx],
+						q->prev.vol[pk][c][0], q->prev.vol[pk][c][1], 0, 0, frames);
+				if (bus64) {
+					server_mix_step_for_channel_f64((frame64 *)bus64 + ((size_t)b * channels + c) * frames, sc->mix64[sc_idx],
+							q->prev.vol[pk][c][0], q->prev.vol[pk][c][1], 0, 0, frames);
+				}
+			}
+		}
+	}
+	q->prev = q->cur;
+}
+
+static int cmp_int(const void *a, const void *b) {
+	return *(const int *)a - *(const int *)b;
+}
+
+int orc_mix_block(orc_world *w, int n_voices, const gas_voice *voices, const gas_frame *src, int src_rows,
+		int frames, gas_frame *bus_out, gas_frame *peaks, double *bus_out64, int threads) {
+	if (n_voices < 0 || frames <= 0 || (frames & 1) || frames > w->cfg.max_frames) {
+		return GAS_ERR_INVALID;
+	}
+	for (int i = 0; i < n_voices; i++) {
+		if (voices[i].voice < 0 || voices[i].voice >= w->cfg.max_voices || voices[i].instance < 0 ||
+				voices[i].instance >= w->cfg.max_instances || voices[i].src_row >= src_rows) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	const int channels = w->cfg.speaker_mode + 1;
+	const size_t bus_frames = (size_t)w->cfg.num_buses * channels * frames;
+	double t0 = now_s();
+	if (bus_out) {
+		memset(bus_out, 0, bus_frames * sizeof(gas_frame));
+	}
+	if (bus_out64) {
+		memset(bus_out64, 0, bus_frames * 2 * sizeof(double));
+	}
+	if (peaks) {
+		memset(peaks, 0, sizeof(gas_frame) * n_voices);
+	}
+
+	/* group voices by instance, keeping list order inside an instance */
+	const int ni = w->cfg.max_instances;
+	int *count = (int *)calloc(ni + 1, sizeof(int));
+	for (int i = 0; i < n_voices; i++) {
+		count[voices[i].instance + 1]++;
+	}
+	for (int i = 0; i < ni; i++) {
+		count[i + 1] += count[i];
+	}
+	int *fill = (int *)malloc(sizeof(int) * (ni + 1));
+	memcpy(fill, count, sizeof(int) * (ni + 1));
+	int *order = (int *)malloc(sizeof(int) * (n_voices > 0 ? n_voices : 1));
+	for (int i = 0; i < n_voices; i++) {
+		order[fill[voices[i].instance]++] = i;
+	}
+	/* instances to step: every active instance (its proxies are mixed by AudioServer every step) */
+	int *todo = (int *)malloc(sizeof(int) * ni);
+	int ntodo = 0;
+	for (int i = 0; i < ni; i++) {
+		if (w->inst[i].active) {
+			todo[ntodo++] = i;
+		}
+	}
+	qsort(todo, ntodo, sizeof(int), cmp_int);
+
+	if (threads <= 1) {
+		scratch sc;
+		scratch_alloc(&sc, frames, bus_out64 != NULL);
+		for (int t = 0; t < ntodo; t++) {
+			int qi = todo[t];
+			mix_instance(w, qi, voices, order + count[qi], count[qi + 1] - count[qi], src, frames, bus_out, peaks, bus_out64, &sc);
+		}
+		scratch_free(&sc);
+	} else {
+#ifdef _OPENMP
+		gas_frame *partials = (gas_frame *)calloc(bus_frames * threads, sizeof(gas_frame));
+#pragma omp parallel num_threads(threads)
+		{
+			int tid = omp_get_thread_num();
+			scratch sc;
+			scratch_alloc(&sc, frames, 0);
+			gas_frame *mine = partials + bus_frames * tid;
+#pragma omp for schedule(static)
+			for (int t = 0; t < ntodo; t++) {
+				int qi = todo[t];
+				mix_instance(w, qi, voices, order + count[qi], count[qi + 1] - count[qi], src, frames, bus_out ? mine : NULL, peaks, NULL, &sc);
+			}
+			scratch_free(&sc);
+		}
+		if (bus_out) {
+			for (int t = 0; t < threads; t++) {
+				const gas_frame *p = partials + bus_frames * t;
+				for (size_t i = 0; i < bus_frames; i++) {
+					bus_out[i].l += p[i].l;
+					bus_out[i].r += p[i].r;
+				}
+			}
+		}
+		free(partials);
+#else
+		free(count);
+		free(fill);
+		free(order);
+		free(todo);
+		return GAS_ERR_STATE;
+#endif
+	}
+	free(count);
+	free(fill);
+	free(order);
+	free(todo);
+	w->last_mix_s = now_s() - t0;
+	return GAS_OK;
+}
+
+int orc_voice_state_export(orc_world *w, int n, const int32_t *voices, gas_voice_state *out) {
+	for (int i = 0; i < n; i++) {
+		if (voices[i] < 0 || voices[i] >= w->cfg.max_voices) {
+			return GAS_ERR_INVALID;
+		}
+		out[i] = w->vs[voices[i]];
+	}
+	return GAS_OK;
+}
+
+int orc_voice_state_import(orc_world *w, int n, const int32_t *voices, const gas_voice_state *in) {
+	for (int i = 0; i < n; i++) {
+		if (voices[i] < 0 || voices[i] >= w->cfg.max_voices) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		gas_voice_state *d = &w->vs[voices[i]];
+		vstate64 *e = &w->vs64[voices[i]];
+		*d = in[i];
+		for (int c = 0; c < 4; c++) {
+			e->prev_mix_volumes[c][0] = d->prev_mix_volumes[c][0];
+			e->prev_mix_volumes[c][1] = d->prev_mix_volumes[c][1];
+		}
+		for (int k = 0; k < 8; k++) {
+			const gas_processor_state *p = &d->filter_processors[k];
+			proc64 *r = &e->filter_processors[k];
+			r->b0 = p->b0;
+			r->b1 = p->b1;
+			r->b2 = p->b2;
+			r->a1 = p->a1;
+			r->a2 = p->a2;
+			r->ha1 = p->ha1;
+			r->ha2 = p->ha2;
+			r->hb1 = p->hb1;
+			r->hb2 = p->hb2;
+		}
+		for (int a = 0; a < GAS_MAX_EFFECTS; a++) {
+			for (int b = 0; b < 2; b++) {
+				for (int c = 0; c < GAS_MAX_FILTER_STAGES; c++) {
+					for (int k = 0; k < 4; k++) {
+						e->effect_history[a][b][c][k] = d->effect_history[a][b][c][k];
+					}
+				}
+			}
+		}
+	}
+	return GAS_OK;
+}
+
+double orc_last_mix_seconds(const orc_world *w) {
+	return w->last_mix_s;
+}
+double orc_last_gain_seconds(const orc_world *w) {
+	return w->last_gain_s;
+}
+int orc_max_threads(void) {
+#ifdef _OPENMP
+	return omp_get_max_threads();
+#else
+	return 1;
+#endif
+}
+
+size_t orc_sizeof(int32_t id) {
+	switch (id) {
+		case GAS_STRUCT_FRAME: return sizeof(gas_frame);
+		case GAS_STRUCT_EFFECT: return sizeof(gas_effect);
+		case GAS_STRUCT_EFFECT_CHAIN: return sizeof(gas_effect_chain);
+		case GAS_STRUCT_SPATIALIZER: return sizeof(gas_spatializer);
+		case GAS_STRUCT_LISTENER: return sizeof(gas_listener);
+		case GAS_STRUCT_AREA: return sizeof(gas_area);
+		case GAS_STRUCT_EMITTER: return sizeof(gas_emitter);
+		case GAS_STRUCT_PARAMS: return sizeof(gas_params);
+		case GAS_STRUCT_VOICE: return sizeof(gas_voice);
+		case GAS_STRUCT_PROCESSOR_STATE: return sizeof(gas_processor_state);
+		case GAS_STRUCT_VOICE_STATE: return sizeof(gas_voice_state);
+		case GAS_STRUCT_CONFIG: return sizeof(gas_config);
+		default: return 0;
+	}
+}

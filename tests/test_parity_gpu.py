@@ -1,0 +1,136 @@
+"""GPU parity: the CUDA path (through the C ABI, libgas_b200.so) against the CPU oracle on identical
+seeded inputs.  Tolerance (north star): samples within 1e-5 relative or below -110 dBFS absolute;
+bus / pair routing bit-exact; integer fields of the computed parameters bit-exact.
+"""
+import numpy as np
+import pytest
+
+import scenarios as S
+
+pytestmark = pytest.mark.gpu
+abi = S.abi
+
+GAIN_RTOL = 2e-6  # float32 gains: a couple of ulps between CUDA libm and glibc
+
+
+def _run_both(gas, orc, sc):
+    cfg = S.config_of(sc)
+    with gas.Mixer(**cfg) as m, orc.OracleMixer(**cfg) as o:
+        launches0 = m.kernel_launches
+        got = S.run(m, sc)
+        assert m.kernel_launches > launches0, "no CUDA kernel was launched"
+        want = S.run(o, sc)
+    return got, want
+
+
+def _check(got, want, sc, state=True):
+    for b, (pg, pw) in enumerate(zip(got["params"], want["params"])):
+        for f in ("update_parameters", "n_bus", "bus"):
+            assert np.array_equal(pg[f], pw[f]), f"block {b}: {f} differs"
+        for f in ("mix_volumes", "bus_volumes", "pitch_scale", "linear_attenuation", "attenuation_filter_cutoff_hz"):
+            np.testing.assert_allclose(pg[f], pw[f], rtol=GAIN_RTOL, atol=1e-9, err_msg=f"block {b}: {f}")
+    for b, (bg, bw) in enumerate(zip(got["bus"], want["bus"])):
+        assert np.array_equal(S.routing(bg), S.routing(bw)), f"block {b}: routing differs"
+        ok, worst, nbad = S.sample_close(bg, bw)
+        assert ok, f"{sc['name']} block {b}: {nbad} samples out of tolerance, worst abs err {worst:.3e}"
+    for b, (kg, kw) in enumerate(zip(got["peaks"], want["peaks"])):
+        flagged = np.zeros(len(kw), dtype=bool)
+        if sc["want_peak_every"]:
+            flagged[:: sc["want_peak_every"]] = True
+        ok, worst, nbad = S.sample_close(kg[flagged], kw[flagged])
+        assert ok, f"block {b}: peaks differ (worst {worst:.3e})"
+        assert np.all(kg[~flagged] == 0)
+    if state:
+        sg, sw = got["state"], want["state"]
+        np.testing.assert_allclose(sg["prev_mix_volumes"], sw["prev_mix_volumes"], rtol=GAIN_RTOL, atol=1e-9)
+        for f in ("b0", "b1", "b2", "a1", "a2"):
+            np.testing.assert_allclose(sg["filter_processors"][f], sw["filter_processors"][f], rtol=1e-4, atol=1e-7)
+        for f in ("ha1", "ha2", "hb1", "hb2"):
+            ok, worst, nbad = S.sample_close(sg["filter_processors"][f], sw["filter_processors"][f], rel=1e-4)
+            assert ok, f"filter history {f}: worst {worst:.3e}"
+        ok, worst, nbad = S.sample_close(sg["effect_history"], sw["effect_history"], rel=1e-4)
+        assert ok, f"effect history: worst {worst:.3e}"
+
+
+MODES = {"A": 0, "B": 1}
+SPEAKERS = {"stereo": abi.SPEAKER_MODE_STEREO, "3.1": abi.SPEAKER_SURROUND_31, "5.1": abi.SPEAKER_SURROUND_51, "7.1": abi.SPEAKER_SURROUND_71}
+
+
+@pytest.mark.parametrize("mode", ["A", "B"])
+@pytest.mark.parametrize("speakers", ["stereo", "5.1", "7.1"])
+def test_streaming_path_filter_off(gas, orc, mode, speakers):
+    """K2: no filter (linear_attenuation forced to 0), ramps change every block."""
+    sc = S.default_scenario(name=f"stream-{mode}-{speakers}", voices=64, speaker_mode=SPEAKERS[speakers],
+                            spat=dict(mix_channel_mode=MODES[mode]), force_filter_off=True, blocks=3)
+    got, want = _run_both(gas, orc, sc)
+    _check(got, want, sc)
+
+
+@pytest.mark.parametrize("mode", ["A", "B"])
+@pytest.mark.parametrize("speakers", ["stereo", "3.1", "5.1", "7.1"])
+def test_filter_path(gas, orc, mode, speakers):
+    """K3: attenuation high-shelf active (default -24 dB), first block fades the filter in (Q12)."""
+    sc = S.default_scenario(name=f"filter-{mode}-{speakers}", voices=48, speaker_mode=SPEAKERS[speakers],
+                            spat=dict(mix_channel_mode=MODES[mode]), blocks=3, want_peak_every=3)
+    got, want = _run_both(gas, orc, sc)
+    _check(got, want, sc)
+
+
+@pytest.mark.parametrize("mode", ["A", "B"])
+def test_reverb_area_two_buses(gas, orc, mode):
+    """Reverb Area3D: half of the voices send to a second bus; uniformity 0 and > 0."""
+    for uni in (0.0, 0.6):
+        sc = S.default_scenario(name=f"reverb-{mode}-{uni}", voices=40, speaker_mode=abi.SPEAKER_SURROUND_51,
+                                spat=dict(mix_channel_mode=MODES[mode]), area=dict(reverb_bus=1, amount=0.5, uniformity=uni),
+                                area_fraction=0.5, force_filter_off=True, blocks=3)
+        got, want = _run_both(gas, orc, sc)
+        _check(got, want, sc)
+
+
+def test_attenuation_models_and_max_distance(gas, orc):
+    for model in range(4):
+        sc = S.default_scenario(name=f"model-{model}", voices=33, speaker_mode=abi.SPEAKER_SURROUND_71,
+                                spat=dict(attenuation_model=model, max_distance=100.0, mix_channel_mode=1,
+                                          emission_angle_enabled=1, emission_angle=30.0),
+                                listeners="two", blocks=2)
+        got, want = _run_both(gas, orc, sc)
+        _check(got, want, sc)
+
+
+def test_effect_chain(gas, orc):
+    """AudioSpatializerEffect: cascaded non-interpolated biquads before multi-bus sends."""
+    for stages in (1, 2, 4):
+        chain = [dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=4000.0, resonance=1.0, gain=0.3, stages=stages)]
+        sc = S.default_scenario(name=f"effect-{stages}", voices=37, speaker_mode=abi.SPEAKER_MODE_STEREO, num_buses=3,
+                                effect_chain=chain, effect_gain_binding=0, area=dict(reverb_bus=2, amount=0.4), area_fraction=0.5,
+                                blocks=3)
+        got, want = _run_both(gas, orc, sc)
+        _check(got, want, sc)
+
+
+def test_polyphony_late_start_silence_and_odd_sizes(gas, orc):
+    """Several voices per instance, voices joining at block 2, silent (tail) voices with peaks,
+    a voice count that is not a multiple of anything and a non-power-of-two block size."""
+    sc = S.default_scenario(name="poly", voices=45, voices_per_instance=3, frames=480, speaker_mode=abi.SPEAKER_SURROUND_51,
+                            spat=dict(mix_channel_mode=1), blocks=4, start_late=2, silent_every=7, want_peak_every=5)
+    got, want = _run_both(gas, orc, sc)
+    _check(got, want, sc)
+    sc = S.default_scenario(name="poly-A-off", voices=45, voices_per_instance=3, frames=130, speaker_mode=abi.SPEAKER_MODE_STEREO,
+                            spat=dict(mix_channel_mode=0), blocks=4, start_late=2, silent_every=7, force_filter_off=True)
+    got, want = _run_both(gas, orc, sc)
+    _check(got, want, sc)
+
+
+def test_empty_block_and_invalid_arguments(gas):
+    with gas.Mixer(max_voices=8, max_instances=8) as m:
+        bus, peaks = m.mix_block(np.zeros(0, dtype=abi.voice), np.zeros((0, 512, 2), np.float32), 512)
+        assert bus.shape == (2, 1, 512, 2) and not bus.any()
+        v = S.synth.make_voices(2)
+        with pytest.raises(gas.GasError):
+            m.mix_block(v, np.zeros((2, 511, 2), np.float32), 511)  # odd frame count
+        v["voice"][1] = 99
+        with pytest.raises(gas.GasError):
+            m.mix_block(v, np.zeros((2, 512, 2), np.float32), 512)  # voice slot out of range
+        bad = abi.spatializer_defaults(max_distance=-1.0)
+        with pytest.raises(gas.GasError):
+            m.spatializer_set(0, bad)  # reference audio_spatializer_3d.cpp:671
