@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py — mixed voice-frames/sec of the batched spatial mixer on N B200s (one process per GPU).
+
+One *step* = one pass of the hot path over one mix block of synthetic input on every rank:
+gain kernel (calculate_spatialization for every instance) -> prologue -> streaming / voice-parallel mix
+kernels -> (N > 1) sum of the per-GPU partial bus buffers.  Workload (BASELINE.json configs[2] shape,
+SURVEY.md §8d): AudioSpatializer3D, 16384 voices per GPU x 512-frame blocks at 48 kHz, 7.1 (4 channel
+pairs), mix_channel_mode on, two buses (Master + a reverb bus fed by the voices inside a reverb Area3D),
+attenuation filter inactive because the reference skips it below 0.001 linear gain
+(audio_spatializer_3d.cpp:568) — obtained with attenuation_filter_db = -80 and unit_size = 1, no override.
+
+value      whole-job voice-frames/s, inputs resident in HBM, CUDA-graph replay of the device-resident
+           C-ABI calls, timed with CUDA events on the mix stream, max over ranks.
+e2e        same metric through gas_gain_compute + gas_mix_block with HOST (pinned) buffers: per step the
+           sources/voices/emitters go host->device and the bus buffers come back, inside the timed region.
+roofline   streaming mix kernel (K2): algorithmic bytes per launch / its mean duration (CUDA events around
+           every launch) vs the measured HBM copy peak in MEASURED_PEAKS.json.
+cpu_baseline  the CPU oracle (restated reference loop, oracle/) on the host cores, bounded sample.
+
+`--impl reference` times the reference's CPU implementation of the path (the oracle port: the reference
+itself needs the Godot engine tree + scons and cannot be built here) on all host threads.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "mixed voice-frames/sec"
+UNIT = "voice-frames/s"
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+WORKLOAD = dict(voices=16384, frames=512, mix_rate=48000.0, speaker_mode=3, num_buses=2, area_fraction=0.25,
+                spat=dict(mix_channel_mode=1, unit_size=1.0, attenuation_filter_db=-80.0), r_min=10.0, r_max=120.0)
+N_SETS = 8  # distinct source / emitter sets rotated through: 8 x 64 MiB = 512 MiB >= 4 x L2
+
+
+def workload_name(w, filt="off"):
+    return (f"AudioSpatializer3D {w['voices']} voices/GPU x {w['frames']}-frame blocks @ {int(w['mix_rate'])} Hz, 7.1, "
+            f"mix_channel_mode, Master + reverb bus ({int(w['area_fraction'] * 100)}% of voices in the reverb area), filter {filt}")
+
+
+def algorithmic_bytes(V, F, C, B_out, filter_on=False):
+    """8 V F (source read) + V S(C) (per-voice parameters/state) + 8 F C B_out (bus write)."""
+    S = 24 + (168 if filter_on else 24) * C
+    return 8 * V * F + V * S + 8 * F * C * B_out
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.005):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self._stop_evt = [], threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.time(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self, t0, t1):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        nv = self.nv
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        seen = set()
+        for _, _, r in inside:
+            for bit, nm in names.items():
+                if r & bit:
+                    seen.add(nm)
+        mhz = sorted(s[1] for s in inside)
+        return {"sm_mhz": (mhz[len(mhz) // 2] if mhz else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(seen),
+                "samples": len(inside)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def build_host_inputs(w, abi, synth, n_emitter_sets=2, src_sets=1):
+    V, F = w["voices"], w["frames"]
+    dt = F / w["mix_rate"]
+    emitters = [synth.make_emitters(V, block=b, dt=dt, area_fraction=w["area_fraction"], r_min=w["r_min"], r_max=w["r_max"])
+                for b in range(n_emitter_sets)]
+    srcs = [synth.make_sources(V, F, block=b, mix_rate=w["mix_rate"]) for b in range(src_sets)]
+    voices = synth.make_voices(V)
+    listeners = np.array([abi.identity_listener()], dtype=abi.listener)
+    areas = np.array([synth.reverb_area(reverb_bus=1, amount=0.5, uniformity=0.0)], dtype=abi.area)
+    return emitters, srcs, voices, listeners, areas
+
+
+def setup_mixer(m, w, abi, emitters, listeners, areas):
+    V = w["voices"]
+    inst = np.arange(V, dtype=np.int32)
+    m.spatializer_set(0, abi.spatializer_defaults(**w["spat"]))
+    m.instance_init(inst, 0)
+    m.gain_compute(emitters[0], listeners, areas, want_params=False)
+    m.instance_start(inst)
+    m.voice_init(inst)
+
+
+def run_cpu(w, steps, warmup, threads, abi, synth, budget_s=None, inputs=None):
+    """Oracle port of the reference loop: gain (serial, like the physics thread) + mix per step.
+    Returns (voice-frames/s, steps actually timed, seconds)."""
+    from oracle import orc
+    V, F = w["voices"], w["frames"]
+    emitters, srcs, voices, listeners, areas = inputs or build_host_inputs(w, abi, synth)
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, max_spatializers=2, num_buses=w["num_buses"], speaker_mode=w["speaker_mode"],
+               mix_rate=w["mix_rate"])
+    with orc.OracleMixer(**cfg) as o:
+        setup_mixer(o, w, abi, emitters, listeners, areas)
+        for k in range(warmup):
+            o.gain_compute(emitters[k % len(emitters)], listeners, areas, want_params=False)
+            o.mix_block(voices, srcs[k % len(srcs)], F, want_peaks=False, threads=threads)
+        t0 = time.perf_counter()
+        done = 0
+        for k in range(steps):
+            o.gain_compute(emitters[k % len(emitters)], listeners, areas, want_params=False)
+            o.mix_block(voices, srcs[k % len(srcs)], F, want_peaks=False, threads=threads)
+            done += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+    return V * F * done / dt, done, dt
+
+
+def reference_arm(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import gaspkg
+    gas = gaspkg.load()
+    abi, synth = gas.abi, gas.synth
+    from oracle import orc
+    w = dict(WORKLOAD)
+    threads = orc.max_threads()
+    steps = max(1, min(args.steps, 40))  # each step is a bounded sample: one full 16384-voice block on the CPU
+    warmup = max(1, min(args.warmup, 2))
+    value, done, secs = run_cpu(w, steps, warmup, threads, abi, synth, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": warmup,
+        "ms_per_step": 1e3 * secs / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(w), "note": "reference CPU path = oracle port (g++ -O2, OpenMP over instances); "
+                   "headless Godot cannot be built here (needs engine tree + scons)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{done} full blocks of {w['voices']} voices x {w['frames']} frames (gain + mix)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+class DeviceWorkload:
+    """Everything one rank needs resident in HBM."""
+
+    def __init__(self, gas, torch, w, device, rank, parity_src=None):
+        abi, synth = gas.abi, gas.synth
+        self.gas, self.torch, self.w = gas, torch, w
+        V, F = w["voices"], w["frames"]
+        self.C = w["speaker_mode"] + 1
+        dt = F / w["mix_rate"]
+        self.listeners = np.array([abi.identity_listener()], dtype=abi.listener)
+        self.areas = np.array([synth.reverb_area(reverb_bus=1, amount=0.5, uniformity=0.0)], dtype=abi.area)
+        self.emitters_host = [synth.make_emitters(V, block=b, dt=dt, area_fraction=w["area_fraction"], r_min=w["r_min"], r_max=w["r_max"],
+                                                  seed0=rank * 1000003) for b in range(N_SETS)]
+        self.voices_host = synth.make_voices(V)
+        self.mixer = gas.Mixer(device=device, max_instances=V, max_voices=V, max_frames=F, max_spatializers=2, num_buses=w["num_buses"],
+                               speaker_mode=w["speaker_mode"], mix_rate=w["mix_rate"])
+        dev = torch.device("cuda", device)
+        self.d_emitters = [torch.from_numpy(e.view(np.uint8).copy()).to(dev) for e in self.emitters_host]
+        self.d_voices = torch.from_numpy(self.voices_host.view(np.uint8).copy()).to(dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + rank)
+        self.d_src = []
+        for k in range(N_SETS):
+            if k == 0 and parity_src is not None:
+                self.d_src.append(torch.from_numpy(parity_src).to(dev))
+            else:
+                self.d_src.append((torch.rand((V, F, 2), generator=g, device=dev, dtype=torch.float32) - 0.5) * 0.5)
+        self.d_bus = [torch.zeros((w["num_buses"], self.C, F, 2), device=dev, dtype=torch.float32) for _ in range(2)]
+        setup_mixer(self.mixer, w, abi, self.emitters_host, self.listeners, self.areas)
+        self.mixer.listeners_set(self.listeners)
+        self.mixer.areas_set(self.areas)
+        self.mixer.sync()
+
+    def step_device(self, k):
+        m, w = self.mixer, self.w
+        s = k % N_SETS
+        m.gain_compute_device(w["voices"], self.d_emitters[s].data_ptr())
+        m.mix_block_device(w["voices"], self.d_voices.data_ptr(), self.d_src[s].data_ptr(), w["voices"], w["frames"], w["frames"],
+                           self.d_bus[k % 2].data_ptr())
+        return self.d_bus[k % 2]
+
+    def capture_steps(self):
+        graphs = []
+        for s in range(N_SETS):
+            self.mixer.capture_begin()
+            self.step_device(s)
+            graphs.append(self.mixer.capture_end())
+        return graphs
+
+
+def parity_gate(gas, w, dw, abi, synth, parity_src, host_inputs):
+    """Full-size parity of the exact bench workload: 2 state-carrying blocks on source set 0 against
+    the float32 oracle (north-star tolerance) and the float64 shadow (accumulation-order budget)."""
+    from oracle import orc
+    import scenarios as S
+    V, F = w["voices"], w["frames"]
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, max_spatializers=2, num_buses=w["num_buses"], speaker_mode=w["speaker_mode"],
+               mix_rate=w["mix_rate"])
+    emitters, _, voices, listeners, areas = host_inputs
+    res = {}
+    with orc.OracleMixer(**cfg) as o, gas.Mixer(device=int(dw.mixer.config["device"]), **cfg) as m:
+        for mm in (o, m):
+            setup_mixer(mm, w, abi, emitters, listeners, areas)
+        for b in range(2):
+            for mm in (o, m):
+                mm.gain_compute(emitters[b % len(emitters)], listeners, areas, want_params=False)
+            want, _ = o.mix_block(voices, parity_src, F, want_peaks=False, shadow=True, threads=1)
+            got, _ = m.mix_block(voices, parity_src, F, want_peaks=False)
+            shadow = o.last_bus64
+            ok, worst, nbad = S.sample_close(got, want)
+            scale = float(np.abs(shadow).max())
+            res[f"block{b}"] = {
+                "routing_exact": bool(np.array_equal(S.routing(got), S.routing(want))),
+                "within_1e-5_rel_or_-110dBFS_of_f32_oracle": ok, "samples_out": nbad, "worst_abs_err_vs_f32_oracle": worst,
+                "max_abs_err_gpu_vs_f64_shadow": float(np.abs(got - shadow).max()),
+                "max_abs_err_f32_oracle_vs_f64_shadow": float(np.abs(want - shadow).max()),
+                "peak_abs_bus_sample": scale,
+            }
+    return res
+
+
+def gpu_arm(args):
+    import torch
+    import gaspkg
+    gas = gaspkg.load()
+    abi, synth = gas.abi, gas.synth
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = dict(WORKLOAD)
+    if args.voices:
+        w["voices"] = args.voices
+    if args.frames:
+        w["frames"] = args.frames
+    V, F, C, B = w["voices"], w["frames"], w["speaker_mode"] + 1, w["num_buses"]
+    K, W = args.steps, max(3, args.warmup)
+
+    parity_src = synth.make_sources(V, F, block=0, mix_rate=w["mix_rate"]) if (rank == 0 and not args.no_parity) else None
+    dw = DeviceWorkload(gas, torch, w, local_rank, rank, parity_src)
+    m = dw.mixer
+    stream = torch.cuda.ExternalStream(m.mix_stream, device=torch.device("cuda", local_rank))
+
+    parity = None
+    host_inputs = None
+    if rank == 0 and not args.no_parity:
+        host_inputs = build_host_inputs(w, abi, synth)
+        parity = parity_gate(gas, w, dw, abi, synth, parity_src, host_inputs)
+
+    graphs = dw.capture_steps()
+
+    def one_step(k):
+        m.graph_launch(graphs[k % N_SETS])
+        if dist is not None:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(dw.d_bus[k % 2])  # sum of the per-GPU partial bus buffers (NCCL over NVLink)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        m.sync()
+        torch.cuda.synchronize()
+
+    # ---- timed region: `value` ----------------------------------------------------------------------------
+    for k in range(W):
+        one_step(k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = m.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    with torch.cuda.stream(stream):
+        ev0.record()
+    for k in range(K):
+        one_step(W + k)
+    with torch.cuda.stream(stream):
+        ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    sampler.stop()
+    sampler.join()
+    ms = ev0.elapsed_time(ev1)
+    gpu_launches = m.kernel_launches - launches0
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * V * F * K / (ms * 1e-3)
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- roofline: per-launch duration of the streaming mix kernel, events around every launch ---------------
+    m.profile_enable(True)
+    kp = max(8, min(K, 256))
+    for k in range(kp):
+        dw.step_device(k)
+    prof = m.profile_read()
+    m.profile_enable(False)
+    k2_ms, k2_n = prof["mix_stream"]
+    peak, peak_src = measured_hbm_peak()
+    bytes_launch = algorithmic_bytes(V, F, C, B)
+    k2_us = 1e3 * k2_ms / max(1, k2_n)
+    achieved = bytes_launch / (k2_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "k_mix_stream (K2)", "us_per_launch": k2_us, "algorithmic_bytes_per_launch": bytes_launch,
+                "peak_source": peak_src,
+                "step_frac_of_hbm_peak": (bytes_launch / (ms * 1e-3 / K) / 1e9) / peak,
+                "other_kernels_us": {"prologue": 1e3 * prof["prologue"][0] / max(1, prof["prologue"][1]),
+                                     "mix_voice_K3": 1e3 * prof["mix_voice"][0] / max(1, prof["mix_voice"][1])}}
+    traffic_file = os.path.join(ROOT, "profiles", "k2_traffic_bytes.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as f:
+                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers through gas_gain_compute + gas_mix_block ------------------------------------------------
+    ke = max(4, min(K, args.e2e_steps))
+    pin_src = [torch.empty((V, F, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for t_ in pin_src:
+        t_.copy_(dw.d_src[0].cpu() if parity_src is None else torch.from_numpy(parity_src))
+    pin_voices = torch.from_numpy(dw.voices_host.view(np.uint8).copy()).pin_memory()
+    pin_bus = torch.empty((B, C, F, 2), dtype=torch.float32).pin_memory()
+    h2d = V * F * 8 + dw.voices_host.nbytes + dw.emitters_host[0].nbytes + dw.listeners.nbytes + dw.areas.nbytes
+    d2h = B * C * F * 8
+
+    def e2e_step(k):
+        m.gain_compute(dw.emitters_host[k % N_SETS], dw.listeners, dw.areas, want_params=False)
+        m.mix_block_host_ptr(V, pin_voices.data_ptr(), pin_src[k % 2].data_ptr(), V, F, pin_bus.data_ptr())
+        if dist is not None:
+            dist.all_reduce(dw.d_bus[0])
+
+    for k in range(3):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(ke):
+        e2e_step(k)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * V * F * ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
+           "ms_per_step": 1e3 * e2e_s / ke, "api": "gas_gain_compute + gas_mix_block (host pointers, pinned)"}
+
+    # ---- cpu baseline (rank 0, N = 1) --------------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import orc
+        threads = orc.max_threads()
+        inputs = host_inputs or build_host_inputs(w, abi, synth)
+        v_all, n_all, s_all = run_cpu(w, 400, 1, threads, abi, synth, budget_s=12.0, inputs=inputs)
+        v_one, n_one, s_one = run_cpu(w, 400, 1, 1, abi, synth, budget_s=8.0, inputs=inputs)
+        cpu = {"value": v_all, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_all} full blocks ({V} voices x {F} frames, gain + mix) in {s_all:.1f} s, OpenMP over instances",
+               "single_thread": {"value": v_one, "blocks": n_one, "seconds": s_one,
+                                 "note": "faithful: Godot mixes on one audio thread"},
+               "note": "oracle port of the reference loop (g++ -O2); headless Godot cannot be built here"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(w), "voices_per_gpu": V, "frames": F, "channel_pairs": C, "buses": B,
+                       "l2": f"{N_SETS} distinct source sets of {V * F * 8 / 2**20:.0f} MiB rotated (> 4x L2)",
+                       "launch": "CUDA-graph replay of gas_gain_compute_device + gas_mix_block_device, one graph per step",
+                       "reduce": "torch.distributed all_reduce (NCCL) of the partial bus buffers" if world > 1 else "none (1 GPU)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
+            "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--voices", type=int, default=0)
+    ap.add_argument("--frames", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -96,17 +96,65 @@ bool spat_valid(const gas_spatializer *s) { // reference audio_spatializer_3d.cp
 	return true;
 }
 
+// per-kernel timing: a pair of timing events around a launch on the mix stream
+int prof_drain(gas_ctx *ctx) {
+	if (ctx->prof_used == 0) {
+		return GAS_OK;
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	for (size_t i = 0; i < ctx->prof_used; i++) {
+		float ms = 0.f;
+		GAS_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_pairs[i].a, ctx->prof_pairs[i].b));
+		ctx->prof_ms[ctx->prof_pairs[i].kind] += ms;
+		ctx->prof_n[ctx->prof_pairs[i].kind] += 1;
+	}
+	ctx->prof_used = 0;
+	return GAS_OK;
+}
+
+gas_ctx::ProfPair *prof_open(gas_ctx *ctx, int kind) {
+	if (!ctx->profiling || ctx->capturing) {
+		return nullptr;
+	}
+	if (ctx->prof_used >= 3072 && prof_drain(ctx) != GAS_OK) {
+		return nullptr;
+	}
+	if (ctx->prof_used == ctx->prof_pairs.size()) {
+		gas_ctx::ProfPair pp{};
+		if (cudaEventCreate(&pp.a) != cudaSuccess || cudaEventCreate(&pp.b) != cudaSuccess) {
+			return nullptr;
+		}
+		ctx->prof_pairs.push_back(pp);
+	}
+	gas_ctx::ProfPair *p = &ctx->prof_pairs[ctx->prof_used++];
+	p->kind = kind;
+	cudaEventRecord(p->a, ctx->s_mix);
+	return p;
+}
+
+void prof_close(gas_ctx *ctx, gas_ctx::ProfPair *p) {
+	if (p) {
+		cudaEventRecord(p->b, ctx->s_mix);
+	}
+}
+
 int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_frame *d_src, int src_stride, int frames,
 		gas_frame *d_bus, gas_frame *d_peaks) {
 	if (ctx->gain_pending) {
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
 	}
+	gas_ctx::ProfPair *pp = prof_open(ctx, GAS_KERNEL_PROLOGUE);
 	GAS_CUDA(ctx, launch_prologue(ctx, n_voices, d_voices, frames, d_bus, d_peaks, ctx->s_mix));
+	prof_close(ctx, pp);
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix));
 	ctx->prologue_pending = true;
 	if (n_voices > 0) {
+		pp = prof_open(ctx, GAS_KERNEL_MIX_STREAM);
 		GAS_CUDA(ctx, launch_mix_stream(ctx, d_src, src_stride, frames, d_bus, ctx->s_mix));
+		prof_close(ctx, pp);
+		pp = prof_open(ctx, GAS_KERNEL_MIX_VOICE);
 		GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_mix));
+		prof_close(ctx, pp);
 	}
 	return GAS_OK;
 }
@@ -265,6 +313,8 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_gain, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_gain_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_prologue_done, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
 	if (ok) {
 		ok = launch_defaults(ctx, ctx->s_gain) == cudaSuccess && cudaStreamSynchronize(ctx->s_gain) == cudaSuccess;
 	}
@@ -306,6 +356,21 @@ void gas_destroy(gas_ctx *ctx) {
 	}
 	if (ctx->ev_prologue_done) {
 		cudaEventDestroy(ctx->ev_prologue_done);
+	}
+	if (ctx->ev_fork) {
+		cudaEventDestroy(ctx->ev_fork);
+	}
+	if (ctx->ev_join) {
+		cudaEventDestroy(ctx->ev_join);
+	}
+	for (auto &g : ctx->graphs) {
+		if (g.exec) {
+			cudaGraphExecDestroy(g.exec);
+		}
+	}
+	for (auto &pp : ctx->prof_pairs) {
+		cudaEventDestroy(pp.a);
+		cudaEventDestroy(pp.b);
 	}
 	if (ctx->s_mix) {
 		cudaStreamDestroy(ctx->s_mix);
@@ -433,20 +498,66 @@ int gas_voice_init(gas_ctx *ctx, int32_t n, const int32_t *voices) {
 
 static int gain_common(gas_ctx *ctx, int32_t n, const gas_emitter *d_em, int32_t n_listeners, const gas_listener *listeners, int32_t n_areas,
 		const gas_area *areas, gas_params *d_out) {
-	if (n_listeners < 0 || n_listeners > GAS_MAX_LISTENERS || (n_listeners > 0 && !listeners)) {
-		return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute: 0..%d listeners", GAS_MAX_LISTENERS);
+	if (listeners) {
+		if (n_listeners < 0 || n_listeners > GAS_MAX_LISTENERS) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute: 0..%d listeners", GAS_MAX_LISTENERS);
+		}
+		if (ctx->capturing) {
+			return gas_fail(ctx, GAS_ERR_STATE, "gas_gain_compute: host listeners cannot be uploaded while capturing; use gas_listeners_set");
+		}
+		if (n_listeners > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_listeners, listeners, n_listeners * sizeof(gas_listener), cudaMemcpyHostToDevice, ctx->s_gain));
+		}
+		ctx->n_listeners_res = n_listeners;
+	} else {
+		n_listeners = ctx->n_listeners_res; // resident copy (gas_listeners_set)
 	}
-	if (n_areas < 0 || n_areas > ctx->max_areas || (n_areas > 0 && !areas)) {
-		return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute: 0..%d areas", ctx->max_areas);
+	if (areas) {
+		if (n_areas < 0 || n_areas > ctx->max_areas) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute: 0..%d areas", ctx->max_areas);
+		}
+		if (ctx->capturing) {
+			return gas_fail(ctx, GAS_ERR_STATE, "gas_gain_compute: host areas cannot be uploaded while capturing; use gas_areas_set");
+		}
+		if (n_areas > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_areas, areas, n_areas * sizeof(gas_area), cudaMemcpyHostToDevice, ctx->s_gain));
+		}
+		ctx->n_areas_res = n_areas;
+	}
+	GAS_CUDA(ctx, launch_gain(ctx, n, d_em, n_listeners, ctx->d_listeners, ctx->d_areas, d_out, ctx->s_gain));
+	return GAS_OK;
+}
+
+int gas_listeners_set(gas_ctx *ctx, int32_t n_listeners, const gas_listener *listeners) {
+	ENTER(ctx);
+	if (n_listeners < 0 || n_listeners > GAS_MAX_LISTENERS || (n_listeners > 0 && !listeners) || ctx->capturing) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_listeners_set: 0..%d listeners, not while capturing", GAS_MAX_LISTENERS);
+	}
+	int st = gain_side_begin(ctx);
+	if (st) {
+		return st;
 	}
 	if (n_listeners > 0) {
 		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_listeners, listeners, n_listeners * sizeof(gas_listener), cudaMemcpyHostToDevice, ctx->s_gain));
 	}
+	ctx->n_listeners_res = n_listeners;
+	return gain_side_end(ctx);
+}
+
+int gas_areas_set(gas_ctx *ctx, int32_t n_areas, const gas_area *areas) {
+	ENTER(ctx);
+	if (n_areas < 0 || n_areas > ctx->max_areas || (n_areas > 0 && !areas) || ctx->capturing) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_areas_set: 0..%d areas, not while capturing", ctx->max_areas);
+	}
+	int st = gain_side_begin(ctx);
+	if (st) {
+		return st;
+	}
 	if (n_areas > 0) {
 		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_areas, areas, n_areas * sizeof(gas_area), cudaMemcpyHostToDevice, ctx->s_gain));
 	}
-	GAS_CUDA(ctx, launch_gain(ctx, n, d_em, n_listeners, ctx->d_listeners, ctx->d_areas, d_out, ctx->s_gain));
-	return GAS_OK;
+	ctx->n_areas_res = n_areas;
+	return gain_side_end(ctx);
 }
 
 int gas_gain_compute(gas_ctx *ctx, int32_t n, const gas_emitter *emitters, int32_t n_listeners, const gas_listener *listeners,
@@ -654,6 +765,115 @@ int gas_voice_state_import(gas_ctx *ctx, int32_t n, const int32_t *voices, const
 	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
 	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, in, n * sizeof(gas_voice_state), cudaMemcpyHostToDevice, ctx->s_mix));
 	GAS_CUDA(ctx, launch_state_import(ctx, n, ctx->d_ids, (const gas_voice_state *)ctx->d_scratch, ctx->s_mix));
+	return GAS_OK;
+}
+
+// ---- CUDA-graph capture ---------------------------------------------------------------------------------
+int gas_capture_begin(gas_ctx *ctx) {
+	ENTER(ctx);
+	if (ctx->capturing) {
+		return gas_fail(ctx, GAS_ERR_STATE, "gas_capture_begin: already capturing");
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_gain));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	ctx->gain_pending = ctx->prologue_pending = false;
+	GAS_CUDA(ctx, cudaStreamBeginCapture(ctx->s_mix, cudaStreamCaptureModeThreadLocal));
+	// fork: the gain stream joins the capture
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->s_mix));
+	GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_gain, ctx->ev_fork, 0));
+	ctx->capturing = true;
+	ctx->capture_launches0 = ctx->launches;
+	return GAS_OK;
+}
+
+int gas_capture_end(gas_ctx *ctx, int32_t *out_graph) {
+	ENTER(ctx);
+	if (!ctx->capturing || !out_graph) {
+		return gas_fail(ctx, GAS_ERR_STATE, "gas_capture_end: not capturing (or null out_graph)");
+	}
+	ctx->capturing = false;
+	cudaGraph_t graph = nullptr;
+	cudaError_t e = cudaEventRecord(ctx->ev_join, ctx->s_gain); // join the gain stream back
+	if (e == cudaSuccess) {
+		e = cudaStreamWaitEvent(ctx->s_mix, ctx->ev_join, 0);
+	}
+	cudaError_t e2 = cudaStreamEndCapture(ctx->s_mix, &graph);
+	const uint64_t kernels = ctx->launches - ctx->capture_launches0;
+	ctx->launches = ctx->capture_launches0; // nothing ran yet
+	ctx->gain_pending = ctx->prologue_pending = false;
+	if (e != cudaSuccess || e2 != cudaSuccess || !graph) {
+		return gas_fail(ctx, GAS_ERR_CUDA, "gas_capture_end: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+	}
+	gas_ctx::Graph g;
+	e = cudaGraphInstantiate(&g.exec, graph, 0);
+	cudaGraphDestroy(graph);
+	if (e != cudaSuccess) {
+		return gas_fail(ctx, GAS_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+	}
+	g.kernels = kernels;
+	ctx->graphs.push_back(g);
+	*out_graph = (int32_t)ctx->graphs.size() - 1;
+	return GAS_OK;
+}
+
+int gas_graph_launch(gas_ctx *ctx, int32_t graph) {
+	ENTER(ctx);
+	if (ctx->capturing || graph < 0 || graph >= (int32_t)ctx->graphs.size() || !ctx->graphs[graph].exec) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_graph_launch: bad graph id or capture in progress");
+	}
+	if (ctx->gain_pending) {
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
+	}
+	GAS_CUDA(ctx, cudaGraphLaunch(ctx->graphs[graph].exec, ctx->s_mix));
+	ctx->launches += ctx->graphs[graph].kernels;
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix)); // later gain-side work waits for the whole graph
+	ctx->prologue_pending = true;
+	return GAS_OK;
+}
+
+int gas_graph_destroy(gas_ctx *ctx, int32_t graph) {
+	ENTER(ctx);
+	if (graph < 0 || graph >= (int32_t)ctx->graphs.size()) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_graph_destroy: bad graph id");
+	}
+	if (ctx->graphs[graph].exec) {
+		GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+		cudaGraphExecDestroy(ctx->graphs[graph].exec);
+		ctx->graphs[graph].exec = nullptr;
+	}
+	return GAS_OK;
+}
+
+// ---- per-kernel timing ------------------------------------------------------------------------------------
+int gas_profile_enable(gas_ctx *ctx, int32_t on) {
+	ENTER(ctx);
+	int st = prof_drain(ctx);
+	if (st) {
+		return st;
+	}
+	ctx->profiling = on != 0;
+	if (on) {
+		for (int k = 0; k < GAS_KERNEL_KINDS; k++) {
+			ctx->prof_ms[k] = 0.0;
+			ctx->prof_n[k] = 0;
+		}
+	}
+	return GAS_OK;
+}
+
+int gas_profile_read(gas_ctx *ctx, double ms_out[GAS_KERNEL_KINDS], uint64_t launches_out[GAS_KERNEL_KINDS]) {
+	ENTER(ctx);
+	if (!ms_out || !launches_out) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_profile_read: null output");
+	}
+	int st = prof_drain(ctx);
+	if (st) {
+		return st;
+	}
+	for (int k = 0; k < GAS_KERNEL_KINDS; k++) {
+		ms_out[k] = ctx->prof_ms[k];
+		launches_out[k] = ctx->prof_n[k];
+	}
 	return GAS_OK;
 }
 

@@ -1,5 +1,5 @@
 // gas_internal.h — context, device tables and per-block records shared by the .cu files.
-// Product code: never includes anything from oracle/.
+// Product code: nothing here depends on the CPU checker that lives outside this package.
 #pragma once
 
 #include "../../include/gas.h"
@@ -9,6 +9,7 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 
 // ---- limits of the per-block plan -----------------------------------------------------------------
 #define GAS_MAX_SENDS 12      // union of current and previous bus details: 6 + 6
@@ -115,7 +116,7 @@ struct gas_ctx {
 	int num_sms = 0;
 	int l2_bytes = 0;
 	cudaStream_t s_mix = nullptr, s_gain = nullptr;
-	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr;
+	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr;
 	bool gain_pending = false, prologue_pending = false;
 	DevTables t{};
 	BlockPlan plan{};
@@ -140,6 +141,25 @@ struct gas_ctx {
 	gas_frame *peer_exchange[8] = {};
 	uint64_t launches = 0;
 	bool k2_smem_attr_set = false;
+	int32_t n_listeners_res = 0, n_areas_res = 0; // resident listeners / areas (gas_listeners_set / gas_areas_set)
+	// CUDA-graph capture
+	bool capturing = false;
+	uint64_t capture_launches0 = 0;
+	struct Graph {
+		cudaGraphExec_t exec = nullptr;
+		uint64_t kernels = 0;
+	};
+	std::vector<Graph> graphs;
+	// per-kernel timing
+	bool profiling = false;
+	struct ProfPair {
+		cudaEvent_t a, b;
+		int kind;
+	};
+	std::vector<ProfPair> prof_pairs;
+	size_t prof_used = 0;
+	double prof_ms[GAS_KERNEL_KINDS] = {};
+	uint64_t prof_n[GAS_KERNEL_KINDS] = {};
 	std::mutex mu;
 	std::string err;
 };

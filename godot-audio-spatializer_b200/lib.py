@@ -33,6 +33,14 @@ PROTOTYPES = {
     "gas_voice_init": (C.c_int, [_vp, _i32, _vp]),
     "gas_gain_compute": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp]),
     "gas_gain_compute_device": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp]),
+    "gas_listeners_set": (C.c_int, [_vp, _i32, _vp]),
+    "gas_areas_set": (C.c_int, [_vp, _i32, _vp]),
+    "gas_capture_begin": (C.c_int, [_vp]),
+    "gas_capture_end": (C.c_int, [_vp, C.POINTER(_i32)]),
+    "gas_graph_launch": (C.c_int, [_vp, _i32]),
+    "gas_graph_destroy": (C.c_int, [_vp, _i32]),
+    "gas_profile_enable": (C.c_int, [_vp, _i32]),
+    "gas_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "gas_params_set": (C.c_int, [_vp, _i32, _vp, _vp]),
     "gas_params_get": (C.c_int, [_vp, _i32, _vp, _vp]),
     "gas_effect_params_set": (C.c_int, [_vp, _i32, _vp, _vp]),

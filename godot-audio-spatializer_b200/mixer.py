@@ -125,11 +125,46 @@ class Mixer:
                                             0 if a is None else a.size, _ptr(a), _ptr(out)))
         return out
 
-    def gain_compute_device(self, n, d_emitters, listeners, areas=None, d_out_params=0):
-        l = _arr(listeners, abi.listener).reshape(-1)
+    def gain_compute_device(self, n, d_emitters, listeners=None, areas=None, d_out_params=0):
+        """Device-resident emitters; listeners/areas None => the resident copies (listeners_set/areas_set)."""
+        l = _arr(listeners, abi.listener).reshape(-1) if listeners is not None else None
         a = _arr(areas, abi.area).reshape(-1) if areas is not None else None
-        self._ck(self._lib.gas_gain_compute_device(self._ctx, int(n), C.c_void_p(d_emitters), l.size, _ptr(l),
+        self._ck(self._lib.gas_gain_compute_device(self._ctx, int(n), C.c_void_p(d_emitters), 0 if l is None else l.size, _ptr(l),
                                                    0 if a is None else a.size, _ptr(a), C.c_void_p(d_out_params)))
+
+    def listeners_set(self, listeners):
+        l = _arr(listeners, abi.listener).reshape(-1)
+        self._ck(self._lib.gas_listeners_set(self._ctx, l.size, _ptr(l)))
+
+    def areas_set(self, areas):
+        a = _arr(areas, abi.area).reshape(-1)
+        self._ck(self._lib.gas_areas_set(self._ctx, a.size, _ptr(a)))
+
+    # ---- CUDA-graph capture / per-kernel timing ---------------------------------------------------------
+    def capture_begin(self):
+        self._ck(self._lib.gas_capture_begin(self._ctx))
+
+    def capture_end(self):
+        g = C.c_int32(-1)
+        self._ck(self._lib.gas_capture_end(self._ctx, C.byref(g)))
+        return int(g.value)
+
+    def graph_launch(self, graph):
+        self._ck(self._lib.gas_graph_launch(self._ctx, int(graph)))
+
+    def graph_destroy(self, graph):
+        self._ck(self._lib.gas_graph_destroy(self._ctx, int(graph)))
+
+    def profile_enable(self, on=True):
+        self._ck(self._lib.gas_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """{kind: (total_ms, launches)} for prologue / mix_stream (K2) / mix_voice (K3)."""
+        ms = (C.c_double * 3)()
+        n = (C.c_uint64 * 3)()
+        self._ck(self._lib.gas_profile_read(self._ctx, ms, n))
+        names = ("prologue", "mix_stream", "mix_voice")
+        return {names[k]: (float(ms[k]), int(n[k])) for k in range(3)}
 
     def params_set(self, instances, params):
         """set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272, :558-564)."""

@@ -298,6 +298,11 @@ GAS_API int gas_gain_compute(gas_ctx *ctx, int32_t n, const gas_emitter *emitter
 GAS_API int gas_gain_compute_device(gas_ctx *ctx, int32_t n, const gas_emitter *d_emitters,
 		int32_t n_listeners, const gas_listener *listeners,
 		int32_t n_areas, const gas_area *areas, gas_params *d_out_params);
+/* Device-resident copies of the listeners / areas, used by gas_gain_compute_device when its
+ * `listeners` (resp. `areas`) argument is NULL.  Needed inside a captured graph, where host-to-device
+ * copies from pageable memory are not allowed. */
+GAS_API int gas_listeners_set(gas_ctx *ctx, int32_t n_listeners, const gas_listener *listeners);
+GAS_API int gas_areas_set(gas_ctx *ctx, int32_t n_areas, const gas_area *areas);
 /* Hand-off of parameters computed elsewhere (a custom _calculate_spatialization): the batched
  * set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272, :558-564).  Validation:
  * n_bus <= 6 (spatializer_parameters.cpp:35-47 sizes are fixed by the struct). */
@@ -334,8 +339,33 @@ GAS_API int gas_sync(gas_ctx *ctx);
  * (collectives, copies) in order with the mixer. */
 GAS_API void *gas_mix_stream(gas_ctx *ctx);
 GAS_API void *gas_gain_stream(gas_ctx *ctx);
-/* Number of kernels this library has launched on ctx since creation (evidence for bench.py). */
+/* Number of kernels this library has launched on ctx since creation (evidence for bench.py); graph
+ * replays count the kernels of the replayed graph. */
 GAS_API uint64_t gas_kernel_launches(const gas_ctx *ctx);
+
+/* ---- CUDA-graph capture of the device-resident path ------------------------------------------------
+ * Everything enqueued by gas_gain_compute_device (with resident listeners/areas) and
+ * gas_mix_block_device between gas_capture_begin and gas_capture_end is recorded into a CUDA graph
+ * instead of being executed; gas_graph_launch replays it on the mix stream.  One block is a handful of
+ * ~10 us kernels, so a caller that renders many blocks back to back (offline render, benchmarks)
+ * removes the per-launch host cost this way.  Other gas_* calls are not allowed while capturing. */
+GAS_API int gas_capture_begin(gas_ctx *ctx);
+GAS_API int gas_capture_end(gas_ctx *ctx, int32_t *out_graph);
+GAS_API int gas_graph_launch(gas_ctx *ctx, int32_t graph);
+GAS_API int gas_graph_destroy(gas_ctx *ctx, int32_t graph);
+
+/* ---- per-kernel timing (CUDA events on the launching stream) ----------------------------------------
+ * While enabled, every mix-side kernel launch outside a capture is bracketed by timing events.
+ * gas_profile_read synchronises and returns, per kernel kind, the summed duration in milliseconds and
+ * the number of launches since gas_profile_enable(ctx, 1). */
+typedef enum gas_kernel_kind {
+	GAS_KERNEL_PROLOGUE = 0, /* k_prologue_inst + k_prologue_voice */
+	GAS_KERNEL_MIX_STREAM = 1, /* K2 */
+	GAS_KERNEL_MIX_VOICE = 2,  /* K3 */
+	GAS_KERNEL_KINDS = 3
+} gas_kernel_kind;
+GAS_API int gas_profile_enable(gas_ctx *ctx, int32_t on);
+GAS_API int gas_profile_read(gas_ctx *ctx, double ms_out[GAS_KERNEL_KINDS], uint64_t launches_out[GAS_KERNEL_KINDS]);
 
 /* ---- persistent state (checkpoint / re-sharding; no reference analogue) ------------- */
 GAS_API int gas_voice_state_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_voice_state *out);

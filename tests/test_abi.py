@@ -1,0 +1,79 @@
+"""The C-ABI library loads, exports every symbol include/gas.h declares, agrees with the numpy record
+layouts, and refuses to run without a GPU (no CPU fallback).  No GPU needed."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gas.h")).read()
+    return sorted(set(re.findall(r"GAS_API\s+[\w\s\*]+?\b(gas_\w+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(gas):
+    declared = _declared_symbols()
+    assert len(declared) >= 35
+    lib = gas.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/gas.h but not exported by libgas_b200.so"
+    assert sorted(gas.PROTOTYPES) == declared, "lib.py PROTOTYPES must list exactly the header's entry points"
+
+
+def test_exports_are_c_abi_only(gas):
+    """Only gas_* symbols are exported (everything else is hidden), i.e. no C++/torch types cross the boundary."""
+    out = subprocess.check_output(["nm", "-D", "--defined-only", gas.LIB_PATH], text=True)
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert exported and all(s.startswith("gas_") for s in exported), [s for s in exported if not s.startswith("gas_")][:5]
+
+
+def test_record_layouts_match(gas, orc):
+    lib = gas.load()
+    gas.abi.check_layout(lib.gas_abi_sizeof, "libgas_b200.so")
+    gas.abi.check_layout(orc.load().orc_sizeof, "libgas_oracle.so")
+    assert lib.gas_abi_sizeof(999) == 0
+    assert lib.gas_abi_version() == 1
+
+
+def test_defaults_match_reference_headers(gas):
+    """AudioSpatializer3D defaults, reference audio_spatializer_3d.h:171-188."""
+    lib = gas.load()
+    import numpy as np
+    s = np.zeros(1, dtype=gas.abi.spatializer)
+    lib.gas_spatializer_defaults(ctypes.c_void_p(s.ctypes.data))
+    want = gas.abi.spatializer_defaults()
+    for f in ("attenuation_model", "unit_size", "max_distance", "panning_strength", "area_mask", "emission_angle_enabled",
+              "emission_angle", "emission_angle_filter_attenuation_db", "attenuation_filter_cutoff_hz", "attenuation_filter_db",
+              "doppler_tracking", "doppler_speed_of_sound", "mix_channel_mode", "effect_gain_binding"):
+        assert s[f][0] == want[f], f
+    assert s["unit_size"][0] == 10.0 and s["attenuation_filter_db"][0] == -24.0 and s["emission_angle"][0] == 45.0
+    assert s["doppler_speed_of_sound"][0] == 343.0 and s["mix_channel_mode"][0] == 0
+
+
+def test_no_cpu_fallback(gas):
+    """Without a usable B200 the product must fail loudly instead of computing on the CPU."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(gas.GasError) as e:
+        gas.Mixer()
+    assert e.value.status == gas.abi.ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package may mention it."""
+    pkg = os.path.join(ROOT, "godot-audio-spatializer_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp", ".cuh")) or f == "Makefile":
+                text = open(os.path.join(d, f), errors="ignore").read()
+                assert "gas_oracle" not in text and "orc_" not in text and "from oracle" not in text and "import oracle" not in text, os.path.join(d, f)
