@@ -138,13 +138,13 @@ void prof_close(gas_ctx *ctx, gas_ctx::ProfPair *p) {
 	}
 }
 
-int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_frame *d_src, int src_stride, int frames,
+int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_frame *d_src, int src_rows, int src_stride, int frames,
 		gas_frame *d_bus, gas_frame *d_peaks) {
 	if (ctx->gain_pending) {
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
 	}
 	gas_ctx::ProfPair *pp = prof_open(ctx, GAS_KERNEL_PROLOGUE);
-	GAS_CUDA(ctx, launch_prologue(ctx, n_voices, d_voices, frames, d_bus, d_peaks, ctx->s_mix));
+	GAS_CUDA(ctx, launch_prologue(ctx, n_voices, d_voices, src_rows, frames, d_bus, d_peaks, ctx->s_mix));
 	prof_close(ctx, pp);
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix));
 	ctx->prologue_pending = true;
@@ -280,13 +280,16 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->t.inst_was_further, I);
 	ALLOC(ctx->t.inst_active, I);
 	ALLOC(ctx->t.inst_cur, I);
-	ALLOC(ctx->t.inst_prev, I);
+	ALLOC(ctx->t.inst_prev, 2 * I);
+	ALLOC(ctx->t.inst_mode, I);
+	ALLOC(ctx->t.blk, (size_t)2);
+	ctx->t.max_instances = (int32_t)I;
 	ALLOC(ctx->t.inst_fx, I);
 	ALLOC(ctx->t.inst_sends, I);
 	ALLOC(ctx->t.vs_prev, V * 8);
 	ALLOC(ctx->t.vs_proc, V * 8);
 	ALLOC(ctx->t.vs_fx, V * (size_t)(GAS_MAX_EFFECTS * 2 * GAS_MAX_FILTER_STAGES * 4));
-	ALLOC(ctx->plan.cls, (size_t)GAS_MAX_CLASSES);
+	ALLOC(ctx->plan.cls, (size_t)2 * GAS_MAX_CLASSES);
 	ALLOC(ctx->plan.n_cls, (size_t)1);
 	ALLOC(ctx->plan.overflow, (size_t)1);
 	ALLOC(ctx->plan.k2_src, (size_t)GAS_MAX_CLASSES * V);
@@ -342,7 +345,7 @@ void gas_destroy(gas_ctx *ctx) {
 	}
 	gas_comm_close(ctx);
 	void *ptrs[] = { ctx->t.spat, ctx->t.inst_spat, ctx->t.inst_params, ctx->t.inst_was_further, ctx->t.inst_active, ctx->t.inst_cur,
-		ctx->t.inst_prev, ctx->t.inst_fx, ctx->t.inst_sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls, ctx->plan.n_cls,
+		ctx->t.inst_prev, ctx->t.inst_mode, ctx->t.blk, ctx->t.inst_fx, ctx->t.inst_sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls, ctx->plan.n_cls,
 		ctx->plan.overflow, ctx->plan.k2_src, ctx->plan.k2_rows, ctx->plan.k3_list, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
 		ctx->d_peaks, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
 		ctx->d_exchange };
@@ -695,7 +698,7 @@ int gas_mix_block(gas_ctx *ctx, int32_t n_voices, const gas_voice *voices, const
 		if (src_rows > 0) {
 			GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_src, src, (size_t)src_rows * frames * sizeof(gas_frame), cudaMemcpyHostToDevice, ctx->s_mix));
 		}
-		int st = mix_core(ctx, n_voices, ctx->d_voices, ctx->d_src, frames, frames, ctx->d_bus, peaks ? ctx->d_peaks : nullptr);
+		int st = mix_core(ctx, n_voices, ctx->d_voices, ctx->d_src, src_rows, frames, frames, ctx->d_bus, peaks ? ctx->d_peaks : nullptr);
 		if (st) {
 			return st;
 		}
@@ -714,7 +717,6 @@ int gas_mix_block(gas_ctx *ctx, int32_t n_voices, const gas_voice *voices, const
 int gas_mix_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices, const gas_frame *d_src, int32_t src_rows,
 		int32_t src_row_stride, int32_t frames, gas_frame *d_bus_out, gas_frame *d_peaks) {
 	ENTER(ctx);
-	(void)src_rows;
 	if (n_voices < 0 || n_voices > ctx->cfg.max_voices || (n_voices > 0 && (!d_voices || !d_src)) || !d_bus_out) {
 		return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_device: bad voice count or null pointer");
 	}
@@ -724,7 +726,7 @@ int gas_mix_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voic
 	if (((uintptr_t)d_src & 15u) || ((uintptr_t)d_bus_out & 15u)) {
 		return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_device: source and bus buffers must be 16-byte aligned");
 	}
-	return mix_core(ctx, n_voices, d_voices, d_src, src_row_stride, frames, d_bus_out, d_peaks);
+	return mix_core(ctx, n_voices, d_voices, d_src, src_rows, src_row_stride, frames, d_bus_out, d_peaks);
 }
 
 int gas_sync(gas_ctx *ctx) {

@@ -307,8 +307,7 @@ __device__ void push_bus_map(const gas_params &p, bool mix_channels, BusDetails 
 }
 
 __device__ __forceinline__ bool inst_mix_channels(const DevTables &t, int q) {
-	const gas_spatializer &s = t.spat[t.inst_spat[q]];
-	return s.kind == GAS_SPATIALIZER_3D && s.mix_channel_mode != 0;
+	return (t.inst_mode[q] & 0xff) == MODE_B;
 }
 
 // set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272)
@@ -504,7 +503,8 @@ __global__ void __launch_bounds__(128) k_instance_start(DevTables t, int n, cons
 			z.vol[k][c][0] = z.vol[k][c][1] = 0.f;
 		}
 	}
-	t.inst_prev[q] = z;
+	t.inst_prev[q] = z; // both parity buffers
+	t.inst_prev[t.max_instances + q] = z;
 	push_bus_map(t.inst_params[q], inst_mix_channels(t, q), t.inst_cur[q]);
 }
 

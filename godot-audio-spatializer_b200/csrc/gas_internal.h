@@ -74,7 +74,7 @@ struct VoiceRec {
 };
 
 struct BlockPlan {
-	ClassInfo *cls;      // [GAS_MAX_CLASSES]
+	ClassInfo *cls;      // [2][GAS_MAX_CLASSES]: by block parity; block n uses [n & 1], clears [(n + 1) & 1]
 	int32_t *n_cls;      // [1]
 	int32_t *overflow;   // [1] set when more than GAS_MAX_CLASSES classes were needed
 	int32_t *k2_src;     // [GAS_MAX_CLASSES][max_voices] source row per list position
@@ -90,7 +90,10 @@ struct DevTables {
 	int32_t *inst_was_further;
 	int32_t *inst_active;
 	BusDetails *inst_cur;
-	BusDetails *inst_prev;
+	BusDetails *inst_prev;   // [2][max_instances]: double-buffered by block parity (read [p], write [1-p])
+	int32_t *inst_mode;      // MODE_A/B/E | (effect_gain_binding + 1) << 8, latched at instantiate()
+	int32_t *blk;            // [0] block counter (parity of inst_prev), [1] CTA ticket of the prologue
+	int32_t max_instances;
 	gas_effect_chain *inst_fx;
 	InstSends *inst_sends;
 	float *vs_prev;              // [max_voices][4][2]
@@ -181,7 +184,7 @@ cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_list
 cudaError_t launch_params_set(gas_ctx *ctx, int n, const int32_t *d_ids, const gas_params *d_params, cudaStream_t st);
 cudaError_t launch_instance_start(gas_ctx *ctx, int n, const int32_t *d_ids, cudaStream_t st);
 // gas_prologue.cu
-cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int frames, gas_frame *d_bus,
+cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int src_rows, int frames, gas_frame *d_bus,
 		gas_frame *d_peaks, cudaStream_t st);
 // gas_mix_stream.cu (K2) / gas_mix_voice.cu (K3)
 cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, cudaStream_t st);

@@ -161,6 +161,36 @@ __device__ __forceinline__ void unit_iter_next(UnitIter &it, const ClassInfo *cl
 	it.remaining = 0;
 }
 
+// One warp-wide load of source-row indices: 32 consecutive list positions = 32/vb consecutive units of
+// one (class, tile).  `val` is the index of list position (first batch * vb + lane).
+struct IdxBlock {
+	int first_seq; // sequence number (within this CTA) of the first unit covered
+	int n_units;
+	int val;
+};
+
+__device__ __forceinline__ IdxBlock idx_block_load(UnitIter &pf, const ClassInfo *cls, const StreamCfg &cf, const int32_t *__restrict__ k2_src,
+		int maxv, int lane, int seq) {
+	IdxBlock b;
+	b.first_seq = seq;
+	b.n_units = 0;
+	b.val = 0;
+	if (pf.remaining <= 0) {
+		return b;
+	}
+	const int upb = 32 / cf.vb; // vb is 8, 16 or 32
+	const int n = min(upb, min(pf.nb - pf.batch, pf.remaining));
+	const int pos = pf.batch * cf.vb + lane;
+	if (lane < n * cf.vb && pos < cls[pf.cid].count) {
+		b.val = __ldg(k2_src + (size_t)pf.cid * maxv + pos);
+	}
+	b.n_units = n;
+	for (int i = 0; i < n; i++) {
+		unit_iter_next(pf, cls, cf);
+	}
+	return b;
+}
+
 struct ConsumerCtx {
 	const unsigned char *smem;
 	uint64_t *full;
@@ -284,7 +314,7 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, GlobalCfg g, StreamCfg cf,
-		const gas_frame *__restrict__ src, float *__restrict__ bus) {
+		const gas_frame *__restrict__ src, float *__restrict__ bus, const int32_t *__restrict__ blk) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ __align__(8) uint64_t s_full[kMaxStages];
@@ -296,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 	const int maxv = g.max_voices;
 
 	if (tid < GAS_MAX_CLASSES) {
-		s_cls[tid] = plan.cls[tid];
+		s_cls[tid] = plan.cls[((blk[0] + 1) & 1) * GAS_MAX_CLASSES + tid]; // the prologue already advanced the counter
 	}
 	if (tid == 0) {
 		for (int s = 0; s < cf.stages; s++) {
@@ -317,7 +347,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		// ===== producer =====
 		int stage = 0;
 		uint32_t phase = 0;
+		// Source-row indices are fetched one warp-wide load (32 list positions = 32/vb units) at a time,
+		// two blocks ahead of the copies that need them, so the gather indirection never stalls the ring.
+		UnitIter pf = it;
+		IdxBlock cur = idx_block_load(pf, s_cls, cf, plan.k2_src, maxv, lane, 0);
+		IdxBlock nxt = idx_block_load(pf, s_cls, cf, plan.k2_src, maxv, lane, cur.n_units);
+		int seq = 0;
 		while (it.remaining > 0) {
+			if (seq >= cur.first_seq + cur.n_units) {
+				cur = nxt;
+				nxt = idx_block_load(pf, s_cls, cf, plan.k2_src, maxv, lane, cur.first_seq + cur.n_units);
+			}
 			const ClassInfo &ci = s_cls[it.cid];
 			const int v0 = it.batch * cf.vb;
 			const int nv = min(cf.vb, ci.count - v0);
@@ -333,10 +373,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 				bulk_g2s(sw, plan.k2_rows + (size_t)it.cid * maxv * GAS_K2_ROW_FLOATS + (size_t)v0 * nf, w_bytes, &s_full[stage]);
 			}
 			__syncwarp();
-			for (int v = lane; v < nv; v += 32) {
-				const int row = plan.k2_src[(size_t)it.cid * maxv + v0 + v];
-				bulk_g2s(sx + (size_t)v * row_bytes, src + (size_t)row * cf.src_stride + (size_t)it.tile * kTileFrames, row_bytes, &s_full[stage]);
+			{
+				const int v = lane - (seq - cur.first_seq) * cf.vb; // this lane's voice inside the stage
+				if (v >= 0 && v < nv) {
+					bulk_g2s(sx + (size_t)v * row_bytes, src + (size_t)cur.val * cf.src_stride + (size_t)it.tile * kTileFrames, row_bytes,
+							&s_full[stage]);
+				}
 			}
+			seq++;
 			if (++stage == cf.stages) {
 				stage = 0;
 				phase ^= 1u;
@@ -392,7 +436,7 @@ static StreamCfg make_cfg(int frames, int src_stride, int smem_limit) {
 		cf.groups = 1;
 	}
 	int vb = 32768 / (cf.tile_frames * 8);
-	vb = vb < 8 ? 8 : (vb > 32 ? 32 : vb);
+	vb = vb >= 32 ? 32 : (vb >= 16 ? 16 : 8); // a divisor of the warp size (index prefetch blocks)
 	cf.vb = vb;
 	cf.x_bytes = vb * cf.tile_frames * 8;
 	cf.w_bytes = (vb * kMaxPairs * 8 + 127) & ~127;
@@ -416,7 +460,7 @@ cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stri
 		}
 		ctx->k2_smem_attr_set = true;
 	}
-	k_mix_stream<<<ctx->num_sms, kThreads, smem, st>>>(ctx->plan, ctx->g, cf, d_src, (float *)d_bus);
+	k_mix_stream<<<ctx->num_sms, kThreads, smem, st>>>(ctx->plan, ctx->g, cf, d_src, (float *)d_bus, ctx->t.blk);
 	ctx->launches++;
 	return cudaGetLastError();
 }

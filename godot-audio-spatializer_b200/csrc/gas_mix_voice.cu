@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_mix_voice(DevTables t, Gl
 		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks) {
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	if (threadIdx.x < GAS_MAX_CLASSES) {
-		s_cls[threadIdx.x] = plan.cls[threadIdx.x];
+		s_cls[threadIdx.x] = plan.cls[((t.blk[0] + 1) & 1) * GAS_MAX_CLASSES + threadIdx.x]; // the prologue already advanced the counter
 	}
 	__syncthreads();
 	const int warp_global = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);

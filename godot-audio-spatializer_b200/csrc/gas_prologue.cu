@@ -1,14 +1,16 @@
-// gas_prologue.cu — per-block prologue: turns the current parameters + persistent ramp state into the
-// block's plan (classes, weight rows, voice records) and advances the ramp state.
+// gas_prologue.cu — per-block prologue (one fused kernel): turns the current parameters + persistent ramp
+// state into the block's plan (classes, weight rows, voice records) and advances the ramp state.
 //
-//   k_prologue_inst  (one thread per instance): the AudioServer side of a mix step for the instance's
-//       proxy playbacks — previous volume looked up by bus, buses that disappeared fade to 0, then
-//       prev <- cur (upstream AudioServer::_mix_step).  Also zeroes the bus
-//       buffers / peaks and clears the class table.
-//   k_prologue_voice (one thread per voice): what process_frames / mix_channel decide before their
-//       sample loop (reference audio_spatializer_3d.cpp:499-523, :562-587, :537-551, :608): ramp end
-//       points, filter on/off, clear-history, target coefficients; classifies the voice and appends it
-//       to its class list.
+//   instance part (thread q < inst_hwm): the AudioServer side of a mix step for the instance's proxy
+//       playbacks — previous volume looked up by bus, buses that disappeared fade to 0, then prev <- cur
+//       (upstream AudioServer::_mix_step).  prev is double-buffered by block parity:
+//       this block reads inst_prev[p] and writes inst_prev[1-p], so the voice part of other threads can
+//       read the old value without a grid-wide barrier.
+//   voice part (thread j < n_voices): what process_frames / mix_channel decide before their sample loop
+//       (reference audio_spatializer_3d.cpp:499-523, :562-587, :537-551, :608): ramp end points, filter
+//       on/off, clear-history, target coefficients; classifies the voice and appends it to its class list.
+//   The kernel also zeroes the bus buffers / peaks, clears the class table of the NEXT block, and its
+//   last CTA advances the block counter.
 //
 // Compiled with -fmad=false (coefficient preparation is double arithmetic narrowed to float).
 #include "gas_internal.h"
@@ -19,104 +21,75 @@ __device__ __forceinline__ int resolve_bus(const GlobalCfg &g, int bus) {
 	return (bus >= 0 && bus < g.num_buses) ? bus : 0;
 }
 
-__global__ void __launch_bounds__(128) k_prologue_inst(DevTables t, GlobalCfg g, BlockPlan plan, int inst_hwm,
-		float4 *__restrict__ bus, int bus_f4, float2 *__restrict__ peaks, int n_voices) {
-	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-	const int nthreads = gridDim.x * blockDim.x;
-	for (int i = tid; i < bus_f4; i += nthreads) {
-		bus[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-	}
-	if (peaks) {
-		for (int i = tid; i < n_voices; i += nthreads) {
-			peaks[i] = make_float2(0.f, 0.f);
+// Sends of one instance for this block: every bus of the current details with the previous volume
+// looked up by bus (absent => 0 => fade-in), then buses only present in the previous details once more
+// towards 0 (fade-out); ascending by bus so that a class is identified by its bus mask.
+__device__ void resolve_sends(const BusDetails &cur, const BusDetails &prev, const GlobalCfg &g, InstSends &s) {
+	s.n = 0;
+	s.mask = 0;
+	for (int k = 0; k < cur.n; k++) {
+		int pk = -1;
+		for (int j = 0; j < prev.n; j++) {
+			if (prev.bus[j] == cur.bus[k]) {
+				pk = j;
+			}
+		}
+		const int slot = s.n++;
+		s.bus[slot] = resolve_bus(g, cur.bus[k]);
+		for (int c = 0; c < 4; c++) {
+			for (int x = 0; x < 2; x++) {
+				s.vp[slot][c][x] = pk >= 0 ? prev.vol[pk][c][x] : 0.f;
+				s.vn[slot][c][x] = cur.vol[k][c][x];
+			}
 		}
 	}
-	if (tid < GAS_MAX_CLASSES) {
-		ClassInfo z{};
-		plan.cls[tid] = z;
-	}
-	if (tid == 0) {
-		*plan.n_cls = 0;
-		*plan.overflow = 0;
-	}
-	for (int q = tid; q < inst_hwm; q += nthreads) {
-		if (!t.inst_active[q]) {
+	for (int j = 0; j < prev.n; j++) {
+		bool still = false;
+		for (int k = 0; k < cur.n; k++) {
+			still |= (cur.bus[k] == prev.bus[j]);
+		}
+		if (still) {
 			continue;
 		}
-		const BusDetails cur = t.inst_cur[q];
-		const BusDetails prev = t.inst_prev[q];
-		InstSends s;
-		s.n = 0;
-		s.mask = 0;
-		// every bus of the current details, previous volume by bus (absent => 0 => fade-in)
-		for (int k = 0; k < cur.n; k++) {
-			int b = resolve_bus(g, cur.bus[k]);
-			int pk = -1;
-			for (int j = 0; j < prev.n; j++) {
-				if (prev.bus[j] == cur.bus[k]) {
-					pk = j;
-				}
+		const int slot = s.n++;
+		s.bus[slot] = resolve_bus(g, prev.bus[j]);
+		for (int c = 0; c < 4; c++) {
+			for (int x = 0; x < 2; x++) {
+				s.vp[slot][c][x] = prev.vol[j][c][x];
+				s.vn[slot][c][x] = 0.f;
 			}
-			int slot = s.n++;
-			s.bus[slot] = b;
+		}
+	}
+	for (int a = 1; a < s.n; a++) { // insertion sort, <= 12 entries
+		for (int b = a; b > 0 && s.bus[b - 1] > s.bus[b]; b--) {
+			const int tb = s.bus[b];
+			s.bus[b] = s.bus[b - 1];
+			s.bus[b - 1] = tb;
 			for (int c = 0; c < 4; c++) {
 				for (int x = 0; x < 2; x++) {
-					s.vp[slot][c][x] = pk >= 0 ? prev.vol[pk][c][x] : 0.f;
-					s.vn[slot][c][x] = cur.vol[k][c][x];
+					const float tp = s.vp[b][c][x], tn = s.vn[b][c][x];
+					s.vp[b][c][x] = s.vp[b - 1][c][x];
+					s.vn[b][c][x] = s.vn[b - 1][c][x];
+					s.vp[b - 1][c][x] = tp;
+					s.vn[b - 1][c][x] = tn;
 				}
 			}
 		}
-		// buses only present in the previous details: once more towards 0 (fade-out)
-		for (int j = 0; j < prev.n; j++) {
-			bool still = false;
-			for (int k = 0; k < cur.n; k++) {
-				still |= (cur.bus[k] == prev.bus[j]);
-			}
-			if (still) {
-				continue;
-			}
-			int slot = s.n++;
-			s.bus[slot] = resolve_bus(g, prev.bus[j]);
-			for (int c = 0; c < 4; c++) {
-				for (int x = 0; x < 2; x++) {
-					s.vp[slot][c][x] = prev.vol[j][c][x];
-					s.vn[slot][c][x] = 0.f;
-				}
-			}
+	}
+	for (int k = 0; k < s.n; k++) {
+		s.mask |= 1u << s.bus[k];
+	}
+}
+
+// only the first `n` entries of a BusDetails are meaningful: load just those
+__device__ __forceinline__ void details_load(BusDetails &d, const BusDetails *src) {
+	d.n = src->n;
+	for (int k = 0; k < d.n && k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+		d.bus[k] = src->bus[k];
+		for (int c = 0; c < 4; c++) {
+			d.vol[k][c][0] = src->vol[k][c][0];
+			d.vol[k][c][1] = src->vol[k][c][1];
 		}
-		// ascending by bus (insertion sort, <= 12 entries) so that a class is identified by its bus mask
-		for (int a = 1; a < s.n; a++) {
-			for (int b = a; b > 0 && s.bus[b - 1] > s.bus[b]; b--) {
-				int tb = s.bus[b];
-				s.bus[b] = s.bus[b - 1];
-				s.bus[b - 1] = tb;
-				for (int c = 0; c < 4; c++) {
-					for (int x = 0; x < 2; x++) {
-						float tp = s.vp[b][c][x], tn = s.vn[b][c][x];
-						s.vp[b][c][x] = s.vp[b - 1][c][x];
-						s.vn[b][c][x] = s.vn[b - 1][c][x];
-						s.vp[b - 1][c][x] = tp;
-						s.vn[b - 1][c][x] = tn;
-					}
-				}
-			}
-		}
-		for (int k = 0; k < s.n; k++) {
-			s.mask |= 1u << s.bus[k];
-		}
-		InstSends *dst = &t.inst_sends[q];
-		dst->n = s.n;
-		dst->mask = s.mask;
-		for (int k = 0; k < s.n; k++) {
-			dst->bus[k] = s.bus[k];
-			for (int c = 0; c < 4; c++) {
-				for (int x = 0; x < 2; x++) {
-					dst->vp[k][c][x] = s.vp[k][c][x];
-					dst->vn[k][c][x] = s.vn[k][c][x];
-				}
-			}
-		}
-		t.inst_prev[q] = cur; // prev <- cur
 	}
 }
 
@@ -252,13 +225,68 @@ __device__ int class_find_or_insert(ClassInfo *cls, unsigned long long key, int 
 	return -1;
 }
 
-__global__ void __launch_bounds__(128) k_prologue_voice(DevTables t, GlobalCfg g, BlockPlan plan, int n_voices,
-		const gas_voice *__restrict__ voices) {
-	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+
+__global__ void __launch_bounds__(128) k_prologue(DevTables t, GlobalCfg g, BlockPlan plan, int inst_hwm, int n_voices,
+		const gas_voice *__restrict__ voices, int src_rows, float4 *__restrict__ bus, int bus_f4, float2 *__restrict__ peaks) {
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int nthreads = gridDim.x * blockDim.x;
 	const unsigned lane = threadIdx.x & 31u;
 	const int C = g.channels;
 	const int maxv = g.max_voices;
+	const int parity = t.blk[0] & 1;
+	ClassInfo *cls = plan.cls + parity * GAS_MAX_CLASSES;
+	const BusDetails *prev_rd = t.inst_prev + (size_t)parity * t.max_instances;
+	BusDetails *prev_wr = t.inst_prev + (size_t)(parity ^ 1) * t.max_instances;
 
+	// ---- housekeeping -------------------------------------------------------------------------------
+	for (int i = tid; i < bus_f4; i += nthreads) {
+		bus[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+	if (peaks) {
+		for (int i = tid; i < n_voices; i += nthreads) {
+			peaks[i] = make_float2(0.f, 0.f);
+		}
+	}
+	if (tid < GAS_MAX_CLASSES) { // class table of the next block
+		ClassInfo z{};
+		plan.cls[(parity ^ 1) * GAS_MAX_CLASSES + tid] = z;
+	}
+
+	// ---- instance part ----------------------------------------------------------------------------------
+	for (int q = tid; q < inst_hwm; q += nthreads) {
+		if (!t.inst_active[q]) {
+			continue;
+		}
+		BusDetails cur, prev;
+		details_load(cur, &t.inst_cur[q]);
+		details_load(prev, &prev_rd[q]);
+		InstSends s;
+		resolve_sends(cur, prev, g, s);
+		InstSends *dst = &t.inst_sends[q]; // read by the voice-parallel kernel
+		dst->n = s.n;
+		dst->mask = s.mask;
+		for (int k = 0; k < s.n; k++) {
+			dst->bus[k] = s.bus[k];
+			for (int c = 0; c < 4; c++) {
+				for (int x = 0; x < 2; x++) {
+					dst->vp[k][c][x] = s.vp[k][c][x];
+					dst->vn[k][c][x] = s.vn[k][c][x];
+				}
+			}
+		}
+		BusDetails *pw = &prev_wr[q]; // prev <- cur
+		pw->n = cur.n;
+		for (int k = 0; k < cur.n; k++) {
+			pw->bus[k] = cur.bus[k];
+			for (int c = 0; c < 4; c++) {
+				pw->vol[k][c][0] = cur.vol[k][c][0];
+				pw->vol[k][c][1] = cur.vol[k][c][1];
+			}
+		}
+	}
+
+	// ---- voice part ----------------------------------------------------------------------------------------
+	const int j = tid;
 	int path = PATH_NONE, mode = MODE_A, n_send = 0, n_group = 0, n_rows = 0;
 	uint32_t cflags = 0, mask = 0;
 	float rows[GAS_K2_ROW_FLOATS];
@@ -269,15 +297,25 @@ __global__ void __launch_bounds__(128) k_prologue_voice(DevTables t, GlobalCfg g
 	if (j < n_voices) {
 		v = voices[j];
 		live = v.voice >= 0 && v.voice < maxv && v.instance >= 0 && v.instance < g.max_instances && t.inst_active[v.instance] != 0;
+		if (v.src_row >= src_rows) {
+			v.src_row = -1;
+		}
 	}
 	if (live) {
 		const int q = v.instance;
-		const gas_spatializer *sp = &t.spat[t.inst_spat[q]];
+		const int imode = t.inst_mode[q];
 		const gas_params *prm = &t.inst_params[q];
-		const InstSends *snd = &t.inst_sends[q];
-		mode = sp->kind == GAS_SPATIALIZER_EFFECT ? MODE_E : (sp->mix_channel_mode ? MODE_B : MODE_A);
-		n_send = snd->n;
-		mask = snd->mask;
+		mode = imode & 0xff;
+		const int fx_binding = (imode >> 8) - 1;
+		InstSends snd;
+		{
+			BusDetails cur, prev;
+			details_load(cur, &t.inst_cur[q]);
+			details_load(prev, &prev_rd[q]);
+			resolve_sends(cur, prev, g, snd);
+		}
+		n_send = snd.n;
+		mask = snd.mask;
 		const float lin_att = prm->linear_attenuation;
 		const bool filt = mode != MODE_E && (double)lin_att >= 0.001; // audio_spatializer_3d.cpp:503, :568
 		const bool want_peak = (v.flags & GAS_VOICE_WANT_PEAK) != 0;
@@ -334,7 +372,7 @@ __global__ void __launch_bounds__(128) k_prologue_voice(DevTables t, GlobalCfg g
 			rec.n_fx = nfx;
 			for (int e = 0; e < nfx; e++) {
 				gas_effect ef = fx->effects[e];
-				if (sp->effect_gain_binding == e) {
+				if (fx_binding == e) {
 					ef.gain = lin_att; // example _process_effects (gd_spatializer_instance.gd:125-127)
 				}
 				int st = ef.stages < 1 ? 1 : (ef.stages > GAS_MAX_FILTER_STAGES ? GAS_MAX_FILTER_STAGES : ef.stages);
@@ -348,16 +386,15 @@ __global__ void __launch_bounds__(128) k_prologue_voice(DevTables t, GlobalCfg g
 		// (vn*t + (1-t)*vp) of the AudioServer ramp times (m_new*t + (1-t)*m_prev) of mix_channel.
 		bool lin = true, shared = n_send >= 2, streamed = false;
 		if (!has_dsp && !want_peak && n_send >= 1) {
-			// first pass: linearity / sharing
 			for (int k = 0; k < n_send; k++) {
 				for (int c = 0; c < C; c++) {
 					for (int x = 0; x < 2; x++) {
-						float dn = snd->vn[k][c][x] - snd->vp[k][c][x];
-						float dm = rec.m_new[c][x] - rec.m_prev[c][x];
+						const float dn = snd.vn[k][c][x] - snd.vp[k][c][x];
+						const float dm = rec.m_new[c][x] - rec.m_prev[c][x];
 						if (dn * dm != 0.f) {
 							lin = false;
 						}
-						if (snd->vn[k][c][x] != snd->vn[0][c][x] || snd->vp[k][c][x] != snd->vp[0][c][x]) {
+						if (snd.vn[k][c][x] != snd.vn[0][c][x] || snd.vp[k][c][x] != snd.vp[0][c][x]) {
 							shared = false;
 						}
 					}
@@ -378,8 +415,8 @@ __global__ void __launch_bounds__(128) k_prologue_voice(DevTables t, GlobalCfg g
 				for (int k = 0; k < n_group; k++) {
 					for (int c = 0; c < C; c++) {
 						for (int x = 0; x < 2; x++) {
-							float np = snd->vp[k][c][x], dn = snd->vn[k][c][x] - np;
-							float mp = rec.m_prev[c][x], dm = rec.m_new[c][x] - mp;
+							const float np = snd.vp[k][c][x], dn = snd.vn[k][c][x] - np;
+							const float mp = rec.m_prev[c][x], dm = rec.m_new[c][x] - mp;
 							rows[((k * P + 0) * C + c) * 2 + x] = np * mp;
 							rows[((k * P + 1) * C + c) * 2 + x] = np * dm + dn * mp;
 							if (!lin) {
@@ -415,9 +452,9 @@ __global__ void __launch_bounds__(128) k_prologue_voice(DevTables t, GlobalCfg g
 	const int leader = __ffs(peers) - 1;
 	int cid = -1, base = 0;
 	if (key != 0ULL && (int)lane == leader) {
-		cid = class_find_or_insert(plan.cls, key, plan.overflow);
+		cid = class_find_or_insert(cls, key, plan.overflow);
 		if (cid >= 0) {
-			ClassInfo *ci = &plan.cls[cid];
+			ClassInfo *ci = &cls[cid];
 			ci->path = path;
 			ci->mode = mode;
 			ci->flags = cflags;
@@ -430,39 +467,43 @@ __global__ void __launch_bounds__(128) k_prologue_voice(DevTables t, GlobalCfg g
 	}
 	cid = __shfl_sync(0xffffffffu, cid, leader);
 	base = __shfl_sync(0xffffffffu, base, leader);
-	if (key == 0ULL || cid < 0) {
-		return;
-	}
-	const int pos = base + __popc(peers & ((1u << lane) - 1u));
-	if (path == PATH_STREAM) {
-		plan.k2_src[(size_t)cid * maxv + pos] = v.src_row;
-		const int nf = n_rows * C * 2;
-		float *dst = plan.k2_rows + (size_t)cid * maxv * GAS_K2_ROW_FLOATS + (size_t)pos * nf;
-		for (int i = 0; i < nf; i++) {
-			dst[i] = rows[i];
+	if (key != 0ULL && cid >= 0) {
+		const int pos = base + __popc(peers & ((1u << lane) - 1u));
+		if (path == PATH_STREAM) {
+			plan.k2_src[(size_t)cid * maxv + pos] = v.src_row;
+			const int nf = n_rows * C * 2;
+			float *dst = plan.k2_rows + (size_t)cid * maxv * GAS_K2_ROW_FLOATS + (size_t)pos * nf;
+			for (int i = 0; i < nf; i++) {
+				dst[i] = rows[i];
+			}
+		} else {
+			plan.k3_list[(size_t)cid * maxv + pos] = j;
+			plan.rec[j] = rec;
 		}
-	} else {
-		plan.k3_list[(size_t)cid * maxv + pos] = j;
-		plan.rec[j] = rec;
+	}
+
+	// ---- the last CTA to finish advances the block counter (every CTA has read it by then) ----------------
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		const int ticket = atomicAdd(&t.blk[1], 1);
+		if (ticket == (int)gridDim.x - 1) {
+			t.blk[1] = 0;
+			t.blk[0] = t.blk[0] + 1;
+		}
 	}
 }
 
 } // namespace
 
-cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int frames, gas_frame *d_bus,
+cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int src_rows, int frames, gas_frame *d_bus,
 		gas_frame *d_peaks, cudaStream_t st) {
 	const int bus_f4 = ctx->g.num_buses * ctx->g.channels * frames / 2;
-	int work = ctx->inst_hwm > bus_f4 ? ctx->inst_hwm : bus_f4;
-	work = work > n_voices ? work : n_voices;
+	int work = ctx->inst_hwm > n_voices ? ctx->inst_hwm : n_voices;
+	work = work > GAS_MAX_CLASSES ? work : GAS_MAX_CLASSES;
 	int blocks = (work + 127) / 128;
-	blocks = blocks < 1 ? 1 : (blocks > 4 * ctx->num_sms ? 4 * ctx->num_sms : blocks);
-	k_prologue_inst<<<blocks, 128, 0, st>>>(ctx->t, ctx->g, ctx->plan, ctx->inst_hwm, (float4 *)d_bus, bus_f4, (float2 *)d_peaks, n_voices);
-	ctx->launches++;
-	cudaError_t e = cudaGetLastError();
-	if (e != cudaSuccess || n_voices <= 0) {
-		return e;
-	}
-	k_prologue_voice<<<(n_voices + 127) / 128, 128, 0, st>>>(ctx->t, ctx->g, ctx->plan, n_voices, d_voices);
+	k_prologue<<<blocks, 128, 0, st>>>(ctx->t, ctx->g, ctx->plan, ctx->inst_hwm, n_voices, d_voices, src_rows, (float4 *)d_bus, bus_f4,
+			(float2 *)d_peaks);
 	ctx->launches++;
 	return cudaGetLastError();
 }

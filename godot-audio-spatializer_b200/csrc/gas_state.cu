@@ -37,6 +37,12 @@ __device__ void instance_reset(DevTables &t, int q, int spat) {
 	t.inst_active[q] = 0;
 	details_clear(t.inst_cur[q]);
 	details_clear(t.inst_prev[q]);
+	details_clear(t.inst_prev[t.max_instances + q]);
+	{ // kind / mix_channel_mode / effect binding are latched at instantiate() (reference audio_spatializer_3d.cpp:645-652)
+		const gas_spatializer &s = t.spat[spat];
+		const int mode = s.kind == GAS_SPATIALIZER_EFFECT ? MODE_E : (s.mix_channel_mode ? MODE_B : MODE_A);
+		t.inst_mode[q] = mode | ((s.effect_gain_binding + 1) << 8);
+	}
 	t.inst_fx[q] = t.spat[spat].chain;
 	t.inst_sends[q].n = 0;
 	t.inst_sends[q].mask = 0;
@@ -83,6 +89,8 @@ __global__ void k_defaults(DevTables t, GlobalCfg g) {
 		t.inst_active[q] = 0;
 		details_clear(t.inst_cur[q]);
 		details_clear(t.inst_prev[q]);
+		details_clear(t.inst_prev[t.max_instances + q]);
+		t.inst_mode[q] = MODE_A;
 		t.inst_fx[q].n_effects = 0;
 		t.inst_sends[q].n = 0;
 		t.inst_sends[q].mask = 0;

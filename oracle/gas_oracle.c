@@ -687,6 +687,8 @@ typedef struct bus_details { /* upstream AudioStreamPlaybackBusDetails, shared b
 
 typedef struct orc_instance {
 	int spatializer;
+	/* latched by AudioSpatializer3D::instantiate (audio_spatializer_3d.cpp:645-652: ins->mix_channel_mode = mix_channel_mode) */
+	int kind, mix_channel_mode, effect_gain_binding;
 	gas_params params;
 	int was_further;
 	int active; /* playback_active: proxies registered with AudioServer */
@@ -818,8 +820,8 @@ int orc_spatializer_set(orc_world *w, int slot, const gas_spatializer *s) {
 }
 
 static int inst_mix_channels(const orc_world *w, const orc_instance *q) {
-	const gas_spatializer *s = &w->spat[q->spatializer];
-	return s->kind == GAS_SPATIALIZER_3D && s->mix_channel_mode;
+	(void)w;
+	return q->kind == GAS_SPATIALIZER_3D && q->mix_channel_mode;
 }
 
 /* get_bus_map for every proxy channel folded into one table: entry [bus][c] is what proxy c (Mode B)
@@ -863,6 +865,9 @@ int orc_instance_init(orc_world *w, int n, const int32_t *instances, const int32
 		orc_instance *q = &w->inst[instances[i]];
 		memset(q, 0, sizeof(*q));
 		q->spatializer = spatializers[i];
+		q->kind = w->spat[q->spatializer].kind;
+		q->mix_channel_mode = w->spat[q->spatializer].mix_channel_mode;
+		q->effect_gain_binding = w->spat[q->spatializer].effect_gain_binding;
 		params_defaults(&q->params);
 		q->fx = w->spat[q->spatializer].chain;
 	}
@@ -1031,15 +1036,15 @@ static int details_find(const bus_details *d, int bus) {
 static void mix_instance(orc_world *w, int qi, const gas_voice *voices, const int *idx, int nv, const gas_frame *src, int frames,
 		gas_frame *bus, gas_frame *peaks, double *bus64, scratch *sc) {
 	orc_instance *q = &w->inst[qi];
-	const gas_spatializer *sp = &w->spat[q->spatializer];
+	const int kind = q->kind; /* latched at instantiate() */
 	const int channels = w->cfg.speaker_mode + 1;
 	const int mix_channels = inst_mix_channels(w, q);                    /* should_mix_channels */
 	const int count = mix_channels ? channels : 1;                       /* init_channels_and_buffers, audio_spatializer.cpp:172-179 */
 	const float mix_rate = w->cfg.mix_rate;
 	const gas_params *prm = &q->params;                                  /* :328 */
 	gas_effect_chain fx = q->fx;
-	if (sp->kind == GAS_SPATIALIZER_EFFECT && sp->effect_gain_binding >= 0 && sp->effect_gain_binding < fx.n_effects) {
-		fx.effects[sp->effect_gain_binding].gain = prm->linear_attenuation; /* example _process_effects, gd_spatializer_instance.gd:125-127 */
+	if (kind == GAS_SPATIALIZER_EFFECT && q->effect_gain_binding >= 0 && q->effect_gain_binding < fx.n_effects) {
+		fx.effects[q->effect_gain_binding].gain = prm->linear_attenuation; /* example _process_effects, gd_spatializer_instance.gd:125-127 */
 	}
 
 	for (int c = 0; c < count; c++) { /* :335-343 */
@@ -1062,7 +1067,7 @@ static void mix_instance(orc_world *w, int qi, const gas_voice *voices, const in
 		const gas_frame *processed = buf;
 		const frame64 *processed64 = sc->src64;
 		if (!mix_channels) { /* should_process_frames: Mode A and Effect, :411-417 */
-			if (sp->kind == GAS_SPATIALIZER_EFFECT) {
+			if (kind == GAS_SPATIALIZER_EFFECT) {
 				process_frames_effect_f32(&fx, st, mix_rate, sc->process, buf, frames);
 				if (bus64) {
 					process_frames_effect_f64(&fx, st64, mix_rate, sc->process64, sc->src64, frames);
