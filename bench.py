@@ -301,6 +301,8 @@ def gpu_arm(args):
         w["voices"] = args.voices
     if args.frames:
         w["frames"] = args.frames
+    if args.area_fraction is not None:
+        w["area_fraction"] = args.area_fraction
     V, F, C, B = w["voices"], w["frames"], w["speaker_mode"] + 1, w["num_buses"]
     K, W = args.steps, max(3, args.warmup)
 
@@ -456,6 +458,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--area-fraction", type=float, default=None, help="fraction of voices inside the reverb area (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

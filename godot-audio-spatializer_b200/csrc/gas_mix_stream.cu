@@ -21,6 +21,8 @@
 // reductions (red.global.add.v4.f32).  No per-voice state is written here.
 #include "gas_internal.h"
 
+#include <stdlib.h>
+
 #ifndef GAS_USE_FFMA2
 #define GAS_USE_FFMA2 1
 #endif
@@ -46,6 +48,7 @@ struct StreamCfg {
 	int x_bytes;       // per stage
 	int w_bytes;       // per stage
 	int stage_bytes;
+	int debug;         // GAS_K2_DEBUG bits (experiments only): 1 = skip the bus reductions, 2 = skip the FMAs
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------
@@ -224,7 +227,7 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		const unsigned char *sx = cc.smem + (size_t)cc.stage * cf.stage_bytes;
 		const unsigned char *sw = sx + cf.x_bytes;
 		mbar_wait(&cc.full[cc.stage], cc.phase);
-		if (mine) {
+		if (mine && !(cf.debug & 2)) {
 			for (int v = cc.group; v < nv; v += cf.groups) {
 				const float4 x = *reinterpret_cast<const float4 *>(sx + (size_t)v * row_bytes + cc.slot * 16);
 				const float2 x0 = make_float2(x.x, x.y), x1 = make_float2(x.z, x.w);
@@ -260,7 +263,7 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		unit_iter_next(it, cc.cls, cf);
 	} while (it.remaining > 0 && it.cid == cid && it.tile == tile);
 
-	if (!mine) {
+	if (!mine || (cf.debug & 1)) {
 		return;
 	}
 	// ---- flush: bus[b][c][i] += A + B t (+ C t^2), rows ordered [group][poly][pair] --------------------
@@ -443,6 +446,15 @@ static StreamCfg make_cfg(int frames, int src_stride, int smem_limit) {
 	cf.stage_bytes = cf.x_bytes + cf.w_bytes;
 	int stages = smem_limit / cf.stage_bytes;
 	cf.stages = stages > kMaxStages ? kMaxStages : stages;
+	if (const char *e = getenv("GAS_K2_STAGES")) {
+		int v = atoi(e);
+		if (v >= 2 && v <= cf.stages) {
+			cf.stages = v;
+		}
+	}
+	if (const char *e = getenv("GAS_K2_DEBUG")) {
+		cf.debug = atoi(e);
+	}
 	return cf;
 }
 
