@@ -238,11 +238,14 @@ class DeviceWorkload:
         self.mixer.sync()
 
     def step_device(self, k):
+        """One step = mix of block k (audio side) with, beside it, the gain computation for block k+1 (physics
+        side): the reference runs the two on different threads with a double-buffered parameter hand-off
+        (audio_spatializer.cpp:558-574); here they are the mix stream and the gain stream of the context."""
         m, w = self.mixer, self.w
         s = k % N_SETS
-        m.gain_compute_device(w["voices"], self.d_emitters[s].data_ptr())
         m.mix_block_device(w["voices"], self.d_voices.data_ptr(), self.d_src[s].data_ptr(), w["voices"], w["frames"], w["frames"],
                            self.d_bus[k % 2].data_ptr())
+        m.gain_compute_device(w["voices"], self.d_emitters[(s + 1) % N_SETS].data_ptr())
         return self.d_bus[k % 2]
 
     def capture_steps(self):
@@ -436,7 +439,9 @@ def gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(w), "voices_per_gpu": V, "frames": F, "channel_pairs": C, "buses": B,
                        "l2": f"{N_SETS} distinct source sets of {V * F * 8 / 2**20:.0f} MiB rotated (> 4x L2)",
-                       "launch": "CUDA-graph replay of gas_gain_compute_device + gas_mix_block_device, one graph per step",
+                       "launch": "CUDA-graph replay of gas_mix_block_device (block k) with gas_gain_compute_device (parameters of block "
+                                 "k+1) beside it on the gain stream, one graph per step",
+                       "pdl": os.environ.get("GAS_PDL", "0"),
                        "reduce": "torch.distributed all_reduce (NCCL) of the partial bus buffers" if world > 1 else "none (1 GPU)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
             "parity": parity,

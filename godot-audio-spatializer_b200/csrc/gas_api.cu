@@ -4,7 +4,9 @@
 #include "gas_internal.h"
 
 #include <stdarg.h>
+#include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -36,6 +38,33 @@ cudaError_t dev_alloc(T **p, size_t n) {
 	return e;
 }
 
+// SpeakerPlacementConfiguration::update_speaker_configuration (reference audio_spatializer_3d.cpp:903-916) with
+// the speaker set of :47-55.  Every operation is a separately rounded IEEE float/double operation (volatile
+// keeps the host compiler from contracting), so the values are bit-identical to a device evaluation.
+void spcap_constants(int speaker_mode, float dir[7][3], float eff[7]) {
+	static const float raw[7][3] = { { -1, 0, -1 }, { 1, 0, -1 }, { 0, 0, -1 }, { -1, 0, 1 }, { 1, 0, 1 }, { -1, 0, 0 }, { 1, 0, 0 } };
+	const int count = speaker_mode == GAS_SPEAKER_SURROUND_31 ? 3 : (speaker_mode == GAS_SPEAKER_SURROUND_51 ? 5 : (speaker_mode == GAS_SPEAKER_SURROUND_71 ? 7 : 2));
+	for (int i = 0; i < 7; i++) { // Vector3::normalized
+		volatile float xx = raw[i][0] * raw[i][0], yy = raw[i][1] * raw[i][1], zz = raw[i][2] * raw[i][2];
+		volatile float l2 = xx + yy;
+		l2 = l2 + zz;
+		volatile float len = sqrtf(l2);
+		for (int k = 0; k < 3; k++) {
+			dir[i][k] = l2 == 0.0f ? 0.0f : raw[i][k] / len;
+		}
+		eff[i] = 0.f;
+	}
+	for (int i = 0; i < count; i++) {
+		for (int j = 0; j < count; j++) {
+			volatile float a = dir[i][0] * dir[j][0], b = dir[i][1] * dir[j][1], c = dir[i][2] * dir[j][2];
+			volatile float d = a + b;
+			d = d + c;
+			volatile double term = 0.5 * (1.0 + (double)d);
+			eff[i] = (float)((double)eff[i] + term);
+		}
+	}
+}
+
 void refresh_globals(gas_ctx *ctx) {
 	ctx->g.speaker_mode = ctx->cfg.speaker_mode;
 	ctx->g.channels = ctx->cfg.speaker_mode + 1;
@@ -45,6 +74,7 @@ void refresh_globals(gas_ctx *ctx) {
 	ctx->g.max_instances = ctx->cfg.max_instances;
 	ctx->g.max_voices = ctx->cfg.max_voices;
 	ctx->g.max_spatializers = ctx->cfg.max_spatializers;
+	spcap_constants(ctx->g.speaker_mode, ctx->g.spk_dir, ctx->g.spk_eff);
 }
 
 // Stream ordering between the gain side and the mix side (the reference's physics / audio threads):
@@ -144,16 +174,24 @@ int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_fr
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
 	}
 	gas_ctx::ProfPair *pp = prof_open(ctx, GAS_KERNEL_PROLOGUE);
-	GAS_CUDA(ctx, launch_prologue(ctx, n_voices, d_voices, src_rows, frames, d_bus, d_peaks, ctx->s_mix));
+	if (!(ctx->skip & 1)) {
+		GAS_CUDA(ctx, launch_prologue(ctx, n_voices, d_voices, src_rows, frames, d_bus, d_peaks, ctx->s_mix));
+	}
 	prof_close(ctx, pp);
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix));
 	ctx->prologue_pending = true;
 	if (n_voices > 0) {
+		// streaming kernel (partial sums into the replica buffers), then the voice-parallel kernel, whose launch
+		// also folds the replicas into the bus buffers
 		pp = prof_open(ctx, GAS_KERNEL_MIX_STREAM);
-		GAS_CUDA(ctx, launch_mix_stream(ctx, d_src, src_stride, frames, d_bus, ctx->s_mix));
+		if (!(ctx->skip & 2)) {
+			GAS_CUDA(ctx, launch_mix_stream(ctx, d_src, src_stride, frames, d_bus, ctx->s_mix));
+		}
 		prof_close(ctx, pp);
 		pp = prof_open(ctx, GAS_KERNEL_MIX_VOICE);
-		GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_mix));
+		if (!(ctx->skip & 4)) {
+			GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_mix));
+		}
 		prof_close(ctx, pp);
 	}
 	return GAS_OK;
@@ -264,6 +302,15 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ctx->num_sms = prop.multiProcessorCount;
 	ctx->l2_bytes = prop.l2CacheSize;
 	refresh_globals(ctx);
+	{
+		const char *e = getenv("GAS_PDL");
+		ctx->pdl = e && atoi(e) != 0;
+		e = getenv("GAS_K2_REPLICAS");
+		ctx->replicas = e ? atoi(e) : 8;
+		ctx->replicas = ctx->replicas < 1 ? 1 : (ctx->replicas > 16 ? 16 : ctx->replicas);
+		e = getenv("GAS_SKIP"); // experiments only: 1 = no prologue, 2 = no streaming kernel, 4 = no voice-parallel kernel
+		ctx->skip = e ? atoi(e) : 0;
+	}
 
 	const size_t I = cfg->max_instances, V = cfg->max_voices, F = cfg->max_frames;
 	const size_t nscratch_ids = (I > V ? I : V);
@@ -285,21 +332,21 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->t.blk, (size_t)2);
 	ctx->t.max_instances = (int32_t)I;
 	ALLOC(ctx->t.inst_fx, I);
-	ALLOC(ctx->t.inst_sends, I);
 	ALLOC(ctx->t.vs_prev, V * 8);
 	ALLOC(ctx->t.vs_proc, V * 8);
 	ALLOC(ctx->t.vs_fx, V * (size_t)(GAS_MAX_EFFECTS * 2 * GAS_MAX_FILTER_STAGES * 4));
-	ALLOC(ctx->plan.cls, (size_t)2 * GAS_MAX_CLASSES);
-	ALLOC(ctx->plan.n_cls, (size_t)1);
+	ALLOC(ctx->plan.cls_key, (size_t)GAS_MAX_CLASSES);
+	ALLOC(ctx->plan.cls_count, (size_t)2 * GAS_MAX_CLASSES);
 	ALLOC(ctx->plan.overflow, (size_t)1);
-	ALLOC(ctx->plan.k2_src, (size_t)GAS_MAX_CLASSES * V);
+	ALLOC(ctx->plan.list, (size_t)GAS_MAX_CLASSES * V);
 	ALLOC(ctx->plan.k2_rows, (size_t)GAS_MAX_CLASSES * V * GAS_K2_ROW_FLOATS + 64);
-	ALLOC(ctx->plan.k3_list, (size_t)GAS_MAX_CLASSES * V);
 	ALLOC(ctx->plan.rec, V);
+	ALLOC(ctx->plan.sends, V);
 	ALLOC(ctx->d_voices, V);
 	ALLOC(ctx->d_src, V * F);
 	ALLOC(ctx->d_bus, (size_t)GAS_MAX_BUSES * GAS_MAX_CHANNELS_PER_BUS * F);
 	ALLOC(ctx->d_peaks, V);
+	ALLOC(ctx->d_rep, (size_t)16 * GAS_MAX_BUSES * GAS_MAX_CHANNELS_PER_BUS * F);
 	ALLOC(ctx->d_emitters, I);
 	ALLOC(ctx->d_listeners, (size_t)GAS_MAX_LISTENERS);
 	ALLOC(ctx->d_areas, (size_t)ctx->max_areas);
@@ -314,6 +361,8 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 #undef ALLOC
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_mix, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_gain, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_aux_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_gain_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_prologue_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
@@ -343,11 +392,14 @@ void gas_destroy(gas_ctx *ctx) {
 	if (ctx->s_gain) {
 		cudaStreamSynchronize(ctx->s_gain);
 	}
+	if (ctx->s_aux) {
+		cudaStreamSynchronize(ctx->s_aux);
+	}
 	gas_comm_close(ctx);
 	void *ptrs[] = { ctx->t.spat, ctx->t.inst_spat, ctx->t.inst_params, ctx->t.inst_was_further, ctx->t.inst_active, ctx->t.inst_cur,
-		ctx->t.inst_prev, ctx->t.inst_mode, ctx->t.blk, ctx->t.inst_fx, ctx->t.inst_sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls, ctx->plan.n_cls,
-		ctx->plan.overflow, ctx->plan.k2_src, ctx->plan.k2_rows, ctx->plan.k3_list, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
-		ctx->d_peaks, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
+		ctx->t.inst_prev, ctx->t.inst_mode, ctx->t.blk, ctx->t.inst_fx, ctx->plan.sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls_key, ctx->plan.cls_count,
+		ctx->plan.overflow, ctx->plan.list, ctx->plan.k2_rows, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
+		ctx->d_peaks, ctx->d_rep, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
 		ctx->d_exchange };
 	for (void *p : ptrs) {
 		if (p) {
@@ -365,6 +417,12 @@ void gas_destroy(gas_ctx *ctx) {
 	}
 	if (ctx->ev_join) {
 		cudaEventDestroy(ctx->ev_join);
+	}
+	if (ctx->ev_aux_done) {
+		cudaEventDestroy(ctx->ev_aux_done);
+	}
+	if (ctx->s_aux) {
+		cudaStreamDestroy(ctx->s_aux);
 	}
 	for (auto &g : ctx->graphs) {
 		if (g.exec) {
@@ -742,6 +800,8 @@ int gas_sync(gas_ctx *ctx) {
 void *gas_mix_stream(gas_ctx *ctx) { return ctx ? (void *)ctx->s_mix : nullptr; }
 void *gas_gain_stream(gas_ctx *ctx) { return ctx ? (void *)ctx->s_gain : nullptr; }
 uint64_t gas_kernel_launches(const gas_ctx *ctx) { return ctx ? ctx->launches : 0; }
+// experiments only (not in gas.h): device pointer of the K2 timeline buffer, [CTA][8] uint64
+extern "C" GAS_API void *gas_debug_timeline(gas_ctx *ctx) { return ctx ? (void *)ctx->d_timeline : nullptr; }
 
 int gas_voice_state_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_voice_state *out) {
 	{

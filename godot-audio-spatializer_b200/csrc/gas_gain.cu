@@ -1,6 +1,10 @@
 // gas_gain.cu — K1: batched AudioSpatializerInstance3D::calculate_spatialization
 // (reference audio_spatializer_3d.cpp:277-489) + update_spatializer_parameters / get_bus_map
-// (reference audio_spatializer.cpp:258-324), one thread per emitter.
+// (reference audio_spatializer.cpp:258-324).  Eight lanes per emitter: the scalar chain (transform,
+// attenuation, filter gain, doppler) is evaluated redundantly by the eight lanes, the SPCAP speaker gains
+// (one double pow each, the long pole) go one speaker per lane, and every lane stores its own
+// (channel pair, side) element of the volume tables, so table traffic is 32-byte segments and the
+// dependent double-precision chains are short enough to hide behind 8x more resident warps.
 //
 // Compiled with -fmad=false: the reference mixes float storage with double intermediates (SURVEY Q3,
 // Q8, Q10) and the gains must come out the way a scalar x86-64 build produces them, so no contraction.
@@ -145,29 +149,32 @@ __device__ __forceinline__ V3 spcap_dir(int i) {
 	return norm3(raw);
 }
 
-// reference audio_spatializer_3d.cpp:57-98 + :903-938
-__device__ void output_vol_surround(int speaker_mode, V3 src, float tightness, float out[4][2]) {
-	int count = speaker_mode == GAS_SPEAKER_SURROUND_31 ? 3 : (speaker_mode == GAS_SPEAKER_SURROUND_51 ? 5 : (speaker_mode == GAS_SPEAKER_SURROUND_71 ? 7 : 2));
-	V3 d[7];
-	float eff[7], sq[7], vol[7];
-	for (int i = 0; i < 7; i++) {
-		d[i] = spcap_dir(i);
-		eff[i] = 0.f;
-		vol[i] = 0.f;
-	}
-	for (int i = 0; i < count; i++) { // :911-915, float accumulator += double term
-		for (int j = 0; j < count; j++) {
-			eff[i] = (float)((double)eff[i] + 0.5 * (1.0 + (double)dot3(d[i], d[j])));
-		}
+// reference audio_spatializer_3d.cpp:57-98 + :903-938.  Lane `l` of the emitter's 8-lane group (mask gm,
+// first lane gbase) owns speaker l; sums run in speaker order exactly like the reference loop.
+__device__ void output_vol_surround(unsigned gm, int gbase, int l, const GlobalCfg &g, V3 src, float tightness, float out[4][2]) {
+	const int speaker_mode = g.speaker_mode;
+	const int count = speaker_mode == GAS_SPEAKER_SURROUND_31 ? 3 : (speaker_mode == GAS_SPEAKER_SURROUND_51 ? 5 : (speaker_mode == GAS_SPEAKER_SURROUND_71 ? 7 : 2));
+	float sq = 0.f;
+	if (l < count) {
+		const V3 dl{ g.spk_dir[l][0], g.spk_dir[l][1], g.spk_dir[l][2] };
+		const float eff = g.spk_eff[l]; // :911-915, precomputed per speaker mode
+		const float gain = (float)(0.5 * pow(1.0 + (double)dot3(dl, src), (double)tightness) / (double)eff); // :929-933
+		sq = gain * gain;
 	}
 	float sum = 0.f;
-	for (int i = 0; i < count; i++) { // :929-933
-		float g = (float)(0.5 * pow(1.0 + (double)dot3(d[i], src), (double)tightness) / (double)eff[i]);
-		sq[i] = g * g;
-		sum += sq[i];
+#pragma unroll
+	for (int i = 0; i < 7; i++) {
+		const float v = __shfl_sync(gm, sq, gbase + i);
+		if (i < count) {
+			sum += v;
+		}
 	}
-	for (int i = 0; i < count; i++) { // :935-937
-		vol[i] = sqrtf(sq[i] / sum);
+	const float mine = sqrtf(sq / sum); // :935-937
+	float vol[7];
+#pragma unroll
+	for (int i = 0; i < 7; i++) {
+		const float v = __shfl_sync(gm, mine, gbase + i);
+		vol[i] = i < count ? v : 0.f;
 	}
 	switch (speaker_mode) {
 		case GAS_SPEAKER_SURROUND_71:
@@ -199,20 +206,20 @@ __device__ void output_vol_stereo(V3 dir, float pan_strength, float out[4][2]) {
 }
 
 // reference audio_spatializer_3d.cpp:112-121
-__device__ void output_vol(const GlobalCfg &g, const gas_spatializer &s, V3 dir, float out[4][2]) {
+__device__ void output_vol(unsigned gm, int gbase, int l, const GlobalCfg &g, const gas_spatializer &s, V3 dir, float out[4][2]) {
 	if (g.speaker_mode == GAS_SPEAKER_MODE_STEREO) {
 		output_vol_stereo(dir, g.global_panning * s.panning_strength, out);
 	} else {
 		float tightness = g.global_panning * 2.0f;
 		tightness *= s.panning_strength;
-		output_vol_surround(g.speaker_mode, dir, tightness, out);
+		output_vol_surround(gm, gbase, l, g, dir, tightness, out);
 	}
 }
 
 __device__ __forceinline__ float lerpf(float a, float b, float w) { return a + (b - a) * w; }
 
 // reference audio_spatializer_3d.cpp:154-197
-__device__ void reverb_vol(const GlobalCfg &g, const gas_spatializer &s, const gas_emitter &e, const gas_area &a,
+__device__ void reverb_vol(unsigned gm, int gbase, int l, const GlobalCfg &g, const gas_spatializer &s, const gas_emitter &e, const gas_area &a,
 		V3 listener_area_pos, const float direct[4][2], float rev[4][2]) {
 	for (int i = 0; i < 4; i++) {
 		rev[i][0] = rev[i][1] = 0.f;
@@ -229,7 +236,7 @@ __device__ void reverb_vol(const GlobalCfg &g, const gas_spatializer &s, const g
 			V3 rp = listener_area_pos;
 			rp.y = 0.f;
 			rp = norm3(rp);
-			output_vol(g, s, rp, rev);
+			output_vol(gm, gbase, l, g, s, rp, rev);
 			for (int i = 0; i < chan; i++) {
 				rev[i][0] = lerpf(rev[i][0], cv, attenuation);
 				rev[i][1] = lerpf(rev[i][1], cv, attenuation);
@@ -318,34 +325,62 @@ __device__ void commit_params(const DevTables &t, int q, const gas_params &p) {
 	}
 }
 
-__global__ void __launch_bounds__(128) k_gain(DevTables t, GlobalCfg g, int n, const gas_emitter *__restrict__ emitters,
+// this lane's element of a [pair][side] table without dynamic indexing (keeps the table in registers)
+__device__ __forceinline__ float pick(const float v[4][2], int c, int x) {
+	float r = 0.f;
+#pragma unroll
+	for (int cc = 0; cc < 4; cc++) {
+#pragma unroll
+		for (int xx = 0; xx < 2; xx++) {
+			r = (cc == c && xx == x) ? v[cc][xx] : r;
+		}
+	}
+	return r;
+}
+
+constexpr int kGainLanes = 8;
+constexpr int kGainThreads = 256;
+
+__global__ void __launch_bounds__(kGainThreads, 4) k_gain(DevTables t, GlobalCfg g, int n, const gas_emitter *__restrict__ emitters,
 		int n_listeners, const gas_listener *__restrict__ listeners, const gas_area *__restrict__ areas, gas_params *__restrict__ out) {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kGainLanes;
+	const int l = threadIdx.x & 7;
+	const int gbase = threadIdx.x & 24; // first lane of this emitter's group inside the warp
+	const unsigned gm = 0xffu << gbase;
+	const int lc = l >> 1, lx = l & 1;
 	if (i >= n) {
 		return;
 	}
 	const gas_emitter e = emitters[i];
-	const gas_spatializer s = t.spat[e.spatializer];
+	// everything behind the emitter record is requested at once: the fields of its spatializer, its area and
+	// the state of its instance
+	const gas_spatializer *sp = &t.spat[e.spatializer];
+	gas_spatializer s;
+	s.attenuation_model = sp->attenuation_model;
+	s.unit_size = sp->unit_size;
+	s.max_distance = sp->max_distance;
+	s.panning_strength = sp->panning_strength;
+	s.emission_angle_enabled = sp->emission_angle_enabled;
+	s.emission_angle = sp->emission_angle;
+	s.emission_angle_filter_attenuation_db = sp->emission_angle_filter_attenuation_db;
+	s.attenuation_filter_cutoff_hz = sp->attenuation_filter_cutoff_hz;
+	s.attenuation_filter_db = sp->attenuation_filter_db;
+	s.doppler_tracking = sp->doppler_tracking;
+	s.doppler_speed_of_sound = sp->doppler_speed_of_sound;
+	const int q = e.instance;
+	const bool was_further = t.inst_was_further[q] != 0;
+	const int q_active = t.inst_active[q];
+	const bool mix_channels = inst_mix_channels(t, q);
 	const bool has_area = e.area >= 0;
-	gas_area a;
-	if (has_area) {
-		a = areas[e.area];
-	}
-	gas_params prm;
-	for (int c = 0; c < 4; c++) {
-		prm.mix_volumes[c][0] = prm.mix_volumes[c][1] = 0.f;
-	}
+	const gas_area *ap = has_area ? &areas[e.area] : nullptr;
+	struct {
+		float pitch_scale, linear_attenuation, attenuation_filter_cutoff_hz;
+		int update_parameters;
+	} prm;
 	prm.pitch_scale = 1.0f;
 	prm.linear_attenuation = 0.0f;
 	prm.attenuation_filter_cutoff_hz = 5000.0f;
 	prm.update_parameters = 0;
-	prm.n_bus = 0;
-	for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
-		prm.bus[k] = 0;
-		for (int c = 0; c < 4; c++) {
-			prm.bus_volumes[k][c][0] = prm.bus_volumes[k][c][1] = 0.f;
-		}
-	}
 
 	const V3 global_pos{ e.origin[0], e.origin[1], e.origin[2] };
 	V3 linear_velocity{ 0.f, 0.f, 0.f };
@@ -360,7 +395,7 @@ __global__ void __launch_bounds__(128) k_gain(DevTables t, GlobalCfg g, int n, c
 		reverb_volume[c][0] = reverb_volume[c][1] = 0.f;
 	}
 	bool in_range_any = false;
-	const bool area_reverb_uniform = has_area && a.use_reverb && a.reverb_uniformity > 0.0f;
+	const bool area_reverb_uniform = has_area && ap->use_reverb && ap->reverb_uniformity > 0.0f;
 
 	for (int li = 0; li < n_listeners; li++) { // :323
 		const gas_listener L = listeners[li];
@@ -374,7 +409,7 @@ __global__ void __launch_bounds__(128) k_gain(DevTables t, GlobalCfg g, int n, c
 		if (area_reverb_uniform) { // :350-353 (plain affine inverse, not orthonormalised)
 			Xf inv2 = lt;
 			affine_invert(inv2);
-			listener_area_pos = xform(inv2, V3{ a.closest_point[li][0], a.closest_point[li][1], a.closest_point[li][2] });
+			listener_area_pos = xform(inv2, V3{ ap->closest_point[li][0], ap->closest_point[li][1], ap->closest_point[li][2] });
 		}
 		float multiplier = db_to_linear_f(attenuation_db(s, e.volume_db, e.max_db, dist)); // :359
 		if (s.max_distance > 0.f) { // :361-373
@@ -409,15 +444,15 @@ __global__ void __launch_bounds__(128) k_gain(DevTables t, GlobalCfg g, int n, c
 		for (int c = 0; c < 4; c++) {
 			tmp_volume[c][0] = tmp_volume[c][1] = 0.f;
 		}
-		output_vol(g, s, local_pos, tmp_volume); // :391 — un-normalised direction (Q1)
+		output_vol(gm, gbase, l, g, s, local_pos, tmp_volume); // :391 — un-normalised direction (Q1)
 		for (int c = 0; c < 4; c++) {            // :393-396
 			tmp_volume[c][0] = multiplier * tmp_volume[c][0];
 			tmp_volume[c][1] = multiplier * tmp_volume[c][1];
 			output_volume[c][0] = output_volume[c][0] > tmp_volume[c][0] ? output_volume[c][0] : tmp_volume[c][0];
 			output_volume[c][1] = output_volume[c][1] > tmp_volume[c][1] ? output_volume[c][1] : tmp_volume[c][1];
 		}
-		if (has_area && a.use_reverb) { // :399-402
-			reverb_vol(g, s, e, a, listener_area_pos, tmp_volume, tmp_reverb);
+		if (has_area && ap->use_reverb) { // :399-402
+			reverb_vol(gm, gbase, l, g, s, e, *ap, listener_area_pos, tmp_volume, tmp_reverb);
 			for (int c = 0; c < 4; c++) {
 				reverb_volume[c][0] = reverb_volume[c][0] > tmp_reverb[c][0] ? reverb_volume[c][0] : tmp_reverb[c][0];
 				reverb_volume[c][1] = reverb_volume[c][1] > tmp_reverb[c][1] ? reverb_volume[c][1] : tmp_reverb[c][1];
@@ -447,30 +482,81 @@ __global__ void __launch_bounds__(128) k_gain(DevTables t, GlobalCfg g, int n, c
 	} else {
 		prm.pitch_scale = e.pitch_scale;
 	}
-	if (in_range_any) { // :437-461
+	// :437-461 — bus entries in Dictionary insertion order; a second add to the same bus overwrites its volumes
+	int n_bus = 0, bus0 = 0, bus1 = 0;
+	bool slot0_is_reverb = false;
+	if (in_range_any) {
 		if (has_area) {
-			add_bus_volume(prm, resolve_bus(g, a.override_bus ? a.bus : e.bus), output_volume);
-			if (a.use_reverb) {
-				add_bus_volume(prm, resolve_bus(g, a.reverb_bus), reverb_volume);
+			bus0 = resolve_bus(g, ap->override_bus ? ap->bus : e.bus);
+			n_bus = 1;
+			if (ap->use_reverb) {
+				const int rb = resolve_bus(g, ap->reverb_bus);
+				if (rb == bus0) {
+					slot0_is_reverb = true;
+				} else {
+					bus1 = rb;
+					n_bus = 2;
+				}
 			}
 		} else {
-			add_bus_volume(prm, resolve_bus(g, e.bus), output_volume);
+			bus0 = resolve_bus(g, e.bus);
+			n_bus = 1;
 		}
 	}
-	for (int c = 0; c < 4; c++) { // :463
-		prm.mix_volumes[c][0] = output_volume[c][0];
-		prm.mix_volumes[c][1] = output_volume[c][1];
-	}
-	const int q = e.instance;
-	const bool was_further = t.inst_was_further[q] != 0;
+	const float mv = pick(output_volume, lc, lx); // :463
+	const float rv = pick(reverb_volume, lc, lx);
+	const float bv0 = n_bus > 0 ? (slot0_is_reverb ? rv : mv) : 0.f;
+	const float bv1 = n_bus > 1 ? rv : 0.f;
 	const bool skip = !in_range_any && was_further; // :466-467
-	t.inst_was_further[q] = in_range_any ? 0 : 1;
+	__syncwarp(gm); // every lane has read was_further before lane 0 rewrites it
 	if (!skip) {
 		prm.update_parameters = 1;
 	}
-	commit_params(t, q, prm);
-	if (out) {
-		out[i] = prm;
+	// set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272), one (pair, side) element per lane
+#pragma unroll
+	for (int pass = 0; pass < 2; pass++) {
+		gas_params *P = pass == 0 ? &t.inst_params[q] : (out ? &out[i] : nullptr);
+		if (!P) {
+			continue;
+		}
+		P->mix_volumes[lc][lx] = mv;
+#pragma unroll
+		for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+			P->bus_volumes[k][lc][lx] = k == 0 ? bv0 : (k == 1 ? bv1 : 0.f);
+		}
+		if (l == 0) {
+			P->pitch_scale = prm.pitch_scale;
+			P->linear_attenuation = prm.linear_attenuation;
+			P->attenuation_filter_cutoff_hz = prm.attenuation_filter_cutoff_hz;
+			P->update_parameters = prm.update_parameters;
+			P->n_bus = n_bus;
+#pragma unroll
+			for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+				P->bus[k] = k == 0 ? bus0 : (k == 1 ? bus1 : 0);
+			}
+		}
+	}
+	if (l == 0) {
+		t.inst_was_further[q] = in_range_any ? 0 : 1;
+	}
+	if (prm.update_parameters && q_active) { // get_bus_map of all proxy channels (audio_spatializer.cpp:274-324)
+		BusDetails *d = &t.inst_cur[q];
+#pragma unroll
+		for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+			float w = 0.f;
+			if (k < n_bus) {
+				const float bv = k == 0 ? bv0 : bv1;
+				w = mix_channels ? (mv > 0.0f ? bv / mv : 0.f) : mv;
+			}
+			d->vol[k][lc][lx] = w;
+		}
+		if (l == 0) {
+			d->n = n_bus;
+#pragma unroll
+			for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+				d->bus[k] = k == 0 ? (n_bus > 0 ? bus0 : 0) : (k == 1 && n_bus > 1 ? bus1 : 0);
+			}
+		}
 	}
 }
 
@@ -515,7 +601,7 @@ cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_list
 	if (n <= 0) {
 		return cudaSuccess;
 	}
-	k_gain<<<(n + 127) / 128, 128, 0, st>>>(ctx->t, ctx->g, n, d_em, n_listeners, d_l, d_areas, d_out);
+	k_gain<<<(n * kGainLanes + kGainThreads - 1) / kGainThreads, kGainThreads, 0, st>>>(ctx->t, ctx->g, n, d_em, n_listeners, d_l, d_areas, d_out);
 	ctx->launches++;
 	return cudaGetLastError();
 }

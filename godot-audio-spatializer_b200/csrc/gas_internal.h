@@ -13,7 +13,7 @@
 
 // ---- limits of the per-block plan -----------------------------------------------------------------
 #define GAS_MAX_SENDS 12      // union of current and previous bus details: 6 + 6
-#define GAS_MAX_CLASSES 16    // distinct (path, mode, send-mask) classes per block
+#define GAS_MAX_CLASSES 128   // class slots: distinct (path, mode, flags, send-mask, degree) combinations seen since the last reset
 #define GAS_K2_MAX_ROWS 6     // weight rows per (pair, side) the streaming kernel holds in registers
 #define GAS_K2_ROW_FLOATS (GAS_K2_MAX_ROWS * GAS_MAX_CHANNELS_PER_BUS * 2)
 
@@ -43,21 +43,51 @@ enum : int32_t {
 enum : int32_t { MODE_A = 0, MODE_B = 1, MODE_E = 2 };
 
 // class flags
-#define CLS_LIN 1u    // every weight is linear in t (2 rows per send instead of 3)
 #define CLS_SHARED 2u // all sends carry identical weights: one row group fanned out to every bus of the mask
 #define CLS_FILT 4u   // attenuation filter active (linear_attenuation >= 0.001)
 
+// A class is identified by a 64-bit key; everything a kernel needs to know about it is decoded from the key:
+//   path [0,2)  mode [2,4)  flags [4,8)  n_send [8,12)  bus mask [16,32)  quad [32,44)
 struct ClassInfo {
 	unsigned long long key; // 0 = empty
-	int32_t count;          // voices appended so far
+	int32_t count;          // voices of the class in this block
 	int32_t path;
 	int32_t mode;
 	uint32_t flags;
 	uint32_t mask;   // bus mask of the sends
+	uint32_t quad;   // bit k set <=> row group k carries a t^2 row (its ramp product is not linear in t)
 	int32_t n_send;  // popcount(mask)
 	int32_t n_group; // row groups: 1 if CLS_SHARED else n_send
-	int32_t n_rows;  // n_group * (LIN ? 2 : 3)
+	int32_t n_rows;  // sum over groups of (2 + quad bit); 0 on the voice-parallel path
+	int32_t slot;    // slot of the class in the global table (addresses its list)
 };
+
+static __host__ __device__ __forceinline__ unsigned long long cls_key(int path, int mode, uint32_t flags, int n_send, uint32_t mask, uint32_t quad) {
+	return (unsigned long long)path | ((unsigned long long)mode << 2) | ((unsigned long long)flags << 4) | ((unsigned long long)n_send << 8) |
+			((unsigned long long)mask << 16) | ((unsigned long long)quad << 32);
+}
+static __host__ __device__ __forceinline__ ClassInfo cls_decode(unsigned long long key, int count) {
+	ClassInfo ci;
+	ci.key = key;
+	ci.count = count;
+	ci.slot = 0;
+	ci.path = (int32_t)(key & 3u);
+	ci.mode = (int32_t)((key >> 2) & 3u);
+	ci.flags = (uint32_t)((key >> 4) & 15u);
+	ci.n_send = (int32_t)((key >> 8) & 15u);
+	ci.mask = (uint32_t)((key >> 16) & 0xffffu);
+	ci.quad = (uint32_t)((key >> 32) & 0xfffu);
+	ci.n_group = ci.path == PATH_STREAM ? ((ci.flags & CLS_SHARED) ? 1 : ci.n_send) : ci.n_send;
+	int rows = 0;
+	if (ci.path == PATH_STREAM) {
+		rows = 2 * ci.n_group;
+		for (uint32_t q = ci.quad; q; q &= q - 1) {
+			rows++;
+		}
+	}
+	ci.n_rows = rows;
+	return ci;
+}
 
 // What K3 needs about one voice besides its persistent state.
 struct VoiceRec {
@@ -74,13 +104,13 @@ struct VoiceRec {
 };
 
 struct BlockPlan {
-	ClassInfo *cls;      // [2][GAS_MAX_CLASSES]: by block parity; block n uses [n & 1], clears [(n + 1) & 1]
-	int32_t *n_cls;      // [1]
+	unsigned long long *cls_key; // [GAS_MAX_CLASSES] slot -> class key (0 = free); slots are stable across blocks
+	int32_t *cls_count;  // [2][GAS_MAX_CLASSES] by block parity; block n fills [n & 1] and clears [(n + 1) & 1]
 	int32_t *overflow;   // [1] set when more than GAS_MAX_CLASSES classes were needed
-	int32_t *k2_src;     // [GAS_MAX_CLASSES][max_voices] source row per list position
-	float *k2_rows;      // [GAS_MAX_CLASSES][max_voices][GAS_K2_ROW_FLOATS] (compact: n_rows*C*2 used)
-	int32_t *k3_list;    // [GAS_MAX_CLASSES][max_voices] call-order index j
+	int2 *list;          // [GAS_MAX_CLASSES][max_voices] {call-order index j, source row} per list position
+	float *k2_rows;      // [GAS_MAX_CLASSES][max_voices][GAS_K2_ROW_FLOATS] by list position (compact: n_rows*C*2 floats per voice)
 	VoiceRec *rec;       // [max_voices] by call-order index
+	InstSends *sends;    // [max_voices] by call-order index: resolved sends of the voice's instance (K3 voices only)
 };
 
 struct DevTables {
@@ -92,10 +122,9 @@ struct DevTables {
 	BusDetails *inst_cur;
 	BusDetails *inst_prev;   // [2][max_instances]: double-buffered by block parity (read [p], write [1-p])
 	int32_t *inst_mode;      // MODE_A/B/E | (effect_gain_binding + 1) << 8, latched at instantiate()
-	int32_t *blk;            // [0] block counter (parity of inst_prev), [1] CTA ticket of the prologue
+	int32_t *blk;            // [0] block counter (parity of inst_prev and of the class counts), [1] CTA ticket of the prologue
 	int32_t max_instances;
 	gas_effect_chain *inst_fx;
-	InstSends *inst_sends;
 	float *vs_prev;              // [max_voices][4][2]
 	gas_processor_state *vs_proc; // [max_voices][8]
 	float *vs_fx;                // [max_voices][GAS_MAX_EFFECTS][2][GAS_MAX_FILTER_STAGES][4]
@@ -110,6 +139,11 @@ struct GlobalCfg {
 	int32_t max_instances;
 	int32_t max_voices;
 	int32_t max_spatializers;
+	// SPCAP constants of the current speaker mode (reference audio_spatializer_3d.cpp:47-55, :903-916), computed
+	// on the host with the reference's float/double sequence: normalised speaker directions and the
+	// "effective number of speakers" per speaker
+	float spk_dir[7][3];
+	float spk_eff[7];
 };
 
 struct gas_ctx {
@@ -118,8 +152,8 @@ struct gas_ctx {
 	int device = 0;
 	int num_sms = 0;
 	int l2_bytes = 0;
-	cudaStream_t s_mix = nullptr, s_gain = nullptr;
-	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr;
+	cudaStream_t s_mix = nullptr, s_gain = nullptr, s_aux = nullptr; // s_aux: the voice-parallel kernel beside the streaming one
+	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_aux_done = nullptr;
 	bool gain_pending = false, prologue_pending = false;
 	DevTables t{};
 	BlockPlan plan{};
@@ -128,6 +162,8 @@ struct gas_ctx {
 	gas_frame *d_src = nullptr;
 	gas_frame *d_bus = nullptr;
 	gas_frame *d_peaks = nullptr;
+	gas_frame *d_rep = nullptr; // [replicas][num_buses][channels][frames]: K2 partial sums, combined by the K3 launch
+	int replicas = 8;           // GAS_K2_REPLICAS (1 = K2 adds straight into the bus buffers)
 	gas_emitter *d_emitters = nullptr;
 	gas_listener *d_listeners = nullptr;
 	gas_area *d_areas = nullptr;
@@ -144,6 +180,9 @@ struct gas_ctx {
 	gas_frame *peer_exchange[8] = {};
 	uint64_t launches = 0;
 	bool k2_smem_attr_set = false;
+	int skip = 0;     // GAS_SKIP bits (experiments only)
+	unsigned long long *d_timeline = nullptr; // GAS_K2_DEBUG & 8: per-CTA globaltimer stamps of the last K2 launch
+	bool pdl = false; // GAS_PDL=1: mix-side kernels are launched with programmatic stream serialization
 	int32_t n_listeners_res = 0, n_areas_res = 0; // resident listeners / areas (gas_listeners_set / gas_areas_set)
 	// CUDA-graph capture
 	bool capturing = false;
@@ -177,6 +216,26 @@ int gas_fail(gas_ctx *ctx, int status, const char *fmt, ...);
 		}                                                                                      \
 	} while (0)
 
+// Launch with (optionally) the programmatic-dependent-launch attribute: the kernel may become resident
+// while its stream predecessor drains; it must execute griddepcontrol.wait before touching global memory.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gas_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+	cudaLaunchConfig_t lc{};
+	lc.gridDim = grid;
+	lc.blockDim = block;
+	lc.dynamicSmemBytes = smem;
+	lc.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	lc.attrs = attr;
+	lc.numAttrs = pdl ? 1 : 0;
+	cudaError_t e = cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);
+	return e != cudaSuccess ? e : cudaGetLastError();
+}
+#define GAS_GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define GAS_GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+
 // ---- kernel launchers (each returns cudaError_t from the launch) -----------------------------------
 // gas_gain.cu
 cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_listeners, const gas_listener *d_l,
@@ -186,6 +245,8 @@ cudaError_t launch_instance_start(gas_ctx *ctx, int n, const int32_t *d_ids, cud
 // gas_prologue.cu
 cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int src_rows, int frames, gas_frame *d_bus,
 		gas_frame *d_peaks, cudaStream_t st);
+// frames of one replica of the partial-sum buffers for a block of `frames` frames (16-byte units)
+static inline int gas_bus_f4(const gas_ctx *ctx, int frames) { return ctx->g.num_buses * ctx->g.channels * frames / 2; }
 // gas_mix_stream.cu (K2) / gas_mix_voice.cu (K3)
 cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, cudaStream_t st);
 cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus,

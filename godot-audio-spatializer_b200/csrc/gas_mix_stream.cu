@@ -11,15 +11,23 @@
 //
 // Structure: persistent, one CTA per SM, warp-specialised.
 //   warp 8      producer: streams voice rows HBM -> shared memory with 1-D bulk async copies (TMA engine,
-//               cp.async.bulk + mbarrier complete_tx) through a ring of stages; rows are gathered by
-//               the class lists, so voices need not be contiguous in memory.
+//               cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) through a ring of stages; rows are
+//               gathered by the class lists, so voices need not be contiguous in memory.  One copy per voice
+//               row plus one per stage for the weights: tools/streamtest.cu measured this pattern (4 KB
+//               rows, 148 CTAs) at 4.6-4.7 TB/s for a 64 MiB pass including launch, against 4.1 TB/s for
+//               per-warp cp.async rings; a bulk copy costs ~75 ns of issue whatever its size, so tiles
+//               narrower than 512 frames (more, smaller copies) stream slower.
 //   warps 0-7   consumers: each thread owns 2 frames of the tile and keeps rows x 2 (L,R) accumulators in
 //               registers; weights are broadcast from shared memory; the FMAs are packed FFMA2
 //               (fma.rn.f32x2: one instruction per (L,R) pair).
-// A CTA owns a contiguous range of (class, frame tile, voice batch) units; when the class or tile
-// changes it evaluates the polynomial and adds its partial sums into the bus buffers with vector
-// reductions (red.global.add.v4.f32).  No per-voice state is written here.
+// A CTA owns a contiguous range of (class, frame tile, voice batch) units; ranges are cut in cost space
+// (accumulator count + a fixed per-voice term) so that the FMA-heavy classes do not pile up on a few SMs.
+// When the class or tile changes the CTA evaluates the polynomial in t and adds its partial sums to the bus
+// buffers: per-thread red.global.add.v4.f32 (default), or (GAS_K2_FLUSH=1) shared-memory staging + bulk
+// async reductions (cp.reduce.async.bulk ... add.f32, SASS UBLKRED).  No per-voice state is written here.
 #include "gas_internal.h"
+
+#include <stdlib.h>
 
 #include <stdlib.h>
 
@@ -35,6 +43,8 @@ constexpr int kThreads = kConsumerThreads + 32;
 constexpr int kTileFrames = 512;       // frames per tile: 2 per consumer thread
 constexpr int kMaxPairs = GAS_K2_MAX_ROWS * GAS_MAX_CHANNELS_PER_BUS; // 24 (L,R) weight pairs per voice
 constexpr int kMaxStages = 8;
+constexpr int kStagingSlot = GAS_MAX_CHANNELS_PER_BUS * kTileFrames * 8; // one row group: C rows of a 512-frame tile
+constexpr int kStagingBytes = 2 * kStagingSlot;                         // double-buffered
 
 struct StreamCfg {
 	int frames;        // F
@@ -48,10 +58,18 @@ struct StreamCfg {
 	int x_bytes;       // per stage
 	int w_bytes;       // per stage
 	int stage_bytes;
-	int debug;         // GAS_K2_DEBUG bits (experiments only): 1 = skip the bus reductions, 2 = skip the FMAs
+	int fixed_cost;    // per-voice term of the partition cost (the other term is the accumulator count)
+	int flush_mode;    // 0 = per-thread red.global.add.v4 (default), 1 = shared-memory staging + bulk async reduce
+	int debug;         // GAS_K2_DEBUG bits (experiments only): 1 = skip the bus reductions, 2 = skip the FMAs, 8 = record a timeline
+	unsigned long long *timeline; // [CTA][8] globaltimer stamps (debug & 8): start, table, first data, last data, flushed
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long gtime() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -82,6 +100,20 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 			"l"(src), "r"(bytes), "r"(smem_u32(bar))
 			: "memory");
 }
+// 1-D bulk async reduction shared -> global, element-wise fp32 add performed at L2 (SASS: UBLKRED)
+__device__ __forceinline__ void bulk_red_add_f32(float *dst, const void *src, uint32_t bytes) {
+	asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+			: "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of the most recent bulk groups still read their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+	asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -104,40 +136,46 @@ __device__ __forceinline__ void fma2(float2 &acc, const float2 w, const float2 x
 #endif
 }
 
-// ---- unit iterator: (class, frame tile, voice batch), identical in every role -------------------------
+// ---- unit iterator: (class, frame tile, voice batch), identical in every role ------------
 struct UnitIter {
-	int cid, tile, batch, nb; // nb: batches of the current class
+	int cid, tile, batch, nb; // cid: index into the CTA's compact table of streaming classes; nb: batches of the current class
 	int remaining;
+	int n_cls;
 };
 
-__device__ void unit_iter_init(UnitIter &it, const ClassInfo *cls, const StreamCfg &cf, int cta, int n_cta) {
-	int total = 0;
-	for (int c = 0; c < GAS_MAX_CLASSES; c++) {
-		if (cls[c].key != 0ULL && cls[c].path == PATH_STREAM) {
-			total += ((cls[c].count + cf.vb - 1) / cf.vb) * cf.n_tiles;
-		}
+// CTA `cta` owns the units whose start lies in [total*cta/n, total*(cta+1)/n) of the cost line, where a
+// unit of class c costs w_c = accumulators + fixed_cost.  Units are ordered class, tile, batch.
+__device__ void unit_iter_init(UnitIter &it, const ClassInfo *cls, int n_cls, const StreamCfg &cf, int C, int cta, int n_cta) {
+	long long total = 0;
+	for (int c = 0; c < n_cls; c++) {
+		const long long units = (long long)((cls[c].count + cf.vb - 1) / cf.vb) * cf.n_tiles;
+		total += units * (cls[c].n_rows * C + cf.fixed_cost);
 	}
-	const long long lo = (long long)total * cta / n_cta;
-	const long long hi = (long long)total * (cta + 1) / n_cta;
-	it.remaining = (int)(hi - lo);
-	it.cid = GAS_MAX_CLASSES;
+	const long long lo = total * cta / n_cta;
+	const long long hi = total * (cta + 1) / n_cta;
+	it.remaining = 0;
+	it.cid = n_cls;
+	it.n_cls = n_cls;
 	it.tile = it.batch = it.nb = 0;
-	int skip = (int)lo;
-	for (int c = 0; c < GAS_MAX_CLASSES && it.remaining > 0; c++) {
-		if (cls[c].key == 0ULL || cls[c].path != PATH_STREAM) {
-			continue;
+	long long base = 0;
+	for (int c = 0; c < n_cls; c++) {
+		const int nb = (cls[c].count + cf.vb - 1) / cf.vb;
+		const long long units = (long long)nb * cf.n_tiles;
+		const long long w = cls[c].n_rows * C + cf.fixed_cost;
+		long long u_lo = lo <= base ? 0 : (lo - base + w - 1) / w;
+		long long u_hi = hi <= base ? 0 : (hi - base + w - 1) / w;
+		u_lo = u_lo > units ? units : u_lo;
+		u_hi = u_hi > units ? units : u_hi;
+		if (u_hi > u_lo) {
+			if (it.remaining == 0) {
+				it.cid = c;
+				it.nb = nb;
+				it.tile = (int)(u_lo / nb);
+				it.batch = (int)(u_lo % nb);
+			}
+			it.remaining += (int)(u_hi - u_lo);
 		}
-		int nb = (cls[c].count + cf.vb - 1) / cf.vb;
-		int u = nb * cf.n_tiles;
-		if (skip >= u) {
-			skip -= u;
-			continue;
-		}
-		it.cid = c;
-		it.nb = nb;
-		it.tile = skip / nb;
-		it.batch = skip % nb;
-		break;
+		base += units * w;
 	}
 }
 
@@ -154,12 +192,10 @@ __device__ __forceinline__ void unit_iter_next(UnitIter &it, const ClassInfo *cl
 		return;
 	}
 	it.tile = 0;
-	for (int c = it.cid + 1; c < GAS_MAX_CLASSES; c++) {
-		if (cls[c].key != 0ULL && cls[c].path == PATH_STREAM && cls[c].count > 0) {
-			it.cid = c;
-			it.nb = (cls[c].count + cf.vb - 1) / cf.vb;
-			return;
-		}
+	if (it.cid + 1 < it.n_cls) {
+		it.cid++;
+		it.nb = (cls[it.cid].count + cf.vb - 1) / cf.vb;
+		return;
 	}
 	it.remaining = 0;
 }
@@ -169,15 +205,15 @@ __device__ __forceinline__ void unit_iter_next(UnitIter &it, const ClassInfo *cl
 struct IdxBlock {
 	int first_seq; // sequence number (within this CTA) of the first unit covered
 	int n_units;
-	int val;
+	int2 val; // {call-order index, source row}
 };
 
-__device__ __forceinline__ IdxBlock idx_block_load(UnitIter &pf, const ClassInfo *cls, const StreamCfg &cf, const int32_t *__restrict__ k2_src,
+__device__ __forceinline__ IdxBlock idx_block_load(UnitIter &pf, const ClassInfo *cls, const StreamCfg &cf, const int2 *__restrict__ list,
 		int maxv, int lane, int seq) {
 	IdxBlock b;
 	b.first_seq = seq;
 	b.n_units = 0;
-	b.val = 0;
+	b.val = make_int2(0, 0);
 	if (pf.remaining <= 0) {
 		return b;
 	}
@@ -185,7 +221,7 @@ __device__ __forceinline__ IdxBlock idx_block_load(UnitIter &pf, const ClassInfo
 	const int n = min(upb, min(pf.nb - pf.batch, pf.remaining));
 	const int pos = pf.batch * cf.vb + lane;
 	if (lane < n * cf.vb && pos < cls[pf.cid].count) {
-		b.val = __ldg(k2_src + (size_t)pf.cid * maxv + pos);
+		b.val = __ldg(list + (size_t)cls[pf.cid].slot * maxv + pos);
 	}
 	b.n_units = n;
 	for (int i = 0; i < n; i++) {
@@ -195,14 +231,17 @@ __device__ __forceinline__ IdxBlock idx_block_load(UnitIter &pf, const ClassInfo
 }
 
 struct ConsumerCtx {
-	const unsigned char *smem;
+	unsigned char *smem;    // stage ring
+	unsigned char *staging; // flush staging (2 slots)
 	uint64_t *full;
 	uint64_t *empty;
 	const ClassInfo *cls;
-	int C, lane, slot, group;
+	int C, tid, lane, slot, group;
 	bool worker;
 	int stage;
 	uint32_t phase;
+	uint32_t flushes; // bulk reduce groups committed so far (thread 0 is the issuer)
+	unsigned long long *tl;
 };
 
 // One run = every consecutive unit of this CTA that shares (class, tile).  NP = (L,R) weight pairs per
@@ -218,7 +257,7 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 	}
 	const int cid = it.cid, tile = it.tile;
 	const ClassInfo &ci = cc.cls[cid];
-	const int tile_w = min(cf.tile_frames, cf.frames - tile * kTileFrames);
+	const int tile_w = min(cf.tile_frames, cf.frames - tile * cf.tile_frames);
 	const int row_bytes = tile_w * 8;
 	const bool mine = cc.worker && cc.slot * 2 < tile_w;
 	do {
@@ -227,7 +266,11 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		const unsigned char *sx = cc.smem + (size_t)cc.stage * cf.stage_bytes;
 		const unsigned char *sw = sx + cf.x_bytes;
 		mbar_wait(&cc.full[cc.stage], cc.phase);
+		if (cc.tl && cc.tl[2] == 0ULL) {
+			cc.tl[2] = gtime();
+		}
 		if (mine && !(cf.debug & 2)) {
+#pragma unroll 2
 			for (int v = cc.group; v < nv; v += cf.groups) {
 				const float4 x = *reinterpret_cast<const float4 *>(sx + (size_t)v * row_bytes + cc.slot * 16);
 				const float2 x0 = make_float2(x.x, x.y), x1 = make_float2(x.z, x.w);
@@ -262,25 +305,35 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		}
 		unit_iter_next(it, cc.cls, cf);
 	} while (it.remaining > 0 && it.cid == cid && it.tile == tile);
-
-	if (!mine || (cf.debug & 1)) {
+	if (cc.tl) {
+		cc.tl[3] = gtime();
+	}
+	if (cf.debug & 1) {
 		return;
 	}
 	// ---- flush: bus[b][c][i] += A + B t (+ C t^2), rows ordered [group][poly][pair] --------------------
 	const int C = cc.C, F = cf.frames;
-	const int frame0 = tile * kTileFrames + cc.slot * 2;
+	const int frame0 = tile * cf.tile_frames + cc.slot * 2;
 	const float t0 = (float)frame0 / (float)F;
 	const float t1 = (float)(frame0 + 1) / (float)F;
-	const bool lin = (ci.flags & CLS_LIN) != 0;
 	const bool shared = (ci.flags & CLS_SHARED) != 0;
-	const int P = lin ? 2 : 3;
-	const int G = NP / (P * C); // row groups
+	const int RG = ci.n_group; // row groups; group k owns 2 rows (A, B) plus a t^2 row when its quad bit is set
 	uint32_t rest = ci.mask;
-	for (int k = 0; k < G; k++) {
+	int r0 = 0; // first row of group k
+	for (int k = 0; k < RG; k++) {
+		const bool quad = (ci.quad >> k) & 1u;
 		const int b_own = __ffs(rest) - 1; // k-th bus of the mask (sends ascend by bus)
 		rest &= rest - 1;
+		unsigned char *stg = cc.staging + (cc.flushes & 1u) * kStagingSlot;
+		if (cf.flush_mode == 1) {
+			// the reduce that read this staging slot two flushes ago must be done with it
+			if (cc.tid == 0) {
+				bulk_wait_read<1>();
+			}
+			consumer_barrier();
+		}
 		for (int c = 0; c < C; c++) {
-			const int pa = (k * P + 0) * C + c, pb = (k * P + 1) * C + c, pc = (k * P + 2) * C + c;
+			const int pa = (r0 + 0) * C + c, pb = (r0 + 1) * C + c, pc = (r0 + 2) * C + c;
 			float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0, c0 = a0, c1 = a0;
 #pragma unroll
 			for (int p = 0; p < NP; p++) { // static indexing only: the accumulators must stay in registers
@@ -292,34 +345,74 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 					b0 = acc[p][0];
 					b1 = acc[p][1];
 				}
-				if (!lin && p == pc) {
+				if (quad && p == pc) {
 					c0 = acc[p][0];
 					c1 = acc[p][1];
 				}
 			}
-			float2 v0, v1;
-			v0.x = fmaf(t0, fmaf(t0, c0.x, b0.x), a0.x);
-			v0.y = fmaf(t0, fmaf(t0, c0.y, b0.y), a0.y);
-			v1.x = fmaf(t1, fmaf(t1, c1.x, b1.x), a1.x);
-			v1.y = fmaf(t1, fmaf(t1, c1.y, b1.y), a1.y);
-			if (shared) { // one row group fanned out to every bus of the mask
-				uint32_t m = ci.mask;
+			float4 v;
+			v.x = fmaf(t0, fmaf(t0, c0.x, b0.x), a0.x);
+			v.y = fmaf(t0, fmaf(t0, c0.y, b0.y), a0.y);
+			v.z = fmaf(t1, fmaf(t1, c1.x, b1.x), a1.x);
+			v.w = fmaf(t1, fmaf(t1, c1.y, b1.y), a1.y);
+			if (cf.flush_mode == 1) {
+				// the warp groups of the CTA (different voices, same frames) are summed in shared memory first
+				float4 *dst = reinterpret_cast<float4 *>(stg + (size_t)c * row_bytes + cc.slot * 16);
+				for (int g = 0; g < cf.groups; g++) {
+					if (mine && cc.group == g) {
+						if (g > 0) {
+							const float4 o = *dst;
+							v.x += o.x;
+							v.y += o.y;
+							v.z += o.z;
+							v.w += o.w;
+						}
+						*dst = v;
+					}
+					if (cf.groups > 1) {
+						consumer_barrier();
+					}
+				}
+			} else if (mine) {
+				if (shared) { // one row group fanned out to every bus of the mask
+					uint32_t m = ci.mask;
+					while (m) {
+						const int b = __ffs(m) - 1;
+						m &= m - 1;
+						red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, v.x, v.y, v.z, v.w);
+					}
+				} else {
+					red_add_v4(bus + ((size_t)(b_own * C + c) * F + frame0) * 2, v.x, v.y, v.z, v.w);
+				}
+			}
+		}
+		if (cf.flush_mode == 1) {
+			fence_proxy_async(); // generic-proxy stores above -> async-proxy reads of the bulk reduce
+			consumer_barrier();
+			if (cc.tid == 0) {
+				const size_t tile_off = (size_t)tile * cf.tile_frames * 2;
+				uint32_t m = shared ? ci.mask : (1u << b_own);
 				while (m) {
 					const int b = __ffs(m) - 1;
 					m &= m - 1;
-					red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, v0.x, v0.y, v1.x, v1.y);
+					for (int c = 0; c < C; c++) {
+						bulk_red_add_f32(bus + (size_t)(b * C + c) * F * 2 + tile_off, stg + (size_t)c * row_bytes, (uint32_t)row_bytes);
+					}
 				}
-			} else {
-				red_add_v4(bus + ((size_t)(b_own * C + c) * F + frame0) * 2, v0.x, v0.y, v1.x, v1.y);
+				bulk_commit();
 			}
+			cc.flushes++;
 		}
+		r0 += quad ? 3 : 2;
 	}
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, GlobalCfg g, StreamCfg cf,
-		const gas_frame *__restrict__ src, float *__restrict__ bus, const int32_t *__restrict__ blk) {
+		const gas_frame *__restrict__ src, float *__restrict__ bus, int rep_stride, int replicas, const int32_t *__restrict__ blk) {
+	bus += (size_t)(blockIdx.x % replicas) * rep_stride;
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
+	__shared__ int s_ncls;
 	__shared__ __align__(8) uint64_t s_full[kMaxStages];
 	__shared__ __align__(8) uint64_t s_empty[kMaxStages];
 
@@ -327,10 +420,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 	const int warp = tid >> 5, lane = tid & 31;
 	const int C = g.channels;
 	const int maxv = g.max_voices;
-
-	if (tid < GAS_MAX_CLASSES) {
-		s_cls[tid] = plan.cls[((blk[0] + 1) & 1) * GAS_MAX_CLASSES + tid]; // the prologue already advanced the counter
+	unsigned long long *tl = (cf.debug & 8) && tid == 0 ? cf.timeline + blockIdx.x * 8 : nullptr;
+	if (tl) {
+		tl[0] = gtime();
 	}
+
 	if (tid == 0) {
 		for (int s = 0; s < cf.stages; s++) {
 			mbar_init(&s_full[s], 1);
@@ -338,13 +432,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	// programmatic dependent launch: the plan the prologue wrote is visible after this wait (a no-op when
+	// launched without the attribute)
+	GAS_GRID_DEP_WAIT();
+	if (warp == 0) {
+		// Compact table of the streaming classes of this block, in slot order (identical in every CTA).  The
+		// counts of both parities are fetched together with the block counter so that no load waits for another.
+		constexpr int R = GAS_MAX_CLASSES / 32;
+		unsigned long long key[R];
+		int cnt[2][R];
+		const int n = *(volatile const int32_t *)blk;
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			key[r] = plan.cls_key[r * 32 + lane];
+			cnt[0][r] = plan.cls_count[r * 32 + lane];
+			cnt[1][r] = plan.cls_count[GAS_MAX_CLASSES + r * 32 + lane];
+		}
+		const int par = (n + 1) & 1; // the prologue already advanced the counter
+		int base = 0;
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			const int count = par ? cnt[1][r] : cnt[0][r];
+			const bool on = key[r] != 0ULL && (int)(key[r] & 3u) == PATH_STREAM && count > 0;
+			const unsigned m = __ballot_sync(0xffffffffu, on);
+			if (on) {
+				ClassInfo ci = cls_decode(key[r], count);
+				ci.slot = r * 32 + lane;
+				s_cls[base + __popc(m & ((1u << lane) - 1u))] = ci;
+			}
+			base += __popc(m);
+		}
+		if (lane == 0) {
+			s_ncls = base;
+		}
+	}
 	__syncthreads();
+	GAS_GRID_DEP_LAUNCH();
 
 	UnitIter it;
-	unit_iter_init(it, s_cls, cf, blockIdx.x, gridDim.x);
+	unit_iter_init(it, s_cls, s_ncls, cf, C, blockIdx.x, gridDim.x);
+	if (tl) {
+		tl[1] = gtime();
+		tl[5] = (unsigned long long)it.remaining;
+	}
 	if (it.remaining <= 0) {
 		return;
 	}
+	unsigned char *ring = smem + kStagingBytes;
 
 	if (warp == kConsumerWarps) {
 		// ===== producer =====
@@ -353,33 +487,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		// Source-row indices are fetched one warp-wide load (32 list positions = 32/vb units) at a time,
 		// two blocks ahead of the copies that need them, so the gather indirection never stalls the ring.
 		UnitIter pf = it;
-		IdxBlock cur = idx_block_load(pf, s_cls, cf, plan.k2_src, maxv, lane, 0);
-		IdxBlock nxt = idx_block_load(pf, s_cls, cf, plan.k2_src, maxv, lane, cur.n_units);
+		IdxBlock cur = idx_block_load(pf, s_cls, cf, plan.list, maxv, lane, 0);
+		IdxBlock nxt = idx_block_load(pf, s_cls, cf, plan.list, maxv, lane, cur.n_units);
 		int seq = 0;
 		while (it.remaining > 0) {
 			if (seq >= cur.first_seq + cur.n_units) {
 				cur = nxt;
-				nxt = idx_block_load(pf, s_cls, cf, plan.k2_src, maxv, lane, cur.first_seq + cur.n_units);
+				nxt = idx_block_load(pf, s_cls, cf, plan.list, maxv, lane, cur.first_seq + cur.n_units);
 			}
 			const ClassInfo &ci = s_cls[it.cid];
 			const int v0 = it.batch * cf.vb;
 			const int nv = min(cf.vb, ci.count - v0);
-			const int tile_w = min(cf.tile_frames, cf.frames - it.tile * kTileFrames); // frames in this tile
+			const int tile_w = min(cf.tile_frames, cf.frames - it.tile * cf.tile_frames); // frames in this tile
 			const uint32_t row_bytes = (uint32_t)tile_w * 8u;
 			const int nf = ci.n_rows * C * 2; // floats of weights per voice
 			const uint32_t w_bytes = ((uint32_t)(nv * nf * 4) + 15u) & ~15u;
-			unsigned char *sx = smem + (size_t)stage * cf.stage_bytes;
+			unsigned char *sx = ring + (size_t)stage * cf.stage_bytes;
 			unsigned char *sw = sx + cf.x_bytes;
 			mbar_wait(&s_empty[stage], phase ^ 1u);
 			if (lane == 0) {
 				mbar_arrive_expect_tx(&s_full[stage], row_bytes * (uint32_t)nv + w_bytes);
-				bulk_g2s(sw, plan.k2_rows + (size_t)it.cid * maxv * GAS_K2_ROW_FLOATS + (size_t)v0 * nf, w_bytes, &s_full[stage]);
+				bulk_g2s(sw, plan.k2_rows + (size_t)ci.slot * maxv * GAS_K2_ROW_FLOATS + (size_t)v0 * nf, w_bytes, &s_full[stage]);
 			}
 			__syncwarp();
 			{
 				const int v = lane - (seq - cur.first_seq) * cf.vb; // this lane's voice inside the stage
 				if (v >= 0 && v < nv) {
-					bulk_g2s(sx + (size_t)v * row_bytes, src + (size_t)cur.val * cf.src_stride + (size_t)it.tile * kTileFrames, row_bytes,
+					bulk_g2s(sx + (size_t)v * row_bytes, src + (size_t)cur.val.y * cf.src_stride + (size_t)it.tile * cf.tile_frames, row_bytes,
 							&s_full[stage]);
 				}
 			}
@@ -393,7 +527,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 	} else {
 		// ===== consumers =====
 		ConsumerCtx cc;
-		cc.smem = smem;
+		cc.smem = ring;
+		cc.staging = smem;
+		cc.tid = tid;
+		cc.flushes = 0;
+		cc.tl = tl;
 		cc.full = s_full;
 		cc.empty = s_empty;
 		cc.cls = s_cls;
@@ -410,29 +548,52 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 				case 2: consumer_run<2>(it, cc, cf, bus); break;
 				case 3: consumer_run<3>(it, cc, cf, bus); break;
 				case 4: consumer_run<4>(it, cc, cf, bus); break;
+				case 5: consumer_run<5>(it, cc, cf, bus); break;
 				case 6: consumer_run<6>(it, cc, cf, bus); break;
 				case 8: consumer_run<8>(it, cc, cf, bus); break;
 				case 9: consumer_run<9>(it, cc, cf, bus); break;
+				case 10: consumer_run<10>(it, cc, cf, bus); break;
 				case 12: consumer_run<12>(it, cc, cf, bus); break;
+				case 15: consumer_run<15>(it, cc, cf, bus); break;
 				case 16: consumer_run<16>(it, cc, cf, bus); break;
 				case 18: consumer_run<18>(it, cc, cf, bus); break;
+				case 20: consumer_run<20>(it, cc, cf, bus); break;
 				case 24: consumer_run<24>(it, cc, cf, bus); break;
 				default: // cannot happen (rows in {2,3,4,6} x pairs in {1..4}); drain so the producer never stalls
 					consumer_run<1>(it, cc, cf, bus);
 					break;
 			}
 		}
+		if (tl) {
+			tl[4] = gtime();
+		}
+		if (tid == 0 && cc.flushes > 0) {
+			bulk_wait_all(); // the staging slots must outlive the reads; the adds are complete when the grid is
+		}
 	}
 }
 
 } // namespace
 
+static int env_int(const char *name, int dflt, int lo, int hi) {
+	const char *e = getenv(name);
+	if (!e || !*e) {
+		return dflt;
+	}
+	const int v = atoi(e);
+	return v < lo ? lo : (v > hi ? hi : v);
+}
+
 static StreamCfg make_cfg(int frames, int src_stride, int smem_limit) {
 	StreamCfg cf{};
 	cf.frames = frames;
 	cf.src_stride = src_stride;
-	cf.tile_frames = frames < kTileFrames ? frames : kTileFrames;
-	cf.n_tiles = (frames + kTileFrames - 1) / kTileFrames;
+	// Frame tile: 512 (4 KB copies) streams fastest; narrower tiles (GAS_K2_TILE) trade copy size for less
+	// reduction traffic into the bus buffers.
+	int tile = env_int("GAS_K2_TILE", kTileFrames, 64, kTileFrames);
+	tile = tile >= 512 ? 512 : (tile >= 256 ? 256 : (tile >= 128 ? 128 : 64));
+	cf.tile_frames = frames < tile ? frames : tile;
+	cf.n_tiles = (frames + cf.tile_frames - 1) / cf.tile_frames;
 	cf.slots = cf.tile_frames / 2;
 	cf.groups = kConsumerThreads / cf.slots;
 	if (cf.groups < 1) {
@@ -444,27 +605,23 @@ static StreamCfg make_cfg(int frames, int src_stride, int smem_limit) {
 	cf.x_bytes = vb * cf.tile_frames * 8;
 	cf.w_bytes = (vb * kMaxPairs * 8 + 127) & ~127;
 	cf.stage_bytes = cf.x_bytes + cf.w_bytes;
-	int stages = smem_limit / cf.stage_bytes;
+	int stages = (smem_limit - kStagingBytes) / cf.stage_bytes;
 	cf.stages = stages > kMaxStages ? kMaxStages : stages;
-	if (const char *e = getenv("GAS_K2_STAGES")) {
-		int v = atoi(e);
-		if (v >= 2 && v <= cf.stages) {
-			cf.stages = v;
-		}
-	}
-	if (const char *e = getenv("GAS_K2_DEBUG")) {
-		cf.debug = atoi(e);
-	}
+	// tuning / experiment knobs (environment, read per launch: they never change results, only schedules)
+	cf.stages = env_int("GAS_K2_STAGES", cf.stages, 2, cf.stages);
+	cf.fixed_cost = env_int("GAS_K2_FIXED_COST", 8, 0, 1024);
+	cf.flush_mode = env_int("GAS_K2_FLUSH", 0, 0, 1);
+	cf.debug = env_int("GAS_K2_DEBUG", 0, 0, 15);
 	return cf;
 }
 
 cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, cudaStream_t st) {
-	static const int kSmemLimit = 208 * 1024;
+	static const int kSmemLimit = 216 * 1024;
 	StreamCfg cf = make_cfg(frames, src_stride, kSmemLimit);
 	if (cf.stages < 2) {
 		return cudaErrorInvalidConfiguration;
 	}
-	const size_t smem = (size_t)cf.stages * cf.stage_bytes;
+	const size_t smem = (size_t)kStagingBytes + (size_t)cf.stages * cf.stage_bytes;
 	if (!ctx->k2_smem_attr_set) {
 		cudaError_t e = cudaFuncSetAttribute(k_mix_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
 		if (e != cudaSuccess) {
@@ -472,7 +629,18 @@ cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stri
 		}
 		ctx->k2_smem_attr_set = true;
 	}
-	k_mix_stream<<<ctx->num_sms, kThreads, smem, st>>>(ctx->plan, ctx->g, cf, d_src, (float *)d_bus, ctx->t.blk);
+	// partial sums go to replica (CTA % replicas) of the bus layout: fewer CTAs contend for the same addresses
+	float *target = ctx->replicas > 1 ? (float *)ctx->d_rep : (float *)d_bus;
+	const int rep_stride = ctx->replicas > 1 ? gas_bus_f4(ctx, frames) * 4 : 0; // floats
+	if (cf.debug & 8) {
+		if (!ctx->d_timeline) {
+			cudaMalloc((void **)&ctx->d_timeline, 256 * 8 * sizeof(unsigned long long));
+		}
+		cudaMemsetAsync(ctx->d_timeline, 0, 256 * 8 * sizeof(unsigned long long), st);
+		cf.timeline = ctx->d_timeline;
+	}
+	cudaError_t e = gas_launch(k_mix_stream, dim3(ctx->num_sms), dim3(kThreads), smem, st, ctx->pdl, ctx->plan, ctx->g, cf, d_src, target,
+			rep_stride, ctx->replicas, (const int32_t *)ctx->t.blk);
 	ctx->launches++;
-	return cudaGetLastError();
+	return e;
 }

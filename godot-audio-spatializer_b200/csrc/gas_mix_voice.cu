@@ -64,7 +64,8 @@ struct Pow2Ceil {
 
 struct ChunkArgs {
 	const VoiceRec *rec;
-	const int32_t *list;  // class list (call-order indices)
+	const InstSends *sends; // by call-order index
+	const int2 *list;     // class list {call-order index, source row}
 	int count;            // voices in the class
 	int chunk;            // which 32-voice chunk
 	uint32_t cls_flags;
@@ -80,7 +81,7 @@ __device__ void voice_pass(const DevTables &t, const GlobalCfg &g, const ChunkAr
 	const int lane = threadIdx.x & 31;
 	const int pos = a.chunk * 32 + lane;
 	const bool active = pos < a.count;
-	const int j = active ? a.list[pos] : -1;
+	const int j = active ? a.list[pos].x : -1;
 	constexpr int NY = (MODE == MODE_B) ? C : 1; // distinct processed streams per voice (pairs)
 	constexpr int NPROC = NY * 2;
 
@@ -107,7 +108,7 @@ __device__ void voice_pass(const DevTables &t, const GlobalCfg &g, const ChunkAr
 	float np[NS][C][2], nn[NS][C][2];
 	int bus_of[NS];
 	{
-		const InstSends *snd = &t.inst_sends[r.instance];
+		const InstSends *snd = &a.sends[active ? j : 0];
 		uint32_t m = a.mask;
 		for (int s = 0; s < send0; s++) {
 			m &= m - 1;
@@ -345,21 +346,65 @@ __device__ void voice_chunk(const DevTables &t, const GlobalCfg &g, const ChunkA
 
 template <int C>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_mix_voice(DevTables t, GlobalCfg g, BlockPlan plan,
-		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks) {
+		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks,
+		const float4 *__restrict__ rep, int bus_f4, int replicas) {
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
-	if (threadIdx.x < GAS_MAX_CLASSES) {
-		s_cls[threadIdx.x] = plan.cls[((t.blk[0] + 1) & 1) * GAS_MAX_CLASSES + threadIdx.x]; // the prologue already advanced the counter
+	__shared__ int s_ncls;
+	GAS_GRID_DEP_WAIT();
+	GAS_GRID_DEP_LAUNCH();
+	// fold the streaming kernel's replica buffers into the bus buffers: one vector reduction per 16 bytes
+	if (replicas > 1) {
+		const int i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i < bus_f4) {
+			float4 a = rep[i];
+			for (int r = 1; r < replicas; r++) {
+				const float4 b = rep[(size_t)r * bus_f4 + i];
+				a.x += b.x;
+				a.y += b.y;
+				a.z += b.z;
+				a.w += b.w;
+			}
+			asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(bus + (size_t)i * 4), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+		}
+	}
+	if (threadIdx.x < 32) {
+		// compact table of the voice-parallel classes of this block, in slot order (identical in every CTA)
+		const int lane = threadIdx.x;
+		constexpr int R = GAS_MAX_CLASSES / 32;
+		unsigned long long key[R];
+		int cnt[2][R];
+		const int n = *(volatile const int32_t *)t.blk;
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			key[r] = plan.cls_key[r * 32 + lane];
+			cnt[0][r] = plan.cls_count[r * 32 + lane];
+			cnt[1][r] = plan.cls_count[GAS_MAX_CLASSES + r * 32 + lane];
+		}
+		const int par = (n + 1) & 1; // the prologue already advanced the counter
+		int base = 0;
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			const int count = par ? cnt[1][r] : cnt[0][r];
+			const bool on = key[r] != 0ULL && (int)(key[r] & 3u) == PATH_VOICE && count > 0;
+			const unsigned m = __ballot_sync(0xffffffffu, on);
+			if (on) {
+				ClassInfo ci = cls_decode(key[r], count);
+				ci.slot = r * 32 + lane;
+				s_cls[base + __popc(m & ((1u << lane) - 1u))] = ci;
+			}
+			base += __popc(m);
+		}
+		if (lane == 0) {
+			s_ncls = base;
+		}
 	}
 	__syncthreads();
 	const int warp_global = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
 	const int n_warps = gridDim.x * kWarpsPerCta;
 	// units: 32-voice chunks of every PATH_VOICE class, dealt round-robin to warps
 	int unit = 0;
-	for (int c = 0; c < GAS_MAX_CLASSES; c++) {
+	for (int c = 0; c < s_ncls; c++) {
 		const ClassInfo &ci = s_cls[c];
-		if (ci.key == 0ULL || ci.path != PATH_VOICE) {
-			continue;
-		}
 		const int chunks = (ci.count + 31) / 32;
 		for (int k = 0; k < chunks; k++, unit++) {
 			if (unit % n_warps != warp_global) {
@@ -367,7 +412,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_mix_voice(DevTables t, Gl
 			}
 			ChunkArgs a;
 			a.rec = plan.rec;
-			a.list = plan.k3_list + (size_t)c * g.max_voices;
+			a.sends = plan.sends;
+			a.list = plan.list + (size_t)ci.slot * g.max_voices;
 			a.count = ci.count;
 			a.chunk = k;
 			a.cls_flags = ci.flags;
@@ -392,21 +438,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_mix_voice(DevTables t, Gl
 
 cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus,
 		gas_frame *d_peaks, cudaStream_t st) {
-	const int grid = ctx->num_sms * 4;
+	const int bus_f4 = gas_bus_f4(ctx, frames);
+	int grid = ctx->num_sms * 4;
+	if (grid * kWarpsPerCta * 32 < bus_f4) {
+		grid = (bus_f4 + kWarpsPerCta * 32 - 1) / (kWarpsPerCta * 32);
+	}
+	cudaError_t e = cudaSuccess;
 	switch (ctx->g.channels) {
 		case 1:
-			k_mix_voice<1><<<grid, kWarpsPerCta * 32, 0, st>>>(ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks);
+			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas);
 			break;
 		case 2:
-			k_mix_voice<2><<<grid, kWarpsPerCta * 32, 0, st>>>(ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks);
+			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas);
 			break;
 		case 3:
-			k_mix_voice<3><<<grid, kWarpsPerCta * 32, 0, st>>>(ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks);
+			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas);
 			break;
 		default:
-			k_mix_voice<4><<<grid, kWarpsPerCta * 32, 0, st>>>(ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks);
+			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas);
 			break;
 	}
 	ctx->launches++;
-	return cudaGetLastError();
+	return e;
 }

@@ -1,94 +1,129 @@
-// gas_prologue.cu — per-block prologue (one fused kernel): turns the current parameters + persistent ramp
-// state into the block's plan (classes, weight rows, voice records) and advances the ramp state.
+// gas_prologue.cu — per-block prologue (one kernel): turns the current parameters + persistent ramp state
+// into the block's plan (classes, weight rows, voice records) and advances the ramp state.
 //
-//   instance part (thread q < inst_hwm): the AudioServer side of a mix step for the instance's proxy
-//       playbacks — previous volume looked up by bus, buses that disappeared fade to 0, then prev <- cur
-//       (upstream AudioServer::_mix_step).  prev is double-buffered by block parity:
-//       this block reads inst_prev[p] and writes inst_prev[1-p], so the voice part of other threads can
-//       read the old value without a grid-wide barrier.
-//   voice part (thread j < n_voices): what process_frames / mix_channel decide before their sample loop
-//       (reference audio_spatializer_3d.cpp:499-523, :562-587, :537-551, :608): ramp end points, filter
-//       on/off, clear-history, target coefficients; classifies the voice and appends it to its class list.
-//   The kernel also zeroes the bus buffers / peaks, clears the class table of the NEXT block, and its
-//   last CTA advances the block counter.
+// Work is laid out 8 lanes per voice (lane = channel pair * 2 + side), 64 voices per CTA, so that every
+// table access of a voice is one 32-byte segment and nothing lives in local memory:
+//   voice part: what process_frames / mix_channel decide before their sample loop (reference
+//       audio_spatializer_3d.cpp:499-523, :562-587, :537-551, :608): ramp end points, filter on/off,
+//       clear-history, target coefficients — plus the AudioServer side of the instance's proxy playbacks
+//       for this mix step (upstream AudioServer::_mix_step): previous volume looked up
+//       by bus, buses that disappeared fade to 0.  The voice is classified by what its weights look like
+//       and appended to its class list (CTA-level aggregation in shared memory, one global atomic per
+//       class per CTA).
+//   instance part: prev <- cur of the bus details.  prev is double-buffered by block parity: this block
+//       reads inst_prev[p] and writes inst_prev[1-p], so no grid-wide barrier is needed.
+//   The kernel also zeroes the bus buffers / peaks, clears the class table of the NEXT block, and its last
+//   CTA advances the block counter.
 //
 // Compiled with -fmad=false (coefficient preparation is double arithmetic narrowed to float).
 #include "gas_internal.h"
 
 namespace {
 
+constexpr int kLanes = 8;          // lanes per voice
+constexpr int kVoicesPerCta = 64;
+constexpr int kCtaThreads = kLanes * kVoicesPerCta;
+constexpr int kBigKey = 0x7fffffff;
+
 __device__ __forceinline__ int resolve_bus(const GlobalCfg &g, int bus) {
 	return (bus >= 0 && bus < g.num_buses) ? bus : 0;
 }
 
-// Sends of one instance for this block: every bus of the current details with the previous volume
-// looked up by bus (absent => 0 => fade-in), then buses only present in the previous details once more
-// towards 0 (fade-out); ascending by bus so that a class is identified by its bus mask.
-__device__ void resolve_sends(const BusDetails &cur, const BusDetails &prev, const GlobalCfg &g, InstSends &s) {
-	s.n = 0;
-	s.mask = 0;
-	for (int k = 0; k < cur.n; k++) {
-		int pk = -1;
-		for (int j = 0; j < prev.n; j++) {
-			if (prev.bus[j] == cur.bus[k]) {
-				pk = j;
-			}
-		}
-		const int slot = s.n++;
-		s.bus[slot] = resolve_bus(g, cur.bus[k]);
-		for (int c = 0; c < 4; c++) {
-			for (int x = 0; x < 2; x++) {
-				s.vp[slot][c][x] = pk >= 0 ? prev.vol[pk][c][x] : 0.f;
-				s.vn[slot][c][x] = cur.vol[k][c][x];
-			}
-		}
-	}
-	for (int j = 0; j < prev.n; j++) {
-		bool still = false;
-		for (int k = 0; k < cur.n; k++) {
-			still |= (cur.bus[k] == prev.bus[j]);
-		}
-		if (still) {
-			continue;
-		}
-		const int slot = s.n++;
-		s.bus[slot] = resolve_bus(g, prev.bus[j]);
-		for (int c = 0; c < 4; c++) {
-			for (int x = 0; x < 2; x++) {
-				s.vp[slot][c][x] = prev.vol[j][c][x];
-				s.vn[slot][c][x] = 0.f;
-			}
-		}
-	}
-	for (int a = 1; a < s.n; a++) { // insertion sort, <= 12 entries
-		for (int b = a; b > 0 && s.bus[b - 1] > s.bus[b]; b--) {
-			const int tb = s.bus[b];
-			s.bus[b] = s.bus[b - 1];
-			s.bus[b - 1] = tb;
-			for (int c = 0; c < 4; c++) {
-				for (int x = 0; x < 2; x++) {
-					const float tp = s.vp[b][c][x], tn = s.vn[b][c][x];
-					s.vp[b][c][x] = s.vp[b - 1][c][x];
-					s.vn[b][c][x] = s.vn[b - 1][c][x];
-					s.vp[b - 1][c][x] = tp;
-					s.vn[b - 1][c][x] = tn;
-				}
-			}
-		}
-	}
-	for (int k = 0; k < s.n; k++) {
-		s.mask |= 1u << s.bus[k];
+// The bus details of one instance as this lane sees them: counts and bus ids (same in the 8 lanes of a
+// voice) plus this lane's (pair, side) element of every volume.  Loaded unconditionally (all 6 slots) so
+// that every load of the kernel is in flight at once; entries beyond n are ignored.
+struct LaneDetails {
+	int n;
+	int bus[GAS_MAX_BUSES_PER_PLAYBACK];
+	float vol[GAS_MAX_BUSES_PER_PLAYBACK];
+};
+
+__device__ __forceinline__ void details_load_lane(LaneDetails &d, const BusDetails *__restrict__ src, int c, int x) {
+	d.n = src->n;
+#pragma unroll
+	for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+		d.bus[k] = src->bus[k];
+		d.vol[k] = src->vol[k][c][x];
 	}
 }
 
-// only the first `n` entries of a BusDetails are meaningful: load just those
-__device__ __forceinline__ void details_load(BusDetails &d, const BusDetails *src) {
-	d.n = src->n;
-	for (int k = 0; k < d.n && k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
-		d.bus[k] = src->bus[k];
-		for (int c = 0; c < 4; c++) {
-			d.vol[k][c][0] = src->vol[k][c][0];
-			d.vol[k][c][1] = src->vol[k][c][1];
+// This lane's element (pair c, side x) of the sends of one instance for this block: every bus of the
+// current details with the previous volume looked up by bus (absent => 0 => fade-in), then buses only
+// present in the previous details once more towards 0 (fade-out); ascending by (bus, appearance) so that
+// a class is identified by its bus mask.  All loops are fully unrolled: everything stays in registers.
+struct LaneSends {
+	int n;
+	uint32_t mask;
+	int bus[GAS_MAX_SENDS];
+	float vp[GAS_MAX_SENDS];
+	float vn[GAS_MAX_SENDS];
+};
+
+// K = number of detail slots examined on each side: the kernel uses K = 2 when neither side has more than two
+// buses (almost always) and the full 6 otherwise; the result is the same, the unrolled code is 9x shorter.
+template <int K>
+__device__ __forceinline__ void resolve_sends_lane(const LaneDetails &cur, const LaneDetails &prev, const GlobalCfg &g, LaneSends &s) {
+	int cn = cur.n, pn = prev.n;
+	cn = cn < 0 ? 0 : (cn > K ? K : cn);
+	pn = pn < 0 ? 0 : (pn > K ? K : pn);
+	int ckey[K], pkey[K];
+	float cvp[K];
+	int total = cn;
+#pragma unroll
+	for (int k = 0; k < K; k++) {
+		ckey[k] = k < cn ? resolve_bus(g, cur.bus[k]) * 16 + k : kBigKey;
+		cvp[k] = 0.f;
+#pragma unroll
+		for (int j = 0; j < K; j++) {
+			if (k < cn && j < pn && prev.bus[j] == cur.bus[k]) {
+				cvp[k] = prev.vol[j]; // the last match wins, like a lookup that keeps scanning
+			}
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < K; j++) {
+		bool only = j < pn;
+#pragma unroll
+		for (int k = 0; k < K; k++) {
+			if (k < cn && cur.bus[k] == prev.bus[j]) {
+				only = false;
+			}
+		}
+		pkey[j] = only ? resolve_bus(g, prev.bus[j]) * 16 + K + j : kBigKey;
+		total += only ? 1 : 0;
+	}
+	s.n = total;
+	s.mask = 0;
+	int last = -1;
+#pragma unroll
+	for (int i = 0; i < GAS_MAX_SENDS; i++) {
+		s.bus[i] = 0;
+		s.vp[i] = 0.f;
+		s.vn[i] = 0.f;
+		if (i < 2 * K && i < total) { // uniform over the 8 lanes of a voice
+			int best = kBigKey;
+			float bp = 0.f, bn = 0.f;
+#pragma unroll
+			for (int k = 0; k < K; k++) {
+				if (ckey[k] > last && ckey[k] < best) {
+					best = ckey[k];
+					bp = cvp[k];
+					bn = cur.vol[k];
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < K; j++) {
+				if (pkey[j] > last && pkey[j] < best) {
+					best = pkey[j];
+					bp = prev.vol[j];
+					bn = 0.f;
+				}
+			}
+			s.bus[i] = best >> 4;
+			s.vp[i] = bp;
+			s.vn[i] = bn;
+			s.mask |= 1u << (best >> 4);
+			last = best;
 		}
 	}
 }
@@ -208,222 +243,254 @@ __device__ void prepare_coefficients(int mode, float cutoff, float resonance, fl
 	out[4] = (float)((double)a2 / (0.0 - a0));
 }
 
-__device__ int class_find_or_insert(ClassInfo *cls, unsigned long long key, int *overflow) {
-	for (int i = 0; i < GAS_MAX_CLASSES; i++) {
-		unsigned long long k = *(volatile unsigned long long *)&cls[i].key;
-		if (k == key) {
-			return i;
-		}
-		if (k == 0ULL) {
-			k = atomicCAS(&cls[i].key, 0ULL, key);
-			if (k == 0ULL || k == key) {
-				return i;
-			}
-		}
-	}
-	*overflow = 1;
-	return -1;
+// reductions over the 8 lanes of one voice (gm = those lanes' bits in the warp)
+__device__ __forceinline__ int group_or(unsigned gm, int v) {
+	v |= __shfl_xor_sync(gm, v, 1);
+	v |= __shfl_xor_sync(gm, v, 2);
+	v |= __shfl_xor_sync(gm, v, 4);
+	return v;
 }
 
+__global__ void __launch_bounds__(kCtaThreads, 2) k_prologue(DevTables t, GlobalCfg g, BlockPlan plan, int inst_hwm, int n_voices,
+		const gas_voice *__restrict__ voices, int src_rows, float4 *__restrict__ bus, int bus_f4, float4 *__restrict__ rep, int rep_f4,
+		float2 *__restrict__ peaks) {
+	__shared__ unsigned long long s_key[kVoicesPerCta];  // classes met in this CTA
+	__shared__ int s_cnt[kVoicesPerCta], s_cid[kVoicesPerCta], s_base[kVoicesPerCta];
+	__shared__ unsigned long long s_gkey[GAS_MAX_CLASSES]; // snapshot of the global slot table
+	__shared__ int s_parity;
 
-__global__ void __launch_bounds__(128) k_prologue(DevTables t, GlobalCfg g, BlockPlan plan, int inst_hwm, int n_voices,
-		const gas_voice *__restrict__ voices, int src_rows, float4 *__restrict__ bus, int bus_f4, float2 *__restrict__ peaks) {
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int nthreads = gridDim.x * blockDim.x;
-	const unsigned lane = threadIdx.x & 31u;
+	const int grp = threadIdx.x >> 3;       // voice slot inside the CTA
+	const int l = threadIdx.x & 7;          // lane of the voice
+	const int c = l >> 1, x = l & 1;        // channel pair, side
+	const unsigned gm = 0xffu << (threadIdx.x & 24);
 	const int C = g.channels;
 	const int maxv = g.max_voices;
-	const int parity = t.blk[0] & 1;
-	ClassInfo *cls = plan.cls + parity * GAS_MAX_CLASSES;
+	const int j = blockIdx.x * kVoicesPerCta + grp;
+	int blk_n = 0, ticket = -1;
+
+	GAS_GRID_DEP_WAIT(); // programmatic dependent launch: the previous block's kernels are complete after this
+	GAS_GRID_DEP_LAUNCH();
+
+	// ---- level 0: everything that needs no other load -------------------------------------------------------
+	gas_voice v{};
+	v.voice = -1;
+	if (j < n_voices) {
+		v = voices[j];
+	}
+	if (threadIdx.x == 0) {
+		// Block counter: read it, then take this CTA's ticket.  The last CTA to take one advances the counter
+		// for the kernels that follow; every CTA has read the old value by then (its read precedes its ticket).
+		blk_n = *(volatile int32_t *)&t.blk[0];
+		s_parity = blk_n & 1;
+		ticket = atomicAdd(&t.blk[1], 1); // consumed at the very end: nothing waits for this round trip
+	}
+	if (threadIdx.x < GAS_MAX_CLASSES) {
+		s_gkey[threadIdx.x] = plan.cls_key[threadIdx.x];
+	}
+	if (threadIdx.x < kVoicesPerCta) {
+		s_key[threadIdx.x] = 0ULL;
+		s_cnt[threadIdx.x] = 0;
+		s_cid[threadIdx.x] = -1;
+		s_base[threadIdx.x] = 0;
+	}
+	const int qi = blockIdx.x * kVoicesPerCta + grp; // instance part: one instance per 8-lane group
+	int i_active = 0;
+	LaneDetails icur;
+	icur.n = 0;
+	if (qi < inst_hwm) {
+		i_active = t.inst_active[qi];
+		details_load_lane(icur, &t.inst_cur[qi], c, x);
+	}
+	__syncthreads();
+	const int parity = s_parity;
+	int32_t *cnt_now = plan.cls_count + parity * GAS_MAX_CLASSES;
 	const BusDetails *prev_rd = t.inst_prev + (size_t)parity * t.max_instances;
 	BusDetails *prev_wr = t.inst_prev + (size_t)(parity ^ 1) * t.max_instances;
 
-	// ---- housekeeping -------------------------------------------------------------------------------
+	// ---- level 1: everything behind the voice record ------------------------------------------------------------
+	const bool valid = v.voice >= 0 && v.voice < maxv && v.instance >= 0 && v.instance < g.max_instances;
+	const int q = valid ? v.instance : 0;
+	const int vslot = valid ? v.voice : 0;
+	const int v_active = t.inst_active[q];
+	const int imode = t.inst_mode[q];
+	const gas_params *prm = &t.inst_params[q];
+	const float lin_att = prm->linear_attenuation;
+	const float cutoff = prm->attenuation_filter_cutoff_hz;
+	const float mixv = prm->mix_volumes[c][x];
+	LaneDetails cur, prev;
+	details_load_lane(cur, &t.inst_cur[q], c, x);
+	details_load_lane(prev, &prev_rd[q], c, x);
+	float *vprev = t.vs_prev + (size_t)vslot * 8;
+	const float vp_l = vprev[l], vp_0 = vprev[0], vp_1 = vprev[1];
+
+	// ---- housekeeping stores --------------------------------------------------------------------------------------
 	for (int i = tid; i < bus_f4; i += nthreads) {
 		bus[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+	for (int i = tid; i < rep_f4; i += nthreads) {
+		rep[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 	}
 	if (peaks) {
 		for (int i = tid; i < n_voices; i += nthreads) {
 			peaks[i] = make_float2(0.f, 0.f);
 		}
 	}
-	if (tid < GAS_MAX_CLASSES) { // class table of the next block
-		ClassInfo z{};
-		plan.cls[(parity ^ 1) * GAS_MAX_CLASSES + tid] = z;
+	if (tid < GAS_MAX_CLASSES) { // class counts of the next block
+		plan.cls_count[(parity ^ 1) * GAS_MAX_CLASSES + tid] = 0;
 	}
 
-	// ---- instance part ----------------------------------------------------------------------------------
-	for (int q = tid; q < inst_hwm; q += nthreads) {
-		if (!t.inst_active[q]) {
-			continue;
+	// ---- instance part: prev <- cur ---------------------------------------------------------------------
+	if (qi < inst_hwm && i_active) {
+		BusDetails *pw = &prev_wr[qi];
+		int cn = icur.n;
+		cn = cn < 0 ? 0 : (cn > GAS_MAX_BUSES_PER_PLAYBACK ? GAS_MAX_BUSES_PER_PLAYBACK : cn);
+		if (l == 0) {
+			pw->n = cn;
 		}
-		BusDetails cur, prev;
-		details_load(cur, &t.inst_cur[q]);
-		details_load(prev, &prev_rd[q]);
-		InstSends s;
-		resolve_sends(cur, prev, g, s);
-		InstSends *dst = &t.inst_sends[q]; // read by the voice-parallel kernel
-		dst->n = s.n;
-		dst->mask = s.mask;
-		for (int k = 0; k < s.n; k++) {
-			dst->bus[k] = s.bus[k];
-			for (int c = 0; c < 4; c++) {
-				for (int x = 0; x < 2; x++) {
-					dst->vp[k][c][x] = s.vp[k][c][x];
-					dst->vn[k][c][x] = s.vn[k][c][x];
+#pragma unroll
+		for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+			if (k < cn) {
+				if (l == 0) {
+					pw->bus[k] = icur.bus[k];
 				}
+				pw->vol[k][c][x] = icur.vol[k];
 			}
 		}
-		BusDetails *pw = &prev_wr[q]; // prev <- cur
-		pw->n = cur.n;
-		for (int k = 0; k < cur.n; k++) {
-			pw->bus[k] = cur.bus[k];
-			for (int c = 0; c < 4; c++) {
-				pw->vol[k][c][0] = cur.vol[k][c][0];
-				pw->vol[k][c][1] = cur.vol[k][c][1];
+	}
+	for (int q2 = qi + gridDim.x * kVoicesPerCta; q2 < inst_hwm; q2 += gridDim.x * kVoicesPerCta) { // only if the grid is smaller than the table
+		if (!t.inst_active[q2]) {
+			continue;
+		}
+		LaneDetails d;
+		details_load_lane(d, &t.inst_cur[q2], c, x);
+		BusDetails *pw = &prev_wr[q2];
+		const int cn = d.n < 0 ? 0 : (d.n > GAS_MAX_BUSES_PER_PLAYBACK ? GAS_MAX_BUSES_PER_PLAYBACK : d.n);
+		if (l == 0) {
+			pw->n = cn;
+		}
+#pragma unroll
+		for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
+			if (k < cn) {
+				if (l == 0) {
+					pw->bus[k] = d.bus[k];
+				}
+				pw->vol[k][c][x] = d.vol[k];
 			}
 		}
 	}
 
 	// ---- voice part ----------------------------------------------------------------------------------------
-	const int j = tid;
 	int path = PATH_NONE, mode = MODE_A, n_send = 0, n_group = 0, n_rows = 0;
-	uint32_t cflags = 0, mask = 0;
-	float rows[GAS_K2_ROW_FLOATS];
-	VoiceRec rec;
-	gas_voice v{};
-	bool live = false;
-
-	if (j < n_voices) {
-		v = voices[j];
-		live = v.voice >= 0 && v.voice < maxv && v.instance >= 0 && v.instance < g.max_instances && t.inst_active[v.instance] != 0;
-		if (v.src_row >= src_rows) {
-			v.src_row = -1;
-		}
+	uint32_t cflags = 0, mask = 0, quad = 0, rflags = 0;
+	const bool live = valid && v_active != 0;
+	if (v.src_row >= src_rows) {
+		v.src_row = -1;
 	}
+	LaneSends snd;
+	snd.n = 0;
+	float m_prev = 1.f, m_new = 1.f; // this lane's (pair, side) element of the mix_channel ramp
+	float target[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
+	int n_fx = 0, fx_stage = 1;
+	float fx_coef[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
+	bool shared = false;
+
 	if (live) {
-		const int q = v.instance;
-		const int imode = t.inst_mode[q];
-		const gas_params *prm = &t.inst_params[q];
 		mode = imode & 0xff;
 		const int fx_binding = (imode >> 8) - 1;
-		InstSends snd;
-		{
-			BusDetails cur, prev;
-			details_load(cur, &t.inst_cur[q]);
-			details_load(prev, &prev_rd[q]);
-			resolve_sends(cur, prev, g, snd);
+		if (cur.n <= 2 && prev.n <= 2) {
+			resolve_sends_lane<2>(cur, prev, g, snd);
+		} else {
+			resolve_sends_lane<GAS_MAX_BUSES_PER_PLAYBACK>(cur, prev, g, snd);
 		}
 		n_send = snd.n;
 		mask = snd.mask;
-		const float lin_att = prm->linear_attenuation;
 		const bool filt = mode != MODE_E && (double)lin_att >= 0.001; // audio_spatializer_3d.cpp:503, :568
 		const bool want_peak = (v.flags & GAS_VOICE_WANT_PEAK) != 0;
-
-		rec.voice = v.voice;
-		rec.instance = q;
-		rec.src_row = v.src_row;
-		rec.flags = v.flags & 0xffu;
-		rec.n_fx = 0;
-		float *vprev = t.vs_prev + (size_t)v.voice * 8;
-		for (int c = 0; c < 4; c++) {
-			rec.m_prev[c][0] = rec.m_prev[c][1] = 1.f;
-			rec.m_new[c][0] = rec.m_new[c][1] = 1.f;
-		}
+		rflags = v.flags & 0xffu;
 		if (mode == MODE_B) {
-			for (int c = 0; c < C; c++) {
-				rec.m_prev[c][0] = vprev[c * 2 + 0]; // :564
-				rec.m_prev[c][1] = vprev[c * 2 + 1];
-				rec.m_new[c][0] = prm->mix_volumes[c][0]; // :565
-				rec.m_new[c][1] = prm->mix_volumes[c][1];
-				if (rec.m_prev[c][0] == 0.f && rec.m_prev[c][1] == 0.f) {
-					rec.flags |= 1u << (8 + c); // is_just_started, :583
-				}
-				vprev[c * 2 + 0] = rec.m_new[c][0]; // :608
-				vprev[c * 2 + 1] = rec.m_new[c][1];
+			if (c < C) {
+				m_prev = vp_l;     // :564
+				m_new = mixv;      // :565
+				vprev[l] = m_new;  // :608
 			}
+			// is_just_started per pair: previous (L, R) exactly (0, 0), :583
+			const int zero = (c < C && m_prev == 0.f) ? 1 : 0;
+			const int both = zero & __shfl_xor_sync(gm, zero, 1);
+			rflags |= (uint32_t)group_or(gm, (both && x == 0) ? (1 << (8 + c)) : 0);
 		} else if (mode == MODE_A) {
-			if (vprev[0] == 0.f && vprev[1] == 0.f) {
-				rec.flags |= 1u << 8; // :518
+			if (vp_0 == 0.f && vp_1 == 0.f) {
+				rflags |= 1u << 8; // :518
 			}
-			float max_volume = 0.f; // :537-551
-			int max_index = 0;
-			for (int c = 0; c < 4; c++) {
-				if (prm->mix_volumes[c][0] > max_volume) {
-					max_volume = prm->mix_volumes[c][0];
-					max_index = c;
-				}
-				if (prm->mix_volumes[c][1] > max_volume) {
-					max_volume = prm->mix_volumes[c][1];
-					max_index = c;
+			// :537-551 — the (L,R) pair holding the first maximum in scan order c0.L, c0.R, c1.L, ...
+			float bv = mixv;
+			int bi = l;
+#pragma unroll
+			for (int d = 1; d < 8; d <<= 1) {
+				const float ov = __shfl_xor_sync(gm, bv, d);
+				const int oi = __shfl_xor_sync(gm, bi, d);
+				if (ov > bv || (ov == bv && oi < bi)) {
+					bv = ov;
+					bi = oi;
 				}
 			}
-			vprev[0] = prm->mix_volumes[max_index][0];
-			vprev[1] = prm->mix_volumes[max_index][1];
+			const int max_index = bv > 0.f ? (bi >> 1) : 0;
+			const float keep = __shfl_sync(gm, mixv, (threadIdx.x & 24) + max_index * 2 + x);
+			if (l < 2) {
+				vprev[l] = keep;
+			}
 		}
 		if (filt) {
 			cflags |= CLS_FILT;
-			prepare_coefficients(GAS_FILTER_HIGHSHELF, prm->attenuation_filter_cutoff_hz, 1.0f, lin_att, 1, g.mix_rate, rec.target); // :504-510
+			if (l == 0) {
+				prepare_coefficients(GAS_FILTER_HIGHSHELF, cutoff, 1.0f, lin_att, 1, g.mix_rate, target); // :504-510
+			}
 		}
 		if (mode == MODE_E) {
 			const gas_effect_chain *fx = &t.inst_fx[q];
-			int nfx = fx->n_effects;
-			nfx = nfx < 0 ? 0 : (nfx > GAS_MAX_EFFECTS ? GAS_MAX_EFFECTS : nfx);
-			rec.n_fx = nfx;
-			for (int e = 0; e < nfx; e++) {
-				gas_effect ef = fx->effects[e];
-				if (fx_binding == e) {
+			n_fx = fx->n_effects;
+			n_fx = n_fx < 0 ? 0 : (n_fx > GAS_MAX_EFFECTS ? GAS_MAX_EFFECTS : n_fx);
+			if (l < n_fx) { // one effect per lane
+				gas_effect ef = fx->effects[l];
+				if (fx_binding == l) {
 					ef.gain = lin_att; // example _process_effects (gd_spatializer_instance.gd:125-127)
 				}
-				int st = ef.stages < 1 ? 1 : (ef.stages > GAS_MAX_FILTER_STAGES ? GAS_MAX_FILTER_STAGES : ef.stages);
-				rec.fx_stages[e] = st;
-				prepare_coefficients(ef.mode, ef.cutoff_hz, ef.resonance, ef.gain, st, g.mix_rate, rec.fx_coef[e]);
+				fx_stage = ef.stages < 1 ? 1 : (ef.stages > GAS_MAX_FILTER_STAGES ? GAS_MAX_FILTER_STAGES : ef.stages);
+				prepare_coefficients(ef.mode, ef.cutoff_hz, ef.resonance, ef.gain, fx_stage, g.mix_rate, fx_coef);
 			}
 		}
-		const bool has_dsp = filt || (mode == MODE_E && rec.n_fx > 0);
+		const bool has_dsp = filt || (mode == MODE_E && n_fx > 0);
 
 		// weight polynomial per (send, pair, side): w(t) = A + B t + Cq t^2 with t = i/F, from
 		// (vn*t + (1-t)*vp) of the AudioServer ramp times (m_new*t + (1-t)*m_prev) of mix_channel.
-		bool lin = true, shared = n_send >= 2, streamed = false;
+		bool streamed = false;
 		if (!has_dsp && !want_peak && n_send >= 1) {
-			for (int k = 0; k < n_send; k++) {
-				for (int c = 0; c < C; c++) {
-					for (int x = 0; x < 2; x++) {
-						const float dn = snd.vn[k][c][x] - snd.vp[k][c][x];
-						const float dm = rec.m_new[c][x] - rec.m_prev[c][x];
-						if (dn * dm != 0.f) {
-							lin = false;
-						}
-						if (snd.vn[k][c][x] != snd.vn[0][c][x] || snd.vp[k][c][x] != snd.vp[0][c][x]) {
-							shared = false;
-						}
+			const float dm = m_new - m_prev;
+			int q_bits = 0, differs = 0;
+#pragma unroll
+			for (int k = 0; k < GAS_MAX_SENDS; k++) {
+				if (k < n_send && c < C) {
+					const float dn = snd.vn[k] - snd.vp[k];
+					if (dn * dm != 0.f) {
+						q_bits |= 1 << k;
+					}
+					if (snd.vn[k] != snd.vn[0] || snd.vp[k] != snd.vp[0]) {
+						differs = 1;
 					}
 				}
 			}
+			q_bits = group_or(gm, q_bits);
+			differs = group_or(gm, differs);
+			shared = n_send >= 2 && !differs;
 			n_group = shared ? 1 : n_send;
-			const int P = lin ? 2 : 3;
-			n_rows = n_group * P;
+			quad = shared ? (q_bits ? 1u : 0u) : (uint32_t)q_bits;
+			n_rows = 2 * n_group + __popc(quad);
 			if (n_rows <= GAS_K2_MAX_ROWS) {
 				streamed = true;
 				path = PATH_STREAM;
-				if (lin) {
-					cflags |= CLS_LIN;
-				}
 				if (shared) {
 					cflags |= CLS_SHARED;
-				}
-				for (int k = 0; k < n_group; k++) {
-					for (int c = 0; c < C; c++) {
-						for (int x = 0; x < 2; x++) {
-							const float np = snd.vp[k][c][x], dn = snd.vn[k][c][x] - np;
-							const float mp = rec.m_prev[c][x], dm = rec.m_new[c][x] - mp;
-							rows[((k * P + 0) * C + c) * 2 + x] = np * mp;
-							rows[((k * P + 1) * C + c) * 2 + x] = np * dm + dn * mp;
-							if (!lin) {
-								rows[((k * P + 2) * C + c) * 2 + x] = dn * dm;
-							}
-						}
-					}
 				}
 				if (v.src_row < 0) {
 					path = PATH_NONE; // silent source, no DSP state to advance: contributes exactly nothing
@@ -438,59 +505,132 @@ __global__ void __launch_bounds__(128) k_prologue(DevTables t, GlobalCfg g, Bloc
 				cflags &= CLS_FILT;
 				n_group = n_send;
 				n_rows = 0;
+				quad = 0;
 			}
 		}
 	}
 
-	// class lookup once per distinct key per warp, then a warp-aggregated append
-	unsigned long long key = 0ULL;
-	if (path != PATH_NONE) {
-		key = (unsigned long long)path | ((unsigned long long)mode << 2) | ((unsigned long long)cflags << 4) |
-				((unsigned long long)n_send << 8) | ((unsigned long long)mask << 16);
-	}
-	const unsigned peers = __match_any_sync(0xffffffffu, key);
-	const int leader = __ffs(peers) - 1;
-	int cid = -1, base = 0;
-	if (key != 0ULL && (int)lane == leader) {
-		cid = class_find_or_insert(cls, key, plan.overflow);
-		if (cid >= 0) {
-			ClassInfo *ci = &cls[cid];
-			ci->path = path;
-			ci->mode = mode;
-			ci->flags = cflags;
-			ci->mask = mask;
-			ci->n_send = n_send;
-			ci->n_group = n_group;
-			ci->n_rows = n_rows;
-			base = atomicAdd(&ci->count, __popc(peers));
+	// ---- class lookup: once per class per CTA in shared memory, then one global atomic per class ------------
+	const unsigned long long key = path != PATH_NONE ? cls_key(path, mode, cflags, n_send, mask, quad) : 0ULL;
+	int slot = -1, lpos = 0;
+	if (key != 0ULL && l == 0) {
+		for (int i = 0; i < kVoicesPerCta; i++) {
+			unsigned long long k = *(volatile unsigned long long *)&s_key[i];
+			if (k == 0ULL) {
+				k = atomicCAS(&s_key[i], 0ULL, key);
+				if (k == 0ULL) {
+					k = key;
+				}
+			}
+			if (k == key) {
+				slot = i;
+				break;
+			}
 		}
+		lpos = atomicAdd(&s_cnt[slot], 1);
 	}
-	cid = __shfl_sync(0xffffffffu, cid, leader);
-	base = __shfl_sync(0xffffffffu, base, leader);
-	if (key != 0ULL && cid >= 0) {
-		const int pos = base + __popc(peers & ((1u << lane) - 1u));
+	__syncthreads();
+	if (threadIdx.x < kVoicesPerCta && s_key[threadIdx.x] != 0ULL) {
+		// Slots are stable across blocks: in the steady state the key is already in the snapshot and the only
+		// global operation is the add that reserves this CTA's range of the class list.
+		const unsigned long long k = s_key[threadIdx.x];
+		int cid = -1;
+		for (int i = 0; i < GAS_MAX_CLASSES; i++) {
+			if (s_gkey[i] == k) {
+				cid = i;
+				break;
+			}
+		}
+		if (cid < 0) { // first appearance of the class: claim a free slot
+			for (int i = 0; i < GAS_MAX_CLASSES && cid < 0; i++) {
+				unsigned long long o = s_gkey[i];
+				if (o != 0ULL && o != k) {
+					continue;
+				}
+				o = atomicCAS(&plan.cls_key[i], 0ULL, k);
+				if (o == 0ULL || o == k) {
+					cid = i;
+				}
+			}
+			if (cid < 0) {
+				*plan.overflow = 1;
+			}
+		}
+		if (cid >= 0) {
+			s_base[threadIdx.x] = atomicAdd(&cnt_now[cid], s_cnt[threadIdx.x]);
+		}
+		s_cid[threadIdx.x] = cid;
+	}
+	__syncthreads();
+	slot = __shfl_sync(gm, slot, threadIdx.x & 24);
+	lpos = __shfl_sync(gm, lpos, threadIdx.x & 24);
+	const int cid = slot >= 0 ? s_cid[slot] : -1;
+	if (cid >= 0) {
+		const int pos = s_base[slot] + lpos;
+		if (l == 0) {
+			plan.list[(size_t)cid * maxv + pos] = make_int2(j, v.src_row);
+		}
 		if (path == PATH_STREAM) {
-			plan.k2_src[(size_t)cid * maxv + pos] = v.src_row;
-			const int nf = n_rows * C * 2;
-			float *dst = plan.k2_rows + (size_t)cid * maxv * GAS_K2_ROW_FLOATS + (size_t)pos * nf;
-			for (int i = 0; i < nf; i++) {
-				dst[i] = rows[i];
+			if (c < C) {
+				const int nf = n_rows * C * 2;
+				float *dst = plan.k2_rows + (size_t)cid * maxv * GAS_K2_ROW_FLOATS + (size_t)pos * nf + c * 2 + x;
+				const float mp = m_prev, dm = m_new - m_prev;
+				int r = 0;
+#pragma unroll
+				for (int k = 0; k < GAS_K2_MAX_ROWS / 2; k++) {
+					if (k < n_group) {
+						const float np = snd.vp[k], dn = snd.vn[k] - np;
+						dst[(size_t)(r + 0) * C * 2] = np * mp;
+						dst[(size_t)(r + 1) * C * 2] = np * dm + dn * mp;
+						if ((quad >> k) & 1u) {
+							dst[(size_t)(r + 2) * C * 2] = dn * dm;
+							r += 3;
+						} else {
+							r += 2;
+						}
+					}
+				}
 			}
 		} else {
-			plan.k3_list[(size_t)cid * maxv + pos] = j;
-			plan.rec[j] = rec;
+			VoiceRec *rec = &plan.rec[j];
+			InstSends *ps = &plan.sends[j];
+			rec->m_prev[c][x] = m_prev;
+			rec->m_new[c][x] = m_new;
+			if (l == 0) {
+				rec->voice = v.voice;
+				rec->instance = v.instance;
+				rec->src_row = v.src_row;
+				rec->flags = rflags;
+				rec->n_fx = n_fx;
+#pragma unroll
+				for (int i = 0; i < 5; i++) {
+					rec->target[i] = target[i];
+				}
+				ps->n = n_send;
+				ps->mask = mask;
+			}
+			if (l < n_fx) {
+				rec->fx_stages[l] = fx_stage;
+#pragma unroll
+				for (int i = 0; i < 5; i++) {
+					rec->fx_coef[l][i] = fx_coef[i];
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < GAS_MAX_SENDS; k++) {
+				if (k < n_send) {
+					if (l == 0) {
+						ps->bus[k] = snd.bus[k];
+					}
+					ps->vp[k][c][x] = snd.vp[k];
+					ps->vn[k][c][x] = snd.vn[k];
+				}
+			}
 		}
 	}
-
-	// ---- the last CTA to finish advances the block counter (every CTA has read it by then) ----------------
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();
-		const int ticket = atomicAdd(&t.blk[1], 1);
-		if (ticket == (int)gridDim.x - 1) {
-			t.blk[1] = 0;
-			t.blk[0] = t.blk[0] + 1;
-		}
+	if (threadIdx.x == 0 && ticket == (int)gridDim.x - 1) {
+		t.blk[1] = 0;
+		t.blk[0] = blk_n + 1;
 	}
 }
 
@@ -498,12 +638,13 @@ __global__ void __launch_bounds__(128) k_prologue(DevTables t, GlobalCfg g, Bloc
 
 cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int src_rows, int frames, gas_frame *d_bus,
 		gas_frame *d_peaks, cudaStream_t st) {
-	const int bus_f4 = ctx->g.num_buses * ctx->g.channels * frames / 2;
+	const int bus_f4 = gas_bus_f4(ctx, frames);
+	const int rep_f4 = ctx->replicas > 1 ? ctx->replicas * bus_f4 : 0;
 	int work = ctx->inst_hwm > n_voices ? ctx->inst_hwm : n_voices;
-	work = work > GAS_MAX_CLASSES ? work : GAS_MAX_CLASSES;
-	int blocks = (work + 127) / 128;
-	k_prologue<<<blocks, 128, 0, st>>>(ctx->t, ctx->g, ctx->plan, ctx->inst_hwm, n_voices, d_voices, src_rows, (float4 *)d_bus, bus_f4,
-			(float2 *)d_peaks);
+	work = work > 1 ? work : 1;
+	const int blocks = (work + kVoicesPerCta - 1) / kVoicesPerCta;
+	cudaError_t e = gas_launch(k_prologue, dim3(blocks), dim3(kCtaThreads), 0, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, ctx->inst_hwm, n_voices,
+			d_voices, src_rows, (float4 *)d_bus, bus_f4, (float4 *)ctx->d_rep, rep_f4, (float2 *)d_peaks);
 	ctx->launches++;
-	return cudaGetLastError();
+	return e;
 }

@@ -44,8 +44,6 @@ __device__ void instance_reset(DevTables &t, int q, int spat) {
 		t.inst_mode[q] = mode | ((s.effect_gain_binding + 1) << 8);
 	}
 	t.inst_fx[q] = t.spat[spat].chain;
-	t.inst_sends[q].n = 0;
-	t.inst_sends[q].mask = 0;
 }
 
 // AudioSpatializer3D defaults, audio_spatializer_3d.h:171-188
@@ -92,8 +90,6 @@ __global__ void k_defaults(DevTables t, GlobalCfg g) {
 		details_clear(t.inst_prev[t.max_instances + q]);
 		t.inst_mode[q] = MODE_A;
 		t.inst_fx[q].n_effects = 0;
-		t.inst_sends[q].n = 0;
-		t.inst_sends[q].mask = 0;
 	}
 }
 
