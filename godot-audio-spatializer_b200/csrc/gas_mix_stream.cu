@@ -59,7 +59,9 @@ struct StreamCfg {
 	int w_bytes;       // per stage
 	int stage_bytes;
 	int fixed_cost;    // per-voice term of the partition cost (the other term is the accumulator count)
-	int flush_mode;    // 0 = per-thread red.global.add.v4 (default), 1 = shared-memory staging + bulk async reduce
+	int flush_mode;    // 0 = per-thread red.global.add.v4, 1 = shared-memory staging + bulk async reduce,
+	                   // 2 = plain stores into this CTA's private slab (GAS_K2_SLAB=1; needs a tile that spans all consumer threads)
+	unsigned long long *slab_mask; // flush_mode 2: per-CTA mask of slab rows written
 	int debug;         // GAS_K2_DEBUG bits (experiments only): 1 = skip the bus reductions, 2 = skip the FMAs, 8 = record a timeline
 	unsigned long long *timeline; // [CTA][8] globaltimer stamps (debug & 8): start, table, first data, last data, flushed
 };
@@ -151,8 +153,14 @@ __device__ void unit_iter_init(UnitIter &it, const ClassInfo *cls, int n_cls, co
 		const long long units = (long long)((cls[c].count + cf.vb - 1) / cf.vb) * cf.n_tiles;
 		total += units * (cls[c].n_rows * C + cf.fixed_cost);
 	}
-	const long long lo = total * cta / n_cta;
-	const long long hi = total * (cta + 1) / n_cta;
+	long long lo, hi;
+	if (total < (1LL << 31) / n_cta) { // 32-bit divisions (the usual case): 64-bit ones are slow software routines
+		lo = (unsigned)total * (unsigned)cta / (unsigned)n_cta;
+		hi = (unsigned)total * (unsigned)(cta + 1) / (unsigned)n_cta;
+	} else {
+		lo = total * cta / n_cta;
+		hi = total * (cta + 1) / n_cta;
+	}
 	it.remaining = 0;
 	it.cid = n_cls;
 	it.n_cls = n_cls;
@@ -162,8 +170,14 @@ __device__ void unit_iter_init(UnitIter &it, const ClassInfo *cls, int n_cls, co
 		const int nb = (cls[c].count + cf.vb - 1) / cf.vb;
 		const long long units = (long long)nb * cf.n_tiles;
 		const long long w = cls[c].n_rows * C + cf.fixed_cost;
-		long long u_lo = lo <= base ? 0 : (lo - base + w - 1) / w;
-		long long u_hi = hi <= base ? 0 : (hi - base + w - 1) / w;
+		long long u_lo, u_hi;
+		if (hi < (1LL << 31)) {
+			u_lo = lo <= base ? 0 : (unsigned)(lo - base + w - 1) / (unsigned)w;
+			u_hi = hi <= base ? 0 : (unsigned)(hi - base + w - 1) / (unsigned)w;
+		} else {
+			u_lo = lo <= base ? 0 : (lo - base + w - 1) / w;
+			u_hi = hi <= base ? 0 : (hi - base + w - 1) / w;
+		}
 		u_lo = u_lo > units ? units : u_lo;
 		u_hi = u_hi > units ? units : u_hi;
 		if (u_hi > u_lo) {
@@ -241,6 +255,7 @@ struct ConsumerCtx {
 	int stage;
 	uint32_t phase;
 	uint32_t flushes; // bulk reduce groups committed so far (thread 0 is the issuer)
+	unsigned long long touched; // flush_mode 2: rows of the slab this CTA has written (identical in every thread)
 	unsigned long long *tl;
 };
 
@@ -317,6 +332,14 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 	const float t0 = (float)frame0 / (float)F;
 	const float t1 = (float)(frame0 + 1) / (float)F;
 	const bool shared = (ci.flags & CLS_SHARED) != 0;
+	// The accumulators were indexed statically so far (registers); the flush picks rows by run-time index, so
+	// they are parked in a thread-local array once (a handful of 16-byte local stores) instead of being
+	// selected through compare chains.
+	float4 dump[NP];
+#pragma unroll
+	for (int p = 0; p < NP; p++) {
+		dump[p] = make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y);
+	}
 	const int RG = ci.n_group; // row groups; group k owns 2 rows (A, B) plus a t^2 row when its quad bit is set
 	uint32_t rest = ci.mask;
 	int r0 = 0; // first row of group k
@@ -334,22 +357,11 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		}
 		for (int c = 0; c < C; c++) {
 			const int pa = (r0 + 0) * C + c, pb = (r0 + 1) * C + c, pc = (r0 + 2) * C + c;
-			float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0, c0 = a0, c1 = a0;
-#pragma unroll
-			for (int p = 0; p < NP; p++) { // static indexing only: the accumulators must stay in registers
-				if (p == pa) {
-					a0 = acc[p][0];
-					a1 = acc[p][1];
-				}
-				if (p == pb) {
-					b0 = acc[p][0];
-					b1 = acc[p][1];
-				}
-				if (quad && p == pc) {
-					c0 = acc[p][0];
-					c1 = acc[p][1];
-				}
-			}
+			const float4 A = dump[pa], B = dump[pb];
+			const float4 Q = quad ? dump[pc] : make_float4(0.f, 0.f, 0.f, 0.f);
+			const float2 a0 = make_float2(A.x, A.y), a1 = make_float2(A.z, A.w);
+			const float2 b0 = make_float2(B.x, B.y), b1 = make_float2(B.z, B.w);
+			const float2 c0 = make_float2(Q.x, Q.y), c1 = make_float2(Q.z, Q.w);
 			float4 v;
 			v.x = fmaf(t0, fmaf(t0, c0.x, b0.x), a0.x);
 			v.y = fmaf(t0, fmaf(t0, c0.y, b0.y), a0.y);
@@ -372,6 +384,28 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 					if (cf.groups > 1) {
 						consumer_barrier();
 					}
+				}
+			} else if (cf.flush_mode == 2) {
+				// private slab: the first visit of a row stores, later visits (another class reaching the same bus)
+				// add to what this very thread stored; no atomics, no zero-fill
+				uint32_t m = shared ? ci.mask : (1u << b_own);
+				while (m) {
+					const int b = __ffs(m) - 1;
+					m &= m - 1;
+					const int r = b * C + c;
+					if (mine) {
+						float4 *dst = reinterpret_cast<float4 *>(bus + ((size_t)r * F + frame0) * 2);
+						float4 o = v;
+						if ((cc.touched >> r) & 1ULL) {
+							const float4 q = *dst;
+							o.x += q.x;
+							o.y += q.y;
+							o.z += q.z;
+							o.w += q.w;
+						}
+						*dst = o;
+					}
+					cc.touched |= 1ULL << r;
 				}
 			} else if (mine) {
 				if (shared) { // one row group fanned out to every bus of the mask
@@ -409,7 +443,8 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 
 __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, GlobalCfg g, StreamCfg cf,
 		const gas_frame *__restrict__ src, float *__restrict__ bus, int rep_stride, int replicas, const int32_t *__restrict__ blk) {
-	bus += (size_t)(blockIdx.x % replicas) * rep_stride;
+	// flush target: this CTA's private slab (flush_mode 2) or replica (CTA % replicas) of the bus layout
+	bus += (size_t)(cf.flush_mode == 2 ? blockIdx.x : blockIdx.x % replicas) * rep_stride;
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ int s_ncls;
@@ -476,6 +511,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		tl[5] = (unsigned long long)it.remaining;
 	}
 	if (it.remaining <= 0) {
+		if (cf.flush_mode == 2 && tid == 0) {
+			cf.slab_mask[blockIdx.x] = 0ULL;
+		}
 		return;
 	}
 	unsigned char *ring = smem + kStagingBytes;
@@ -531,6 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		cc.staging = smem;
 		cc.tid = tid;
 		cc.flushes = 0;
+		cc.touched = 0ULL;
 		cc.tl = tl;
 		cc.full = s_full;
 		cc.empty = s_empty;
@@ -566,6 +605,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		}
 		if (tl) {
 			tl[4] = gtime();
+		}
+		if (cf.flush_mode == 2 && tid == 0) {
+			cf.slab_mask[blockIdx.x] = cc.touched;
 		}
 		if (tid == 0 && cc.flushes > 0) {
 			bulk_wait_all(); // the staging slots must outlive the reads; the adds are complete when the grid is
@@ -629,9 +671,25 @@ cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stri
 		}
 		ctx->k2_smem_attr_set = true;
 	}
-	// partial sums go to replica (CTA % replicas) of the bus layout: fewer CTAs contend for the same addresses
-	float *target = ctx->replicas > 1 ? (float *)ctx->d_rep : (float *)d_bus;
-	const int rep_stride = ctx->replicas > 1 ? gas_bus_f4(ctx, frames) * 4 : 0; // floats
+	// Partial sums: atomic adds into replica (CTA % replicas) of the bus layout, or (GAS_K2_SLAB=1) plain stores
+	// into one private slab per CTA.  Either way the voice-parallel kernel's launch folds them into d_bus.
+	// Measured on B200 (16384 voices): the slab variant does not shorten K2 and its fold is slower.
+	const bool env_flush = getenv("GAS_K2_FLUSH") != nullptr;
+	if (!env_flush && ctx->use_slab && cf.groups == 1 && ctx->g.num_buses * ctx->g.channels <= 64) {
+		cf.flush_mode = 2;
+	}
+	float *target;
+	int rep_stride; // floats
+	if (cf.flush_mode == 2) {
+		target = (float *)ctx->d_slab;
+		rep_stride = gas_bus_f4(ctx, frames) * 4;
+		cf.slab_mask = ctx->d_slab_mask;
+		ctx->slab_ctas = ctx->num_sms;
+	} else {
+		target = ctx->replicas > 1 ? (float *)ctx->d_rep : (float *)d_bus;
+		rep_stride = ctx->replicas > 1 ? gas_bus_f4(ctx, frames) * 4 : 0;
+		ctx->slab_ctas = 0;
+	}
 	if (cf.debug & 8) {
 		if (!ctx->d_timeline) {
 			cudaMalloc((void **)&ctx->d_timeline, 256 * 8 * sizeof(unsigned long long));
