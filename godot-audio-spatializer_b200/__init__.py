@@ -8,6 +8,6 @@ API (host/) and the ctypes binding used by tests and bench.py.
 The directory name carries a hyphen, so import it through ``gaspkg.load()`` at the repo root, which
 registers it as ``godot_audio_spatializer_b200``.
 """
-from . import abi, synth  # noqa: F401
+from . import abi, shard, synth  # noqa: F401
 from .lib import GasError, LIB_PATH, PROTOTYPES, load  # noqa: F401
 from .mixer import Mixer  # noqa: F401

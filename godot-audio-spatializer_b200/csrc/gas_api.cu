@@ -132,6 +132,7 @@ int prof_drain(gas_ctx *ctx) {
 		return GAS_OK;
 	}
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_gain));
 	for (size_t i = 0; i < ctx->prof_used; i++) {
 		float ms = 0.f;
 		GAS_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_pairs[i].a, ctx->prof_pairs[i].b));
@@ -142,9 +143,29 @@ int prof_drain(gas_ctx *ctx) {
 	return GAS_OK;
 }
 
-gas_ctx::ProfPair *prof_open(gas_ctx *ctx, int kind) {
-	if (!ctx->profiling || ctx->capturing) {
+// Inside a capture the timing events become event-record nodes of the graph (cudaEventRecordExternal), so a
+// profiled graph reports each kernel's duration as it runs inside the replayed step.
+static gas_ctx::ProfPair g_graph_pair[GAS_KERNEL_KINDS];
+
+gas_ctx::ProfPair *prof_open(gas_ctx *ctx, int kind, cudaStream_t st = nullptr) {
+	st = st ? st : ctx->s_mix;
+	if (!ctx->profiling) {
 		return nullptr;
+	}
+	if (ctx->capturing) {
+		if (!ctx->gev[kind][0]) {
+			if (cudaEventCreate(&ctx->gev[kind][0]) != cudaSuccess || cudaEventCreate(&ctx->gev[kind][1]) != cudaSuccess) {
+				return nullptr;
+			}
+		}
+		ctx->gev_used[kind] = true;
+		ctx->capture_profiled = true;
+		g_graph_pair[kind].a = ctx->gev[kind][0];
+		g_graph_pair[kind].b = ctx->gev[kind][1];
+		g_graph_pair[kind].kind = kind;
+		g_graph_pair[kind].st = st;
+		cudaEventRecordWithFlags(g_graph_pair[kind].a, st, cudaEventRecordExternal);
+		return &g_graph_pair[kind];
 	}
 	if (ctx->prof_used >= 3072 && prof_drain(ctx) != GAS_OK) {
 		return nullptr;
@@ -158,13 +179,14 @@ gas_ctx::ProfPair *prof_open(gas_ctx *ctx, int kind) {
 	}
 	gas_ctx::ProfPair *p = &ctx->prof_pairs[ctx->prof_used++];
 	p->kind = kind;
-	cudaEventRecord(p->a, ctx->s_mix);
+	p->st = st;
+	cudaEventRecord(p->a, st);
 	return p;
 }
 
 void prof_close(gas_ctx *ctx, gas_ctx::ProfPair *p) {
 	if (p) {
-		cudaEventRecord(p->b, ctx->s_mix);
+		cudaEventRecordWithFlags(p->b, p->st, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
 	}
 }
 
@@ -437,6 +459,13 @@ void gas_destroy(gas_ctx *ctx) {
 		cudaEventDestroy(pp.a);
 		cudaEventDestroy(pp.b);
 	}
+	for (int k = 0; k < GAS_KERNEL_KINDS; k++) {
+		for (int e = 0; e < 2; e++) {
+			if (ctx->gev[k][e]) {
+				cudaEventDestroy(ctx->gev[k][e]);
+			}
+		}
+	}
 	if (ctx->s_mix) {
 		cudaStreamDestroy(ctx->s_mix);
 	}
@@ -589,7 +618,9 @@ static int gain_common(gas_ctx *ctx, int32_t n, const gas_emitter *d_em, int32_t
 		}
 		ctx->n_areas_res = n_areas;
 	}
+	gas_ctx::ProfPair *pp = prof_open(ctx, GAS_KERNEL_GAIN, ctx->s_gain);
 	GAS_CUDA(ctx, launch_gain(ctx, n, d_em, n_listeners, ctx->d_listeners, ctx->d_areas, d_out, ctx->s_gain));
+	prof_close(ctx, pp);
 	return GAS_OK;
 }
 
@@ -848,6 +879,10 @@ int gas_capture_begin(gas_ctx *ctx) {
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->s_mix));
 	GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_gain, ctx->ev_fork, 0));
 	ctx->capturing = true;
+	ctx->capture_profiled = false;
+	for (int k = 0; k < GAS_KERNEL_KINDS; k++) {
+		ctx->gev_used[k] = false;
+	}
 	ctx->capture_launches0 = ctx->launches;
 	return GAS_OK;
 }
@@ -877,6 +912,7 @@ int gas_capture_end(gas_ctx *ctx, int32_t *out_graph) {
 		return gas_fail(ctx, GAS_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
 	}
 	g.kernels = kernels;
+	g.profiled = ctx->capture_profiled;
 	ctx->graphs.push_back(g);
 	*out_graph = (int32_t)ctx->graphs.size() - 1;
 	return GAS_OK;
@@ -892,6 +928,18 @@ int gas_graph_launch(gas_ctx *ctx, int32_t graph) {
 	}
 	GAS_CUDA(ctx, cudaGraphLaunch(ctx->graphs[graph].exec, ctx->s_mix));
 	ctx->launches += ctx->graphs[graph].kernels;
+	if (ctx->graphs[graph].profiled && ctx->profiling) { // a profiled graph is read back after every launch
+		GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+		for (int k = 0; k < GAS_KERNEL_KINDS; k++) {
+			if (ctx->gev[k][0]) {
+				float ms = 0.f;
+				if (cudaEventElapsedTime(&ms, ctx->gev[k][0], ctx->gev[k][1]) == cudaSuccess) {
+					ctx->prof_ms[k] += ms;
+					ctx->prof_n[k] += 1;
+				}
+			}
+		}
+	}
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix)); // later gain-side work waits for the whole graph
 	ctx->prologue_pending = true;
 	return GAS_OK;

@@ -194,6 +194,8 @@ struct gas_ctx {
 	struct Graph {
 		cudaGraphExec_t exec = nullptr;
 		uint64_t kernels = 0;
+		bool profiled = false; // captured while per-kernel timing was on: carries event-record nodes around the kernels
+		int prof_blocks = 0;   // mix blocks in the graph (only the last block's events survive a launch)
 	};
 	std::vector<Graph> graphs;
 	// per-kernel timing
@@ -201,8 +203,12 @@ struct gas_ctx {
 	struct ProfPair {
 		cudaEvent_t a, b;
 		int kind;
+		cudaStream_t st;
 	};
 	std::vector<ProfPair> prof_pairs;
+	cudaEvent_t gev[GAS_KERNEL_KINDS][2] = {}; // event-record nodes of profiled graphs
+	bool gev_used[GAS_KERNEL_KINDS] = {};
+	bool capture_profiled = false;
 	size_t prof_used = 0;
 	double prof_ms[GAS_KERNEL_KINDS] = {};
 	uint64_t prof_n[GAS_KERNEL_KINDS] = {};

@@ -160,11 +160,11 @@ class Mixer:
 
     def profile_read(self):
         """{kind: (total_ms, launches)} for prologue / mix_stream (K2) / mix_voice (K3)."""
-        ms = (C.c_double * 3)()
-        n = (C.c_uint64 * 3)()
+        ms = (C.c_double * 4)()
+        n = (C.c_uint64 * 4)()
         self._ck(self._lib.gas_profile_read(self._ctx, ms, n))
-        names = ("prologue", "mix_stream", "mix_voice")
-        return {names[k]: (float(ms[k]), int(n[k])) for k in range(3)}
+        names = ("prologue", "mix_stream", "mix_voice", "gain")
+        return {names[k]: (float(ms[k]), int(n[k])) for k in range(4)}
 
     def params_set(self, instances, params):
         """set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272, :558-564)."""

@@ -355,14 +355,17 @@ GAS_API int gas_graph_launch(gas_ctx *ctx, int32_t graph);
 GAS_API int gas_graph_destroy(gas_ctx *ctx, int32_t graph);
 
 /* ---- per-kernel timing (CUDA events on the launching stream) ----------------------------------------
- * While enabled, every mix-side kernel launch outside a capture is bracketed by timing events.
+ * While enabled, every kernel launch is bracketed by timing events.  Inside a capture they become
+ * event-record nodes of the graph: a graph captured with timing on is synchronised and read back after
+ * every gas_graph_launch, so it reports each kernel's duration as it runs inside the replayed step.
  * gas_profile_read synchronises and returns, per kernel kind, the summed duration in milliseconds and
  * the number of launches since gas_profile_enable(ctx, 1). */
 typedef enum gas_kernel_kind {
 	GAS_KERNEL_PROLOGUE = 0, /* k_prologue_inst + k_prologue_voice */
 	GAS_KERNEL_MIX_STREAM = 1, /* K2 */
 	GAS_KERNEL_MIX_VOICE = 2,  /* K3 */
-	GAS_KERNEL_KINDS = 3
+	GAS_KERNEL_GAIN = 3,       /* K1 (timed on the gain stream) */
+	GAS_KERNEL_KINDS = 4
 } gas_kernel_kind;
 GAS_API int gas_profile_enable(gas_ctx *ctx, int32_t on);
 GAS_API int gas_profile_read(gas_ctx *ctx, double ms_out[GAS_KERNEL_KINDS], uint64_t launches_out[GAS_KERNEL_KINDS]);

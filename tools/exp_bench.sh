@@ -10,5 +10,5 @@ import json,sys
 tag,envs=sys.argv[1],sys.argv[2]
 d=json.loads(open(f"gpurun_out/exp_{tag}.json").read().strip().splitlines()[-1])
 r=d["roofline"]
-print("%-14s %-40s step %.2f us  value %.1f G  K2 %.2f us (%.1f%% hbm)  prologue %.2f  K3 %.2f  e2e %.2f ms  clocks %s" % (tag, envs, d["ms_per_step"]*1e3, d["value"]/1e9, r["us_per_launch"], 100*r["frac"], r["other_kernels_us"]["prologue"], r["other_kernels_us"]["mix_voice_K3"], d["e2e"]["ms_per_step"], d["clocks"]["sm_mhz"]))
+print("%-14s %-40s step %.2f us  value %.1f G  K2 %.2f us (%.1f%% hbm)  gain %.2f prologue %.2f  K3 %.2f  e2e %.2f ms  clocks %s" % (tag, envs, d["ms_per_step"]*1e3, d["value"]/1e9, r["us_per_launch"], 100*r["frac"], r["other_kernels_us"]["gain_K1"], r["other_kernels_us"]["prologue"], r["other_kernels_us"]["mix_voice_K3"], d["e2e"]["ms_per_step"], d["clocks"]["sm_mhz"]))
 PY
