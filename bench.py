@@ -237,6 +237,24 @@ class DeviceWorkload:
         self.mixer.areas_set(self.areas)
         self.mixer.sync()
 
+    def comm_setup(self, dist):
+        """Peer-memory reduce: every rank exports its exchange buffer (CUDA IPC handle), all ranks open all."""
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, self.mixer.comm_export())
+        self.mixer.comm_open(dist.get_rank(), handles)
+        dist.barrier()
+        self.peer_reduce = True
+
+    def reduce_prime(self):
+        """One outstanding begin, so that the first captured step finds a block to end."""
+        if getattr(self, "peer_reduce", False):
+            self.mixer.reduce_bus_begin_device(self.d_bus[1].data_ptr(), self.w["frames"])
+
+    def reduce_drain(self, k_last):
+        """Ends the reduce of the last block."""
+        if getattr(self, "peer_reduce", False):
+            self.mixer.reduce_bus_end_device(self.d_bus[k_last % 2].data_ptr(), self.w["frames"])
+
     def step_device(self, k):
         """One step = mix of block k (audio side) with, beside it, the gain computation for block k+1 (physics
         side): the reference runs the two on different threads with a double-buffered parameter hand-off
@@ -245,6 +263,11 @@ class DeviceWorkload:
         s = k % N_SETS
         m.mix_block_device(w["voices"], self.d_voices.data_ptr(), self.d_src[s].data_ptr(), w["voices"], w["frames"], w["frames"],
                            self.d_bus[k % 2].data_ptr())
+        if getattr(self, "peer_reduce", False):
+            # N > 1: sum of the per-GPU partial bus buffers over peer memory, inside the graph.  The previous block's
+            # reduce is ended here, after this block's mix has been enqueued, so the other ranks' skew hides behind it.
+            m.reduce_bus_end_device(self.d_bus[(k + 1) % 2].data_ptr(), w["frames"])
+            m.reduce_bus_begin_device(self.d_bus[k % 2].data_ptr(), w["frames"])
         m.gain_compute_device(w["voices"], self.d_emitters[(s + 1) % N_SETS].data_ptr())
         return self.d_bus[k % 2]
 
@@ -320,11 +343,14 @@ def gpu_arm(args):
         host_inputs = build_host_inputs(w, abi, synth)
         parity = parity_gate(gas, w, dw, abi, synth, parity_src, host_inputs)
 
+    peer = dist is not None and args.reduce == "peer"
+    if peer:
+        dw.comm_setup(dist)
     graphs = dw.capture_steps()
 
     def one_step(k):
         m.graph_launch(graphs[k % N_SETS])
-        if dist is not None:
+        if dist is not None and not peer and not os.environ.get("GAS_BENCH_NOREDUCE"):
             with torch.cuda.stream(stream):
                 dist.all_reduce(dw.d_bus[k % 2])  # sum of the per-GPU partial bus buffers (NCCL over NVLink)
 
@@ -335,6 +361,7 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     # ---- timed region: `value` ----------------------------------------------------------------------------
+    dw.reduce_prime()
     for k in range(W):
         one_step(k)
     barrier()
@@ -347,6 +374,7 @@ def gpu_arm(args):
         ev0.record()
     for k in range(K):
         one_step(W + k)
+    dw.reduce_drain(W + K - 1)
     with torch.cuda.stream(stream):
         ev1.record()
     barrier()
@@ -369,8 +397,10 @@ def gpu_arm(args):
     m.profile_enable(True)
     pgraphs = dw.capture_steps()
     kp = max(8, min(K, 256))
+    dw.reduce_prime()
     for k in range(kp):
         m.graph_launch(pgraphs[k % N_SETS])
+    dw.reduce_drain(kp - 1)
     prof = m.profile_read()
     m.profile_enable(False)
     k2_ms, k2_n = prof["mix_stream"]
@@ -449,7 +479,10 @@ def gpu_arm(args):
                        "launch": "CUDA-graph replay of gas_mix_block_device (block k) with gas_gain_compute_device (parameters of block "
                                  "k+1) beside it on the gain stream, one graph per step",
                        "pdl": os.environ.get("GAS_PDL", "0"),
-                       "reduce": "torch.distributed all_reduce (NCCL) of the partial bus buffers" if world > 1 else "none (1 GPU)"},
+                       "reduce": ("none (1 GPU)" if world == 1 else
+                                  "gas_reduce_bus_device inside the step graph: every rank adds its partial bus buffer into every rank's "
+                                  "exchange buffer with vector reductions on peer pointers (NVLink), one arrival-counter round per block"
+                                  if peer else "torch.distributed all_reduce (NCCL) of the partial bus buffers, one call per step")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
             "parity": parity,
         }
@@ -468,6 +501,7 @@ def main():
     ap.add_argument("--voices", type=int, default=0)
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N > 1: how the partial bus buffers are summed")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--area-fraction", type=float, default=None, help="fraction of voices inside the reverb area (experiments)")

@@ -426,7 +426,7 @@ void gas_destroy(gas_ctx *ctx) {
 		ctx->t.inst_prev, ctx->t.inst_mode, ctx->t.blk, ctx->t.inst_fx, ctx->plan.sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls_key, ctx->plan.cls_count,
 		ctx->plan.overflow, ctx->plan.list, ctx->plan.k2_rows, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
 		ctx->d_peaks, ctx->d_rep, ctx->d_slab, ctx->d_slab_mask, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
-		ctx->d_exchange };
+		ctx->d_exchange, ctx->d_comm_seq, ctx->d_comm_ticket };
 	for (void *p : ptrs) {
 		if (p) {
 			cudaFree(p);
@@ -991,16 +991,24 @@ int gas_profile_read(gas_ctx *ctx, double ms_out[GAS_KERNEL_KINDS], uint64_t lau
 	return GAS_OK;
 }
 
-// ---- multi-GPU exchange (round 1: handles only; the fused peer epilogue lands with the N>1 work) ----------
+// ---- multi-GPU exchange: peer-memory sum of the partial bus buffers (gas_comm.cu) --------------------------------
+static size_t comm_alloc_bytes(gas_ctx *ctx) {
+	return ((size_t)2 * ctx->comm_stride_f4 + 16) * sizeof(float4); // two parity buffers + the arrival counter
+}
+
 int gas_comm_export(gas_ctx *ctx, void *handle_out, size_t handle_bytes) {
 	ENTER(ctx);
 	if (!handle_out || handle_bytes < sizeof(cudaIpcMemHandle_t)) {
 		return gas_fail(ctx, GAS_ERR_INVALID, "gas_comm_export: handle buffer must hold %zu bytes", sizeof(cudaIpcMemHandle_t));
 	}
 	if (!ctx->d_exchange) {
-		const size_t n = (size_t)8 * GAS_MAX_BUSES * GAS_MAX_CHANNELS_PER_BUS * ctx->cfg.max_frames;
-		GAS_CUDA(ctx, cudaMalloc((void **)&ctx->d_exchange, n * sizeof(gas_frame)));
-		GAS_CUDA(ctx, cudaMemset(ctx->d_exchange, 0, n * sizeof(gas_frame)));
+		ctx->comm_stride_f4 = ctx->cfg.num_buses * GAS_MAX_CHANNELS_PER_BUS * ctx->cfg.max_frames / 2;
+		GAS_CUDA(ctx, cudaMalloc((void **)&ctx->d_exchange, comm_alloc_bytes(ctx)));
+		GAS_CUDA(ctx, cudaMemset(ctx->d_exchange, 0, comm_alloc_bytes(ctx)));
+		GAS_CUDA(ctx, cudaMalloc((void **)&ctx->d_comm_seq, 2 * sizeof(unsigned long long)));
+		GAS_CUDA(ctx, cudaMemset(ctx->d_comm_seq, 0, 2 * sizeof(unsigned long long)));
+		GAS_CUDA(ctx, cudaMalloc((void **)&ctx->d_comm_ticket, 2 * sizeof(int)));
+		GAS_CUDA(ctx, cudaMemset(ctx->d_comm_ticket, 0, 2 * sizeof(int)));
 	}
 	cudaIpcMemHandle_t h;
 	GAS_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->d_exchange));
@@ -1030,6 +1038,38 @@ int gas_comm_open(gas_ctx *ctx, int32_t rank, int32_t n_ranks, const void *handl
 	ctx->comm_rank = rank;
 	ctx->comm_ranks = n_ranks;
 	return GAS_OK;
+}
+
+static int reduce_half(gas_ctx *ctx, gas_frame *d_bus, int32_t frames, bool begin, bool end, const char *who) {
+	if (!d_bus || frames < 2 || (frames & 1) || frames > ctx->cfg.max_frames || ((uintptr_t)d_bus & 15u)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "%s: bad buffer or frame count", who);
+	}
+	if (ctx->comm_ranks <= 1) {
+		return GAS_OK; // one rank: the partial sum is the sum
+	}
+	if (!ctx->d_exchange || !ctx->peer_exchange[ctx->comm_ranks - 1]) {
+		return gas_fail(ctx, GAS_ERR_STATE, "%s: gas_comm_open has not been called", who);
+	}
+	if (begin) {
+		GAS_CUDA(ctx, launch_comm_push(ctx, d_bus, frames, ctx->s_mix));
+	}
+	if (end) {
+		GAS_CUDA(ctx, launch_comm_finish(ctx, d_bus, frames, ctx->s_mix));
+	}
+	return GAS_OK;
+}
+
+int gas_reduce_bus_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames) {
+	ENTER(ctx);
+	return reduce_half(ctx, d_bus, frames, true, true, "gas_reduce_bus_device");
+}
+int gas_reduce_bus_begin_device(gas_ctx *ctx, const gas_frame *d_bus, int32_t frames) {
+	ENTER(ctx);
+	return reduce_half(ctx, const_cast<gas_frame *>(d_bus), frames, true, false, "gas_reduce_bus_begin_device");
+}
+int gas_reduce_bus_end_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames) {
+	ENTER(ctx);
+	return reduce_half(ctx, d_bus, frames, false, true, "gas_reduce_bus_end_device");
 }
 
 int gas_comm_close(gas_ctx *ctx) {

@@ -133,22 +133,6 @@ __device__ float attenuation_db(const gas_spatializer &s, float volume_db, float
 	return att;
 }
 
-// SPCAP speaker set (reference audio_spatializer_3d.cpp:47-55), normalised in float exactly as
-// Vector3(-1,0,-1).normalized() does: x / sqrtf(2.f).
-__device__ __forceinline__ V3 spcap_dir(int i) {
-	V3 raw;
-	switch (i) {
-		case 0: raw = V3{ -1.f, 0.f, -1.f }; break;
-		case 1: raw = V3{ 1.f, 0.f, -1.f }; break;
-		case 2: raw = V3{ 0.f, 0.f, -1.f }; break;
-		case 3: raw = V3{ -1.f, 0.f, 1.f }; break;
-		case 4: raw = V3{ 1.f, 0.f, 1.f }; break;
-		case 5: raw = V3{ -1.f, 0.f, 0.f }; break;
-		default: raw = V3{ 1.f, 0.f, 0.f }; break;
-	}
-	return norm3(raw);
-}
-
 // reference audio_spatializer_3d.cpp:57-98 + :903-938.  Lane `l` of the emitter's 8-lane group (mask gm,
 // first lane gbase) owns speaker l; sums run in speaker order exactly like the reference loop.
 __device__ void output_vol_surround(unsigned gm, int gbase, int l, const GlobalCfg &g, V3 src, float tightness, float out[4][2]) {
@@ -262,26 +246,6 @@ __device__ void reverb_vol(unsigned gm, int gbase, int l, const GlobalCfg &g, co
 
 __device__ __forceinline__ int resolve_bus(const GlobalCfg &g, int bus) { // audio_stream_player_spatial.cpp:405-413
 	return (bus >= 0 && bus < g.num_buses) ? bus : 0;
-}
-
-__device__ void add_bus_volume(gas_params &p, int bus, const float vol[4][2]) { // spatializer_parameters.cpp:35-38
-	int slot = -1;
-	for (int i = 0; i < p.n_bus; i++) {
-		if (p.bus[i] == bus) {
-			slot = i;
-		}
-	}
-	if (slot < 0) {
-		if (p.n_bus >= GAS_MAX_BUSES_PER_PLAYBACK) {
-			return;
-		}
-		slot = p.n_bus++;
-		p.bus[slot] = bus;
-	}
-	for (int c = 0; c < 4; c++) {
-		p.bus_volumes[slot][c][0] = vol[c][0];
-		p.bus_volumes[slot][c][1] = vol[c][1];
-	}
 }
 
 // AudioSpatializerInstance::get_bus_map for all proxy channels at once (audio_spatializer.cpp:274-324):

@@ -182,6 +182,9 @@ struct gas_ctx {
 	gas_frame *d_exchange = nullptr;
 	int32_t comm_rank = 0, comm_ranks = 1;
 	gas_frame *peer_exchange[8] = {};
+	int comm_stride_f4 = 0;                  // 16-byte elements between the two parity buffers of an exchange allocation
+	unsigned long long *d_comm_seq = nullptr; // [2] blocks pushed / finished so far (device-side, so that captured graphs stay valid)
+	int *d_comm_ticket = nullptr;             // [2] CTA tickets of the two exchange kernels
 	uint64_t launches = 0;
 	bool k2_smem_attr_set = false;
 	int skip = 0;     // GAS_SKIP bits (experiments only)
@@ -261,6 +264,9 @@ static inline int gas_bus_f4(const gas_ctx *ctx, int frames) { return ctx->g.num
 cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, cudaStream_t st);
 cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus,
 		gas_frame *d_peaks, cudaStream_t st);
+// gas_comm.cu
+cudaError_t launch_comm_push(gas_ctx *ctx, const gas_frame *d_bus, int frames, cudaStream_t st);
+cudaError_t launch_comm_finish(gas_ctx *ctx, gas_frame *d_bus, int frames, cudaStream_t st);
 // gas_state.cu
 cudaError_t launch_instance_init(gas_ctx *ctx, int n, const int32_t *d_ids, const int32_t *d_spat, cudaStream_t st);
 cudaError_t launch_instance_stop(gas_ctx *ctx, int n, const int32_t *d_ids, cudaStream_t st);

@@ -54,6 +54,9 @@ PROTOTYPES = {
     "gas_voice_state_import": (C.c_int, [_vp, _i32, _vp, _vp]),
     "gas_comm_export": (C.c_int, [_vp, _vp, _sz]),
     "gas_comm_open": (C.c_int, [_vp, _i32, _i32, _vp, _sz]),
+    "gas_reduce_bus_device": (C.c_int, [_vp, _vp, _i32]),
+    "gas_reduce_bus_begin_device": (C.c_int, [_vp, _vp, _i32]),
+    "gas_reduce_bus_end_device": (C.c_int, [_vp, _vp, _i32]),
     "gas_comm_close": (C.c_int, [_vp]),
 }
 

@@ -253,5 +253,15 @@ class Mixer:
         blob = b"".join(handles)
         self._ck(self._lib.gas_comm_open(self._ctx, int(rank), len(handles), blob, 64))
 
+    def reduce_bus_device(self, d_bus, frames):
+        """gas_reduce_bus_device: d_bus (partial sums of this rank) becomes the sum over all ranks; asynchronous."""
+        self._ck(self._lib.gas_reduce_bus_device(self._ctx, C.c_void_p(d_bus), int(frames)))
+
+    def reduce_bus_begin_device(self, d_bus, frames):
+        self._ck(self._lib.gas_reduce_bus_begin_device(self._ctx, C.c_void_p(d_bus), int(frames)))
+
+    def reduce_bus_end_device(self, d_bus, frames):
+        self._ck(self._lib.gas_reduce_bus_end_device(self._ctx, C.c_void_p(d_bus), int(frames)))
+
     def comm_close(self):
         self._ck(self._lib.gas_comm_close(self._ctx))

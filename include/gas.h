@@ -374,12 +374,22 @@ GAS_API int gas_profile_read(gas_ctx *ctx, double ms_out[GAS_KERNEL_KINDS], uint
 GAS_API int gas_voice_state_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_voice_state *out);
 GAS_API int gas_voice_state_import(gas_ctx *ctx, int32_t n, const int32_t *voices, const gas_voice_state *in);
 
-/* ---- multi-GPU: voices sharded over ranks, partial bus buffers summed ---------------------------- */
-/* Peer-memory reduce: every rank exports an IPC handle of its partial-bus exchange buffer; rank r
- * opens the others and the mix epilogue pushes partial sums straight into the root's buffer over
- * NVLink.  handle_out: 64 bytes (cudaIpcMemHandle_t). */
+/* ---- multi-GPU: voices sharded over ranks, partial bus buffers summed over peer memory ----------------
+ * No reference analogue (one audio thread).  Every rank exports an IPC handle of its exchange allocation and
+ * opens the others'; gas_reduce_bus_device then turns every rank's partial bus buffer into the sum over all
+ * ranks: each rank adds its partial sums straight into every rank's exchange buffer with vector reductions on
+ * peer pointers (NVLink / NVSwitch), one arrival counter round per block is the only synchronisation.
+ * handle_out: 64 bytes (cudaIpcMemHandle_t).  All ranks must call gas_reduce_bus_device once per block, in the
+ * same order; it is asynchronous on the mix stream and can be captured into a step graph. */
 GAS_API int gas_comm_export(gas_ctx *ctx, void *handle_out, size_t handle_bytes);
 GAS_API int gas_comm_open(gas_ctx *ctx, int32_t rank, int32_t n_ranks, const void *handles, size_t handle_bytes);
+GAS_API int gas_reduce_bus_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames);
+/* The two halves of gas_reduce_bus_device, for callers that overlap the other ranks' skew with their next block:
+ * begin pushes this rank's partial sums of block n to every rank, end waits for every rank's push of the oldest
+ * unfinished block and writes its complete sum to d_bus.  Per rank the order must be begin(n), ..., end(n) with
+ * end(n) before begin(n + 2) at the latest (two exchange buffers). */
+GAS_API int gas_reduce_bus_begin_device(gas_ctx *ctx, const gas_frame *d_bus, int32_t frames);
+GAS_API int gas_reduce_bus_end_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames);
 GAS_API int gas_comm_close(gas_ctx *ctx);
 
 #ifdef __cplusplus
