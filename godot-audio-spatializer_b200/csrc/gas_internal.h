@@ -186,7 +186,7 @@ struct gas_ctx {
 	unsigned long long *d_comm_seq = nullptr; // [2] blocks pushed / finished so far (device-side, so that captured graphs stay valid)
 	int *d_comm_ticket = nullptr;             // [2] CTA tickets of the two exchange kernels
 	uint64_t launches = 0;
-	bool k2_smem_attr_set = false;
+	bool k2_smem_attr_set = false, k3_smem_attr_set = false;
 	int skip = 0;     // GAS_SKIP bits (experiments only)
 	unsigned long long *d_timeline = nullptr; // GAS_K2_DEBUG & 8: per-CTA globaltimer stamps of the last K2 launch
 	bool pdl = false; // GAS_PDL=1: mix-side kernels are launched with programmatic stream serialization

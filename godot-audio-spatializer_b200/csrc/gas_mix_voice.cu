@@ -17,8 +17,19 @@
 
 namespace {
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 8;
+constexpr int kMaxTileBytes = 96 * 1024; // CTA-wide accumulation tile (whole bus layout of the block) when it fits
 constexpr unsigned kFull = 0xffffffffu;
+
+// add into the CTA's accumulation tile (explicit shared-space reduction: a generic-address atomicAdd on shared
+// memory is an order of magnitude slower) or, without a tile, into the bus buffers
+__device__ __forceinline__ void acc_add(float *bus, uint32_t tile_s, size_t o, float v) {
+	if (tile_s) {
+		asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(tile_s + (uint32_t)o * 4u), "f"(v) : "memory");
+	} else {
+		atomicAdd(bus + o, v);
+	}
+}
 
 struct Biquad {
 	float ha1, ha2, hb1, hb2;
@@ -77,7 +88,7 @@ struct ChunkArgs {
 // in this pass (1 or 2).  `emit` false => NS == 1 with no bus output (state/peak only).
 template <int MODE, int C, int NS>
 __device__ void voice_pass(const DevTables &t, const GlobalCfg &g, const ChunkArgs &a, int send0, bool emit, bool last_pass,
-		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks) {
+		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
 	const int lane = threadIdx.x & 31;
 	const int pos = a.chunk * 32 + lane;
 	const bool active = pos < a.count;
@@ -286,7 +297,8 @@ __device__ void voice_pass(const DevTables &t, const GlobalCfg &g, const ChunkAr
 				if (owner) {
 					const int side = idx & 1, f = (idx >> 1) & 1, sc = idx >> 2;
 					const int c = sc % C, s = sc / C;
-					atomicAdd(bus + ((size_t)(bus_of[s] * C + c) * F + ia + f) * 2 + side, tot);
+					const size_t o = ((size_t)(bus_of[s] * C + c) * F + ia + f) * 2 + side;
+					acc_add(bus, tile, o, tot); // the CTA adds its tile to the bus buffers once, at its end
 				}
 			}
 		}
@@ -326,29 +338,166 @@ __device__ void voice_pass(const DevTables &t, const GlobalCfg &g, const ChunkAr
 	}
 }
 
-template <int MODE, int C>
-__device__ void voice_chunk(const DevTables &t, const GlobalCfg &g, const ChunkArgs &a, const gas_frame *__restrict__ src, int src_stride,
-		int F, float *__restrict__ bus, float2 *__restrict__ peaks) {
-	const int n = a.n_send;
-	if (n == 0) {
-		voice_pass<MODE, C, 1>(t, g, a, 0, false, true, src, src_stride, F, bus, peaks);
-		return;
+// Mode B with the attenuation filter on: 2C biquads per voice.  Here a lane is one (voice, pair, side) stream — 8
+// lanes per voice, 4 voices per warp — so a voice's biquads run side by side instead of one after the other in a
+// single lane, and 8x more warps hide the recurrence latency.  Frames are fetched 8 at a time (one float2 per lane
+// of the voice = 64 contiguous bytes) and handed round with shuffles; t = i / F is computed once per frame by the
+// lane that fetched it.  The 4 voices of the warp are summed with two shuffles per send before the add into the
+// CTA's accumulation tile (or the bus buffers).
+template <int C, int NS>
+__device__ void voice_pass_b(const DevTables &t, const ChunkArgs &a, int send0, bool last_pass, const gas_frame *__restrict__ src,
+		int src_stride, int F, float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
+	const int lane = threadIdx.x & 31;
+	const int g = lane >> 3, l = lane & 7, c = l >> 1, side = l & 1;
+	const int gbase = lane & 24;
+	const int pos = a.chunk * 4 + g;
+	const bool has_voice = pos < a.count;
+	const bool active = has_voice && c < C;
+	const int j = has_voice ? a.list[pos].x : -1;
+	const VoiceRec *rec = &a.rec[has_voice ? j : 0];
+	const int voice = has_voice ? rec->voice : 0;
+	const int src_row = has_voice ? rec->src_row : -1;
+	const uint32_t flags = has_voice ? rec->flags : 0u;
+	const float m_prev = active ? rec->m_prev[c][side] : 0.f;
+	const float m_new = active ? rec->m_new[c][side] : 0.f;
+	float target[5];
+#pragma unroll
+	for (int q = 0; q < 5; q++) {
+		target[q] = active ? rec->target[q] : 0.f;
 	}
-	for (int s0 = 0; s0 < n; s0 += 2) {
-		const bool last = s0 + 2 >= n;
-		if (n - s0 >= 2) {
-			voice_pass<MODE, C, 2>(t, g, a, s0, true, last, src, src_stride, F, bus, peaks);
-		} else {
-			voice_pass<MODE, C, 1>(t, g, a, s0, true, last, src, src_stride, F, bus, peaks);
+	float np[NS], nn[NS];
+	int bus_of[NS];
+	{
+		const InstSends *snd = &a.sends[has_voice ? j : 0];
+		uint32_t m = a.mask;
+		for (int s = 0; s < send0; s++) {
+			m &= m - 1;
+		}
+#pragma unroll
+		for (int s = 0; s < NS; s++) {
+			bus_of[s] = m ? (__ffs(m) - 1) : 0;
+			m &= m - 1;
+			const bool ok = active && (send0 + s) < a.n_send;
+			np[s] = ok ? snd->vp[send0 + s][c][side] : 0.f;
+			nn[s] = ok ? snd->vn[send0 + s][c][side] : 0.f;
+		}
+	}
+	gas_processor_state *ps = t.vs_proc + (size_t)voice * 8 + l; // processor index pair * 2 + (left ? 0 : 1)
+	gas_processor_state st{};
+	if (active) {
+		st = *ps;
+	}
+	const bool clear = (flags >> (8 + c)) & 1u; // is_just_started => clear history (:583-586)
+	Biquad h;
+	h.ha1 = clear ? 0.f : st.ha1;
+	h.ha2 = clear ? 0.f : st.ha2;
+	h.hb1 = clear ? 0.f : st.hb1;
+	h.hb2 = clear ? 0.f : st.hb2;
+	float cf[5] = { st.b0, st.b1, st.b2, st.a1, st.a2 }, inc[5];
+#pragma unroll
+	for (int q = 0; q < 5; q++) { // update_coeffs(F): per-sample increment towards the target
+		inc[q] = (target[q] - cf[q]) / (float)F;
+	}
+	float pk = 0.f;
+	const float2 *row = src_row >= 0 ? reinterpret_cast<const float2 *>(src + (size_t)src_row * src_stride) : nullptr;
+	for (int i0 = 0; i0 < F; i0 += 8) {
+		const int mi = i0 + l;
+		const float2 mx = (row && mi < F) ? __ldg(row + mi) : make_float2(0.f, 0.f);
+		const float mt = (float)mi / (float)F; // :591
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			const int i = i0 + k;
+			if (i >= F) {
+				break;
+			}
+			const float xl = __shfl_sync(kFull, mx.x, gbase + k);
+			const float xr = __shfl_sync(kFull, mx.y, gbase + k);
+			const float tt = __shfl_sync(kFull, mt, gbase + k);
+			const float omt = 1.0f - tt;
+			const float vol = m_new * tt + omt * m_prev; // :592
+			float y = vol * (side ? xr : xl);             // :593
+			y = biquad_step(h, y, cf[0], cf[1], cf[2], cf[3], cf[4]); // :594-595
+#pragma unroll
+			for (int q = 0; q < 5; q++) { // process_one_interp: coeffs += incr
+				cf[q] += inc[q];
+			}
+			pk = fmaxf(pk, fabsf(y));
+#pragma unroll
+			for (int s = 0; s < NS; s++) {
+				float v = (nn[s] * tt + omt * np[s]) * y; // AudioServer ramp of this send (upstream _mix_step_for_channel)
+				v += __shfl_xor_sync(kFull, v, 8);
+				v += __shfl_xor_sync(kFull, v, 16);
+				if (g == 0 && c < C && (send0 + s) < a.n_send) {
+					const size_t o = ((size_t)(bus_of[s] * C + c) * F + i) * 2 + side;
+					acc_add(bus, tile, o, v);
+				}
+			}
+		}
+	}
+	if (last_pass) {
+		if (active) {
+			st.b0 = cf[0];
+			st.b1 = cf[1];
+			st.b2 = cf[2];
+			st.a1 = cf[3];
+			st.a2 = cf[4];
+			st.ha1 = h.ha1;
+			st.ha2 = h.ha2;
+			st.hb1 = h.hb1;
+			st.hb2 = h.hb2;
+			*ps = st;
+		}
+		// block peak: max over the voice's pairs, per side (audio_spatializer.cpp:436-443)
+		pk = fmaxf(pk, __shfl_xor_sync(kFull, pk, 2));
+		pk = fmaxf(pk, __shfl_xor_sync(kFull, pk, 4));
+		if (has_voice && (flags & GAS_VOICE_WANT_PEAK) && peaks && l < 2) {
+			reinterpret_cast<float *>(peaks + j)[l] = pk;
 		}
 	}
 }
 
 template <int C>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_mix_voice(DevTables t, GlobalCfg g, BlockPlan plan,
+__device__ void voice_chunk_b(const DevTables &t, const ChunkArgs &a, const gas_frame *__restrict__ src, int src_stride, int F,
+		float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
+	const int n = a.n_send;
+	if (n == 0) {
+		voice_pass_b<C, 1>(t, a, 0, true, src, src_stride, F, bus, tile, peaks); // state / peak only: every send test fails
+		return;
+	}
+	for (int s0 = 0; s0 < n; s0 += 2) {
+		const bool last = s0 + 2 >= n;
+		if (n - s0 >= 2) {
+			voice_pass_b<C, 2>(t, a, s0, last, src, src_stride, F, bus, tile, peaks);
+		} else {
+			voice_pass_b<C, 1>(t, a, s0, last, src, src_stride, F, bus, tile, peaks);
+		}
+	}
+}
+
+template <int MODE, int C>
+__device__ void voice_chunk(const DevTables &t, const GlobalCfg &g, const ChunkArgs &a, const gas_frame *__restrict__ src, int src_stride,
+		int F, float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
+	const int n = a.n_send;
+	if (n == 0) {
+		voice_pass<MODE, C, 1>(t, g, a, 0, false, true, src, src_stride, F, bus, tile, peaks);
+		return;
+	}
+	for (int s0 = 0; s0 < n; s0 += 2) {
+		const bool last = s0 + 2 >= n;
+		if (n - s0 >= 2) {
+			voice_pass<MODE, C, 2>(t, g, a, s0, true, last, src, src_stride, F, bus, tile, peaks);
+		} else {
+			voice_pass<MODE, C, 1>(t, g, a, s0, true, last, src, src_stride, F, bus, tile, peaks);
+		}
+	}
+}
+
+template <int C>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t, GlobalCfg g, BlockPlan plan,
 		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks,
 		const float4 *__restrict__ rep, int bus_f4, int replicas, const float4 *__restrict__ slab,
-		const unsigned long long *__restrict__ slab_mask, int slab_ctas) {
+		const unsigned long long *__restrict__ slab_mask, int slab_ctas, int tile_floats) {
+	extern __shared__ __align__(16) float s_tile[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ int s_ncls;
 	GAS_GRID_DEP_WAIT();
@@ -440,36 +589,75 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_mix_voice(DevTables t, Gl
 		}
 	}
 	__syncthreads();
-	const int warp_global = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-	const int n_warps = gridDim.x * kWarpsPerCta;
-	// units: 32-voice chunks of every PATH_VOICE class, dealt round-robin to warps
-	int unit = 0;
+	// CTA-wide accumulation tile: the voices of all chunks this CTA visits are summed in shared memory and reach the
+	// bus buffers as one vector reduction per 16 bytes (instead of one scalar atomic per element per 32 voices)
+	const uint32_t tile = tile_floats > 0 ? (uint32_t)__cvta_generic_to_shared(s_tile) : 0u;
+	bool cta_has_work = false;
+	{
+		int units = 0;
+		for (int c = 0; c < s_ncls; c++) {
+			const bool by_stream = s_cls[c].mode == MODE_B && (s_cls[c].flags & CLS_FILT);
+			units += by_stream ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 31) / 32;
+		}
+		cta_has_work = units > (int)blockIdx.x; // units are dealt round-robin to CTAs, then to the warps of a CTA
+	}
+	if (tile && cta_has_work) {
+		for (int i = threadIdx.x; i < tile_floats / 4; i += blockDim.x) {
+			reinterpret_cast<float4 *>(s_tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+		__syncthreads();
+	}
+	const int my_warp = threadIdx.x >> 5;
+	// Units (32-voice chunks, or 4-voice chunks for the stream-parallel Mode B path) are numbered class by class and
+	// dealt round-robin to the CTAs, then to the warps of a CTA: this warp owns units b + grid * (w + 8 r), r = 0, 1, ...
+	int total_units = 0;
 	for (int c = 0; c < s_ncls; c++) {
-		const ClassInfo &ci = s_cls[c];
-		const int chunks = (ci.count + 31) / 32;
-		for (int k = 0; k < chunks; k++, unit++) {
-			if (unit % n_warps != warp_global) {
-				continue;
+		const bool by_stream = s_cls[c].mode == MODE_B && (s_cls[c].flags & CLS_FILT);
+		total_units += by_stream ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 31) / 32;
+	}
+	for (int unit = (int)blockIdx.x + (int)gridDim.x * my_warp; unit < total_units; unit += (int)gridDim.x * kWarpsPerCta) {
+		int c = 0, k = unit;
+		bool by_stream = false;
+		for (; c < s_ncls; c++) { // class and chunk of the unit
+			by_stream = s_cls[c].mode == MODE_B && (s_cls[c].flags & CLS_FILT); // lane = (voice, pair, side): 4 voices per warp
+			const int chunks = by_stream ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 31) / 32;
+			if (k < chunks) {
+				break;
 			}
-			ChunkArgs a;
-			a.rec = plan.rec;
-			a.sends = plan.sends;
-			a.list = plan.list + (size_t)ci.slot * g.max_voices;
-			a.count = ci.count;
-			a.chunk = k;
-			a.cls_flags = ci.flags;
-			a.mask = ci.mask;
-			a.n_send = ci.n_send;
-			switch (ci.mode) {
-				case MODE_A:
-					voice_chunk<MODE_A, C>(t, g, a, src, src_stride, F, bus, peaks);
-					break;
-				case MODE_B:
-					voice_chunk<MODE_B, C>(t, g, a, src, src_stride, F, bus, peaks);
-					break;
-				default:
-					voice_chunk<MODE_E, C>(t, g, a, src, src_stride, F, bus, peaks);
-					break;
+			k -= chunks;
+		}
+		const ClassInfo &ci = s_cls[c];
+		ChunkArgs a;
+		a.rec = plan.rec;
+		a.sends = plan.sends;
+		a.list = plan.list + (size_t)ci.slot * g.max_voices;
+		a.count = ci.count;
+		a.chunk = k;
+		a.cls_flags = ci.flags;
+		a.mask = ci.mask;
+		a.n_send = ci.n_send;
+		switch (ci.mode) {
+			case MODE_A:
+				voice_chunk<MODE_A, C>(t, g, a, src, src_stride, F, bus, tile, peaks);
+				break;
+			case MODE_B:
+				if (by_stream) {
+					voice_chunk_b<C>(t, a, src, src_stride, F, bus, tile, peaks);
+				} else {
+					voice_chunk<MODE_B, C>(t, g, a, src, src_stride, F, bus, tile, peaks);
+				}
+				break;
+			default:
+				voice_chunk<MODE_E, C>(t, g, a, src, src_stride, F, bus, tile, peaks);
+				break;
+		}
+	}
+	if (tile && cta_has_work) {
+		__syncthreads();
+		for (int i = threadIdx.x; i < tile_floats / 4; i += blockDim.x) {
+			const float4 v = reinterpret_cast<const float4 *>(s_tile)[i];
+			if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+				asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(bus + (size_t)i * 4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 			}
 		}
 	}
@@ -480,23 +668,37 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_mix_voice(DevTables t, Gl
 cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus,
 		gas_frame *d_peaks, cudaStream_t st) {
 	const int bus_f4 = gas_bus_f4(ctx, frames);
-	int grid = ctx->num_sms * 4;
-	if (grid * kWarpsPerCta * 32 < bus_f4 * 8) {
-		grid = (bus_f4 * 8 + kWarpsPerCta * 32 - 1) / (kWarpsPerCta * 32);
+	const int threads = kWarpsPerCta * 32;
+	int grid = ctx->num_sms * 2; // two CTAs per SM (128 registers): many chunks per CTA make the shared-memory tile pay
+	const int fold_threads = ctx->slab_ctas > 0 ? bus_f4 * 8 : bus_f4;
+	if (grid * threads < fold_threads) {
+		grid = (fold_threads + threads - 1) / threads;
+	}
+	int tile_floats = bus_f4 * 4;
+	if ((size_t)tile_floats * sizeof(float) > (size_t)kMaxTileBytes) {
+		tile_floats = 0; // too many buses x frames for shared memory: scalar atomics straight into the bus buffers
+	}
+	const size_t smem = (size_t)tile_floats * sizeof(float);
+	if (!ctx->k3_smem_attr_set) {
+		cudaFuncSetAttribute(k_mix_voice<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes);
+		cudaFuncSetAttribute(k_mix_voice<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes);
+		cudaFuncSetAttribute(k_mix_voice<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes);
+		cudaFuncSetAttribute(k_mix_voice<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes);
+		ctx->k3_smem_attr_set = true;
 	}
 	cudaError_t e = cudaSuccess;
 	switch (ctx->g.channels) {
 		case 1:
-			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas);
+			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(threads), smem, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
 			break;
 		case 2:
-			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas);
+			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(threads), smem, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
 			break;
 		case 3:
-			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas);
+			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(threads), smem, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
 			break;
 		default:
-			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas);
+			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(threads), smem, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
 			break;
 	}
 	ctx->launches++;
