@@ -4,11 +4,15 @@
 // process_frames / mix_channel (reference audio_spatializer_3d.cpp:503-529, :568-597, upstream
 // AudioFilterSW::Processor) or an AudioSpatializerEffect filter chain (reference
 // audio_spatializer_effect.cpp:33-77) — and voices that must report a block peak
-// (reference audio_spatializer.cpp:419-461) run here: one lane per voice, serial in time, filter state in
-// registers for the whole block, 32 voices of one class per warp.  After the per-voice work the
-// AudioServer ramp (upstream _mix_step_for_channel) is applied per lane and the 32 voices are summed
-// with a transposing warp-shuffle reduction; each lane ends up owning one (send, pair, frame, side)
-// element which it adds to the bus buffer.
+// (reference audio_spatializer.cpp:419-461) run here, serial in time with the filter state in registers for
+// the whole block.  The parallel axis is the *stream*, not the voice:
+//   Mode B   one lane per (voice, pair, side): the voice's 2C biquads run side by side, 4 voices per warp;
+//   Mode A / effect chains   one lane per (voice, side), 16 voices per warp.
+// After the per-stream work the AudioServer ramp (upstream _mix_step_for_channel) is applied per lane, the
+// voices of the warp are summed with shuffles and the result is added to a CTA-wide accumulation tile in
+// shared memory (the whole bus layout of the block, explicit red.shared); the CTA adds its tile to the bus
+// buffers once, with one vector reduction per 16 bytes.  The launch also folds the streaming kernel's partial
+// sums (replicas or slabs) into the bus buffers, so it runs every block.
 //
 // Sends are processed two at a time; a voice with more than two sends (bus transitions) is run in
 // several passes from the same initial state — every pass recomputes bit-identical samples, only the
@@ -45,34 +49,6 @@ __device__ __forceinline__ float biquad_step(Biquad &h, float x, float b0, float
 	return y;
 }
 
-// Transposing reduction: NV (power of two <= 32) per-lane values are summed over the 32 lanes; on
-// return v[0] of lane l holds the total of element l >> (5 - log2 NV).
-template <int NV>
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane) {
-	int m = 16;
-#pragma unroll
-	for (int w = NV / 2; w >= 1; w >>= 1) {
-		const bool upper = (lane & m) != 0;
-#pragma unroll
-		for (int i = 0; i < w; i++) {
-			const float send = upper ? v[i] : v[i + w];
-			const float keep = upper ? v[i + w] : v[i];
-			v[i] = keep + __shfl_xor_sync(kFull, send, m);
-		}
-		m >>= 1;
-	}
-#pragma unroll
-	for (; m >= 1; m >>= 1) {
-		v[0] += __shfl_xor_sync(kFull, v[0], m);
-	}
-	return v[0];
-}
-
-template <int N>
-struct Pow2Ceil {
-	static constexpr int value = N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : 32));
-};
-
 struct ChunkArgs {
 	const VoiceRec *rec;
 	const InstSends *sends; // by call-order index
@@ -84,261 +60,46 @@ struct ChunkArgs {
 	int n_send;
 };
 
-// One pass of one 32-voice chunk.  MODE: MODE_A / MODE_B / MODE_E.  C: channel pairs.  NS: sends handled
-// in this pass (1 or 2).  `emit` false => NS == 1 with no bus output (state/peak only).
-template <int MODE, int C, int NS>
-__device__ void voice_pass(const DevTables &t, const GlobalCfg &g, const ChunkArgs &a, int send0, bool emit, bool last_pass,
-		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
-	const int lane = threadIdx.x & 31;
-	const int pos = a.chunk * 32 + lane;
-	const bool active = pos < a.count;
-	const int j = active ? a.list[pos].x : -1;
-	constexpr int NY = (MODE == MODE_B) ? C : 1; // distinct processed streams per voice (pairs)
-	constexpr int NPROC = NY * 2;
-
-	VoiceRec r;
-	if (active) {
-		r = a.rec[j];
-	} else {
-		r.voice = 0;
-		r.instance = 0;
-		r.src_row = -1;
-		r.flags = 0;
-		r.n_fx = 0;
-		for (int c = 0; c < 4; c++) {
-			r.m_prev[c][0] = r.m_prev[c][1] = r.m_new[c][0] = r.m_new[c][1] = 0.f;
-		}
-		for (int k = 0; k < 5; k++) {
-			r.target[k] = 0.f;
+// Transposing reduction over the high lane bits (16, 8, ... for LEVELS levels) of a batch of N per-lane values.
+// At every level the lanes with the bit set keep the upper half of what is left and receive the lower lanes'
+// upper half (and vice versa), so all shuffles of a level are independent of each other; once a single value is
+// left the remaining levels are plain butterfly sums.  On return v[0 .. max(1, N >> LEVELS)) hold totals over the
+// reduced lanes of the original values base .. base + count, and `owner` tells the one lane of every group of
+// identical results that should use them.
+template <int W, int LVL, int LEVELS, int N>
+struct ReduceHi {
+	static __device__ __forceinline__ void run(float (&v)[N], int lane, int &base, bool &owner) {
+		constexpr int m = 16 >> LVL;
+		if (W > 1) {
+			constexpr int H = W / 2 > 0 ? W / 2 : 1;
+			const bool upper = (lane & m) != 0;
+#pragma unroll
+			for (int i = 0; i < H; i++) {
+				const float send = upper ? v[i] : v[i + H];
+				const float keep = upper ? v[i + H] : v[i];
+				v[i] = keep + __shfl_xor_sync(kFull, send, m);
+			}
+			base += upper ? H : 0;
+			ReduceHi<H, LVL + 1, LEVELS, N>::run(v, lane, base, owner);
+		} else {
+			v[0] += __shfl_xor_sync(kFull, v[0], m);
+			owner = owner && (lane & m) == 0;
+			ReduceHi<1, LVL + 1, LEVELS, N>::run(v, lane, base, owner);
 		}
 	}
-	const bool filt = (a.cls_flags & CLS_FILT) != 0;
-	const bool want_peak = active && (r.flags & GAS_VOICE_WANT_PEAK);
-
-	// AudioServer ramps of the sends handled in this pass
-	float np[NS][C][2], nn[NS][C][2];
-	int bus_of[NS];
-	{
-		const InstSends *snd = &a.sends[active ? j : 0];
-		uint32_t m = a.mask;
-		for (int s = 0; s < send0; s++) {
-			m &= m - 1;
-		}
-#pragma unroll
-		for (int s = 0; s < NS; s++) {
-			bus_of[s] = m ? (__ffs(m) - 1) : 0;
-			m &= m - 1;
-#pragma unroll
-			for (int c = 0; c < C; c++) {
-				const bool ok = active && emit && (send0 + s) < a.n_send;
-				np[s][c][0] = ok ? snd->vp[send0 + s][c][0] : 0.f;
-				np[s][c][1] = ok ? snd->vp[send0 + s][c][1] : 0.f;
-				nn[s][c][0] = ok ? snd->vn[send0 + s][c][0] : 0.f;
-				nn[s][c][1] = ok ? snd->vn[send0 + s][c][1] : 0.f;
-			}
-		}
-	}
-
-	// ---- filter state -------------------------------------------------------------------------------
-	// MODE_A/B: interpolated high-shelf processors (pair*2 + side), MODE_E: constant-coefficient chain.
-	Biquad h[NPROC];
-	float cf[NPROC][5], inc[NPROC][5];
-	gas_processor_state *ps = t.vs_proc + (size_t)r.voice * 8;
-	if (MODE != MODE_E) {
-#pragma unroll
-		for (int k = 0; k < NPROC; k++) {
-			const int pair = k >> 1;
-			gas_processor_state st{};
-			if (active && filt) {
-				st = ps[k];
-			}
-			const bool clear = (r.flags >> (8 + pair)) & 1u; // is_just_started => clear history (:518-521, :583-586)
-			h[k].ha1 = clear ? 0.f : st.ha1;
-			h[k].ha2 = clear ? 0.f : st.ha2;
-			h[k].hb1 = clear ? 0.f : st.hb1;
-			h[k].hb2 = clear ? 0.f : st.hb2;
-			cf[k][0] = st.b0;
-			cf[k][1] = st.b1;
-			cf[k][2] = st.b2;
-			cf[k][3] = st.a1;
-			cf[k][4] = st.a2;
-#pragma unroll
-			for (int q = 0; q < 5; q++) { // update_coeffs(F): per-sample increment towards the target
-				inc[k][q] = (r.target[q] - cf[k][q]) / (float)F;
-			}
-		}
-	}
-	// effect chain history lives in local memory (dynamic structure); [effect][side][stage]{ha1,ha2,hb1,hb2}
-	float fxh[GAS_MAX_EFFECTS][2][GAS_MAX_FILTER_STAGES][4];
-	float *fxs = t.vs_fx + (size_t)r.voice * (GAS_MAX_EFFECTS * 2 * GAS_MAX_FILTER_STAGES * 4);
-	if (MODE == MODE_E) {
-		for (int e = 0; e < GAS_MAX_EFFECTS; e++) {
-			for (int s = 0; s < 2; s++) {
-				for (int q = 0; q < GAS_MAX_FILTER_STAGES; q++) {
-					for (int k = 0; k < 4; k++) {
-						fxh[e][s][q][k] = (active && e < r.n_fx) ? fxs[((e * 2 + s) * GAS_MAX_FILTER_STAGES + q) * 4 + k] : 0.f;
-					}
-				}
-			}
-		}
-	}
-
-	float pk_l = 0.f, pk_r = 0.f;
-	const float4 *row = (active && r.src_row >= 0) ? reinterpret_cast<const float4 *>(src + (size_t)r.src_row * src_stride) : nullptr;
-	const float invF = 1.0f; // t is computed as (float)i / F exactly like the reference
-	(void)invF;
-
-	constexpr int NVRAW = NS * C * 4;            // values per 2-frame group
-	constexpr int NV = Pow2Ceil<NVRAW>::value;
-	const int shift = (NV == 32) ? 0 : (NV == 16 ? 1 : (NV == 8 ? 2 : 3));
-
-	for (int i0 = 0; i0 < F; i0 += 8) { // 8 frames (64 bytes of this voice's row) per trip
-		float4 xb[4];
-#pragma unroll
-		for (int u = 0; u < 4; u++) {
-			xb[u] = (row && (i0 + 2 * u) < F) ? __ldg(row + (i0 >> 1) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-		}
-#pragma unroll
-		for (int u = 0; u < 4; u++) {
-			const int ia = i0 + 2 * u;
-			if (ia >= F) {
-				break;
-			}
-			float v[NV];
-#pragma unroll
-			for (int k = 0; k < NV; k++) {
-				v[k] = 0.f;
-			}
-#pragma unroll
-			for (int f = 0; f < 2; f++) {
-				const int i = ia + f;
-				const float tt = (float)i / (float)F;   // :591
-				const float omt = 1.0f - tt;
-				const float xl = f == 0 ? xb[u].x : xb[u].z;
-				const float xr = f == 0 ? xb[u].y : xb[u].w;
-				float y[NY][2];
-				if (MODE == MODE_B) {
-#pragma unroll
-					for (int c = 0; c < C; c++) {
-						const float vl = r.m_new[c][0] * tt + omt * r.m_prev[c][0]; // :592
-						const float vr = r.m_new[c][1] * tt + omt * r.m_prev[c][1];
-						float ml = vl * xl, mr = vr * xr;                         // :593
-						if (filt) {
-							const int kl = c * 2, kr = c * 2 + 1;
-							ml = biquad_step(h[kl], ml, cf[kl][0], cf[kl][1], cf[kl][2], cf[kl][3], cf[kl][4]); // :594
-							mr = biquad_step(h[kr], mr, cf[kr][0], cf[kr][1], cf[kr][2], cf[kr][3], cf[kr][4]); // :595
-#pragma unroll
-							for (int q = 0; q < 5; q++) { // process_one_interp: coeffs += incr
-								cf[kl][q] += inc[kl][q];
-								cf[kr][q] += inc[kr][q];
-							}
-						}
-						y[c][0] = ml;
-						y[c][1] = mr;
-					}
-				} else if (MODE == MODE_A) {
-					float ml = xl, mr = xr;
-					if (filt) { // :524-529
-						ml = biquad_step(h[0], ml, cf[0][0], cf[0][1], cf[0][2], cf[0][3], cf[0][4]);
-						mr = biquad_step(h[1], mr, cf[1][0], cf[1][1], cf[1][2], cf[1][3], cf[1][4]);
-#pragma unroll
-						for (int q = 0; q < 5; q++) {
-							cf[0][q] += inc[0][q];
-							cf[1][q] += inc[1][q];
-						}
-					}
-					y[0][0] = ml;
-					y[0][1] = mr;
-				} else { // MODE_E: cascaded constant-coefficient biquads per effect, left then right
-					float ml = xl, mr = xr;
-					for (int e = 0; e < r.n_fx; e++) {
-						const float b0 = r.fx_coef[e][0], b1 = r.fx_coef[e][1], b2 = r.fx_coef[e][2], a1 = r.fx_coef[e][3], a2 = r.fx_coef[e][4];
-						for (int q = 0; q < r.fx_stages[e]; q++) {
-							float *hl = fxh[e][0][q], *hr = fxh[e][1][q];
-							float pl = ml, pr = mr;
-							ml = ml * b0 + hl[2] * b1 + hl[3] * b2 + hl[0] * a1 + hl[1] * a2;
-							mr = mr * b0 + hr[2] * b1 + hr[3] * b2 + hr[0] * a1 + hr[1] * a2;
-							hl[1] = hl[0];
-							hl[3] = hl[2];
-							hl[2] = pl;
-							hl[0] = ml;
-							hr[1] = hr[0];
-							hr[3] = hr[2];
-							hr[2] = pr;
-							hr[0] = mr;
-						}
-					}
-					y[0][0] = ml;
-					y[0][1] = mr;
-				}
-				// block peak over all processed streams (audio_spatializer.cpp:436-443, :453-460)
-#pragma unroll
-				for (int c = 0; c < NY; c++) {
-					pk_l = fmaxf(pk_l, fabsf(y[c][0]));
-					pk_r = fmaxf(pk_r, fabsf(y[c][1]));
-				}
-				// AudioServer ramp per send / pair / side (upstream _mix_step_for_channel)
-#pragma unroll
-				for (int s = 0; s < NS; s++) {
-#pragma unroll
-					for (int c = 0; c < C; c++) {
-						const int yc = (MODE == MODE_B) ? c : 0;
-						const float wl = nn[s][c][0] * tt + omt * np[s][c][0];
-						const float wr = nn[s][c][1] * tt + omt * np[s][c][1];
-						v[((s * C + c) * 2 + f) * 2 + 0] = wl * y[yc][0];
-						v[((s * C + c) * 2 + f) * 2 + 1] = wr * y[yc][1];
-					}
-				}
-			}
-			if (emit) {
-				const float tot = warp_transpose_reduce<NV>(v, lane);
-				const int idx = lane >> shift;
-				const bool owner = (lane & ((1 << shift) - 1)) == 0 && idx < NVRAW;
-				if (owner) {
-					const int side = idx & 1, f = (idx >> 1) & 1, sc = idx >> 2;
-					const int c = sc % C, s = sc / C;
-					const size_t o = ((size_t)(bus_of[s] * C + c) * F + ia + f) * 2 + side;
-					acc_add(bus, tile, o, tot); // the CTA adds its tile to the bus buffers once, at its end
-				}
-			}
-		}
-	}
-
-	if (last_pass && active) {
-		if (MODE != MODE_E && filt) {
-#pragma unroll
-			for (int k = 0; k < NPROC; k++) {
-				gas_processor_state st;
-				st.b0 = cf[k][0];
-				st.b1 = cf[k][1];
-				st.b2 = cf[k][2];
-				st.a1 = cf[k][3];
-				st.a2 = cf[k][4];
-				st.ha1 = h[k].ha1;
-				st.ha2 = h[k].ha2;
-				st.hb1 = h[k].hb1;
-				st.hb2 = h[k].hb2;
-				ps[k] = st;
-			}
-		}
-		if (MODE == MODE_E) {
-			for (int e = 0; e < r.n_fx; e++) {
-				for (int s = 0; s < 2; s++) {
-					for (int q = 0; q < GAS_MAX_FILTER_STAGES; q++) {
-						for (int k = 0; k < 4; k++) {
-							fxs[((e * 2 + s) * GAS_MAX_FILTER_STAGES + q) * 4 + k] = fxh[e][s][q][k];
-						}
-					}
-				}
-			}
-		}
-		if (want_peak && peaks) {
-			peaks[j] = make_float2(pk_l, pk_r);
-		}
-	}
+};
+template <int W, int LEVELS, int N>
+struct ReduceHi<W, LEVELS, LEVELS, N> {
+	static __device__ __forceinline__ void run(float (&)[N], int, int &, bool &) {}
+};
+template <int N, int LEVELS>
+__device__ __forceinline__ void reduce_hi(float (&v)[N], int lane, int &base, bool &owner) {
+	base = 0;
+	owner = true;
+	ReduceHi<N, 0, LEVELS, N>::run(v, lane, base, owner);
 }
 
-// Mode B with the attenuation filter on: 2C biquads per voice.  Here a lane is one (voice, pair, side) stream — 8
+// Mode B (with or without the attenuation filter: up to 2C biquads per voice).  A lane is one (voice, pair, side) stream — 8
 // lanes per voice, 4 voices per warp — so a voice's biquads run side by side instead of one after the other in a
 // single lane, and 8x more warps hide the recurrence latency.  Frames are fetched 8 at a time (one float2 per lane
 // of the voice = 64 contiguous bytes) and handed round with shuffles; t = i / F is computed once per frame by the
@@ -382,9 +143,10 @@ __device__ void voice_pass_b(const DevTables &t, const ChunkArgs &a, int send0, 
 			nn[s] = ok ? snd->vn[send0 + s][c][side] : 0.f;
 		}
 	}
+	const bool filt = (a.cls_flags & CLS_FILT) != 0;
 	gas_processor_state *ps = t.vs_proc + (size_t)voice * 8 + l; // processor index pair * 2 + (left ? 0 : 1)
 	gas_processor_state st{};
-	if (active) {
+	if (active && filt) {
 		st = *ps;
 	}
 	const bool clear = (flags >> (8 + c)) & 1u; // is_just_started => clear history (:583-586)
@@ -400,42 +162,54 @@ __device__ void voice_pass_b(const DevTables &t, const ChunkArgs &a, int send0, 
 	}
 	float pk = 0.f;
 	const float2 *row = src_row >= 0 ? reinterpret_cast<const float2 *>(src + (size_t)src_row * src_stride) : nullptr;
+	float2 nx = (row && l < F) ? __ldg(row + l) : make_float2(0.f, 0.f); // next trip's frames, fetched a trip ahead
 	for (int i0 = 0; i0 < F; i0 += 8) {
 		const int mi = i0 + l;
-		const float2 mx = (row && mi < F) ? __ldg(row + mi) : make_float2(0.f, 0.f);
+		const float2 mx = nx;
+		nx = (row && mi + 8 < F) ? __ldg(row + mi + 8) : make_float2(0.f, 0.f);
 		const float mt = (float)mi / (float)F; // :591
+		float v[8 * NS]; // [frame][send]
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
-			const int i = i0 + k;
-			if (i >= F) {
-				break;
-			}
 			const float xl = __shfl_sync(kFull, mx.x, gbase + k);
 			const float xr = __shfl_sync(kFull, mx.y, gbase + k);
 			const float tt = __shfl_sync(kFull, mt, gbase + k);
 			const float omt = 1.0f - tt;
 			const float vol = m_new * tt + omt * m_prev; // :592
 			float y = vol * (side ? xr : xl);             // :593
-			y = biquad_step(h, y, cf[0], cf[1], cf[2], cf[3], cf[4]); // :594-595
+			if (i0 + k < F) {
+				if (filt) {
+					y = biquad_step(h, y, cf[0], cf[1], cf[2], cf[3], cf[4]); // :594-595
 #pragma unroll
-			for (int q = 0; q < 5; q++) { // process_one_interp: coeffs += incr
-				cf[q] += inc[q];
+					for (int q = 0; q < 5; q++) { // process_one_interp: coeffs += incr
+						cf[q] += inc[q];
+					}
+				}
+				pk = fmaxf(pk, fabsf(y));
+			} else {
+				y = 0.f;
 			}
-			pk = fmaxf(pk, fabsf(y));
 #pragma unroll
 			for (int s = 0; s < NS; s++) {
-				float v = (nn[s] * tt + omt * np[s]) * y; // AudioServer ramp of this send (upstream _mix_step_for_channel)
-				v += __shfl_xor_sync(kFull, v, 8);
-				v += __shfl_xor_sync(kFull, v, 16);
-				if (g == 0 && c < C && (send0 + s) < a.n_send) {
-					const size_t o = ((size_t)(bus_of[s] * C + c) * F + i) * 2 + side;
-					acc_add(bus, tile, o, v);
+				v[k * NS + s] = (nn[s] * tt + omt * np[s]) * y; // AudioServer ramp of this send (upstream _mix_step_for_channel)
+			}
+		}
+		// the 4 voices of the warp: one transposing reduction over lane bits 4 and 3 for the whole trip
+		int base;
+		bool owner;
+		reduce_hi<8 * NS, 2>(v, lane, base, owner);
+		if (owner && c < C) {
+#pragma unroll
+			for (int r = 0; r < (8 * NS) / 4; r++) {
+				const int idx = base + r, k = idx / NS, s = idx % NS;
+				if ((send0 + s) < a.n_send && i0 + k < F) {
+					acc_add(bus, tile, ((size_t)(bus_of[s] * C + c) * F + i0 + k) * 2 + side, v[r]);
 				}
 			}
 		}
 	}
 	if (last_pass) {
-		if (active) {
+		if (active && filt) {
 			st.b0 = cf[0];
 			st.b1 = cf[1];
 			st.b2 = cf[2];
@@ -474,20 +248,201 @@ __device__ void voice_chunk_b(const DevTables &t, const ChunkArgs &a, const gas_
 	}
 }
 
+template <int N>
+struct Pow2Ceil8 {
+	static constexpr int value = N <= 1 ? 1 : (N <= 2 ? 2 : (N <= 4 ? 4 : 8));
+};
+
+// Mode A (one high-shelf pair per voice, in front of every ramp) and AudioSpatializerEffect chains (cascaded
+// constant-coefficient biquads): one lane per (voice, side), 16 voices per warp.  Each lane produces one processed
+// stream y and NS * C weighted contributions per frame; the contributions of 8 frames are batched and the 16 voices
+// summed with one transposing shuffle reduction over lane bits 4..1 (bit 0 is the side and is not reduced).
+template <int MODE, int C, int NS>
+__device__ void voice_pass_s(const DevTables &t, const ChunkArgs &a, int send0, bool emit, bool last_pass, const gas_frame *__restrict__ src,
+		int src_stride, int F, float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
+	const int lane = threadIdx.x & 31;
+	const int side = lane & 1;
+	const int pos = a.chunk * 16 + (lane >> 1);
+	const bool active = pos < a.count;
+	const int j = active ? a.list[pos].x : -1;
+	const VoiceRec *rec = &a.rec[active ? j : 0];
+	const int voice = active ? rec->voice : 0;
+	const int src_row = active ? rec->src_row : -1;
+	const uint32_t flags = active ? rec->flags : 0u;
+	const bool filt = MODE == MODE_A && (a.cls_flags & CLS_FILT) != 0;
+	const int n_fx = (MODE == MODE_E && active) ? rec->n_fx : 0;
+
+	float np[NS][C], nn[NS][C];
+	int bus_of[NS];
+	{
+		const InstSends *snd = &a.sends[active ? j : 0];
+		uint32_t m = a.mask;
+		for (int s = 0; s < send0; s++) {
+			m &= m - 1;
+		}
+#pragma unroll
+		for (int s = 0; s < NS; s++) {
+			bus_of[s] = m ? (__ffs(m) - 1) : 0;
+			m &= m - 1;
+			const bool ok = active && emit && (send0 + s) < a.n_send;
+#pragma unroll
+			for (int c = 0; c < C; c++) {
+				np[s][c] = ok ? snd->vp[send0 + s][c][side] : 0.f;
+				nn[s][c] = ok ? snd->vn[send0 + s][c][side] : 0.f;
+			}
+		}
+	}
+	// MODE_A: the interpolated high-shelf processor of this side (index 0 left, 1 right, :524-529)
+	gas_processor_state *ps = t.vs_proc + (size_t)voice * 8 + side;
+	gas_processor_state st{};
+	if (active && filt) {
+		st = *ps;
+	}
+	const bool clear = (flags >> 8) & 1u; // is_just_started => clear history (:518-521)
+	Biquad h;
+	h.ha1 = clear ? 0.f : st.ha1;
+	h.ha2 = clear ? 0.f : st.ha2;
+	h.hb1 = clear ? 0.f : st.hb1;
+	h.hb2 = clear ? 0.f : st.hb2;
+	float cf[5] = { st.b0, st.b1, st.b2, st.a1, st.a2 }, inc[5];
+#pragma unroll
+	for (int q = 0; q < 5; q++) {
+		inc[q] = ((active ? rec->target[q] : 0.f) - cf[q]) / (float)F; // update_coeffs(F)
+	}
+	// MODE_E: histories of this side's cascaded stages, [effect][stage]{ha1,ha2,hb1,hb2} (dynamic shape: local memory)
+	float fxh[GAS_MAX_EFFECTS][GAS_MAX_FILTER_STAGES][4];
+	float *fxs = t.vs_fx + (size_t)voice * (GAS_MAX_EFFECTS * 2 * GAS_MAX_FILTER_STAGES * 4);
+	if (MODE == MODE_E) {
+		for (int e = 0; e < GAS_MAX_EFFECTS; e++) {
+			for (int q = 0; q < GAS_MAX_FILTER_STAGES; q++) {
+				for (int k = 0; k < 4; k++) {
+					fxh[e][q][k] = e < n_fx ? fxs[((e * 2 + side) * GAS_MAX_FILTER_STAGES + q) * 4 + k] : 0.f;
+				}
+			}
+		}
+	}
+	float pk = 0.f;
+	const float4 *row = src_row >= 0 ? reinterpret_cast<const float4 *>(src + (size_t)src_row * src_stride) : nullptr;
+	constexpr int NVRAW = NS * C;
+	constexpr int NV = Pow2Ceil8<NVRAW>::value;
+	float4 xb[4], xn[4]; // 8 frames = 64 bytes of this voice's row (both lanes of the voice fetch the same bytes); xn: next trip
+#pragma unroll
+	for (int u = 0; u < 4; u++) {
+		xn[u] = (row && 2 * u < F) ? __ldg(row + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+	for (int i0 = 0; i0 < F; i0 += 8) {
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			xb[u] = xn[u];
+			xn[u] = (row && (i0 + 8 + 2 * u) < F) ? __ldg(row + ((i0 + 8) >> 1) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+		const float mt = (float)(i0 + (lane & 7)) / (float)F; // t of frame i0 + (lane & 7), handed round below (:591)
+		float v[8 * NV]; // [frame][send * C + pair]
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			const float4 x4 = xb[k >> 1];
+			float y = (k & 1) ? (side ? x4.w : x4.z) : (side ? x4.y : x4.x);
+			const float tt = __shfl_sync(kFull, mt, (lane & 24) + k);
+			const float omt = 1.0f - tt;
+			if (i0 + k < F) {
+				if (MODE == MODE_A) {
+					if (filt) {
+						y = biquad_step(h, y, cf[0], cf[1], cf[2], cf[3], cf[4]);
+#pragma unroll
+						for (int q = 0; q < 5; q++) {
+							cf[q] += inc[q];
+						}
+					}
+				} else { // cascaded constant-coefficient biquads per effect (upstream AudioEffectFilter::process)
+					for (int e = 0; e < n_fx; e++) {
+						const float b0 = rec->fx_coef[e][0], b1 = rec->fx_coef[e][1], b2 = rec->fx_coef[e][2], a1 = rec->fx_coef[e][3], a2 = rec->fx_coef[e][4];
+						const int stages = rec->fx_stages[e];
+						for (int q = 0; q < stages; q++) {
+							float *hh = fxh[e][q];
+							const float pre = y;
+							y = y * b0 + hh[2] * b1 + hh[3] * b2 + hh[0] * a1 + hh[1] * a2;
+							hh[1] = hh[0];
+							hh[3] = hh[2];
+							hh[2] = pre;
+							hh[0] = y;
+						}
+					}
+				}
+				pk = fmaxf(pk, fabsf(y)); // block peak (audio_spatializer.cpp:436-443, :453-460)
+			} else {
+				y = 0.f;
+			}
+#pragma unroll
+			for (int q = 0; q < NV; q++) {
+				v[k * NV + q] = 0.f;
+			}
+#pragma unroll
+			for (int s2 = 0; s2 < NS; s2++) {
+#pragma unroll
+				for (int c = 0; c < C; c++) {
+					v[k * NV + s2 * C + c] = (nn[s2][c] * tt + omt * np[s2][c]) * y; // AudioServer ramp per send / pair
+				}
+			}
+		}
+		if (emit) {
+			int base;
+			bool owner;
+			reduce_hi<8 * NV, 4>(v, lane, base, owner);
+			constexpr int kLeft = (8 * NV) / 16 > 0 ? (8 * NV) / 16 : 1;
+			if (owner) {
+#pragma unroll
+				for (int r = 0; r < kLeft; r++) {
+					const int idx = base + r, k = idx / NV, q = idx % NV;
+					const int s2 = q / C, c = q % C;
+					if (q < NVRAW && (send0 + s2) < a.n_send && i0 + k < F) {
+						acc_add(bus, tile, ((size_t)(bus_of[s2] * C + c) * F + i0 + k) * 2 + side, v[r]);
+					}
+				}
+			}
+		}
+	}
+	if (last_pass && active) {
+		if (MODE == MODE_A && filt) {
+			st.b0 = cf[0];
+			st.b1 = cf[1];
+			st.b2 = cf[2];
+			st.a1 = cf[3];
+			st.a2 = cf[4];
+			st.ha1 = h.ha1;
+			st.ha2 = h.ha2;
+			st.hb1 = h.hb1;
+			st.hb2 = h.hb2;
+			*ps = st;
+		}
+		if (MODE == MODE_E) {
+			for (int e = 0; e < n_fx; e++) {
+				for (int q = 0; q < GAS_MAX_FILTER_STAGES; q++) {
+					for (int k = 0; k < 4; k++) {
+						fxs[((e * 2 + side) * GAS_MAX_FILTER_STAGES + q) * 4 + k] = fxh[e][q][k];
+					}
+				}
+			}
+		}
+		if ((flags & GAS_VOICE_WANT_PEAK) && peaks) {
+			reinterpret_cast<float *>(peaks + j)[side] = pk;
+		}
+	}
+}
+
 template <int MODE, int C>
-__device__ void voice_chunk(const DevTables &t, const GlobalCfg &g, const ChunkArgs &a, const gas_frame *__restrict__ src, int src_stride,
-		int F, float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
+__device__ void voice_chunk_s(const DevTables &t, const ChunkArgs &a, const gas_frame *__restrict__ src, int src_stride, int F,
+		float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
 	const int n = a.n_send;
 	if (n == 0) {
-		voice_pass<MODE, C, 1>(t, g, a, 0, false, true, src, src_stride, F, bus, tile, peaks);
+		voice_pass_s<MODE, C, 1>(t, a, 0, false, true, src, src_stride, F, bus, tile, peaks);
 		return;
 	}
 	for (int s0 = 0; s0 < n; s0 += 2) {
 		const bool last = s0 + 2 >= n;
 		if (n - s0 >= 2) {
-			voice_pass<MODE, C, 2>(t, g, a, s0, true, last, src, src_stride, F, bus, tile, peaks);
+			voice_pass_s<MODE, C, 2>(t, a, s0, true, last, src, src_stride, F, bus, tile, peaks);
 		} else {
-			voice_pass<MODE, C, 1>(t, g, a, s0, true, last, src, src_stride, F, bus, tile, peaks);
+			voice_pass_s<MODE, C, 1>(t, a, s0, true, last, src, src_stride, F, bus, tile, peaks);
 		}
 	}
 }
@@ -596,8 +551,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	{
 		int units = 0;
 		for (int c = 0; c < s_ncls; c++) {
-			const bool by_stream = s_cls[c].mode == MODE_B && (s_cls[c].flags & CLS_FILT);
-			units += by_stream ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 31) / 32;
+			const bool per_pair = s_cls[c].mode == MODE_B;
+			units += per_pair ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 15) / 16;
 		}
 		cta_has_work = units > (int)blockIdx.x; // units are dealt round-robin to CTAs, then to the warps of a CTA
 	}
@@ -612,15 +567,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	// dealt round-robin to the CTAs, then to the warps of a CTA: this warp owns units b + grid * (w + 8 r), r = 0, 1, ...
 	int total_units = 0;
 	for (int c = 0; c < s_ncls; c++) {
-		const bool by_stream = s_cls[c].mode == MODE_B && (s_cls[c].flags & CLS_FILT);
-		total_units += by_stream ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 31) / 32;
+		total_units += s_cls[c].mode == MODE_B ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 15) / 16;
 	}
 	for (int unit = (int)blockIdx.x + (int)gridDim.x * my_warp; unit < total_units; unit += (int)gridDim.x * kWarpsPerCta) {
 		int c = 0, k = unit;
-		bool by_stream = false;
-		for (; c < s_ncls; c++) { // class and chunk of the unit
-			by_stream = s_cls[c].mode == MODE_B && (s_cls[c].flags & CLS_FILT); // lane = (voice, pair, side): 4 voices per warp
-			const int chunks = by_stream ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 31) / 32;
+		for (; c < s_ncls; c++) { // class and chunk of the unit: Mode B 4 voices per warp, Mode A / effect chains 16
+			const int chunks = s_cls[c].mode == MODE_B ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 15) / 16;
 			if (k < chunks) {
 				break;
 			}
@@ -638,17 +590,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 		a.n_send = ci.n_send;
 		switch (ci.mode) {
 			case MODE_A:
-				voice_chunk<MODE_A, C>(t, g, a, src, src_stride, F, bus, tile, peaks);
+				voice_chunk_s<MODE_A, C>(t, a, src, src_stride, F, bus, tile, peaks);
 				break;
 			case MODE_B:
-				if (by_stream) {
-					voice_chunk_b<C>(t, a, src, src_stride, F, bus, tile, peaks);
-				} else {
-					voice_chunk<MODE_B, C>(t, g, a, src, src_stride, F, bus, tile, peaks);
-				}
+				voice_chunk_b<C>(t, a, src, src_stride, F, bus, tile, peaks);
 				break;
 			default:
-				voice_chunk<MODE_E, C>(t, g, a, src, src_stride, F, bus, tile, peaks);
+				voice_chunk_s<MODE_E, C>(t, a, src, src_stride, F, bus, tile, peaks);
 				break;
 		}
 	}

@@ -81,18 +81,25 @@ def run(name, V, F, speaker_mode, num_buses, sc_kw, steps=200, sets=4):
 
 
 def main():
-    run("configs[1] 3D 1024 voices 5.1 inverse-square + attenuation filter (Mode B)", 1024, 512, abi.SPEAKER_SURROUND_51, 2,
-        dict(spat=dict(mix_channel_mode=1, attenuation_model=abi.ATTENUATION_INVERSE_SQUARE_DISTANCE), area=dict(reverb_bus=1, amount=0.5),
-             area_fraction=0.25))
-    for stages in (1, 4):
-        run(f"configs[3] Effect 4096 voices stereo, {stages}-stage high-shelf chain, Master + reverb + area bus", 4096, 512,
-            abi.SPEAKER_MODE_STEREO, 3,
-            dict(effect_chain=[dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=4000.0, resonance=1.0, gain=0.3, stages=stages)], effect_gain_binding=0,
-                 area=dict(reverb_bus=2, amount=0.4, override_bus=True, bus=1), area_fraction=0.5))
-    run("headline workload with the attenuation filter ON (16384 voices 7.1, Mode B: 8 biquads per voice-frame)", 16384, 512,
-        abi.SPEAKER_SURROUND_71, 2, dict(spat=dict(mix_channel_mode=1), area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25), steps=50)
-    run("headline workload, Mode A with the attenuation filter ON (2 biquads per voice-frame)", 16384, 512,
-        abi.SPEAKER_SURROUND_71, 2, dict(spat=dict(mix_channel_mode=0), area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25), steps=50)
+    only = set(int(a) for a in sys.argv[1:])  # optional: indices of the configurations to run
+    cfgs = [
+        ("configs[1] 3D 1024 voices 5.1 inverse-square + attenuation filter (Mode B)", 1024, 512, abi.SPEAKER_SURROUND_51, 2,
+         dict(spat=dict(mix_channel_mode=1, attenuation_model=abi.ATTENUATION_INVERSE_SQUARE_DISTANCE), area=dict(reverb_bus=1, amount=0.5),
+              area_fraction=0.25), 200),
+        ("configs[3] Effect 4096 voices stereo, 1-stage high-shelf chain, Master + reverb + area bus", 4096, 512, abi.SPEAKER_MODE_STEREO, 3,
+         dict(effect_chain=[dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=4000.0, resonance=1.0, gain=0.3, stages=1)], effect_gain_binding=0,
+              area=dict(reverb_bus=2, amount=0.4, override_bus=True, bus=1), area_fraction=0.5), 200),
+        ("configs[3] Effect 4096 voices stereo, 4-stage high-shelf chain, Master + reverb + area bus", 4096, 512, abi.SPEAKER_MODE_STEREO, 3,
+         dict(effect_chain=[dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=4000.0, resonance=1.0, gain=0.3, stages=4)], effect_gain_binding=0,
+              area=dict(reverb_bus=2, amount=0.4, override_bus=True, bus=1), area_fraction=0.5), 200),
+        ("headline workload with the attenuation filter ON (16384 voices 7.1, Mode B: 8 biquads per voice-frame)", 16384, 512,
+         abi.SPEAKER_SURROUND_71, 2, dict(spat=dict(mix_channel_mode=1), area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25), 50),
+        ("headline workload, Mode A with the attenuation filter ON (2 biquads per voice-frame)", 16384, 512,
+         abi.SPEAKER_SURROUND_71, 2, dict(spat=dict(mix_channel_mode=0), area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25), 50),
+    ]
+    for k, (name, V, F, mode, buses, kw, steps) in enumerate(cfgs):
+        if not only or k in only:
+            run(name, V, F, mode, buses, kw, steps=steps)
 
 
 if __name__ == "__main__":
