@@ -268,7 +268,8 @@ class DeviceWorkload:
             # reduce is ended here, after this block's mix has been enqueued, so the other ranks' skew hides behind it.
             m.reduce_bus_end_device(self.d_bus[(k + 1) % 2].data_ptr(), w["frames"])
             m.reduce_bus_begin_device(self.d_bus[k % 2].data_ptr(), w["frames"])
-        m.gain_compute_device(w["voices"], self.d_emitters[(s + 1) % N_SETS].data_ptr())
+        if not os.environ.get("GAS_BENCH_NOGAIN"):  # experiments only: leave K1 out of the step
+            m.gain_compute_device(w["voices"], self.d_emitters[(s + 1) % N_SETS].data_ptr())
         return self.d_bus[k % 2]
 
     def capture_steps(self):
