@@ -285,28 +285,54 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 			cc.tl[2] = gtime();
 		}
 		if (mine && !(cf.debug & 2)) {
-#pragma unroll 2
-			for (int v = cc.group; v < nv; v += cf.groups) {
+			// the loads of several voices are issued before their FMAs (4 voices for the small classes, 2 for the
+			// large ones: the register budget): two consumer warps per scheduler cannot hide the shared-memory latency
+			// of one voice at a time
+			constexpr int U = NP <= 10 ? 4 : 2;
+			int v = cc.group;
+			for (; v + (U - 1) * cf.groups < nv; v += U * cf.groups) {
+				float4 x[U];
+				float4 w[U][(NP + 1) / 2];
+#pragma unroll
+				for (int u = 0; u < U; u++) {
+					const int vv = v + u * cf.groups;
+					x[u] = *reinterpret_cast<const float4 *>(sx + (size_t)vv * row_bytes + cc.slot * 16);
+					const unsigned char *wv = sw + vv * (NP * 8);
+#pragma unroll
+					for (int p = 0; p < NP; p += 2) {
+						if (NP % 2 == 0) {
+							w[u][p / 2] = *reinterpret_cast<const float4 *>(wv + p * 8);
+						} else {
+							const float2 a = *reinterpret_cast<const float2 *>(wv + p * 8);
+							const float2 b = p + 1 < NP ? *reinterpret_cast<const float2 *>(wv + p * 8 + 8) : make_float2(0.f, 0.f);
+							w[u][p / 2] = make_float4(a.x, a.y, b.x, b.y);
+						}
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < U; u++) {
+					const float2 x0 = make_float2(x[u].x, x[u].y), x1 = make_float2(x[u].z, x[u].w);
+#pragma unroll
+					for (int p = 0; p < NP; p += 2) {
+						const float2 wa = make_float2(w[u][p / 2].x, w[u][p / 2].y), wb = make_float2(w[u][p / 2].z, w[u][p / 2].w);
+						fma2(acc[p][0], wa, x0);
+						fma2(acc[p][1], wa, x1);
+						if (p + 1 < NP) {
+							fma2(acc[p + 1][0], wb, x0);
+							fma2(acc[p + 1][1], wb, x1);
+						}
+					}
+				}
+			}
+			for (; v < nv; v += cf.groups) { // remainder
 				const float4 x = *reinterpret_cast<const float4 *>(sx + (size_t)v * row_bytes + cc.slot * 16);
 				const float2 x0 = make_float2(x.x, x.y), x1 = make_float2(x.z, x.w);
 				const unsigned char *wv = sw + v * (NP * 8);
-				if (NP % 2 == 0) { // per-voice weight block is a multiple of 16 bytes: 128-bit broadcast loads
 #pragma unroll
-					for (int p = 0; p < NP; p += 2) {
-						const float4 w = *reinterpret_cast<const float4 *>(wv + p * 8);
-						const float2 wa = make_float2(w.x, w.y), wb = make_float2(w.z, w.w);
-						fma2(acc[p][0], wa, x0);
-						fma2(acc[p][1], wa, x1);
-						fma2(acc[p + 1][0], wb, x0);
-						fma2(acc[p + 1][1], wb, x1);
-					}
-				} else {
-#pragma unroll
-					for (int p = 0; p < NP; p++) {
-						const float2 wa = *reinterpret_cast<const float2 *>(wv + p * 8);
-						fma2(acc[p][0], wa, x0);
-						fma2(acc[p][1], wa, x1);
-					}
+				for (int p = 0; p < NP; p++) {
+					const float2 wa = *reinterpret_cast<const float2 *>(wv + p * 8);
+					fma2(acc[p][0], wa, x0);
+					fma2(acc[p][1], wa, x1);
 				}
 			}
 		}
@@ -651,7 +677,7 @@ static StreamCfg make_cfg(int frames, int src_stride, int smem_limit) {
 	cf.stages = stages > kMaxStages ? kMaxStages : stages;
 	// tuning / experiment knobs (environment, read per launch: they never change results, only schedules)
 	cf.stages = env_int("GAS_K2_STAGES", cf.stages, 2, cf.stages);
-	cf.fixed_cost = env_int("GAS_K2_FIXED_COST", 8, 0, 1024);
+	cf.fixed_cost = env_int("GAS_K2_FIXED_COST", 40, 0, 1024);
 	cf.flush_mode = env_int("GAS_K2_FLUSH", 0, 0, 1);
 	cf.debug = env_int("GAS_K2_DEBUG", 0, 0, 15);
 	return cf;
