@@ -142,7 +142,11 @@ __device__ void output_vol_surround(unsigned gm, int gbase, int l, const GlobalC
 	if (l < count) {
 		const V3 dl{ g.spk_dir[l][0], g.spk_dir[l][1], g.spk_dir[l][2] };
 		const float eff = g.spk_eff[l]; // :911-915, precomputed per speaker mode
-		const float gain = (float)(0.5 * pow(1.0 + (double)dot3(dl, src), (double)tightness) / (double)eff); // :929-933
+		// :929-933.  pow(x, 1) and pow(x, 2) are exact in one rounding (x, x * x), which is what a correctly rounded
+		// pow returns: the default 3d_panning_strength / panning_strength (tightness 1) never pays for the general pow
+		const double base1 = 1.0 + (double)dot3(dl, src);
+		const double pw = tightness == 1.0f ? base1 : (tightness == 2.0f ? base1 * base1 : pow(base1, (double)tightness));
+		const float gain = (float)(0.5 * pw / (double)eff);
 		sq = gain * gain;
 	}
 	float sum = 0.f;
