@@ -387,8 +387,6 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 #undef ALLOC
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_mix, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_gain, cudaStreamNonBlocking) == cudaSuccess;
-	ok = ok && cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) == cudaSuccess;
-	ok = ok && cudaEventCreateWithFlags(&ctx->ev_aux_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_gain_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_prologue_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
@@ -418,9 +416,6 @@ void gas_destroy(gas_ctx *ctx) {
 	if (ctx->s_gain) {
 		cudaStreamSynchronize(ctx->s_gain);
 	}
-	if (ctx->s_aux) {
-		cudaStreamSynchronize(ctx->s_aux);
-	}
 	gas_comm_close(ctx);
 	void *ptrs[] = { ctx->t.spat, ctx->t.inst_spat, ctx->t.inst_params, ctx->t.inst_was_further, ctx->t.inst_active, ctx->t.inst_cur,
 		ctx->t.inst_prev, ctx->t.inst_mode, ctx->t.blk, ctx->t.inst_fx, ctx->plan.sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls_key, ctx->plan.cls_count,
@@ -444,12 +439,7 @@ void gas_destroy(gas_ctx *ctx) {
 	if (ctx->ev_join) {
 		cudaEventDestroy(ctx->ev_join);
 	}
-	if (ctx->ev_aux_done) {
-		cudaEventDestroy(ctx->ev_aux_done);
-	}
-	if (ctx->s_aux) {
-		cudaStreamDestroy(ctx->s_aux);
-	}
+
 	for (auto &g : ctx->graphs) {
 		if (g.exec) {
 			cudaGraphExecDestroy(g.exec);
@@ -804,6 +794,16 @@ int gas_mix_block(gas_ctx *ctx, int32_t n_voices, const gas_voice *voices, const
 		}
 	}
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	{
+		// more distinct routing classes than the plan has slots: the voices of the classes that did not fit were left
+		// out of this block — say so instead of returning a silently incomplete mix
+		int32_t overflow = 0;
+		GAS_CUDA(ctx, cudaMemcpy(&overflow, ctx->plan.overflow, sizeof(overflow), cudaMemcpyDeviceToHost));
+		if (overflow) {
+			cudaMemset(ctx->plan.overflow, 0, sizeof(overflow));
+			return gas_fail(ctx, GAS_ERR_STATE, "gas_mix_block: more than %d distinct routing classes in use; the block is incomplete", GAS_MAX_CLASSES);
+		}
+	}
 	return GAS_OK;
 }
 

@@ -152,8 +152,8 @@ struct gas_ctx {
 	int device = 0;
 	int num_sms = 0;
 	int l2_bytes = 0;
-	cudaStream_t s_mix = nullptr, s_gain = nullptr, s_aux = nullptr; // s_aux: the voice-parallel kernel beside the streaming one
-	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_aux_done = nullptr;
+	cudaStream_t s_mix = nullptr, s_gain = nullptr;
+	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr;
 	bool gain_pending = false, prologue_pending = false;
 	DevTables t{};
 	BlockPlan plan{};

@@ -1,0 +1,160 @@
+"""GPU tests of the rest of the C-ABI surface: CUDA-graph capture of the device-resident calls, per-kernel timing,
+voice-state export / import (checkpoint, re-sharding), run-time AudioServer globals, class-table overflow."""
+import numpy as np
+import pytest
+
+import scenarios as S
+
+pytestmark = pytest.mark.gpu
+abi, synth = S.abi, S.synth
+
+
+def _scene(m, V, F, mode, spat=None, area_fraction=0.5):
+    inst = np.arange(V, dtype=np.int32)
+    listeners = np.array([abi.identity_listener()], dtype=abi.listener)
+    areas = np.array([synth.reverb_area(reverb_bus=1, amount=0.5)], dtype=abi.area)
+    m.spatializer_set(0, abi.spatializer_defaults(**(spat or dict(mix_channel_mode=1))))
+    m.instance_init(inst, 0)
+    m.gain_compute(synth.make_emitters(V, block=0, dt=F / 48000.0, area_fraction=area_fraction), listeners, areas, want_params=False)
+    m.instance_start(inst)
+    m.voice_init(inst)
+    return listeners, areas
+
+
+def test_graph_replay_matches_eager_calls(gas):
+    """gas_capture_begin/end + gas_graph_launch of (mix block, gain for the next block) equals the same calls made eagerly."""
+    import torch
+    V, F, mode, blocks = 256, 256, abi.SPEAKER_SURROUND_51, 4
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, num_buses=2, speaker_mode=mode, mix_rate=48000.0)
+    dev = torch.device("cuda", 0)
+    voices = torch.from_numpy(synth.make_voices(V).view(np.uint8).copy()).to(dev)
+    src = [torch.from_numpy(synth.make_sources(V, F, block=b)).to(dev) for b in range(blocks)]
+    ems = [torch.from_numpy(synth.make_emitters(V, block=b + 1, dt=F / 48000.0, area_fraction=0.5).view(np.uint8).copy()).to(dev)
+           for b in range(blocks)]
+    outs = []
+    for use_graph in (False, True):
+        with gas.Mixer(**cfg) as m:
+            listeners, areas = _scene(m, V, F, mode, spat=dict(mix_channel_mode=1, attenuation_filter_db=-6.0))
+            m.listeners_set(listeners)
+            m.areas_set(areas)
+            bus = torch.zeros((2, mode + 1, F, 2), device=dev)
+            got = []
+            for b in range(blocks):
+                def step():
+                    m.mix_block_device(V, voices.data_ptr(), src[b].data_ptr(), V, F, F, bus.data_ptr())
+                    m.gain_compute_device(V, ems[b].data_ptr())
+                if use_graph:
+                    m.capture_begin()
+                    step()
+                    g = m.capture_end()
+                    launches0 = m.kernel_launches
+                    m.graph_launch(g)
+                    assert m.kernel_launches > launches0
+                    m.sync()
+                    m.graph_destroy(g)
+                else:
+                    step()
+                    m.sync()
+                got.append(bus.cpu().numpy().copy())
+            outs.append(got)
+    for e, g in zip(*outs):
+        assert e.any()
+        ok, worst, nbad = S.sample_close(g, e)
+        assert ok, f"graph replay differs from eager calls: {nbad} samples, worst {worst:.3e}"
+
+
+def test_profile_counts_every_kernel(gas):
+    V, F = 128, 256
+    with gas.Mixer(max_instances=V, max_voices=V, max_frames=F, speaker_mode=abi.SPEAKER_MODE_STEREO) as m:
+        _scene(m, V, F, abi.SPEAKER_MODE_STEREO)
+        src = synth.make_sources(V, F)
+        m.profile_enable(True)
+        for _ in range(3):
+            m.mix_block(synth.make_voices(V), src, F, want_peaks=False)
+        prof = m.profile_read()
+        m.profile_enable(False)
+    for kind in ("prologue", "mix_stream", "mix_voice"):
+        ms, n = prof[kind]
+        assert n == 3 and ms > 0.0, f"{kind}: {n} launches, {ms} ms"
+
+
+def test_voice_state_export_import_resumes_bit_identically(gas):
+    """Checkpoint / re-sharding: a second context that imports the voice state (and replays the parameters) continues
+    the filtered mix exactly where the first one stopped."""
+    V, F, mode = 64, 256, abi.SPEAKER_SURROUND_31
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, num_buses=2, speaker_mode=mode, mix_rate=48000.0)
+    voices = synth.make_voices(V)
+    ids = np.arange(V, dtype=np.int32)
+    listeners = np.array([abi.identity_listener()], dtype=abi.listener)
+    areas = np.array([synth.reverb_area(reverb_bus=1, amount=0.5)], dtype=abi.area)
+    ems = [synth.make_emitters(V, block=b, dt=F / 48000.0, area_fraction=0.5) for b in range(4)]
+    with gas.Mixer(**cfg) as a:
+        _scene(a, V, F, mode)  # default filter: active for every voice
+        for b in range(2):
+            a.gain_compute(ems[b], listeners, areas, want_params=False)
+            a.mix_block(voices, synth.make_sources(V, F, block=b), F, want_peaks=False)
+        state = a.voice_state_export(ids)
+        params = a.params_get(ids)
+        assert np.abs(state["filter_processors"]["ha1"]).max() > 0
+        with gas.Mixer(**cfg) as b_:
+            b_.spatializer_set(0, abi.spatializer_defaults(mix_channel_mode=1))
+            b_.instance_init(ids, 0)
+            b_.params_set(ids, params)
+            b_.instance_start(ids)
+            b_.voice_state_import(ids, state)
+            # one block on both to get b_'s bus details past their fade-in, compared from the next block on
+            outs = []
+            for m in (a, b_):
+                got = []
+                for blk in (2, 3):
+                    m.gain_compute(ems[blk], listeners, areas, want_params=False)
+                    got.append(m.mix_block(voices, synth.make_sources(V, F, block=blk), F, want_peaks=False)[0])
+                outs.append(got)
+            sa, sb = a.voice_state_export(ids), b_.voice_state_export(ids)
+    ok, worst, nbad = S.sample_close(outs[1][1], outs[0][1])
+    assert ok, f"resumed context diverges: {nbad} samples, worst {worst:.3e}"
+    np.testing.assert_allclose(sb["prev_mix_volumes"], sa["prev_mix_volumes"], rtol=0, atol=0)
+    ok, worst, nbad = S.sample_close(sb["filter_processors"]["ha1"], sa["filter_processors"]["ha1"], rel=1e-4)
+    assert ok, f"filter history diverges: worst {worst:.3e}"
+
+
+def test_speaker_mode_and_mix_rate_change_at_run_time(gas, orc):
+    """AudioServer::get_speaker_mode / get_mix_rate are read per tick (audio_spatializer_3d.cpp:59,113,506): changing them
+    between blocks behaves like a context created with the new values."""
+    V, F = 48, 256
+    sc = S.default_scenario(voices=V, frames=F, speaker_mode=abi.SPEAKER_SURROUND_71, spat=dict(mix_channel_mode=1), blocks=2, mix_rate=44100.0)
+    cfg = S.config_of(sc)
+    start = dict(cfg, speaker_mode=abi.SPEAKER_MODE_STEREO, mix_rate=48000.0)
+    with gas.Mixer(**start) as m, orc.OracleMixer(**cfg) as o:
+        m.set_speaker_mode(abi.SPEAKER_SURROUND_71)
+        m.set_mix_rate(44100.0)
+        assert m.channels == 4
+        got, want = S.run(m, sc, collect_state=False), S.run(o, sc, collect_state=False)
+    for bg, bw in zip(got["bus"], want["bus"]):
+        ok, worst, nbad = S.sample_close(bg, bw)
+        assert ok and np.array_equal(S.routing(bg), S.routing(bw)), f"{nbad} samples, worst {worst:.3e}"
+
+
+def test_class_table_overflow_is_reported(gas):
+    """More distinct routing classes than the plan has slots (128): gas_mix_block says so instead of returning a
+    silently incomplete mix.  16 buses give 120 two-bus combinations + 16 single-bus ones."""
+    B, F = 16, 64
+    combos = [(a, b) for a in range(B) for b in range(a + 1, B)] + [(a, a) for a in range(B)]
+    V = len(combos)
+    ids = np.arange(V, dtype=np.int32)
+    with gas.Mixer(max_instances=V, max_voices=V, max_frames=F, num_buses=B, speaker_mode=abi.SPEAKER_MODE_STEREO) as m:
+        m.spatializer_set(0, abi.spatializer_defaults(mix_channel_mode=1))
+        m.instance_init(ids, 0)
+        p = np.zeros(V, dtype=abi.params)
+        p["mix_volumes"][:, 0, :] = 0.5
+        p["pitch_scale"], p["update_parameters"] = 1.0, 1
+        for k, (a, b) in enumerate(combos):
+            p["n_bus"][k] = 1 if a == b else 2
+            p["bus"][k, 0], p["bus"][k, 1] = a, b
+            p["bus_volumes"][k, 0, 0, :] = 0.5
+            p["bus_volumes"][k, 1, 0, :] = 0.25
+        m.params_set(ids, p)
+        m.instance_start(ids)
+        m.voice_init(ids)
+        with pytest.raises(gas.GasError, match="routing classes"):
+            m.mix_block(synth.make_voices(V), synth.make_sources(V, F), F, want_peaks=False)
