@@ -232,6 +232,7 @@ class DeviceWorkload:
             else:
                 self.d_src.append((torch.rand((V, F, 2), generator=g, device=dev, dtype=torch.float32) - 0.5) * 0.5)
         self.d_bus = [torch.zeros((w["num_buses"], self.C, F, 2), device=dev, dtype=torch.float32) for _ in range(2)]
+        self.d_sum = [torch.zeros((w["num_buses"], self.C, F, 2), device=dev, dtype=torch.float32) for _ in range(2)]  # N > 1: reduced
         setup_mixer(self.mixer, w, abi, self.emitters_host, self.listeners, self.areas)
         self.mixer.listeners_set(self.listeners)
         self.mixer.areas_set(self.areas)
@@ -246,14 +247,14 @@ class DeviceWorkload:
         self.peer_reduce = True
 
     def reduce_prime(self):
-        """One outstanding begin, so that the first captured step finds a block to end."""
-        if getattr(self, "peer_reduce", False):
-            self.mixer.reduce_bus_begin_device(self.d_bus[1].data_ptr(), self.w["frames"])
+        pass  # the first exchange finds no outstanding block and only pushes
 
     def reduce_drain(self, k_last):
-        """Ends the reduce of the last block."""
+        """Pushes the last block and ends the two blocks still in flight."""
         if getattr(self, "peer_reduce", False):
-            self.mixer.reduce_bus_end_device(self.d_bus[k_last % 2].data_ptr(), self.w["frames"])
+            F = self.w["frames"]
+            self.mixer.reduce_bus_exchange_device(self.d_bus[k_last % 2].data_ptr(), self.d_sum[(k_last + 1) % 2].data_ptr(), F)
+            self.mixer.reduce_bus_end_device(self.d_sum[k_last % 2].data_ptr(), F)
 
     def step_device(self, k):
         """One step = mix of block k (audio side) with, beside it, the gain computation for block k+1 (physics
@@ -264,10 +265,10 @@ class DeviceWorkload:
         m.mix_block_device(w["voices"], self.d_voices.data_ptr(), self.d_src[s].data_ptr(), w["voices"], w["frames"], w["frames"],
                            self.d_bus[k % 2].data_ptr())
         if getattr(self, "peer_reduce", False):
-            # N > 1: sum of the per-GPU partial bus buffers over peer memory, inside the graph.  The previous block's
-            # reduce is ended here, after this block's mix has been enqueued, so the other ranks' skew hides behind it.
-            m.reduce_bus_end_device(self.d_bus[(k + 1) % 2].data_ptr(), w["frames"])
-            m.reduce_bus_begin_device(self.d_bus[k % 2].data_ptr(), w["frames"])
+            # N > 1: sum of the per-GPU partial bus buffers over peer memory, inside the graph, one block in flight: while
+            # block k mixes, the exchange stream pushes block k-1's partial sums to every rank and writes block k-2's
+            # complete sum — the whole exchange (NVLink round trip, system-scope fences, rank skew) is off the critical path.
+            m.reduce_bus_exchange_device(self.d_bus[(k + 1) % 2].data_ptr(), self.d_sum[k % 2].data_ptr(), w["frames"])
         if not os.environ.get("GAS_BENCH_NOGAIN"):  # experiments only: leave K1 out of the step
             m.gain_compute_device(w["voices"], self.d_emitters[(s + 1) % N_SETS].data_ptr())
         return self.d_bus[k % 2]
@@ -481,8 +482,9 @@ def gpu_arm(args):
                                  "k+1) beside it on the gain stream, one graph per step",
                        "pdl": os.environ.get("GAS_PDL", "0"),
                        "reduce": ("none (1 GPU)" if world == 1 else
-                                  "gas_reduce_bus_device inside the step graph: every rank adds its partial bus buffer into every rank's "
-                                  "exchange buffer with vector reductions on peer pointers (NVLink), one arrival-counter round per block"
+                                  "gas_reduce_bus_exchange_device inside the step graph, one block in flight on the exchange stream: every rank "
+                                  "adds its partial bus buffer into every rank's exchange buffer with vector reductions on peer pointers "
+                                  "(NVLink), one arrival-counter round per block"
                                   if peer else "torch.distributed all_reduce (NCCL) of the partial bus buffers, one call per step")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
             "parity": parity,

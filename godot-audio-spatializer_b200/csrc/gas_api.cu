@@ -195,6 +195,10 @@ int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_fr
 	if (ctx->gain_pending) {
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
 	}
+	if (ctx->comm_pending && !ctx->capturing) { // an exchange on the exchange stream may still read / write bus buffers
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_comm_done, 0));
+		ctx->comm_pending = false;
+	}
 	gas_ctx::ProfPair *pp = prof_open(ctx, GAS_KERNEL_PROLOGUE);
 	if (!(ctx->skip & 1)) {
 		GAS_CUDA(ctx, launch_prologue(ctx, n_voices, d_voices, src_rows, frames, d_bus, d_peaks, ctx->s_mix));
@@ -215,6 +219,10 @@ int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_fr
 			GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_mix));
 		}
 		prof_close(ctx, pp);
+	}
+	if (!ctx->capturing) {
+		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_mix_done, ctx->s_mix));
+		ctx->mix_pending = true;
 	}
 	return GAS_OK;
 }
@@ -387,6 +395,10 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 #undef ALLOC
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_mix, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_gain, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&ctx->s_comm, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_mix_done, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_comm_done, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_gain_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_prologue_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
@@ -416,6 +428,9 @@ void gas_destroy(gas_ctx *ctx) {
 	if (ctx->s_gain) {
 		cudaStreamSynchronize(ctx->s_gain);
 	}
+	if (ctx->s_comm) {
+		cudaStreamSynchronize(ctx->s_comm);
+	}
 	gas_comm_close(ctx);
 	void *ptrs[] = { ctx->t.spat, ctx->t.inst_spat, ctx->t.inst_params, ctx->t.inst_was_further, ctx->t.inst_active, ctx->t.inst_cur,
 		ctx->t.inst_prev, ctx->t.inst_mode, ctx->t.blk, ctx->t.inst_fx, ctx->plan.sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls_key, ctx->plan.cls_count,
@@ -438,6 +453,14 @@ void gas_destroy(gas_ctx *ctx) {
 	}
 	if (ctx->ev_join) {
 		cudaEventDestroy(ctx->ev_join);
+	}
+	for (cudaEvent_t e : { ctx->ev_mix_done, ctx->ev_comm_done, ctx->ev_join2 }) {
+		if (e) {
+			cudaEventDestroy(e);
+		}
+	}
+	if (ctx->s_comm) {
+		cudaStreamDestroy(ctx->s_comm);
 	}
 
 	for (auto &g : ctx->graphs) {
@@ -828,6 +851,7 @@ int gas_sync(gas_ctx *ctx) {
 	}
 	GAS_CUDA(ctx, cudaSetDevice(ctx->device));
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_gain));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_comm));
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
 	return GAS_OK;
 }
@@ -872,12 +896,14 @@ int gas_capture_begin(gas_ctx *ctx) {
 		return gas_fail(ctx, GAS_ERR_STATE, "gas_capture_begin: already capturing");
 	}
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_gain));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_comm));
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
-	ctx->gain_pending = ctx->prologue_pending = false;
+	ctx->gain_pending = ctx->prologue_pending = ctx->mix_pending = ctx->comm_pending = false;
 	GAS_CUDA(ctx, cudaStreamBeginCapture(ctx->s_mix, cudaStreamCaptureModeThreadLocal));
 	// fork: the gain stream joins the capture
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->s_mix));
 	GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_gain, ctx->ev_fork, 0));
+	GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comm, ctx->ev_fork, 0));
 	ctx->capturing = true;
 	ctx->capture_profiled = false;
 	for (int k = 0; k < GAS_KERNEL_KINDS; k++) {
@@ -897,6 +923,12 @@ int gas_capture_end(gas_ctx *ctx, int32_t *out_graph) {
 	cudaError_t e = cudaEventRecord(ctx->ev_join, ctx->s_gain); // join the gain stream back
 	if (e == cudaSuccess) {
 		e = cudaStreamWaitEvent(ctx->s_mix, ctx->ev_join, 0);
+	}
+	if (e == cudaSuccess) {
+		e = cudaEventRecord(ctx->ev_join2, ctx->s_comm); // and the exchange stream
+	}
+	if (e == cudaSuccess) {
+		e = cudaStreamWaitEvent(ctx->s_mix, ctx->ev_join2, 0);
 	}
 	cudaError_t e2 = cudaStreamEndCapture(ctx->s_mix, &graph);
 	const uint64_t kernels = ctx->launches - ctx->capture_launches0;
@@ -942,6 +974,8 @@ int gas_graph_launch(gas_ctx *ctx, int32_t graph) {
 	}
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix)); // later gain-side work waits for the whole graph
 	ctx->prologue_pending = true;
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_mix_done, ctx->s_mix)); // ... and so does a later exchange
+	ctx->mix_pending = true;
 	return GAS_OK;
 }
 
@@ -1050,6 +1084,10 @@ static int reduce_half(gas_ctx *ctx, gas_frame *d_bus, int32_t frames, bool begi
 	if (!ctx->d_exchange || !ctx->peer_exchange[ctx->comm_ranks - 1]) {
 		return gas_fail(ctx, GAS_ERR_STATE, "%s: gas_comm_open has not been called", who);
 	}
+	if (ctx->comm_pending && !ctx->capturing) {
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_comm_done, 0));
+		ctx->comm_pending = false;
+	}
 	if (begin) {
 		GAS_CUDA(ctx, launch_comm_push(ctx, d_bus, frames, ctx->s_mix));
 	}
@@ -1070,6 +1108,25 @@ int gas_reduce_bus_begin_device(gas_ctx *ctx, const gas_frame *d_bus, int32_t fr
 int gas_reduce_bus_end_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames) {
 	ENTER(ctx);
 	return reduce_half(ctx, d_bus, frames, false, true, "gas_reduce_bus_end_device");
+}
+
+int gas_reduce_bus_exchange_device(gas_ctx *ctx, const gas_frame *d_partial, gas_frame *d_prev_sum, int32_t frames) {
+	ENTER(ctx);
+	if (!d_partial || frames < 2 || (frames & 1) || frames > ctx->cfg.max_frames || ((uintptr_t)d_partial & 15u) || ((uintptr_t)d_prev_sum & 15u)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_reduce_bus_exchange_device: bad buffer or frame count");
+	}
+	if (ctx->comm_ranks <= 1) {
+		return gas_fail(ctx, GAS_ERR_STATE, "gas_reduce_bus_exchange_device: needs an opened exchange of at least 2 ranks");
+	}
+	if (!ctx->capturing && ctx->mix_pending) { // the partial sums must be complete
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comm, ctx->ev_mix_done, 0));
+	}
+	GAS_CUDA(ctx, launch_comm_exchange(ctx, d_partial, d_prev_sum, frames, ctx->s_comm));
+	if (!ctx->capturing) {
+		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done, ctx->s_comm));
+		ctx->comm_pending = true;
+	}
+	return GAS_OK;
 }
 
 int gas_comm_close(gas_ctx *ctx) {

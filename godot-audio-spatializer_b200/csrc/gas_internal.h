@@ -152,8 +152,9 @@ struct gas_ctx {
 	int device = 0;
 	int num_sms = 0;
 	int l2_bytes = 0;
-	cudaStream_t s_mix = nullptr, s_gain = nullptr;
-	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr;
+	cudaStream_t s_mix = nullptr, s_gain = nullptr, s_comm = nullptr; // s_comm: the multi-GPU exchange, beside the next block's mix
+	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_mix_done = nullptr, ev_comm_done = nullptr, ev_join2 = nullptr;
+	bool mix_pending = false, comm_pending = false;
 	bool gain_pending = false, prologue_pending = false;
 	DevTables t{};
 	BlockPlan plan{};
@@ -267,6 +268,7 @@ cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_strid
 // gas_comm.cu
 cudaError_t launch_comm_push(gas_ctx *ctx, const gas_frame *d_bus, int frames, cudaStream_t st);
 cudaError_t launch_comm_finish(gas_ctx *ctx, gas_frame *d_bus, int frames, cudaStream_t st);
+cudaError_t launch_comm_exchange(gas_ctx *ctx, const gas_frame *d_partial, gas_frame *d_prev_sum, int frames, cudaStream_t st);
 // gas_state.cu
 cudaError_t launch_instance_init(gas_ctx *ctx, int n, const int32_t *d_ids, const int32_t *d_spat, cudaStream_t st);
 cudaError_t launch_instance_stop(gas_ctx *ctx, int n, const int32_t *d_ids, cudaStream_t st);

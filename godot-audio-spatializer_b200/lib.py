@@ -57,6 +57,7 @@ PROTOTYPES = {
     "gas_reduce_bus_device": (C.c_int, [_vp, _vp, _i32]),
     "gas_reduce_bus_begin_device": (C.c_int, [_vp, _vp, _i32]),
     "gas_reduce_bus_end_device": (C.c_int, [_vp, _vp, _i32]),
+    "gas_reduce_bus_exchange_device": (C.c_int, [_vp, _vp, _vp, _i32]),
     "gas_comm_close": (C.c_int, [_vp]),
 }
 

@@ -263,5 +263,9 @@ class Mixer:
     def reduce_bus_end_device(self, d_bus, frames):
         self._ck(self._lib.gas_reduce_bus_end_device(self._ctx, C.c_void_p(d_bus), int(frames)))
 
+    def reduce_bus_exchange_device(self, d_partial, d_prev_sum, frames):
+        """finish(previous block) -> d_prev_sum, push(d_partial), on the exchange stream (gas_reduce_bus_exchange_device)."""
+        self._ck(self._lib.gas_reduce_bus_exchange_device(self._ctx, C.c_void_p(d_partial), C.c_void_p(d_prev_sum), int(frames)))
+
     def comm_close(self):
         self._ck(self._lib.gas_comm_close(self._ctx))

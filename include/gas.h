@@ -390,6 +390,13 @@ GAS_API int gas_reduce_bus_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames
  * end(n) before begin(n + 2) at the latest (two exchange buffers). */
 GAS_API int gas_reduce_bus_begin_device(gas_ctx *ctx, const gas_frame *d_bus, int32_t frames);
 GAS_API int gas_reduce_bus_end_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames);
+/* One block in flight, off the critical path: on the context's exchange stream (beside whatever the mix stream
+ * does next) write the complete sum of the previously pushed block to d_prev_sum (skipped when no block is
+ * outstanding; may be NULL then) and push d_partial as the next block.  d_partial must stay untouched until the
+ * call after next has been enqueued (the mix stream waits for the exchange before it reuses bus buffers; inside a
+ * captured graph the exchange is a branch that joins at the end of the graph).  Drain with
+ * gas_reduce_bus_end_device. */
+GAS_API int gas_reduce_bus_exchange_device(gas_ctx *ctx, const gas_frame *d_partial, gas_frame *d_prev_sum, int32_t frames);
 GAS_API int gas_comm_close(gas_ctx *ctx);
 
 #ifdef __cplusplus

@@ -61,6 +61,28 @@ def main():
             got.append(d_bus.cpu().numpy().copy())
         m.sync()
         dist.barrier()
+        # the pipelined variant: one block in flight on the exchange stream, sums arrive one call later
+        got2 = []
+        m.instance_init(inst, 0)
+        d_part = [torch.zeros_like(d_bus) for _ in range(2)]
+        d_sum = [torch.zeros_like(d_bus) for _ in range(2)]
+        for b in range(blocks):
+            em = synth.make_emitters(V, block=b, dt=F / sc["mix_rate"], area_fraction=sc["area_fraction"])[lo:hi].copy()
+            em["instance"] -= lo
+            m.gain_compute(em, listeners, areas, want_params=False)
+            if b == 0:
+                m.instance_start(inst)
+                m.voice_init(inst)
+            src = torch.from_numpy(synth.make_sources(V, F, block=b, mix_rate=sc["mix_rate"])[idx].copy()).to(dev)
+            m.mix_block_device(n_loc, d_voices.data_ptr(), src.data_ptr(), n_loc, F, F, d_part[b % 2].data_ptr())
+            m.reduce_bus_exchange_device(d_part[b % 2].data_ptr(), d_sum[(b + 1) % 2].data_ptr(), F)  # pushes b, finishes b - 1
+            m.sync()
+            if b >= 1:
+                got2.append(d_sum[(b + 1) % 2].cpu().numpy().copy())
+        m.reduce_bus_end_device(d_sum[blocks % 2].data_ptr(), F)
+        m.sync()
+        got2.append(d_sum[blocks % 2].cpu().numpy().copy())
+        dist.barrier()
     with orc.OracleMixer(**S.config_of(sc)) as o:
         want = S.run(o, sc, collect_state=False)["bus"]
     ok_all = True
@@ -69,6 +91,10 @@ def main():
         routing = np.array_equal(S.routing(got[b]), S.routing(want[b]))
         ok_all &= ok and routing
         print(f"rank {rank} block {b}: ok={ok} routing={routing} worst_abs_err={worst:.3e} bad={nbad}", flush=True)
+    for b in range(blocks):
+        ok, worst, nbad = S.sample_close(got2[b], want[b])
+        ok_all &= ok
+        print(f"rank {rank} block {b} (pipelined exchange): ok={ok} worst_abs_err={worst:.3e} bad={nbad}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok_all else 1)
