@@ -269,7 +269,7 @@ class DeviceWorkload:
             # block k mixes, the exchange stream pushes block k-1's partial sums to every rank and writes block k-2's
             # complete sum — the whole exchange (NVLink round trip, system-scope fences, rank skew) is off the critical path.
             m.reduce_bus_exchange_device(self.d_bus[(k + 1) % 2].data_ptr(), self.d_sum[k % 2].data_ptr(), w["frames"])
-        if not os.environ.get("GAS_BENCH_NOGAIN"):  # experiments only: leave K1 out of the step
+        if not (os.environ.get("GAS_BENCH_NOGAIN") or getattr(self, "no_gain", False)):  # K1 left out: experiments / K2-alone timing
             m.gain_compute_device(w["voices"], self.d_emitters[(s + 1) % N_SETS].data_ptr())
         return self.d_bus[k % 2]
 
@@ -404,6 +404,16 @@ def gpu_arm(args):
         m.graph_launch(pgraphs[k % N_SETS])
     dw.reduce_drain(kp - 1)
     prof = m.profile_read()
+    # once more without K1 beside the mix: K2 with the GPU to itself (reported next to the in-step figure, not instead of it)
+    dw.no_gain = True
+    m.profile_enable(True)
+    agraphs = dw.capture_steps()
+    dw.reduce_prime()
+    for k in range(kp):
+        m.graph_launch(agraphs[k % N_SETS])
+    dw.reduce_drain(kp - 1)
+    prof_alone = m.profile_read()
+    dw.no_gain = False
     m.profile_enable(False)
     k2_ms, k2_n = prof["mix_stream"]
     peak, peak_src = measured_hbm_peak()
@@ -418,6 +428,9 @@ def gpu_arm(args):
                 "kernel": "k_mix_stream (K2)", "us_per_launch": k2_us, "algorithmic_bytes_per_launch": bytes_launch,
                 "peak_source": peak_src, "timing": "CUDA event-record nodes around the kernel inside the replayed step graph",
                 "step_frac_of_hbm_peak": (bytes_launch / (ms * 1e-3 / K) / 1e9) / peak,
+                "alone": {"note": "same kernel in the same graph without K1 running beside it on the gain stream",
+                          "us_per_launch": 1e3 * prof_alone["mix_stream"][0] / max(1, prof_alone["mix_stream"][1]),
+                          "frac": bytes_launch / (1e3 * prof_alone["mix_stream"][0] / max(1, prof_alone["mix_stream"][1]) * 1e-6) / 1e9 / peak},
                 "other_kernels_us": {"gain_K1": us("gain"), "prologue": us("prologue"), "mix_voice_K3": us("mix_voice")}}
     traffic_file = os.path.join(ROOT, "profiles", "k2_traffic_bytes.json")
     if os.path.exists(traffic_file):
