@@ -23,11 +23,13 @@
 // A CTA owns a contiguous range of (class, frame tile, voice batch) units; ranges are cut in cost space
 // (accumulator count + a fixed per-voice term) so that the FMA-heavy classes do not pile up on a few SMs.
 // When the class or tile changes the CTA evaluates the polynomial in t and adds its partial sums to the bus
-// buffers: per-thread red.global.add.v4.f32 (default), or (GAS_K2_FLUSH=1) shared-memory staging + bulk
-// async reductions (cp.reduce.async.bulk ... add.f32, SASS UBLKRED).  No per-voice state is written here.
+// buffers with per-thread red.global.add.v4.f32, straight out of the accumulator registers (the row layout of a
+// class is resolved by a switch over compile-time layouts: a first version parked the accumulators in a
+// thread-local array and indexed it at run time, and with 216 KB of the SM's SRAM carved out as shared memory
+// those local loads went to L2 one dependent round trip after another, ~3 us per flush).  Two other flush
+// shapes were measured and dropped: shared-memory staging + bulk async reductions (cp.reduce.async.bulk, +4 us)
+// and plain stores into per-CTA slabs folded later (no gain).  No per-voice state is written here.
 #include "gas_internal.h"
-
-#include <stdlib.h>
 
 #include <stdlib.h>
 
@@ -43,8 +45,6 @@ constexpr int kThreads = kConsumerThreads + 32;
 constexpr int kTileFrames = 512;       // frames per tile: 2 per consumer thread
 constexpr int kMaxPairs = GAS_K2_MAX_ROWS * GAS_MAX_CHANNELS_PER_BUS; // 24 (L,R) weight pairs per voice
 constexpr int kMaxStages = 8;
-constexpr int kStagingSlot = GAS_MAX_CHANNELS_PER_BUS * kTileFrames * 8; // one row group: C rows of a 512-frame tile
-constexpr int kStagingBytes = 2 * kStagingSlot;                         // double-buffered
 
 struct StreamCfg {
 	int frames;        // F
@@ -59,11 +59,8 @@ struct StreamCfg {
 	int w_bytes;       // per stage
 	int stage_bytes;
 	int fixed_cost;    // per-voice term of the partition cost (the other term is the accumulator count)
-	int flush_mode;    // 0 = per-thread red.global.add.v4, 1 = shared-memory staging + bulk async reduce,
-	                   // 2 = plain stores into this CTA's private slab (GAS_K2_SLAB=1; needs a tile that spans all consumer threads)
-	unsigned long long *slab_mask; // flush_mode 2: per-CTA mask of slab rows written
 	int debug;         // GAS_K2_DEBUG bits (experiments only): 1 = skip the bus reductions, 2 = skip the FMAs, 8 = record a timeline
-	unsigned long long *timeline; // [CTA][8] globaltimer stamps (debug & 8): start, table, first data, last data, flushed
+	unsigned long long *timeline; // [CTA][16] globaltimer stamps (debug & 8), see tools/k2bench.cpp for the slots
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------
@@ -102,20 +99,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 			"l"(src), "r"(bytes), "r"(smem_u32(bar))
 			: "memory");
 }
-// 1-D bulk async reduction shared -> global, element-wise fp32 add performed at L2 (SASS: UBLKRED)
-__device__ __forceinline__ void bulk_red_add_f32(float *dst, const void *src, uint32_t bytes) {
-	asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
-			: "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// wait until at most N of the most recent bulk groups still read their shared-memory source
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-	asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -147,37 +130,23 @@ struct UnitIter {
 
 // CTA `cta` owns the units whose start lies in [total*cta/n, total*(cta+1)/n) of the cost line, where a
 // unit of class c costs w_c = accumulators + fixed_cost.  Units are ordered class, tile, batch.
-__device__ void unit_iter_init(UnitIter &it, const ClassInfo *cls, int n_cls, const StreamCfg &cf, int C, int cta, int n_cta) {
+// Everything is 32-bit unsigned arithmetic (64-bit divisions are long software routines and this runs on the
+// critical path of every CTA's start): the cost line of the largest context (65536 voices x 4 tiles x cost <= 90)
+// times the grid size stays below 2^32; beyond that the wide variant takes over.
+__device__ __noinline__ void unit_iter_init_wide(UnitIter &it, const ClassInfo *cls, int n_cls, const StreamCfg &cf, int C, int cta, int n_cta) {
 	long long total = 0;
 	for (int c = 0; c < n_cls; c++) {
 		const long long units = (long long)((cls[c].count + cf.vb - 1) / cf.vb) * cf.n_tiles;
 		total += units * (cls[c].n_rows * C + cf.fixed_cost);
 	}
-	long long lo, hi;
-	if (total < (1LL << 31) / n_cta) { // 32-bit divisions (the usual case): 64-bit ones are slow software routines
-		lo = (unsigned)total * (unsigned)cta / (unsigned)n_cta;
-		hi = (unsigned)total * (unsigned)(cta + 1) / (unsigned)n_cta;
-	} else {
-		lo = total * cta / n_cta;
-		hi = total * (cta + 1) / n_cta;
-	}
-	it.remaining = 0;
-	it.cid = n_cls;
-	it.n_cls = n_cls;
-	it.tile = it.batch = it.nb = 0;
+	const long long lo = total * cta / n_cta, hi = total * (cta + 1) / n_cta;
 	long long base = 0;
 	for (int c = 0; c < n_cls; c++) {
 		const int nb = (cls[c].count + cf.vb - 1) / cf.vb;
 		const long long units = (long long)nb * cf.n_tiles;
 		const long long w = cls[c].n_rows * C + cf.fixed_cost;
-		long long u_lo, u_hi;
-		if (hi < (1LL << 31)) {
-			u_lo = lo <= base ? 0 : (unsigned)(lo - base + w - 1) / (unsigned)w;
-			u_hi = hi <= base ? 0 : (unsigned)(hi - base + w - 1) / (unsigned)w;
-		} else {
-			u_lo = lo <= base ? 0 : (lo - base + w - 1) / w;
-			u_hi = hi <= base ? 0 : (hi - base + w - 1) / w;
-		}
+		long long u_lo = lo <= base ? 0 : (lo - base + w - 1) / w;
+		long long u_hi = hi <= base ? 0 : (hi - base + w - 1) / w;
 		u_lo = u_lo > units ? units : u_lo;
 		u_hi = u_hi > units ? units : u_hi;
 		if (u_hi > u_lo) {
@@ -186,6 +155,46 @@ __device__ void unit_iter_init(UnitIter &it, const ClassInfo *cls, int n_cls, co
 				it.nb = nb;
 				it.tile = (int)(u_lo / nb);
 				it.batch = (int)(u_lo % nb);
+			}
+			it.remaining += (int)(u_hi - u_lo);
+		}
+		base += units * w;
+	}
+}
+
+__device__ __forceinline__ void unit_iter_init(UnitIter &it, const ClassInfo *cls, int n_cls, const StreamCfg &cf, int C, int cta, int n_cta) {
+	const int vb_shift = 31 - __clz(cf.vb); // vb is 8, 16 or 32
+	unsigned long long total64 = 0;
+	for (int c = 0; c < n_cls; c++) {
+		const unsigned units = (unsigned)((cls[c].count + cf.vb - 1) >> vb_shift) * (unsigned)cf.n_tiles;
+		total64 += (unsigned long long)units * (unsigned)(cls[c].n_rows * C + cf.fixed_cost);
+	}
+	it.remaining = 0;
+	it.cid = n_cls;
+	it.n_cls = n_cls;
+	it.tile = it.batch = it.nb = 0;
+	if (total64 * (unsigned)(n_cta + 1) >= (1ULL << 32)) {
+		unit_iter_init_wide(it, cls, n_cls, cf, C, cta, n_cta);
+		return;
+	}
+	const unsigned total = (unsigned)total64;
+	const unsigned lo = total * (unsigned)cta / (unsigned)n_cta;
+	const unsigned hi = total * (unsigned)(cta + 1) / (unsigned)n_cta;
+	unsigned base = 0;
+	for (int c = 0; c < n_cls; c++) {
+		const unsigned nb = (unsigned)(cls[c].count + cf.vb - 1) >> vb_shift;
+		const unsigned units = nb * (unsigned)cf.n_tiles;
+		const unsigned w = (unsigned)(cls[c].n_rows * C + cf.fixed_cost);
+		unsigned u_lo = lo <= base ? 0u : (lo - base + w - 1u) / w;
+		unsigned u_hi = hi <= base ? 0u : (hi - base + w - 1u) / w;
+		u_lo = min(u_lo, units);
+		u_hi = min(u_hi, units);
+		if (u_hi > u_lo) {
+			if (it.remaining == 0) {
+				it.cid = c;
+				it.nb = (int)nb;
+				it.tile = (int)(u_lo / nb);
+				it.batch = (int)(u_lo - (u_lo / nb) * nb);
 			}
 			it.remaining += (int)(u_hi - u_lo);
 		}
@@ -246,7 +255,6 @@ __device__ __forceinline__ IdxBlock idx_block_load(UnitIter &pf, const ClassInfo
 
 struct ConsumerCtx {
 	unsigned char *smem;    // stage ring
-	unsigned char *staging; // flush staging (2 slots)
 	uint64_t *full;
 	uint64_t *empty;
 	const ClassInfo *cls;
@@ -254,16 +262,50 @@ struct ConsumerCtx {
 	bool worker;
 	int stage;
 	uint32_t phase;
-	uint32_t flushes; // bulk reduce groups committed so far (thread 0 is the issuer)
-	unsigned long long touched; // flush_mode 2: rows of the slab this CTA has written (identical in every thread)
 	unsigned long long *tl;
 };
 
-// One run = every consecutive unit of this CTA that shares (class, tile).  NP = (L,R) weight pairs per
-// voice = rows * pairs.  The accumulators live in registers for the whole run; at its end the polynomial
+// One row group (rows R0, R0+1 and, when `quad`, R0+2 of a class with R rows) of one run: evaluate the
+// polynomial at this thread's two frames and add the result to bus `b_own`, or to every bus of `fan` when the
+// group is shared by all sends.  Every accumulator index is a compile-time constant.
+template <int R, int C, int R0>
+__device__ __forceinline__ void flush_group(const float2 (&acc)[R * C][2], bool quad, uint32_t fan, int b_own, float t0, float t1, float *__restrict__ bus,
+		int F, int frame0) {
+#pragma unroll
+	for (int c = 0; c < C; c++) {
+		const float2 a0 = acc[R0 * C + c][0], a1 = acc[R0 * C + c][1];
+		const float2 b0 = acc[(R0 + 1) * C + c][0], b1 = acc[(R0 + 1) * C + c][1];
+		float2 c0 = make_float2(0.f, 0.f), c1 = make_float2(0.f, 0.f);
+		if (R0 + 2 < R) {
+			if (quad) {
+				c0 = acc[(R0 + 2 < R ? R0 + 2 : 0) * C + c][0];
+				c1 = acc[(R0 + 2 < R ? R0 + 2 : 0) * C + c][1];
+			}
+		}
+		float4 v;
+		v.x = fmaf(t0, fmaf(t0, c0.x, b0.x), a0.x);
+		v.y = fmaf(t0, fmaf(t0, c0.y, b0.y), a0.y);
+		v.z = fmaf(t1, fmaf(t1, c1.x, b1.x), a1.x);
+		v.w = fmaf(t1, fmaf(t1, c1.y, b1.y), a1.y);
+		if (fan) { // one row group fanned out to every bus of the mask
+			uint32_t m = fan;
+			while (m) {
+				const int b = __ffs(m) - 1;
+				m &= m - 1;
+				red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, v.x, v.y, v.z, v.w);
+			}
+		} else {
+			red_add_v4(bus + ((size_t)(b_own * C + c) * F + frame0) * 2, v.x, v.y, v.z, v.w);
+		}
+	}
+}
+
+// One run = every consecutive unit of this CTA that shares (class, tile).  R rows x C channel pairs = NP (L,R)
+// weight pairs per voice.  The accumulators live in registers for the whole run; at its end the polynomial
 // is evaluated in t and the partial sums are added to the bus buffers.
-template <int NP>
+template <int R, int C>
 __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, const StreamCfg &cf, float *__restrict__ bus) {
+	constexpr int NP = R * C;
 	float2 acc[NP][2];
 #pragma unroll
 	for (int p = 0; p < NP; p++) {
@@ -349,23 +391,18 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 	if (cc.tl) {
 		cc.tl[3] = gtime();
 	}
-	if (cf.debug & 1) {
+	if ((cf.debug & 1) || !mine) {
 		return;
 	}
 	// ---- flush: bus[b][c][i] += A + B t (+ C t^2), rows ordered [group][poly][pair] --------------------
-	const int C = cc.C, F = cf.frames;
+	if (cc.tl) {
+		cc.tl[9] = gtime();
+	}
+	const int F = cf.frames;
 	const int frame0 = tile * cf.tile_frames + cc.slot * 2;
 	const float t0 = (float)frame0 / (float)F;
 	const float t1 = (float)(frame0 + 1) / (float)F;
-	const bool shared = (ci.flags & CLS_SHARED) != 0;
-	// The accumulators were indexed statically so far (registers); the flush picks rows by run-time index, so
-	// they are parked in a thread-local array once (a handful of 16-byte local stores) instead of being
-	// selected through compare chains.
-	float4 dump[NP];
-#pragma unroll
-	for (int p = 0; p < NP; p++) {
-		dump[p] = make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y);
-	}
+	const uint32_t fan = (ci.flags & CLS_SHARED) ? ci.mask : 0u;
 	const int RG = ci.n_group; // row groups; group k owns 2 rows (A, B) plus a t^2 row when its quad bit is set
 	uint32_t rest = ci.mask;
 	int r0 = 0; // first row of group k
@@ -373,95 +410,24 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		const bool quad = (ci.quad >> k) & 1u;
 		const int b_own = __ffs(rest) - 1; // k-th bus of the mask (sends ascend by bus)
 		rest &= rest - 1;
-		unsigned char *stg = cc.staging + (cc.flushes & 1u) * kStagingSlot;
-		if (cf.flush_mode == 1) {
-			// the reduce that read this staging slot two flushes ago must be done with it
-			if (cc.tid == 0) {
-				bulk_wait_read<1>();
-			}
-			consumer_barrier();
-		}
-		for (int c = 0; c < C; c++) {
-			const int pa = (r0 + 0) * C + c, pb = (r0 + 1) * C + c, pc = (r0 + 2) * C + c;
-			const float4 A = dump[pa], B = dump[pb];
-			const float4 Q = quad ? dump[pc] : make_float4(0.f, 0.f, 0.f, 0.f);
-			const float2 a0 = make_float2(A.x, A.y), a1 = make_float2(A.z, A.w);
-			const float2 b0 = make_float2(B.x, B.y), b1 = make_float2(B.z, B.w);
-			const float2 c0 = make_float2(Q.x, Q.y), c1 = make_float2(Q.z, Q.w);
-			float4 v;
-			v.x = fmaf(t0, fmaf(t0, c0.x, b0.x), a0.x);
-			v.y = fmaf(t0, fmaf(t0, c0.y, b0.y), a0.y);
-			v.z = fmaf(t1, fmaf(t1, c1.x, b1.x), a1.x);
-			v.w = fmaf(t1, fmaf(t1, c1.y, b1.y), a1.y);
-			if (cf.flush_mode == 1) {
-				// the warp groups of the CTA (different voices, same frames) are summed in shared memory first
-				float4 *dst = reinterpret_cast<float4 *>(stg + (size_t)c * row_bytes + cc.slot * 16);
-				for (int g = 0; g < cf.groups; g++) {
-					if (mine && cc.group == g) {
-						if (g > 0) {
-							const float4 o = *dst;
-							v.x += o.x;
-							v.y += o.y;
-							v.z += o.z;
-							v.w += o.w;
-						}
-						*dst = v;
-					}
-					if (cf.groups > 1) {
-						consumer_barrier();
-					}
+		// a group starts at row 0, 2, 3 or 4 (at most GAS_K2_MAX_ROWS = 6 rows, 2 or 3 per group)
+		switch (r0) {
+			case 0: flush_group<R, C, 0>(acc, quad, fan, b_own, t0, t1, bus, F, frame0); break;
+			case 2:
+				if (R >= 4) {
+					flush_group<R, C, (R >= 4 ? 2 : 0)>(acc, quad, fan, b_own, t0, t1, bus, F, frame0);
 				}
-			} else if (cf.flush_mode == 2) {
-				// private slab: the first visit of a row stores, later visits (another class reaching the same bus)
-				// add to what this very thread stored; no atomics, no zero-fill
-				uint32_t m = shared ? ci.mask : (1u << b_own);
-				while (m) {
-					const int b = __ffs(m) - 1;
-					m &= m - 1;
-					const int r = b * C + c;
-					if (mine) {
-						float4 *dst = reinterpret_cast<float4 *>(bus + ((size_t)r * F + frame0) * 2);
-						float4 o = v;
-						if ((cc.touched >> r) & 1ULL) {
-							const float4 q = *dst;
-							o.x += q.x;
-							o.y += q.y;
-							o.z += q.z;
-							o.w += q.w;
-						}
-						*dst = o;
-					}
-					cc.touched |= 1ULL << r;
+				break;
+			case 3:
+				if (R >= 5) {
+					flush_group<R, C, (R >= 5 ? 3 : 0)>(acc, quad, fan, b_own, t0, t1, bus, F, frame0);
 				}
-			} else if (mine) {
-				if (shared) { // one row group fanned out to every bus of the mask
-					uint32_t m = ci.mask;
-					while (m) {
-						const int b = __ffs(m) - 1;
-						m &= m - 1;
-						red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, v.x, v.y, v.z, v.w);
-					}
-				} else {
-					red_add_v4(bus + ((size_t)(b_own * C + c) * F + frame0) * 2, v.x, v.y, v.z, v.w);
+				break;
+			default:
+				if (R >= 6) {
+					flush_group<R, C, (R >= 6 ? 4 : 0)>(acc, quad, fan, b_own, t0, t1, bus, F, frame0);
 				}
-			}
-		}
-		if (cf.flush_mode == 1) {
-			fence_proxy_async(); // generic-proxy stores above -> async-proxy reads of the bulk reduce
-			consumer_barrier();
-			if (cc.tid == 0) {
-				const size_t tile_off = (size_t)tile * cf.tile_frames * 2;
-				uint32_t m = shared ? ci.mask : (1u << b_own);
-				while (m) {
-					const int b = __ffs(m) - 1;
-					m &= m - 1;
-					for (int c = 0; c < C; c++) {
-						bulk_red_add_f32(bus + (size_t)(b * C + c) * F * 2 + tile_off, stg + (size_t)c * row_bytes, (uint32_t)row_bytes);
-					}
-				}
-				bulk_commit();
-			}
-			cc.flushes++;
+				break;
 		}
 		r0 += quad ? 3 : 2;
 	}
@@ -469,8 +435,8 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 
 __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, GlobalCfg g, StreamCfg cf,
 		const gas_frame *__restrict__ src, float *__restrict__ bus, int rep_stride, int replicas, const int32_t *__restrict__ blk) {
-	// flush target: this CTA's private slab (flush_mode 2) or replica (CTA % replicas) of the bus layout
-	bus += (size_t)(cf.flush_mode == 2 ? blockIdx.x : blockIdx.x % replicas) * rep_stride;
+	// flush target: replica (CTA % replicas) of the bus layout
+	bus += (size_t)(blockIdx.x % replicas) * rep_stride;
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ int s_ncls;
@@ -481,9 +447,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 	const int warp = tid >> 5, lane = tid & 31;
 	const int C = g.channels;
 	const int maxv = g.max_voices;
-	unsigned long long *tl = (cf.debug & 8) && tid == 0 ? cf.timeline + blockIdx.x * 8 : nullptr;
+	unsigned long long *tl = (cf.debug & 8) && tid == 0 ? cf.timeline + blockIdx.x * 16 : nullptr;
 	if (tl) {
 		tl[0] = gtime();
+		unsigned smid;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		tl[6] = smid;
 	}
 
 	if (tid == 0) {
@@ -502,6 +471,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		constexpr int R = GAS_MAX_CLASSES / 32;
 		unsigned long long key[R];
 		int cnt[2][R];
+		if (tl) {
+			tl[7] = gtime();
+		}
 		const int n = *(volatile const int32_t *)blk;
 #pragma unroll
 		for (int r = 0; r < R; r++) {
@@ -529,6 +501,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 	}
 	__syncthreads();
 	GAS_GRID_DEP_LAUNCH();
+	if (tl) {
+		tl[11] = gtime();
+	}
 
 	UnitIter it;
 	unit_iter_init(it, s_cls, s_ncls, cf, C, blockIdx.x, gridDim.x);
@@ -537,12 +512,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		tl[5] = (unsigned long long)it.remaining;
 	}
 	if (it.remaining <= 0) {
-		if (cf.flush_mode == 2 && tid == 0) {
-			cf.slab_mask[blockIdx.x] = 0ULL;
-		}
 		return;
 	}
-	unsigned char *ring = smem + kStagingBytes;
+	unsigned char *ring = smem;
 
 	if (warp == kConsumerWarps) {
 		// ===== producer =====
@@ -554,6 +526,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		IdxBlock cur = idx_block_load(pf, s_cls, cf, plan.list, maxv, lane, 0);
 		IdxBlock nxt = idx_block_load(pf, s_cls, cf, plan.list, maxv, lane, cur.n_units);
 		int seq = 0;
+		unsigned long long *tlp = (cf.debug & 8) && lane == 0 ? cf.timeline + blockIdx.x * 16 : nullptr;
+		if (tlp) {
+			tlp[12] = gtime() + (cur.val.y == -12345 ? 1ULL : 0ULL); // first indices have arrived
+		}
 		while (it.remaining > 0) {
 			if (seq >= cur.first_seq + cur.n_units) {
 				cur = nxt;
@@ -581,6 +557,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 							&s_full[stage]);
 				}
 			}
+			if (tlp && seq < 2) {
+				tlp[13 + seq] = gtime(); // copies of the first / second stage issued
+			}
 			seq++;
 			if (++stage == cf.stages) {
 				stage = 0;
@@ -592,10 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		// ===== consumers =====
 		ConsumerCtx cc;
 		cc.smem = ring;
-		cc.staging = smem;
 		cc.tid = tid;
-		cc.flushes = 0;
-		cc.touched = 0ULL;
 		cc.tl = tl;
 		cc.full = s_full;
 		cc.empty = s_empty;
@@ -608,35 +584,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		cc.stage = 0;
 		cc.phase = 0;
 		while (it.remaining > 0) {
-			const int np = s_cls[it.cid].n_rows * C;
-			switch (np) {
-				case 2: consumer_run<2>(it, cc, cf, bus); break;
-				case 3: consumer_run<3>(it, cc, cf, bus); break;
-				case 4: consumer_run<4>(it, cc, cf, bus); break;
-				case 5: consumer_run<5>(it, cc, cf, bus); break;
-				case 6: consumer_run<6>(it, cc, cf, bus); break;
-				case 8: consumer_run<8>(it, cc, cf, bus); break;
-				case 9: consumer_run<9>(it, cc, cf, bus); break;
-				case 10: consumer_run<10>(it, cc, cf, bus); break;
-				case 12: consumer_run<12>(it, cc, cf, bus); break;
-				case 15: consumer_run<15>(it, cc, cf, bus); break;
-				case 16: consumer_run<16>(it, cc, cf, bus); break;
-				case 18: consumer_run<18>(it, cc, cf, bus); break;
-				case 20: consumer_run<20>(it, cc, cf, bus); break;
-				case 24: consumer_run<24>(it, cc, cf, bus); break;
-				default: // cannot happen (rows in {2,3,4,6} x pairs in {1..4}); drain so the producer never stalls
-					consumer_run<1>(it, cc, cf, bus);
+			// dispatch on (rows, channel pairs): rows in 2..6, pairs in 1..4
+			const int code = s_cls[it.cid].n_rows * 8 + C;
+#define GAS_RUN(R_, C_) \
+	case (R_) * 8 + (C_): consumer_run<R_, C_>(it, cc, cf, bus); break;
+			switch (code) {
+				GAS_RUN(2, 1) GAS_RUN(2, 2) GAS_RUN(2, 3) GAS_RUN(2, 4)
+				GAS_RUN(3, 1) GAS_RUN(3, 2) GAS_RUN(3, 3) GAS_RUN(3, 4)
+				GAS_RUN(4, 1) GAS_RUN(4, 2) GAS_RUN(4, 3) GAS_RUN(4, 4)
+				GAS_RUN(5, 1) GAS_RUN(5, 2) GAS_RUN(5, 3) GAS_RUN(5, 4)
+				GAS_RUN(6, 1) GAS_RUN(6, 2) GAS_RUN(6, 3) GAS_RUN(6, 4)
+				default: // cannot happen; drain so the producer never stalls
+					consumer_run<2, 1>(it, cc, cf, bus);
 					break;
 			}
+#undef GAS_RUN
 		}
 		if (tl) {
 			tl[4] = gtime();
-		}
-		if (cf.flush_mode == 2 && tid == 0) {
-			cf.slab_mask[blockIdx.x] = cc.touched;
-		}
-		if (tid == 0 && cc.flushes > 0) {
-			bulk_wait_all(); // the staging slots must outlive the reads; the adds are complete when the grid is
 		}
 	}
 }
@@ -673,12 +638,11 @@ static StreamCfg make_cfg(int frames, int src_stride, int smem_limit) {
 	cf.x_bytes = vb * cf.tile_frames * 8;
 	cf.w_bytes = (vb * kMaxPairs * 8 + 127) & ~127;
 	cf.stage_bytes = cf.x_bytes + cf.w_bytes;
-	int stages = (smem_limit - kStagingBytes) / cf.stage_bytes;
+	int stages = smem_limit / cf.stage_bytes;
 	cf.stages = stages > kMaxStages ? kMaxStages : stages;
 	// tuning / experiment knobs (environment, read per launch: they never change results, only schedules)
 	cf.stages = env_int("GAS_K2_STAGES", cf.stages, 2, cf.stages);
 	cf.fixed_cost = env_int("GAS_K2_FIXED_COST", 40, 0, 1024);
-	cf.flush_mode = env_int("GAS_K2_FLUSH", 0, 0, 1);
 	cf.debug = env_int("GAS_K2_DEBUG", 0, 0, 15);
 	return cf;
 }
@@ -689,7 +653,7 @@ cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stri
 	if (cf.stages < 2) {
 		return cudaErrorInvalidConfiguration;
 	}
-	const size_t smem = (size_t)kStagingBytes + (size_t)cf.stages * cf.stage_bytes;
+	const size_t smem = (size_t)cf.stages * cf.stage_bytes;
 	if (!ctx->k2_smem_attr_set) {
 		cudaError_t e = cudaFuncSetAttribute(k_mix_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
 		if (e != cudaSuccess) {
@@ -697,30 +661,16 @@ cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stri
 		}
 		ctx->k2_smem_attr_set = true;
 	}
-	// Partial sums: atomic adds into replica (CTA % replicas) of the bus layout, or (GAS_K2_SLAB=1) plain stores
-	// into one private slab per CTA.  Either way the voice-parallel kernel's launch folds them into d_bus.
-	// Measured on B200 (16384 voices): the slab variant does not shorten K2 and its fold is slower.
-	const bool env_flush = getenv("GAS_K2_FLUSH") != nullptr;
-	if (!env_flush && ctx->use_slab && cf.groups == 1 && ctx->g.num_buses * ctx->g.channels <= 64) {
-		cf.flush_mode = 2;
-	}
-	float *target;
-	int rep_stride; // floats
-	if (cf.flush_mode == 2) {
-		target = (float *)ctx->d_slab;
-		rep_stride = gas_bus_f4(ctx, frames) * 4;
-		cf.slab_mask = ctx->d_slab_mask;
-		ctx->slab_ctas = ctx->num_sms;
-	} else {
-		target = ctx->replicas > 1 ? (float *)ctx->d_rep : (float *)d_bus;
-		rep_stride = ctx->replicas > 1 ? gas_bus_f4(ctx, frames) * 4 : 0;
-		ctx->slab_ctas = 0;
-	}
+	// Partial sums: atomic adds into replica (CTA % replicas) of the bus layout; the voice-parallel kernel's
+	// launch folds the replicas into d_bus.
+	float *target = ctx->replicas > 1 ? (float *)ctx->d_rep : (float *)d_bus;
+	const int rep_stride = ctx->replicas > 1 ? gas_bus_f4(ctx, frames) * 4 : 0; // floats
+	ctx->slab_ctas = 0;
 	if (cf.debug & 8) {
 		if (!ctx->d_timeline) {
-			cudaMalloc((void **)&ctx->d_timeline, 256 * 8 * sizeof(unsigned long long));
+			cudaMalloc((void **)&ctx->d_timeline, 256 * 16 * sizeof(unsigned long long));
 		}
-		cudaMemsetAsync(ctx->d_timeline, 0, 256 * 8 * sizeof(unsigned long long), st);
+		cudaMemsetAsync(ctx->d_timeline, 0, 256 * 16 * sizeof(unsigned long long), st);
 		cf.timeline = ctx->d_timeline;
 	}
 	cudaError_t e = gas_launch(k_mix_stream, dim3(ctx->num_sms), dim3(kThreads), smem, st, ctx->pdl, ctx->plan, ctx->g, cf, d_src, target,
