@@ -59,6 +59,9 @@ struct StreamCfg {
 	int w_bytes;       // per stage
 	int stage_bytes;
 	int fixed_cost;    // per-voice term of the partition cost (the other term is the accumulator count)
+	int vb_shift;      // log2(vb)
+	double inv_grid;   // 1 / CTAs
+	double inv_cost[kMaxPairs + 1]; // 1 / (accumulators + fixed_cost)
 	int debug;         // GAS_K2_DEBUG bits (experiments only): 1 = skip the bus reductions, 2 = skip the FMAs, 8 = record a timeline
 	unsigned long long *timeline; // [CTA][16] globaltimer stamps (debug & 8), see tools/k2bench.cpp for the slots
 };
@@ -133,18 +136,25 @@ struct UnitIter {
 // Everything is 32-bit unsigned arithmetic (64-bit divisions are long software routines and this runs on the
 // critical path of every CTA's start): the cost line of the largest context (65536 voices x 4 tiles x cost <= 90)
 // times the grid size stays below 2^32; beyond that the wide variant takes over.
-__device__ __noinline__ void unit_iter_init_wide(UnitIter &it, const ClassInfo *cls, int n_cls, const StreamCfg &cf, int C, int cta, int n_cta) {
+__device__ __noinline__ UnitIter unit_iter_init_wide(const ClassInfo *cls, int n_cls, int vb, int n_tiles, int fixed_cost, int C, int cta, int n_cta) {
+	// by value in and out: a reference parameter of an out-of-line function would pin the caller's iterator (and the
+	// whole StreamCfg) in local memory for the rest of the kernel
+	UnitIter it;
+	it.remaining = 0;
+	it.cid = n_cls;
+	it.n_cls = n_cls;
+	it.tile = it.batch = it.nb = 0;
 	long long total = 0;
 	for (int c = 0; c < n_cls; c++) {
-		const long long units = (long long)((cls[c].count + cf.vb - 1) / cf.vb) * cf.n_tiles;
-		total += units * (cls[c].n_rows * C + cf.fixed_cost);
+		const long long units = (long long)((cls[c].count + vb - 1) / vb) * n_tiles;
+		total += units * (cls[c].n_rows * C + fixed_cost);
 	}
 	const long long lo = total * cta / n_cta, hi = total * (cta + 1) / n_cta;
 	long long base = 0;
 	for (int c = 0; c < n_cls; c++) {
-		const int nb = (cls[c].count + cf.vb - 1) / cf.vb;
-		const long long units = (long long)nb * cf.n_tiles;
-		const long long w = cls[c].n_rows * C + cf.fixed_cost;
+		const int nb = (cls[c].count + vb - 1) / vb;
+		const long long units = (long long)nb * n_tiles;
+		const long long w = cls[c].n_rows * C + fixed_cost;
 		long long u_lo = lo <= base ? 0 : (lo - base + w - 1) / w;
 		long long u_hi = hi <= base ? 0 : (hi - base + w - 1) / w;
 		u_lo = u_lo > units ? units : u_lo;
@@ -160,7 +170,12 @@ __device__ __noinline__ void unit_iter_init_wide(UnitIter &it, const ClassInfo *
 		}
 		base += units * w;
 	}
+	return it;
 }
+
+// floor(x / d) for x < 2^32 and 1 <= d < 2^31 through one double multiply: with inv = RN(1/d) the product
+// (x + 0.5) * inv is off by less than 2^-20 from (x + 0.5) / d, which never comes closer than 1 / (2 d) to an integer.
+__device__ __forceinline__ unsigned div_floor_u32(unsigned x, double inv) { return (unsigned)__double2uint_rz(((double)x + 0.5) * inv); }
 
 __device__ __forceinline__ void unit_iter_init(UnitIter &it, const ClassInfo *cls, int n_cls, const StreamCfg &cf, int C, int cta, int n_cta) {
 	const int vb_shift = 31 - __clz(cf.vb); // vb is 8, 16 or 32
@@ -174,31 +189,97 @@ __device__ __forceinline__ void unit_iter_init(UnitIter &it, const ClassInfo *cl
 	it.n_cls = n_cls;
 	it.tile = it.batch = it.nb = 0;
 	if (total64 * (unsigned)(n_cta + 1) >= (1ULL << 32)) {
-		unit_iter_init_wide(it, cls, n_cls, cf, C, cta, n_cta);
+		it = unit_iter_init_wide(cls, n_cls, cf.vb, cf.n_tiles, cf.fixed_cost, C, cta, n_cta);
 		return;
 	}
 	const unsigned total = (unsigned)total64;
-	const unsigned lo = total * (unsigned)cta / (unsigned)n_cta;
-	const unsigned hi = total * (unsigned)(cta + 1) / (unsigned)n_cta;
+	const double inv_n = 1.0 / (double)n_cta;
+	const unsigned lo = div_floor_u32(total * (unsigned)cta, inv_n);
+	const unsigned hi = div_floor_u32(total * (unsigned)(cta + 1), inv_n);
 	unsigned base = 0;
 	for (int c = 0; c < n_cls; c++) {
 		const unsigned nb = (unsigned)(cls[c].count + cf.vb - 1) >> vb_shift;
 		const unsigned units = nb * (unsigned)cf.n_tiles;
 		const unsigned w = (unsigned)(cls[c].n_rows * C + cf.fixed_cost);
-		unsigned u_lo = lo <= base ? 0u : (lo - base + w - 1u) / w;
-		unsigned u_hi = hi <= base ? 0u : (hi - base + w - 1u) / w;
+		const double inv_w = 1.0 / (double)w;
+		unsigned u_lo = lo <= base ? 0u : div_floor_u32(lo - base + w - 1u, inv_w);
+		unsigned u_hi = hi <= base ? 0u : div_floor_u32(hi - base + w - 1u, inv_w);
 		u_lo = min(u_lo, units);
 		u_hi = min(u_hi, units);
 		if (u_hi > u_lo) {
 			if (it.remaining == 0) {
 				it.cid = c;
 				it.nb = (int)nb;
-				it.tile = (int)(u_lo / nb);
-				it.batch = (int)(u_lo - (u_lo / nb) * nb);
+				if (cf.n_tiles == 1) {
+					it.tile = 0;
+					it.batch = (int)u_lo;
+				} else {
+					it.tile = (int)(u_lo / nb);
+					it.batch = (int)(u_lo - (u_lo / nb) * nb);
+				}
 			}
 			it.remaining += (int)(u_hi - u_lo);
 		}
 		base += units * w;
+	}
+}
+
+// The same partition computed by one warp, one class per lane (up to 32 streaming classes; more fall back to the
+// loop above): class costs -> warp scan -> this CTA's [lo, hi) -> per-class unit ranges -> first class and unit count
+// by ballot / warp reduction.  Reciprocals come from the host (StreamCfg).  Every lane returns the same iterator.
+__device__ __forceinline__ void unit_iter_init_warp(UnitIter &it, const ClassInfo *cls, int n_cls, const StreamCfg &cf, int C, int cta, int n_cta, int lane) {
+	if (n_cls > 32) {
+		unit_iter_init(it, cls, n_cls, cf, C, cta, n_cta);
+		return;
+	}
+	unsigned nb = 0, units = 0, w = 1;
+	int np = 0;
+	if (lane < n_cls) {
+		nb = (unsigned)(cls[lane].count + cf.vb - 1) >> cf.vb_shift;
+		units = nb * (unsigned)cf.n_tiles;
+		np = cls[lane].n_rows * C;
+		w = (unsigned)(np + cf.fixed_cost);
+	}
+	const unsigned cost = units * w; // <= 32768 units x ~90 per class: the sum over 32 classes fits 32 bits
+	unsigned incl = cost;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+		incl += lane >= d ? o : 0u;
+	}
+	const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+	it.remaining = 0;
+	it.cid = n_cls;
+	it.n_cls = n_cls;
+	it.tile = it.batch = it.nb = 0;
+	if ((unsigned long long)total * (unsigned)(n_cta + 1) >= (1ULL << 32)) {
+		it = unit_iter_init_wide(cls, n_cls, cf.vb, cf.n_tiles, cf.fixed_cost, C, cta, n_cta);
+		return;
+	}
+	const unsigned base = incl - cost;
+	const unsigned lo = div_floor_u32(total * (unsigned)cta, cf.inv_grid);
+	const unsigned hi = div_floor_u32(total * (unsigned)(cta + 1), cf.inv_grid);
+	const double inv_w = cf.inv_cost[np];
+	unsigned u_lo = lo <= base ? 0u : div_floor_u32(lo - base + w - 1u, inv_w);
+	unsigned u_hi = hi <= base ? 0u : div_floor_u32(hi - base + w - 1u, inv_w);
+	u_lo = min(u_lo, units);
+	u_hi = min(u_hi, units);
+	const unsigned mine = u_hi > u_lo ? u_hi - u_lo : 0u;
+	const unsigned have = __ballot_sync(0xffffffffu, mine > 0u);
+	if (have == 0u) {
+		return;
+	}
+	const int first = __ffs(have) - 1;
+	it.remaining = (int)__reduce_add_sync(0xffffffffu, mine);
+	it.cid = first;
+	const unsigned nb0 = __shfl_sync(0xffffffffu, nb, first);
+	const unsigned u0 = __shfl_sync(0xffffffffu, u_lo, first);
+	it.nb = (int)nb0;
+	if (cf.n_tiles == 1) {
+		it.batch = (int)u0;
+	} else {
+		it.tile = (int)(u0 / nb0);
+		it.batch = (int)(u0 - (u0 / nb0) * nb0);
 	}
 }
 
@@ -217,7 +298,7 @@ __device__ __forceinline__ void unit_iter_next(UnitIter &it, const ClassInfo *cl
 	it.tile = 0;
 	if (it.cid + 1 < it.n_cls) {
 		it.cid++;
-		it.nb = (cls[it.cid].count + cf.vb - 1) / cf.vb;
+		it.nb = (cls[it.cid].count + cf.vb - 1) >> cf.vb_shift;
 		return;
 	}
 	it.remaining = 0;
@@ -240,16 +321,17 @@ __device__ __forceinline__ IdxBlock idx_block_load(UnitIter &pf, const ClassInfo
 	if (pf.remaining <= 0) {
 		return b;
 	}
-	const int upb = 32 / cf.vb; // vb is 8, 16 or 32
+	const int upb = 32 >> cf.vb_shift; // vb is 8, 16 or 32
 	const int n = min(upb, min(pf.nb - pf.batch, pf.remaining));
 	const int pos = pf.batch * cf.vb + lane;
 	if (lane < n * cf.vb && pos < cls[pf.cid].count) {
 		b.val = __ldg(list + (size_t)cls[pf.cid].slot * maxv + pos);
 	}
 	b.n_units = n;
-	for (int i = 0; i < n; i++) {
-		unit_iter_next(pf, cls, cf);
-	}
+	// advance by n units: they all lie in the current (class, tile) row of batches
+	pf.remaining -= n - 1;
+	pf.batch += n - 1;
+	unit_iter_next(pf, cls, cf);
 	return b;
 }
 
@@ -439,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 	bus += (size_t)(blockIdx.x % replicas) * rep_stride;
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
-	__shared__ int s_ncls;
+	__shared__ UnitIter s_it;
 	__shared__ __align__(8) uint64_t s_full[kMaxStages];
 	__shared__ __align__(8) uint64_t s_empty[kMaxStages];
 
@@ -447,39 +529,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 	const int warp = tid >> 5, lane = tid & 31;
 	const int C = g.channels;
 	const int maxv = g.max_voices;
+	// timeline (debug & 8): the first lane of the producer warp stamps the start-up, thread 0 the consumer side
+	unsigned long long *tlp = (cf.debug & 8) && tid == kConsumerThreads ? cf.timeline + blockIdx.x * 16 : nullptr;
 	unsigned long long *tl = (cf.debug & 8) && tid == 0 ? cf.timeline + blockIdx.x * 16 : nullptr;
-	if (tl) {
-		tl[0] = gtime();
-		unsigned smid;
-		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-		tl[6] = smid;
-	}
 
-	if (tid == 0) {
-		for (int s = 0; s < cf.stages; s++) {
-			mbar_init(&s_full[s], 1);
-			mbar_init(&s_empty[s], kConsumerWarps);
+	// Start-up runs on the producer warp alone, with nothing but its own dependent loads in the way of the first
+	// copy: class table (one round of loads) -> partition -> first source-row indices -> copies.  The consumer warps
+	// wait on a named barrier for the table and their iterator; they have nothing to do before data lands anyway.
+	UnitIter it;
+	if (warp == kConsumerWarps) {
+		if (tlp) {
+			tlp[0] = gtime();
+			unsigned smid;
+			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+			tlp[6] = smid;
 		}
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	// programmatic dependent launch: the plan the prologue wrote is visible after this wait (a no-op when
-	// launched without the attribute)
-	GAS_GRID_DEP_WAIT();
-	if (warp == 0) {
+		// programmatic dependent launch: the plan the prologue wrote is visible after this wait (a no-op when
+		// launched without the attribute)
+		GAS_GRID_DEP_WAIT();
 		// Compact table of the streaming classes of this block, in slot order (identical in every CTA).  The
 		// counts of both parities are fetched together with the block counter so that no load waits for another.
 		constexpr int R = GAS_MAX_CLASSES / 32;
 		unsigned long long key[R];
 		int cnt[2][R];
-		if (tl) {
-			tl[7] = gtime();
-		}
 		const int n = *(volatile const int32_t *)blk;
 #pragma unroll
 		for (int r = 0; r < R; r++) {
 			key[r] = plan.cls_key[r * 32 + lane];
 			cnt[0][r] = plan.cls_count[r * 32 + lane];
 			cnt[1][r] = plan.cls_count[GAS_MAX_CLASSES + r * 32 + lane];
+		}
+		if (lane == 0) { // while the loads fly
+			for (int s = 0; s < cf.stages; s++) {
+				mbar_init(&s_full[s], 1);
+				mbar_init(&s_empty[s], kConsumerWarps);
+			}
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
 		const int par = (n + 1) & 1; // the prologue already advanced the counter
 		int base = 0;
@@ -495,21 +580,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 			}
 			base += __popc(m);
 		}
-		if (lane == 0) {
-			s_ncls = base;
+		__syncwarp();
+		if (tlp) {
+			tlp[11] = gtime();
 		}
-	}
-	__syncthreads();
-	GAS_GRID_DEP_LAUNCH();
-	if (tl) {
-		tl[11] = gtime();
-	}
-
-	UnitIter it;
-	unit_iter_init(it, s_cls, s_ncls, cf, C, blockIdx.x, gridDim.x);
-	if (tl) {
-		tl[1] = gtime();
-		tl[5] = (unsigned long long)it.remaining;
+		unit_iter_init_warp(it, s_cls, base, cf, C, blockIdx.x, gridDim.x, lane);
+		if (lane == 0) {
+			s_it = it;
+		}
+		__syncwarp();
+		asm volatile("bar.arrive 2, %0;" ::"n"(kThreads) : "memory");
+		if (tlp) {
+			tlp[1] = gtime();
+			tlp[5] = (unsigned long long)it.remaining;
+		}
+	} else {
+		asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+		it = s_it;
+		GAS_GRID_DEP_LAUNCH();
 	}
 	if (it.remaining <= 0) {
 		return;
@@ -526,7 +614,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		IdxBlock cur = idx_block_load(pf, s_cls, cf, plan.list, maxv, lane, 0);
 		IdxBlock nxt = idx_block_load(pf, s_cls, cf, plan.list, maxv, lane, cur.n_units);
 		int seq = 0;
-		unsigned long long *tlp = (cf.debug & 8) && lane == 0 ? cf.timeline + blockIdx.x * 16 : nullptr;
 		if (tlp) {
 			tlp[12] = gtime() + (cur.val.y == -12345 ? 1ULL : 0ULL); // first indices have arrived
 		}
@@ -617,7 +704,7 @@ static int env_int(const char *name, int dflt, int lo, int hi) {
 	return v < lo ? lo : (v > hi ? hi : v);
 }
 
-static StreamCfg make_cfg(int frames, int src_stride, int smem_limit) {
+static StreamCfg make_cfg(int frames, int src_stride, int smem_limit, int n_cta) {
 	StreamCfg cf{};
 	cf.frames = frames;
 	cf.src_stride = src_stride;
@@ -644,12 +731,17 @@ static StreamCfg make_cfg(int frames, int src_stride, int smem_limit) {
 	cf.stages = env_int("GAS_K2_STAGES", cf.stages, 2, cf.stages);
 	cf.fixed_cost = env_int("GAS_K2_FIXED_COST", 40, 0, 1024);
 	cf.debug = env_int("GAS_K2_DEBUG", 0, 0, 15);
+	cf.vb_shift = vb >= 32 ? 5 : (vb >= 16 ? 4 : 3);
+	cf.inv_grid = 1.0 / (double)n_cta;
+	for (int np = 0; np <= kMaxPairs; np++) {
+		cf.inv_cost[np] = 1.0 / (double)(np + cf.fixed_cost > 0 ? np + cf.fixed_cost : 1);
+	}
 	return cf;
 }
 
 cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, cudaStream_t st) {
 	static const int kSmemLimit = 216 * 1024;
-	StreamCfg cf = make_cfg(frames, src_stride, kSmemLimit);
+	StreamCfg cf = make_cfg(frames, src_stride, kSmemLimit, ctx->num_sms);
 	if (cf.stages < 2) {
 		return cudaErrorInvalidConfiguration;
 	}

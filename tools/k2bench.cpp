@@ -163,9 +163,8 @@ int main(int argc, char **argv) {
 		for (int c = 0; c < 148; c++) {
 			if (h[c * 16] && h[c * 16] < t0) t0 = h[c * 16];
 		}
-		const char *names[16] = { "start", "table+partition", "first data", "last data", "flushed", "", "", "before table loads", "table loaded", "flush: dumped", "", "table in smem", "first indices", "stage 0 issued", "stage 1 issued", "flush pass 1 (dbg 4)" };
+		const char *names[16] = { "start", "table+partition", "first data", "last data", "flushed", "", "", "before table loads", "table loaded", "flush begins", "partition again (dbg 4)", "table in smem", "first indices", "stage 0 issued", "stage 1 issued", "flush pass 1 (dbg 4)" };
 		for (int k = 0; k < 16; k++) {
-			if (k == 10) continue;
 			if (k == 5 || k == 6) continue;
 			double mn = 1e30, mx = 0, av = 0;
 			int n = 0;

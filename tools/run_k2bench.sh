@@ -4,5 +4,6 @@ out=gpurun_out/k2bench.txt; : > $out
 run() { echo "## $*" >> $out; timeout 30 env "$@" >> $out 2>&1 || echo "   (exit $?)" >> $out; }
 B="stdbuf -o0 tools/k2bench"
 run GAS_K2_DEBUG=8 $B 16384 512 0.25 16
-run GAS_K2_DEBUG=8 $B 16384 512 1.0 16
 run GAS_K2_DEBUG=0 $B 16384 512 0.25 16
+run GAS_K2_DEBUG=0 $B 16384 512 1.0 16
+run GAS_K2_DEBUG=0 $B 2048 512 0.25 16
