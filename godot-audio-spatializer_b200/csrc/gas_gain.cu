@@ -1,15 +1,17 @@
 // gas_gain.cu — K1: batched AudioSpatializerInstance3D::calculate_spatialization
 // (reference audio_spatializer_3d.cpp:277-489) + update_spatializer_parameters / get_bus_map
-// (reference audio_spatializer.cpp:258-324).  Eight lanes per emitter: the scalar chain (transform,
-// attenuation, filter gain, doppler) is evaluated redundantly by the eight lanes, the SPCAP speaker gains
-// (one double pow each, the long pole) go one speaker per lane, and every lane stores its own
-// (channel pair, side) element of the volume tables, so table traffic is 32-byte segments and the
-// dependent double-precision chains are short enough to hide behind 8x more resident warps.
+// (reference audio_spatializer.cpp:258-324).  A few lanes per emitter (4 by default): the scalar chain
+// (transform, attenuation, filter gain, doppler) is evaluated redundantly by the lanes of an emitter, the SPCAP
+// speaker gains (one double pow each, the long pole) are dealt across them, and every lane stores its own
+// (channel pair, side) elements of the volume tables.  The kernel is a long dependent chain per emitter
+// (latency-bound, ~12 us whatever the batch size up to a full GPU), so what matters is enough registers to
+// schedule the independent sub-chains side by side (128, no spills) and CTAs small enough to slip in beside
+// the mix kernels of the previous block.
 //
 // Compiled with -fmad=false: the reference mixes float storage with double intermediates (SURVEY Q3,
 // Q8, Q10) and the gains must come out the way a scalar x86-64 build produces them, so no contraction.
 // float transcendentals are evaluated in double and narrowed, which is correctly rounded in practice
-// and therefore agrees with a correctly-rounded libm.  V is small here; cost is irrelevant.
+// and therefore agrees with a correctly-rounded libm.
 #include "gas_internal.h"
 
 #define CMP_EPSILON 0.00001
@@ -133,35 +135,46 @@ __device__ float attenuation_db(const gas_spatializer &s, float volume_db, float
 	return att;
 }
 
-// reference audio_spatializer_3d.cpp:57-98 + :903-938.  Lane `l` of the emitter's 8-lane group (mask gm,
-// first lane gbase) owns speaker l; sums run in speaker order exactly like the reference loop.
+// reference audio_spatializer_3d.cpp:57-98 + :903-938.  Lane `l` of the emitter's NL-lane group (mask gm,
+// first lane gbase) owns speakers l, l + NL, ...; sums run in speaker order exactly like the reference loop.
+template <int NL>
 __device__ void output_vol_surround(unsigned gm, int gbase, int l, const GlobalCfg &g, V3 src, float tightness, float out[4][2]) {
+	constexpr int S = 8 / NL; // speakers per lane
 	const int speaker_mode = g.speaker_mode;
 	const int count = speaker_mode == GAS_SPEAKER_SURROUND_31 ? 3 : (speaker_mode == GAS_SPEAKER_SURROUND_51 ? 5 : (speaker_mode == GAS_SPEAKER_SURROUND_71 ? 7 : 2));
-	float sq = 0.f;
-	if (l < count) {
-		const V3 dl{ g.spk_dir[l][0], g.spk_dir[l][1], g.spk_dir[l][2] };
-		const float eff = g.spk_eff[l]; // :911-915, precomputed per speaker mode
-		// :929-933.  pow(x, 1) and pow(x, 2) are exact in one rounding (x, x * x), which is what a correctly rounded
-		// pow returns: the default 3d_panning_strength / panning_strength (tightness 1) never pays for the general pow
-		const double base1 = 1.0 + (double)dot3(dl, src);
-		const double pw = tightness == 1.0f ? base1 : (tightness == 2.0f ? base1 * base1 : pow(base1, (double)tightness));
-		const float gain = (float)(0.5 * pw / (double)eff);
-		sq = gain * gain;
+	float sq[S];
+#pragma unroll
+	for (int k = 0; k < S; k++) {
+		const int spk = l + k * NL;
+		sq[k] = 0.f;
+		if (spk < count) {
+			const V3 dl{ g.spk_dir[spk][0], g.spk_dir[spk][1], g.spk_dir[spk][2] };
+			const float eff = g.spk_eff[spk]; // :911-915, precomputed per speaker mode
+			// :929-933.  pow(x, 1) and pow(x, 2) are exact in one rounding (x, x * x), which is what a correctly rounded
+			// pow returns: the default 3d_panning_strength / panning_strength (tightness 1) never pays for the general pow
+			const double base1 = 1.0 + (double)dot3(dl, src);
+			const double pw = tightness == 1.0f ? base1 : (tightness == 2.0f ? base1 * base1 : pow(base1, (double)tightness));
+			const float gain = (float)(0.5 * pw / (double)eff);
+			sq[k] = gain * gain;
+		}
 	}
 	float sum = 0.f;
 #pragma unroll
 	for (int i = 0; i < 7; i++) {
-		const float v = __shfl_sync(gm, sq, gbase + i);
+		const float v = NL == 1 ? sq[i % S] : __shfl_sync(gm, sq[i / NL], gbase + (i % NL));
 		if (i < count) {
 			sum += v;
 		}
 	}
-	const float mine = sqrtf(sq / sum); // :935-937
+	float mine[S];
+#pragma unroll
+	for (int k = 0; k < S; k++) {
+		mine[k] = sqrtf(sq[k] / sum); // :935-937
+	}
 	float vol[7];
 #pragma unroll
 	for (int i = 0; i < 7; i++) {
-		const float v = __shfl_sync(gm, mine, gbase + i);
+		const float v = NL == 1 ? mine[i % S] : __shfl_sync(gm, mine[i / NL], gbase + (i % NL));
 		vol[i] = i < count ? v : 0.f;
 	}
 	switch (speaker_mode) {
@@ -194,19 +207,21 @@ __device__ void output_vol_stereo(V3 dir, float pan_strength, float out[4][2]) {
 }
 
 // reference audio_spatializer_3d.cpp:112-121
+template <int NL>
 __device__ void output_vol(unsigned gm, int gbase, int l, const GlobalCfg &g, const gas_spatializer &s, V3 dir, float out[4][2]) {
 	if (g.speaker_mode == GAS_SPEAKER_MODE_STEREO) {
 		output_vol_stereo(dir, g.global_panning * s.panning_strength, out);
 	} else {
 		float tightness = g.global_panning * 2.0f;
 		tightness *= s.panning_strength;
-		output_vol_surround(gm, gbase, l, g, dir, tightness, out);
+		output_vol_surround<NL>(gm, gbase, l, g, dir, tightness, out);
 	}
 }
 
 __device__ __forceinline__ float lerpf(float a, float b, float w) { return a + (b - a) * w; }
 
 // reference audio_spatializer_3d.cpp:154-197
+template <int NL>
 __device__ void reverb_vol(unsigned gm, int gbase, int l, const GlobalCfg &g, const gas_spatializer &s, const gas_emitter &e, const gas_area &a,
 		V3 listener_area_pos, const float direct[4][2], float rev[4][2]) {
 	for (int i = 0; i < 4; i++) {
@@ -224,7 +239,7 @@ __device__ void reverb_vol(unsigned gm, int gbase, int l, const GlobalCfg &g, co
 			V3 rp = listener_area_pos;
 			rp.y = 0.f;
 			rp = norm3(rp);
-			output_vol(gm, gbase, l, g, s, rp, rev);
+			output_vol<NL>(gm, gbase, l, g, s, rp, rev);
 			for (int i = 0; i < chan; i++) {
 				rev[i][0] = lerpf(rev[i][0], cv, attenuation);
 				rev[i][1] = lerpf(rev[i][1], cv, attenuation);
@@ -306,16 +321,18 @@ __device__ __forceinline__ float pick(const float v[4][2], int c, int x) {
 	return r;
 }
 
-constexpr int kGainLanes = 8;
-constexpr int kGainThreads = 256;
-
-__global__ void __launch_bounds__(kGainThreads, 4) k_gain(DevTables t, GlobalCfg g, int n, const gas_emitter *__restrict__ emitters,
+// NL lanes per emitter (8, 4 or 2).  The scalar chain is evaluated redundantly by the NL lanes; the SPCAP speaker gains
+// and the stores are dealt across them (lane l owns elements l, l + NL, ... of the [pair][side] tables).  Fewer lanes
+// = fewer, longer threads: slower on an empty GPU (the chain is latency-bound), but a smaller footprint beside the
+// mix kernels, which is what a step pays for (see launch_gain for the measured shapes).
+template <int NL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_gain(DevTables t, GlobalCfg g, int n, const gas_emitter *__restrict__ emitters,
 		int n_listeners, const gas_listener *__restrict__ listeners, const gas_area *__restrict__ areas, gas_params *__restrict__ out) {
-	const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kGainLanes;
-	const int l = threadIdx.x & 7;
-	const int gbase = threadIdx.x & 24; // first lane of this emitter's group inside the warp
-	const unsigned gm = 0xffu << gbase;
-	const int lc = l >> 1, lx = l & 1;
+	constexpr int S = 8 / NL;
+	const int i = (blockIdx.x * blockDim.x + threadIdx.x) / NL;
+	const int l = threadIdx.x & (NL - 1);
+	const int gbase = threadIdx.x & (32 - NL); // first lane of this emitter's group inside the warp
+	const unsigned gm = ((1u << NL) - 1u) << gbase;
 	if (i >= n) {
 		return;
 	}
@@ -412,7 +429,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(DevTables t, GlobalCfg
 		for (int c = 0; c < 4; c++) {
 			tmp_volume[c][0] = tmp_volume[c][1] = 0.f;
 		}
-		output_vol(gm, gbase, l, g, s, local_pos, tmp_volume); // :391 — un-normalised direction (Q1)
+		output_vol<NL>(gm, gbase, l, g, s, local_pos, tmp_volume); // :391 — un-normalised direction (Q1)
 		for (int c = 0; c < 4; c++) {            // :393-396
 			tmp_volume[c][0] = multiplier * tmp_volume[c][0];
 			tmp_volume[c][1] = multiplier * tmp_volume[c][1];
@@ -420,7 +437,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(DevTables t, GlobalCfg
 			output_volume[c][1] = output_volume[c][1] > tmp_volume[c][1] ? output_volume[c][1] : tmp_volume[c][1];
 		}
 		if (has_area && ap->use_reverb) { // :399-402
-			reverb_vol(gm, gbase, l, g, s, e, *ap, listener_area_pos, tmp_volume, tmp_reverb);
+			reverb_vol<NL>(gm, gbase, l, g, s, e, *ap, listener_area_pos, tmp_volume, tmp_reverb);
 			for (int c = 0; c < 4; c++) {
 				reverb_volume[c][0] = reverb_volume[c][0] > tmp_reverb[c][0] ? reverb_volume[c][0] : tmp_reverb[c][0];
 				reverb_volume[c][1] = reverb_volume[c][1] > tmp_reverb[c][1] ? reverb_volume[c][1] : tmp_reverb[c][1];
@@ -471,26 +488,35 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(DevTables t, GlobalCfg
 			n_bus = 1;
 		}
 	}
-	const float mv = pick(output_volume, lc, lx); // :463
-	const float rv = pick(reverb_volume, lc, lx);
-	const float bv0 = n_bus > 0 ? (slot0_is_reverb ? rv : mv) : 0.f;
-	const float bv1 = n_bus > 1 ? rv : 0.f;
+	float mv[S], bv0[S], bv1[S]; // this lane's elements (pair, side) = ((l + k L) >> 1, (l + k L) & 1)
+#pragma unroll
+	for (int k = 0; k < S; k++) {
+		const int el = l + k * NL;
+		mv[k] = pick(output_volume, el >> 1, el & 1); // :463
+		const float rv = pick(reverb_volume, el >> 1, el & 1);
+		bv0[k] = n_bus > 0 ? (slot0_is_reverb ? rv : mv[k]) : 0.f;
+		bv1[k] = n_bus > 1 ? rv : 0.f;
+	}
 	const bool skip = !in_range_any && was_further; // :466-467
 	__syncwarp(gm); // every lane has read was_further before lane 0 rewrites it
 	if (!skip) {
 		prm.update_parameters = 1;
 	}
-	// set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272), one (pair, side) element per lane
+	// set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272), the (pair, side) elements dealt over the lanes
 #pragma unroll
 	for (int pass = 0; pass < 2; pass++) {
 		gas_params *P = pass == 0 ? &t.inst_params[q] : (out ? &out[i] : nullptr);
 		if (!P) {
 			continue;
 		}
-		P->mix_volumes[lc][lx] = mv;
 #pragma unroll
-		for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
-			P->bus_volumes[k][lc][lx] = k == 0 ? bv0 : (k == 1 ? bv1 : 0.f);
+		for (int k = 0; k < S; k++) {
+			const int el = l + k * NL;
+			P->mix_volumes[el >> 1][el & 1] = mv[k];
+#pragma unroll
+			for (int b = 0; b < GAS_MAX_BUSES_PER_PLAYBACK; b++) {
+				P->bus_volumes[b][el >> 1][el & 1] = b == 0 ? bv0[k] : (b == 1 ? bv1[k] : 0.f);
+			}
 		}
 		if (l == 0) {
 			P->pitch_scale = prm.pitch_scale;
@@ -499,8 +525,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(DevTables t, GlobalCfg
 			P->update_parameters = prm.update_parameters;
 			P->n_bus = n_bus;
 #pragma unroll
-			for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
-				P->bus[k] = k == 0 ? bus0 : (k == 1 ? bus1 : 0);
+			for (int b = 0; b < GAS_MAX_BUSES_PER_PLAYBACK; b++) {
+				P->bus[b] = b == 0 ? bus0 : (b == 1 ? bus1 : 0);
 			}
 		}
 	}
@@ -510,19 +536,23 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(DevTables t, GlobalCfg
 	if (prm.update_parameters && q_active) { // get_bus_map of all proxy channels (audio_spatializer.cpp:274-324)
 		BusDetails *d = &t.inst_cur[q];
 #pragma unroll
-		for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
-			float w = 0.f;
-			if (k < n_bus) {
-				const float bv = k == 0 ? bv0 : bv1;
-				w = mix_channels ? (mv > 0.0f ? bv / mv : 0.f) : mv;
+		for (int k = 0; k < S; k++) {
+			const int el = l + k * NL;
+#pragma unroll
+			for (int b = 0; b < GAS_MAX_BUSES_PER_PLAYBACK; b++) {
+				float w = 0.f;
+				if (b < n_bus) {
+					const float bv = b == 0 ? bv0[k] : bv1[k];
+					w = mix_channels ? (mv[k] > 0.0f ? bv / mv[k] : 0.f) : mv[k];
+				}
+				d->vol[b][el >> 1][el & 1] = w;
 			}
-			d->vol[k][lc][lx] = w;
 		}
 		if (l == 0) {
 			d->n = n_bus;
 #pragma unroll
-			for (int k = 0; k < GAS_MAX_BUSES_PER_PLAYBACK; k++) {
-				d->bus[k] = k == 0 ? (n_bus > 0 ? bus0 : 0) : (k == 1 && n_bus > 1 ? bus1 : 0);
+			for (int b = 0; b < GAS_MAX_BUSES_PER_PLAYBACK; b++) {
+				d->bus[b] = b == 0 ? (n_bus > 0 ? bus0 : 0) : (b == 1 && n_bus > 1 ? bus1 : 0);
 			}
 		}
 	}
@@ -569,7 +599,26 @@ cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_list
 	if (n <= 0) {
 		return cudaSuccess;
 	}
-	k_gain<<<(n * kGainLanes + kGainThreads - 1) / kGainThreads, kGainThreads, 0, st>>>(ctx->t, ctx->g, n, d_em, n_listeners, d_l, d_areas, d_out);
+	// Launch shape, measured inside the mix step on B200 (16384 emitters, the kernel running beside the mix kernels):
+	//   4 lanes x 64-thread CTAs, 128 registers (no spills): 44.7 us / step, 12.3 us alone    <- default
+	//   8 lanes x 64-thread CTAs, 128 registers:             45.0 us / step, 14.4 us alone
+	//   8 lanes x 256-thread CTAs, 64 registers (spills):    50.7 us / step, 15.1 us alone
+	//   2 lanes x 64-thread CTAs:                            49.9 us / step
+	// Small CTAs matter more than anything else: the streaming mix kernel leaves ~17 K registers per SM free, which
+	// two 64 x 128-register CTAs fill, while one 256-thread CTA has to squeeze into 64 registers per thread to get in.
+	static int shape = -1;
+	if (shape < 0) {
+		const char *e = getenv("GAS_K1_SHAPE"); // experiments: 1 = 8 lanes x 256 threads, 2 = 8 lanes x 64 threads
+		shape = e ? atoi(e) : 0;
+	}
+#define GAS_K1_LAUNCH(NL_, T_, M_)                                                                                          \
+	k_gain<NL_, T_, M_><<<(int)(((long long)n * NL_ + T_ - 1) / T_), T_, 0, st>>>(ctx->t, ctx->g, n, d_em, n_listeners, d_l, d_areas, d_out)
+	switch (shape) {
+		case 1: GAS_K1_LAUNCH(8, 256, 4); break;
+		case 2: GAS_K1_LAUNCH(8, 64, 8); break;
+		default: GAS_K1_LAUNCH(4, 64, 8); break;
+	}
+#undef GAS_K1_LAUNCH
 	ctx->launches++;
 	return cudaGetLastError();
 }
