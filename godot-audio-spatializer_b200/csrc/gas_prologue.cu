@@ -1,8 +1,8 @@
 // gas_prologue.cu — per-block prologue (one kernel): turns the current parameters + persistent ramp state
 // into the block's plan (classes, weight rows, voice records) and advances the ramp state.
 //
-// Work is laid out 8 lanes per voice (lane = channel pair * 2 + side), 64 voices per CTA, so that every
-// table access of a voice is one 32-byte segment and nothing lives in local memory:
+// Work is laid out 8 lanes per voice (lane = channel pair * 2 + side), 16 voices per CTA, so that every
+// table access of a voice is one 32-byte segment:
 //   voice part: what process_frames / mix_channel decide before their sample loop (reference
 //       audio_spatializer_3d.cpp:499-523, :562-587, :537-551, :608): ramp end points, filter on/off,
 //       clear-history, target coefficients — plus the AudioServer side of the instance's proxy playbacks
@@ -21,7 +21,9 @@
 namespace {
 
 constexpr int kLanes = 8;          // lanes per voice
-constexpr int kVoicesPerCta = 64;
+// 128-thread CTAs at ~120 registers: measured best inside the step on B200 (64 voices per CTA capped at
+// 64 registers spilled and cost +1.5 us; 8 voices per CTA pays +1 us for the extra class-table atomics)
+constexpr int kVoicesPerCta = 16;
 constexpr int kCtaThreads = kLanes * kVoicesPerCta;
 constexpr int kBigKey = 0x7fffffff;
 
@@ -251,7 +253,7 @@ __device__ __forceinline__ int group_or(unsigned gm, int v) {
 	return v;
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 2) k_prologue(DevTables t, GlobalCfg g, BlockPlan plan, int inst_hwm, int n_voices,
+__global__ void __launch_bounds__(kCtaThreads, 4) k_prologue(DevTables t, GlobalCfg g, BlockPlan plan, int inst_hwm, int n_voices,
 		const gas_voice *__restrict__ voices, int src_rows, float4 *__restrict__ bus, int bus_f4, float4 *__restrict__ rep, int rep_f4,
 		float2 *__restrict__ peaks) {
 	__shared__ unsigned long long s_key[kVoicesPerCta];  // classes met in this CTA
@@ -286,8 +288,8 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_prologue(DevTables t, Global
 		s_parity = blk_n & 1;
 		ticket = atomicAdd(&t.blk[1], 1); // consumed at the very end: nothing waits for this round trip
 	}
-	if (threadIdx.x < GAS_MAX_CLASSES) {
-		s_gkey[threadIdx.x] = plan.cls_key[threadIdx.x];
+	for (int i = threadIdx.x; i < GAS_MAX_CLASSES; i += kCtaThreads) {
+		s_gkey[i] = plan.cls_key[i];
 	}
 	if (threadIdx.x < kVoicesPerCta) {
 		s_key[threadIdx.x] = 0ULL;
