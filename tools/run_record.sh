@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-end record: full bench line, reference arm, ncu launch list and one full capture of K2 (same command, plain run first).
+# Round record, part 1: full bench line, reference arm, ncu launch list (same command, plain run first).
 mkdir -p gpurun_out
 tag=${1:-r01}
 timeout 600 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
@@ -8,7 +8,4 @@ CMD="python bench.py --steps 8 --warmup 3 --no-cpu --no-parity --e2e-steps 4"
 timeout 300 $CMD > gpurun_out/plain_$tag.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_launches_$tag.log 2>&1
 echo "ncu launches rc=$?"
-timeout 300 $CMD > gpurun_out/plain2_$tag.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mix_stream -s 12 -c 2 -f -o gpurun_out/k2_$tag $CMD > gpurun_out/ncu_k2_$tag.log 2>&1
-echo "ncu full rc=$?"
-cat gpurun_out/bench_$tag.json | cut -c1-1800
+cat gpurun_out/bench_$tag.json | cut -c1-2400
