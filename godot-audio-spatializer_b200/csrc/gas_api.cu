@@ -206,7 +206,23 @@ int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_fr
 	prof_close(ctx, pp);
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix));
 	ctx->prologue_pending = true;
-	if (n_voices > 0) {
+	if (n_voices > 0 && ctx->par_voice) {
+		// the voice-parallel kernel on its own stream beside the streaming kernel: both only add into the bus buffers
+		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_voice_fork, ctx->s_mix));
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_voice, ctx->ev_voice_fork, 0));
+		pp = prof_open(ctx, GAS_KERNEL_MIX_VOICE, ctx->s_voice);
+		if (!(ctx->skip & 4)) {
+			GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_voice));
+		}
+		prof_close(ctx, pp);
+		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_voice_join, ctx->s_voice));
+		pp = prof_open(ctx, GAS_KERNEL_MIX_STREAM);
+		if (!(ctx->skip & 2)) {
+			GAS_CUDA(ctx, launch_mix_stream(ctx, d_src, src_stride, frames, d_bus, ctx->s_mix));
+		}
+		prof_close(ctx, pp);
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_voice_join, 0));
+	} else if (n_voices > 0) {
 		// streaming kernel (partial sums into the replica buffers), then the voice-parallel kernel, whose launch
 		// also folds the replicas into the bus buffers
 		pp = prof_open(ctx, GAS_KERNEL_MIX_STREAM);
@@ -335,9 +351,22 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	{
 		const char *e = getenv("GAS_PDL");
 		ctx->pdl = e && atoi(e) != 0;
+		// The voice-parallel kernel needs nothing the streaming kernel produces (both add into the bus buffers with
+		// reductions), so with GAS_K3_PARALLEL=1 it runs beside it on its own stream and K2 adds straight into the bus
+		// buffers (1 replica; more replicas are folded by the K3 launch, which then has to wait for K2).  Measured on
+		// B200: blocks with real K3 work gain 2-15 % (effect chains 191 -> 179 us and 206 -> 186 us, Mode A + filter
+		// 170 -> 145 us); a block whose K3 has nothing to do loses 3 us, because the idle K3 CTAs hold the SMs K2's
+		// one-CTA-per-SM grid is waiting for (41.7 -> 44.9 us; K2 enqueued first is worse: 51 us).  Whether a block
+		// has K3 work is decided on the device (per-voice filter gain), so the host cannot choose per block: off by
+		// default, for the caller to turn on for filter / effect-chain heavy scenes.
+		e = getenv("GAS_K3_PARALLEL");
+		ctx->par_voice = e && atoi(e) != 0;
 		e = getenv("GAS_K2_REPLICAS");
-		ctx->replicas = e ? atoi(e) : 8;
+		ctx->replicas = e ? atoi(e) : (ctx->par_voice ? 1 : 8);
 		ctx->replicas = ctx->replicas < 1 ? 1 : (ctx->replicas > 16 ? 16 : ctx->replicas);
+		if (ctx->replicas > 1) {
+			ctx->par_voice = false;
+		}
 		e = getenv("GAS_K2_SLAB");
 		ctx->use_slab = e ? atoi(e) : 0;
 		e = getenv("GAS_SKIP"); // experiments only: 1 = no prologue, 2 = no streaming kernel, 4 = no voice-parallel kernel
@@ -396,6 +425,9 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_mix, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_gain, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_comm, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&ctx->s_voice, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_voice_fork, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_voice_join, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_mix_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_comm_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) == cudaSuccess;
@@ -454,7 +486,11 @@ void gas_destroy(gas_ctx *ctx) {
 	if (ctx->ev_join) {
 		cudaEventDestroy(ctx->ev_join);
 	}
-	for (cudaEvent_t e : { ctx->ev_mix_done, ctx->ev_comm_done, ctx->ev_join2 }) {
+	if (ctx->s_voice) {
+		cudaStreamSynchronize(ctx->s_voice);
+		cudaStreamDestroy(ctx->s_voice);
+	}
+	for (cudaEvent_t e : { ctx->ev_mix_done, ctx->ev_comm_done, ctx->ev_join2, ctx->ev_voice_fork, ctx->ev_voice_join }) {
 		if (e) {
 			cudaEventDestroy(e);
 		}

@@ -153,6 +153,9 @@ struct gas_ctx {
 	int num_sms = 0;
 	int l2_bytes = 0;
 	cudaStream_t s_mix = nullptr, s_gain = nullptr, s_comm = nullptr; // s_comm: the multi-GPU exchange, beside the next block's mix
+	cudaStream_t s_voice = nullptr; // the voice-parallel kernel of a block, beside its streaming kernel (par_voice)
+	cudaEvent_t ev_voice_fork = nullptr, ev_voice_join = nullptr;
+	bool par_voice = false;
 	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_mix_done = nullptr, ev_comm_done = nullptr, ev_join2 = nullptr;
 	bool mix_pending = false, comm_pending = false;
 	bool gain_pending = false, prologue_pending = false;

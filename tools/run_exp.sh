@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out; : > gpurun_out/exp_summary.txt
-for f in 40 24 12 6 40; do
-  timeout 120 bash tools/exp_bench.sh f$f "GAS_K2_FIXED_COST=$f" > /dev/null
-done
-timeout 120 bash tools/exp_bench.sh st4 "GAS_K2_STAGES=4" > /dev/null
-timeout 120 bash tools/exp_bench.sh rep1 "GAS_K2_REPLICAS=1" > /dev/null
+timeout 120 bash tools/exp_bench.sh par1 "GAS_K3_PARALLEL=1" > /dev/null
+timeout 120 bash tools/exp_bench.sh par0 "GAS_K3_PARALLEL=0" > /dev/null
+timeout 120 bash tools/exp_bench.sh par1b "GAS_K3_PARALLEL=1" > /dev/null
+timeout 120 bash tools/exp_bench.sh par0r1 "GAS_K3_PARALLEL=0 GAS_K2_REPLICAS=1" > /dev/null
