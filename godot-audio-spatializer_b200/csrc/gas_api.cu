@@ -350,7 +350,7 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	refresh_globals(ctx);
 	{
 		const char *e = getenv("GAS_PDL");
-		ctx->pdl = e && atoi(e) != 0;
+		ctx->pdl = e ? atoi(e) : 0;
 		// The voice-parallel kernel needs nothing the streaming kernel produces (both add into the bus buffers with
 		// reductions), so with GAS_K3_PARALLEL=1 it runs beside it on its own stream and K2 adds straight into the bus
 		// buffers (1 replica; more replicas are folded by the K3 launch, which then has to wait for K2).  Measured on

@@ -193,7 +193,7 @@ struct gas_ctx {
 	bool k2_smem_attr_set = false, k3_smem_attr_set = false;
 	int skip = 0;     // GAS_SKIP bits (experiments only)
 	unsigned long long *d_timeline = nullptr; // GAS_K2_DEBUG & 8: per-CTA globaltimer stamps of the last K2 launch
-	bool pdl = false; // GAS_PDL=1: mix-side kernels are launched with programmatic stream serialization
+	int pdl = 0; // GAS_PDL bit mask (experiments): programmatic dependent launch of 1 = prologue, 2 = streaming kernel, 4 = voice-parallel kernel
 	int32_t n_listeners_res = 0, n_areas_res = 0; // resident listeners / areas (gas_listeners_set / gas_areas_set)
 	// CUDA-graph capture
 	bool capturing = false;

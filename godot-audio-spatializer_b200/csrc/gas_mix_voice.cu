@@ -637,16 +637,16 @@ cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_strid
 	cudaError_t e = cudaSuccess;
 	switch (ctx->g.channels) {
 		case 1:
-			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(threads), smem, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
+			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
 			break;
 		case 2:
-			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(threads), smem, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
+			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
 			break;
 		case 3:
-			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(threads), smem, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
+			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
 			break;
 		default:
-			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(threads), smem, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
+			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
 			break;
 	}
 	ctx->launches++;

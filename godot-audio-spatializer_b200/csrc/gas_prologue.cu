@@ -645,7 +645,7 @@ cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voice
 	int work = ctx->inst_hwm > n_voices ? ctx->inst_hwm : n_voices;
 	work = work > 1 ? work : 1;
 	const int blocks = (work + kVoicesPerCta - 1) / kVoicesPerCta;
-	cudaError_t e = gas_launch(k_prologue, dim3(blocks), dim3(kCtaThreads), 0, st, ctx->pdl, ctx->t, ctx->g, ctx->plan, ctx->inst_hwm, n_voices,
+	cudaError_t e = gas_launch(k_prologue, dim3(blocks), dim3(kCtaThreads), 0, st, (ctx->pdl & 1) != 0, ctx->t, ctx->g, ctx->plan, ctx->inst_hwm, n_voices,
 			d_voices, src_rows, (float4 *)d_bus, bus_f4, (float4 *)ctx->d_rep, rep_f4, (float2 *)d_peaks);
 	ctx->launches++;
 	return e;
