@@ -392,6 +392,30 @@ def gpu_arm(args):
     value = world * V * F * K / (ms * 1e-3)
     clocks = sampler.summary(t_wall0, t_wall1)
 
+    if os.environ.get("GAS_K2_DEBUG") and int(os.environ["GAS_K2_DEBUG"]) & 8:
+        # experiments: K2's in-kernel timeline (globaltimer stamps of every CTA) of the last replayed step, to stderr
+        import ctypes
+        torch.cuda.synchronize()
+        fn = m._lib.gas_debug_timeline
+        fn.restype = ctypes.c_void_p
+        fn.argtypes = [ctypes.c_void_p]
+        ptr = fn(m._ctx)
+        if ptr:
+            tl = torch.empty(148 * 16, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+            ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(tl.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(148 * 16 * 8), 3)
+            t = tl.cpu().numpy().reshape(148, 16).astype(np.float64)
+            t0 = t[:, 0][t[:, 0] > 0].min()
+            names = {0: "start", 11: "table in smem", 1: "partition", 12: "first indices", 13: "stage 0 issued", 2: "first data", 3: "last data", 9: "flush begins", 4: "flushed"}
+            for k, nm in names.items():
+                v = (t[:, k][t[:, k] > 0] - t0) * 1e-3
+                if v.size:
+                    print(f"  K2 timeline {nm:16s} min {v.min():7.2f} avg {v.mean():7.2f} max {v.max():7.2f} us", file=sys.stderr)
+            units = t[:, 5]
+            per = (t[:, 3] - t[:, 2]) * 1e-3 / np.maximum(units, 1)
+            for u in sorted(set(units.astype(int))):
+                sel = units == u
+                print(f"  K2 units {u:2d}: n={int(sel.sum()):3d} per-unit {per[sel].mean():.3f} us  last data {((t[sel, 3] - t0) * 1e-3).mean():.2f}  flushed {((t[sel, 4] - t0) * 1e-3).mean():.2f}", file=sys.stderr)
+
     # ---- roofline: per-launch duration of the streaming mix kernel ----------------------------------------------
     # The same steps are captured once more with per-kernel timing on: the graphs then carry event-record nodes
     # around every kernel, so each duration is measured on the device, on the launching stream, as the kernel

@@ -369,6 +369,10 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 		}
 		e = getenv("GAS_K2_SLAB");
 		ctx->use_slab = e ? atoi(e) : 0;
+		e = getenv("GAS_K2_DEBUG"); // the timeline buffer must exist before anything is captured into a graph
+		if (e && (atoi(e) & 8)) {
+			cudaMalloc((void **)&ctx->d_timeline, 256 * 16 * sizeof(unsigned long long));
+		}
 		e = getenv("GAS_SKIP"); // experiments only: 1 = no prologue, 2 = no streaming kernel, 4 = no voice-parallel kernel
 		ctx->skip = e ? atoi(e) : 0;
 	}
