@@ -63,6 +63,54 @@ def test_graph_replay_matches_eager_calls(gas):
         assert ok, f"graph replay differs from eager calls: {nbad} samples, worst {worst:.3e}"
 
 
+def test_voice_kernel_beside_stream_kernel_matches_default_order(gas, monkeypatch):
+    """GAS_K3_PARALLEL=1 (K3 on its own stream beside K2, K2 adding straight into the bus buffers) gives the same block
+    as the default prologue -> K2 -> K3 order, eagerly and in a replayed graph; filtered and unfiltered voices mixed."""
+    import torch
+    V, F, mode, blocks = 512, 256, abi.SPEAKER_SURROUND_71, 3
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, num_buses=2, speaker_mode=mode, mix_rate=48000.0)
+    dev = torch.device("cuda", 0)
+    voices = torch.from_numpy(synth.make_voices(V).view(np.uint8).copy()).to(dev)
+    src = [torch.from_numpy(synth.make_sources(V, F, block=b)).to(dev) for b in range(blocks)]
+    ems = [torch.from_numpy(synth.make_emitters(V, block=b + 1, dt=F / 48000.0, area_fraction=0.5).view(np.uint8).copy()).to(dev)
+           for b in range(blocks)]
+    outs = []
+    for parallel, use_graph in ((False, False), (True, False), (True, True)):
+        if parallel:
+            monkeypatch.setenv("GAS_K3_PARALLEL", "1")
+        else:
+            monkeypatch.delenv("GAS_K3_PARALLEL", raising=False)
+        with gas.Mixer(**cfg) as m:
+            # -6 dB filter attenuation: near voices keep the attenuation filter (K3), far ones fall below 0.001 and stream (K2)
+            listeners, areas = _scene(m, V, F, mode, spat=dict(mix_channel_mode=1, attenuation_filter_db=-6.0))
+            m.listeners_set(listeners)
+            m.areas_set(areas)
+            bus = torch.zeros((2, mode + 1, F, 2), device=dev)
+            got = []
+            for b in range(blocks):
+                def step():
+                    m.mix_block_device(V, voices.data_ptr(), src[b].data_ptr(), V, F, F, bus.data_ptr())
+                    m.gain_compute_device(V, ems[b].data_ptr())
+                if use_graph:
+                    m.capture_begin()
+                    step()
+                    g = m.capture_end()
+                    m.graph_launch(g)
+                    m.sync()
+                    m.graph_destroy(g)
+                else:
+                    step()
+                    m.sync()
+                got.append(bus.cpu().numpy().copy())
+            outs.append(got)
+    monkeypatch.delenv("GAS_K3_PARALLEL", raising=False)
+    for other in outs[1:]:
+        for e, g in zip(outs[0], other):
+            assert e.any()
+            ok, worst, nbad = S.sample_close(g, e)
+            assert ok, f"parallel K3 differs from the default order: {nbad} samples, worst {worst:.3e}"
+
+
 def test_profile_counts_every_kernel(gas):
     V, F = 128, 256
     with gas.Mixer(max_instances=V, max_voices=V, max_frames=F, speaker_mode=abi.SPEAKER_MODE_STEREO) as m:
