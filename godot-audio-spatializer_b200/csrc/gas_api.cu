@@ -367,8 +367,6 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 		if (ctx->replicas > 1) {
 			ctx->par_voice = false;
 		}
-		e = getenv("GAS_K2_SLAB");
-		ctx->use_slab = e ? atoi(e) : 0;
 		e = getenv("GAS_K2_DEBUG"); // the timeline buffer must exist before anything is captured into a graph
 		if (e && (atoi(e) & 8)) {
 			cudaMalloc((void **)&ctx->d_timeline, 256 * 16 * sizeof(unsigned long long));
@@ -412,8 +410,6 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->d_bus, (size_t)GAS_MAX_BUSES * GAS_MAX_CHANNELS_PER_BUS * F);
 	ALLOC(ctx->d_peaks, V);
 	ALLOC(ctx->d_rep, (size_t)16 * GAS_MAX_BUSES * GAS_MAX_CHANNELS_PER_BUS * F);
-	ALLOC(ctx->d_slab, (size_t)ctx->num_sms * cfg->num_buses * GAS_MAX_CHANNELS_PER_BUS * F);
-	ALLOC(ctx->d_slab_mask, (size_t)ctx->num_sms);
 	ALLOC(ctx->d_emitters, I);
 	ALLOC(ctx->d_listeners, (size_t)GAS_MAX_LISTENERS);
 	ALLOC(ctx->d_areas, (size_t)ctx->max_areas);
@@ -471,7 +467,7 @@ void gas_destroy(gas_ctx *ctx) {
 	void *ptrs[] = { ctx->t.spat, ctx->t.inst_spat, ctx->t.inst_params, ctx->t.inst_was_further, ctx->t.inst_active, ctx->t.inst_cur,
 		ctx->t.inst_prev, ctx->t.inst_mode, ctx->t.blk, ctx->t.inst_fx, ctx->plan.sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls_key, ctx->plan.cls_count,
 		ctx->plan.overflow, ctx->plan.list, ctx->plan.k2_rows, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
-		ctx->d_peaks, ctx->d_rep, ctx->d_slab, ctx->d_slab_mask, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
+		ctx->d_peaks, ctx->d_rep, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
 		ctx->d_exchange, ctx->d_comm_seq, ctx->d_comm_ticket };
 	for (void *p : ptrs) {
 		if (p) {

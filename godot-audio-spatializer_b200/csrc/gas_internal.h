@@ -168,10 +168,6 @@ struct gas_ctx {
 	gas_frame *d_peaks = nullptr;
 	gas_frame *d_rep = nullptr; // [replicas][num_buses][channels][frames]: K2 partial sums, combined by the K3 launch
 	int replicas = 8;           // GAS_K2_REPLICAS (1 = K2 adds straight into the bus buffers)
-	gas_frame *d_slab = nullptr;         // [num_sms][num_buses][channels][frames]: one private partial-sum slab per K2 CTA
-	unsigned long long *d_slab_mask = nullptr; // [num_sms] bit (bus * channels + pair) set <=> the CTA wrote that row of its slab
-	int use_slab = 0;                    // GAS_K2_SLAB=1: plain stores into private slabs instead of atomics into the replicas (measured slower)
-	int slab_ctas = 0;                   // CTAs of the last K2 launch when it used slabs, else 0
 	gas_emitter *d_emitters = nullptr;
 	gas_listener *d_listeners = nullptr;
 	gas_area *d_areas = nullptr;

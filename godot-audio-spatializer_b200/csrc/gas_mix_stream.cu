@@ -757,7 +757,6 @@ cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stri
 	// launch folds the replicas into d_bus.
 	float *target = ctx->replicas > 1 ? (float *)ctx->d_rep : (float *)d_bus;
 	const int rep_stride = ctx->replicas > 1 ? gas_bus_f4(ctx, frames) * 4 : 0; // floats
-	ctx->slab_ctas = 0;
 	if (cf.debug & 8) {
 		if (!ctx->d_timeline) {
 			cudaMalloc((void **)&ctx->d_timeline, 256 * 16 * sizeof(unsigned long long));

@@ -12,7 +12,7 @@
 // voices of the warp are summed with shuffles and the result is added to a CTA-wide accumulation tile in
 // shared memory (the whole bus layout of the block, explicit red.shared); the CTA adds its tile to the bus
 // buffers once, with one vector reduction per 16 bytes.  The launch also folds the streaming kernel's partial
-// sums (replicas or slabs) into the bus buffers, so it runs every block.
+// sums (replicas) into the bus buffers, so it runs every block.
 //
 // Sends are processed two at a time; a voice with more than two sends (bus transitions) is run in
 // several passes from the same initial state — every pass recomputes bit-identical samples, only the
@@ -450,55 +450,14 @@ __device__ void voice_chunk_s(const DevTables &t, const ChunkArgs &a, const gas_
 template <int C>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t, GlobalCfg g, BlockPlan plan,
 		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks,
-		const float4 *__restrict__ rep, int bus_f4, int replicas, const float4 *__restrict__ slab,
-		const unsigned long long *__restrict__ slab_mask, int slab_ctas, int tile_floats) {
+		const float4 *__restrict__ rep, int bus_f4, int replicas, int tile_floats) {
 	extern __shared__ __align__(16) float s_tile[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ int s_ncls;
 	GAS_GRID_DEP_WAIT();
 	GAS_GRID_DEP_LAUNCH();
 	// fold the streaming kernel's partial sums into the bus buffers: one vector reduction per 16 bytes
-	if (slab_ctas > 0) {
-		// private slabs: 8 lanes share one output element, each sums every 8th CTA's slab where the row was written
-		const int i = blockIdx.x * blockDim.x + threadIdx.x;
-		const int idx = i >> 3, part = i & 7;
-		const bool on = idx < bus_f4;
-		const int r = on ? idx / (F / 2) : 0;
-		float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-		if (on) {
-			// every slab is read (they are allocated, unwritten rows hold stale finite-or-not bits that the
-			// mask discards), so the loads of a lane are independent and in flight together
-			constexpr int kPer = 24; // up to 192 CTAs
-			float4 b[kPer];
-			unsigned long long m[kPer];
-#pragma unroll
-			for (int k = 0; k < kPer; k++) {
-				const int cta = part + 8 * k;
-				const bool in = cta < slab_ctas;
-				m[k] = in ? slab_mask[cta] : 0ULL;
-				b[k] = in ? slab[(size_t)cta * bus_f4 + idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-			}
-#pragma unroll
-			for (int k = 0; k < kPer; k++) {
-				if ((m[k] >> r) & 1ULL) {
-					a.x += b[k].x;
-					a.y += b[k].y;
-					a.z += b[k].z;
-					a.w += b[k].w;
-				}
-			}
-		}
-#pragma unroll
-		for (int d = 1; d < 8; d <<= 1) {
-			a.x += __shfl_xor_sync(kFull, a.x, d);
-			a.y += __shfl_xor_sync(kFull, a.y, d);
-			a.z += __shfl_xor_sync(kFull, a.z, d);
-			a.w += __shfl_xor_sync(kFull, a.w, d);
-		}
-		if (on && part == 0) {
-			asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(bus + (size_t)idx * 4), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
-		}
-	} else if (replicas > 1) {
+	if (replicas > 1) {
 		const int i = blockIdx.x * blockDim.x + threadIdx.x;
 		if (i < bus_f4) {
 			float4 a = rep[i];
@@ -618,7 +577,7 @@ cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_strid
 	const int bus_f4 = gas_bus_f4(ctx, frames);
 	const int threads = kWarpsPerCta * 32;
 	int grid = ctx->num_sms * 2; // two CTAs per SM (128 registers): many chunks per CTA make the shared-memory tile pay
-	const int fold_threads = ctx->slab_ctas > 0 ? bus_f4 * 8 : bus_f4;
+	const int fold_threads = bus_f4;
 	if (grid * threads < fold_threads) {
 		grid = (fold_threads + threads - 1) / threads;
 	}
@@ -637,16 +596,16 @@ cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_strid
 	cudaError_t e = cudaSuccess;
 	switch (ctx->g.channels) {
 		case 1:
-			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
+			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats);
 			break;
 		case 2:
-			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
+			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats);
 			break;
 		case 3:
-			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
+			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats);
 			break;
 		default:
-			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, (const float4 *)ctx->d_slab, ctx->d_slab_mask, ctx->slab_ctas, tile_floats);
+			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats);
 			break;
 	}
 	ctx->launches++;
