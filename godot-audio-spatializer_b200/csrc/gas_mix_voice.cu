@@ -460,13 +460,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	if (replicas > 1) {
 		const int i = blockIdx.x * blockDim.x + threadIdx.x;
 		if (i < bus_f4) {
-			float4 a = rep[i];
-			for (int r = 1; r < replicas; r++) {
-				const float4 b = rep[(size_t)r * bus_f4 + i];
-				a.x += b.x;
-				a.y += b.y;
-				a.z += b.z;
-				a.w += b.w;
+			// all replicas requested before any is added: a rolled loop would pay one L2 round trip per replica
+			float4 v[16];
+#pragma unroll
+			for (int r = 0; r < 16; r++) {
+				v[r] = r < replicas ? __ldcg(rep + (size_t)r * bus_f4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+			float4 a = v[0];
+#pragma unroll
+			for (int r = 1; r < 16; r++) {
+				a.x += v[r].x;
+				a.y += v[r].y;
+				a.z += v[r].z;
+				a.w += v[r].w;
 			}
 			asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(bus + (size_t)i * 4), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
 		}
