@@ -25,7 +25,9 @@ __device__ __forceinline__ float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y
 __device__ __forceinline__ float len3(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
 __device__ __forceinline__ V3 sub3(V3 a, V3 b) { return V3{ a.x - b.x, a.y - b.y, a.z - b.z }; }
 __device__ __forceinline__ V3 mul3(V3 a, float s) { return V3{ a.x * s, a.y * s, a.z * s }; }
-__device__ __forceinline__ V3 norm3(V3 a) { // upstream Vector3::normalized
+// out of line (like the double transcendentals below): the kernel runs once per thread straight through ~70 KB of code,
+// and its instruction-fetch stalls shrink with every call site that shares one copy
+__device__ __noinline__ V3 norm3(V3 a) { // upstream Vector3::normalized
 	float l2 = a.x * a.x + a.y * a.y + a.z * a.z;
 	if (l2 == 0.0f) {
 		return V3{ 0.f, 0.f, 0.f };
@@ -104,11 +106,15 @@ __device__ Xf load_xf(const gas_listener &l) {
 }
 
 // upstream Math::db_to_linear(float) / linear_to_db(double)
-__device__ __forceinline__ float db_to_linear_f(float db) {
+__device__ __noinline__ float db_to_linear_f(float db) {
 	float a = db * (float)0.11512925464970228420089957273422;
 	return (float)exp((double)a);
 }
-__device__ __forceinline__ double linear_to_db_d(double lin) { return log(lin) * 8.6858896380650365530225783783321; }
+__device__ __noinline__ double log_d(double x) { return log(x); }
+__device__ __noinline__ double pow_d(double a, double b) { return pow(a, b); }
+__device__ __noinline__ double acos_d(double x) { return acos(x); }
+__device__ __noinline__ double log2_d(double x) { return log2(x); }
+__device__ __forceinline__ double linear_to_db_d(double lin) { return log_d(lin) * 8.6858896380650365530225783783321; }
 
 // reference audio_spatializer_3d.cpp:123-151
 __device__ float attenuation_db(const gas_spatializer &s, float volume_db, float max_db, float dist) {
@@ -123,7 +129,7 @@ __device__ float attenuation_db(const gas_spatializer &s, float volume_db, float
 			att = (float)linear_to_db_d(1.0 / ((double)d + CMP_EPSILON));
 		} break;
 		case GAS_ATTENUATION_LOGARITHMIC:
-			att = (float)(-20.0 * log((double)(dist / s.unit_size) + CMP_EPSILON));
+			att = (float)(-20.0 * log_d((double)(dist / s.unit_size) + CMP_EPSILON));
 			break;
 		default:
 			break;
@@ -153,7 +159,7 @@ __device__ void output_vol_surround(unsigned gm, int gbase, int l, const GlobalC
 			// :929-933.  pow(x, 1) and pow(x, 2) are exact in one rounding (x, x * x), which is what a correctly rounded
 			// pow returns: the default 3d_panning_strength / panning_strength (tightness 1) never pays for the general pow
 			const double base1 = 1.0 + (double)dot3(dl, src);
-			const double pw = tightness == 1.0f ? base1 : (tightness == 2.0f ? base1 * base1 : pow(base1, (double)tightness));
+			const double pw = tightness == 1.0f ? base1 : (tightness == 2.0f ? base1 * base1 : pow_d(base1, (double)tightness));
 			const float gain = (float)(0.5 * pw / (double)eff);
 			sq[k] = gain * gain;
 		}
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gain(DevTables t, GlobalCfg g
 		if (s.emission_angle_enabled) { // :378-385
 			V3 listenertopos = sub3(global_pos, V3{ L.origin[0], L.origin[1], L.origin[2] });
 			float c = dot3(norm3(listenertopos), norm3(V3{ e.basis_z[0], e.basis_z[1], e.basis_z[2] }));
-			float ac = c < -1.0f ? (float)3.14159265358979323846 : (c > 1.0f ? 0.0f : (float)acos((double)c));
+			float ac = c < -1.0f ? (float)3.14159265358979323846 : (c > 1.0f ? 0.0f : (float)acos_d((double)c));
 			float angle = ac * (float)(180.0 / 3.14159265358979323846);
 			if (angle > s.emission_angle) {
 				db_att -= -s.emission_angle_filter_attenuation_db;
@@ -457,13 +463,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gain(DevTables t, GlobalCfg g
 					weight = weight > tmp_volume[c][0] ? weight : tmp_volume[c][0];
 					weight = weight > tmp_volume[c][1] ? weight : tmp_volume[c][1];
 				}
-				log_pitch_scale += weight * (float)log2((double)dps);
+				log_pitch_scale += weight * (float)log2_d((double)dps);
 				log_pitch_weight += weight;
 			}
 		}
 	}
 	if (log_pitch_weight > 0.f) { // :430-434
-		prm.pitch_scale = (float)pow(2.0, (double)(log_pitch_scale / log_pitch_weight));
+		prm.pitch_scale = (float)pow_d(2.0, (double)(log_pitch_scale / log_pitch_weight));
 	} else {
 		prm.pitch_scale = e.pitch_scale;
 	}
