@@ -183,6 +183,51 @@ def test_speaker_mode_and_mix_rate_change_at_run_time(gas, orc):
         assert ok and np.array_equal(S.routing(bg), S.routing(bw)), f"{nbad} samples, worst {worst:.3e}"
 
 
+def test_many_routing_classes_match_the_oracle(gas, orc):
+    """78 distinct streaming classes (12 buses: 66 two-bus combinations + 12 single-bus ones), several voices each, two blocks
+    (the second one ramps from the first one's volumes): more classes than the streaming kernel's one-class-per-lane partition
+    handles, so its fallback path is what gets compared with the oracle here."""
+    B, F, per = 12, 128, 5
+    combos = [(a, b) for a in range(B) for b in range(a + 1, B)] + [(a, a) for a in range(B)]
+    V = len(combos) * per
+    ids = np.arange(V, dtype=np.int32)
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, num_buses=B, speaker_mode=abi.SPEAKER_MODE_STEREO, mix_rate=48000.0)
+    rng = np.random.default_rng(7)
+
+    def params(block):
+        p = np.zeros(V, dtype=abi.params)
+        p["mix_volumes"][:, 0, :] = 0.25 + 0.5 * rng.random((V, 2)).astype(np.float32)
+        p["pitch_scale"], p["update_parameters"] = 1.0, 1
+        for k in range(V):
+            a, b = combos[k // per]
+            p["n_bus"][k] = 1 if a == b else 2
+            p["bus"][k, 0], p["bus"][k, 1] = a, b
+            p["bus_volumes"][k, 0, 0, :] = 0.5 - 0.1 * block
+            p["bus_volumes"][k, 1, 0, :] = 0.25 + 0.1 * block
+        return p
+
+    ps = [params(b) for b in range(2)]
+    voices = synth.make_voices(V)
+    outs = []
+    for make in (lambda: gas.Mixer(**cfg), lambda: orc.OracleMixer(**cfg)):
+        with make() as m:
+            m.spatializer_set(0, abi.spatializer_defaults(mix_channel_mode=1))
+            m.instance_init(ids, 0)
+            m.params_set(ids, ps[0])
+            m.instance_start(ids)
+            m.voice_init(ids)
+            got = []
+            for b in range(2):
+                if b:
+                    m.params_set(ids, ps[b])
+                got.append(m.mix_block(voices, synth.make_sources(V, F, block=b), F, want_peaks=False)[0])
+            outs.append(got)
+    for g, e in zip(*outs):
+        assert e.any()
+        ok, worst, nbad = S.sample_close(g, e)
+        assert ok, f"{nbad} samples differ from the oracle, worst {worst:.3e}"
+
+
 def test_class_table_overflow_is_reported(gas):
     """More distinct routing classes than the plan has slots (128): gas_mix_block says so instead of returning a
     silently incomplete mix.  16 buses give 120 two-bus combinations + 16 single-bus ones."""

@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out; : > gpurun_out/exp_summary.txt
-timeout 120 bash tools/exp_bench.sh noinl "" > /dev/null
-timeout 120 bash tools/exp_bench.sh noinl_alone "GAS_SKIP=7" > /dev/null
-timeout 120 bash tools/exp_bench.sh noinl2 "" > /dev/null
+for p in 0 2 0 2 6 0 2; do
+timeout 120 bash tools/exp_bench.sh pdl$p "GAS_PDL=$p" > /dev/null
+done
