@@ -452,6 +452,9 @@ def gpu_arm(args):
                 "kernel": "k_mix_stream (K2)", "us_per_launch": k2_us, "algorithmic_bytes_per_launch": bytes_launch,
                 "peak_source": peak_src, "timing": "CUDA event-record nodes around the kernel inside the replayed step graph",
                 "step_frac_of_hbm_peak": (bytes_launch / (ms * 1e-3 / K) / 1e9) / peak,
+                "event_pair_overhead_us": 1e3 * prof["none"][0] / max(1, prof["none"][1]),
+                "event_pair_note": "what an event-record pair with nothing between its records reads in the same graph; us_per_launch and "
+                                   "frac above are the raw readings and include it",
                 "alone": {"note": "same kernel in the same graph without K1 running beside it on the gain stream",
                           "us_per_launch": 1e3 * prof_alone["mix_stream"][0] / max(1, prof_alone["mix_stream"][1]),
                           "frac": bytes_launch / (1e3 * prof_alone["mix_stream"][0] / max(1, prof_alone["mix_stream"][1]) * 1e-6) / 1e9 / peak},

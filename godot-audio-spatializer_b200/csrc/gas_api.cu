@@ -204,6 +204,8 @@ int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_fr
 		GAS_CUDA(ctx, launch_prologue(ctx, n_voices, d_voices, src_rows, frames, d_bus, d_peaks, ctx->s_mix));
 	}
 	prof_close(ctx, pp);
+	pp = prof_open(ctx, GAS_KERNEL_NONE); // the timer's own reading: a pair with nothing between its two records
+	prof_close(ctx, pp);
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix));
 	ctx->prologue_pending = true;
 	if (n_voices > 0 && ctx->par_voice) {

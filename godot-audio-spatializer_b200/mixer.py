@@ -159,12 +159,13 @@ class Mixer:
         self._ck(self._lib.gas_profile_enable(self._ctx, 1 if on else 0))
 
     def profile_read(self):
-        """{kind: (total_ms, launches)} for prologue / mix_stream (K2) / mix_voice (K3)."""
-        ms = (C.c_double * 4)()
-        n = (C.c_uint64 * 4)()
+        """{kind: (total_ms, launches)} for prologue / mix_stream (K2) / mix_voice (K3) / gain (K1) / none (an event pair
+        around nothing, once per mix block: what the timer itself reads)."""
+        ms = (C.c_double * 5)()
+        n = (C.c_uint64 * 5)()
         self._ck(self._lib.gas_profile_read(self._ctx, ms, n))
-        names = ("prologue", "mix_stream", "mix_voice", "gain")
-        return {names[k]: (float(ms[k]), int(n[k])) for k in range(4)}
+        names = ("prologue", "mix_stream", "mix_voice", "gain", "none")
+        return {names[k]: (float(ms[k]), int(n[k])) for k in range(5)}
 
     def params_set(self, instances, params):
         """set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272, :558-564)."""

@@ -365,7 +365,9 @@ typedef enum gas_kernel_kind {
 	GAS_KERNEL_MIX_STREAM = 1, /* K2 */
 	GAS_KERNEL_MIX_VOICE = 2,  /* K3 */
 	GAS_KERNEL_GAIN = 3,       /* K1 (timed on the gain stream) */
-	GAS_KERNEL_KINDS = 4
+	GAS_KERNEL_NONE = 4,       /* an event pair around nothing, recorded once per mix block right after the prologue's:
+	                              what the timer itself reads inside the same graph / stream (to be subtracted by the reader) */
+	GAS_KERNEL_KINDS = 5
 } gas_kernel_kind;
 GAS_API int gas_profile_enable(gas_ctx *ctx, int32_t on);
 GAS_API int gas_profile_read(gas_ctx *ctx, double ms_out[GAS_KERNEL_KINDS], uint64_t launches_out[GAS_KERNEL_KINDS]);

@@ -121,9 +121,10 @@ def test_profile_counts_every_kernel(gas):
             m.mix_block(synth.make_voices(V), src, F, want_peaks=False)
         prof = m.profile_read()
         m.profile_enable(False)
-    for kind in ("prologue", "mix_stream", "mix_voice"):
+    for kind in ("prologue", "mix_stream", "mix_voice", "none"):
         ms, n = prof[kind]
         assert n == 3 and ms > 0.0, f"{kind}: {n} launches, {ms} ms"
+    assert prof["none"][0] < prof["mix_stream"][0]  # the empty pair (the timer's own reading) is the smallest of them
 
 
 def test_voice_state_export_import_resumes_bit_identically(gas):
