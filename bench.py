@@ -396,6 +396,18 @@ def gpu_arm(args):
         # experiments: K2's in-kernel timeline (globaltimer stamps of every CTA) of the last replayed step, to stderr
         import ctypes
         torch.cuda.synchronize()
+        keys = (ctypes.c_uint64 * 128)()
+        counts = (ctypes.c_int32 * 256)()
+        if m._lib.gas_debug_classes(m._ctx, keys, counts) == 0:
+            for i in range(128):
+                k = keys[i]
+                if k and (counts[i] or counts[128 + i]):
+                    quad = (k >> 32) & 0xff
+                    n_send = (k >> 8) & 0xff
+                    flags = (k >> 4) & 0xf
+                    groups = 1 if (flags & 2) and n_send >= 2 else n_send  # CLS_SHARED
+                    print(f"  class slot {i}: path {k & 3} mode {(k >> 2) & 3} flags {flags:#x} sends {n_send} mask {(k >> 16) & 0xffff:#x} "
+                          f"quad {quad:#x} counts {counts[i]}/{counts[128 + i]}", file=sys.stderr)
         fn = m._lib.gas_debug_timeline
         fn.restype = ctypes.c_void_p
         fn.argtypes = [ctypes.c_void_p]

@@ -899,6 +899,17 @@ void *gas_gain_stream(gas_ctx *ctx) { return ctx ? (void *)ctx->s_gain : nullptr
 uint64_t gas_kernel_launches(const gas_ctx *ctx) { return ctx ? ctx->launches : 0; }
 // experiments only (not in gas.h): device pointer of the K2 timeline buffer, [CTA][8] uint64
 extern "C" GAS_API void *gas_debug_timeline(gas_ctx *ctx) { return ctx ? (void *)ctx->d_timeline : nullptr; }
+// experiments only (not in gas.h): the routing-class table after a synchronise — keys[128], counts[2][128] (by block parity)
+extern "C" GAS_API int gas_debug_classes(gas_ctx *ctx, unsigned long long *keys, int32_t *counts) {
+	if (!ctx || !keys || !counts) {
+		return GAS_ERR_INVALID;
+	}
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	cudaMemcpy(keys, ctx->plan.cls_key, GAS_MAX_CLASSES * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+	cudaMemcpy(counts, ctx->plan.cls_count, 2 * GAS_MAX_CLASSES * sizeof(int32_t), cudaMemcpyDeviceToHost);
+	return GAS_OK;
+}
 
 int gas_voice_state_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_voice_state *out) {
 	{

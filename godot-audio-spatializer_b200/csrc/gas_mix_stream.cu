@@ -62,7 +62,7 @@ struct StreamCfg {
 	int vb_shift;      // log2(vb)
 	double inv_grid;   // 1 / CTAs
 	double inv_cost[kMaxPairs + 1]; // 1 / (accumulators + fixed_cost)
-	int debug;         // GAS_K2_DEBUG bits (experiments only): 1 = skip the bus reductions, 2 = skip the FMAs, 8 = record a timeline
+	int debug;         // GAS_K2_DEBUG bits (experiments only): 1 = skip the bus reductions, 2 = skip the FMAs, 4 = skip the copies, 8 = record a timeline
 	unsigned long long *timeline; // [CTA][16] globaltimer stamps (debug & 8), see tools/k2bench.cpp for the slots
 };
 
@@ -345,6 +345,7 @@ struct ConsumerCtx {
 	int stage;
 	uint32_t phase;
 	unsigned long long *tl;
+	bool tl_first;
 };
 
 // One row group (rows R0, R0+1 and, when `quad`, R0+2 of a class with R rows) of one run: evaluate the
@@ -405,8 +406,9 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		const unsigned char *sx = cc.smem + (size_t)cc.stage * cf.stage_bytes;
 		const unsigned char *sw = sx + cf.x_bytes;
 		mbar_wait(&cc.full[cc.stage], cc.phase);
-		if (cc.tl && cc.tl[2] == 0ULL) {
+		if (cc.tl && !cc.tl_first) { // (a register flag: reading the stamp back from global memory every stage cost 0.3 us per stage)
 			cc.tl[2] = gtime();
+			cc.tl_first = true;
 		}
 		if (mine && !(cf.debug & 2)) {
 			// the loads of several voices are issued before their FMAs (4 voices for the small classes, 2 for the
@@ -632,14 +634,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 			unsigned char *sx = ring + (size_t)stage * cf.stage_bytes;
 			unsigned char *sw = sx + cf.x_bytes;
 			mbar_wait(&s_empty[stage], phase ^ 1u);
+			const bool no_copy = (cf.debug & 4) != 0; // experiment: arm the stage without copying anything into it
 			if (lane == 0) {
-				mbar_arrive_expect_tx(&s_full[stage], row_bytes * (uint32_t)nv + w_bytes);
-				bulk_g2s(sw, plan.k2_rows + (size_t)ci.slot * maxv * GAS_K2_ROW_FLOATS + (size_t)v0 * nf, w_bytes, &s_full[stage]);
+				mbar_arrive_expect_tx(&s_full[stage], no_copy ? 0u : row_bytes * (uint32_t)nv + w_bytes);
+				if (!no_copy) {
+					bulk_g2s(sw, plan.k2_rows + (size_t)ci.slot * maxv * GAS_K2_ROW_FLOATS + (size_t)v0 * nf, w_bytes, &s_full[stage]);
+				}
 			}
 			__syncwarp();
 			{
 				const int v = lane - (seq - cur.first_seq) * cf.vb; // this lane's voice inside the stage
-				if (v >= 0 && v < nv) {
+				if (v >= 0 && v < nv && !no_copy) {
 					bulk_g2s(sx + (size_t)v * row_bytes, src + (size_t)cur.val.y * cf.src_stride + (size_t)it.tile * cf.tile_frames, row_bytes,
 							&s_full[stage]);
 				}
@@ -660,6 +665,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		cc.smem = ring;
 		cc.tid = tid;
 		cc.tl = tl;
+		cc.tl_first = false;
 		cc.full = s_full;
 		cc.empty = s_empty;
 		cc.cls = s_cls;
@@ -719,7 +725,7 @@ static StreamCfg make_cfg(int frames, int src_stride, int smem_limit, int n_cta)
 	if (cf.groups < 1) {
 		cf.groups = 1;
 	}
-	int vb = 32768 / (cf.tile_frames * 8);
+	int vb = 32768 / (cf.tile_frames * 8); // 32 KB stages (64 KB stages, i.e. 16 voices: measured +1.3 us per block, coarser partition)
 	vb = vb >= 32 ? 32 : (vb >= 16 ? 16 : 8); // a divisor of the warp size (index prefetch blocks)
 	cf.vb = vb;
 	cf.x_bytes = vb * cf.tile_frames * 8;
