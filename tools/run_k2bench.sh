@@ -3,8 +3,8 @@ mkdir -p gpurun_out
 out=gpurun_out/k2bench.txt; : > $out
 run() { echo "## $*" >> $out; timeout 30 env "$@" >> $out 2>&1 || echo "   (exit $?)" >> $out; }
 B="stdbuf -o0 tools/k2bench"
-run GAS_K2_STAGE_BYTES=32768 $B 16384 512 0.25 16
-run GAS_K2_STAGE_BYTES=65536 $B 16384 512 0.25 16
-run GAS_K2_STAGE_BYTES=32768 $B 16384 512 1.0 16
-run GAS_K2_STAGE_BYTES=65536 $B 16384 512 1.0 16
-run GAS_K2_STAGE_BYTES=65536 GAS_K2_DEBUG=8 GAS_K2_DUMP=1 $B 16384 512 0.25 16
+run X=1 $B 16384 512 0.25 16
+run X=1 $B 16384 512 1.0 16
+run X=1 $B 16384 512 0.0 16
+run GAS_K2_DEBUG=12 GAS_K2_DUMP=1 $B 16384 512 1.0 16
+run GAS_K2_DEBUG=8 GAS_K2_DUMP=1 $B 16384 512 0.25 16
