@@ -41,8 +41,7 @@ namespace {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = kConsumerThreads + 128; // two consumer warpgroups + the producer's (one live warp, three that only hand their registers over)
-constexpr int kLiveThreads = kConsumerThreads + 32;
+constexpr int kThreads = kConsumerThreads + 32;
 constexpr int kTileFrames = 512;       // frames per tile: 2 per consumer thread
 constexpr int kMaxPairs = GAS_K2_MAX_ROWS * GAS_MAX_CHANNELS_PER_BUS; // 24 (L,R) weight pairs per voice
 constexpr int kMaxStages = 8;
@@ -401,13 +400,9 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 	const int tile_w = min(cf.tile_frames, cf.frames - tile * cf.tile_frames);
 	const int row_bytes = tile_w * 8;
 	const bool mine = cc.worker && cc.slot * 2 < tile_w;
-	// The run is a counted loop: the consecutive batches of this (class, tile) that belong to the CTA.  Every stage but
-	// the last holds vb voices; the iterator is advanced once, after the loop (the per-stage bookkeeping of the consumers
-	// is not hidden behind anything: it adds to the FMA time of every stage, so it is kept to the bare hand-shake).
-	const int n_run = min(it.remaining, it.nb - it.batch);
-	const int nv_last = min(cf.vb, ci.count - (it.batch + n_run - 1) * cf.vb);
-	for (int rs = 0; rs < n_run; rs++) {
-		const int nv = rs == n_run - 1 ? nv_last : cf.vb;
+	do {
+		const int v0 = it.batch * cf.vb;
+		const int nv = min(cf.vb, ci.count - v0);
 		const unsigned char *sx = cc.smem + (size_t)cc.stage * cf.stage_bytes;
 		const unsigned char *sw = sx + cf.x_bytes;
 		mbar_wait(&cc.full[cc.stage], cc.phase);
@@ -475,10 +470,8 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 			cc.stage = 0;
 			cc.phase ^= 1u;
 		}
-	}
-	it.remaining -= n_run - 1; // past the run: n_run - 1 steps inside the row of batches, the last one may leave it
-	it.batch += n_run - 1;
-	unit_iter_next(it, cc.cls, cf);
+		unit_iter_next(it, cc.cls, cf);
+	} while (it.remaining > 0 && it.cid == cid && it.tile == tile);
 	if (cc.tl) {
 		cc.tl[3] = gtime();
 	}
@@ -545,16 +538,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 	// Start-up runs on the producer warp alone, with nothing but its own dependent loads in the way of the first
 	// copy: class table (one round of loads) -> partition -> first source-row indices -> copies.  The consumer warps
 	// wait on a named barrier for the table and their iterator; they have nothing to do before data lands anyway.
-	// Register hand-over (setmaxnreg): the launch gives every thread 168 registers; the producer's warpgroup goes down to
-	// 72 (warps 9-11 exist only for that and leave at once, the producer itself after its start-up) and the two consumer
-	// warpgroups go up to 208.
-	if (warp > kConsumerWarps) {
-		asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-		return;
-	}
-	if (warp < kConsumerWarps) {
-		asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-	}
 	UnitIter it;
 	if (warp == kConsumerWarps) {
 		if (tlp) {
@@ -608,14 +591,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 			s_it = it;
 		}
 		__syncwarp();
-		asm volatile("bar.arrive 2, %0;" ::"n"(kLiveThreads) : "memory");
-		asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+		asm volatile("bar.arrive 2, %0;" ::"n"(kThreads) : "memory");
 		if (tlp) {
 			tlp[1] = gtime();
 			tlp[5] = (unsigned long long)it.remaining;
 		}
 	} else {
-		asm volatile("bar.sync 2, %0;" ::"n"(kLiveThreads) : "memory");
+		asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
 		it = s_it;
 		GAS_GRID_DEP_LAUNCH();
 	}
