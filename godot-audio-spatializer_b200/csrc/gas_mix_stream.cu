@@ -348,6 +348,61 @@ struct ConsumerCtx {
 	bool tl_first;
 };
 
+// The FMAs of one stage for one thread: `n` voices spaced `step` apart (rows `row_bytes` apart starting at xp, weight
+// records NP*8 bytes apart starting at wp).  The loads of several voices are issued before their FMAs (4 voices for
+// the small classes, 2 for the large ones: the register budget): two consumer warps per scheduler cannot hide the
+// shared-memory latency of one voice at a time.  STATIC: step 1 and 4 KB rows, every offset an immediate.
+template <int NP, bool STATIC>
+__device__ __forceinline__ void voice_loop(float2 (&acc)[NP][2], const unsigned char *xp, const unsigned char *wp, int n, int step, int row_bytes) {
+	constexpr int U = NP <= 10 ? 4 : 2;
+	const int xs = STATIC ? kTileFrames * 8 : step * row_bytes; // bytes between consecutive voices of this thread
+	const int ws = STATIC ? NP * 8 : step * (NP * 8);
+	int left = STATIC ? n : (n + step - 1) / step; // voices this thread still has to do
+	for (; left >= U; left -= U, xp += U * xs, wp += U * ws) {
+		float4 x[U];
+		float4 w[U][(NP + 1) / 2];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			x[u] = *reinterpret_cast<const float4 *>(xp + u * xs);
+			const unsigned char *wv = wp + u * ws;
+#pragma unroll
+			for (int p = 0; p < NP; p += 2) {
+				if (NP % 2 == 0) {
+					w[u][p / 2] = *reinterpret_cast<const float4 *>(wv + p * 8);
+				} else {
+					const float2 a = *reinterpret_cast<const float2 *>(wv + p * 8);
+					const float2 b = p + 1 < NP ? *reinterpret_cast<const float2 *>(wv + p * 8 + 8) : make_float2(0.f, 0.f);
+					w[u][p / 2] = make_float4(a.x, a.y, b.x, b.y);
+				}
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const float2 x0 = make_float2(x[u].x, x[u].y), x1 = make_float2(x[u].z, x[u].w);
+#pragma unroll
+			for (int p = 0; p < NP; p += 2) {
+				const float2 wa = make_float2(w[u][p / 2].x, w[u][p / 2].y), wb = make_float2(w[u][p / 2].z, w[u][p / 2].w);
+				fma2(acc[p][0], wa, x0);
+				fma2(acc[p][1], wa, x1);
+				if (p + 1 < NP) {
+					fma2(acc[p + 1][0], wb, x0);
+					fma2(acc[p + 1][1], wb, x1);
+				}
+			}
+		}
+	}
+	for (; left > 0; left--, xp += xs, wp += ws) { // remainder
+		const float4 x = *reinterpret_cast<const float4 *>(xp);
+		const float2 x0 = make_float2(x.x, x.y), x1 = make_float2(x.z, x.w);
+#pragma unroll
+		for (int p = 0; p < NP; p++) {
+			const float2 wa = *reinterpret_cast<const float2 *>(wp + p * 8);
+			fma2(acc[p][0], wa, x0);
+			fma2(acc[p][1], wa, x1);
+		}
+	}
+}
+
 // One row group (rows R0, R0+1 and, when `quad`, R0+2 of a class with R rows) of one run: evaluate the
 // polynomial at this thread's two frames and add the result to bus `b_own`, or to every bus of `fan` when the
 // group is shared by all sends.  Every accumulator index is a compile-time constant.
@@ -411,55 +466,12 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 			cc.tl_first = true;
 		}
 		if (mine && !(cf.debug & 2)) {
-			// the loads of several voices are issued before their FMAs (4 voices for the small classes, 2 for the
-			// large ones: the register budget): two consumer warps per scheduler cannot hide the shared-memory latency
-			// of one voice at a time
-			constexpr int U = NP <= 10 ? 4 : 2;
-			int v = cc.group;
-			for (; v + (U - 1) * cf.groups < nv; v += U * cf.groups) {
-				float4 x[U];
-				float4 w[U][(NP + 1) / 2];
-#pragma unroll
-				for (int u = 0; u < U; u++) {
-					const int vv = v + u * cf.groups;
-					x[u] = *reinterpret_cast<const float4 *>(sx + (size_t)vv * row_bytes + cc.slot * 16);
-					const unsigned char *wv = sw + vv * (NP * 8);
-#pragma unroll
-					for (int p = 0; p < NP; p += 2) {
-						if (NP % 2 == 0) {
-							w[u][p / 2] = *reinterpret_cast<const float4 *>(wv + p * 8);
-						} else {
-							const float2 a = *reinterpret_cast<const float2 *>(wv + p * 8);
-							const float2 b = p + 1 < NP ? *reinterpret_cast<const float2 *>(wv + p * 8 + 8) : make_float2(0.f, 0.f);
-							w[u][p / 2] = make_float4(a.x, a.y, b.x, b.y);
-						}
-					}
-				}
-#pragma unroll
-				for (int u = 0; u < U; u++) {
-					const float2 x0 = make_float2(x[u].x, x[u].y), x1 = make_float2(x[u].z, x[u].w);
-#pragma unroll
-					for (int p = 0; p < NP; p += 2) {
-						const float2 wa = make_float2(w[u][p / 2].x, w[u][p / 2].y), wb = make_float2(w[u][p / 2].z, w[u][p / 2].w);
-						fma2(acc[p][0], wa, x0);
-						fma2(acc[p][1], wa, x1);
-						if (p + 1 < NP) {
-							fma2(acc[p + 1][0], wb, x0);
-							fma2(acc[p + 1][1], wb, x1);
-						}
-					}
-				}
-			}
-			for (; v < nv; v += cf.groups) { // remainder
-				const float4 x = *reinterpret_cast<const float4 *>(sx + (size_t)v * row_bytes + cc.slot * 16);
-				const float2 x0 = make_float2(x.x, x.y), x1 = make_float2(x.z, x.w);
-				const unsigned char *wv = sw + v * (NP * 8);
-#pragma unroll
-				for (int p = 0; p < NP; p++) {
-					const float2 wa = *reinterpret_cast<const float2 *>(wv + p * 8);
-					fma2(acc[p][0], wa, x0);
-					fma2(acc[p][1], wa, x1);
-				}
+			// full 512-frame tiles (one voice group, 4 KB rows) take the loop whose strides are compile-time constants:
+			// the generic one spends as many instructions on addresses as on loads
+			if (cf.groups == 1 && row_bytes == kTileFrames * 8) {
+				voice_loop<NP, true>(acc, sx + cc.slot * 16, sw, nv, 1, kTileFrames * 8);
+			} else {
+				voice_loop<NP, false>(acc, sx + (size_t)cc.group * row_bytes + cc.slot * 16, sw + cc.group * (NP * 8), nv - cc.group, cf.groups, row_bytes);
 			}
 		}
 		__syncwarp();
