@@ -65,9 +65,10 @@ def measured_hbm_peak():
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.005):
+    def __init__(self, index, period=None):
         super().__init__(daemon=True)
-        self.index, self.period = index, period
+        # NVML queries are not free for the GPU they ask about: a few samples inside the timed region, not hundreds
+        self.index, self.period = index, float(os.environ.get("GAS_BENCH_SAMPLE_PERIOD", "0.02")) if period is None else period
         self.samples, self._stop_evt = [], threading.Event()
         self.max_mhz = None
         try:
