@@ -1,6 +1,6 @@
 /*
  * gas_oracle.c — CPU oracle (scalar C restatement of the reference hot path).
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED — see gas_oracle.h.
+ * TEST INFRASTRUCTURE ONLY; pinned against the reference's own code by oracle/_ref — see gas_oracle.h.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp (no -ffast-math): Godot's release optimisation level
  * without FMA contraction, so every float operation below rounds where the reference's does on a
@@ -702,6 +702,10 @@ struct orc_world {
 	orc_instance *inst;
 	gas_voice_state *vs;
 	vstate64 *vs64;
+	/* start order of the voices: SafeList::insert puts a new SpatialPlaybackListNode at the HEAD of playback_list
+	 * (audio_spatializer.cpp:74), so _mix_from_playback_list meets the most recently started voice first */
+	uint64_t *start_seq;
+	uint64_t next_seq;
 	double last_mix_s, last_gain_s;
 };
 
@@ -747,6 +751,8 @@ orc_world *orc_create(const gas_config *cfg) {
 	w->inst = (orc_instance *)calloc(cfg->max_instances, sizeof(orc_instance));
 	w->vs = (gas_voice_state *)calloc(cfg->max_voices, sizeof(gas_voice_state));
 	w->vs64 = (vstate64 *)calloc(cfg->max_voices, sizeof(vstate64));
+	w->start_seq = (uint64_t *)calloc(cfg->max_voices, sizeof(uint64_t));
+	w->next_seq = 1;
 	for (int i = 0; i < cfg->max_spatializers; i++) {
 		spat_defaults(&w->spat[i]);
 	}
@@ -764,6 +770,7 @@ void orc_destroy(orc_world *w) {
 	free(w->inst);
 	free(w->vs);
 	free(w->vs64);
+	free(w->start_seq);
 	free(w);
 }
 
@@ -910,6 +917,7 @@ int orc_voice_init(orc_world *w, int n, const int32_t *voices) {
 	for (int i = 0; i < n; i++) {
 		memset(&w->vs[voices[i]], 0, sizeof(gas_voice_state));
 		memset(&w->vs64[voices[i]], 0, sizeof(vstate64));
+		w->start_seq[voices[i]] = w->next_seq++;
 	}
 	return GAS_OK;
 }
@@ -1169,6 +1177,40 @@ static void mix_instance(orc_world *w, int qi, const gas_voice *voices, const in
 				}
 			}
 		}
+		/* Mode B: proxy c' is a playback of its own whose bus map is masked to pair c' (audio_spatializer.cpp:298-312),
+		 * but AudioServer still runs _mix_step_for_channel for EVERY pair of every bus of the map, with volume 0 for the
+		 * masked-out pairs.  0 * x only matters when x is not finite — which the module produces itself (Q1: NaN pan
+		 * gains) — and then the NaN reaches every pair of the bus, same side.  Adding +-0 is a no-op otherwise, so the
+		 * cross terms are only run for pair buffers that hold a non-finite sample.  Pinned by oracle/_ref. */
+		if (mix_channels) {
+			for (int cp = 0; cp < channels; cp++) {
+				int bad = 0;
+				for (int i = 0; i < frames && !bad; i++) {
+					bad = !isfinite(sc->mix[cp][i].l) || !isfinite(sc->mix[cp][i].r);
+				}
+				if (!bad) {
+					continue;
+				}
+				for (int pass = 0; pass < 2; pass++) {
+					const bus_details *d = pass == 0 ? &q->cur : &q->prev;
+					for (int k = 0; k < d->n; k++) {
+						if (pass == 1 && details_find(&q->cur, d->bus[k]) >= 0) {
+							continue;
+						}
+						int b = resolve_bus(&w->cfg, d->bus[k]);
+						for (int c = 0; c < channels; c++) {
+							if (c == cp) {
+								continue;
+							}
+							server_mix_step_for_channel_f32(bus + ((size_t)b * channels + c) * frames, sc->mix[cp], 0, 0, 0, 0, frames);
+							if (bus64) {
+								server_mix_step_for_channel_f64((frame64 *)bus64 + ((size_t)b * channels + c) * frames, sc->mix64[cp], 0, 0, 0, 0, frames);
+							}
+						}
+					}
+				}
+			}
+		}
 	}
 	q->prev = q->cur;
 }
@@ -1215,6 +1257,18 @@ int orc_mix_block(orc_world *w, int n_voices, const gas_voice *voices, const gas
 	int *order = (int *)malloc(sizeof(int) * (n_voices > 0 ? n_voices : 1));
 	for (int i = 0; i < n_voices; i++) {
 		order[fill[voices[i].instance]++] = i;
+	}
+	/* inside an instance: most recently started voice first (the order only fixes the float summation order) */
+	for (int q = 0; q < ni; q++) {
+		for (int a = count[q] + 1; a < count[q + 1]; a++) {
+			int v = order[a];
+			int b = a - 1;
+			while (b >= count[q] && w->start_seq[voices[order[b]].voice] < w->start_seq[voices[v].voice]) {
+				order[b + 1] = order[b];
+				b--;
+			}
+			order[b + 1] = v;
+		}
 	}
 	/* instances to step: every active instance (its proxies are mixed by AudioServer every step) */
 	int *todo = (int *)malloc(sizeof(int) * ni);

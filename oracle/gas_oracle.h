@@ -4,13 +4,18 @@
  * TEST INFRASTRUCTURE ONLY.  Nothing under godot-audio-spatializer_b200/ may include, link or call this;
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
  *
- * PARITY UNPINNED: the reference (BuzzLord/godot-audio-spatializer) ships no tests, golden vectors or
- * fixtures for this path and cannot be compiled here (it needs the Godot engine tree + scons).  The
- * oracle follows the cited reference lines operation by operation (float32 with the reference's
- * double intermediates); the upstream-Godot pieces that are not under /root/reference
- * (AudioFilterSW, AudioServer::_mix_step_for_channel, Math::*, Basis/Transform3D) are restated from
- * Godot 4.x as recalled in SURVEY.md Appendix A.  Its pins are the self-derived known-answer tests in
- * tests/test_oracle_kat.py and the golden vectors under tests/golden/ (generated by this oracle).
+ * PARITY PINNED BY REFERENCE CODE (module side) / RECALLED (upstream side):
+ *  - every module-side line of the path is pinned bit for bit against the reference's own sources:
+ *    oracle/_ref/libgas_ref.so is /root/reference/*.cpp, UNMODIFIED, compiled against the godot-lite stand-in
+ *    headers (oracle/godot_lite/) by `make -C oracle ref` and driven by oracle/ref_harness.cpp;
+ *    tests/test_oracle_vs_ref.py compares oracle == _ref on float32 bit patterns (gains, bus maps, bus buffers,
+ *    persistent voice state, NaN cases included), tests/test_lifecycle.py does the same for the lookahead / end
+ *    fade / deactivation path, and tests/golden/*.npz are outputs of _ref (tests/golden/make_golden.py);
+ *  - the upstream-Godot pieces that are not under /root/reference (AudioFilterSW, AudioServer::_mix_step /
+ *    _mix_step_for_channel, Math::*, Basis/Transform3D, AudioEffectFilter; godotengine/godot 4.x — the example
+ *    project declares feature "4.6", no commit is pinned) are restated from Godot 4.x as recalled (SURVEY.md
+ *    Appendix A), twice and independently (C here, C++ in oracle/godot_lite/), and the two restatements are checked
+ *    against each other.  That part remains unpinned by executed upstream code: there is no Godot tree here.
  *
  * The oracle uses the same POD records as the C ABI (include/gas.h) so that a parity test drives both
  * with identical call sequences.

@@ -1,0 +1,3 @@
+/* godot-lite forwarding header (test infrastructure): upstream scene/3d/camera_3d.h */
+#pragma once
+#include "../../godot_lite_scene.h"

@@ -2,7 +2,8 @@
 product's Mixer, so a parity test can drive both with one call sequence.
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs; never by the product package.  PARITY UNPINNED (see gas_oracle.h).
+--impl reference legs; never by the product package.  Pinned against the reference's own code by oracle/_ref
+(oracle/ref.py, tests/test_oracle_vs_ref.py); see gas_oracle.h for what that covers.
 """
 import ctypes as C
 import os

@@ -1,15 +1,17 @@
 #!/usr/bin/env python
 """Generates tests/golden/*.npz — committed golden input/output vectors for the hot path.
 
-Provenance: the reference ships no golden vectors, no tests and cannot be built in this container
-(it is a Godot engine module: every translation unit includes engine headers and is built by the engine's
-scons), so these vectors are minted with the CPU oracle (oracle/, a restatement of the
-reference loop that is itself pinned by the hand-derived known-answer tests in tests/test_oracle_kat.py).
-They freeze today's answers: a later change of the oracle or of the CUDA path that moves any of them
-shows up as a diff against a committed file.  Inputs are not stored: they are a pure function of the
-scenario dict (splitmix64 generator in godot-audio-spatializer_b200/synth.py), which is stored.
+Provenance: the vectors are OUTPUTS OF THE REFERENCE ITSELF, run in this container: oracle/_ref is
+/root/reference/*.cpp, unmodified, compiled against the godot-lite stand-in headers (oracle/godot_lite/,
+oracle/Makefile target `ref`) and driven by oracle/ref_harness.cpp.  Parameters, bus buffers and the final
+previous-volume state come from that library; `peaks` come from the CPU oracle (the reference keeps a voice's block
+peak in a local variable, audio_spatializer.cpp:419 — it is observable only through deactivation, which
+tests/test_lifecycle.py covers).  The generator refuses to write a file unless the CPU oracle reproduces the
+reference's numbers bit for bit.  The reference cannot travel to the GPU box, these files can.
+Inputs are not stored: they are a pure function of the scenario dict (splitmix64 generator in
+godot-audio-spatializer_b200/synth.py), which is stored.
 
-Usage:  python tests/golden/make_golden.py        (rewrites the .npz files)
+Usage:  python tests/golden/make_golden.py        (rewrites the .npz files; needs /root/reference)
 """
 import json
 import os
@@ -63,6 +65,16 @@ def run_oracle(name):
         return S.run(o, sc)
 
 
+def run_reference(name):
+    """The same scenario through the reference module's own code (oracle/_ref); peaks filled in from the oracle."""
+    from oracle import ref
+    sc = scenario(name)
+    with ref.RefMixer(**S.config_of(sc)) as r:
+        out = S.run(r, sc)
+    out["peaks"] = run_oracle(name)["peaks"]
+    return out
+
+
 def pack(out):
     d = {"bus": np.stack(out["bus"]), "peaks": np.stack(out["peaks"])}
     p = np.stack(out["params"])
@@ -75,9 +87,14 @@ def pack(out):
 
 def main():
     for name in SCENARIOS:
-        d = pack(run_oracle(name))
+        d = pack(run_reference(name))
+        o = pack(run_oracle(name))
+        for k in d:
+            if not np.array_equal(d[k], o[k], equal_nan=True):
+                raise SystemExit(f"{name}: the oracle does not reproduce the reference's {k}; not writing")
         d["scenario_json"] = np.array(json.dumps({k: (v if not isinstance(v, np.generic) else v.item()) for k, v in SCENARIOS[name].items()},
                                                  default=lambda o: o.item() if hasattr(o, "item") else str(o)))
+        d["minted_by"] = np.array("oracle/_ref: /root/reference/*.cpp (unmodified) + oracle/godot_lite + oracle/ref_harness.cpp")
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **d)
         print(f"{name}: bus {d['bus'].shape}, {os.path.getsize(path) / 1024:.0f} KiB")

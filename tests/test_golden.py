@@ -1,7 +1,7 @@
-"""Committed golden vectors (tests/golden/*.npz, minted by tests/golden/make_golden.py — see its header for
-provenance: self-derived with the CPU oracle, the reference ships none).
+"""Committed golden vectors (tests/golden/*.npz, minted by tests/golden/make_golden.py from the outputs of the REFERENCE
+ITSELF: oracle/_ref = /root/reference/*.cpp compiled against the godot-lite stand-in, see the generator's header).
 
-CPU: the oracle must still reproduce them bit for bit (they freeze its answers).
+CPU: the oracle must reproduce them bit for bit, and so must oracle/_ref wherever it is available.
 GPU: the CUDA path, through the C ABI, must match them at the north-star tolerance
      (samples within 1e-5 relative or below -110 dBFS; routing and integer parameter fields bit-exact)."""
 import glob
@@ -35,6 +35,18 @@ def test_every_scenario_has_a_fixture():
 def test_oracle_reproduces_golden_bit_exact(orc, name):
     want = _load(name)
     got = mg.pack(mg.run_oracle(name))
+    for k in got:
+        assert np.array_equal(got[k], want[k]), f"{name}: {k} changed"
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_reproduces_golden_bit_exact(name):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built and /root/reference not present")
+    want = _load(name)
+    assert "oracle/_ref" in str(want["minted_by"])
+    got = mg.pack(mg.run_reference(name))
     for k in got:
         assert np.array_equal(got[k], want[k]), f"{name}: {k} changed"
 
