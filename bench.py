@@ -17,9 +17,14 @@ roofline   streaming mix kernel (K2): algorithmic bytes per launch / its mean du
            every launch) vs the measured HBM copy peak in MEASURED_PEAKS.json.
 cpu_baseline  the CPU oracle (restated reference loop, oracle/) on the host cores, bounded sample.
 
-`--impl reference` times the reference's CPU implementation of the path (the oracle port: the reference
-itself needs the Godot engine tree + scons and cannot be built here) on all host threads.
+configs    (N = 1) the other BASELINE.json configurations, time-boxed: us per block, voice-frames/s, fraction of the HBM
+           and fp32 rooflines, CPU baseline and a full-size parity flag each.
+
+`--impl reference` times the reference's CPU implementation of the path on all host threads: the oracle port (the
+reference module itself is compiled and executed only as the checker that pins the oracle, oracle/_ref — it is a
+single-threaded object graph, not a batch mixer; headless Godot cannot be built here).
 """
+import hashlib
 import argparse
 import json
 import os
@@ -175,6 +180,28 @@ def run_cpu(w, steps, warmup, threads, abi, synth, budget_s=None, inputs=None):
     return V * F * done / dt, done, dt
 
 
+def host_threads():
+    """Host threads the CPU arms may use: the affinity mask, not OMP_NUM_THREADS (torchrun forces that to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def bench_config(w, world, peer=True):
+    """The `config` object of the JSON line: identical in the GPU arm and the reference arm."""
+    V, F, C, B = w["voices"], w["frames"], w["speaker_mode"] + 1, w["num_buses"]
+    return {"workload": workload_name(w), "voices_per_gpu": V, "frames": F, "channel_pairs": C, "buses": B,
+            "l2": f"{N_SETS} distinct source sets of {V * F * 8 / 2**20:.0f} MiB rotated (> 4x L2)",
+            "launch": "CUDA-graph replay of gas_mix_block_device (block k) with gas_gain_compute_device (parameters of block "
+                      "k+1) beside it on the gain stream, one graph per step",
+            "reduce": ("none (1 GPU)" if world == 1 else
+                       "gas_reduce_bus_exchange_device inside the step graph, one block in flight on the exchange stream: every rank "
+                       "adds its partial bus buffer into every rank's exchange buffer with vector reductions on peer pointers "
+                       "(NVLink), one arrival-counter round per block"
+                       if peer else "torch.distributed all_reduce (NCCL) of the partial bus buffers, one call per step")}
+
+
 def reference_arm(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -182,18 +209,18 @@ def reference_arm(args):
     import gaspkg
     gas = gaspkg.load()
     abi, synth = gas.abi, gas.synth
-    from oracle import orc
     w = dict(WORKLOAD)
-    threads = orc.max_threads()
-    steps = max(1, min(args.steps, 40))  # each step is a bounded sample: one full 16384-voice block on the CPU
-    warmup = max(1, min(args.warmup, 2))
-    value, done, secs = run_cpu(w, steps, warmup, threads, abi, synth, budget_s=120.0)
+    threads = host_threads()
+    # every step is a bounded sample of the workload: one full block of one GPU's share (16384 voices) on the CPU
+    steps = max(1, args.steps)
+    warmup = max(1, args.warmup)
+    value, done, secs = run_cpu(w, steps, warmup, threads, abi, synth, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": warmup,
         "ms_per_step": 1e3 * secs / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": workload_name(w), "note": "reference CPU path = oracle port (g++ -O2, OpenMP over instances); "
-                   "headless Godot cannot be built here (needs engine tree + scons)"},
+        "data": "synthetic", "config": bench_config(w, max(1, args.gpus), args.reduce == "peer"),
+        "note": "reference CPU path = oracle port (gcc -O2, OpenMP over instances), pinned bit for bit against the reference module's "
+                "own code by oracle/_ref; headless Godot cannot be built here (needs the engine tree + scons)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{done} full blocks of {w['voices']} voices x {w['frames']} frames (gain + mix)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -234,6 +261,7 @@ class DeviceWorkload:
                 self.d_src.append((torch.rand((V, F, 2), generator=g, device=dev, dtype=torch.float32) - 0.5) * 0.5)
         self.d_bus = [torch.zeros((w["num_buses"], self.C, F, 2), device=dev, dtype=torch.float32) for _ in range(2)]
         self.d_sum = [torch.zeros((w["num_buses"], self.C, F, 2), device=dev, dtype=torch.float32) for _ in range(2)]  # N > 1: reduced
+        self.d_gate = torch.zeros((w["num_buses"], self.C, F, 2), device=dev, dtype=torch.float32)  # N > 1: start gate scratch
         setup_mixer(self.mixer, w, abi, self.emitters_host, self.listeners, self.areas)
         self.mixer.listeners_set(self.listeners)
         self.mixer.areas_set(self.areas)
@@ -283,7 +311,7 @@ class DeviceWorkload:
         return graphs
 
 
-def parity_gate(gas, w, dw, abi, synth, parity_src, host_inputs):
+def parity_gate(gas, w, device, abi, synth, parity_src, host_inputs):
     """Full-size parity of the exact bench workload: 2 state-carrying blocks on source set 0 against
     the float32 oracle (north-star tolerance) and the float64 shadow (accumulation-order budget)."""
     from oracle import orc
@@ -293,13 +321,13 @@ def parity_gate(gas, w, dw, abi, synth, parity_src, host_inputs):
                mix_rate=w["mix_rate"])
     emitters, _, voices, listeners, areas = host_inputs
     res = {}
-    with orc.OracleMixer(**cfg) as o, gas.Mixer(device=int(dw.mixer.config["device"]), **cfg) as m:
+    with orc.OracleMixer(**cfg) as o, gas.Mixer(device=device, **cfg) as m:
         for mm in (o, m):
             setup_mixer(mm, w, abi, emitters, listeners, areas)
         for b in range(2):
             for mm in (o, m):
                 mm.gain_compute(emitters[b % len(emitters)], listeners, areas, want_params=False)
-            want, _ = o.mix_block(voices, parity_src, F, want_peaks=False, shadow=True, threads=1)
+            want, _ = o.mix_block(voices, parity_src, F, want_peaks=False, shadow=True, threads=host_threads())
             got, _ = m.mix_block(voices, parity_src, F, want_peaks=False)
             shadow = o.last_bus64
             ok, worst, nbad = S.sample_close(got, want)
@@ -312,6 +340,257 @@ def parity_gate(gas, w, dw, abi, synth, parity_src, host_inputs):
                 "peak_abs_bus_sample": scale,
             }
     return res
+
+
+def parity_gate_multi(gas, torch, dist, w, local_rank, rank, world, abi, synth):
+    """N > 1: one block of the bench workload on every rank (its own shard of N x V voices), summed by
+    gas_reduce_bus_device over peer memory; rank 0 compares the reduced bus buffers with the oracle's mix of ALL voices."""
+    import scenarios as S
+    V, F = w["voices"], w["frames"]
+    dt = F / w["mix_rate"]
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, max_spatializers=2, num_buses=w["num_buses"], speaker_mode=w["speaker_mode"],
+               mix_rate=w["mix_rate"])
+    listeners = np.array([abi.identity_listener()], dtype=abi.listener)
+    areas = np.array([synth.reverb_area(reverb_bus=1, amount=0.5, uniformity=0.0)], dtype=abi.area)
+
+    def rank_inputs(r):
+        em = synth.make_emitters(V, block=0, dt=dt, area_fraction=w["area_fraction"], r_min=w["r_min"], r_max=w["r_max"], seed0=r * 1000003)
+        return em, synth.make_sources(V, F, block=0, mix_rate=w["mix_rate"], voice0=r * V)
+
+    dev = torch.device("cuda", local_rank)
+    em, src = rank_inputs(rank)
+    voices = synth.make_voices(V)
+    with gas.Mixer(device=local_rank, **cfg) as m:
+        handles = [None] * world
+        dist.all_gather_object(handles, m.comm_export())
+        m.comm_open(rank, handles)
+        dist.barrier()
+        setup_mixer(m, w, abi, [em], listeners, areas)
+        d_voices = torch.from_numpy(voices.view(np.uint8).copy()).to(dev)
+        d_src = torch.from_numpy(src).to(dev)
+        d_bus = torch.zeros((w["num_buses"], w["speaker_mode"] + 1, F, 2), device=dev, dtype=torch.float32)
+        m.mix_block_device(V, d_voices.data_ptr(), d_src.data_ptr(), V, F, F, d_bus.data_ptr())
+        m.reduce_bus_device(d_bus.data_ptr(), F)
+        m.sync()
+        got = d_bus.cpu().numpy()
+        dist.barrier()
+        m.comm_close()
+    if rank != 0:
+        return None
+    from oracle import orc
+    cfg_all = dict(cfg, max_instances=V * world, max_voices=V * world)
+    ems, srcs = [], []
+    for r in range(world):
+        e, s_ = (em, src) if r == 0 else rank_inputs(r)
+        e = e.copy()
+        e["instance"] += r * V
+        ems.append(e)
+        srcs.append(s_)
+    with orc.OracleMixer(**cfg_all) as o:
+        setup_mixer(o, dict(w, voices=V * world), abi, [np.concatenate(ems)], listeners, areas)
+        want, _ = o.mix_block(synth.make_voices(V * world), np.concatenate(srcs), F, want_peaks=False, threads=host_threads())
+    ok, worst, nbad = S.sample_close(got, want)
+    return {"ranks": world, "voices_total": V * world, "routing_exact": bool(np.array_equal(S.routing(got), S.routing(want))),
+            "reduced_sum_within_1e-5_rel_or_-110dBFS_of_f32_oracle": ok, "samples_out": nbad, "worst_abs_err": worst,
+            "peak_abs_bus_sample": float(np.abs(want).max())}
+
+
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FMA lanes x 2 flop at the measured max SM clock
+
+
+def flops_per_voice_frame(kind, C, n_send, stages=0, n_fx=0):
+    """fp32 operations per voice-frame of the filtered paths, counted from the reference loops:
+    ramp 4 + multiply 1 + biquad 9 + coefficient increments 5 per stream, plus 5 per (send, pair, side) for the bus ramp."""
+    if kind == "B-filter":      # mix_channel: 2C streams of (ramp, mul, interpolated biquad), audio_spatializer_3d.cpp:589-597
+        return 2 * C * (4 + 1 + 9 + 5) + 2 * C * n_send * 5
+    if kind == "A-filter":      # process_frames: 2 interpolated biquads, then Q15 sends, :524-529
+        return 2 * (9 + 5) + 2 * C * n_send * 5
+    if kind == "effect":        # n_fx effects x stages biquads per side (no interpolation), audio_spatializer_effect.cpp:52-75
+        return 2 * 9 * stages * n_fx + 2 * C * n_send * 5
+    return 2 * C * n_send * 2   # unfiltered polynomial rows
+
+
+EXTRA_CONFIGS = [
+    dict(name="configs[1]: AudioSpatializer3D, 1024 voices, 5.1, inverse-square attenuation + attenuation filter, Mode B", voices=1024, frames=512,
+         speaker_mode=2, num_buses=2, kind="B-filter", n_send=1.25,
+         sc=dict(spat=dict(mix_channel_mode=1, attenuation_model=1), area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25)),
+    dict(name="configs[3]: AudioSpatializerEffect, 4096 voices, stereo, 1-stage high-shelf chain, Master/area bus + reverb bus", voices=4096,
+         frames=512, speaker_mode=0, num_buses=3, kind="effect", stages=1, n_fx=1, n_send=1.5,
+         sc=dict(effect_chain=[dict(mode=7, cutoff_hz=4000.0, resonance=1.0, gain=0.3, stages=1)], effect_gain_binding=0,
+                 area=dict(reverb_bus=2, amount=0.4, override_bus=True, bus=1), area_fraction=0.5)),
+    dict(name="configs[3]: AudioSpatializerEffect, 4096 voices, stereo, 4-stage high-shelf chain, Master/area bus + reverb bus", voices=4096,
+         frames=512, speaker_mode=0, num_buses=3, kind="effect", stages=4, n_fx=1, n_send=1.5,
+         sc=dict(effect_chain=[dict(mode=7, cutoff_hz=4000.0, resonance=1.0, gain=0.3, stages=4)], effect_gain_binding=0,
+                 area=dict(reverb_bus=2, amount=0.4, override_bus=True, bus=1), area_fraction=0.5)),
+    dict(name="configs[2] with the attenuation filter ON, Mode A (process_frames: 2 biquads per voice-frame)", voices=16384, frames=512,
+         speaker_mode=3, num_buses=2, kind="A-filter", n_send=1.25,
+         sc=dict(spat=dict(mix_channel_mode=0), area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25)),
+    dict(name="configs[4] corner: 256 voices x 128-frame blocks, stereo, filter off", voices=256, frames=128, speaker_mode=0, num_buses=2,
+         kind="stream", n_send=1.25, sc=dict(spat=dict(mix_channel_mode=1, unit_size=1.0, attenuation_filter_db=-80.0),
+                                             area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25, r_min=10.0)),
+    dict(name="configs[4] corner: 65536 voices x 2048-frame blocks, 7.1, filter off", voices=65536, frames=2048, speaker_mode=3, num_buses=2,
+         kind="stream", n_send=1.25, sc=dict(spat=dict(mix_channel_mode=1, unit_size=1.0, attenuation_filter_db=-80.0),
+                                             area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25, r_min=10.0), sets=2, steps=12),
+    dict(name="configs[4] corner: 4096 voices x 1024-frame blocks, 3.1, filter off", voices=4096, frames=1024, speaker_mode=1, num_buses=2,
+         kind="stream", n_send=1.25, sc=dict(spat=dict(mix_channel_mode=1, unit_size=1.0, attenuation_filter_db=-80.0),
+                                             area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25, r_min=10.0)),
+]
+
+
+def measure_config(gas, torch, spec, device, peak_gbs, cpu_budget_s=2.5):
+    """One secondary configuration on one GPU: us per block (CUDA-graph replay, CUDA events), fractions of the HBM and fp32
+    rooflines, the CPU oracle beside it and a full-size parity check of two blocks."""
+    import scenarios as S
+    from oracle import orc
+    abi, synth = gas.abi, gas.synth
+    V, F, mode, B = spec["voices"], spec["frames"], spec["speaker_mode"], spec["num_buses"]
+    C = mode + 1
+    kw = dict(spec["sc"])
+    r_min = kw.pop("r_min", 0.5)
+    sc = S.default_scenario(voices=V, frames=F, speaker_mode=mode, num_buses=B, **kw)
+    sets, steps = spec.get("sets", 4), spec.get("steps", 100)
+    dev = torch.device("cuda", device)
+    inst = np.arange(V, dtype=np.int32)
+    listeners = np.array([abi.identity_listener()], dtype=abi.listener)
+    areas = np.array([synth.reverb_area(**sc["area"])], dtype=abi.area) if sc["area"] else None
+    dt = F / sc["mix_rate"]
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, max_spatializers=2, num_buses=B, speaker_mode=mode, mix_rate=sc["mix_rate"])
+    ems = [synth.make_emitters(V, block=b, dt=dt, area_fraction=sc["area_fraction"], r_min=r_min) for b in range(sets)]
+    voices = synth.make_voices(V)
+    spat = S.make_spatializer(sc)
+
+    def setup(mm):
+        mm.spatializer_set(0, spat)
+        mm.instance_init(inst, 0)
+        mm.gain_compute(ems[0], listeners, areas, want_params=False)
+        mm.instance_start(inst)
+        mm.voice_init(inst)
+
+    with gas.Mixer(device=device, **cfg) as m:
+        setup(m)
+        m.listeners_set(listeners)
+        if areas is not None:
+            m.areas_set(areas)
+        d_em = [torch.from_numpy(e.view(np.uint8).copy()).to(dev) for e in ems]
+        d_voices = torch.from_numpy(voices.view(np.uint8).copy()).to(dev)
+        d_src = [(torch.rand((V, F, 2), device=dev) - 0.5) * 0.5 for _ in range(sets)]
+        d_bus = torch.zeros((B, C, F, 2), device=dev)
+
+        def capture():
+            gs = []
+            for s_ in range(sets):
+                m.capture_begin()
+                m.mix_block_device(V, d_voices.data_ptr(), d_src[s_].data_ptr(), V, F, F, d_bus.data_ptr())
+                m.gain_compute_device(V, d_em[(s_ + 1) % sets].data_ptr())
+                gs.append(m.capture_end())
+            return gs
+
+        graphs = capture()
+        stream = torch.cuda.ExternalStream(m.mix_stream, device=dev)
+        for k in range(max(8, sets)):
+            m.graph_launch(graphs[k % sets])
+        m.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+        for k in range(steps):
+            m.graph_launch(graphs[k % sets])
+        with torch.cuda.stream(stream):
+            e1.record()
+        m.sync()
+        us = 1e3 * e0.elapsed_time(e1) / steps
+        m.profile_enable(True)
+        pg = capture()
+        for k in range(16):
+            m.graph_launch(pg[k % sets])
+        prof = m.profile_read()
+        m.profile_enable(False)
+        del d_src
+    # parity: two state-carrying blocks, full size, against the oracle (bounded: the largest corner is checked on a slice of time)
+    parity = None
+    if V * F <= 16384 * 512:
+        src_h = [synth.make_sources(V, F, block=b, mix_rate=sc["mix_rate"]) for b in range(2)]
+        with gas.Mixer(device=device, **cfg) as m, orc.OracleMixer(**cfg) as o:
+            ok_all, worst_all, routing = True, 0.0, True
+            for mm in (m, o):
+                setup(mm)
+            for b in range(2):
+                for mm in (m, o):
+                    mm.gain_compute(ems[b % sets], listeners, areas, want_params=False)
+                got, _ = m.mix_block(voices, src_h[b], F, want_peaks=False)
+                want, _ = o.mix_block(voices, src_h[b], F, want_peaks=False, threads=host_threads())
+                ok, worst, _ = S.sample_close(got, want)
+                ok_all, worst_all = ok_all and ok, max(worst_all, worst)
+                routing = routing and bool(np.array_equal(S.routing(got), S.routing(want)))
+            parity = {"blocks": 2, "routing_exact": routing, "within_tolerance": ok_all, "worst_abs_err": worst_all}
+    # CPU oracle beside it (bounded sample)
+    cpu = None
+    src0 = synth.make_sources(min(V, 4096), F, block=0, mix_rate=sc["mix_rate"])
+    if V > 4096:
+        src0 = np.tile(src0, (V // 4096, 1, 1))
+    with orc.OracleMixer(**cfg) as o:
+        setup(o)
+        thr = host_threads()
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < cpu_budget_s or n < 1:
+            o.gain_compute(ems[n % sets], listeners, areas, want_params=False)
+            o.mix_block(voices, src0, F, want_peaks=False, threads=thr)
+            n += 1
+        cs = time.perf_counter() - t0
+        cpu = {"value": V * F * n / cs, "unit": UNIT, "cores": thr, "kind": "port", "sample": f"{n} blocks in {cs:.1f} s"}
+    filt = spec["kind"] != "stream"
+    bytes_blk = algorithmic_bytes(V, F, C, B, filter_on=(spec["kind"] == "B-filter"))
+    fl = flops_per_voice_frame(spec["kind"], C, spec["n_send"], spec.get("stages", 0), spec.get("n_fx", 0)) * V * F
+    return {"config": spec["name"], "voices": V, "frames": F, "channel_pairs": C, "buses": B, "us_per_block": us,
+            "voice_frames_per_s": V * F / (us * 1e-6), "x_realtime": dt / (us * 1e-6),
+            "roofline": {"hbm_frac": bytes_blk / (us * 1e-6) / 1e9 / peak_gbs, "algorithmic_bytes_per_block": bytes_blk,
+                         "fp32_frac": (fl / (us * 1e-6) / 1e12 / FP32_PEAK_TFLOPS) if filt else None,
+                         "fp32_flop_per_block": fl if filt else None, "fp32_peak_tflops": FP32_PEAK_TFLOPS,
+                         "bound": "fp32 issue / recurrence latency" if filt else "hbm (launch latency for the small corner)"},
+            "kernels_us": {k: 1e3 * v[0] / max(1, v[1]) for k, v in prof.items()}, "cpu_baseline": cpu, "parity": parity}
+
+
+def k2_debug_dump(m, torch):
+    """experiments (GAS_K2_DEBUG & 8): K2's in-kernel timeline (globaltimer stamps of every CTA) of the last replayed step, to stderr"""
+    import ctypes
+    torch.cuda.synchronize()
+    keys = (ctypes.c_uint64 * 128)()
+    counts = (ctypes.c_int32 * 256)()
+    if m._lib.gas_debug_classes(m._ctx, keys, counts) == 0:
+        for i in range(128):
+            k = keys[i]
+            if k and (counts[i] or counts[128 + i]):
+                print(f"  class slot {i}: path {k & 3} mode {(k >> 2) & 3} flags {(k >> 4) & 0xf:#x} sends {(k >> 8) & 0xf} mask {(k >> 16) & 0xffff:#x} "
+                      f"quad {(k >> 32) & 0xfff:#x} counts {counts[i]}/{counts[128 + i]}", file=sys.stderr)
+    fn = m._lib.gas_debug_timeline
+    fn.restype = ctypes.c_void_p
+    fn.argtypes = [ctypes.c_void_p]
+    ptr = fn(m._ctx)
+    if ptr:
+        tl = torch.empty(148 * 16, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(tl.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(148 * 16 * 8), 3)
+        t = tl.cpu().numpy().reshape(148, 16).astype(np.float64)
+        t0 = t[:, 0][t[:, 0] > 0].min()
+        names = {0: "start", 11: "table in smem", 1: "partition", 12: "first indices", 13: "stage 0 issued", 2: "first data", 3: "last data",
+                 9: "flush begins", 4: "flushed"}
+        for k, nm in names.items():
+            v = (t[:, k][t[:, k] > 0] - t0) * 1e-3
+            if v.size:
+                print(f"  K2 timeline {nm:16s} min {v.min():7.2f} avg {v.mean():7.2f} max {v.max():7.2f} us", file=sys.stderr)
+        units = t[:, 5]
+        per = (t[:, 3] - t[:, 2]) * 1e-3 / np.maximum(units, 1)
+        for u in sorted(set(units.astype(int))):
+            sel = units == u
+            print(f"  K2 units {u:2d}: n={int(sel.sum()):3d} per-unit {per[sel].mean():.3f} us  last data {((t[sel, 3] - t0) * 1e-3).mean():.2f}  "
+                  f"flushed {((t[sel, 4] - t0) * 1e-3).mean():.2f}", file=sys.stderr)
+
+
+def file_sha16(path):
+    try:
+        with open(path, "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()[:16]
+    except Exception:
+        return None
 
 
 def gpu_arm(args):
@@ -333,7 +612,8 @@ def gpu_arm(args):
     if args.area_fraction is not None:
         w["area_fraction"] = args.area_fraction
     V, F, C, B = w["voices"], w["frames"], w["speaker_mode"] + 1, w["num_buses"]
-    K, W = args.steps, max(3, args.warmup)
+    # every step graph is launched at least once before the timed region (first launches upload the graph)
+    K, W = args.steps, max(3, args.warmup, N_SETS)
 
     parity_src = synth.make_sources(V, F, block=0, mix_rate=w["mix_rate"]) if (rank == 0 and not args.no_parity) else None
     dw = DeviceWorkload(gas, torch, w, local_rank, rank, parity_src)
@@ -351,6 +631,7 @@ def gpu_arm(args):
     if peer:
         dw.comm_setup(dist)
     graphs = dw.capture_steps()
+    sampler = ClockSampler(local_rank)  # NVML initialised here, outside the timed region
 
     def one_step(k):
         m.graph_launch(graphs[k % N_SETS])
@@ -368,67 +649,42 @@ def gpu_arm(args):
     dw.reduce_prime()
     for k in range(W):
         one_step(k)
+    dw.reduce_drain(W - 1)
     barrier()
-    sampler = ClockSampler(local_rank)
     sampler.start()
+    if peer:
+        # device-side start gate: an in-order reduce of a scratch buffer is one arrival round over peer memory, so every
+        # rank's mix stream leaves it within an NVLink round trip of the others; host-side skew after the barrier above
+        # stays outside the timed region
+        m.reduce_bus_device(dw.d_gate.data_ptr(), F)
     launches0 = m.kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     t_wall0 = time.time()
     with torch.cuda.stream(stream):
         ev0.record()
     for k in range(K):
         one_step(W + k)
-    dw.reduce_drain(W + K - 1)
     with torch.cuda.stream(stream):
         ev1.record()
+    gpu_launches = m.kernel_launches - launches0
+    dw.reduce_drain(W + K - 1)  # the two blocks still in flight in the exchange pipeline: reported separately
+    with torch.cuda.stream(stream):
+        ev2.record()
     barrier()
     t_wall1 = time.time()
     sampler.stop()
     sampler.join()
     ms = ev0.elapsed_time(ev1)
-    gpu_launches = m.kernel_launches - launches0
+    drain_ms = ev1.elapsed_time(ev2)
     if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, drain_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, drain_ms = float(t[0].item()), float(t[1].item())
     value = world * V * F * K / (ms * 1e-3)
     clocks = sampler.summary(t_wall0, t_wall1)
 
     if os.environ.get("GAS_K2_DEBUG") and int(os.environ["GAS_K2_DEBUG"]) & 8:
-        # experiments: K2's in-kernel timeline (globaltimer stamps of every CTA) of the last replayed step, to stderr
-        import ctypes
-        torch.cuda.synchronize()
-        keys = (ctypes.c_uint64 * 128)()
-        counts = (ctypes.c_int32 * 256)()
-        if m._lib.gas_debug_classes(m._ctx, keys, counts) == 0:
-            for i in range(128):
-                k = keys[i]
-                if k and (counts[i] or counts[128 + i]):
-                    quad = (k >> 32) & 0xff
-                    n_send = (k >> 8) & 0xff
-                    flags = (k >> 4) & 0xf
-                    groups = 1 if (flags & 2) and n_send >= 2 else n_send  # CLS_SHARED
-                    print(f"  class slot {i}: path {k & 3} mode {(k >> 2) & 3} flags {flags:#x} sends {n_send} mask {(k >> 16) & 0xffff:#x} "
-                          f"quad {quad:#x} counts {counts[i]}/{counts[128 + i]}", file=sys.stderr)
-        fn = m._lib.gas_debug_timeline
-        fn.restype = ctypes.c_void_p
-        fn.argtypes = [ctypes.c_void_p]
-        ptr = fn(m._ctx)
-        if ptr:
-            tl = torch.empty(148 * 16, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
-            ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(tl.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(148 * 16 * 8), 3)
-            t = tl.cpu().numpy().reshape(148, 16).astype(np.float64)
-            t0 = t[:, 0][t[:, 0] > 0].min()
-            names = {0: "start", 11: "table in smem", 1: "partition", 12: "first indices", 13: "stage 0 issued", 2: "first data", 3: "last data", 9: "flush begins", 4: "flushed"}
-            for k, nm in names.items():
-                v = (t[:, k][t[:, k] > 0] - t0) * 1e-3
-                if v.size:
-                    print(f"  K2 timeline {nm:16s} min {v.min():7.2f} avg {v.mean():7.2f} max {v.max():7.2f} us", file=sys.stderr)
-            units = t[:, 5]
-            per = (t[:, 3] - t[:, 2]) * 1e-3 / np.maximum(units, 1)
-            for u in sorted(set(units.astype(int))):
-                sel = units == u
-                print(f"  K2 units {u:2d}: n={int(sel.sum()):3d} per-unit {per[sel].mean():.3f} us  last data {((t[sel, 3] - t0) * 1e-3).mean():.2f}  flushed {((t[sel, 4] - t0) * 1e-3).mean():.2f}", file=sys.stderr)
+        k2_debug_dump(m, torch)
 
     # ---- roofline: per-launch duration of the streaming mix kernel ----------------------------------------------
     # The same steps are captured once more with per-kernel timing on: the graphs then carry event-record nodes
@@ -453,8 +709,14 @@ def gpu_arm(args):
     prof_alone = m.profile_read()
     dw.no_gain = False
     m.profile_enable(False)
+    barrier()
+    parity_multi = None
+    if dist is not None and peer and not args.no_parity:
+        parity_multi = parity_gate_multi(gas, torch, dist, w, local_rank, rank, world, abi, synth)
     if rank == 0 and not args.no_parity:
-        parity = parity_gate(gas, w, dw, abi, synth, parity_src, host_inputs)
+        parity = parity_gate(gas, w, local_rank, abi, synth, parity_src, host_inputs)
+        if parity_multi is not None:
+            parity["multi_gpu_reduced_sum"] = parity_multi
     k2_ms, k2_n = prof["mix_stream"]
     peak, peak_src = measured_hbm_peak()
     bytes_launch = algorithmic_bytes(V, F, C, B)
@@ -475,15 +737,23 @@ def gpu_arm(args):
                           "us_per_launch": 1e3 * prof_alone["mix_stream"][0] / max(1, prof_alone["mix_stream"][1]),
                           "frac": bytes_launch / (1e3 * prof_alone["mix_stream"][0] / max(1, prof_alone["mix_stream"][1]) * 1e-6) / 1e9 / peak},
                 "other_kernels_us": {"gain_K1": us("gain"), "prologue": us("prologue"), "mix_voice_K3": us("mix_voice")}}
+    # DRAM traffic of the kernel comes from one `ncu --set full` capture (profiles/): valid only for the kernel source it was
+    # taken from, so the file carries the hash of gas_mix_stream.cu and a stale file reports null instead of an old number
     traffic_file = os.path.join(ROOT, "profiles", "k2_traffic_bytes.json")
+    k2_src = os.path.join(ROOT, "godot-audio-spatializer_b200", "csrc", "gas_mix_stream.cu")
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as f:
-                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("k2_source_sha16") == file_sha16(k2_src):
+                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = tj.get("source")
+            else:
+                roofline["traffic_note"] = "profiles/k2_traffic_bytes.json was captured from another version of gas_mix_stream.cu"
         except Exception:
             pass
 
-    # ---- e2e: host buffers through gas_gain_compute + gas_mix_block ------------------------------------------------
+    # ---- e2e: host buffers through the public API ---------------------------------------------------------------------
     ke = max(4, min(K, args.e2e_steps))
     pin_src = [torch.empty((V, F, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
     for t_ in pin_src:
@@ -492,12 +762,28 @@ def gpu_arm(args):
     pin_bus = torch.empty((B, C, F, 2), dtype=torch.float32).pin_memory()
     h2d = V * F * 8 + dw.voices_host.nbytes + dw.emitters_host[0].nbytes + dw.listeners.nbytes + dw.areas.nbytes
     d2h = B * C * F * 8
+    d_e2e_src = torch.empty((V, F, 2), dtype=torch.float32, device=torch.device("cuda", local_rank)) if dist is not None else None
 
     def e2e_step(k):
         m.gain_compute(dw.emitters_host[k % N_SETS], dw.listeners, dw.areas, want_params=False)
-        m.mix_block_host_ptr(V, pin_voices.data_ptr(), pin_src[k % 2].data_ptr(), V, F, pin_bus.data_ptr())
-        if dist is not None:
-            dist.all_reduce(dw.d_bus[0])
+        if dist is None:
+            # gas_mix_block: sources and voices host -> device, the bus buffers device -> host, all inside the call
+            m.mix_block_host_ptr(V, pin_voices.data_ptr(), pin_src[k % 2].data_ptr(), V, F, pin_bus.data_ptr())
+        else:
+            # N > 1: the rank's sources go up, its partial bus buffers are summed over peer memory (gas_reduce_bus_device)
+            # and the complete sum comes back to the host
+            with torch.cuda.stream(stream):
+                d_e2e_src.copy_(pin_src[k % 2], non_blocking=True)
+                dw.d_voices.copy_(pin_voices, non_blocking=True)
+            m.mix_block_device(V, dw.d_voices.data_ptr(), d_e2e_src.data_ptr(), V, F, F, dw.d_bus[0].data_ptr())
+            if peer:
+                m.reduce_bus_device(dw.d_bus[0].data_ptr(), F)
+            else:
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(dw.d_bus[0])
+            with torch.cuda.stream(stream):
+                pin_bus.copy_(dw.d_bus[0], non_blocking=True)
+            m.sync()
 
     for k in range(3):
         e2e_step(k)
@@ -512,13 +798,14 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = {"value": world * V * F * ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
-           "ms_per_step": 1e3 * e2e_s / ke, "api": "gas_gain_compute + gas_mix_block (host pointers, pinned)"}
+           "ms_per_step": 1e3 * e2e_s / ke,
+           "api": "gas_gain_compute + gas_mix_block (host pointers, pinned)" if dist is None else
+                  "gas_gain_compute + pinned host->device copy + gas_mix_block_device + gas_reduce_bus_device + device->host copy of the sum"}
 
     # ---- cpu baseline (rank 0, N = 1) --------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import orc
-        threads = orc.max_threads()
+        threads = host_threads()
         inputs = host_inputs or build_host_inputs(w, abi, synth)
         v_all, n_all, s_all = run_cpu(w, 400, 1, threads, abi, synth, budget_s=12.0, inputs=inputs)
         v_one, n_one, s_one = run_cpu(w, 400, 1, 1, abi, synth, budget_s=8.0, inputs=inputs)
@@ -526,24 +813,34 @@ def gpu_arm(args):
                "sample": f"{n_all} full blocks ({V} voices x {F} frames, gain + mix) in {s_all:.1f} s, OpenMP over instances",
                "single_thread": {"value": v_one, "blocks": n_one, "seconds": s_one,
                                  "note": "faithful: Godot mixes on one audio thread"},
-               "note": "oracle port of the reference loop (g++ -O2); headless Godot cannot be built here"}
+               "note": "oracle port of the reference loop (gcc -O2), pinned bit for bit against the reference module's own code "
+                       "(oracle/_ref); headless Godot cannot be built here"}
+
+    # ---- the other BASELINE.json configurations (rank 0, N = 1, time-boxed) ---------------------------------------------------
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        dw.mixer.close()
+        del dw
+        torch.cuda.empty_cache()
+        configs = []
+        t_cfg0 = time.perf_counter()
+        for spec in EXTRA_CONFIGS:
+            if time.perf_counter() - t_cfg0 > args.configs_budget:
+                configs.append({"config": spec["name"], "skipped": "time box"})
+                continue
+            try:
+                configs.append(measure_config(gas, torch, spec, local_rank, peak))
+            except Exception as ex:  # a secondary configuration must not take the headline line down with it
+                configs.append({"config": spec["name"], "error": repr(ex)[:300]})
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(w), "voices_per_gpu": V, "frames": F, "channel_pairs": C, "buses": B,
-                       "l2": f"{N_SETS} distinct source sets of {V * F * 8 / 2**20:.0f} MiB rotated (> 4x L2)",
-                       "launch": "CUDA-graph replay of gas_mix_block_device (block k) with gas_gain_compute_device (parameters of block "
-                                 "k+1) beside it on the gain stream, one graph per step",
-                       "pdl": os.environ.get("GAS_PDL", "0"),
-                       "reduce": ("none (1 GPU)" if world == 1 else
-                                  "gas_reduce_bus_exchange_device inside the step graph, one block in flight on the exchange stream: every rank "
-                                  "adds its partial bus buffer into every rank's exchange buffer with vector reductions on peer pointers "
-                                  "(NVLink), one arrival-counter round per block"
-                                  if peer else "torch.distributed all_reduce (NCCL) of the partial bus buffers, one call per step")},
+            "config": bench_config(w, world, peer),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
-            "parity": parity,
+            "parity": parity, "pdl": os.environ.get("GAS_PDL", "default"),
+            "exchange_drain_ms": drain_ms if world > 1 else None, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -563,6 +860,8 @@ def main():
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N > 1: how the partial bus buffers are summed")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE.json configurations")
+    ap.add_argument("--configs-budget", type=float, default=100.0, help="seconds after which remaining secondary configurations are skipped")
     ap.add_argument("--area-fraction", type=float, default=None, help="fraction of voices inside the reverb area (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":

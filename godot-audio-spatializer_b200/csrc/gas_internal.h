@@ -45,11 +45,20 @@ enum : int32_t { MODE_A = 0, MODE_B = 1, MODE_E = 2 };
 // class flags
 #define CLS_SHARED 2u // all sends carry identical weights: one row group fanned out to every bus of the mask
 #define CLS_FILT 4u   // attenuation filter active (linear_attenuation >= 0.001)
+#define CLS_SCALED 8u // every send is send 0 times one scalar per send (the class's aux word): one row group, scaled at the flush
+#define CLS_AUX_NONE 0xffffffffffffffffULL // aux word of a free slot / of a slot whose claimer has not published it yet
+#define CLS_GENERIC 1u // voice-parallel path only: the class of voices whose own class found no slot; one voice per unit
+#define GAS_CLS_GENERIC_SLOTS 6 // (mode A / B / E) x (filter off / on), the last slots of the table, set up at creation
+#define GAS_CLS_DYNAMIC (GAS_MAX_CLASSES - GAS_CLS_GENERIC_SLOTS) // slots claimed and recycled at run time
+#define GAS_CLS_IDLE_BLOCKS 8 // a class slot that stayed empty for this many blocks is recycled
 
 // A class is identified by a 64-bit key; everything a kernel needs to know about it is decoded from the key:
 //   path [0,2)  mode [2,4)  flags [4,8)  n_send [8,12)  bus mask [16,32)  quad [32,44)
+// CLS_SCALED classes are told apart by a second word as well (aux: the float bits of the scale of send 1 in the low
+// half, of send 2 in the high half): two voices share a class only if their sends are the same multiples of send 0.
 struct ClassInfo {
 	unsigned long long key; // 0 = empty
+	float scale[2];         // CLS_SCALED: send 1 = scale[0] * send 0, send 2 = scale[1] * send 0
 	int32_t count;          // voices of the class in this block
 	int32_t path;
 	int32_t mode;
@@ -77,7 +86,8 @@ static __host__ __device__ __forceinline__ ClassInfo cls_decode(unsigned long lo
 	ci.n_send = (int32_t)((key >> 8) & 15u);
 	ci.mask = (uint32_t)((key >> 16) & 0xffffu);
 	ci.quad = (uint32_t)((key >> 32) & 0xfffu);
-	ci.n_group = ci.path == PATH_STREAM ? ((ci.flags & CLS_SHARED) ? 1 : ci.n_send) : ci.n_send;
+	ci.scale[0] = ci.scale[1] = 0.f;
+	ci.n_group = ci.path == PATH_STREAM ? ((ci.flags & (CLS_SHARED | CLS_SCALED)) ? 1 : ci.n_send) : ci.n_send;
 	int rows = 0;
 	if (ci.path == PATH_STREAM) {
 		rows = 2 * ci.n_group;
@@ -105,6 +115,8 @@ struct VoiceRec {
 
 struct BlockPlan {
 	unsigned long long *cls_key; // [GAS_MAX_CLASSES] slot -> class key (0 = free); slots are stable across blocks
+	unsigned long long *cls_aux; // [GAS_MAX_CLASSES] second word of the class identity (CLS_SCALED: the scales), CLS_AUX_NONE when unset
+	int32_t *cls_idle;   // [GAS_MAX_CLASSES] consecutive blocks the slot stayed empty (recycled at GAS_CLS_IDLE_BLOCKS)
 	int32_t *cls_count;  // [2][GAS_MAX_CLASSES] by block parity; block n fills [n & 1] and clears [(n + 1) & 1]
 	int32_t *overflow;   // [1] set when more than GAS_MAX_CLASSES classes were needed
 	int2 *list;          // [GAS_MAX_CLASSES][max_voices] {call-order index j, source row} per list position
@@ -156,6 +168,7 @@ struct gas_ctx {
 	cudaStream_t s_voice = nullptr; // the voice-parallel kernel of a block, beside its streaming kernel (par_voice)
 	cudaEvent_t ev_voice_fork = nullptr, ev_voice_join = nullptr;
 	bool par_voice = false;
+	bool scaled_classes = true; // GAS_K2_SCALED=0 turns the scaled-send classes off (experiments)
 	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_mix_done = nullptr, ev_comm_done = nullptr, ev_join2 = nullptr;
 	bool mix_pending = false, comm_pending = false;
 	bool gain_pending = false, prologue_pending = false;

@@ -407,8 +407,8 @@ __device__ __forceinline__ void voice_loop(float2 (&acc)[NP][2], const unsigned 
 // polynomial at this thread's two frames and add the result to bus `b_own`, or to every bus of `fan` when the
 // group is shared by all sends.  Every accumulator index is a compile-time constant.
 template <int R, int C, int R0>
-__device__ __forceinline__ void flush_group(const float2 (&acc)[R * C][2], bool quad, uint32_t fan, int b_own, float t0, float t1, float *__restrict__ bus,
-		int F, int frame0) {
+__device__ __forceinline__ void flush_group(const float2 (&acc)[R * C][2], bool quad, uint32_t fan, float sc1, float sc2, int b_own, float t0, float t1,
+		float *__restrict__ bus, int F, int frame0) {
 #pragma unroll
 	for (int c = 0; c < C; c++) {
 		const float2 a0 = acc[R0 * C + c][0], a1 = acc[R0 * C + c][1];
@@ -425,12 +425,15 @@ __device__ __forceinline__ void flush_group(const float2 (&acc)[R * C][2], bool 
 		v.y = fmaf(t0, fmaf(t0, c0.y, b0.y), a0.y);
 		v.z = fmaf(t1, fmaf(t1, c1.x, b1.x), a1.x);
 		v.w = fmaf(t1, fmaf(t1, c1.y, b1.y), a1.y);
-		if (fan) { // one row group fanned out to every bus of the mask
+		if (fan) { // one row group fanned out to every bus of the mask: as it is (shared), or times the send's scale (scaled)
 			uint32_t m = fan;
+			float sc = 1.f, nxt = sc1;
 			while (m) {
 				const int b = __ffs(m) - 1;
 				m &= m - 1;
-				red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, v.x, v.y, v.z, v.w);
+				red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, v.x * sc, v.y * sc, v.z * sc, v.w * sc);
+				sc = nxt;
+				nxt = sc2;
 			}
 		} else {
 			red_add_v4(bus + ((size_t)(b_own * C + c) * F + frame0) * 2, v.x, v.y, v.z, v.w);
@@ -498,7 +501,8 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 	const int frame0 = tile * cf.tile_frames + cc.slot * 2;
 	const float t0 = (float)frame0 / (float)F;
 	const float t1 = (float)(frame0 + 1) / (float)F;
-	const uint32_t fan = (ci.flags & CLS_SHARED) ? ci.mask : 0u;
+	const uint32_t fan = (ci.flags & (CLS_SHARED | CLS_SCALED)) ? ci.mask : 0u;
+	const float sc1 = (ci.flags & CLS_SCALED) ? ci.scale[0] : 1.f, sc2 = (ci.flags & CLS_SCALED) ? ci.scale[1] : 1.f;
 	const int RG = ci.n_group; // row groups; group k owns 2 rows (A, B) plus a t^2 row when its quad bit is set
 	uint32_t rest = ci.mask;
 	int r0 = 0; // first row of group k
@@ -508,20 +512,20 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		rest &= rest - 1;
 		// a group starts at row 0, 2, 3 or 4 (at most GAS_K2_MAX_ROWS = 6 rows, 2 or 3 per group)
 		switch (r0) {
-			case 0: flush_group<R, C, 0>(acc, quad, fan, b_own, t0, t1, bus, F, frame0); break;
+			case 0: flush_group<R, C, 0>(acc, quad, fan, sc1, sc2, b_own, t0, t1, bus, F, frame0); break;
 			case 2:
 				if (R >= 4) {
-					flush_group<R, C, (R >= 4 ? 2 : 0)>(acc, quad, fan, b_own, t0, t1, bus, F, frame0);
+					flush_group<R, C, (R >= 4 ? 2 : 0)>(acc, quad, fan, 1.f, 1.f, b_own, t0, t1, bus, F, frame0);
 				}
 				break;
 			case 3:
 				if (R >= 5) {
-					flush_group<R, C, (R >= 5 ? 3 : 0)>(acc, quad, fan, b_own, t0, t1, bus, F, frame0);
+					flush_group<R, C, (R >= 5 ? 3 : 0)>(acc, quad, fan, 1.f, 1.f, b_own, t0, t1, bus, F, frame0);
 				}
 				break;
 			default:
 				if (R >= 6) {
-					flush_group<R, C, (R >= 6 ? 4 : 0)>(acc, quad, fan, b_own, t0, t1, bus, F, frame0);
+					flush_group<R, C, (R >= 6 ? 4 : 0)>(acc, quad, fan, 1.f, 1.f, b_own, t0, t1, bus, F, frame0);
 				}
 				break;
 		}
@@ -564,14 +568,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		// Compact table of the streaming classes of this block, in slot order (identical in every CTA).  The
 		// counts of both parities are fetched together with the block counter so that no load waits for another.
 		constexpr int R = GAS_MAX_CLASSES / 32;
-		unsigned long long key[R];
-		int cnt[2][R];
+		unsigned long long key[R], auxw[R];
+		int cnt[2][R], idle[R];
 		const int n = *(volatile const int32_t *)blk;
 #pragma unroll
 		for (int r = 0; r < R; r++) {
 			key[r] = plan.cls_key[r * 32 + lane];
+			auxw[r] = plan.cls_aux[r * 32 + lane];
 			cnt[0][r] = plan.cls_count[r * 32 + lane];
 			cnt[1][r] = plan.cls_count[GAS_MAX_CLASSES + r * 32 + lane];
+			idle[r] = blockIdx.x == 0 ? plan.cls_idle[r * 32 + lane] : 0;
 		}
 		if (lane == 0) { // while the loads fly
 			for (int s = 0; s < cf.stages; s++) {
@@ -590,9 +596,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 			if (on) {
 				ClassInfo ci = cls_decode(key[r], count);
 				ci.slot = r * 32 + lane;
+				if (ci.flags & CLS_SCALED) {
+					ci.scale[0] = __uint_as_float((unsigned)(auxw[r] & 0xffffffffu));
+					ci.scale[1] = __uint_as_float((unsigned)(auxw[r] >> 32));
+				}
 				s_cls[base + __popc(m & ((1u << lane) - 1u))] = ci;
 			}
 			base += __popc(m);
+			// Slot recycling (one CTA, once per block, between two prologues): a slot whose class stayed empty for
+			// GAS_CLS_IDLE_BLOCKS blocks is handed back.  Nothing reads a slot with a zero count, so clearing it here
+			// cannot race with the other CTAs of this launch or with the voice-parallel kernel.
+			if (blockIdx.x == 0 && r * 32 + lane < GAS_CLS_DYNAMIC && key[r] != 0ULL) {
+				const int age = count > 0 ? 0 : idle[r] + 1;
+				if (age >= GAS_CLS_IDLE_BLOCKS) {
+					plan.cls_aux[r * 32 + lane] = CLS_AUX_NONE;
+					plan.cls_key[r * 32 + lane] = 0ULL;
+					plan.cls_idle[r * 32 + lane] = 0;
+				} else if (age != idle[r]) {
+					plan.cls_idle[r * 32 + lane] = age;
+				}
+			}
 		}
 		__syncwarp();
 		if (tlp) {

@@ -447,6 +447,15 @@ __device__ void voice_chunk_s(const DevTables &t, const ChunkArgs &a, const gas_
 	}
 }
 
+// units of a class: Mode B runs 4 voices per warp, Mode A / effect chains 16; the generic class (voices whose own class
+// found no slot) runs one voice per unit, because its voices do not share a send layout
+__device__ __forceinline__ int units_of(const ClassInfo &ci) {
+	if (ci.flags & CLS_GENERIC) {
+		return ci.count;
+	}
+	return ci.mode == MODE_B ? (ci.count + 3) / 4 : (ci.count + 15) / 16;
+}
+
 template <int C>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t, GlobalCfg g, BlockPlan plan,
 		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks,
@@ -454,8 +463,37 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	extern __shared__ __align__(16) float s_tile[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ int s_ncls;
-	GAS_GRID_DEP_WAIT();
 	GAS_GRID_DEP_LAUNCH();
+	// Programmatic dependent launch: this kernel may become resident while the streaming kernel (its stream predecessor)
+	// still runs.  What it reads first — the class table of the block — was written by the prologue, which completed
+	// before the streaming kernel started, so it is read BEFORE the dependency wait: a block without voice-parallel work
+	// (nothing filtered, no peaks: the common case of the unfiltered mix) ends here, one thread staying behind to keep the
+	// stream order intact, and costs the step nothing but this look.
+	if (replicas <= 1) {
+		__shared__ int s_any;
+		if (threadIdx.x < 32) {
+			const int lane = threadIdx.x;
+			const int n = *(volatile const int32_t *)t.blk;
+			const int par = (n + 1) & 1;
+			int any = 0;
+			for (int i = lane; i < GAS_MAX_CLASSES; i += 32) {
+				const unsigned long long k = plan.cls_key[i];
+				any |= (k != 0ULL && (int)(k & 3u) == PATH_VOICE && plan.cls_count[par * GAS_MAX_CLASSES + i] > 0) ? 1 : 0;
+			}
+			any = __any_sync(0xffffffffu, any);
+			if (lane == 0) {
+				s_any = any;
+			}
+		}
+		__syncthreads();
+		if (!s_any) {
+			if (blockIdx.x == 0 && threadIdx.x == 0) {
+				GAS_GRID_DEP_WAIT();
+			}
+			return;
+		}
+	}
+	GAS_GRID_DEP_WAIT();
 	// fold the streaming kernel's partial sums into the bus buffers: one vector reduction per 16 bytes
 	if (replicas > 1) {
 		const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -516,8 +554,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	{
 		int units = 0;
 		for (int c = 0; c < s_ncls; c++) {
-			const bool per_pair = s_cls[c].mode == MODE_B;
-			units += per_pair ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 15) / 16;
+			units += units_of(s_cls[c]);
 		}
 		cta_has_work = units > (int)blockIdx.x; // units are dealt round-robin to CTAs, then to the warps of a CTA
 	}
@@ -532,12 +569,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	// dealt round-robin to the CTAs, then to the warps of a CTA: this warp owns units b + grid * (w + 8 r), r = 0, 1, ...
 	int total_units = 0;
 	for (int c = 0; c < s_ncls; c++) {
-		total_units += s_cls[c].mode == MODE_B ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 15) / 16;
+		total_units += units_of(s_cls[c]);
 	}
 	for (int unit = (int)blockIdx.x + (int)gridDim.x * my_warp; unit < total_units; unit += (int)gridDim.x * kWarpsPerCta) {
 		int c = 0, k = unit;
 		for (; c < s_ncls; c++) { // class and chunk of the unit: Mode B 4 voices per warp, Mode A / effect chains 16
-			const int chunks = s_cls[c].mode == MODE_B ? (s_cls[c].count + 3) / 4 : (s_cls[c].count + 15) / 16;
+			const int chunks = units_of(s_cls[c]);
 			if (k < chunks) {
 				break;
 			}
@@ -553,6 +590,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 		a.cls_flags = ci.flags;
 		a.mask = ci.mask;
 		a.n_send = ci.n_send;
+		if (ci.flags & CLS_GENERIC) { // one voice, with its own send layout
+			a.list += k;
+			a.count = 1;
+			a.chunk = 0;
+			const InstSends *own = &plan.sends[a.list[0].x];
+			a.mask = own->mask;
+			a.n_send = own->n;
+		}
 		switch (ci.mode) {
 			case MODE_A:
 				voice_chunk_s<MODE_A, C>(t, a, src, src_stride, F, bus, tile, peaks);

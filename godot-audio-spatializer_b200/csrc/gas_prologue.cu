@@ -255,10 +255,12 @@ __device__ __forceinline__ int group_or(unsigned gm, int v) {
 
 __global__ void __launch_bounds__(kCtaThreads, 4) k_prologue(DevTables t, GlobalCfg g, BlockPlan plan, int inst_hwm, int n_voices,
 		const gas_voice *__restrict__ voices, int src_rows, float4 *__restrict__ bus, int bus_f4, float4 *__restrict__ rep, int rep_f4,
-		float2 *__restrict__ peaks) {
+		float2 *__restrict__ peaks, int g_scaled_classes) {
 	__shared__ unsigned long long s_key[kVoicesPerCta];  // classes met in this CTA
 	__shared__ int s_cnt[kVoicesPerCta], s_cid[kVoicesPerCta], s_base[kVoicesPerCta];
 	__shared__ unsigned long long s_gkey[GAS_MAX_CLASSES]; // snapshot of the global slot table
+	__shared__ unsigned long long s_gaux[GAS_MAX_CLASSES];
+	__shared__ unsigned long long s_aux[kVoicesPerCta];    // aux word of the classes met in this CTA
 	__shared__ int s_parity;
 
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -290,9 +292,11 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_prologue(DevTables t, Global
 	}
 	for (int i = threadIdx.x; i < GAS_MAX_CLASSES; i += kCtaThreads) {
 		s_gkey[i] = plan.cls_key[i];
+		s_gaux[i] = plan.cls_aux[i];
 	}
 	if (threadIdx.x < kVoicesPerCta) {
 		s_key[threadIdx.x] = 0ULL;
+		s_aux[threadIdx.x] = CLS_AUX_NONE;
 		s_cnt[threadIdx.x] = 0;
 		s_cid[threadIdx.x] = -1;
 		s_base[threadIdx.x] = 0;
@@ -397,6 +401,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_prologue(DevTables t, Global
 	int n_fx = 0, fx_stage = 1;
 	float fx_coef[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
 	bool shared = false;
+	unsigned long long aux = CLS_AUX_NONE; // second word of the class identity
 
 	if (live) {
 		mode = imode & 0xff;
@@ -463,6 +468,25 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_prologue(DevTables t, Global
 			}
 		}
 		const bool has_dsp = filt || (mode == MODE_E && n_fx > 0);
+		if (mode == MODE_B) {
+			// Every Mode-B proxy is a playback of its own: AudioServer runs _mix_step_for_channel for every pair of every
+			// bus of its map, with volume 0 for the pairs the map masks out (reference audio_spatializer.cpp:298-312).
+			// 0 * x only matters when the proxy's buffer is not finite, which the module produces itself (NaN pan gains,
+			// SURVEY Q1): the NaN then reaches every pair of every bus the instance sends to, same side.  A NaN ramp end
+			// point of any pair therefore poisons this side's send volumes of the voice.
+			int bad = (c < C && (m_prev != m_prev || m_new != m_new)) ? 1 : 0;
+			bad |= __shfl_xor_sync(gm, bad, 2);
+			bad |= __shfl_xor_sync(gm, bad, 4);
+			if (bad) {
+				const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+				for (int k = 0; k < GAS_MAX_SENDS; k++) {
+					if (k < n_send) {
+						snd.vn[k] = qnan;
+					}
+				}
+			}
+		}
 
 		// weight polynomial per (send, pair, side): w(t) = A + B t + Cq t^2 with t = i/F, from
 		// (vn*t + (1-t)*vp) of the AudioServer ramp times (m_new*t + (1-t)*m_prev) of mix_channel.
@@ -485,14 +509,50 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_prologue(DevTables t, Global
 			q_bits = group_or(gm, q_bits);
 			differs = group_or(gm, differs);
 			shared = n_send >= 2 && !differs;
-			n_group = shared ? 1 : n_send;
-			quad = shared ? (q_bits ? 1u : 0u) : (uint32_t)q_bits;
+			// Scaled sends: every further send is send 0 times ONE scalar (same for both ramp end points, all pairs, both
+			// sides) — what a reverb send with uniformity 0 is (reverb_vol = direct * area_send, reference
+			// audio_spatializer_3d.cpp:192-196, so bus_vol / mix_vol is area_send to the last bit or two on every pair).
+			// Such a voice needs one row group: the flush adds the sums to bus 0 as they are and to the other buses times
+			// the class's scales.  The scalar of a send is taken from the first lane with a non-zero base volume; a lane
+			// accepts it if it reproduces its own volumes within 3e-7 relative (2-3 ulp: far inside the 1e-5 tolerance).
+			bool scaled = false;
+			float sc1 = 0.f, sc2 = 0.f;
+			if (n_send >= 2 && n_send <= 3 && !shared && g_scaled_classes) {
+				const bool base_nz = c < C && (snd.vn[0] != 0.f || snd.vp[0] != 0.f);
+				const unsigned nzm = __ballot_sync(gm, base_nz) & gm;
+				int ok = nzm != 0u;
+				if (ok) {
+					const int src_lane = __ffs(nzm) - 1;
+					const float bn = snd.vn[0], bp = snd.vp[0];
+					const bool use_n = bn != 0.f;
+					const float r1 = use_n ? snd.vn[1] / bn : snd.vp[1] / bp;
+					const float r2 = n_send > 2 ? (use_n ? snd.vn[2] / bn : snd.vp[2] / bp) : 0.f;
+					sc1 = __shfl_sync(gm, r1, src_lane);
+					sc2 = __shfl_sync(gm, r2, src_lane);
+					if (c < C) {
+						const float tol = 3e-7f;
+						ok = fabsf(snd.vn[1] - sc1 * bn) <= tol * fabsf(snd.vn[1]) && fabsf(snd.vp[1] - sc1 * bp) <= tol * fabsf(snd.vp[1]);
+						if (n_send > 2) {
+							ok = ok && fabsf(snd.vn[2] - sc2 * bn) <= tol * fabsf(snd.vn[2]) && fabsf(snd.vp[2] - sc2 * bp) <= tol * fabsf(snd.vp[2]);
+						}
+						ok = ok && (sc1 == sc1) && (sc2 == sc2) && fabsf(sc1) < 3.0e38f && fabsf(sc2) < 3.0e38f;
+					}
+				}
+				ok = !group_or(gm, ok ? 0 : 1);
+				scaled = ok != 0;
+			}
+			n_group = (shared || scaled) ? 1 : n_send;
+			quad = (shared || scaled) ? ((scaled ? (q_bits & 1) : q_bits) ? 1u : 0u) : (uint32_t)q_bits;
 			n_rows = 2 * n_group + __popc(quad);
 			if (n_rows <= GAS_K2_MAX_ROWS) {
 				streamed = true;
 				path = PATH_STREAM;
 				if (shared) {
 					cflags |= CLS_SHARED;
+				}
+				if (scaled) {
+					cflags |= CLS_SCALED;
+					aux = (unsigned long long)__float_as_uint(sc1) | ((unsigned long long)__float_as_uint(sc2) << 32);
 				}
 				if (v.src_row < 0) {
 					path = PATH_NONE; // silent source, no DSP state to advance: contributes exactly nothing
@@ -513,7 +573,13 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_prologue(DevTables t, Global
 	}
 
 	// ---- class lookup: once per class per CTA in shared memory, then one global atomic per class ------------
-	const unsigned long long key = path != PATH_NONE ? cls_key(path, mode, cflags, n_send, mask, quad) : 0ULL;
+	// A class is (key, aux).  The key of a scaled class carries a 20-bit hash of its aux word in its spare bits, so that
+	// the compare-and-swap that claims a slot sees (almost always) the whole identity; the aux words are compared once
+	// they are published (after the barrier in the CTA table; after a short wait in the global table).
+	unsigned long long key = path != PATH_NONE ? cls_key(path, mode, cflags, n_send, mask, quad) : 0ULL;
+	if (key != 0ULL && aux != CLS_AUX_NONE) {
+		key |= ((aux * 0x9E3779B97F4A7C15ULL) >> 44) << 44;
+	}
 	int slot = -1, lpos = 0;
 	if (key != 0ULL && l == 0) {
 		for (int i = 0; i < kVoicesPerCta; i++) {
@@ -522,6 +588,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_prologue(DevTables t, Global
 				k = atomicCAS(&s_key[i], 0ULL, key);
 				if (k == 0ULL) {
 					k = key;
+					s_aux[i] = aux;
 				}
 			}
 			if (k == key) {
@@ -529,48 +596,83 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_prologue(DevTables t, Global
 				break;
 			}
 		}
-		lpos = atomicAdd(&s_cnt[slot], 1);
 	}
 	__syncthreads();
-	if (threadIdx.x < kVoicesPerCta && s_key[threadIdx.x] != 0ULL) {
-		// Slots are stable across blocks: in the steady state the key is already in the snapshot and the only
+	if (slot >= 0 && s_aux[slot] != aux) {
+		// two scaled classes whose aux words hash alike met in one CTA (one in 2^20 pairs): this voice takes the generic
+		// class of the voice-parallel kernel instead, which mixes any voice
+		slot = -2;
+	}
+	if (slot >= 0) {
+		lpos = atomicAdd(&s_cnt[slot], 1);
+	}
+	int gpos = 0; // position in the generic class when slot == -2
+	const int generic_cid = GAS_CLS_DYNAMIC + mode * 2 + ((cflags & CLS_FILT) ? 1 : 0);
+	if (slot == -2) {
+		gpos = atomicAdd(&cnt_now[generic_cid], 1);
+	}
+	__syncthreads();
+	if (threadIdx.x < kVoicesPerCta && s_key[threadIdx.x] != 0ULL && s_cnt[threadIdx.x] > 0) {
+		// Slots are stable across blocks: in the steady state the class is already in the snapshot and the only
 		// global operation is the add that reserves this CTA's range of the class list.
 		const unsigned long long k = s_key[threadIdx.x];
+		const unsigned long long ka = s_aux[threadIdx.x];
 		int cid = -1;
-		for (int i = 0; i < GAS_MAX_CLASSES; i++) {
-			if (s_gkey[i] == k) {
+		for (int i = 0; i < GAS_CLS_DYNAMIC; i++) {
+			if (s_gkey[i] == k && s_gaux[i] == ka) {
 				cid = i;
 				break;
 			}
 		}
-		if (cid < 0) { // first appearance of the class: claim a free slot
-			for (int i = 0; i < GAS_MAX_CLASSES && cid < 0; i++) {
+		if (cid < 0) { // first appearance of the class: claim a free slot, or find the one another CTA just claimed
+			for (int i = 0; i < GAS_CLS_DYNAMIC && cid < 0; i++) {
 				unsigned long long o = s_gkey[i];
 				if (o != 0ULL && o != k) {
 					continue;
 				}
 				o = atomicCAS(&plan.cls_key[i], 0ULL, k);
-				if (o == 0ULL || o == k) {
+				if (o == 0ULL) {
+					*(volatile unsigned long long *)&plan.cls_aux[i] = ka; // the claimer publishes the aux word
+					__threadfence();
 					cid = i;
+				} else if (o == k) {
+					// another CTA owns the slot under the same key: the same class if its aux word matches.  Its claimer
+					// publishes the aux word right after its compare-and-swap; give it a moment, then look elsewhere (a class
+					// may end up in two slots during the block it first appears in: the kernels treat them as two classes).
+					unsigned long long a = *(volatile unsigned long long *)&plan.cls_aux[i];
+					if (ka != CLS_AUX_NONE) {
+						for (int spin = 0; spin < 256 && a == CLS_AUX_NONE; spin++) {
+							a = *(volatile unsigned long long *)&plan.cls_aux[i];
+						}
+					}
+					if (a == ka) {
+						cid = i;
+					}
 				}
 			}
 			if (cid < 0) {
+				// more distinct classes than slots: the voices go to the generic class of their mode
 				*plan.overflow = 1;
+				const int kmode = (int)((k >> 2) & 3u);
+				const int kfilt = ((k >> 4) & CLS_FILT) ? 1 : 0;
+				cid = GAS_CLS_DYNAMIC + kmode * 2 + kfilt;
 			}
 		}
-		if (cid >= 0) {
-			s_base[threadIdx.x] = atomicAdd(&cnt_now[cid], s_cnt[threadIdx.x]);
-		}
+		s_base[threadIdx.x] = atomicAdd(&cnt_now[cid], s_cnt[threadIdx.x]);
 		s_cid[threadIdx.x] = cid;
 	}
 	__syncthreads();
 	slot = __shfl_sync(gm, slot, threadIdx.x & 24);
 	lpos = __shfl_sync(gm, lpos, threadIdx.x & 24);
-	const int cid = slot >= 0 ? s_cid[slot] : -1;
+	gpos = __shfl_sync(gm, gpos, threadIdx.x & 24);
+	const int cid = slot >= 0 ? s_cid[slot] : (slot == -2 ? generic_cid : -1);
 	if (cid >= 0) {
-		const int pos = s_base[slot] + lpos;
+		const int pos = slot >= 0 ? s_base[slot] + lpos : gpos;
 		if (l == 0) {
 			plan.list[(size_t)cid * maxv + pos] = make_int2(j, v.src_row);
+		}
+		if (cid >= GAS_CLS_DYNAMIC) {
+			path = PATH_VOICE; // generic class: the voice-parallel kernel mixes any voice
 		}
 		if (path == PATH_STREAM) {
 			if (c < C) {
@@ -646,7 +748,7 @@ cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voice
 	work = work > 1 ? work : 1;
 	const int blocks = (work + kVoicesPerCta - 1) / kVoicesPerCta;
 	cudaError_t e = gas_launch(k_prologue, dim3(blocks), dim3(kCtaThreads), 0, st, (ctx->pdl & 1) != 0, ctx->t, ctx->g, ctx->plan, ctx->inst_hwm, n_voices,
-			d_voices, src_rows, (float4 *)d_bus, bus_f4, (float4 *)ctx->d_rep, rep_f4, (float2 *)d_peaks);
+			d_voices, src_rows, (float4 *)d_bus, bus_f4, (float4 *)ctx->d_rep, rep_f4, (float2 *)d_peaks, ctx->scaled_classes ? 1 : 0);
 	ctx->launches++;
 	return e;
 }

@@ -193,9 +193,26 @@ inline int blocks_for(int n) { return (n + 127) / 128; }
 	ctx->launches++;                                             \
 	return cudaGetLastError();
 
+// class table of the block plan: every slot free, aux words unset, the generic classes in the last slots
+__global__ void k_plan_defaults(BlockPlan plan) {
+	const int i = threadIdx.x;
+	if (i >= GAS_MAX_CLASSES) {
+		return;
+	}
+	plan.cls_aux[i] = CLS_AUX_NONE;
+	plan.cls_idle[i] = 0;
+	unsigned long long key = 0ULL;
+	if (i >= GAS_CLS_DYNAMIC) {
+		const int k = i - GAS_CLS_DYNAMIC; // mode * 2 + filter
+		key = cls_key(PATH_VOICE, k >> 1, CLS_GENERIC | ((k & 1) ? CLS_FILT : 0u), 0, 0u, 0u);
+	}
+	plan.cls_key[i] = key;
+}
+
 cudaError_t launch_defaults(gas_ctx *ctx, cudaStream_t st) {
 	k_defaults<<<64, 128, 0, st>>>(ctx->t, ctx->g);
-	ctx->launches++;
+	k_plan_defaults<<<1, GAS_MAX_CLASSES, 0, st>>>(ctx->plan);
+	ctx->launches += 2;
 	return cudaGetLastError();
 }
 cudaError_t launch_instance_init(gas_ctx *ctx, int n, const int32_t *d_ids, const int32_t *d_spat, cudaStream_t st) { LAUNCH1(k_instance_init, n, d_ids, d_spat) }

@@ -132,15 +132,19 @@ def run(mixer, sc, collect_state=True):
 
 
 def sample_close(got, want, rel=REL_TOL, abs_tol=ABS_TOL):
-    """north-star sample criterion: |g-w| <= rel*|w|  or  |g-w| < abs_tol.  Returns (ok, worst)."""
+    """north-star sample criterion: |g-w| <= rel*|w|  or  |g-w| < abs_tol.  Returns (ok, worst, n_bad).
+    A NaN passes only against a NaN in the same place (the reference produces NaN gains itself)."""
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
-    err = np.abs(got - want)
-    ok = (err <= rel * np.abs(want)) | (err < abs_tol)
-    worst = float(err.max()) if err.size else 0.0
+    both_nan = np.isnan(got) & np.isnan(want)
+    with np.errstate(invalid="ignore"):
+        err = np.abs(got - want)
+        ok = (err <= rel * np.abs(want)) | (err < abs_tol) | both_nan
+    finite = err[np.isfinite(err)]
+    worst = float(finite.max()) if finite.size else 0.0
     return bool(ok.all()), worst, int((~ok).sum())
 
 
 def routing(bus):
-    """Boolean [bus, pair, side] pattern of non-silent outputs: the bit-exact routing gate."""
-    return (np.abs(np.asarray(bus)).max(axis=2) > 0)
+    """Boolean [bus, pair, side] pattern of non-silent outputs: the bit-exact routing gate (a NaN counts as signal)."""
+    return (np.nan_to_num(np.abs(np.asarray(bus)), nan=1.0).max(axis=2) > 0)

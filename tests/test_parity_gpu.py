@@ -134,3 +134,105 @@ def test_empty_block_and_invalid_arguments(gas):
         bad = abi.spatializer_defaults(max_distance=-1.0)
         with pytest.raises(gas.GasError):
             m.spatializer_set(0, bad)  # reference audio_spatializer_3d.cpp:671
+
+
+@pytest.mark.parametrize("tracking", [1, 2])
+def test_doppler_tracking(gas, orc, tracking):
+    """Doppler pitch (audio_spatializer_3d.cpp:405-434): moving emitters, two moving / rotated listeners."""
+    listeners = [S.synth.rotated_listener(velocity=(1.0, -2.0, 0.5)), S.synth.rotated_listener(yaw=-1.1, origin=(-5, 0, 2), velocity=(0, 0, 0))]
+    sc = S.default_scenario(name=f"doppler-{tracking}", voices=50, speaker_mode=abi.SPEAKER_SURROUND_51, listeners=listeners, blocks=2,
+                            spat=dict(mix_channel_mode=1, doppler_tracking=tracking, doppler_speed_of_sound=200.0))
+    got, want = _run_both(gas, orc, sc)
+    _check(got, want, sc)
+    assert np.ptp(want["params"][0]["pitch_scale"]) > 1e-3, "Doppler did not move the pitch"
+
+
+@pytest.mark.parametrize("speakers", ["3.1", "5.1", "7.1"])
+@pytest.mark.parametrize("filt", [False, True])
+def test_q1_non_integer_tightness_nan_like_the_reference(gas, orc, speakers, filt):
+    """un-normalised source direction into SPCAP with a non-integer tightness gives pow(negative, frac) = NaN
+    in the reference (audio_spatializer_3d.cpp:391 -> :930).  The CUDA path must produce NaN gains for the same voices and
+    NaN on the same (bus, pair, side) outputs — including the pairs the NaN reaches through the masked-out, zero-volume
+    proxy sends of Mode B (pinned by oracle/_ref) — and finite values everywhere else."""
+    sc = S.default_scenario(name=f"q1-{speakers}-{filt}", voices=64, speaker_mode=SPEAKERS[speakers], blocks=2,
+                            spat=dict(mix_channel_mode=1, panning_strength=0.37), force_filter_off=not filt,
+                            area=dict(reverb_bus=1, amount=0.5), area_fraction=0.5)
+    got, want = _run_both(gas, orc, sc)
+    assert np.isnan(want["params"][0]["mix_volumes"]).any(), "scenario did not reach the NaN case"
+    for b in range(len(want["bus"])):
+        assert np.array_equal(np.isnan(got["bus"][b]), np.isnan(want["bus"][b])), f"block {b}: NaN pattern differs"
+    _check(got, want, sc, state=False)
+    # Mode A keeps the NaN on the pairs whose own mix volume is NaN (one proxy, no masked-out sends)
+    sc = S.default_scenario(name=f"q1-A-{speakers}", voices=64, speaker_mode=SPEAKERS[speakers], blocks=2,
+                            spat=dict(mix_channel_mode=0, panning_strength=1.3), force_filter_off=not filt)
+    got, want = _run_both(gas, orc, sc)
+    for b in range(len(want["bus"])):
+        assert np.array_equal(np.isnan(got["bus"][b]), np.isnan(want["bus"][b])), f"Mode A block {b}: NaN pattern differs"
+    _check(got, want, sc, state=False)
+
+
+def test_scaled_send_classes(gas, orc):
+    """Reverb sends with uniformity 0 are the direct send times the area's amount: the streaming kernel keeps one row
+    group for such voices and scales at the flush.  Several areas' worth of amounts, a third (override) bus, and the
+    block in which the sends fade in (not scaled: quadratic ramp) all have to match the oracle."""
+    for amount, override in ((0.5, False), (0.3, True), (1.7, False)):
+        sc = S.default_scenario(name=f"scaled-{amount}", voices=96, speaker_mode=abi.SPEAKER_SURROUND_71, num_buses=3,
+                                spat=dict(mix_channel_mode=1, unit_size=1.0, attenuation_filter_db=-80.0), force_filter_off=True,
+                                area=dict(reverb_bus=1, amount=amount, override_bus=override, bus=2), area_fraction=0.5, blocks=4)
+        got, want = _run_both(gas, orc, sc)
+        _check(got, want, sc)
+
+
+def test_full_size_configs_1_and_3(gas, orc):
+    """BASELINE.json configs[1] (1024 voices, 5.1, inverse-square + attenuation filter) and configs[3] (4096-voice
+    AudioSpatializerEffect chain before three buses) at FULL size against the oracle."""
+    sc = S.default_scenario(name="cfg1-full", voices=1024, speaker_mode=abi.SPEAKER_SURROUND_51, blocks=2,
+                            spat=dict(mix_channel_mode=1, attenuation_model=abi.ATTENUATION_INVERSE_SQUARE_DISTANCE),
+                            area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25, want_peak_every=16)
+    got, want = _run_both(gas, orc, sc)
+    _check(got, want, sc)
+    chain = [dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=4000.0, resonance=1.0, gain=0.3, stages=2),
+             dict(mode=abi.FILTER_LOWPASS, cutoff_hz=9000.0, resonance=0.7, gain=1.0, stages=1)]
+    sc = S.default_scenario(name="cfg3-full", voices=4096, speaker_mode=abi.SPEAKER_MODE_STEREO, num_buses=3, effect_chain=chain,
+                            effect_gain_binding=0, area=dict(reverb_bus=2, amount=0.4, override_bus=True, bus=1), area_fraction=0.5, blocks=2)
+    got, want = _run_both(gas, orc, sc)
+    _check(got, want, sc)
+
+
+def test_class_table_overflow_falls_back_to_the_generic_class(gas, orc):
+    """More distinct routing classes than the plan has slots: the voices whose class found no slot go through the generic
+    class of the voice-parallel kernel and are still mixed (round 1 dropped them).  150+ classes are made with one
+    instance per distinct (bus mask, scale) combination through gas_params_set."""
+    V, F = 200, 128
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, max_spatializers=2, num_buses=16, speaker_mode=abi.SPEAKER_MODE_STEREO,
+               mix_rate=48000.0)
+    rng = np.random.default_rng(5)
+    inst = np.arange(V, dtype=np.int32)
+    p = np.zeros(V, dtype=abi.params)
+    p["pitch_scale"] = 1.0
+    p["update_parameters"] = 1
+    p["mix_volumes"][:, 0, :] = rng.uniform(0.2, 1.0, (V, 2)).astype(np.float32)
+    for i in range(V):  # instance i: Master plus one more bus at its own scale: 200 distinct (mask, scale) classes > 122 slots
+        p["n_bus"][i] = 2
+        p["bus"][i, :2] = [0, 1 + i % 15]
+        p["bus_volumes"][i, 0, 0] = p["mix_volumes"][i, 0]
+        p["bus_volumes"][i, 1, 0] = p["mix_volumes"][i, 0] * np.float32(0.2 + 0.003 * i)
+    voices = S.synth.make_voices(V)
+    src = S.synth.make_sources(V, F)
+    out = []
+    for mk in (lambda: gas.Mixer(**cfg), lambda: orc.OracleMixer(**cfg)):
+        with mk() as m:
+            m.spatializer_set(0, abi.spatializer_defaults(mix_channel_mode=1))
+            m.instance_init(inst, 0)
+            m.params_set(inst, p)
+            m.instance_start(inst)
+            m.voice_init(inst)
+            blocks = []
+            for b in range(3):
+                m.params_set(inst, p)
+                blocks.append(m.mix_block(voices, src, F, want_peaks=False)[0])
+            out.append(blocks)
+    for b, (bg, bw) in enumerate(zip(*out)):
+        assert np.array_equal(S.routing(bg), S.routing(bw)), f"block {b}: routing differs"
+        ok, worst, nbad = S.sample_close(bg, bw)
+        assert ok, f"block {b}: {nbad} samples out of tolerance, worst {worst:.3e}"
