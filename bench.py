@@ -194,7 +194,7 @@ def bench_config(w, world, peer=True):
     return {"workload": workload_name(w), "voices_per_gpu": V, "frames": F, "channel_pairs": C, "buses": B,
             "l2": f"{N_SETS} distinct source sets of {V * F * 8 / 2**20:.0f} MiB rotated (> 4x L2)",
             "launch": "CUDA-graph replay of gas_mix_block_device (block k) with gas_gain_compute_device (parameters of block "
-                      "k+1) beside it on the gain stream, one graph per step",
+                      "k+1) beside it on the gain stream; up to 8 consecutive steps per graph launch",
             "reduce": ("none (1 GPU)" if world == 1 else
                        "gas_reduce_bus_exchange_device inside the step graph, one block in flight on the exchange stream: every rank "
                        "adds its partial bus buffer into every rank's exchange buffer with vector reductions on peer pointers "
@@ -302,13 +302,29 @@ class DeviceWorkload:
             m.gain_compute_device(w["voices"], self.d_emitters[(s + 1) % N_SETS].data_ptr())
         return self.d_bus[k % 2]
 
-    def capture_steps(self):
+    def capture_steps(self, chunk=1):
+        """One CUDA graph per `chunk` consecutive steps (chunk divides N_SETS): graph g replays steps g*chunk .. g*chunk+chunk-1 of
+        the source-set rotation.  Several steps per graph take the graph-to-graph launch gap off all but one step in `chunk`."""
         graphs = []
-        for s in range(N_SETS):
+        for g in range(N_SETS // chunk):
             self.mixer.capture_begin()
-            self.step_device(s)
+            for j in range(chunk):
+                self.step_device(g * chunk + j)
             graphs.append(self.mixer.capture_end())
         return graphs
+
+
+def steps_per_graph(K):
+    """Largest of 8, 4, 2, 1 that divides the timed step count (GAS_BENCH_CHUNK overrides)."""
+    forced = os.environ.get("GAS_BENCH_CHUNK")
+    if forced:
+        c = int(forced)
+        if c in (1, 2, 4, 8) and K % c == 0:
+            return c
+    for c in (8, 4, 2):
+        if K % c == 0:
+            return c
+    return 1
 
 
 def parity_gate(gas, w, device, abi, synth, parity_src, host_inputs):
@@ -612,8 +628,12 @@ def gpu_arm(args):
     if args.area_fraction is not None:
         w["area_fraction"] = args.area_fraction
     V, F, C, B = w["voices"], w["frames"], w["speaker_mode"] + 1, w["num_buses"]
-    # every step graph is launched at least once before the timed region (first launches upload the graph)
-    K, W = args.steps, max(3, args.warmup, N_SETS)
+    # every step graph is launched at least once before the timed region (first launches upload the graph); the warm-up is
+    # rounded up to whole graphs
+    K = args.steps
+    chunk = steps_per_graph(K)
+    W = max(3, args.warmup, N_SETS)
+    W = ((W + chunk - 1) // chunk) * chunk
 
     parity_src = synth.make_sources(V, F, block=0, mix_rate=w["mix_rate"]) if (rank == 0 and not args.no_parity) else None
     dw = DeviceWorkload(gas, torch, w, local_rank, rank, parity_src)
@@ -630,14 +650,19 @@ def gpu_arm(args):
     peer = dist is not None and args.reduce == "peer"
     if peer:
         dw.comm_setup(dist)
-    graphs = dw.capture_steps()
+    if dist is not None and not peer:
+        chunk = 1  # the NCCL variant reduces between graph launches
+        W = max(3, args.warmup, N_SETS)
+    graphs = dw.capture_steps(chunk)
     sampler = ClockSampler(local_rank)  # NVML initialised here, outside the timed region
 
-    def one_step(k):
-        m.graph_launch(graphs[k % N_SETS])
-        if dist is not None and not peer and not os.environ.get("GAS_BENCH_NOREDUCE"):
-            with torch.cuda.stream(stream):
-                dist.all_reduce(dw.d_bus[k % 2])  # sum of the per-GPU partial bus buffers (NCCL over NVLink)
+    def run_steps(k0, n):
+        # steps k0 .. k0 + n - 1 (k0 and n multiples of `chunk`): one graph launch per `chunk` steps
+        for k in range(k0, k0 + n, chunk):
+            m.graph_launch(graphs[(k // chunk) % len(graphs)])
+            if dist is not None and not peer and not os.environ.get("GAS_BENCH_NOREDUCE"):
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(dw.d_bus[k % 2])  # sum of the per-GPU partial bus buffers (NCCL over NVLink)
 
     def barrier():
         if dist is not None:
@@ -647,8 +672,7 @@ def gpu_arm(args):
 
     # ---- timed region: `value` ----------------------------------------------------------------------------
     dw.reduce_prime()
-    for k in range(W):
-        one_step(k)
+    run_steps(0, W)
     dw.reduce_drain(W - 1)
     barrier()
     sampler.start()
@@ -662,8 +686,7 @@ def gpu_arm(args):
     t_wall0 = time.time()
     with torch.cuda.stream(stream):
         ev0.record()
-    for k in range(K):
-        one_step(W + k)
+    run_steps(W, K)
     with torch.cuda.stream(stream):
         ev1.record()
     gpu_launches = m.kernel_launches - launches0
@@ -839,7 +862,7 @@ def gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": bench_config(w, world, peer),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
-            "parity": parity, "pdl": os.environ.get("GAS_PDL", "default"),
+            "parity": parity, "pdl": os.environ.get("GAS_PDL", "default"), "steps_per_graph_launch": chunk,
             "exchange_drain_ms": drain_ms if world > 1 else None, "configs": configs,
         }
         print(json.dumps(line), flush=True)

@@ -50,13 +50,16 @@ processor_state = np.dtype([("b0", f4), ("b1", f4), ("b2", f4), ("a1", f4), ("a2
 voice_state = np.dtype([("prev_mix_volumes", f4, (MAX_CHANNELS_PER_BUS, 2)),
                         ("filter_processors", processor_state, (2 * MAX_CHANNELS_PER_BUS,)),
                         ("effect_history", f4, (MAX_EFFECTS, 2, MAX_FILTER_STAGES, 4))], align=True)
+voice_life = np.dtype([("lookahead", frame, (LOOKAHEAD_BUFFER_SIZE,)), ("flags", u4)], align=True)
+VOICE_ACTIVE, VOICE_HAS_FRAMES = 1, 2
+STATUS_CLASS_OVERFLOW = 1
 config = np.dtype([("device", i4), ("max_instances", i4), ("max_voices", i4), ("max_frames", i4),
                    ("max_spatializers", i4), ("num_buses", i4), ("speaker_mode", i4), ("mix_rate", f4),
                    ("global_panning_strength", f4)], align=True)
 
 # gas_struct_id order (include/gas.h)
 STRUCT_IDS = [frame, effect, effect_chain, spatializer, listener, area, emitter, params, voice,
-              processor_state, voice_state, config]
+              processor_state, voice_state, config, voice_life]
 
 
 def check_layout(sizeof_fn, who):

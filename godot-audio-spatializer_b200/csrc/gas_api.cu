@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 static thread_local std::string g_create_error;
 
@@ -83,6 +84,13 @@ void refresh_globals(gas_ctx *ctx) {
 int gain_side_begin(gas_ctx *ctx) {
 	if (ctx->prologue_pending) {
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_gain, ctx->ev_prologue_done, 0));
+	}
+	if (ctx->stream_started_pending) {
+		// ... and for the streaming kernel of that block to have all its CTAs resident: the gain kernel's many small CTAs
+		// would otherwise take the SMs first and hold the streaming kernel's one-CTA-per-SM grid up by most of their own
+		// duration (measured: its CTAs started 8 us late on average); started afterwards they run beside it
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_gain, ctx->ev_stream_started, 0));
+		ctx->stream_started_pending = false;
 	}
 	return GAS_OK;
 }
@@ -195,7 +203,7 @@ int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_fr
 	if (ctx->gain_pending) {
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
 	}
-	if (ctx->comm_pending && !ctx->capturing) { // an exchange on the exchange stream may still read / write bus buffers
+	if (ctx->comm_pending) { // an exchange on the exchange stream may still read / write bus buffers (inside a capture this is a graph edge)
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_comm_done, 0));
 		ctx->comm_pending = false;
 	}
@@ -214,7 +222,7 @@ int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_fr
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_voice, ctx->ev_voice_fork, 0));
 		pp = prof_open(ctx, GAS_KERNEL_MIX_VOICE, ctx->s_voice);
 		if (!(ctx->skip & 4)) {
-			GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_voice));
+			GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_voice, false));
 		}
 		prof_close(ctx, pp);
 		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_voice_join, ctx->s_voice));
@@ -234,14 +242,12 @@ int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_fr
 		prof_close(ctx, pp);
 		pp = prof_open(ctx, GAS_KERNEL_MIX_VOICE);
 		if (!(ctx->skip & 4)) {
-			GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_mix));
+			GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_mix, !(ctx->skip & 2)));
 		}
 		prof_close(ctx, pp);
 	}
-	if (!ctx->capturing) {
-		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_mix_done, ctx->s_mix));
-		ctx->mix_pending = true;
-	}
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_mix_done, ctx->s_mix)); // inside a capture: the edge a later exchange of this block hangs on
+	ctx->mix_pending = true;
 	return GAS_OK;
 }
 
@@ -265,6 +271,7 @@ size_t gas_abi_sizeof(int32_t id) {
 		case GAS_STRUCT_PROCESSOR_STATE: return sizeof(gas_processor_state);
 		case GAS_STRUCT_VOICE_STATE: return sizeof(gas_voice_state);
 		case GAS_STRUCT_CONFIG: return sizeof(gas_config);
+		case GAS_STRUCT_VOICE_LIFE: return sizeof(gas_voice_life);
 		default: return 0;
 	}
 }
@@ -365,6 +372,8 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 		// default, for the caller to turn on for filter / effect-chain heavy scenes.
 		e = getenv("GAS_K3_PARALLEL");
 		ctx->par_voice = e && atoi(e) != 0;
+		e = getenv("GAS_K1_GATE");
+		ctx->gain_after_stream = !(e && atoi(e) == 0);
 		e = getenv("GAS_K2_SCALED");
 		ctx->scaled_classes = !(e && atoi(e) == 0);
 		e = getenv("GAS_K2_REPLICAS");
@@ -404,6 +413,15 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->t.vs_prev, V * 8);
 	ALLOC(ctx->t.vs_proc, V * 8);
 	ALLOC(ctx->t.vs_fx, V * (size_t)(GAS_MAX_EFFECTS * 2 * GAS_MAX_FILTER_STAGES * 4));
+	ALLOC(ctx->t.vs_look, V * (size_t)GAS_LOOKAHEAD_BUFFER_SIZE);
+	ALLOC(ctx->t.vs_life, V);
+	ALLOC(ctx->t.inst_threshold, I);
+	ctx->t.max_voices = (int32_t)V;
+	ctx->t.threshold_default = expf(-80.0f * (float)0.11512925464970228420089957273422); // upstream Math::db_to_linear(float)
+	ALLOC(ctx->d_stage, V * F);
+	ALLOC(ctx->d_voices_stage, V);
+	ALLOC(ctx->d_mixed, V);
+	ALLOC(ctx->d_status, V);
 	ALLOC(ctx->plan.cls_key, (size_t)GAS_MAX_CLASSES);
 	ALLOC(ctx->plan.cls_aux, (size_t)GAS_MAX_CLASSES);
 	ALLOC(ctx->plan.cls_idle, (size_t)GAS_MAX_CLASSES);
@@ -434,6 +452,7 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_gain, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_comm, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_voice, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_stream_started, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_voice_fork, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_voice_join, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_mix_done, cudaEventDisableTiming) == cudaSuccess;
@@ -476,7 +495,8 @@ void gas_destroy(gas_ctx *ctx) {
 		ctx->t.inst_prev, ctx->t.inst_mode, ctx->t.blk, ctx->t.inst_fx, ctx->plan.sends, ctx->t.vs_prev, ctx->t.vs_proc, ctx->t.vs_fx, ctx->plan.cls_key, ctx->plan.cls_aux, ctx->plan.cls_idle, ctx->plan.cls_count,
 		ctx->plan.overflow, ctx->plan.list, ctx->plan.k2_rows, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
 		ctx->d_peaks, ctx->d_rep, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
-		ctx->d_exchange, ctx->d_comm_seq, ctx->d_comm_ticket };
+		ctx->d_exchange, ctx->d_comm_seq, ctx->d_comm_ticket, ctx->t.vs_look, ctx->t.vs_life, ctx->t.inst_threshold, ctx->d_stage, ctx->d_voices_stage,
+		ctx->d_mixed, ctx->d_status };
 	for (void *p : ptrs) {
 		if (p) {
 			cudaFree(p);
@@ -498,7 +518,7 @@ void gas_destroy(gas_ctx *ctx) {
 		cudaStreamSynchronize(ctx->s_voice);
 		cudaStreamDestroy(ctx->s_voice);
 	}
-	for (cudaEvent_t e : { ctx->ev_mix_done, ctx->ev_comm_done, ctx->ev_join2, ctx->ev_voice_fork, ctx->ev_voice_join }) {
+	for (cudaEvent_t e : { ctx->ev_mix_done, ctx->ev_comm_done, ctx->ev_join2, ctx->ev_voice_fork, ctx->ev_voice_join, ctx->ev_stream_started }) {
 		if (e) {
 			cudaEventDestroy(e);
 		}
@@ -879,6 +899,143 @@ int gas_mix_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voic
 	return mix_core(ctx, n_voices, d_voices, d_src, src_rows, src_row_stride, frames, d_bus_out, d_peaks);
 }
 
+// ---- stream form: voice lifecycle around the block path (gas_life.cu) ---------------------------------------------
+static int stream_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_frame *d_src, int src_rows, int src_stride, int frames,
+		const int32_t *d_mixed, gas_frame *d_bus, int32_t *d_status) {
+	// stage: lookahead splice / end fade into the staging rows + rewritten voice list; then the ordinary block path with
+	// peaks; then the deactivation pass
+	GAS_CUDA(ctx, launch_life_stage(ctx, n_voices, d_voices, d_mixed, d_src, src_rows, src_stride, frames, ctx->d_voices_stage, ctx->d_stage, frames,
+			ctx->s_mix));
+	int st = mix_core(ctx, n_voices, ctx->d_voices_stage, ctx->d_stage, n_voices, frames, frames, d_bus, ctx->d_peaks);
+	if (st) {
+		return st;
+	}
+	GAS_CUDA(ctx, launch_life_post(ctx, n_voices, ctx->d_voices_stage, ctx->d_peaks, d_status, ctx->s_mix));
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_mix_done, ctx->s_mix));
+	return GAS_OK;
+}
+
+int gas_mix_block_stream(gas_ctx *ctx, int32_t n_voices, const gas_voice *voices, const gas_frame *src, int32_t src_rows, int32_t frames,
+		const int32_t *mixed_frames, gas_frame *bus_out, int32_t *status_out) {
+	{
+		ENTER(ctx);
+		if (n_voices < 0 || n_voices > ctx->cfg.max_voices || (n_voices > 0 && (!voices || !mixed_frames))) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_stream: 0..max_voices voices, one frame count per voice");
+		}
+		if (frames < 2 || (frames & 1) || frames > ctx->cfg.max_frames) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_stream: frames must be even and in [2, max_frames]");
+		}
+		if (src_rows < 0 || src_rows > ctx->cfg.max_voices || (src_rows > 0 && !src)) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_stream: 0..max_voices source rows");
+		}
+		for (int i = 0; i < n_voices; i++) {
+			const gas_voice &v = voices[i];
+			if (v.voice < 0 || v.voice >= ctx->cfg.max_voices || v.instance < 0 || v.instance >= ctx->cfg.max_instances || v.src_row >= src_rows ||
+					mixed_frames[i] < 0 || mixed_frames[i] > frames) {
+				return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_stream: voice %d references a bad slot / row or has a frame count outside [0, frames]", i);
+			}
+		}
+		if (n_voices > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_voices, voices, n_voices * sizeof(gas_voice), cudaMemcpyHostToDevice, ctx->s_mix));
+			GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_mixed, mixed_frames, n_voices * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+		}
+		if (src_rows > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_src, src, (size_t)src_rows * frames * sizeof(gas_frame), cudaMemcpyHostToDevice, ctx->s_mix));
+		}
+		int st = stream_core(ctx, n_voices, ctx->d_voices, ctx->d_src, src_rows, frames, frames, ctx->d_mixed, ctx->d_bus, ctx->d_status);
+		if (st) {
+			return st;
+		}
+		if (bus_out) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(bus_out, ctx->d_bus, (size_t)ctx->cfg.num_buses * (ctx->cfg.speaker_mode + 1) * frames * sizeof(gas_frame),
+					cudaMemcpyDeviceToHost, ctx->s_mix));
+		}
+		if (status_out && n_voices > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(status_out, ctx->d_status, n_voices * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_mix));
+		}
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	return GAS_OK;
+}
+
+int gas_mix_block_stream_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices, const gas_frame *d_src, int32_t src_rows,
+		int32_t src_row_stride, int32_t frames, const int32_t *d_mixed_frames, gas_frame *d_bus_out, int32_t *d_status_out) {
+	ENTER(ctx);
+	if (n_voices < 0 || n_voices > ctx->cfg.max_voices || (n_voices > 0 && (!d_voices || !d_mixed_frames)) || !d_bus_out) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_stream_device: bad voice count or null pointer");
+	}
+	if (frames < 2 || (frames & 1) || frames > ctx->cfg.max_frames || src_row_stride < frames || (src_row_stride & 1)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_stream_device: frames/stride must be even, frames <= max_frames, stride >= frames");
+	}
+	if (((uintptr_t)d_src & 7u) || ((uintptr_t)d_bus_out & 15u)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_stream_device: source rows must be 8-byte, bus buffers 16-byte aligned");
+	}
+	return stream_core(ctx, n_voices, d_voices, d_src, src_rows, src_row_stride, frames, d_mixed_frames, d_bus_out, d_status_out);
+}
+
+int gas_set_playback_disable_threshold_db(gas_ctx *ctx, int32_t n, const int32_t *instances, const float *db) {
+	ENTER(ctx);
+	if (n < 0 || n > ctx->cfg.max_instances || (n > 0 && (!instances || !db)) || !ids_valid(instances, n, ctx->cfg.max_instances)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_set_playback_disable_threshold_db: bad instance slot");
+	}
+	std::vector<float> lin((size_t)(n > 0 ? n : 1));
+	for (int i = 0; i < n; i++) {
+		lin[(size_t)i] = expf(db[i] * (float)0.11512925464970228420089957273422); // upstream Math::db_to_linear(float), on the host like the reference
+	}
+	// the mix stream owns the lifecycle tables; its own staging buffers (d_mixed as ids, d_status as payload) keep the call
+	// off the gain stream's scratch
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_mixed, instances, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_status, lin.data(), n * sizeof(float), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, launch_threshold_set(ctx, n, ctx->d_mixed, (const float *)ctx->d_status, ctx->s_mix));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix)); // `lin` is pageable and about to go out of scope
+	return GAS_OK;
+}
+
+int gas_voice_life_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_voice_life *out) {
+	{
+		ENTER(ctx);
+		if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && (!voices || !out)) || !ids_valid(voices, n, ctx->cfg.max_voices)) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_life_export: bad voice slot");
+		}
+		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_mixed, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+		GAS_CUDA(ctx, launch_life_export(ctx, n, ctx->d_mixed, (gas_voice_life *)ctx->d_stage, ctx->s_mix));
+		if (n > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_stage, n * sizeof(gas_voice_life), cudaMemcpyDeviceToHost, ctx->s_mix));
+		}
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	return GAS_OK;
+}
+
+int gas_voice_life_import(gas_ctx *ctx, int32_t n, const int32_t *voices, const gas_voice_life *in) {
+	ENTER(ctx);
+	if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && (!voices || !in)) || !ids_valid(voices, n, ctx->cfg.max_voices)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_life_import: bad voice slot");
+	}
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_mixed, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, in, n * sizeof(gas_voice_life), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, launch_life_import(ctx, n, ctx->d_mixed, (const gas_voice_life *)ctx->d_stage, ctx->s_mix));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	return GAS_OK;
+}
+
+int gas_status_flags(gas_ctx *ctx, uint32_t *out_flags) {
+	{
+		ENTER(ctx);
+		if (!out_flags) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_status_flags: null output");
+		}
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	int32_t overflow = 0;
+	GAS_CUDA(ctx, cudaMemcpy(&overflow, ctx->plan.overflow, sizeof(overflow), cudaMemcpyDeviceToHost));
+	if (overflow) {
+		GAS_CUDA(ctx, cudaMemset(ctx->plan.overflow, 0, sizeof(overflow)));
+	}
+	*out_flags = overflow ? GAS_STATUS_CLASS_OVERFLOW : 0u;
+	return GAS_OK;
+}
+
 int gas_sync(gas_ctx *ctx) {
 	if (!ctx) {
 		return gas_fail(nullptr, GAS_ERR_INVALID, "gas_sync: null context");
@@ -944,6 +1101,7 @@ int gas_capture_begin(gas_ctx *ctx) {
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_comm));
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
 	ctx->gain_pending = ctx->prologue_pending = ctx->mix_pending = ctx->comm_pending = false;
+	ctx->stream_started_pending = false;
 	GAS_CUDA(ctx, cudaStreamBeginCapture(ctx->s_mix, cudaStreamCaptureModeThreadLocal));
 	// fork: the gain stream joins the capture
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->s_mix));
@@ -978,7 +1136,8 @@ int gas_capture_end(gas_ctx *ctx, int32_t *out_graph) {
 	cudaError_t e2 = cudaStreamEndCapture(ctx->s_mix, &graph);
 	const uint64_t kernels = ctx->launches - ctx->capture_launches0;
 	ctx->launches = ctx->capture_launches0; // nothing ran yet
-	ctx->gain_pending = ctx->prologue_pending = false;
+	ctx->gain_pending = ctx->prologue_pending = ctx->mix_pending = ctx->comm_pending = false; // events recorded while capturing are graph edges only
+	ctx->stream_started_pending = false;
 	if (e != cudaSuccess || e2 != cudaSuccess || !graph) {
 		return gas_fail(ctx, GAS_ERR_CUDA, "gas_capture_end: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
 	}
@@ -1129,15 +1288,20 @@ static int reduce_half(gas_ctx *ctx, gas_frame *d_bus, int32_t frames, bool begi
 	if (!ctx->d_exchange || !ctx->peer_exchange[ctx->comm_ranks - 1]) {
 		return gas_fail(ctx, GAS_ERR_STATE, "%s: gas_comm_open has not been called", who);
 	}
-	if (ctx->comm_pending && !ctx->capturing) {
+	if (ctx->comm_pending) {
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_comm_done, 0));
 		ctx->comm_pending = false;
 	}
+	if (begin && !end && ctx->reduce_open) {
+		return gas_fail(ctx, GAS_ERR_STATE, "%s: the previous block's gas_reduce_bus_end_device has not been called", who);
+	}
 	if (begin) {
 		GAS_CUDA(ctx, launch_comm_push(ctx, d_bus, frames, ctx->s_mix));
+		ctx->reduce_open = !end;
 	}
 	if (end) {
 		GAS_CUDA(ctx, launch_comm_finish(ctx, d_bus, frames, ctx->s_mix));
+		ctx->reduce_open = false;
 	}
 	return GAS_OK;
 }
@@ -1163,14 +1327,12 @@ int gas_reduce_bus_exchange_device(gas_ctx *ctx, const gas_frame *d_partial, gas
 	if (ctx->comm_ranks <= 1) {
 		return gas_fail(ctx, GAS_ERR_STATE, "gas_reduce_bus_exchange_device: needs an opened exchange of at least 2 ranks");
 	}
-	if (!ctx->capturing && ctx->mix_pending) { // the partial sums must be complete
+	if (ctx->mix_pending) { // the partial sums must be complete (also when they were mixed earlier in the same capture)
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comm, ctx->ev_mix_done, 0));
 	}
 	GAS_CUDA(ctx, launch_comm_exchange(ctx, d_partial, d_prev_sum, frames, ctx->s_comm));
-	if (!ctx->capturing) {
-		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done, ctx->s_comm));
-		ctx->comm_pending = true;
-	}
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done, ctx->s_comm));
+	ctx->comm_pending = true;
 	return GAS_OK;
 }
 

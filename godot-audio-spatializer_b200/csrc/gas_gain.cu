@@ -622,6 +622,10 @@ cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_list
 	switch (shape) {
 		case 1: GAS_K1_LAUNCH(8, 256, 4); break;
 		case 2: GAS_K1_LAUNCH(8, 64, 8); break;
+		case 3: GAS_K1_LAUNCH(1, 32, 16); break; // one lane per emitter: 8x fewer issue slots, the whole grid fits beside the streaming kernel
+		case 4: GAS_K1_LAUNCH(2, 32, 16); break;
+		case 5: GAS_K1_LAUNCH(2, 64, 8); break;
+		case 6: GAS_K1_LAUNCH(4, 32, 16); break;
 		default: GAS_K1_LAUNCH(4, 64, 8); break;
 	}
 #undef GAS_K1_LAUNCH

@@ -140,6 +140,12 @@ struct DevTables {
 	float *vs_prev;              // [max_voices][4][2]
 	gas_processor_state *vs_proc; // [max_voices][8]
 	float *vs_fx;                // [max_voices][GAS_MAX_EFFECTS][2][GAS_MAX_FILTER_STAGES][4]
+	// voice lifecycle (stream form of the mix)
+	gas_frame *vs_look;          // [max_voices][64] lookahead
+	uint32_t *vs_life;           // [max_voices] GAS_VOICE_ACTIVE | GAS_VOICE_HAS_FRAMES
+	float *inst_threshold;       // [max_instances] db_to_linear(playback_disable_threshold_db)
+	float threshold_default;     // db_to_linear(-80 dB), evaluated on the host like the reference does (audio_spatializer.cpp:465)
+	int32_t max_voices;
 };
 
 struct GlobalCfg {
@@ -168,9 +174,13 @@ struct gas_ctx {
 	cudaStream_t s_voice = nullptr; // the voice-parallel kernel of a block, beside its streaming kernel (par_voice)
 	cudaEvent_t ev_voice_fork = nullptr, ev_voice_join = nullptr;
 	bool par_voice = false;
+	bool gain_after_stream = true; // GAS_K1_GATE=0: gain-side work no longer waits for the streaming kernel's CTAs to be resident
+	cudaEvent_t ev_stream_started = nullptr; // programmatic event of the last streaming kernel launch
+	bool stream_started_pending = false;
 	bool scaled_classes = true; // GAS_K2_SCALED=0 turns the scaled-send classes off (experiments)
 	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_mix_done = nullptr, ev_comm_done = nullptr, ev_join2 = nullptr;
 	bool mix_pending = false, comm_pending = false;
+	bool reduce_open = false; // gas_reduce_bus_begin_device without its _end yet
 	bool gain_pending = false, prologue_pending = false;
 	DevTables t{};
 	BlockPlan plan{};
@@ -180,6 +190,9 @@ struct gas_ctx {
 	gas_frame *d_bus = nullptr;
 	gas_frame *d_peaks = nullptr;
 	gas_frame *d_rep = nullptr; // [replicas][num_buses][channels][frames]: K2 partial sums, combined by the K3 launch
+	gas_frame *d_stage = nullptr;    // [max_voices][max_frames]: post-lookahead blocks of the stream form
+	gas_voice *d_voices_stage = nullptr; // [max_voices] voice list rewritten by the lifecycle stage
+	int32_t *d_mixed = nullptr, *d_status = nullptr; // [max_voices] staging of the host-pointer stream form
 	int replicas = 8;           // GAS_K2_REPLICAS (1 = K2 adds straight into the bus buffers)
 	gas_emitter *d_emitters = nullptr;
 	gas_listener *d_listeners = nullptr;
@@ -244,20 +257,39 @@ int gas_fail(gas_ctx *ctx, int status, const char *fmt, ...);
 
 // Launch with (optionally) the programmatic-dependent-launch attribute: the kernel may become resident
 // while its stream predecessor drains; it must execute griddepcontrol.wait before touching global memory.
+// `started` (optional): a timing-disabled event that fires once every CTA of the grid has started (programmatic
+// event, triggered at block start): work on another stream that waits for it runs BESIDE this kernel instead of
+// racing it for the SMs at launch.
 template <typename... KArgs, typename... Args>
-static inline cudaError_t gas_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+static inline cudaError_t gas_launch_ev(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, cudaEvent_t started,
+		Args... args) {
 	cudaLaunchConfig_t lc{};
 	lc.gridDim = grid;
 	lc.blockDim = block;
 	lc.dynamicSmemBytes = smem;
 	lc.stream = st;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cudaLaunchAttribute attr[2];
+	int na = 0;
+	if (pdl) {
+		attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[na].val.programmaticStreamSerializationAllowed = 1;
+		na++;
+	}
+	if (started) {
+		attr[na].id = cudaLaunchAttributeProgrammaticEvent;
+		attr[na].val.programmaticEvent.event = started;
+		attr[na].val.programmaticEvent.flags = 0;
+		attr[na].val.programmaticEvent.triggerAtBlockStart = 1;
+		na++;
+	}
 	lc.attrs = attr;
-	lc.numAttrs = pdl ? 1 : 0;
+	lc.numAttrs = na;
 	cudaError_t e = cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);
 	return e != cudaSuccess ? e : cudaGetLastError();
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gas_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+	return gas_launch_ev(kernel, grid, block, smem, st, pdl, (cudaEvent_t) nullptr, args...);
 }
 #define GAS_GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define GAS_GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
@@ -275,12 +307,20 @@ cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voice
 static inline int gas_bus_f4(const gas_ctx *ctx, int frames) { return ctx->g.num_buses * ctx->g.channels * frames / 2; }
 // gas_mix_stream.cu (K2) / gas_mix_voice.cu (K3)
 cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, cudaStream_t st);
+// after_stream: launched right behind the streaming kernel on the same stream (its class-table look may then precede the dependency wait)
 cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus,
-		gas_frame *d_peaks, cudaStream_t st);
+		gas_frame *d_peaks, cudaStream_t st, bool after_stream);
 // gas_comm.cu
 cudaError_t launch_comm_push(gas_ctx *ctx, const gas_frame *d_bus, int frames, cudaStream_t st);
 cudaError_t launch_comm_finish(gas_ctx *ctx, gas_frame *d_bus, int frames, cudaStream_t st);
 cudaError_t launch_comm_exchange(gas_ctx *ctx, const gas_frame *d_partial, gas_frame *d_prev_sum, int frames, cudaStream_t st);
+// gas_life.cu
+cudaError_t launch_life_stage(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const int32_t *d_mixed, const gas_frame *d_src, int src_rows,
+		int src_stride, int frames, gas_voice *d_out_voices, gas_frame *d_stage, int stage_stride, cudaStream_t st);
+cudaError_t launch_life_post(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_frame *d_peaks, int32_t *d_status, cudaStream_t st);
+cudaError_t launch_threshold_set(gas_ctx *ctx, int n, const int32_t *d_ids, const float *d_lin, cudaStream_t st);
+cudaError_t launch_life_export(gas_ctx *ctx, int n, const int32_t *d_ids, gas_voice_life *d_out, cudaStream_t st);
+cudaError_t launch_life_import(gas_ctx *ctx, int n, const int32_t *d_ids, const gas_voice_life *d_in, cudaStream_t st);
 // gas_state.cu
 cudaError_t launch_instance_init(gas_ctx *ctx, int n, const int32_t *d_ids, const int32_t *d_spat, cudaStream_t st);
 cudaError_t launch_instance_stop(gas_ctx *ctx, int n, const int32_t *d_ids, cudaStream_t st);

@@ -805,8 +805,10 @@ cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stri
 		cudaMemsetAsync(ctx->d_timeline, 0, 256 * 16 * sizeof(unsigned long long), st);
 		cf.timeline = ctx->d_timeline;
 	}
-	cudaError_t e = gas_launch(k_mix_stream, dim3(ctx->num_sms), dim3(kThreads), smem, st, (ctx->pdl & 2) != 0, ctx->plan, ctx->g, cf, d_src, target,
-			rep_stride, ctx->replicas, (const int32_t *)ctx->t.blk);
+	cudaError_t e = gas_launch_ev(k_mix_stream, dim3(ctx->num_sms), dim3(kThreads), smem, st, (ctx->pdl & 2) != 0,
+			ctx->gain_after_stream ? ctx->ev_stream_started : (cudaEvent_t) nullptr, ctx->plan, ctx->g, cf, d_src, target, rep_stride, ctx->replicas,
+			(const int32_t *)ctx->t.blk);
+	ctx->stream_started_pending = ctx->gain_after_stream;
 	ctx->launches++;
 	return e;
 }

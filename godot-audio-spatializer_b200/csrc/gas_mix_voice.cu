@@ -459,7 +459,7 @@ __device__ __forceinline__ int units_of(const ClassInfo &ci) {
 template <int C>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t, GlobalCfg g, BlockPlan plan,
 		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks,
-		const float4 *__restrict__ rep, int bus_f4, int replicas, int tile_floats) {
+		const float4 *__restrict__ rep, int bus_f4, int replicas, int tile_floats, int early_look) {
 	extern __shared__ __align__(16) float s_tile[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ int s_ncls;
@@ -469,6 +469,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	// before the streaming kernel started, so it is read BEFORE the dependency wait: a block without voice-parallel work
 	// (nothing filtered, no peaks: the common case of the unfiltered mix) ends here, one thread staying behind to keep the
 	// stream order intact, and costs the step nothing but this look.
+	if (!early_look) {
+		GAS_GRID_DEP_WAIT(); // not behind the streaming kernel: the class table may not be final before the dependency is met
+	}
 	if (replicas <= 1) {
 		__shared__ int s_any;
 		if (threadIdx.x < 32) {
@@ -624,7 +627,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 } // namespace
 
 cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus,
-		gas_frame *d_peaks, cudaStream_t st) {
+		gas_frame *d_peaks, cudaStream_t st, bool after_stream) {
+	const bool pdl = after_stream && (ctx->pdl & 4) != 0;
+	const int early_look = after_stream ? 1 : 0;
 	const int bus_f4 = gas_bus_f4(ctx, frames);
 	const int threads = kWarpsPerCta * 32;
 	int grid = ctx->num_sms * 2; // two CTAs per SM (128 registers): many chunks per CTA make the shared-memory tile pay
@@ -647,16 +652,16 @@ cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_strid
 	cudaError_t e = cudaSuccess;
 	switch (ctx->g.channels) {
 		case 1:
-			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats);
+			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look);
 			break;
 		case 2:
-			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats);
+			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look);
 			break;
 		case 3:
-			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats);
+			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look);
 			break;
 		default:
-			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(threads), smem, st, (ctx->pdl & 4) != 0, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats);
+			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look);
 			break;
 	}
 	ctx->launches++;

@@ -18,6 +18,8 @@
 // Compiled with -fmad=false (coefficient preparation is double arithmetic narrowed to float).
 #include "gas_internal.h"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int kLanes = 8;          // lanes per voice
@@ -253,7 +255,10 @@ __device__ __forceinline__ int group_or(unsigned gm, int v) {
 	return v;
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 4) k_prologue(DevTables t, GlobalCfg g, BlockPlan plan, int inst_hwm, int n_voices,
+// MINB: CTAs per SM the register allocation is capped for.  4 (122 registers, no spills) makes the grid of a 16384-voice
+// block 1.7 waves; 7 (72 registers, a few hundred bytes of spills in the rare six-bus path) makes it one.
+template <int MINB>
+__global__ void __launch_bounds__(kCtaThreads, MINB) k_prologue(DevTables t, GlobalCfg g, BlockPlan plan, int inst_hwm, int n_voices,
 		const gas_voice *__restrict__ voices, int src_rows, float4 *__restrict__ bus, int bus_f4, float4 *__restrict__ rep, int rep_f4,
 		float2 *__restrict__ peaks, int g_scaled_classes) {
 	__shared__ unsigned long long s_key[kVoicesPerCta];  // classes met in this CTA
@@ -747,8 +752,22 @@ cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voice
 	int work = ctx->inst_hwm > n_voices ? ctx->inst_hwm : n_voices;
 	work = work > 1 ? work : 1;
 	const int blocks = (work + kVoicesPerCta - 1) / kVoicesPerCta;
-	cudaError_t e = gas_launch(k_prologue, dim3(blocks), dim3(kCtaThreads), 0, st, (ctx->pdl & 1) != 0, ctx->t, ctx->g, ctx->plan, ctx->inst_hwm, n_voices,
-			d_voices, src_rows, (float4 *)d_bus, bus_f4, (float4 *)ctx->d_rep, rep_f4, (float2 *)d_peaks, ctx->scaled_classes ? 1 : 0);
+	static int minb = -1;
+	if (minb < 0) {
+		const char *e = getenv("GAS_PROLOGUE_MINB");
+		minb = e ? atoi(e) : 4;
+	}
+	cudaError_t e;
+#define GAS_PRO_LAUNCH(M_)                                                                                                                       \
+	e = gas_launch(k_prologue<M_>, dim3(blocks), dim3(kCtaThreads), 0, st, (ctx->pdl & 1) != 0, ctx->t, ctx->g, ctx->plan, ctx->inst_hwm, n_voices, \
+			d_voices, src_rows, (float4 *)d_bus, bus_f4, (float4 *)ctx->d_rep, rep_f4, (float2 *)d_peaks, ctx->scaled_classes ? 1 : 0)
+	switch (minb) {
+		case 6: GAS_PRO_LAUNCH(6); break;
+		case 7: GAS_PRO_LAUNCH(7); break;
+		case 8: GAS_PRO_LAUNCH(8); break;
+		default: GAS_PRO_LAUNCH(4); break;
+	}
+#undef GAS_PRO_LAUNCH
 	ctx->launches++;
 	return e;
 }

@@ -44,6 +44,7 @@ __device__ void instance_reset(DevTables &t, int q, int spat) {
 		t.inst_mode[q] = mode | ((s.effect_gain_binding + 1) << 8);
 	}
 	t.inst_fx[q] = t.spat[spat].chain;
+	t.inst_threshold[q] = t.threshold_default; // playback_disable_threshold_db = -80 (reference audio_spatializer.h:87)
 }
 
 // AudioSpatializer3D defaults, audio_spatializer_3d.h:171-188
@@ -90,6 +91,7 @@ __global__ void k_defaults(DevTables t, GlobalCfg g) {
 		details_clear(t.inst_prev[t.max_instances + q]);
 		t.inst_mode[q] = MODE_A;
 		t.inst_fx[q].n_effects = 0;
+		t.inst_threshold[q] = t.threshold_default;
 	}
 }
 
@@ -125,6 +127,11 @@ __global__ void k_voice_init(DevTables t, int n, const int32_t *__restrict__ ids
 	for (int k = 0; k < kFxFloats; k++) {
 		t.vs_fx[(size_t)v * kFxFloats + k] = 0.f;
 	}
+	// start_playback_stream (reference audio_spatializer.cpp:57-72): lookahead zeroed, active and has_frames set
+	for (int k = 0; k < GAS_LOOKAHEAD_BUFFER_SIZE; k++) {
+		t.vs_look[(size_t)v * GAS_LOOKAHEAD_BUFFER_SIZE + k] = gas_frame{ 0.f, 0.f };
+	}
+	t.vs_life[v] = GAS_VOICE_ACTIVE | GAS_VOICE_HAS_FRAMES;
 }
 
 __global__ void k_state_export(DevTables t, int n, const int32_t *__restrict__ ids, gas_voice_state *__restrict__ out) {

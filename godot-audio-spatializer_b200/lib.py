@@ -46,6 +46,12 @@ PROTOTYPES = {
     "gas_effect_params_set": (C.c_int, [_vp, _i32, _vp, _vp]),
     "gas_mix_block": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "gas_mix_block_device": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "gas_mix_block_stream": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "gas_mix_block_stream_device": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "gas_set_playback_disable_threshold_db": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "gas_voice_life_export": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "gas_voice_life_import": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "gas_status_flags": (C.c_int, [_vp, C.POINTER(C.c_uint32)]),
     "gas_sync": (C.c_int, [_vp]),
     "gas_mix_stream": (_vp, [_vp]),
     "gas_gain_stream": (_vp, [_vp]),
@@ -84,8 +90,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.gas_abi_version() != 1:
-        raise ImportError(f"libgas_b200.so has ABI version {lib.gas_abi_version()}, this binding expects 1")
+    if lib.gas_abi_version() != 2:
+        raise ImportError(f"libgas_b200.so has ABI version {lib.gas_abi_version()}, this binding expects 2")
     abi.check_layout(lib.gas_abi_sizeof, "libgas_b200.so")
     _lib = lib
     return lib

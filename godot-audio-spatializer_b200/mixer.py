@@ -227,6 +227,54 @@ class Mixer:
         self._ck(self._lib.gas_mix_block_device(self._ctx, int(n_voices), C.c_void_p(d_voices), C.c_void_p(d_src), int(src_rows),
                                                 int(src_row_stride), int(frames), C.c_void_p(d_bus_out), C.c_void_p(d_peaks)))
 
+    def mix_block_stream(self, voices, src, mixed_frames, frames=None):
+        """gas_mix_block_stream: the voice lifecycle of _mix_from_playback_list on the device (audio_spatializer.cpp:353-408,
+        :464-469).  src row r = the mixed_frames[i] frames AudioStreamPlayback::mix returned for voice i this block.
+        Returns (bus, status) with status = VOICE_ACTIVE | VOICE_HAS_FRAMES per voice after the block."""
+        v = _arr(voices, abi.voice).reshape(-1)
+        s = np.asarray(src)
+        if s.dtype == abi.frame:
+            s = s.view(np.float32).reshape(s.shape + (2,))
+        s = np.ascontiguousarray(s, dtype=np.float32)
+        rows = 0 if s.size == 0 else s.shape[0]
+        if frames is None:
+            frames = s.shape[1]
+        mf = _arr(mixed_frames, np.int32)
+        if mf.size != v.size:
+            raise ValueError("one frame count per voice")
+        bus = np.empty((self.num_buses, self.channels, frames, 2), dtype=np.float32)
+        status = np.zeros(max(v.size, 1), dtype=np.int32)
+        self._ck(self._lib.gas_mix_block_stream(self._ctx, v.size, _ptr(v), _ptr(s), rows, int(frames), C.c_void_p(mf.ctypes.data), _ptr(bus),
+                                                C.c_void_p(status.ctypes.data)))
+        return bus, status[: v.size]
+
+    def mix_block_stream_device(self, n_voices, d_voices, d_src, src_rows, src_row_stride, frames, d_mixed_frames, d_bus_out, d_status=0):
+        self._ck(self._lib.gas_mix_block_stream_device(self._ctx, int(n_voices), C.c_void_p(d_voices), C.c_void_p(d_src), int(src_rows),
+                                                       int(src_row_stride), int(frames), C.c_void_p(d_mixed_frames), C.c_void_p(d_bus_out),
+                                                       C.c_void_p(d_status)))
+
+    def set_playback_disable_threshold_db(self, instances, db):
+        """AudioSpatializerInstance::set_playback_disable_threshold_db (audio_spatializer.cpp:576-582)."""
+        i = _arr(instances, np.int32)
+        d = np.broadcast_to(_arr(db, np.float32), i.shape).copy()
+        self._ck(self._lib.gas_set_playback_disable_threshold_db(self._ctx, i.size, _ptr(i), _ptr(d)))
+
+    def voice_life_export(self, voices):
+        v = _arr(voices, np.int32)
+        out = np.zeros(v.size, dtype=abi.voice_life)
+        self._ck(self._lib.gas_voice_life_export(self._ctx, v.size, _ptr(v), _ptr(out)))
+        return out
+
+    def voice_life_import(self, voices, life):
+        v = _arr(voices, np.int32)
+        s = _arr(life, abi.voice_life).reshape(-1)
+        self._ck(self._lib.gas_voice_life_import(self._ctx, v.size, _ptr(v), _ptr(s)))
+
+    def status_flags(self):
+        f = C.c_uint32(0)
+        self._ck(self._lib.gas_status_flags(self._ctx, C.byref(f)))
+        return int(f.value)
+
     def sync(self):
         self._ck(self._lib.gas_sync(self._ctx))
 

@@ -51,7 +51,7 @@ extern "C" {
 #define GAS_MAX_EFFECTS 4        /* AudioEffectFilter instances per AudioSpatializerEffect chain */
 #define GAS_MAX_FILTER_STAGES 4  /* AudioEffectFilter FILTER_6DB..FILTER_24DB */
 #define GAS_MAX_BUSES 16         /* bus indices a context can mix into */
-#define GAS_ABI_VERSION 1
+#define GAS_ABI_VERSION 2
 
 typedef enum gas_status {
 	GAS_OK = 0,
@@ -219,6 +219,15 @@ typedef struct gas_voice_state {
 	float effect_history[GAS_MAX_EFFECTS][2][GAS_MAX_FILTER_STAGES][4];  /* [effect][l/r][stage]{ha1,ha2,hb1,hb2} */
 } gas_voice_state;
 
+/* The rest of SpatialPlaybackListNode (audio_spatializer.h:55-66) kept per voice slot for the stream form of the mix:
+ * flags bit 0 = active, bit 1 = has_frames. */
+#define GAS_VOICE_ACTIVE 1u
+#define GAS_VOICE_HAS_FRAMES 2u
+typedef struct gas_voice_life {
+	gas_frame lookahead[GAS_LOOKAHEAD_BUFFER_SIZE];
+	uint32_t flags;
+} gas_voice_life;
+
 typedef struct gas_config {
 	int32_t device; /* CUDA ordinal */
 	int32_t max_instances;
@@ -249,7 +258,8 @@ typedef enum gas_struct_id {
 	GAS_STRUCT_VOICE = 8,
 	GAS_STRUCT_PROCESSOR_STATE = 9,
 	GAS_STRUCT_VOICE_STATE = 10,
-	GAS_STRUCT_CONFIG = 11
+	GAS_STRUCT_CONFIG = 11,
+	GAS_STRUCT_VOICE_LIFE = 12
 } gas_struct_id;
 GAS_API size_t gas_abi_sizeof(int32_t struct_id);
 GAS_API void gas_config_defaults(gas_config *cfg);
@@ -321,7 +331,8 @@ GAS_API int gas_effect_params_set(gas_ctx *ctx, int32_t n, const int32_t *instan
  *   voices   n_voices descriptors (host); a voice slot may appear at most once per block.
  *   src      src_rows x frames AudioFrames (host): the post-lookahead playback buffers
  *            (audio_spatializer.cpp:367-408), row r used by voices with src_row == r.
- *   frames   block size, even, <= max_frames.
+ *   frames   block size, even, <= max_frames (the reference accepts any count; frames travel as 16-byte pairs here, and
+ *            AudioServer's block is 512).
  *   bus_out  host, [num_buses][channel_count][frames] AudioFrames, fully overwritten.
  *   peaks    optional host, n_voices entries: per-voice block peak (max |sample| over pairs, l/r
  *            separately), valid for voices flagged GAS_VOICE_WANT_PEAK, else {0,0}.
@@ -334,6 +345,28 @@ GAS_API int gas_mix_block(gas_ctx *ctx, int32_t n_voices, const gas_voice *voice
 GAS_API int gas_mix_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices,
 		const gas_frame *d_src, int32_t src_rows, int32_t src_row_stride, int32_t frames,
 		gas_frame *d_bus_out, gas_frame *d_peaks);
+/* ---- stream form: the voice lifecycle of _mix_from_playback_list on the device (audio_spatializer.cpp:353-408, :464-492) ----
+ * Row r of `src` holds what AudioStreamPlayback::mix returned for the voice this block (audio_spatializer.cpp:378):
+ * mixed_frames[i] <= frames new frames, NOT yet spliced behind the lookahead.  Per voice slot the context keeps the node's
+ * 64-frame lookahead, `has_frames` and `active` (set / zeroed by gas_voice_init, like start_playback_stream :57-72) and does
+ * what the reference does around the per-voice call: inactive voices are skipped (:355); the lookahead goes in front of the
+ * new frames and the last 64 frames become the next lookahead (:369-373, :401-403); a short count ends the stream — the last
+ * 64 valid frames are faded with 0.96^k * (64 - k) / 64, the rest is zeroed, has_frames is cleared (:380-398); a voice without
+ * frames is mixed with silence (filter tails, :405-408) and deactivated once its block peak is at or below its instance's
+ * playback_disable_threshold_db (:464-469).  status_out[i] (optional): GAS_VOICE_ACTIVE | GAS_VOICE_HAS_FRAMES after the block;
+ * a voice that comes back without GAS_VOICE_ACTIVE should be dropped from the list (_manage_playback_state, :473-492), and an
+ * instance whose voices are all gone stopped with gas_instance_stop.
+ * Deliberate difference: in the block in which the LAST voice of a Mode-B instance is deactivated the reference delivers that
+ * block (at or below the threshold) only on the pair whose proxy AudioServer happens to mix first, because playback_active is
+ * cleared in the middle of the mix step (:484-491, :683-690); this library mixes it on every pair
+ * (tests/test_lifecycle.py::test_reference_drops_the_last_block_of_the_other_pairs). */
+GAS_API int gas_mix_block_stream(gas_ctx *ctx, int32_t n_voices, const gas_voice *voices, const gas_frame *src, int32_t src_rows,
+		int32_t frames, const int32_t *mixed_frames, gas_frame *bus_out, int32_t *status_out);
+GAS_API int gas_mix_block_stream_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices, const gas_frame *d_src, int32_t src_rows,
+		int32_t src_row_stride, int32_t frames, const int32_t *d_mixed_frames, gas_frame *d_bus_out, int32_t *d_status_out);
+/* AudioSpatializerInstance::set_playback_disable_threshold_db (audio_spatializer.cpp:576-582; default -80, reset by
+ * gas_instance_init). */
+GAS_API int gas_set_playback_disable_threshold_db(gas_ctx *ctx, int32_t n, const int32_t *instances, const float *db);
 GAS_API int gas_sync(gas_ctx *ctx);
 /* cudaStream_t of the mix / gain streams as void*, for callers that enqueue their own work
  * (collectives, copies) in order with the mixer. */
@@ -375,6 +408,12 @@ GAS_API int gas_profile_read(gas_ctx *ctx, double ms_out[GAS_KERNEL_KINDS], uint
 /* ---- persistent state (checkpoint / re-sharding; no reference analogue) ------------- */
 GAS_API int gas_voice_state_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_voice_state *out);
 GAS_API int gas_voice_state_import(gas_ctx *ctx, int32_t n, const int32_t *voices, const gas_voice_state *in);
+GAS_API int gas_voice_life_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_voice_life *out);
+GAS_API int gas_voice_life_import(gas_ctx *ctx, int32_t n, const int32_t *voices, const gas_voice_life *in);
+/* Sticky status bits since the last call (then cleared).  Bit 0: more distinct routing classes were in use than the plan has
+ * dynamic slots; the voices concerned were mixed through the generic class of the voice-parallel kernel (correct, slower). */
+#define GAS_STATUS_CLASS_OVERFLOW 1u
+GAS_API int gas_status_flags(gas_ctx *ctx, uint32_t *out_flags);
 
 /* ---- multi-GPU: voices sharded over ranks, partial bus buffers summed over peer memory ----------------
  * No reference analogue (one audio thread).  Every rank exports an IPC handle of its exchange allocation and
@@ -388,16 +427,19 @@ GAS_API int gas_comm_open(gas_ctx *ctx, int32_t rank, int32_t n_ranks, const voi
 GAS_API int gas_reduce_bus_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames);
 /* The two halves of gas_reduce_bus_device, for callers that overlap the other ranks' skew with their next block:
  * begin pushes this rank's partial sums of block n to every rank, end waits for every rank's push of the oldest
- * unfinished block and writes its complete sum to d_bus.  Per rank the order must be begin(n), ..., end(n) with
- * end(n) before begin(n + 2) at the latest (two exchange buffers). */
+ * unfinished block and writes its complete sum to d_bus.  Per rank the order must be begin(n), end(n), begin(n + 1), ...:
+ * begin(n + 1) zeroes the exchange buffer block n is still accumulating in, so it must follow end(n) (enforced:
+ * GAS_ERR_STATE otherwise).  What overlaps the other ranks' skew is the caller's work between begin(n) and end(n); the
+ * one-block-in-flight form is gas_reduce_bus_exchange_device. */
 GAS_API int gas_reduce_bus_begin_device(gas_ctx *ctx, const gas_frame *d_bus, int32_t frames);
 GAS_API int gas_reduce_bus_end_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames);
 /* One block in flight, off the critical path: on the context's exchange stream (beside whatever the mix stream
  * does next) write the complete sum of the previously pushed block to d_prev_sum (skipped when no block is
  * outstanding; may be NULL then) and push d_partial as the next block.  d_partial must stay untouched until the
- * call after next has been enqueued (the mix stream waits for the exchange before it reuses bus buffers; inside a
- * captured graph the exchange is a branch that joins at the end of the graph).  Drain with
- * gas_reduce_bus_end_device. */
+ * call after next has been enqueued (the mix stream waits for the exchange before it reuses bus buffers, and the exchange
+ * waits for the mix that produced d_partial — as stream events outside a capture, as graph edges inside one; an exchange
+ * captured without the mix of its block in the same graph relies on graph launches being ordered on the mix stream).
+ * Drain with gas_reduce_bus_end_device. */
 GAS_API int gas_reduce_bus_exchange_device(gas_ctx *ctx, const gas_frame *d_partial, gas_frame *d_prev_sum, int32_t frames);
 GAS_API int gas_comm_close(gas_ctx *ctx);
 

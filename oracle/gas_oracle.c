@@ -706,6 +706,10 @@ struct orc_world {
 	 * (audio_spatializer.cpp:74), so _mix_from_playback_list meets the most recently started voice first */
 	uint64_t *start_seq;
 	uint64_t next_seq;
+	/* SpatialPlaybackListNode lifecycle (audio_spatializer.h:55-66), used by orc_mix_block_stream only */
+	gas_frame (*lookahead)[GAS_LOOKAHEAD_BUFFER_SIZE];
+	unsigned char *v_active, *v_has_frames;
+	float *inst_threshold_db; /* playback_disable_threshold_db, audio_spatializer.h:87 */
 	double last_mix_s, last_gain_s;
 };
 
@@ -753,6 +757,13 @@ orc_world *orc_create(const gas_config *cfg) {
 	w->vs64 = (vstate64 *)calloc(cfg->max_voices, sizeof(vstate64));
 	w->start_seq = (uint64_t *)calloc(cfg->max_voices, sizeof(uint64_t));
 	w->next_seq = 1;
+	w->lookahead = calloc(cfg->max_voices, sizeof(*w->lookahead));
+	w->v_active = (unsigned char *)calloc(cfg->max_voices, 1);
+	w->v_has_frames = (unsigned char *)calloc(cfg->max_voices, 1);
+	w->inst_threshold_db = (float *)malloc(sizeof(float) * cfg->max_instances);
+	for (int i = 0; i < cfg->max_instances; i++) {
+		w->inst_threshold_db[i] = -80.0f;
+	}
 	for (int i = 0; i < cfg->max_spatializers; i++) {
 		spat_defaults(&w->spat[i]);
 	}
@@ -771,6 +782,10 @@ void orc_destroy(orc_world *w) {
 	free(w->vs);
 	free(w->vs64);
 	free(w->start_seq);
+	free(w->lookahead);
+	free(w->v_active);
+	free(w->v_has_frames);
+	free(w->inst_threshold_db);
 	free(w);
 }
 
@@ -877,6 +892,7 @@ int orc_instance_init(orc_world *w, int n, const int32_t *instances, const int32
 		q->effect_gain_binding = w->spat[q->spatializer].effect_gain_binding;
 		params_defaults(&q->params);
 		q->fx = w->spat[q->spatializer].chain;
+		w->inst_threshold_db[instances[i]] = -80.0f;
 	}
 	return GAS_OK;
 }
@@ -918,6 +934,10 @@ int orc_voice_init(orc_world *w, int n, const int32_t *voices) {
 		memset(&w->vs[voices[i]], 0, sizeof(gas_voice_state));
 		memset(&w->vs64[voices[i]], 0, sizeof(vstate64));
 		w->start_seq[voices[i]] = w->next_seq++;
+		/* start_playback_stream, audio_spatializer.cpp:57-72: lookahead zeroed, active and has_frames set */
+		memset(w->lookahead[voices[i]], 0, sizeof(w->lookahead[0]));
+		w->v_active[voices[i]] = 1;
+		w->v_has_frames[voices[i]] = 1;
 	}
 	return GAS_OK;
 }
@@ -1330,6 +1350,132 @@ int orc_mix_block(orc_world *w, int n_voices, const gas_voice *voices, const gas
 	return GAS_OK;
 }
 
+int orc_set_playback_disable_threshold_db(orc_world *w, int n, const int32_t *instances, const float *db) {
+	for (int i = 0; i < n; i++) {
+		if (instances[i] < 0 || instances[i] >= w->cfg.max_instances) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		w->inst_threshold_db[instances[i]] = db[i];
+	}
+	return GAS_OK;
+}
+
+/* AudioSpatializerInstance::_mix_from_playback_list around the per-voice call, audio_spatializer.cpp:353-408 and :464-469:
+ * row r of `src` holds the mixed_frames[i] frames AudioStreamPlayback::mix returned for voice i this block (:378).
+ *   :355      inactive voices are skipped
+ *   :369-373  the lookahead (last 64 frames of the previous mix) goes in front, the new frames behind it: the block that is
+ *             processed is buf[0..F), the new lookahead buf[F..F+64)
+ *   :380-398  a short mix ends the stream: over the last 64 valid frames  coef *= 0.96; buf[idx] *= coef * (64 - k) / 64,
+ *             zeros after them; has_frames is cleared
+ *   :405-408  without frames the voice is processed with a zero-filled buffer (filter tails)
+ *   :464-469  a voice without frames is deactivated once its block peak <= db_to_linear(playback_disable_threshold_db)
+ * status_out[i]: bit 0 = active after the block, bit 1 = has_frames after the block. */
+int orc_mix_block_stream(orc_world *w, int n_voices, const gas_voice *voices, const gas_frame *src, int src_rows, int frames,
+		const int32_t *mixed_frames, gas_frame *bus_out, gas_frame *peaks, int32_t *status_out, int threads) {
+	const int L = GAS_LOOKAHEAD_BUFFER_SIZE;
+	if (n_voices < 0 || frames <= 0 || (frames & 1) || frames > w->cfg.max_frames || !mixed_frames) {
+		return GAS_ERR_INVALID;
+	}
+	for (int i = 0; i < n_voices; i++) {
+		if (voices[i].voice < 0 || voices[i].voice >= w->cfg.max_voices || voices[i].instance < 0 || voices[i].instance >= w->cfg.max_instances ||
+				voices[i].src_row >= src_rows || mixed_frames[i] < 0 || mixed_frames[i] > frames) {
+			return GAS_ERR_INVALID;
+		}
+	}
+	gas_frame *stage = (gas_frame *)calloc((size_t)(n_voices > 0 ? n_voices : 1) * frames, sizeof(gas_frame));
+	gas_voice *vl = (gas_voice *)calloc(n_voices > 0 ? n_voices : 1, sizeof(gas_voice));
+	int *map = (int *)malloc(sizeof(int) * (n_voices > 0 ? n_voices : 1));
+	gas_frame *buf = (gas_frame *)malloc(sizeof(gas_frame) * (size_t)(frames + L));
+	int nl = 0;
+	for (int i = 0; i < n_voices; i++) {
+		const int v = voices[i].voice;
+		if (!w->v_active[v]) { /* :355 */
+			continue;
+		}
+		gas_voice o = voices[i];
+		o.flags |= GAS_VOICE_WANT_PEAK; /* :419: the reference always tracks the peak */
+		if (w->v_has_frames[v]) {
+			const int mixed = voices[i].src_row >= 0 ? mixed_frames[i] : 0;
+			const gas_frame *row = voices[i].src_row >= 0 ? src + (size_t)voices[i].src_row * frames : NULL;
+			for (int k = 0; k < L; k++) { /* :371-373 */
+				buf[k] = w->lookahead[v][k];
+			}
+			for (int k = 0; k < frames; k++) { /* :378 — frames the playback did not deliver keep whatever the buffer held */
+				if (k < mixed) {
+					buf[L + k] = row[k];
+				} else {
+					buf[L + k].l = buf[L + k].r = 0.0f;
+				}
+			}
+			if (mixed != frames) { /* :380-398 */
+				float fadeout_base = (float)0.96;
+				float fadeout_coefficient = 1;
+				float buffer_size_float = (float)L;
+				float buffer_linear_fade_idx = 0.0f;
+				int fade_limit = mixed + L;
+				for (int idx = mixed; idx < frames; idx++) {
+					if (idx < fade_limit) {
+						fadeout_coefficient *= fadeout_base;
+						float f = fadeout_coefficient * (buffer_size_float - buffer_linear_fade_idx) / buffer_size_float;
+						buf[idx].l *= f;
+						buf[idx].r *= f;
+						buffer_linear_fade_idx += 1.0f;
+					} else {
+						buf[idx].l *= 0.0f;
+						buf[idx].r *= 0.0f;
+					}
+				}
+				w->v_has_frames[v] = 0;
+			} else {
+				for (int k = 0; k < L; k++) { /* :401-403 */
+					w->lookahead[v][k] = buf[frames + k];
+				}
+			}
+			memcpy(stage + (size_t)nl * frames, buf, sizeof(gas_frame) * frames);
+			o.src_row = nl;
+		} else {
+			o.src_row = -1; /* :405-408 */
+		}
+		map[nl] = i;
+		vl[nl++] = o;
+	}
+	gas_frame *pk = (gas_frame *)calloc(nl > 0 ? nl : 1, sizeof(gas_frame));
+	int st = orc_mix_block(w, nl, vl, stage, nl, frames, bus_out, pk, NULL, threads);
+	if (status_out) {
+		for (int i = 0; i < n_voices; i++) {
+			status_out[i] = 0;
+		}
+	}
+	if (peaks) {
+		memset(peaks, 0, sizeof(gas_frame) * n_voices);
+	}
+	if (st == GAS_OK) {
+		for (int j = 0; j < nl; j++) {
+			const int v = vl[j].voice;
+			if (peaks) {
+				peaks[map[j]] = pk[j];
+			}
+			if (!w->v_has_frames[v]) { /* :464-469 */
+				float m = pk[j].r > pk[j].l ? pk[j].r : pk[j].l;
+				if (m <= orc_db_to_linear_f(w->inst_threshold_db[vl[j].instance])) {
+					w->v_active[v] = 0;
+				}
+			}
+			if (status_out) {
+				status_out[map[j]] = (w->v_active[v] ? 1 : 0) | (w->v_has_frames[v] ? 2 : 0);
+			}
+		}
+	}
+	free(pk);
+	free(stage);
+	free(vl);
+	free(map);
+	free(buf);
+	return st;
+}
+
 int orc_voice_state_export(orc_world *w, int n, const int32_t *voices, gas_voice_state *out) {
 	for (int i = 0; i < n; i++) {
 		if (voices[i] < 0 || voices[i] >= w->cfg.max_voices) {
@@ -1408,6 +1554,7 @@ size_t orc_sizeof(int32_t id) {
 		case GAS_STRUCT_PROCESSOR_STATE: return sizeof(gas_processor_state);
 		case GAS_STRUCT_VOICE_STATE: return sizeof(gas_voice_state);
 		case GAS_STRUCT_CONFIG: return sizeof(gas_config);
+		case GAS_STRUCT_VOICE_LIFE: return sizeof(gas_voice_life);
 		default: return 0;
 	}
 }

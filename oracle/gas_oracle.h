@@ -6,11 +6,11 @@
  *
  * PARITY PINNED BY REFERENCE CODE (module side) / RECALLED (upstream side):
  *  - every module-side line of the path is pinned bit for bit against the reference's own sources:
- *    oracle/_ref/libgas_ref.so is /root/reference/*.cpp, UNMODIFIED, compiled against the godot-lite stand-in
+ *    oracle/_ref/libgas_ref.so is the .cpp files of /root/reference, UNMODIFIED, compiled against the godot-lite stand-in
  *    headers (oracle/godot_lite/) by `make -C oracle ref` and driven by oracle/ref_harness.cpp;
  *    tests/test_oracle_vs_ref.py compares oracle == _ref on float32 bit patterns (gains, bus maps, bus buffers,
  *    persistent voice state, NaN cases included), tests/test_lifecycle.py does the same for the lookahead / end
- *    fade / deactivation path, and tests/golden/*.npz are outputs of _ref (tests/golden/make_golden.py);
+ *    fade / deactivation path, and the .npz files under tests/golden/ are outputs of _ref (tests/golden/make_golden.py);
  *  - the upstream-Godot pieces that are not under /root/reference (AudioFilterSW, AudioServer::_mix_step /
  *    _mix_step_for_channel, Math::*, Basis/Transform3D, AudioEffectFilter; godotengine/godot 4.x — the example
  *    project declares feature "4.6", no commit is pinned) are restated from Godot 4.x as recalled (SURVEY.md
@@ -89,6 +89,11 @@ int orc_effect_params_set(orc_world *w, int n, const int32_t *instances, const g
  * shadow state inside the world) for error budgeting. */
 int orc_mix_block(orc_world *w, int n_voices, const gas_voice *voices, const gas_frame *src, int src_rows,
 		int frames, gas_frame *bus_out, gas_frame *peaks, double *bus_out64, int threads);
+/* Stream form: the voice lifecycle of _mix_from_playback_list (lookahead splice, end-of-stream fade, zero-input tails,
+ * deactivation below the threshold), audio_spatializer.cpp:353-408, :464-469.  See gas_mix_block_stream in gas.h. */
+int orc_mix_block_stream(orc_world *w, int n_voices, const gas_voice *voices, const gas_frame *src, int src_rows, int frames,
+		const int32_t *mixed_frames, gas_frame *bus_out, gas_frame *peaks, int32_t *status_out, int threads);
+int orc_set_playback_disable_threshold_db(orc_world *w, int n, const int32_t *instances, const float *db);
 int orc_voice_state_export(orc_world *w, int n, const int32_t *voices, gas_voice_state *out);
 int orc_voice_state_import(orc_world *w, int n, const int32_t *voices, const gas_voice_state *in);
 /* seconds spent inside the last orc_mix_block / orc_gain_compute (steady_clock), for bench.py */

@@ -54,6 +54,8 @@ def load():
         "orc_params_get": (C.c_int, [_vp, C.c_int, _vp, _vp]),
         "orc_effect_params_set": (C.c_int, [_vp, C.c_int, _vp, _vp]),
         "orc_mix_block": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
+        "orc_mix_block_stream": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int]),
+        "orc_set_playback_disable_threshold_db": (C.c_int, [_vp, C.c_int, _vp, _vp]),
         "orc_voice_state_export": (C.c_int, [_vp, C.c_int, _vp, _vp]),
         "orc_voice_state_import": (C.c_int, [_vp, C.c_int, _vp, _vp]),
         "orc_last_mix_seconds": (C.c_double, [_vp]),
@@ -207,6 +209,31 @@ class OracleMixer:
         self._ck(self._lib.orc_mix_block(self._w, v.size, _ptr(v), _ptr(s), rows, int(frames), _ptr(bus), _ptr(peaks), _ptr(bus64), int(threads)))
         self.last_bus64 = bus64
         return bus, peaks
+
+    def mix_block_stream(self, voices, src, mixed_frames, frames=None, threads=1):
+        """Stream form (voice lifecycle inside): returns (bus, status) with status bit 0 = active, bit 1 = has_frames."""
+        v = _arr(voices, abi.voice).reshape(-1)
+        s = np.asarray(src)
+        if s.dtype == abi.frame:
+            s = s.view(np.float32).reshape(s.shape + (2,))
+        s = np.ascontiguousarray(s, dtype=np.float32)
+        rows = 0 if s.size == 0 else s.shape[0]
+        if frames is None:
+            frames = s.shape[1]
+        mf = _arr(mixed_frames, np.int32)
+        assert mf.size == v.size
+        bus = np.zeros((self.num_buses, self.channels, frames, 2), dtype=np.float32)
+        peaks = np.zeros((max(v.size, 1), 2), dtype=np.float32)
+        status = np.zeros(max(v.size, 1), dtype=np.int32)
+        self._ck(self._lib.orc_mix_block_stream(self._w, v.size, _ptr(v), _ptr(s), rows, int(frames), C.c_void_p(mf.ctypes.data), _ptr(bus),
+                                                _ptr(peaks), _ptr(status), int(threads)))
+        self.last_peaks = peaks[: v.size]
+        return bus, status[: v.size]
+
+    def set_playback_disable_threshold_db(self, instances, db):
+        i = _arr(instances, np.int32)
+        d = np.broadcast_to(_arr(db, np.float32), i.shape).copy()
+        self._ck(self._lib.orc_set_playback_disable_threshold_db(self._w, i.size, _ptr(i), _ptr(d)))
 
     def voice_state_export(self, voices):
         v = _arr(voices, np.int32)

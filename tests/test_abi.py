@@ -36,7 +36,7 @@ def test_record_layouts_match(gas, orc):
     gas.abi.check_layout(lib.gas_abi_sizeof, "libgas_b200.so")
     gas.abi.check_layout(orc.load().orc_sizeof, "libgas_oracle.so")
     assert lib.gas_abi_sizeof(999) == 0
-    assert lib.gas_abi_version() == 1
+    assert lib.gas_abi_version() == 2
 
 
 def test_defaults_match_reference_headers(gas):
@@ -77,3 +77,4 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp", ".cuh")) or f == "Makefile":
                 text = open(os.path.join(d, f), errors="ignore").read()
                 assert "gas_oracle" not in text and "orc_" not in text and "from oracle" not in text and "import oracle" not in text, os.path.join(d, f)
+                assert "libgas_ref" not in text and "godot_lite" not in text and "ref_harness" not in text, os.path.join(d, f)

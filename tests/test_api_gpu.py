@@ -229,26 +229,68 @@ def test_many_routing_classes_match_the_oracle(gas, orc):
         assert ok, f"{nbad} samples differ from the oracle, worst {worst:.3e}"
 
 
-def test_class_table_overflow_is_reported(gas):
-    """More distinct routing classes than the plan has slots (128): gas_mix_block says so instead of returning a
-    silently incomplete mix.  16 buses give 120 two-bus combinations + 16 single-bus ones."""
+def test_class_table_overflow_is_reported_and_mixed(gas, orc):
+    """More distinct routing classes than the plan has dynamic slots (122): the voices concerned go through the generic
+    class of the voice-parallel kernel — the mix stays complete (round 1 dropped them) — and gas_status_flags says so.
+    16 buses give 120 two-bus combinations + 16 single-bus ones."""
     B, F = 16, 64
     combos = [(a, b) for a in range(B) for b in range(a + 1, B)] + [(a, a) for a in range(B)]
     V = len(combos)
     ids = np.arange(V, dtype=np.int32)
+    p = np.zeros(V, dtype=abi.params)
+    p["mix_volumes"][:, 0, :] = 0.5
+    p["pitch_scale"], p["update_parameters"] = 1.0, 1
+    for k, (a, b) in enumerate(combos):
+        p["n_bus"][k] = 1 if a == b else 2
+        p["bus"][k, 0], p["bus"][k, 1] = a, b
+        p["bus_volumes"][k, 0, 0, :] = 0.5
+        p["bus_volumes"][k, 1, 0, :] = (0.25, 0.125)  # not a multiple of send 0: no scaled class
+    voices, src = synth.make_voices(V), synth.make_sources(V, F)
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, num_buses=B, speaker_mode=abi.SPEAKER_MODE_STEREO)
+    out = []
+    flags = 0
+    for mk in (lambda: gas.Mixer(**cfg), lambda: orc.OracleMixer(**cfg)):
+        with mk() as m:
+            m.spatializer_set(0, abi.spatializer_defaults(mix_channel_mode=1))
+            m.instance_init(ids, 0)
+            m.params_set(ids, p)
+            m.instance_start(ids)
+            m.voice_init(ids)
+            out.append([m.mix_block(voices, src, F, want_peaks=False)[0] for _ in range(3)])
+            if hasattr(m, "status_flags"):
+                flags = m.status_flags()
+    assert flags & abi.STATUS_CLASS_OVERFLOW, "the overflow was not reported"
+    for b, (bg, bw) in enumerate(zip(*out)):
+        assert np.array_equal(S.routing(bg), S.routing(bw)), f"block {b}: routing differs"
+        ok, worst, nbad = S.sample_close(bg, bw)
+        assert ok, f"block {b}: {nbad} samples out of tolerance, worst {worst:.3e}"
+
+
+def test_class_slots_are_recycled(gas):
+    """A class slot that stayed empty for GAS_CLS_IDLE_BLOCKS blocks is handed back: a long session that walks through more
+    routing classes than there are slots, a few at a time, never overflows."""
+    B, F, V = 16, 64, 8
+    ids = np.arange(V, dtype=np.int32)
+    voices, src = synth.make_voices(V), synth.make_sources(V, F)
     with gas.Mixer(max_instances=V, max_voices=V, max_frames=F, num_buses=B, speaker_mode=abi.SPEAKER_MODE_STEREO) as m:
         m.spatializer_set(0, abi.spatializer_defaults(mix_channel_mode=1))
         m.instance_init(ids, 0)
         p = np.zeros(V, dtype=abi.params)
         p["mix_volumes"][:, 0, :] = 0.5
-        p["pitch_scale"], p["update_parameters"] = 1.0, 1
-        for k, (a, b) in enumerate(combos):
-            p["n_bus"][k] = 1 if a == b else 2
-            p["bus"][k, 0], p["bus"][k, 1] = a, b
-            p["bus_volumes"][k, 0, 0, :] = 0.5
-            p["bus_volumes"][k, 1, 0, :] = 0.25
-        m.params_set(ids, p)
-        m.instance_start(ids)
-        m.voice_init(ids)
-        with pytest.raises(gas.GasError, match="routing classes"):
-            m.mix_block(synth.make_voices(V), synth.make_sources(V, F), F, want_peaks=False)
+        p["pitch_scale"], p["update_parameters"], p["n_bus"] = 1.0, 1, 2
+        p["bus_volumes"][:, 0, 0, :] = 0.5
+        p["bus_volumes"][:, 1, 0, :] = (0.25, 0.125)
+        started = False
+        for rnd in range(40):  # 40 rounds x 8 new bus pairs = 320 classes over the session (plus their fade-in / fade-out variants)
+            for k in range(V):
+                n = rnd * V + k
+                p["bus"][k, 0], p["bus"][k, 1] = n % 15, 15 - (n // 15) % 15 if (n % 15) != 15 - (n // 15) % 15 else (n + 1) % 15
+            m.params_set(ids, p)
+            if not started:
+                m.instance_start(ids)
+                m.voice_init(ids)
+                started = True
+            for _ in range(10):
+                bus, _ = m.mix_block(voices, src, F, want_peaks=False)
+                assert np.isfinite(bus).all()
+        assert not (m.status_flags() & abi.STATUS_CLASS_OVERFLOW), "slots were not recycled"
