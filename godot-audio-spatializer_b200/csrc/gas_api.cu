@@ -442,10 +442,21 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->d_params_out, I);
 	ALLOC(ctx->d_ids, nscratch_ids);
 	ALLOC(ctx->d_ids2, nscratch_ids);
+	ALLOC(ctx->d_ids_mix, nscratch_ids);
 	{
 		unsigned char *p = nullptr;
 		ok = ok && (dev_alloc(&p, ctx->scratch_bytes) == cudaSuccess);
 		ctx->d_scratch = p;
+		// Staging is per stream: the gain stream (instance_init/start/stop, params_set/get, effect_params_set) and the mix
+		// stream (voice_init, state / lifecycle export and import, thresholds) are not ordered against each other, so a
+		// shared buffer could be overwritten by one while a kernel of the other has not read it yet.
+		size_t mix_bytes = V * (sizeof(gas_voice_state) > sizeof(gas_voice_life) ? sizeof(gas_voice_state) : sizeof(gas_voice_life));
+		if (mix_bytes < I * sizeof(float)) {
+			mix_bytes = I * sizeof(float);
+		}
+		p = nullptr;
+		ok = ok && (dev_alloc(&p, mix_bytes) == cudaSuccess);
+		ctx->d_scratch_mix = p;
 	}
 #undef ALLOC
 	ok = ok && cudaStreamCreateWithFlags(&ctx->s_mix, cudaStreamNonBlocking) == cudaSuccess;
@@ -496,7 +507,7 @@ void gas_destroy(gas_ctx *ctx) {
 		ctx->plan.overflow, ctx->plan.list, ctx->plan.k2_rows, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
 		ctx->d_peaks, ctx->d_rep, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
 		ctx->d_exchange, ctx->d_comm_seq, ctx->d_comm_ticket, ctx->t.vs_look, ctx->t.vs_life, ctx->t.inst_threshold, ctx->d_stage, ctx->d_voices_stage,
-		ctx->d_mixed, ctx->d_status };
+		ctx->d_mixed, ctx->d_status, ctx->d_ids_mix, ctx->d_scratch_mix };
 	for (void *p : ptrs) {
 		if (p) {
 			cudaFree(p);
@@ -662,8 +673,8 @@ int gas_voice_init(gas_ctx *ctx, int32_t n, const int32_t *voices) {
 	if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && !voices) || !ids_valid(voices, n, ctx->cfg.max_voices)) {
 		return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_init: bad voice slot");
 	}
-	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
-	GAS_CUDA(ctx, launch_voice_init(ctx, n, ctx->d_ids, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids_mix, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, launch_voice_init(ctx, n, ctx->d_ids_mix, ctx->s_mix));
 	return GAS_OK;
 }
 
@@ -740,10 +751,11 @@ int gas_gain_compute(gas_ctx *ctx, int32_t n, const gas_emitter *emitters, int32
 		if (n < 0 || n > ctx->cfg.max_instances || (n > 0 && !emitters)) {
 			return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute: 0..max_instances emitters");
 		}
+		const int32_t area_limit = areas ? n_areas : ctx->n_areas_res; // without an areas argument the resident copy is used
 		for (int i = 0; i < n; i++) {
 			const gas_emitter &e = emitters[i];
 			if (e.instance < 0 || e.instance >= ctx->cfg.max_instances || e.spatializer < 0 || e.spatializer >= ctx->cfg.max_spatializers ||
-					e.area >= n_areas) {
+					e.area >= area_limit) {
 				return gas_fail(ctx, GAS_ERR_INVALID, "gas_gain_compute: emitter %d references a bad instance/spatializer/area", i);
 			}
 		}
@@ -982,11 +994,10 @@ int gas_set_playback_disable_threshold_db(gas_ctx *ctx, int32_t n, const int32_t
 	for (int i = 0; i < n; i++) {
 		lin[(size_t)i] = expf(db[i] * (float)0.11512925464970228420089957273422); // upstream Math::db_to_linear(float), on the host like the reference
 	}
-	// the mix stream owns the lifecycle tables; its own staging buffers (d_mixed as ids, d_status as payload) keep the call
-	// off the gain stream's scratch
-	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_mixed, instances, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
-	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_status, lin.data(), n * sizeof(float), cudaMemcpyHostToDevice, ctx->s_mix));
-	GAS_CUDA(ctx, launch_threshold_set(ctx, n, ctx->d_mixed, (const float *)ctx->d_status, ctx->s_mix));
+	// the mix stream owns the lifecycle tables and has staging buffers of its own
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids_mix, instances, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch_mix, lin.data(), n * sizeof(float), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, launch_threshold_set(ctx, n, ctx->d_ids_mix, (const float *)ctx->d_scratch_mix, ctx->s_mix));
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix)); // `lin` is pageable and about to go out of scope
 	return GAS_OK;
 }
@@ -997,10 +1008,10 @@ int gas_voice_life_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_vo
 		if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && (!voices || !out)) || !ids_valid(voices, n, ctx->cfg.max_voices)) {
 			return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_life_export: bad voice slot");
 		}
-		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_mixed, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
-		GAS_CUDA(ctx, launch_life_export(ctx, n, ctx->d_mixed, (gas_voice_life *)ctx->d_stage, ctx->s_mix));
+		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids_mix, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+		GAS_CUDA(ctx, launch_life_export(ctx, n, ctx->d_ids_mix, (gas_voice_life *)ctx->d_scratch_mix, ctx->s_mix));
 		if (n > 0) {
-			GAS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_stage, n * sizeof(gas_voice_life), cudaMemcpyDeviceToHost, ctx->s_mix));
+			GAS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scratch_mix, n * sizeof(gas_voice_life), cudaMemcpyDeviceToHost, ctx->s_mix));
 		}
 	}
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
@@ -1012,9 +1023,9 @@ int gas_voice_life_import(gas_ctx *ctx, int32_t n, const int32_t *voices, const 
 	if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && (!voices || !in)) || !ids_valid(voices, n, ctx->cfg.max_voices)) {
 		return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_life_import: bad voice slot");
 	}
-	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_mixed, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
-	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, in, n * sizeof(gas_voice_life), cudaMemcpyHostToDevice, ctx->s_mix));
-	GAS_CUDA(ctx, launch_life_import(ctx, n, ctx->d_mixed, (const gas_voice_life *)ctx->d_stage, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids_mix, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch_mix, in, n * sizeof(gas_voice_life), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, launch_life_import(ctx, n, ctx->d_ids_mix, (const gas_voice_life *)ctx->d_scratch_mix, ctx->s_mix));
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
 	return GAS_OK;
 }
@@ -1070,10 +1081,10 @@ int gas_voice_state_export(gas_ctx *ctx, int32_t n, const int32_t *voices, gas_v
 		if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && (!voices || !out)) || !ids_valid(voices, n, ctx->cfg.max_voices)) {
 			return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_state_export: bad voice slot");
 		}
-		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
-		GAS_CUDA(ctx, launch_state_export(ctx, n, ctx->d_ids, (gas_voice_state *)ctx->d_scratch, ctx->s_mix));
+		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids_mix, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+		GAS_CUDA(ctx, launch_state_export(ctx, n, ctx->d_ids_mix, (gas_voice_state *)ctx->d_scratch_mix, ctx->s_mix));
 		if (n > 0) {
-			GAS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scratch, n * sizeof(gas_voice_state), cudaMemcpyDeviceToHost, ctx->s_mix));
+			GAS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scratch_mix, n * sizeof(gas_voice_state), cudaMemcpyDeviceToHost, ctx->s_mix));
 		}
 	}
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
@@ -1085,9 +1096,9 @@ int gas_voice_state_import(gas_ctx *ctx, int32_t n, const int32_t *voices, const
 	if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && (!voices || !in)) || !ids_valid(voices, n, ctx->cfg.max_voices)) {
 		return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_state_import: bad voice slot");
 	}
-	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
-	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, in, n * sizeof(gas_voice_state), cudaMemcpyHostToDevice, ctx->s_mix));
-	GAS_CUDA(ctx, launch_state_import(ctx, n, ctx->d_ids, (const gas_voice_state *)ctx->d_scratch, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_ids_mix, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch_mix, in, n * sizeof(gas_voice_state), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, launch_state_import(ctx, n, ctx->d_ids_mix, (const gas_voice_state *)ctx->d_scratch_mix, ctx->s_mix));
 	return GAS_OK;
 }
 

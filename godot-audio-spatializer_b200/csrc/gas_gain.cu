@@ -333,7 +333,7 @@ __device__ __forceinline__ float pick(const float v[4][2], int c, int x) {
 // mix kernels, which is what a step pays for (see launch_gain for the measured shapes).
 template <int NL, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_gain(DevTables t, GlobalCfg g, int n, const gas_emitter *__restrict__ emitters,
-		int n_listeners, const gas_listener *__restrict__ listeners, const gas_area *__restrict__ areas, gas_params *__restrict__ out) {
+		int n_listeners, const gas_listener *__restrict__ listeners, const gas_area *__restrict__ areas, int n_areas, gas_params *__restrict__ out) {
 	constexpr int S = 8 / NL;
 	const int i = (blockIdx.x * blockDim.x + threadIdx.x) / NL;
 	const int l = threadIdx.x & (NL - 1);
@@ -342,7 +342,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gain(DevTables t, GlobalCfg g
 	if (i >= n) {
 		return;
 	}
-	const gas_emitter e = emitters[i];
+	gas_emitter e = emitters[i];
+	// Device-resident emitter records are not seen by the host: a record that points outside the tables is skipped (its
+	// instance keeps its parameters), an area index outside the resident areas counts as "no area" — like the prologue
+	// does with voice records.  Uniform over the emitter's lanes, so the shuffles below stay converged.
+	if (e.instance < 0 || e.instance >= g.max_instances || e.spatializer < 0 || e.spatializer >= g.max_spatializers) {
+		return;
+	}
+	if (e.area >= n_areas) {
+		e.area = -1;
+	}
 	// everything behind the emitter record is requested at once: the fields of its spatializer, its area and
 	// the state of its instance
 	const gas_spatializer *sp = &t.spat[e.spatializer];
@@ -618,7 +627,7 @@ cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_list
 		shape = e ? atoi(e) : 0;
 	}
 #define GAS_K1_LAUNCH(NL_, T_, M_)                                                                                          \
-	k_gain<NL_, T_, M_><<<(int)(((long long)n * NL_ + T_ - 1) / T_), T_, 0, st>>>(ctx->t, ctx->g, n, d_em, n_listeners, d_l, d_areas, d_out)
+	k_gain<NL_, T_, M_><<<(int)(((long long)n * NL_ + T_ - 1) / T_), T_, 0, st>>>(ctx->t, ctx->g, n, d_em, n_listeners, d_l, d_areas, ctx->n_areas_res, d_out)
 	switch (shape) {
 		case 1: GAS_K1_LAUNCH(8, 256, 4); break;
 		case 2: GAS_K1_LAUNCH(8, 64, 8); break;

@@ -201,7 +201,9 @@ struct gas_ctx {
 	gas_params *d_params_out = nullptr;
 	int32_t *d_ids = nullptr;  // scratch id list [max(max_voices,max_instances)]
 	int32_t *d_ids2 = nullptr;
-	void *d_scratch = nullptr; // generic scratch for set/get/import/export payloads
+	void *d_scratch = nullptr; // gain-stream scratch for set/get payloads
+	int32_t *d_ids_mix = nullptr; // mix-stream twins of d_ids / d_scratch (the two streams are not ordered against each other)
+	void *d_scratch_mix = nullptr;
 	size_t scratch_bytes = 0;
 	int32_t inst_hwm = 0; // instances [0, inst_hwm) have been initialised at least once
 	// multi-GPU exchange

@@ -755,7 +755,7 @@ cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voice
 	static int minb = -1;
 	if (minb < 0) {
 		const char *e = getenv("GAS_PROLOGUE_MINB");
-		minb = e ? atoi(e) : 4;
+		minb = e ? atoi(e) : 7; // one wave for a 16384-voice block: measured 0.7-2 us faster per step than the 122-register variant
 	}
 	cudaError_t e;
 #define GAS_PRO_LAUNCH(M_)                                                                                                                       \

@@ -72,7 +72,7 @@ def run_stream(mixer, sc, threshold_db=-80.0, keep_alive=False):
             started |= fresh
             alive |= fresh
         live = np.nonzero(alive)[0]
-        src = np.zeros((V + 1, F, 2), dtype=np.float32)
+        src = np.zeros((V + (1 if keep_alive else 0), F, 2), dtype=np.float32)
         mixed = np.zeros(V, dtype=np.int32)
         for v in live:
             n = int(min(F, max(0, sc["length"][v] - pos[v])))
