@@ -418,7 +418,7 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->t.inst_threshold, I);
 	ctx->t.max_voices = (int32_t)V;
 	ctx->t.threshold_default = expf(-80.0f * (float)0.11512925464970228420089957273422); // upstream Math::db_to_linear(float)
-	ALLOC(ctx->d_stage, V * F);
+	ALLOC(ctx->d_stage, V * F + 2 * F); // + in/out rows of the per-call entry points
 	ALLOC(ctx->d_voices_stage, V);
 	ALLOC(ctx->d_mixed, V);
 	ALLOC(ctx->d_status, V);
@@ -1044,6 +1044,54 @@ int gas_status_flags(gas_ctx *ctx, uint32_t *out_flags) {
 		GAS_CUDA(ctx, cudaMemset(ctx->plan.overflow, 0, sizeof(overflow)));
 	}
 	*out_flags = overflow ? GAS_STATUS_CLASS_OVERFLOW : 0u;
+	return GAS_OK;
+}
+
+// ---- the per-call virtuals on one voice (gas_single.cu) ---------------------------------------------------------------
+static int single_call(gas_ctx *ctx, int32_t instance, int32_t voice, int32_t channel, gas_frame *out, const gas_frame *src, int32_t frames, const char *who) {
+	if (instance < 0 || instance >= ctx->cfg.max_instances || voice < 0 || voice >= ctx->cfg.max_voices || !out || !src) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "%s: bad instance / voice slot or null buffer", who);
+	}
+	if (frames < 1 || frames > ctx->cfg.max_frames) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "%s: frames must be in [1, max_frames]", who);
+	}
+	// ordered after the gain side (the instance's parameters) and on the mix stream (the voice's playback data)
+	if (ctx->gain_pending) {
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
+	}
+	gas_frame *d_in = ctx->d_stage, *d_out = ctx->d_stage + ctx->cfg.max_frames;
+	GAS_CUDA(ctx, cudaMemcpyAsync(d_in, src, (size_t)frames * sizeof(gas_frame), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, launch_single_voice(ctx, instance, voice, channel, d_out, d_in, frames, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)frames * sizeof(gas_frame), cudaMemcpyDeviceToHost, ctx->s_mix));
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix)); // later gain-side work waits for this read of the parameters
+	ctx->prologue_pending = true;
+	return GAS_OK;
+}
+
+int gas_process_frames(gas_ctx *ctx, int32_t instance, int32_t voice, gas_frame *out, const gas_frame *src, int32_t frames) {
+	{
+		ENTER(ctx);
+		int st = single_call(ctx, instance, voice, -1, out, src, frames, "gas_process_frames");
+		if (st) {
+			return st;
+		}
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	return GAS_OK;
+}
+
+int gas_mix_channel(gas_ctx *ctx, int32_t instance, int32_t voice, int32_t channel, gas_frame *out, const gas_frame *src, int32_t frames) {
+	{
+		ENTER(ctx);
+		if (channel < 0 || channel >= GAS_MAX_CHANNELS_PER_BUS) { // ERR_FAIL_INDEX of get_filter_processor, audio_spatializer_3d.cpp:888
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_channel: channel must be in [0, %d)", GAS_MAX_CHANNELS_PER_BUS);
+		}
+		int st = single_call(ctx, instance, voice, channel, out, src, frames, "gas_mix_channel");
+		if (st) {
+			return st;
+		}
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
 	return GAS_OK;
 }
 

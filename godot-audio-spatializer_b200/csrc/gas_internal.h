@@ -323,6 +323,8 @@ cudaError_t launch_life_post(gas_ctx *ctx, int n_voices, const gas_voice *d_voic
 cudaError_t launch_threshold_set(gas_ctx *ctx, int n, const int32_t *d_ids, const float *d_lin, cudaStream_t st);
 cudaError_t launch_life_export(gas_ctx *ctx, int n, const int32_t *d_ids, gas_voice_life *d_out, cudaStream_t st);
 cudaError_t launch_life_import(gas_ctx *ctx, int n, const int32_t *d_ids, const gas_voice_life *d_in, cudaStream_t st);
+// gas_single.cu: channel < 0 = process_frames, else mix_channel of that pair
+cudaError_t launch_single_voice(gas_ctx *ctx, int instance, int voice, int channel, gas_frame *d_out, const gas_frame *d_src, int frames, cudaStream_t st);
 // gas_state.cu
 cudaError_t launch_instance_init(gas_ctx *ctx, int n, const int32_t *d_ids, const int32_t *d_spat, cudaStream_t st);
 cudaError_t launch_instance_stop(gas_ctx *ctx, int n, const int32_t *d_ids, cudaStream_t st);

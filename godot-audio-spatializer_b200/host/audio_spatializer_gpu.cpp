@@ -198,6 +198,49 @@ void AudioSpatializerInstance::stop_playback_stream(const Ref<SpatializerPlaybac
 		mixer->started[slot] = 0;
 	}
 }
+void AudioSpatializerInstance::set_playback_disable_threshold_db(float v) {
+	playback_disable_threshold_db = v;
+	if (mixer && slot >= 0) {
+		int32_t q = slot;
+		if (gas_set_playback_disable_threshold_db(mixer->context(), 1, &q, &v) != GAS_OK) {
+			set_last_error(gas_last_error(mixer->context()));
+		}
+	}
+}
+
+// reference ERR_FAIL_COND_MSG(!Object::cast_to<...>) at the top of the virtuals (audio_spatializer_3d.cpp:493-494, :556-557):
+// wrong or foreign playback data => the call is a no-op with an error
+static bool per_call_args_ok(const AudioSpatializerInstance *self, const Ref<SpatializerPlaybackData> &pd, const char *what) {
+	if (!self->mixer || self->slot < 0) {
+		set_last_error(std::string(what) + ": instance is not registered with a BatchMixer");
+		return false;
+	}
+	if (!pd || pd->mixer != self->mixer || pd->voice_slot < 0 ||
+			std::find(self->playbacks.begin(), self->playbacks.end(), pd) == self->playbacks.end()) {
+		set_last_error(std::string(what) + ": Unexpected SpatializerPlaybackData; expected one of this instance's playbacks");
+		return false;
+	}
+	return true;
+}
+void AudioSpatializerInstance::process_frames(const Ref<SpatializerParameters> &, const Ref<SpatializerPlaybackData> &p_playback_data,
+		AudioFrame *p_output_buf, const AudioFrame *p_source_buf, int p_frame_count) {
+	if (!per_call_args_ok(this, p_playback_data, "process_frames")) {
+		return;
+	}
+	if (gas_process_frames(mixer->context(), slot, p_playback_data->voice_slot, p_output_buf, p_source_buf, p_frame_count) != GAS_OK) {
+		set_last_error(gas_last_error(mixer->context()));
+	}
+}
+void AudioSpatializerInstance::mix_channel(const Ref<SpatializerParameters> &, const Ref<SpatializerPlaybackData> &p_playback_data, int p_channel,
+		AudioFrame *p_output_buf, const AudioFrame *p_source_buf, int p_frame_count) {
+	if (!per_call_args_ok(this, p_playback_data, "mix_channel")) {
+		return;
+	}
+	if (gas_mix_channel(mixer->context(), slot, p_playback_data->voice_slot, p_channel, p_output_buf, p_source_buf, p_frame_count) != GAS_OK) {
+		set_last_error(gas_last_error(mixer->context()));
+	}
+}
+
 Ref<SpatializerParameters> AudioSpatializerInstance::get_spatializer_parameters() const {
 	if (!mixer) {
 		return nullptr;
@@ -390,9 +433,88 @@ std::vector<Ref<SpatializerPlaybackData>> BatchMixer::playback_order() const {
 	return out;
 }
 
+bool BatchMixer::refuse_custom_dsp() const {
+	for (auto &ins : instances) {
+		if (ins && !ins->playbacks.empty() && !ins->uses_builtin_dsp()) {
+			set_last_error("instance " + std::to_string(ins->slot) + " overrides process_frames / mix_channel (uses_builtin_dsp() == false): the batched mix "
+					"cannot run a per-voice override; mix this instance's playbacks with your own loop (the base-class virtuals run the built-in "
+					"behaviour per call) and free it from the BatchMixer step");
+			return true;
+		}
+	}
+	return false;
+}
+
+bool BatchMixer::mix_streams(int frames, const std::vector<const AudioFrame *> &sources, const std::vector<int> &counts, AudioFrame *bus_out,
+		std::vector<Ref<SpatializerPlaybackData>> *finished) {
+	GAS_FAIL_COND_V(!ctx, "no device context", false);
+	std::vector<std::pair<Ref<AudioSpatializerInstance>, Ref<SpatializerPlaybackData>>> order;
+	std::vector<gas_voice> voices;
+	std::vector<int32_t> mixed;
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		if (refuse_custom_dsp()) {
+			return false;
+		}
+		size_t k = 0;
+		for (auto &ins : instances) {
+			if (!ins) {
+				continue;
+			}
+			for (auto &pb : ins->playbacks) {
+				gas_voice v;
+				v.voice = pb->voice_slot;
+				v.instance = ins->slot;
+				const bool has = k < sources.size() && sources[k] && k < counts.size() && counts[k] > 0;
+				v.src_row = has ? (int)k : -1;
+				v.flags = 0u;
+				voices.push_back(v);
+				mixed.push_back(has ? counts[k] : 0);
+				order.emplace_back(ins, pb);
+				k++;
+			}
+		}
+		GAS_FAIL_COND_V(sources.size() != voices.size() || counts.size() != voices.size(), "one source pointer and one frame count per live playback (see playback_order())", false);
+		GAS_FAIL_COND_V(frames <= 0 || frames > cfg.max_frames || (frames & 1), "Condition \"p_frame_count != mix_buffer[ch].size()\" is true.", false);
+		staging.resize(voices.size() * (size_t)frames);
+		for (size_t i = 0; i < voices.size(); i++) {
+			GAS_FAIL_COND_V(mixed[i] > frames, "a playback cannot return more frames than were asked for", false);
+			memset(&staging[i * frames], 0, (size_t)frames * sizeof(AudioFrame));
+			if (voices[i].src_row >= 0) {
+				memcpy(&staging[i * frames], sources[i], (size_t)mixed[i] * sizeof(AudioFrame));
+			}
+		}
+		std::vector<int32_t> status(voices.size() ? voices.size() : 1);
+		if (gas_mix_block_stream(ctx, (int)voices.size(), voices.data(), staging.data(), (int)voices.size(), frames, mixed.data(), bus_out,
+					status.data()) != GAS_OK) {
+			set_last_error(gas_last_error(ctx));
+			return false;
+		}
+		// _manage_playback_state (audio_spatializer.cpp:473-492): inactive playbacks leave the list
+		for (size_t i = 0; i < order.size(); i++) {
+			if (!(status[i] & GAS_VOICE_ACTIVE)) {
+				if (finished) {
+					finished->push_back(order[i].second);
+				}
+			} else {
+				order[i].second.reset();
+			}
+		}
+	}
+	for (auto &e : order) {
+		if (e.second) {
+			e.first->stop_playback_stream(e.second); // frees the slot; stops the instance's proxies when it was the last one
+		}
+	}
+	return true;
+}
+
 bool BatchMixer::mix(int frames, const std::vector<const AudioFrame *> &sources, AudioFrame *bus_out, AudioFrame *peaks) {
 	GAS_FAIL_COND_V(!ctx, "no device context", false);
 	std::lock_guard<std::mutex> lk(mu);
+	if (refuse_custom_dsp()) {
+		return false;
+	}
 	std::vector<gas_voice> voices;
 	size_t k = 0;
 	for (auto &ins : instances) {

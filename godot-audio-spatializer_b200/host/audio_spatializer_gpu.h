@@ -189,6 +189,19 @@ public:
 	virtual bool should_mix_channels() const { return false; }
 	virtual Ref<SpatializerPlaybackData> instantiate_playback_data() { return std::make_shared<SpatializerPlaybackData>(); }
 	virtual void initialize_audio_player() {}
+	// The per-call virtuals with the reference's signature (audio_spatializer.h:146,148; raw-pointer GDVIRTUAL mirror
+	// :103-112).  The base implementations ARE the built-in behaviour (AudioSpatializerInstance3D::process_frames /
+	// mix_channel, AudioSpatializerInstanceEffect::process_frames), run on the device for this one playback through
+	// gas_process_frames / gas_mix_channel: p_parameters must be the instance's current parameters (nullptr = current)
+	// and p_playback_data one of its playbacks.  The batched mix does the same work for all voices at once and does NOT
+	// call them, so a subclass that overrides one must say so with uses_builtin_dsp() = false; BatchMixer then refuses to
+	// batch that instance (mix() fails with a message naming it) and the caller mixes it with its own loop, where the
+	// override may still call the base implementation for the built-in part.
+	virtual void process_frames(const Ref<SpatializerParameters> &p_parameters, const Ref<SpatializerPlaybackData> &p_playback_data,
+			AudioFrame *p_output_buf, const AudioFrame *p_source_buf, int p_frame_count);
+	virtual void mix_channel(const Ref<SpatializerParameters> &p_parameters, const Ref<SpatializerPlaybackData> &p_playback_data, int p_channel,
+			AudioFrame *p_output_buf, const AudioFrame *p_source_buf, int p_frame_count);
+	virtual bool uses_builtin_dsp() const { return true; }
 
 	// --- what the reference reads from get_audio_player() / the scene (audio_stream_player_spatial.h:60,101-105) ---
 	void set_global_transform(const Transform3D &t) { transform = t; }
@@ -204,7 +217,7 @@ public:
 	void stop_playback_stream(const Ref<SpatializerPlaybackData> &p);
 	bool is_playback_active() const { return !playbacks.empty(); }
 	float get_playback_disable_threshold_db() const { return playback_disable_threshold_db; }
-	void set_playback_disable_threshold_db(float v) { playback_disable_threshold_db = v; }
+	void set_playback_disable_threshold_db(float v); // audio_spatializer.cpp:580-582; reaches the device's lifecycle table
 
 	Ref<SpatializerParameters> get_spatializer_parameters() const; // last parameters handed to the mixer
 
@@ -267,6 +280,14 @@ public:
 	// playback k in playback_order() (nullptr = silent tail).  bus_out: [num_buses][channels][frames].
 	// peaks (optional): one AudioFrame per playback in playback_order().
 	bool mix(int frames, const std::vector<const AudioFrame *> &sources, AudioFrame *bus_out, AudioFrame *peaks = nullptr);
+	// The same step with the voice lifecycle of _mix_from_playback_list on the device (audio_spatializer.cpp:353-408,
+	// :464-492): sources[k] points at the counts[k] <= frames frames AudioStreamPlayback::mix returned for playback k this
+	// block (not spliced behind the lookahead; nullptr / 0 once the stream has ended).  Lookahead, end-of-stream fade,
+	// silent tails and the deactivation below playback_disable_threshold_db happen in gas_mix_block_stream; playbacks that
+	// come back inactive are dropped (_manage_playback_state) and an instance whose last playback is gone is stopped.
+	// finished (optional) receives the playbacks dropped by this step.
+	bool mix_streams(int frames, const std::vector<const AudioFrame *> &sources, const std::vector<int> &counts, AudioFrame *bus_out,
+			std::vector<Ref<SpatializerPlaybackData>> *finished = nullptr);
 	// the playbacks a mix() call expects sources for, in order (instances by slot, playbacks by start order)
 	std::vector<Ref<SpatializerPlaybackData>> playback_order() const;
 
@@ -286,6 +307,7 @@ private:
 	std::vector<int> started; // instances whose first playback has been registered (gas_instance_start)
 	std::vector<gas_listener> listeners;
 	std::vector<gas_frame> staging;
+	bool refuse_custom_dsp() const; // sets last_error and returns true if an instance with uses_builtin_dsp() == false has playbacks
 	std::map<int, Ref<SpatializerParameters>> last_params;
 };
 

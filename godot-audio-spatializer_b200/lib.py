@@ -46,6 +46,8 @@ PROTOTYPES = {
     "gas_effect_params_set": (C.c_int, [_vp, _i32, _vp, _vp]),
     "gas_mix_block": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "gas_mix_block_device": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "gas_process_frames": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32]),
+    "gas_mix_channel": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32]),
     "gas_mix_block_stream": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "gas_mix_block_stream_device": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "gas_set_playback_disable_threshold_db": (C.c_int, [_vp, _i32, _vp, _vp]),

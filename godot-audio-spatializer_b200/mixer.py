@@ -227,6 +227,21 @@ class Mixer:
         self._ck(self._lib.gas_mix_block_device(self._ctx, int(n_voices), C.c_void_p(d_voices), C.c_void_p(d_src), int(src_rows),
                                                 int(src_row_stride), int(frames), C.c_void_p(d_bus_out), C.c_void_p(d_peaks)))
 
+    def process_frames(self, instance, voice, src):
+        """gas_process_frames: the reference's process_frames virtual on one voice (audio_spatializer_3d.cpp:491-552,
+        audio_spatializer_effect.cpp:33-77).  src float32 [frames, 2]; returns out [frames, 2]."""
+        s = np.ascontiguousarray(np.asarray(src, dtype=np.float32))
+        out = np.empty_like(s)
+        self._ck(self._lib.gas_process_frames(self._ctx, int(instance), int(voice), _ptr(out), _ptr(s), s.shape[0]))
+        return out
+
+    def mix_channel(self, instance, voice, channel, src):
+        """gas_mix_channel: the reference's mix_channel virtual on one voice and one channel pair (audio_spatializer_3d.cpp:554-609)."""
+        s = np.ascontiguousarray(np.asarray(src, dtype=np.float32))
+        out = np.empty_like(s)
+        self._ck(self._lib.gas_mix_channel(self._ctx, int(instance), int(voice), int(channel), _ptr(out), _ptr(s), s.shape[0]))
+        return out
+
     def mix_block_stream(self, voices, src, mixed_frames, frames=None):
         """gas_mix_block_stream: the voice lifecycle of _mix_from_playback_list on the device (audio_spatializer.cpp:353-408,
         :464-469).  src row r = the mixed_frames[i] frames AudioStreamPlayback::mix returned for voice i this block.

@@ -345,6 +345,19 @@ GAS_API int gas_mix_block(gas_ctx *ctx, int32_t n_voices, const gas_voice *voice
 GAS_API int gas_mix_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices,
 		const gas_frame *d_src, int32_t src_rows, int32_t src_row_stride, int32_t frames,
 		gas_frame *d_bus_out, gas_frame *d_peaks);
+/* ---- the per-call virtuals, one voice per call (reference audio_spatializer.h:146,148; GDVIRTUAL mirror :103-112) --------
+ * Same argument meaning as the reference: the instance's current SpatializerParameters and the voice's SpatializerPlaybackData
+ * are the two Ref arguments (addressed by slot), out/src are caller-owned host arrays of `frames` AudioFrames, out is fully
+ * overwritten (Q13), the playback data advance.
+ *   gas_process_frames  AudioSpatializerInstance3D::process_frames (audio_spatializer_3d.cpp:491-552) for a 3D instance,
+ *                       AudioSpatializerInstanceEffect::process_frames (audio_spatializer_effect.cpp:33-77) for an EFFECT one
+ *   gas_mix_channel     AudioSpatializerInstance3D::mix_channel (audio_spatializer_3d.cpp:554-609) for pair `channel` (0..3)
+ * The batched mix never calls these: they are what a subclass that overrides one of the two virtuals calls for the built-in
+ * behaviour, and how a single playback is processed outside a mix step.  Synchronous; any frame count in [1, max_frames]. */
+GAS_API int gas_process_frames(gas_ctx *ctx, int32_t instance, int32_t voice, gas_frame *out, const gas_frame *src, int32_t frames);
+GAS_API int gas_mix_channel(gas_ctx *ctx, int32_t instance, int32_t voice, int32_t channel, gas_frame *out, const gas_frame *src,
+		int32_t frames);
+
 /* ---- stream form: the voice lifecycle of _mix_from_playback_list on the device (audio_spatializer.cpp:353-408, :464-492) ----
  * Row r of `src` holds what AudioStreamPlayback::mix returned for the voice this block (audio_spatializer.cpp:378):
  * mixed_frames[i] <= frames new frames, NOT yet spliced behind the lookahead.  Per voice slot the context keeps the node's

@@ -530,6 +530,14 @@ public:
 		PlaybackNode *n = gl_find(p_playback);
 		return n ? n->paused : false;
 	}
+	int get_bus_index(const StringName &p_bus_name) const { /* upstream: -1 when there is no such bus */
+		for (size_t i = 0; i < gl_bus_names.size(); i++) {
+			if (gl_bus_names[i] == String(p_bus_name)) {
+				return (int)i;
+			}
+		}
+		return -1;
+	}
 	int gl_bus_index(const StringName &p_name) const { /* thread_find_bus_index: unknown => Master */
 		for (size_t i = 0; i < gl_bus_names.size(); i++) {
 			if (gl_bus_names[i] == String(p_name)) {

@@ -1,6 +1,9 @@
 // host_test — exercises the C++ host mirror (godot-audio-spatializer_b200/host) the way a Godot-side caller would.
 //   host_test validate                 : setter / parameter validation (reference ERR_FAIL_* behaviour); no GPU needed
 //   host_test scene <in.bin> <out.bin> : plays a scene read from in.bin through BatchMixer on cuda:0, writes the bus buffers
+//   host_test stream <in.bin> <out.bin>: the same through BatchMixer::mix_streams (voice lifecycle on the device): streams of
+//                                        given lengths, per block the bus buffers and the number of playbacks still alive
+//   host_test percall                  : the per-call virtuals (process_frames / mix_channel) and the refusal of overriders
 // in.bin : int32 {V, F, blocks, speaker_mode, num_buses, mix_channel_mode, custom_last, has_area}, gas_area,
 //          then per block: gas_emitter[V], float[V][F][2]
 // out.bin: per block float[num_buses][channels][F][2]
@@ -167,6 +170,184 @@ static int scene(const char *in_path, const char *out_path) {
 	return 0;
 }
 
+// in.bin : int32 {V, F, blocks, speaker_mode, num_buses, mix_channel_mode}, int32 length[V], then per block gas_emitter[V], float[V][F][2]
+// out.bin: per block float[num_buses][channels][F][2], int32 alive_after
+static int stream(const char *in_path, const char *out_path) {
+	FILE *fi = fopen(in_path, "rb");
+	CHECK(fi);
+	int32_t h[6];
+	CHECK(fread(h, sizeof(int32_t), 6, fi) == 6);
+	const int V = h[0], F = h[1], blocks = h[2], speaker_mode = h[3], num_buses = h[4], mode_b = h[5];
+	std::vector<int32_t> length(V);
+	CHECK(fread(length.data(), sizeof(int32_t), V, fi) == (size_t)V);
+	BatchMixerConfig cfg;
+	cfg.max_instances = V;
+	cfg.max_voices = V;
+	cfg.max_frames = F;
+	cfg.num_buses = num_buses;
+	cfg.speaker_mode = speaker_mode;
+	cfg.mix_rate = 48000.f;
+	BatchMixer mixer(cfg);
+	if (!mixer.ok()) {
+		fprintf(stderr, "no device: %s\n", last_error().c_str());
+		return 2;
+	}
+	auto spat = std::make_shared<AudioSpatializer3D>();
+	spat->set_mix_channel_mode(mode_b != 0);
+	std::vector<Ref<AudioSpatializerInstance>> inst(V);
+	std::vector<Ref<SpatializerPlaybackData>> pb(V);
+	std::vector<int64_t> pos(V, 0);
+	for (int i = 0; i < V; i++) {
+		inst[i] = mixer.instantiate(spat);
+		CHECK(inst[i]);
+	}
+	gas_listener l;
+	memset(&l, 0, sizeof(l));
+	l.basis[0] = l.basis[4] = l.basis[8] = 1.f;
+	mixer.set_listeners({ l });
+	const int C = speaker_mode + 1;
+	std::vector<gas_emitter> em(V);
+	std::vector<AudioFrame> src((size_t)V * F), bus((size_t)num_buses * C * F);
+	FILE *fo = fopen(out_path, "wb");
+	CHECK(fo);
+	for (int b = 0; b < blocks; b++) {
+		CHECK(fread(em.data(), sizeof(gas_emitter), V, fi) == (size_t)V);
+		CHECK(fread(src.data(), sizeof(AudioFrame), (size_t)V * F, fi) == (size_t)V * F);
+		for (int i = 0; i < V; i++) {
+			Transform3D t;
+			t.origin = Vector3{ em[i].origin[0], em[i].origin[1], em[i].origin[2] };
+			inst[i]->set_global_transform(t);
+			inst[i]->set_volume_db(em[i].volume_db);
+			inst[i]->set_max_db(em[i].max_db);
+			if (b == 0) {
+				pb[i] = inst[i]->start_playback_stream();
+				CHECK(pb[i]);
+			}
+		}
+		CHECK(mixer.update_spatializer_parameters());
+		// the live playbacks in the mixer's order, with what their streams still deliver
+		auto order = mixer.playback_order();
+		std::vector<const AudioFrame *> ptrs;
+		std::vector<int> counts;
+		for (auto &d : order) {
+			int i = 0;
+			while (i < V && pb[i] != d) {
+				i++;
+			}
+			CHECK(i < V);
+			const int64_t left = length[i] - pos[i];
+			const int n = (int)(left < 0 ? 0 : (left > F ? F : left));
+			ptrs.push_back(n > 0 ? &src[(size_t)i * F] : nullptr);
+			counts.push_back(n);
+			pos[i] += n;
+		}
+		std::vector<Ref<SpatializerPlaybackData>> finished;
+		CHECK(mixer.mix_streams(F, ptrs, counts, bus.data(), &finished));
+		for (auto &d : finished) { // a finished playback is no longer in any instance's list
+			for (int i = 0; i < V; i++) {
+				if (pb[i] == d) {
+					CHECK(!inst[i]->is_playback_active());
+				}
+			}
+		}
+		const int32_t alive = (int32_t)mixer.playback_order().size();
+		CHECK(fwrite(bus.data(), sizeof(AudioFrame), bus.size(), fo) == bus.size());
+		CHECK(fwrite(&alive, sizeof(alive), 1, fo) == 1);
+	}
+	fclose(fo);
+	fclose(fi);
+	printf("stream ok\n");
+	return 0;
+}
+
+// an instance whose subclass brings its own per-voice DSP: BatchMixer must refuse to batch it
+class CustomDspInstance : public FixedInstance {
+public:
+	bool uses_builtin_dsp() const override { return false; }
+	void process_frames(const Ref<SpatializerParameters> &p, const Ref<SpatializerPlaybackData> &d, AudioFrame *out, const AudioFrame *src, int n) override {
+		AudioSpatializerInstance::process_frames(p, d, out, src, n); // built-in part first
+		for (int i = 0; i < n; i++) {
+			out[i].l *= 0.5f;
+		}
+	}
+};
+class CustomDspSpatializer : public AudioSpatializer3D {
+public:
+	Ref<AudioSpatializerInstance> instantiate() override {
+		auto i = std::make_shared<CustomDspInstance>();
+		i->base = shared_from_this();
+		i->mix_channel_mode = get_mix_channel_mode();
+		return i;
+	}
+};
+
+static int percall() {
+	BatchMixerConfig cfg;
+	cfg.max_instances = 4;
+	cfg.max_voices = 4;
+	cfg.max_frames = 64;
+	cfg.speaker_mode = GAS_SPEAKER_SURROUND_71;
+	BatchMixer mixer(cfg);
+	if (!mixer.ok()) {
+		fprintf(stderr, "no device: %s\n", last_error().c_str());
+		return 2;
+	}
+	const int F = 50; // any frame count, like the reference's virtuals
+	std::vector<AudioFrame> src(F), out(F);
+	for (int i = 0; i < F; i++) {
+		src[i] = AudioFrame{ 0.01f * (i + 1), -0.02f * (i + 1) };
+	}
+	// Mode A, filter gain 0 (< 0.001): process_frames is a copy (audio_spatializer_3d.cpp:531-534) and stores the prev volume (:537-551)
+	auto fa = std::make_shared<FixedSpatializer>();
+	auto ia = mixer.instantiate(fa);
+	auto pa = ia->start_playback_stream();
+	CHECK(ia && pa && mixer.update_spatializer_parameters());
+	ia->process_frames(nullptr, pa, out.data(), src.data(), F);
+	for (int i = 0; i < F; i++) {
+		CHECK(out[i].l == src[i].l && out[i].r == src[i].r);
+	}
+	auto pda = std::dynamic_pointer_cast<SpatializerPlaybackData3D>(pa);
+	CHECK(pda && pda->get_prev_mix_volume(0).x == 0.25f && pda->get_prev_mix_volume(0).y == 0.5f);
+	// Mode B: mix_channel ramps from the previous volume (0 on the first call) to volumes[channel] with t = i / F (:589-604)
+	auto fb = std::make_shared<FixedSpatializer>();
+	fb->set_mix_channel_mode(true);
+	auto ib = mixer.instantiate(fb);
+	auto pbk = ib->start_playback_stream();
+	CHECK(ib && pbk && mixer.update_spatializer_parameters());
+	ib->mix_channel(nullptr, pbk, 2, out.data(), src.data(), F);
+	for (int i = 0; i < F; i++) {
+		const float t = (float)i / F;
+		const float vl = 0.25f * t + (1 - t) * 0.0f, vr = 0.5f * t + (1 - t) * 0.0f;
+		CHECK(out[i].l == vl * src[i].l && out[i].r == vr * src[i].r);
+	}
+	ib->mix_channel(nullptr, pbk, 2, out.data(), src.data(), F); // second call: prev == new, the ramp is flat
+	CHECK(fabsf(out[7].l - 0.25f * src[7].l) < 1e-7f && fabsf(out[7].r - 0.5f * src[7].r) < 1e-7f);
+	// wrong playback data => no-op with an error (ERR_FAIL_COND_MSG, :493-494)
+	out[0].l = 123.f;
+	ib->mix_channel(nullptr, pa, 0, out.data(), src.data(), F);
+	CHECK(out[0].l == 123.f && last_error().find("Unexpected SpatializerPlaybackData") != std::string::npos);
+	ib->mix_channel(nullptr, pbk, 4, out.data(), src.data(), F); // ERR_FAIL_INDEX of get_filter_processor (:888)
+	CHECK(out[0].l == 123.f);
+	// the batched step still runs with built-in instances only ...
+	std::vector<AudioFrame> bus((size_t)cfg.num_buses * 4 * 64), blk(64);
+	std::vector<const AudioFrame *> ptrs(2, blk.data());
+	CHECK(mixer.mix(64, ptrs, bus.data()));
+	// ... and refuses an instance that brings its own per-voice DSP
+	auto fc = std::make_shared<CustomDspSpatializer>();
+	auto ic = mixer.instantiate(fc);
+	auto pc = ic->start_playback_stream();
+	CHECK(ic && pc && mixer.update_spatializer_parameters());
+	ptrs.push_back(blk.data());
+	CHECK(!mixer.mix(64, ptrs, bus.data()) && last_error().find("uses_builtin_dsp") != std::string::npos);
+	ic->process_frames(nullptr, pc, out.data(), src.data(), F); // its override still reaches the built-in part per call
+	CHECK(out[3].l == 0.5f * src[3].l && out[3].r == src[3].r);
+	ic->stop_playback_stream(pc);
+	ptrs.pop_back();
+	CHECK(mixer.mix(64, ptrs, bus.data()));
+	printf("percall ok\n");
+	return 0;
+}
+
 int main(int argc, char **argv) {
 	if (argc >= 2 && !strcmp(argv[1], "validate")) {
 		return validate();
@@ -174,6 +355,12 @@ int main(int argc, char **argv) {
 	if (argc >= 4 && !strcmp(argv[1], "scene")) {
 		return scene(argv[2], argv[3]);
 	}
-	fprintf(stderr, "usage: host_test validate | scene in.bin out.bin\n");
+	if (argc >= 4 && !strcmp(argv[1], "stream")) {
+		return stream(argv[2], argv[3]);
+	}
+	if (argc >= 2 && !strcmp(argv[1], "percall")) {
+		return percall();
+	}
+	fprintf(stderr, "usage: host_test validate | scene in.bin out.bin | stream in.bin out.bin | percall\n");
 	return 64;
 }

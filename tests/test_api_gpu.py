@@ -294,3 +294,72 @@ def test_class_slots_are_recycled(gas):
                 bus, _ = m.mix_block(voices, src, F, want_peaks=False)
                 assert np.isfinite(bus).all()
         assert not (m.status_flags() & abi.STATUS_CLASS_OVERFLOW), "slots were not recycled"
+
+
+@pytest.mark.parametrize("gain", [0.0, 0.0009, 0.25, 1.0])
+def test_per_call_process_frames_and_mix_channel(gas, orc, gain):
+    """gas_process_frames / gas_mix_channel: the reference's per-call virtuals (audio_spatializer.h:146,148) on one voice,
+    against the oracle's twins (which tests/test_oracle_vs_ref.py pins bit for bit to the reference's own functions):
+    odd frame counts, three state-carrying blocks, filter threshold and first-block coefficient fade-in."""
+    import ctypes as C
+    lo = orc.load()
+    rng = np.random.default_rng(31)
+    F = 255  # the per-call entry points take any frame count, like the reference
+    p = np.zeros(1, dtype=abi.params)
+    p["pitch_scale"], p["update_parameters"], p["n_bus"] = 1.0, 1, 1
+    p["attenuation_filter_cutoff_hz"] = 4000.0
+    for mode_b in (0, 1):
+        with gas.Mixer(max_instances=2, max_voices=2, max_frames=256, num_buses=2, speaker_mode=abi.SPEAKER_SURROUND_71, mix_rate=48000.0) as m:
+            m.spatializer_set(0, abi.spatializer_defaults(mix_channel_mode=mode_b))
+            m.instance_init([0], 0)
+            m.voice_init([1])
+            st = np.zeros(1, dtype=abi.voice_state)
+            for blk in range(3):
+                p["mix_volumes"] = rng.uniform(0, 1, (1, 4, 2)).astype(np.float32)
+                p["bus_volumes"][0, 0] = p["mix_volumes"][0]
+                p["linear_attenuation"] = gain
+                m.params_set([0], p)
+                src = rng.uniform(-0.5, 0.5, (F, 2)).astype(np.float32)
+                if mode_b:
+                    for ch in range(4):
+                        want = np.zeros((F, 2), np.float32)
+                        lo.orc_mix_channel_3d(C.c_void_p(p.ctypes.data), C.c_void_p(st.ctypes.data), 48000.0, ch, C.c_void_p(want.ctypes.data),
+                                              C.c_void_p(src.ctypes.data), F)
+                        got = m.mix_channel(0, 1, ch, src)
+                        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7, err_msg=f"mix_channel block {blk} pair {ch}")
+                else:
+                    want = np.zeros((F, 2), np.float32)
+                    lo.orc_process_frames_3d(C.c_void_p(p.ctypes.data), C.c_void_p(st.ctypes.data), 48000.0, C.c_void_p(want.ctypes.data),
+                                             C.c_void_p(src.ctypes.data), F)
+                    got = m.process_frames(0, 1, src)
+                    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7, err_msg=f"process_frames block {blk}")
+                dev = m.voice_state_export([1])
+                np.testing.assert_allclose(dev["prev_mix_volumes"], st["prev_mix_volumes"], rtol=0, atol=0)
+            with pytest.raises(gas.GasError):
+                m.mix_channel(0, 1, 4, src)  # ERR_FAIL_INDEX of get_filter_processor (audio_spatializer_3d.cpp:888)
+
+
+def test_per_call_process_frames_effect_chain(gas, orc):
+    import ctypes as C
+    lo = orc.load()
+    rng = np.random.default_rng(37)
+    F = 200
+    chain = np.zeros(1, dtype=abi.effect_chain)
+    chain["n_effects"] = 2
+    chain["effects"][0, 0] = (abi.FILTER_HIGHSHELF, 4000.0, 1.0, 0.3, 2)
+    chain["effects"][0, 1] = (abi.FILTER_LOWPASS, 9000.0, 0.7, 1.0, 1)
+    spat = abi.spatializer_defaults()
+    spat["kind"] = abi.SPATIALIZER_EFFECT
+    spat["chain"] = chain[0]
+    with gas.Mixer(max_instances=1, max_voices=1, max_frames=256, num_buses=2, mix_rate=44100.0) as m:
+        m.spatializer_set(0, spat)
+        m.instance_init([0], 0)
+        m.voice_init([0])
+        st = np.zeros(1, dtype=abi.voice_state)
+        for blk in range(3):
+            src = rng.uniform(-0.5, 0.5, (F, 2)).astype(np.float32)
+            want = np.zeros((F, 2), np.float32)
+            lo.orc_process_frames_effect(C.c_void_p(chain.ctypes.data), C.c_void_p(st.ctypes.data), 44100.0, C.c_void_p(want.ctypes.data),
+                                         C.c_void_p(src.ctypes.data), F)
+            got = m.process_frames(0, 0, src)
+            np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7, err_msg=f"effect chain block {blk}")
