@@ -21,8 +21,10 @@ abi = gaspkg.load().abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libgas_ref.so")
+LIB_PATH_GPU = os.path.join(_HERE, "_ref", "libgas_ref_gpu.so")  # + integration/godot_module (the GPU-backed spatializer classes)
 REFERENCE_DIR = os.environ.get("GAS_REFERENCE_DIR", "/root/reference")
 _lib = None
+_lib_gpu = None
 _vp, _i32, _f32 = C.c_void_p, C.c_int32, C.c_float
 
 
@@ -50,12 +52,21 @@ def build(force=False):
     return LIB_PATH
 
 
-def load():
-    global _lib
-    if _lib is not None:
-        return _lib
-    build()
-    lib = C.CDLL(LIB_PATH)
+def build_gpu():
+    """The same harness with the Godot-module shim linked in (needs the product library to link against)."""
+    if not sources_present():
+        if os.path.exists(LIB_PATH_GPU):
+            return LIB_PATH_GPU
+        raise FileNotFoundError("oracle/_ref/libgas_ref_gpu.so is not built and the reference tree is not present")
+    subprocess.check_call(["make", "-C", _HERE, "-s", "refgpu", f"REF={REFERENCE_DIR}"])
+    return LIB_PATH_GPU
+
+
+def gpu_available():
+    return os.path.exists(LIB_PATH_GPU) or sources_present()
+
+
+def _bind(lib):
     sig = {
         "ref_create": (_vp, [_vp]),
         "ref_destroy": (None, [_vp]),
@@ -66,6 +77,8 @@ def load():
         "ref_set_mix_rate": (C.c_int, [_vp, _f32]),
         "ref_set_global_panning_strength": (C.c_int, [_vp, _f32]),
         "ref_set_server_lookahead": (C.c_int, [_vp, C.c_int]),
+        "ref_use_gpu_shim": (C.c_int, [_vp, C.c_int]),
+        "ref_has_gpu_shim": (C.c_int, []),
         "ref_spatializer_set": (C.c_int, [_vp, C.c_int, _vp]),
         "ref_instance_init": (C.c_int, [_vp, C.c_int, _vp, _vp]),
         "ref_instance_start": (C.c_int, [_vp, C.c_int, _vp]),
@@ -90,8 +103,23 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
     return lib
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = _bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def load_gpu():
+    global _lib_gpu
+    if _lib_gpu is None:
+        build_gpu()
+        _lib_gpu = _bind(C.CDLL(LIB_PATH_GPU))
+    return _lib_gpu
 
 
 def _arr(x, dtype):
@@ -109,12 +137,16 @@ class RefError(RuntimeError):
 class RefMixer:
     """Same methods as OracleMixer, computed by the reference module's own code."""
 
-    def __init__(self, **config):
-        self._lib = load()
+    def __init__(self, gpu_shim=False, **config):
+        """gpu_shim: AudioSpatializer3D resources become AudioSpatializer3DGPU (integration/godot_module): the reference's
+        plumbing around the GPU-backed classes.  One such world at a time; needs a B200."""
+        self._lib = load_gpu() if gpu_shim else load()
         self.config = abi.config_defaults(**config)
         self._w = self._lib.ref_create(_ptr(self.config.reshape(1)))
         if not self._w:
             raise RefError("ref_create: invalid configuration")
+        if gpu_shim:
+            self._ck(self._lib.ref_use_gpu_shim(self._w, 1))
 
     def close(self):
         if getattr(self, "_w", None):

@@ -33,6 +33,10 @@
 #include "scene/3d/velocity_tracker_3d.h"
 #include "scene/main/viewport.h"
 #include "servers/audio/audio_server.h"
+#ifdef GAS_REF_WITH_SHIM
+#include "audio_spatializer_3d_gpu.h" /* integration/godot_module: the GPU-backed spatializer classes */
+#include "gas_backend.h"
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -98,6 +102,7 @@ struct RefSpatializer {
 	Ref<AudioSpatializer3D> res3d;       /* the 3D resource (for EFFECT: the formulas the script mirrors) */
 	Ref<AudioSpatializerEffect> res_fx;  /* EFFECT kind */
 	bool valid = false;
+	bool gpu = false; // res3d is an AudioSpatializer3DGPU (integration/godot_module), see ref_use_gpu_shim
 };
 
 struct RefWorld {
@@ -119,6 +124,7 @@ struct RefWorld {
 	const gas_area *cur_area = nullptr;
 	int closest_calls = 0;
 	bool stream_mode = false;
+	bool use_gpu_shim = false;
 };
 
 String bus_name(int idx) {
@@ -289,6 +295,11 @@ void pose_player(RefWorld *w, RefInstance &q, const gas_emitter *e, int n_listen
 	if (AudioSpatializerInstance3D *i3 = Object::cast_to<AudioSpatializerInstance3D>(instance_of(q))) {
 		i3->velocity_tracker->gl_velocity = vel;
 	}
+#ifdef GAS_REF_WITH_SHIM
+	if (AudioSpatializerInstance3DGPU *ig = Object::cast_to<AudioSpatializerInstance3DGPU>(instance_of(q))) {
+		ig->velocity_tracker->gl_velocity = vel;
+	}
+#endif
 	if (q.companion.is_valid()) {
 		q.companion->velocity_tracker->gl_velocity = vel;
 	}
@@ -343,7 +354,7 @@ GAS_API ref_world *ref_create(const gas_config *cfg) {
 	w->server.gl_order_key = [w](AudioStreamPlayback *p) -> int64_t {
 		AudioStreamPlaybackSpatial *sp = Object::cast_to<AudioStreamPlaybackSpatial>(p);
 		if (!sp) {
-			return 0;
+			return INT64_MAX; // not a spatializer proxy (the GPU shim's feeders): after every proxy, as upstream's newest-first list has them
 		}
 		for (size_t i = 0; i < w->inst.size(); i++) {
 			if (w->inst[i].player && w->inst[i].player->spatializer.ptr() == sp->spatializer) {
@@ -360,10 +371,15 @@ GAS_API void ref_destroy(ref_world *w) {
 		return;
 	}
 	Scope sc(w);
-	w->server.gl_playbacks.clear();
 	for (RefInstance &q : w->inst) {
 		destroy_instance(q);
 	}
+#ifdef GAS_REF_WITH_SHIM
+	if (w->use_gpu_shim) {
+		GasBackend::shutdown();
+	}
+#endif
+	w->server.gl_playbacks.clear();
 	delete w;
 }
 
@@ -390,6 +406,26 @@ GAS_API int ref_set_global_panning_strength(ref_world *w, float s) {
 }
 /* upstream AudioServer mixes each playback through its own 64-frame lookahead; off by default because the
  * batched path is defined at the bus-accumulate input. */
+/* 1 = AudioSpatializer3D resources are created as AudioSpatializer3DGPU (integration/godot_module): the same scene, the same
+ * reference plumbing around it, the arithmetic on the device.  Only in the library built with the shim (libgas_ref_gpu.so);
+ * one world at a time (the shim keeps one device context per process, like one AudioServer per engine). */
+GAS_API int ref_use_gpu_shim(ref_world *w, int on) {
+#ifdef GAS_REF_WITH_SHIM
+	w->use_gpu_shim = on != 0;
+	return GAS_OK;
+#else
+	(void)w;
+	return on ? GAS_ERR_STATE : GAS_OK;
+#endif
+}
+GAS_API int ref_has_gpu_shim(void) {
+#ifdef GAS_REF_WITH_SHIM
+	return 1;
+#else
+	return 0;
+#endif
+}
+
 GAS_API int ref_set_server_lookahead(ref_world *w, int on) {
 	w->server.gl_playback_lookahead = on != 0;
 	return GAS_OK;
@@ -404,8 +440,18 @@ GAS_API int ref_spatializer_set(ref_world *w, int slot, const gas_spatializer *s
 	Scope sc(w);
 	RefSpatializer &r = w->spat[(size_t)slot];
 	int errors0 = godot_lite::error_log().count;
-	if (!r.valid || r.pod.kind != s->kind) {
-		r.res3d.instantiate();
+	if (!r.valid || r.pod.kind != s->kind || r.gpu != w->use_gpu_shim) {
+#ifdef GAS_REF_WITH_SHIM
+		if (w->use_gpu_shim && s->kind == GAS_SPATIALIZER_3D) {
+			Ref<AudioSpatializer3DGPU> g;
+			g.instantiate();
+			r.res3d = g;
+		} else
+#endif
+		{
+			r.res3d.instantiate();
+		}
+		r.gpu = w->use_gpu_shim;
 		r.res_fx.unref();
 		if (s->kind == GAS_SPATIALIZER_EFFECT) {
 			r.res_fx.instantiate();

@@ -95,7 +95,11 @@ def main():
         ok, worst, nbad = S.sample_close(got2[b], want[b])
         ok_all &= ok
         print(f"rank {rank} block {b} (pipelined exchange): ok={ok} worst_abs_err={worst:.3e} bad={nbad}", flush=True)
+    flag = torch.tensor([1 if ok_all else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
+    if rank == 0 and int(flag.item()) == 1:
+        print(f"multi-GPU check ok: {world} ranks, in-order and pipelined exchange match the unsharded oracle", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok_all else 1)
 
