@@ -198,8 +198,27 @@ void prof_close(gas_ctx *ctx, gas_ctx::ProfPair *p) {
 	}
 }
 
+// Outstanding voice-parallel kernels of pipelined steps (side stream): the mix stream waits for them.
+int join_voice_stream(gas_ctx *ctx) {
+	for (int i = 0; i < GAS_PLAN_DEPTH; i++) {
+		if (ctx->block_inflight[i]) {
+			GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_block_done[i], 0));
+			ctx->block_inflight[i] = false;
+		}
+	}
+	return GAS_OK;
+}
+
+// One block, one call: plan (k_plan), stream (step kernel without control work), voice-parallel kernel, in order on the mix stream.
 int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_frame *d_src, int src_rows, int src_stride, int frames,
 		gas_frame *d_bus, gas_frame *d_peaks) {
+	if (ctx->planned.valid) {
+		return gas_fail(ctx, GAS_ERR_STATE, "a block planned by gas_step_device is waiting to be streamed: finish the pipelined run first (gas_step_device with next = NULL)");
+	}
+	int st = join_voice_stream(ctx);
+	if (st) {
+		return st;
+	}
 	if (ctx->gain_pending) {
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
 	}
@@ -208,46 +227,96 @@ int mix_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_fr
 		ctx->comm_pending = false;
 	}
 	gas_ctx::ProfPair *pp = prof_open(ctx, GAS_KERNEL_PROLOGUE);
-	if (!(ctx->skip & 1)) {
-		GAS_CUDA(ctx, launch_prologue(ctx, n_voices, d_voices, src_rows, frames, d_bus, d_peaks, ctx->s_mix));
-	}
+	GAS_CUDA(ctx, launch_plan(ctx, n_voices, d_voices, src_rows, frames, d_bus, d_peaks, ctx->s_mix));
 	prof_close(ctx, pp);
 	pp = prof_open(ctx, GAS_KERNEL_NONE); // the timer's own reading: a pair with nothing between its two records
 	prof_close(ctx, pp);
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix));
 	ctx->prologue_pending = true;
-	if (n_voices > 0 && ctx->par_voice) {
-		// the voice-parallel kernel on its own stream beside the streaming kernel: both only add into the bus buffers
-		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_voice_fork, ctx->s_mix));
-		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_voice, ctx->ev_voice_fork, 0));
-		pp = prof_open(ctx, GAS_KERNEL_MIX_VOICE, ctx->s_voice);
-		if (!(ctx->skip & 4)) {
-			GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_voice, false));
-		}
-		prof_close(ctx, pp);
-		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_voice_join, ctx->s_voice));
-		pp = prof_open(ctx, GAS_KERNEL_MIX_STREAM);
-		if (!(ctx->skip & 2)) {
-			GAS_CUDA(ctx, launch_mix_stream(ctx, d_src, src_stride, frames, d_bus, ctx->s_mix));
-		}
-		prof_close(ctx, pp);
-		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_voice_join, 0));
-	} else if (n_voices > 0) {
-		// streaming kernel (partial sums into the replica buffers), then the voice-parallel kernel, whose launch
-		// also folds the replicas into the bus buffers
-		pp = prof_open(ctx, GAS_KERNEL_MIX_STREAM);
-		if (!(ctx->skip & 2)) {
-			GAS_CUDA(ctx, launch_mix_stream(ctx, d_src, src_stride, frames, d_bus, ctx->s_mix));
-		}
-		prof_close(ctx, pp);
-		pp = prof_open(ctx, GAS_KERNEL_MIX_VOICE);
-		if (!(ctx->skip & 4)) {
-			GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_mix, !(ctx->skip & 2)));
-		}
-		prof_close(ctx, pp);
-	}
+	// every planned block gets exactly one launch of the step kernel and of the voice-parallel kernel (they count blocks on the device)
+	pp = prof_open(ctx, GAS_KERNEL_MIX_STREAM);
+	GAS_CUDA(ctx, launch_step(ctx, d_src, src_stride, frames, d_bus, nullptr, ctx->s_mix, (ctx->pdl & 2) != 0));
+	prof_close(ctx, pp);
+	pp = prof_open(ctx, GAS_KERNEL_MIX_VOICE);
+	GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, frames, d_bus, d_peaks, ctx->s_mix, true));
+	prof_close(ctx, pp);
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_mix_done, ctx->s_mix)); // inside a capture: the edge a later exchange of this block hangs on
 	ctx->mix_pending = true;
+	return GAS_OK;
+}
+
+// Pipelined form: one launch of the step kernel streams the planned block and prepares the next one on its control warps; the
+// voice-parallel kernel of the streamed block runs on the side stream, off the chain of step kernels.
+int step_core(gas_ctx *ctx, const gas_frame *d_src, int src_stride, const StepNext *next) {
+	const bool have = ctx->planned.valid;
+	if (!have && !next) {
+		return GAS_OK;
+	}
+	if (ctx->gain_pending) {
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
+	}
+	if (ctx->comm_pending) {
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_comm_done, 0));
+		ctx->comm_pending = false;
+	}
+	constexpr int D = GAS_PLAN_DEPTH;
+	const int i = (int)(ctx->step_count % D), im1 = (int)((ctx->step_count + D - 1) % D), im2 = (int)((ctx->step_count + D - 2) % D);
+	if (!have) {
+		// first block of a run: gains and plan by the stand-alone kernels, in order on the mix stream
+		int st = join_voice_stream(ctx);
+		if (st) {
+			return st;
+		}
+		if (next->n_emitters > 0) {
+			gas_ctx::ProfPair *pg = prof_open(ctx, GAS_KERNEL_GAIN);
+			GAS_CUDA(ctx, launch_gain(ctx, next->n_emitters, next->d_emitters, ctx->n_listeners_res, ctx->d_listeners, ctx->d_areas, nullptr, ctx->s_mix));
+			prof_close(ctx, pg);
+		}
+		gas_ctx::ProfPair *pp = prof_open(ctx, GAS_KERNEL_PROLOGUE);
+		GAS_CUDA(ctx, launch_plan(ctx, next->n_voices, next->d_voices, next->src_rows, next->frames, next->d_bus, next->d_peaks, ctx->s_mix));
+		prof_close(ctx, pp);
+		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_step_done[im1], ctx->s_mix));
+		ctx->step_done_valid = true;
+	} else {
+		// plan slots and output buffers about to be rewritten by this launch's control warps must be free: the voice-parallel kernel
+		// of the block before last (its plan slot comes up for clearing), and the last one's if the next block reuses its buffers
+		if (ctx->block_inflight[im2]) {
+			GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_block_done[im2], 0));
+			ctx->block_inflight[im2] = false;
+		}
+		if (next && ctx->block_inflight[im1] && (ctx->inflight_bus[im1] == next->d_bus || (next->d_peaks && ctx->inflight_peaks[im1] == next->d_peaks))) {
+			GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_block_done[im1], 0));
+			ctx->block_inflight[im1] = false;
+		}
+		// the voice-parallel kernel of this block: its plan is complete once the previous step kernel (or the priming plan) is
+		if (ctx->step_done_valid) {
+			GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_voice, ctx->ev_step_done[im1], 0));
+		}
+		gas_ctx::ProfPair *pp = prof_open(ctx, GAS_KERNEL_MIX_VOICE, ctx->s_voice);
+		GAS_CUDA(ctx, launch_mix_voice(ctx, d_src, src_stride, ctx->planned.frames, ctx->planned.bus, ctx->planned.peaks, ctx->s_voice, false));
+		prof_close(ctx, pp);
+		pp = prof_open(ctx, GAS_KERNEL_MIX_STREAM);
+		GAS_CUDA(ctx, launch_step(ctx, d_src, src_stride, ctx->planned.frames, ctx->planned.bus, next, ctx->s_mix, (ctx->pdl & 8) != 0));
+		prof_close(ctx, pp);
+		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_step_done[i], ctx->s_mix));
+		ctx->step_done_valid = true;
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_voice, ctx->ev_step_done[i], 0));
+		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_block_done[i], ctx->s_voice));
+		ctx->block_inflight[i] = true;
+		ctx->inflight_bus[i] = ctx->planned.bus;
+		ctx->inflight_peaks[i] = ctx->planned.peaks;
+		ctx->step_count++;
+	}
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix)); // gain-side calls wait for the control warps
+	ctx->prologue_pending = true;
+	ctx->planned.valid = next != nullptr;
+	if (next) {
+		ctx->planned.n_voices = next->n_voices;
+		ctx->planned.frames = next->frames;
+		ctx->planned.src_rows = next->src_rows;
+		ctx->planned.bus = next->d_bus;
+		ctx->planned.peaks = next->d_peaks;
+	}
 	return GAS_OK;
 }
 
@@ -376,12 +445,8 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 		ctx->gain_after_stream = !(e && atoi(e) == 0);
 		e = getenv("GAS_K2_SCALED");
 		ctx->scaled_classes = !(e && atoi(e) == 0);
-		e = getenv("GAS_K2_REPLICAS");
-		ctx->replicas = e ? atoi(e) : 1; // the streaming kernel adds straight into the bus buffers (measured flat against 8 replicas + fold)
-		ctx->replicas = ctx->replicas < 1 ? 1 : (ctx->replicas > 16 ? 16 : ctx->replicas);
-		if (ctx->replicas > 1) {
-			ctx->par_voice = false;
-		}
+		ctx->replicas = 1; // the step kernel adds straight into the bus buffers (8 replicas + fold measured no faster)
+		ctx->par_voice = false;
 		e = getenv("GAS_K2_DEBUG"); // the timeline buffer must exist before anything is captured into a graph
 		if (e && (atoi(e) & 8)) {
 			cudaMalloc((void **)&ctx->d_timeline, 256 * 16 * sizeof(unsigned long long));
@@ -407,7 +472,7 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->t.inst_cur, I);
 	ALLOC(ctx->t.inst_prev, 2 * I);
 	ALLOC(ctx->t.inst_mode, I);
-	ALLOC(ctx->t.blk, (size_t)2);
+	ALLOC(ctx->t.blk, (size_t)BLK_WORDS);
 	ctx->t.max_instances = (int32_t)I;
 	ALLOC(ctx->t.inst_fx, I);
 	ALLOC(ctx->t.vs_prev, V * 8);
@@ -425,12 +490,13 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->plan.cls_key, (size_t)GAS_MAX_CLASSES);
 	ALLOC(ctx->plan.cls_aux, (size_t)GAS_MAX_CLASSES);
 	ALLOC(ctx->plan.cls_idle, (size_t)GAS_MAX_CLASSES);
-	ALLOC(ctx->plan.cls_count, (size_t)2 * GAS_MAX_CLASSES);
+	ALLOC(ctx->plan.cls_count, (size_t)GAS_PLAN_DEPTH * GAS_MAX_CLASSES);
 	ALLOC(ctx->plan.overflow, (size_t)1);
-	ALLOC(ctx->plan.list, (size_t)GAS_MAX_CLASSES * V);
-	ALLOC(ctx->plan.k2_rows, (size_t)GAS_MAX_CLASSES * V * GAS_K2_ROW_FLOATS + 64);
-	ALLOC(ctx->plan.rec, V);
-	ALLOC(ctx->plan.sends, V);
+	ALLOC(ctx->plan.list, (size_t)GAS_PLAN_DEPTH * GAS_MAX_CLASSES * V);
+	ALLOC(ctx->plan.k2_rows, (size_t)GAS_PLAN_ROW_DEPTH * GAS_MAX_CLASSES * V * GAS_K2_ROW_FLOATS + 64);
+	ALLOC(ctx->plan.rec, (size_t)GAS_PLAN_DEPTH * V);
+	ALLOC(ctx->plan.sends, (size_t)GAS_PLAN_DEPTH * V);
+	ALLOC(ctx->plan.hdr, (size_t)GAS_PLAN_DEPTH);
 	ALLOC(ctx->d_voices, V);
 	ALLOC(ctx->d_src, V * F);
 	ALLOC(ctx->d_bus, (size_t)GAS_MAX_BUSES * GAS_MAX_CHANNELS_PER_BUS * F);
@@ -473,6 +539,10 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_prologue_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+	for (int i = 0; i < GAS_PLAN_DEPTH; i++) {
+		ok = ok && cudaEventCreateWithFlags(&ctx->ev_step_done[i], cudaEventDisableTiming) == cudaSuccess;
+		ok = ok && cudaEventCreateWithFlags(&ctx->ev_block_done[i], cudaEventDisableTiming) == cudaSuccess;
+	}
 	if (ok) {
 		ok = launch_defaults(ctx, ctx->s_gain) == cudaSuccess && cudaStreamSynchronize(ctx->s_gain) == cudaSuccess;
 	}
@@ -507,7 +577,7 @@ void gas_destroy(gas_ctx *ctx) {
 		ctx->plan.overflow, ctx->plan.list, ctx->plan.k2_rows, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
 		ctx->d_peaks, ctx->d_rep, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
 		ctx->d_exchange, ctx->d_comm_seq, ctx->d_comm_ticket, ctx->t.vs_look, ctx->t.vs_life, ctx->t.inst_threshold, ctx->d_stage, ctx->d_voices_stage,
-		ctx->d_mixed, ctx->d_status, ctx->d_ids_mix, ctx->d_scratch_mix };
+		ctx->d_mixed, ctx->d_status, ctx->d_ids_mix, ctx->d_scratch_mix, ctx->plan.hdr };
 	for (void *p : ptrs) {
 		if (p) {
 			cudaFree(p);
@@ -532,6 +602,14 @@ void gas_destroy(gas_ctx *ctx) {
 	for (cudaEvent_t e : { ctx->ev_mix_done, ctx->ev_comm_done, ctx->ev_join2, ctx->ev_voice_fork, ctx->ev_voice_join, ctx->ev_stream_started }) {
 		if (e) {
 			cudaEventDestroy(e);
+		}
+	}
+	for (int i = 0; i < GAS_PLAN_DEPTH; i++) {
+		if (ctx->ev_step_done[i]) {
+			cudaEventDestroy(ctx->ev_step_done[i]);
+		}
+		if (ctx->ev_block_done[i]) {
+			cudaEventDestroy(ctx->ev_block_done[i]);
 		}
 	}
 	if (ctx->s_comm) {
@@ -911,6 +989,48 @@ int gas_mix_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voic
 	return mix_core(ctx, n_voices, d_voices, d_src, src_rows, src_row_stride, frames, d_bus_out, d_peaks);
 }
 
+// ---- pipelined form -----------------------------------------------------------------------------------------------
+int gas_step_device(gas_ctx *ctx, const gas_frame *d_src, int32_t src_row_stride, const gas_step_next *next) {
+	ENTER(ctx);
+	StepNext nx{};
+	if (next) {
+		if (next->n_voices < 0 || next->n_voices > ctx->cfg.max_voices || (next->n_voices > 0 && !next->d_voices) || !next->d_bus_out) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_step_device: next block: bad voice count or null pointer");
+		}
+		if (next->frames < 2 || (next->frames & 1) || next->frames > ctx->cfg.max_frames || ((uintptr_t)next->d_bus_out & 15u)) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_step_device: next block: frames must be even and <= max_frames, bus buffers 16-byte aligned");
+		}
+		if (next->n_emitters < 0 || next->n_emitters > ctx->cfg.max_instances || (next->n_emitters > 0 && !next->d_emitters)) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_step_device: next block: bad emitter count or null pointer");
+		}
+		if (next->n_emitters > 0 && ctx->n_listeners_res <= 0) {
+			return gas_fail(ctx, GAS_ERR_STATE, "gas_step_device: gains need resident listeners (gas_listeners_set)");
+		}
+		if (ctx->planned.valid && (next->d_bus_out == ctx->planned.bus || (next->d_peaks && next->d_peaks == ctx->planned.peaks))) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_step_device: the next block must not share output buffers with the block being streamed");
+		}
+		nx.n_emitters = next->n_emitters;
+		nx.d_emitters = next->d_emitters;
+		nx.n_voices = next->n_voices;
+		nx.d_voices = next->d_voices;
+		nx.src_rows = next->src_rows;
+		nx.frames = next->frames;
+		nx.d_bus = next->d_bus_out;
+		nx.d_peaks = next->d_peaks;
+	}
+	if (ctx->planned.valid) {
+		if ((ctx->planned.n_voices > 0 && !d_src) || src_row_stride < ctx->planned.frames || (src_row_stride & 1) || ((uintptr_t)d_src & 15u)) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_step_device: source rows of the planned block: null / misaligned pointer or stride < frames");
+		}
+	}
+	return step_core(ctx, d_src, src_row_stride, next ? &nx : nullptr);
+}
+
+int gas_step_join_device(gas_ctx *ctx) {
+	ENTER(ctx);
+	return join_voice_stream(ctx);
+}
+
 // ---- stream form: voice lifecycle around the block path (gas_life.cu) ---------------------------------------------
 static int stream_core(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, const gas_frame *d_src, int src_rows, int src_stride, int frames,
 		const int32_t *d_mixed, gas_frame *d_bus, int32_t *d_status) {
@@ -1103,6 +1223,7 @@ int gas_sync(gas_ctx *ctx) {
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_gain));
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_comm));
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_voice));
 	return GAS_OK;
 }
 
@@ -1111,7 +1232,7 @@ void *gas_gain_stream(gas_ctx *ctx) { return ctx ? (void *)ctx->s_gain : nullptr
 uint64_t gas_kernel_launches(const gas_ctx *ctx) { return ctx ? ctx->launches : 0; }
 // experiments only (not in gas.h): device pointer of the K2 timeline buffer, [CTA][8] uint64
 extern "C" GAS_API void *gas_debug_timeline(gas_ctx *ctx) { return ctx ? (void *)ctx->d_timeline : nullptr; }
-// experiments only (not in gas.h): the routing-class table after a synchronise — keys[128], counts[2][128] (by block parity)
+// experiments only (not in gas.h): the routing-class table after a synchronise — keys[128], counts[2][128] (the two most recent plan slots)
 extern "C" GAS_API int gas_debug_classes(gas_ctx *ctx, unsigned long long *keys, int32_t *counts) {
 	if (!ctx || !keys || !counts) {
 		return GAS_ERR_INVALID;
@@ -1119,7 +1240,12 @@ extern "C" GAS_API int gas_debug_classes(gas_ctx *ctx, unsigned long long *keys,
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	cudaMemcpy(keys, ctx->plan.cls_key, GAS_MAX_CLASSES * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-	cudaMemcpy(counts, ctx->plan.cls_count, 2 * GAS_MAX_CLASSES * sizeof(int32_t), cudaMemcpyDeviceToHost);
+	int32_t p = 0;
+	cudaMemcpy(&p, ctx->t.blk + BLK_P, sizeof(int32_t), cudaMemcpyDeviceToHost);
+	for (int i = 0; i < 2; i++) { // counts[0] = the last planned block, counts[1] = the one before
+		const int slot = (p - 1 - i) & (GAS_PLAN_DEPTH - 1);
+		cudaMemcpy(counts + i * GAS_MAX_CLASSES, ctx->plan.cls_count + slot * GAS_MAX_CLASSES, GAS_MAX_CLASSES * sizeof(int32_t), cudaMemcpyDeviceToHost);
+	}
 	return GAS_OK;
 }
 
@@ -1159,13 +1285,19 @@ int gas_capture_begin(gas_ctx *ctx) {
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_gain));
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_comm));
 	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_voice));
 	ctx->gain_pending = ctx->prologue_pending = ctx->mix_pending = ctx->comm_pending = false;
 	ctx->stream_started_pending = false;
+	ctx->step_done_valid = false;
+	for (int i = 0; i < GAS_PLAN_DEPTH; i++) {
+		ctx->block_inflight[i] = false;
+	}
 	GAS_CUDA(ctx, cudaStreamBeginCapture(ctx->s_mix, cudaStreamCaptureModeThreadLocal));
-	// fork: the gain stream joins the capture
+	// fork: the gain, exchange and voice streams join the capture
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->s_mix));
 	GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_gain, ctx->ev_fork, 0));
 	GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comm, ctx->ev_fork, 0));
+	GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_voice, ctx->ev_fork, 0));
 	ctx->capturing = true;
 	ctx->capture_profiled = false;
 	for (int k = 0; k < GAS_KERNEL_KINDS; k++) {
@@ -1191,6 +1323,16 @@ int gas_capture_end(gas_ctx *ctx, int32_t *out_graph) {
 	}
 	if (e == cudaSuccess) {
 		e = cudaStreamWaitEvent(ctx->s_mix, ctx->ev_join2, 0);
+	}
+	if (e == cudaSuccess) {
+		e = cudaEventRecord(ctx->ev_voice_join, ctx->s_voice); // and the voice stream
+	}
+	if (e == cudaSuccess) {
+		e = cudaStreamWaitEvent(ctx->s_mix, ctx->ev_voice_join, 0);
+	}
+	ctx->step_done_valid = false;
+	for (int i = 0; i < GAS_PLAN_DEPTH; i++) {
+		ctx->block_inflight[i] = false;
 	}
 	cudaError_t e2 = cudaStreamEndCapture(ctx->s_mix, &graph);
 	const uint64_t kernels = ctx->launches - ctx->capture_launches0;
@@ -1239,6 +1381,9 @@ int gas_graph_launch(gas_ctx *ctx, int32_t graph) {
 	ctx->prologue_pending = true;
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_mix_done, ctx->s_mix)); // ... and so does a later exchange
 	ctx->mix_pending = true;
+	// ... and the voice-parallel kernel of a pipelined step enqueued after this launch (its plan may come out of this graph)
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_step_done[(ctx->step_count + GAS_PLAN_DEPTH - 1) % GAS_PLAN_DEPTH], ctx->s_mix));
+	ctx->step_done_valid = true;
 	return GAS_OK;
 }
 

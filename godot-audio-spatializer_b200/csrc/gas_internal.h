@@ -14,8 +14,11 @@
 // ---- limits of the per-block plan -----------------------------------------------------------------
 #define GAS_MAX_SENDS 12      // union of current and previous bus details: 6 + 6
 #define GAS_MAX_CLASSES 128   // class slots: distinct (path, mode, flags, send-mask, degree) combinations seen since the last reset
-#define GAS_K2_MAX_ROWS 6     // weight rows per (pair, side) the streaming kernel holds in registers
+#define GAS_K2_MAX_ROWS 6     // polynomial rows per (pair, side) of a streamed voice: 2 (A, B) or 3 (A, B, C) per row group
 #define GAS_K2_ROW_FLOATS (GAS_K2_MAX_ROWS * GAS_MAX_CHANNELS_PER_BUS * 2)
+#define GAS_PLAN_DEPTH 4      // plans in flight: block b lives in slot b % 4 (the step kernel of block b plans block b + 1 while the
+                              // voice-parallel kernels of blocks b - 1 and b may still be reading theirs)
+#define GAS_PLAN_ROW_DEPTH 2  // weight rows are only read by the streaming part of the step kernel: block parity is enough
 
 // upstream AudioStreamPlaybackBusDetails of an instance's proxy playbacks, folded over the proxies:
 // vol[k][c] is what reaches pair c of bus[k] (reference audio_spatializer.cpp:274-324).
@@ -53,7 +56,7 @@ enum : int32_t { MODE_A = 0, MODE_B = 1, MODE_E = 2 };
 #define GAS_CLS_IDLE_BLOCKS 8 // a class slot that stayed empty for this many blocks is recycled
 
 // A class is identified by a 64-bit key; everything a kernel needs to know about it is decoded from the key:
-//   path [0,2)  mode [2,4)  flags [4,8)  n_send [8,12)  bus mask [16,32)  quad [32,44)
+//   path [0,2)  mode [2,4)  flags [4,8)  n_send [8,12)  bus mask [16,32)  quad [32,33)
 // CLS_SCALED classes are told apart by a second word as well (aux: the float bits of the scale of send 1 in the low
 // half, of send 2 in the high half): two voices share a class only if their sends are the same multiples of send 0.
 struct ClassInfo {
@@ -64,12 +67,14 @@ struct ClassInfo {
 	int32_t mode;
 	uint32_t flags;
 	uint32_t mask;   // bus mask of the sends
-	uint32_t quad;   // bit k set <=> row group k carries a t^2 row (its ramp product is not linear in t)
+	uint32_t quad;   // 1 <=> every row group carries a t^2 row (some ramp product of the class is not linear in t)
 	int32_t n_send;  // popcount(mask)
-	int32_t n_group; // row groups: 1 if CLS_SHARED else n_send
-	int32_t n_rows;  // sum over groups of (2 + quad bit); 0 on the voice-parallel path
+	int32_t n_group; // row groups: 1 if CLS_SHARED / CLS_SCALED else n_send
+	int32_t n_rows;  // n_group * (2 + quad); 0 on the voice-parallel path
 	int32_t slot;    // slot of the class in the global table (addresses its list)
+	int32_t pad[2];  // 64 bytes: tables of these are copied 16 bytes at a time
 };
+static_assert(sizeof(ClassInfo) == 64, "ClassInfo is copied as int4 words");
 
 static __host__ __device__ __forceinline__ unsigned long long cls_key(int path, int mode, uint32_t flags, int n_send, uint32_t mask, uint32_t quad) {
 	return (unsigned long long)path | ((unsigned long long)mode << 2) | ((unsigned long long)flags << 4) | ((unsigned long long)n_send << 8) |
@@ -85,19 +90,40 @@ static __host__ __device__ __forceinline__ ClassInfo cls_decode(unsigned long lo
 	ci.flags = (uint32_t)((key >> 4) & 15u);
 	ci.n_send = (int32_t)((key >> 8) & 15u);
 	ci.mask = (uint32_t)((key >> 16) & 0xffffu);
-	ci.quad = (uint32_t)((key >> 32) & 0xfffu);
+	ci.quad = (uint32_t)((key >> 32) & 1u);
 	ci.scale[0] = ci.scale[1] = 0.f;
 	ci.n_group = ci.path == PATH_STREAM ? ((ci.flags & (CLS_SHARED | CLS_SCALED)) ? 1 : ci.n_send) : ci.n_send;
-	int rows = 0;
-	if (ci.path == PATH_STREAM) {
-		rows = 2 * ci.n_group;
-		for (uint32_t q = ci.quad; q; q &= q - 1) {
-			rows++;
-		}
-	}
-	ci.n_rows = rows;
+	ci.n_rows = ci.path == PATH_STREAM ? ci.n_group * (2 + (int)ci.quad) : 0;
+	ci.pad[0] = ci.pad[1] = 0;
 	return ci;
 }
+
+// Weight record of one streamed voice (floats): per row group g and pair c a 16-byte element {A_L, A_R, B_L, B_R}, then,
+// for classes with a t^2 row, per (g, c) an 8-byte element {C_L, C_R}; padded to a multiple of 16 bytes.
+static __host__ __device__ __forceinline__ int cls_row_floats(int n_group, int quad, int C) { return (n_group * C * (quad ? 6 : 4) + 3) & ~3; }
+
+// Complete description of one planned block, written by the planner's last CTA and published through `seq`.
+struct PlanHdr {
+	int32_t seq;    // block index + 1 once the plan is complete (release store; readers acquire)
+	int32_t n_cls;  // streaming classes with voices in this block (compact table below, slot order)
+	int32_t n_vcls; // voice-parallel classes with voices in this block (0: the voice-parallel kernel has nothing to do)
+	int32_t pad;
+	ClassInfo cls[GAS_MAX_CLASSES];
+	ClassInfo vcls[GAS_MAX_CLASSES];
+};
+
+// device-side counters (DevTables::blk), one per 32-byte sector
+enum : int32_t {
+	BLK_P = 0,       // plans produced so far = index of the next block to plan
+	BLK_P_TICKET = 8,
+	BLK_S = 16,      // step-kernel launches so far = index of the next block to stream
+	BLK_S_TICKET = 24,
+	BLK_Q = 32,      // voice-parallel launches so far = index of the next block it mixes
+	BLK_Q_TICKET = 40,
+	BLK_BAR_CNT = 48, // grid barrier of the control warps (count, generation)
+	BLK_BAR_GEN = 56,
+	BLK_WORDS = 64
+};
 
 // What K3 needs about one voice besides its persistent state.
 struct VoiceRec {
@@ -117,13 +143,20 @@ struct BlockPlan {
 	unsigned long long *cls_key; // [GAS_MAX_CLASSES] slot -> class key (0 = free); slots are stable across blocks
 	unsigned long long *cls_aux; // [GAS_MAX_CLASSES] second word of the class identity (CLS_SCALED: the scales), CLS_AUX_NONE when unset
 	int32_t *cls_idle;   // [GAS_MAX_CLASSES] consecutive blocks the slot stayed empty (recycled at GAS_CLS_IDLE_BLOCKS)
-	int32_t *cls_count;  // [2][GAS_MAX_CLASSES] by block parity; block n fills [n & 1] and clears [(n + 1) & 1]
+	int32_t *cls_count;  // [GAS_PLAN_DEPTH][GAS_MAX_CLASSES] by plan slot; the planner of block b clears the counts of slot (b + 1) % depth when it is done
 	int32_t *overflow;   // [1] set when more than GAS_MAX_CLASSES classes were needed
-	int2 *list;          // [GAS_MAX_CLASSES][max_voices] {call-order index j, source row} per list position
-	float *k2_rows;      // [GAS_MAX_CLASSES][max_voices][GAS_K2_ROW_FLOATS] by list position (compact: n_rows*C*2 floats per voice)
-	VoiceRec *rec;       // [max_voices] by call-order index
-	InstSends *sends;    // [max_voices] by call-order index: resolved sends of the voice's instance (K3 voices only)
+	int2 *list;          // [GAS_PLAN_DEPTH][GAS_MAX_CLASSES][max_voices] {call-order index j, source row} per list position
+	float *k2_rows;      // [GAS_PLAN_ROW_DEPTH][GAS_MAX_CLASSES][max_voices][GAS_K2_ROW_FLOATS] by list position (compact: cls_row_floats per voice)
+	VoiceRec *rec;       // [GAS_PLAN_DEPTH][max_voices] by call-order index
+	InstSends *sends;    // [GAS_PLAN_DEPTH][max_voices] by call-order index: resolved sends of the voice's instance (K3 voices only)
+	PlanHdr *hdr;        // [GAS_PLAN_DEPTH]
 };
+static __host__ __device__ __forceinline__ int2 *plan_list(const BlockPlan &p, int slot, int cid, int maxv) {
+	return p.list + ((size_t)slot * GAS_MAX_CLASSES + cid) * maxv;
+}
+static __host__ __device__ __forceinline__ float *plan_rows(const BlockPlan &p, int block, int cid, int maxv) {
+	return p.k2_rows + ((size_t)(block & (GAS_PLAN_ROW_DEPTH - 1)) * GAS_MAX_CLASSES + cid) * maxv * GAS_K2_ROW_FLOATS;
+}
 
 struct DevTables {
 	gas_spatializer *spat;
@@ -134,7 +167,7 @@ struct DevTables {
 	BusDetails *inst_cur;
 	BusDetails *inst_prev;   // [2][max_instances]: double-buffered by block parity (read [p], write [1-p])
 	int32_t *inst_mode;      // MODE_A/B/E | (effect_gain_binding + 1) << 8, latched at instantiate()
-	int32_t *blk;            // [0] block counter (parity of inst_prev and of the class counts), [1] CTA ticket of the prologue
+	int32_t *blk;            // [BLK_WORDS] device-side block counters and tickets (BLK_*)
 	int32_t max_instances;
 	gas_effect_chain *inst_fx;
 	float *vs_prev;              // [max_voices][4][2]
@@ -182,6 +215,19 @@ struct gas_ctx {
 	bool mix_pending = false, comm_pending = false;
 	bool reduce_open = false; // gas_reduce_bus_begin_device without its _end yet
 	bool gain_pending = false, prologue_pending = false;
+	// pipelined form (gas_step_device): the block that has been planned and not streamed yet, and the voice-parallel kernels
+	// still in flight on the side stream
+	struct PlannedBlock {
+		bool valid = false;
+		int n_voices = 0, frames = 0, src_rows = 0;
+		gas_frame *bus = nullptr, *peaks = nullptr;
+	} planned;
+	uint64_t step_count = 0;                        // pipelined steps launched (or captured) so far
+	cudaEvent_t ev_step_done[GAS_PLAN_DEPTH] = {};  // recorded on the mix stream behind the step kernel of step % depth (and behind a priming plan)
+	cudaEvent_t ev_block_done[GAS_PLAN_DEPTH] = {}; // recorded on the voice stream: step kernel AND voice-parallel kernel of that block are complete
+	bool block_inflight[GAS_PLAN_DEPTH] = {};
+	gas_frame *inflight_bus[GAS_PLAN_DEPTH] = {}, *inflight_peaks[GAS_PLAN_DEPTH] = {};
+	bool step_done_valid = false; // ev_step_done[(step_count - 1) % depth] has been recorded
 	DevTables t{};
 	BlockPlan plan{};
 	// staging (device)
@@ -303,12 +349,24 @@ cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_list
 cudaError_t launch_params_set(gas_ctx *ctx, int n, const int32_t *d_ids, const gas_params *d_params, cudaStream_t st);
 cudaError_t launch_instance_start(gas_ctx *ctx, int n, const int32_t *d_ids, cudaStream_t st);
 // gas_prologue.cu
-cudaError_t launch_prologue(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int src_rows, int frames, gas_frame *d_bus,
+cudaError_t launch_plan(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int src_rows, int frames, gas_frame *d_bus,
 		gas_frame *d_peaks, cudaStream_t st);
 // frames of one replica of the partial-sum buffers for a block of `frames` frames (16-byte units)
 static inline int gas_bus_f4(const gas_ctx *ctx, int frames) { return ctx->g.num_buses * ctx->g.channels * frames / 2; }
-// gas_mix_stream.cu (K2) / gas_mix_voice.cu (K3)
-cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, cudaStream_t st);
+// gas_mix_stream.cu (the step kernel) / gas_mix_voice.cu (K3)
+// what the control warps of a step launch prepare: gains (n_emitters > 0, resident listeners / areas) and plan of the next block
+struct StepNext {
+	int n_emitters;
+	const gas_emitter *d_emitters;
+	int n_voices;
+	const gas_voice *d_voices;
+	int src_rows;
+	int frames;
+	gas_frame *d_bus;
+	gas_frame *d_peaks;
+};
+cudaError_t launch_step(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, const StepNext *next, cudaStream_t st,
+		bool pdl);
 // after_stream: launched right behind the streaming kernel on the same stream (its class-table look may then precede the dependency wait)
 cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus,
 		gas_frame *d_peaks, cudaStream_t st, bool after_stream);

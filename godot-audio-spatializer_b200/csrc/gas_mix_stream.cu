@@ -1,35 +1,46 @@
-// gas_mix_stream.cu — K2: the streaming mix kernel (sm_100a).
+// gas_mix_stream.cu — the step kernel (sm_100a): streams the voices of block k into its bus buffers and, on the same
+// SMs and in the same launch, computes the gains and the plan of block k + 1.
 //
-// For every voice whose block needs no per-sample recurrence (no attenuation filter, no effect chain)
+// Streaming part.  For every voice whose block needs no per-sample recurrence (no attenuation filter, no effect chain)
 // the reference's per-voice work (mix_channel ramp, reference audio_spatializer_3d.cpp:600-604, the
 // += into the instance mix buffer, audio_spatializer.cpp:433-434, and the AudioServer ramped bus
 // accumulate, upstream _mix_step_for_channel) collapses to
 //       bus[b][c][i] += (A + B t + C t^2) * x_v[i],   t = i / F
-// with the polynomial rows prepared by the prologue.  Summed over voices this is a skinny fp32
-// contraction  Out[rows, F] = W[rows, V] . X[V, F]  followed by the evaluation in t — HBM-bound: every
-// source frame (8 bytes) is read exactly once and feeds 2*rows FMAs.
+// with the polynomial coefficients prepared by the planner.  Summed over voices this is a skinny fp32
+// contraction — HBM-bound: every source frame (8 bytes) is read exactly once.
 //
-// Structure: persistent, one CTA per SM, warp-specialised.
+// Structure: persistent, one CTA per SM, 16 warps, warp-specialised.
 //   warp 8      producer: streams voice rows HBM -> shared memory with 1-D bulk async copies (TMA engine,
 //               cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) through a ring of stages; rows are
 //               gathered by the class lists, so voices need not be contiguous in memory.  One copy per voice
-//               row plus one per stage for the weights: tools/streamtest.cu measured this pattern (4 KB
+//               row plus one per stage for the weight records: tools/streamtest.cu measured this pattern (4 KB
 //               rows, 148 CTAs) at 4.6-4.7 TB/s for a 64 MiB pass including launch, against 4.1 TB/s for
 //               per-warp cp.async rings; a bulk copy costs ~75 ns of issue whatever its size, so tiles
 //               narrower than 512 frames (more, smaller copies) stream slower.
-//   warps 0-7   consumers: each thread owns 2 frames of the tile and keeps rows x 2 (L,R) accumulators in
-//               registers; weights are broadcast from shared memory; the FMAs are packed FFMA2
-//               (fma.rn.f32x2: one instruction per (L,R) pair).
+//   warps 0-7   consumers: each thread owns 2 frames of the tile and keeps one (L,R) accumulator per (row group, pair,
+//               frame) in registers; per voice it evaluates the weight at its two frames, w = A + t (B + t C), and adds
+//               w * x: the FMAs are packed FFMA2 (fma.rn.f32x2: one instruction per (L,R) pair), weights are 128-bit
+//               shared-memory broadcasts.  (The first version accumulated sum A x, sum B x, sum C x separately and applied
+//               the polynomial at the flush: the same FMA count, but 2-3 times the accumulator registers — 168 per thread,
+//               which left no room on the SM for anything else.)
+//   warps 9-15  control: gains (calculate_spatialization, gas_gain.cuh) and plan (gas_plan.cuh) of the NEXT block, two
+//               lanes per emitter / voice: latency-bound dependent chains that need few issue slots and no bandwidth,
+//               i.e. exactly what the streaming warps leave idle.  As separate kernels they cost the step 12 + 14 us
+//               beside 21 us of streaming; here they hide behind it.
 // A CTA owns a contiguous range of (class, frame tile, voice batch) units; ranges are cut in cost space
-// (accumulator count + a fixed per-voice term) so that the FMA-heavy classes do not pile up on a few SMs.
-// When the class or tile changes the CTA evaluates the polynomial in t and adds its partial sums to the bus
-// buffers with per-thread red.global.add.v4.f32, straight out of the accumulator registers (the row layout of a
-// class is resolved by a switch over compile-time layouts: a first version parked the accumulators in a
-// thread-local array and indexed it at run time, and with 216 KB of the SM's SRAM carved out as shared memory
-// those local loads went to L2 one dependent round trip after another, ~3 us per flush).  Two other flush
-// shapes were measured and dropped: shared-memory staging + bulk async reductions (cp.reduce.async.bulk, +4 us)
-// and plain stores into per-CTA slabs folded later (no gain).  No per-voice state is written here.
-#include "gas_internal.h"
+// (weight count + a fixed per-voice term).  When the class or tile changes the CTA adds its partial sums to the bus
+// buffers with per-thread red.global.add.v4.f32 straight out of the accumulator registers.
+//
+// Chaining.  Block indices live on the device (BLK_S: launches of this kernel so far; BLK_P: plans produced), so a
+// replayed CUDA graph needs no host-side state.  Launched with programmatic stream serialization, the next step's CTAs
+// start on an SM as soon as this step's CTA there has left: its streaming warps only need the plan of their block
+// (PlanHdr::seq, acquire) — published by the previous launch's control warps — while its control warps first wait for
+// the previous launch to be complete (griddepcontrol.wait), because they overwrite what that launch may still be reading.
+//
+// Compiled with -fmad=false (the control warps reproduce the reference's rounding sequence); every FMA of the
+// streaming part is explicit.
+#include "gas_gain.cuh"
+#include "gas_plan.cuh"
 
 #include <stdlib.h>
 
@@ -41,9 +52,12 @@ namespace {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = kConsumerThreads + 32;
+constexpr int kStreamThreads = kConsumerThreads + 32; // consumers + producer
+constexpr int kControlWarps = 7;
+constexpr int kControlThreads = kControlWarps * 32;
+constexpr int kThreads = kStreamThreads + kControlThreads; // 512
 constexpr int kTileFrames = 512;       // frames per tile: 2 per consumer thread
-constexpr int kMaxPairs = GAS_K2_MAX_ROWS * GAS_MAX_CHANNELS_PER_BUS; // 24 (L,R) weight pairs per voice
+constexpr int kMaxPairs = GAS_K2_MAX_ROWS * GAS_MAX_CHANNELS_PER_BUS; // 24 (L,R) weights per voice
 constexpr int kMaxStages = 8;
 
 struct StreamCfg {
@@ -58,12 +72,27 @@ struct StreamCfg {
 	int x_bytes;       // per stage
 	int w_bytes;       // per stage
 	int stage_bytes;
-	int fixed_cost;    // per-voice term of the partition cost (the other term is the accumulator count)
+	int fixed_cost;    // per-voice term of the partition cost (the other term is the weight count)
 	int vb_shift;      // log2(vb)
 	double inv_grid;   // 1 / CTAs
-	double inv_cost[kMaxPairs + 1]; // 1 / (accumulators + fixed_cost)
+	double inv_cost[kMaxPairs + 1]; // 1 / (weights + fixed_cost)
 	int debug;         // GAS_K2_DEBUG bits (experiments only): 1 = skip the bus reductions, 2 = skip the FMAs, 4 = skip the copies, 8 = record a timeline
 	unsigned long long *timeline; // [CTA][16] globaltimer stamps (debug & 8), see tools/k2bench.cpp for the slots
+};
+
+// Everything one launch needs.  Streaming part: block BLK_S (planned earlier).  Control part: the next block.
+struct StepArgs {
+	gasplan::PlanArgs p; // tables + the next block's voice list and outputs
+	StreamCfg cf;
+	const gas_frame *src;
+	float *bus;
+	int control_on;      // 0: the control warps leave at once (one-call-per-block entry points plan with k_plan)
+	int n_emitters;      // gain side of the next block (0: parameters stay)
+	const gas_emitter *emitters;
+	int n_listeners;
+	const gas_listener *listeners;
+	const gas_area *areas;
+	int n_areas;
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------
@@ -105,23 +134,25 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-// packed (L,R) FMA: acc += w * x on both halves with one instruction (SASS: FFMA2)
-__device__ __forceinline__ void fma2(float2 &acc, const float2 w, const float2 x) {
+// packed (L,R) FMA: a * b + c on both halves with one instruction (SASS: FFMA2)
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+	float2 d;
 #if GAS_USE_FFMA2
 	asm("{\n"
-		".reg .b64 a, ww, xx;\n"
-		"mov.b64 a, {%0, %1};\n"
-		"mov.b64 ww, {%2, %3};\n"
-		"mov.b64 xx, {%4, %5};\n"
-		"fma.rn.f32x2 a, ww, xx, a;\n"
-		"mov.b64 {%0, %1}, a;\n"
+		".reg .b64 ra, rb, rc, rd;\n"
+		"mov.b64 ra, {%2, %3};\n"
+		"mov.b64 rb, {%4, %5};\n"
+		"mov.b64 rc, {%6, %7};\n"
+		"fma.rn.f32x2 rd, ra, rb, rc;\n"
+		"mov.b64 {%0, %1}, rd;\n"
 		"}\n"
-		: "+f"(acc.x), "+f"(acc.y)
-		: "f"(w.x), "f"(w.y), "f"(x.x), "f"(x.y));
+		: "=f"(d.x), "=f"(d.y)
+		: "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
 #else
-	acc.x = fmaf(w.x, x.x, acc.x);
-	acc.y = fmaf(w.y, x.y, acc.y);
+	d.x = fmaf(a.x, b.x, c.x);
+	d.y = fmaf(a.y, b.y, c.y);
 #endif
+	return d;
 }
 
 // ---- unit iterator: (class, frame tile, voice batch), identical in every role ------------
@@ -325,7 +356,7 @@ __device__ __forceinline__ IdxBlock idx_block_load(UnitIter &pf, const ClassInfo
 	const int n = min(upb, min(pf.nb - pf.batch, pf.remaining));
 	const int pos = pf.batch * cf.vb + lane;
 	if (lane < n * cf.vb && pos < cls[pf.cid].count) {
-		b.val = __ldg(list + (size_t)cls[pf.cid].slot * maxv + pos);
+		b.val = __ldcg(list + (size_t)cls[pf.cid].slot * maxv + pos);
 	}
 	b.n_units = n;
 	// advance by n units: they all lie in the current (class, tile) row of batches
@@ -340,7 +371,7 @@ struct ConsumerCtx {
 	uint64_t *full;
 	uint64_t *empty;
 	const ClassInfo *cls;
-	int C, tid, lane, slot, group;
+	int tid, lane, slot, group;
 	bool worker;
 	int stage;
 	uint32_t phase;
@@ -349,30 +380,29 @@ struct ConsumerCtx {
 };
 
 // The FMAs of one stage for one thread: `n` voices spaced `step` apart (rows `row_bytes` apart starting at xp, weight
-// records NP*8 bytes apart starting at wp).  The loads of several voices are issued before their FMAs (4 voices for
-// the small classes, 2 for the large ones: the register budget): two consumer warps per scheduler cannot hide the
-// shared-memory latency of one voice at a time.  STATIC: step 1 and 4 KB rows, every offset an immediate.
-template <int NP, bool STATIC>
-__device__ __forceinline__ void voice_loop(float2 (&acc)[NP][2], const unsigned char *xp, const unsigned char *wp, int n, int step, int row_bytes) {
-	constexpr int U = NP <= 10 ? 4 : 2;
+// records `w_stride` bytes apart starting at wp).  E = row groups x pairs: element e of a record is {A_L, A_R, B_L, B_R} at
+// e * 16, its t^2 part {C_L, C_R} at E * 16 + e * 8.  The loads of several voices are issued before their FMAs: two consumer
+// warps per scheduler cannot hide the shared-memory latency of one voice at a time.  STATIC: step 1 and 4 KB rows.
+template <int E, bool QUAD, bool STATIC>
+__device__ __forceinline__ void voice_loop(float2 (&acc)[E][2], const unsigned char *xp, const unsigned char *wp, int n, int step, int row_bytes,
+		int w_stride, const float2 T0, const float2 T1) {
+	constexpr int U = QUAD ? (E <= 2 ? 4 : (E <= 4 ? 2 : 1)) : (E <= 4 ? 4 : (E <= 8 ? 2 : 1));
 	const int xs = STATIC ? kTileFrames * 8 : step * row_bytes; // bytes between consecutive voices of this thread
-	const int ws = STATIC ? NP * 8 : step * (NP * 8);
+	const int ws = step * w_stride;
 	int left = STATIC ? n : (n + step - 1) / step; // voices this thread still has to do
 	for (; left >= U; left -= U, xp += U * xs, wp += U * ws) {
 		float4 x[U];
-		float4 w[U][(NP + 1) / 2];
+		float4 w[U][E];
+		float2 qd[U][QUAD ? E : 1];
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			x[u] = *reinterpret_cast<const float4 *>(xp + u * xs);
 			const unsigned char *wv = wp + u * ws;
 #pragma unroll
-			for (int p = 0; p < NP; p += 2) {
-				if (NP % 2 == 0) {
-					w[u][p / 2] = *reinterpret_cast<const float4 *>(wv + p * 8);
-				} else {
-					const float2 a = *reinterpret_cast<const float2 *>(wv + p * 8);
-					const float2 b = p + 1 < NP ? *reinterpret_cast<const float2 *>(wv + p * 8 + 8) : make_float2(0.f, 0.f);
-					w[u][p / 2] = make_float4(a.x, a.y, b.x, b.y);
+			for (int e = 0; e < E; e++) {
+				w[u][e] = *reinterpret_cast<const float4 *>(wv + e * 16);
+				if (QUAD) {
+					qd[u][e] = *reinterpret_cast<const float2 *>(wv + E * 16 + e * 8);
 				}
 			}
 		}
@@ -380,14 +410,16 @@ __device__ __forceinline__ void voice_loop(float2 (&acc)[NP][2], const unsigned 
 		for (int u = 0; u < U; u++) {
 			const float2 x0 = make_float2(x[u].x, x[u].y), x1 = make_float2(x[u].z, x[u].w);
 #pragma unroll
-			for (int p = 0; p < NP; p += 2) {
-				const float2 wa = make_float2(w[u][p / 2].x, w[u][p / 2].y), wb = make_float2(w[u][p / 2].z, w[u][p / 2].w);
-				fma2(acc[p][0], wa, x0);
-				fma2(acc[p][1], wa, x1);
-				if (p + 1 < NP) {
-					fma2(acc[p + 1][0], wb, x0);
-					fma2(acc[p + 1][1], wb, x1);
+			for (int e = 0; e < E; e++) {
+				const float2 a = make_float2(w[u][e].x, w[u][e].y);
+				float2 b0 = make_float2(w[u][e].z, w[u][e].w), b1 = b0;
+				if (QUAD) {
+					b0 = ffma2(qd[u][e], T0, b0);
+					b1 = ffma2(qd[u][e], T1, b1);
 				}
+				const float2 w0 = ffma2(b0, T0, a), w1 = ffma2(b1, T1, a);
+				acc[e][0] = ffma2(w0, x0, acc[e][0]);
+				acc[e][1] = ffma2(w1, x1, acc[e][1]);
 			}
 		}
 	}
@@ -395,69 +427,44 @@ __device__ __forceinline__ void voice_loop(float2 (&acc)[NP][2], const unsigned 
 		const float4 x = *reinterpret_cast<const float4 *>(xp);
 		const float2 x0 = make_float2(x.x, x.y), x1 = make_float2(x.z, x.w);
 #pragma unroll
-		for (int p = 0; p < NP; p++) {
-			const float2 wa = *reinterpret_cast<const float2 *>(wp + p * 8);
-			fma2(acc[p][0], wa, x0);
-			fma2(acc[p][1], wa, x1);
+		for (int e = 0; e < E; e++) {
+			const float4 w = *reinterpret_cast<const float4 *>(wp + e * 16);
+			const float2 a = make_float2(w.x, w.y);
+			float2 b0 = make_float2(w.z, w.w), b1 = b0;
+			if (QUAD) {
+				const float2 qd = *reinterpret_cast<const float2 *>(wp + E * 16 + e * 8);
+				b0 = ffma2(qd, T0, b0);
+				b1 = ffma2(qd, T1, b1);
+			}
+			const float2 w0 = ffma2(b0, T0, a), w1 = ffma2(b1, T1, a);
+			acc[e][0] = ffma2(w0, x0, acc[e][0]);
+			acc[e][1] = ffma2(w1, x1, acc[e][1]);
 		}
 	}
 }
 
-// One row group (rows R0, R0+1 and, when `quad`, R0+2 of a class with R rows) of one run: evaluate the
-// polynomial at this thread's two frames and add the result to bus `b_own`, or to every bus of `fan` when the
-// group is shared by all sends.  Every accumulator index is a compile-time constant.
-template <int R, int C, int R0>
-__device__ __forceinline__ void flush_group(const float2 (&acc)[R * C][2], bool quad, uint32_t fan, float sc1, float sc2, int b_own, float t0, float t1,
-		float *__restrict__ bus, int F, int frame0) {
-#pragma unroll
-	for (int c = 0; c < C; c++) {
-		const float2 a0 = acc[R0 * C + c][0], a1 = acc[R0 * C + c][1];
-		const float2 b0 = acc[(R0 + 1) * C + c][0], b1 = acc[(R0 + 1) * C + c][1];
-		float2 c0 = make_float2(0.f, 0.f), c1 = make_float2(0.f, 0.f);
-		if (R0 + 2 < R) {
-			if (quad) {
-				c0 = acc[(R0 + 2 < R ? R0 + 2 : 0) * C + c][0];
-				c1 = acc[(R0 + 2 < R ? R0 + 2 : 0) * C + c][1];
-			}
-		}
-		float4 v;
-		v.x = fmaf(t0, fmaf(t0, c0.x, b0.x), a0.x);
-		v.y = fmaf(t0, fmaf(t0, c0.y, b0.y), a0.y);
-		v.z = fmaf(t1, fmaf(t1, c1.x, b1.x), a1.x);
-		v.w = fmaf(t1, fmaf(t1, c1.y, b1.y), a1.y);
-		if (fan) { // one row group fanned out to every bus of the mask: as it is (shared), or times the send's scale (scaled)
-			uint32_t m = fan;
-			float sc = 1.f, nxt = sc1;
-			while (m) {
-				const int b = __ffs(m) - 1;
-				m &= m - 1;
-				red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, v.x * sc, v.y * sc, v.z * sc, v.w * sc);
-				sc = nxt;
-				nxt = sc2;
-			}
-		} else {
-			red_add_v4(bus + ((size_t)(b_own * C + c) * F + frame0) * 2, v.x, v.y, v.z, v.w);
-		}
-	}
-}
-
-// One run = every consecutive unit of this CTA that shares (class, tile).  R rows x C channel pairs = NP (L,R)
-// weight pairs per voice.  The accumulators live in registers for the whole run; at its end the polynomial
-// is evaluated in t and the partial sums are added to the bus buffers.
-template <int R, int C>
+// One run = every consecutive unit of this CTA that shares (class, tile).  NG row groups x C channel pairs accumulators
+// per frame, in registers for the whole run; at its end the partial sums are added to the bus buffers.
+template <int NG, int C, bool QUAD>
 __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, const StreamCfg &cf, float *__restrict__ bus) {
-	constexpr int NP = R * C;
-	float2 acc[NP][2];
+	constexpr int E = NG * C;
+	float2 acc[E][2];
 #pragma unroll
-	for (int p = 0; p < NP; p++) {
-		acc[p][0] = make_float2(0.f, 0.f);
-		acc[p][1] = make_float2(0.f, 0.f);
+	for (int e = 0; e < E; e++) {
+		acc[e][0] = make_float2(0.f, 0.f);
+		acc[e][1] = make_float2(0.f, 0.f);
 	}
 	const int cid = it.cid, tile = it.tile;
 	const ClassInfo &ci = cc.cls[cid];
 	const int tile_w = min(cf.tile_frames, cf.frames - tile * cf.tile_frames);
 	const int row_bytes = tile_w * 8;
+	const int w_stride = cls_row_floats(NG, QUAD ? 1 : 0, C) * 4;
 	const bool mine = cc.worker && cc.slot * 2 < tile_w;
+	const int F = cf.frames;
+	const int frame0 = tile * cf.tile_frames + cc.slot * 2;
+	const float t0 = (float)frame0 / (float)F;
+	const float t1 = (float)(frame0 + 1) / (float)F;
+	const float2 T0 = make_float2(t0, t0), T1 = make_float2(t1, t1);
 	do {
 		const int v0 = it.batch * cf.vb;
 		const int nv = min(cf.vb, ci.count - v0);
@@ -469,12 +476,12 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 			cc.tl_first = true;
 		}
 		if (mine && !(cf.debug & 2)) {
-			// full 512-frame tiles (one voice group, 4 KB rows) take the loop whose strides are compile-time constants:
-			// the generic one spends as many instructions on addresses as on loads
+			// full 512-frame tiles (one voice group, 4 KB rows) take the loop whose row stride is a compile-time constant
 			if (cf.groups == 1 && row_bytes == kTileFrames * 8) {
-				voice_loop<NP, true>(acc, sx + cc.slot * 16, sw, nv, 1, kTileFrames * 8);
+				voice_loop<E, QUAD, true>(acc, sx + cc.slot * 16, sw, nv, 1, kTileFrames * 8, w_stride, T0, T1);
 			} else {
-				voice_loop<NP, false>(acc, sx + (size_t)cc.group * row_bytes + cc.slot * 16, sw + cc.group * (NP * 8), nv - cc.group, cf.groups, row_bytes);
+				voice_loop<E, QUAD, false>(acc, sx + (size_t)cc.group * row_bytes + cc.slot * 16, sw + cc.group * w_stride, nv - cc.group, cf.groups,
+						row_bytes, w_stride, T0, T1);
 			}
 		}
 		__syncwarp();
@@ -493,68 +500,114 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 	if ((cf.debug & 1) || !mine) {
 		return;
 	}
-	// ---- flush: bus[b][c][i] += A + B t (+ C t^2), rows ordered [group][poly][pair] --------------------
+	// ---- flush: bus[b][c][i] += the sums of this thread's two frames ------------------------------------------------
 	if (cc.tl) {
 		cc.tl[9] = gtime();
 	}
-	const int F = cf.frames;
-	const int frame0 = tile * cf.tile_frames + cc.slot * 2;
-	const float t0 = (float)frame0 / (float)F;
-	const float t1 = (float)(frame0 + 1) / (float)F;
-	const uint32_t fan = (ci.flags & (CLS_SHARED | CLS_SCALED)) ? ci.mask : 0u;
-	const float sc1 = (ci.flags & CLS_SCALED) ? ci.scale[0] : 1.f, sc2 = (ci.flags & CLS_SCALED) ? ci.scale[1] : 1.f;
-	const int RG = ci.n_group; // row groups; group k owns 2 rows (A, B) plus a t^2 row when its quad bit is set
-	uint32_t rest = ci.mask;
-	int r0 = 0; // first row of group k
-	for (int k = 0; k < RG; k++) {
-		const bool quad = (ci.quad >> k) & 1u;
-		const int b_own = __ffs(rest) - 1; // k-th bus of the mask (sends ascend by bus)
-		rest &= rest - 1;
-		// a group starts at row 0, 2, 3 or 4 (at most GAS_K2_MAX_ROWS = 6 rows, 2 or 3 per group)
-		switch (r0) {
-			case 0: flush_group<R, C, 0>(acc, quad, fan, sc1, sc2, b_own, t0, t1, bus, F, frame0); break;
-			case 2:
-				if (R >= 4) {
-					flush_group<R, C, (R >= 4 ? 2 : 0)>(acc, quad, fan, 1.f, 1.f, b_own, t0, t1, bus, F, frame0);
-				}
-				break;
-			case 3:
-				if (R >= 5) {
-					flush_group<R, C, (R >= 5 ? 3 : 0)>(acc, quad, fan, 1.f, 1.f, b_own, t0, t1, bus, F, frame0);
-				}
-				break;
-			default:
-				if (R >= 6) {
-					flush_group<R, C, (R >= 6 ? 4 : 0)>(acc, quad, fan, 1.f, 1.f, b_own, t0, t1, bus, F, frame0);
-				}
-				break;
+	if (ci.flags & (CLS_SHARED | CLS_SCALED)) {
+		// one row group fanned out to every bus of the mask: as it is (shared), or times the send's scale (scaled)
+		uint32_t m = ci.mask;
+		float sc = 1.f, nxt = (ci.flags & CLS_SCALED) ? ci.scale[0] : 1.f;
+		const float nxt2 = (ci.flags & CLS_SCALED) ? ci.scale[1] : 1.f;
+		while (m) {
+			const int b = __ffs(m) - 1;
+			m &= m - 1;
+#pragma unroll
+			for (int c = 0; c < C; c++) {
+				red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, acc[c][0].x * sc, acc[c][0].y * sc, acc[c][1].x * sc, acc[c][1].y * sc);
+			}
+			sc = nxt;
+			nxt = nxt2;
 		}
-		r0 += quad ? 3 : 2;
+	} else {
+		uint32_t rest = ci.mask;
+#pragma unroll
+		for (int k = 0; k < NG; k++) {
+			const int b = __ffs(rest) - 1; // k-th bus of the mask (sends ascend by bus)
+			rest &= rest - 1;
+#pragma unroll
+			for (int c = 0; c < C; c++) {
+				red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, acc[k * C + c][0].x, acc[k * C + c][0].y, acc[k * C + c][1].x, acc[k * C + c][1].y);
+			}
+		}
 	}
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, GlobalCfg g, StreamCfg cf,
-		const gas_frame *__restrict__ src, float *__restrict__ bus, int rep_stride, int replicas, const int32_t *__restrict__ blk) {
-	// flush target: replica (CTA % replicas) of the bus layout
-	bus += (size_t)(blockIdx.x % replicas) * rep_stride;
+// grid-wide barrier of the control groups (all CTAs of the launch are resident: one per SM)
+__device__ __forceinline__ void control_grid_barrier(int32_t *blk, int n_cta, int ctl_tid) {
+	__threadfence();
+	asm volatile("bar.sync 3, %0;" ::"n"(kControlThreads) : "memory");
+	if (ctl_tid == 0) {
+		const int gen = gasplan::ld_volatile(&blk[BLK_BAR_GEN]);
+		if (atomicAdd(&blk[BLK_BAR_CNT], 1) == n_cta - 1) {
+			blk[BLK_BAR_CNT] = 0;
+			__threadfence();
+			atomicAdd(&blk[BLK_BAR_GEN], 1);
+		} else {
+			while (gasplan::ld_volatile(&blk[BLK_BAR_GEN]) == gen) {
+				__nanosleep(64);
+			}
+		}
+		__threadfence();
+	}
+	asm volatile("bar.sync 3, %0;" ::"n"(kControlThreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ StepArgs A) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ UnitIter s_it;
 	__shared__ __align__(8) uint64_t s_full[kMaxStages];
 	__shared__ __align__(8) uint64_t s_empty[kMaxStages];
+	__shared__ gasplan::PlanSmem s_plan;
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
+	const StreamCfg &cf = A.cf;
+	const GlobalCfg &g = A.p.g;
+	const BlockPlan &plan = A.p.plan;
+	int32_t *blk = A.p.t.blk;
 	const int C = g.channels;
 	const int maxv = g.max_voices;
+
+	if (warp > kConsumerWarps) {
+		// ===== control warps: gains and plan of the next block =====
+		if (!A.control_on) {
+			return;
+		}
+		const int ctl_tid = tid - kStreamThreads;
+		// the previous launch is complete after this (its streaming warps read the plan slot and the bus buffers that
+		// are rewritten here; its control warps wrote the tables that are read here)
+		GAS_GRID_DEP_WAIT();
+		if (A.n_emitters > 0) {
+			const int pairs = kControlThreads / 2;
+			const int gbase = lane & 30;
+			const unsigned gm = 3u << gbase;
+			for (int e = blockIdx.x * pairs + (ctl_tid >> 1); e < A.n_emitters; e += gridDim.x * pairs) {
+				gasgain::gain_emitter<2>(A.p.t, g, e, ctl_tid & 1, gbase, gm, A.emitters, A.n_listeners, A.listeners, A.areas, A.n_areas, nullptr);
+			}
+			// every instance's parameters are in place before any voice reads them
+			control_grid_barrier(blk, gridDim.x, ctl_tid);
+		}
+		gasplan::PlanGroup G;
+		G.tid = ctl_tid;
+		G.nthreads = kControlThreads;
+		G.cta = blockIdx.x;
+		G.n_cta = gridDim.x;
+		G.bar_id = 3;
+		gasplan::plan_block(G, s_plan, A.p);
+		return;
+	}
+
 	// timeline (debug & 8): the first lane of the producer warp stamps the start-up, thread 0 the consumer side
 	unsigned long long *tlp = (cf.debug & 8) && tid == kConsumerThreads ? cf.timeline + blockIdx.x * 16 : nullptr;
 	unsigned long long *tl = (cf.debug & 8) && tid == 0 ? cf.timeline + blockIdx.x * 16 : nullptr;
 
 	// Start-up runs on the producer warp alone, with nothing but its own dependent loads in the way of the first
-	// copy: class table (one round of loads) -> partition -> first source-row indices -> copies.  The consumer warps
-	// wait on a named barrier for the table and their iterator; they have nothing to do before data lands anyway.
+	// copy: block index -> plan header (class table) -> partition -> first source-row indices -> copies.  The consumer
+	// warps wait on a named barrier for the table and their iterator; they have nothing to do before data lands anyway.
 	UnitIter it;
+	int slot_p = 0, k = 0;
 	if (warp == kConsumerWarps) {
 		if (tlp) {
 			tlp[0] = gtime();
@@ -562,79 +615,56 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
 			tlp[6] = smid;
 		}
-		// programmatic dependent launch: the plan the prologue wrote is visible after this wait (a no-op when
-		// launched without the attribute)
-		GAS_GRID_DEP_WAIT();
-		// Compact table of the streaming classes of this block, in slot order (identical in every CTA).  The
-		// counts of both parities are fetched together with the block counter so that no load waits for another.
-		constexpr int R = GAS_MAX_CLASSES / 32;
-		unsigned long long key[R], auxw[R];
-		int cnt[2][R], idle[R];
-		const int n = *(volatile const int32_t *)blk;
-#pragma unroll
-		for (int r = 0; r < R; r++) {
-			key[r] = plan.cls_key[r * 32 + lane];
-			auxw[r] = plan.cls_aux[r * 32 + lane];
-			cnt[0][r] = plan.cls_count[r * 32 + lane];
-			cnt[1][r] = plan.cls_count[GAS_MAX_CLASSES + r * 32 + lane];
-			idle[r] = blockIdx.x == 0 ? plan.cls_idle[r * 32 + lane] : 0;
-		}
-		if (lane == 0) { // while the loads fly
+		// Which block: every CTA reads the launch counter, then takes a ticket; the CTA with the last ticket advances the
+		// counter, and only then lets the dependent launch go (a dependent launch starts once EVERY CTA of this one has
+		// triggered, so all of its CTAs read the advanced counter and none of this launch's reads a value later than its own).
+		k = gasplan::ld_volatile(&blk[BLK_S]);
+		if (lane == 0) {
+			const int ticket = atomicAdd(&blk[BLK_S_TICKET], 1);
+			if (ticket == (int)gridDim.x - 1) {
+				blk[BLK_S_TICKET] = 0;
+				*(volatile int32_t *)&blk[BLK_S] = k + 1;
+				__threadfence();
+			}
 			for (int s = 0; s < cf.stages; s++) {
 				mbar_init(&s_full[s], 1);
 				mbar_init(&s_empty[s], kConsumerWarps);
 			}
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			GAS_GRID_DEP_LAUNCH();
 		}
-		const int par = (n + 1) & 1; // the prologue already advanced the counter
-		int base = 0;
-#pragma unroll
-		for (int r = 0; r < R; r++) {
-			const int count = par ? cnt[1][r] : cnt[0][r];
-			const bool on = key[r] != 0ULL && (int)(key[r] & 3u) == PATH_STREAM && count > 0;
-			const unsigned m = __ballot_sync(0xffffffffu, on);
-			if (on) {
-				ClassInfo ci = cls_decode(key[r], count);
-				ci.slot = r * 32 + lane;
-				if (ci.flags & CLS_SCALED) {
-					ci.scale[0] = __uint_as_float((unsigned)(auxw[r] & 0xffffffffu));
-					ci.scale[1] = __uint_as_float((unsigned)(auxw[r] >> 32));
-				}
-				s_cls[base + __popc(m & ((1u << lane) - 1u))] = ci;
-			}
-			base += __popc(m);
-			// Slot recycling (one CTA, once per block, between two prologues): a slot whose class stayed empty for
-			// GAS_CLS_IDLE_BLOCKS blocks is handed back.  Nothing reads a slot with a zero count, so clearing it here
-			// cannot race with the other CTAs of this launch or with the voice-parallel kernel.
-			if (blockIdx.x == 0 && r * 32 + lane < GAS_CLS_DYNAMIC && key[r] != 0ULL) {
-				const int age = count > 0 ? 0 : idle[r] + 1;
-				if (age >= GAS_CLS_IDLE_BLOCKS) {
-					plan.cls_aux[r * 32 + lane] = CLS_AUX_NONE;
-					plan.cls_key[r * 32 + lane] = 0ULL;
-					plan.cls_idle[r * 32 + lane] = 0;
-				} else if (age != idle[r]) {
-					plan.cls_idle[r * 32 + lane] = age;
-				}
+		slot_p = k & (GAS_PLAN_DEPTH - 1);
+		const PlanHdr *hdr = &plan.hdr[slot_p];
+		// the plan of this block: published by the planner's last CTA (normally long before this launch starts)
+		while (gasplan::ld_acquire(&hdr->seq) != k + 1) {
+			__nanosleep(100);
+		}
+		const int n_cls = __ldcg(&hdr->n_cls);
+		{
+			const int4 *srcw = reinterpret_cast<const int4 *>(hdr->cls);
+			int4 *dstw = reinterpret_cast<int4 *>(s_cls);
+			const int words = n_cls * (int)(sizeof(ClassInfo) / 16);
+			for (int i = lane; i < words; i += 32) {
+				dstw[i] = __ldcg(srcw + i);
 			}
 		}
 		__syncwarp();
 		if (tlp) {
 			tlp[11] = gtime();
 		}
-		unit_iter_init_warp(it, s_cls, base, cf, C, blockIdx.x, gridDim.x, lane);
+		unit_iter_init_warp(it, s_cls, n_cls, cf, C, blockIdx.x, gridDim.x, lane);
 		if (lane == 0) {
 			s_it = it;
 		}
 		__syncwarp();
-		asm volatile("bar.arrive 2, %0;" ::"n"(kThreads) : "memory");
+		asm volatile("bar.arrive 2, %0;" ::"n"(kStreamThreads) : "memory");
 		if (tlp) {
 			tlp[1] = gtime();
 			tlp[5] = (unsigned long long)it.remaining;
 		}
 	} else {
-		asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+		asm volatile("bar.sync 2, %0;" ::"n"(kStreamThreads) : "memory");
 		it = s_it;
-		GAS_GRID_DEP_LAUNCH();
 	}
 	if (it.remaining <= 0) {
 		return;
@@ -645,11 +675,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		// ===== producer =====
 		int stage = 0;
 		uint32_t phase = 0;
+		const int2 *list = plan.list + (size_t)slot_p * GAS_MAX_CLASSES * maxv;
+		const float *rows = plan_rows(plan, k, 0, maxv);
 		// Source-row indices are fetched one warp-wide load (32 list positions = 32/vb units) at a time,
 		// two blocks ahead of the copies that need them, so the gather indirection never stalls the ring.
 		UnitIter pf = it;
-		IdxBlock cur = idx_block_load(pf, s_cls, cf, plan.list, maxv, lane, 0);
-		IdxBlock nxt = idx_block_load(pf, s_cls, cf, plan.list, maxv, lane, cur.n_units);
+		IdxBlock cur = idx_block_load(pf, s_cls, cf, list, maxv, lane, 0);
+		IdxBlock nxt = idx_block_load(pf, s_cls, cf, list, maxv, lane, cur.n_units);
 		int seq = 0;
 		if (tlp) {
 			tlp[12] = gtime() + (cur.val.y == -12345 ? 1ULL : 0ULL); // first indices have arrived
@@ -657,15 +689,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		while (it.remaining > 0) {
 			if (seq >= cur.first_seq + cur.n_units) {
 				cur = nxt;
-				nxt = idx_block_load(pf, s_cls, cf, plan.list, maxv, lane, cur.first_seq + cur.n_units);
+				nxt = idx_block_load(pf, s_cls, cf, list, maxv, lane, cur.first_seq + cur.n_units);
 			}
 			const ClassInfo &ci = s_cls[it.cid];
 			const int v0 = it.batch * cf.vb;
 			const int nv = min(cf.vb, ci.count - v0);
 			const int tile_w = min(cf.tile_frames, cf.frames - it.tile * cf.tile_frames); // frames in this tile
 			const uint32_t row_bytes = (uint32_t)tile_w * 8u;
-			const int nf = ci.n_rows * C * 2; // floats of weights per voice
-			const uint32_t w_bytes = ((uint32_t)(nv * nf * 4) + 15u) & ~15u;
+			const int nf = cls_row_floats(ci.n_group, (int)ci.quad, C); // floats of weights per voice
+			const uint32_t w_bytes = (uint32_t)(nv * nf * 4);
 			unsigned char *sx = ring + (size_t)stage * cf.stage_bytes;
 			unsigned char *sw = sx + cf.x_bytes;
 			mbar_wait(&s_empty[stage], phase ^ 1u);
@@ -673,14 +705,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 			if (lane == 0) {
 				mbar_arrive_expect_tx(&s_full[stage], no_copy ? 0u : row_bytes * (uint32_t)nv + w_bytes);
 				if (!no_copy) {
-					bulk_g2s(sw, plan.k2_rows + (size_t)ci.slot * maxv * GAS_K2_ROW_FLOATS + (size_t)v0 * nf, w_bytes, &s_full[stage]);
+					bulk_g2s(sw, rows + (size_t)ci.slot * maxv * GAS_K2_ROW_FLOATS + (size_t)v0 * nf, w_bytes, &s_full[stage]);
 				}
 			}
 			__syncwarp();
 			{
 				const int v = lane - (seq - cur.first_seq) * cf.vb; // this lane's voice inside the stage
 				if (v >= 0 && v < nv && !no_copy) {
-					bulk_g2s(sx + (size_t)v * row_bytes, src + (size_t)cur.val.y * cf.src_stride + (size_t)it.tile * cf.tile_frames, row_bytes,
+					bulk_g2s(sx + (size_t)v * row_bytes, A.src + (size_t)cur.val.y * cf.src_stride + (size_t)it.tile * cf.tile_frames, row_bytes,
 							&s_full[stage]);
 				}
 			}
@@ -704,26 +736,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_mix_stream(BlockPlan plan, Glob
 		cc.full = s_full;
 		cc.empty = s_empty;
 		cc.cls = s_cls;
-		cc.C = C;
 		cc.lane = lane;
 		cc.slot = tid % cf.slots;
 		cc.group = tid / cf.slots;
 		cc.worker = cc.group < cf.groups;
 		cc.stage = 0;
 		cc.phase = 0;
+		float *bus = A.bus;
 		while (it.remaining > 0) {
-			// dispatch on (rows, channel pairs): rows in 2..6, pairs in 1..4
-			const int code = s_cls[it.cid].n_rows * 8 + C;
-#define GAS_RUN(R_, C_) \
-	case (R_) * 8 + (C_): consumer_run<R_, C_>(it, cc, cf, bus); break;
+			// dispatch on (row groups, quadratic, channel pairs): groups in 1..3 (quadratic: 1..2), pairs in 1..4
+			const ClassInfo &ci = s_cls[it.cid];
+			const int code = (ci.n_group * 2 + (int)ci.quad) * 8 + C;
+#define GAS_RUN(G_, Q_, C_) \
+	case ((G_) * 2 + (Q_)) * 8 + (C_): consumer_run<G_, C_, (Q_) != 0>(it, cc, cf, bus); break;
 			switch (code) {
-				GAS_RUN(2, 1) GAS_RUN(2, 2) GAS_RUN(2, 3) GAS_RUN(2, 4)
-				GAS_RUN(3, 1) GAS_RUN(3, 2) GAS_RUN(3, 3) GAS_RUN(3, 4)
-				GAS_RUN(4, 1) GAS_RUN(4, 2) GAS_RUN(4, 3) GAS_RUN(4, 4)
-				GAS_RUN(5, 1) GAS_RUN(5, 2) GAS_RUN(5, 3) GAS_RUN(5, 4)
-				GAS_RUN(6, 1) GAS_RUN(6, 2) GAS_RUN(6, 3) GAS_RUN(6, 4)
+				GAS_RUN(1, 0, 1) GAS_RUN(1, 0, 2) GAS_RUN(1, 0, 3) GAS_RUN(1, 0, 4)
+				GAS_RUN(1, 1, 1) GAS_RUN(1, 1, 2) GAS_RUN(1, 1, 3) GAS_RUN(1, 1, 4)
+				GAS_RUN(2, 0, 1) GAS_RUN(2, 0, 2) GAS_RUN(2, 0, 3) GAS_RUN(2, 0, 4)
+				GAS_RUN(2, 1, 1) GAS_RUN(2, 1, 2) GAS_RUN(2, 1, 3) GAS_RUN(2, 1, 4)
+				GAS_RUN(3, 0, 1) GAS_RUN(3, 0, 2) GAS_RUN(3, 0, 3) GAS_RUN(3, 0, 4)
 				default: // cannot happen; drain so the producer never stalls
-					consumer_run<2, 1>(it, cc, cf, bus);
+					consumer_run<1, 1, false>(it, cc, cf, bus);
 					break;
 			}
 #undef GAS_RUN
@@ -780,35 +813,54 @@ static StreamCfg make_cfg(int frames, int src_stride, int smem_limit, int n_cta)
 	return cf;
 }
 
-cudaError_t launch_mix_stream(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, cudaStream_t st) {
-	static const int kSmemLimit = 216 * 1024;
-	StreamCfg cf = make_cfg(frames, src_stride, kSmemLimit, ctx->num_sms);
-	if (cf.stages < 2) {
+// One launch of the step kernel on `st`: streams the planned block (src rows -> d_bus) and, when `next` is given, computes
+// the gains (next->n_emitters > 0) and the plan of the next block on its control warps.
+cudaError_t launch_step(gas_ctx *ctx, const gas_frame *d_src, int src_stride, int frames, gas_frame *d_bus, const StepNext *next, cudaStream_t st,
+		bool pdl) {
+	static const int kSmemLimit = 206 * 1024;
+	StepArgs A{};
+	A.cf = make_cfg(frames, src_stride, kSmemLimit, ctx->num_sms);
+	if (A.cf.stages < 2) {
 		return cudaErrorInvalidConfiguration;
 	}
-	const size_t smem = (size_t)cf.stages * cf.stage_bytes;
+	const size_t smem = (size_t)A.cf.stages * A.cf.stage_bytes;
 	if (!ctx->k2_smem_attr_set) {
-		cudaError_t e = cudaFuncSetAttribute(k_mix_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+		cudaError_t e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
 		if (e != cudaSuccess) {
 			return e;
 		}
 		ctx->k2_smem_attr_set = true;
 	}
-	// Partial sums: atomic adds into replica (CTA % replicas) of the bus layout; the voice-parallel kernel's
-	// launch folds the replicas into d_bus.
-	float *target = ctx->replicas > 1 ? (float *)ctx->d_rep : (float *)d_bus;
-	const int rep_stride = ctx->replicas > 1 ? gas_bus_f4(ctx, frames) * 4 : 0; // floats
-	if (cf.debug & 8) {
+	if (A.cf.debug & 8) {
 		if (!ctx->d_timeline) {
 			cudaMalloc((void **)&ctx->d_timeline, 256 * 16 * sizeof(unsigned long long));
 		}
 		cudaMemsetAsync(ctx->d_timeline, 0, 256 * 16 * sizeof(unsigned long long), st);
-		cf.timeline = ctx->d_timeline;
+		A.cf.timeline = ctx->d_timeline;
 	}
-	cudaError_t e = gas_launch_ev(k_mix_stream, dim3(ctx->num_sms), dim3(kThreads), smem, st, (ctx->pdl & 2) != 0,
-			ctx->gain_after_stream ? ctx->ev_stream_started : (cudaEvent_t) nullptr, ctx->plan, ctx->g, cf, d_src, target, rep_stride, ctx->replicas,
-			(const int32_t *)ctx->t.blk);
-	ctx->stream_started_pending = ctx->gain_after_stream;
+	A.p.t = ctx->t;
+	A.p.g = ctx->g;
+	A.p.plan = ctx->plan;
+	A.src = d_src;
+	A.bus = (float *)d_bus;
+	if (next) {
+		A.control_on = 1;
+		A.p.inst_hwm = ctx->inst_hwm;
+		A.p.n_voices = next->n_voices;
+		A.p.voices = next->d_voices;
+		A.p.src_rows = next->src_rows;
+		A.p.bus = (float4 *)next->d_bus;
+		A.p.bus_f4 = gas_bus_f4(ctx, next->frames);
+		A.p.peaks = (float2 *)next->d_peaks;
+		A.p.scaled_classes = ctx->scaled_classes ? 1 : 0;
+		A.n_emitters = next->n_emitters;
+		A.emitters = next->d_emitters;
+		A.n_listeners = ctx->n_listeners_res;
+		A.listeners = ctx->d_listeners;
+		A.areas = ctx->d_areas;
+		A.n_areas = ctx->n_areas_res;
+	}
+	cudaError_t e = gas_launch(k_step, dim3(ctx->num_sms), dim3(kThreads), smem, st, pdl, A);
 	ctx->launches++;
 	return e;
 }

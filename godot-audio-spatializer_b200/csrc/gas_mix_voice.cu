@@ -472,81 +472,41 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	if (!early_look) {
 		GAS_GRID_DEP_WAIT(); // not behind the streaming kernel: the class table may not be final before the dependency is met
 	}
-	if (replicas <= 1) {
-		__shared__ int s_any;
-		if (threadIdx.x < 32) {
-			const int lane = threadIdx.x;
-			const int n = *(volatile const int32_t *)t.blk;
-			const int par = (n + 1) & 1;
-			int any = 0;
-			for (int i = lane; i < GAS_MAX_CLASSES; i += 32) {
-				const unsigned long long k = plan.cls_key[i];
-				any |= (k != 0ULL && (int)(k & 3u) == PATH_VOICE && plan.cls_count[par * GAS_MAX_CLASSES + i] > 0) ? 1 : 0;
+	// Which block: launches of this kernel are counted on the device (BLK_Q), so that replayed graphs need no host-side
+	// block index; the plan of block q lives in slot q % GAS_PLAN_DEPTH and was published before this kernel was launched.
+	__shared__ int s_q;
+	if (threadIdx.x == 0) {
+		s_q = *(volatile const int32_t *)&t.blk[BLK_Q];
+	}
+	__syncthreads();
+	const int slot_p = s_q & (GAS_PLAN_DEPTH - 1);
+	const PlanHdr *hdr = &plan.hdr[slot_p];
+	const int n_vcls = __ldcg(&hdr->n_vcls);
+	if (n_vcls <= 0) {
+		// nothing filtered, no peaks (the common case of the unfiltered mix): the block costs this kernel one look
+		if (threadIdx.x == 0) {
+			if (blockIdx.x == 0) {
+				GAS_GRID_DEP_WAIT(); // keeps the stream order intact for whatever follows
 			}
-			any = __any_sync(0xffffffffu, any);
-			if (lane == 0) {
-				s_any = any;
+			if (atomicAdd(&t.blk[BLK_Q_TICKET], 1) == (int)gridDim.x - 1) {
+				t.blk[BLK_Q_TICKET] = 0;
+				__threadfence();
+				*(volatile int32_t *)&t.blk[BLK_Q] = s_q + 1;
 			}
 		}
-		__syncthreads();
-		if (!s_any) {
-			if (blockIdx.x == 0 && threadIdx.x == 0) {
-				GAS_GRID_DEP_WAIT();
-			}
-			return;
-		}
+		return;
 	}
 	GAS_GRID_DEP_WAIT();
-	// fold the streaming kernel's partial sums into the bus buffers: one vector reduction per 16 bytes
-	if (replicas > 1) {
-		const int i = blockIdx.x * blockDim.x + threadIdx.x;
-		if (i < bus_f4) {
-			// all replicas requested before any is added: a rolled loop would pay one L2 round trip per replica
-			float4 v[16];
-#pragma unroll
-			for (int r = 0; r < 16; r++) {
-				v[r] = r < replicas ? __ldcg(rep + (size_t)r * bus_f4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-			}
-			float4 a = v[0];
-#pragma unroll
-			for (int r = 1; r < 16; r++) {
-				a.x += v[r].x;
-				a.y += v[r].y;
-				a.z += v[r].z;
-				a.w += v[r].w;
-			}
-			asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(bus + (size_t)i * 4), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+	{
+		// compact table of the voice-parallel classes of this block (written by the planner's last CTA)
+		const int4 *srcw = reinterpret_cast<const int4 *>(hdr->vcls);
+		int4 *dstw = reinterpret_cast<int4 *>(s_cls);
+		const int words = n_vcls * (int)(sizeof(ClassInfo) / 16);
+		for (int i = threadIdx.x; i < words; i += blockDim.x) {
+			dstw[i] = __ldcg(srcw + i);
 		}
-	}
-	if (threadIdx.x < 32) {
-		// compact table of the voice-parallel classes of this block, in slot order (identical in every CTA)
-		const int lane = threadIdx.x;
-		constexpr int R = GAS_MAX_CLASSES / 32;
-		unsigned long long key[R];
-		int cnt[2][R];
-		const int n = *(volatile const int32_t *)t.blk;
-#pragma unroll
-		for (int r = 0; r < R; r++) {
-			key[r] = plan.cls_key[r * 32 + lane];
-			cnt[0][r] = plan.cls_count[r * 32 + lane];
-			cnt[1][r] = plan.cls_count[GAS_MAX_CLASSES + r * 32 + lane];
-		}
-		const int par = (n + 1) & 1; // the prologue already advanced the counter
-		int base = 0;
-#pragma unroll
-		for (int r = 0; r < R; r++) {
-			const int count = par ? cnt[1][r] : cnt[0][r];
-			const bool on = key[r] != 0ULL && (int)(key[r] & 3u) == PATH_VOICE && count > 0;
-			const unsigned m = __ballot_sync(0xffffffffu, on);
-			if (on) {
-				ClassInfo ci = cls_decode(key[r], count);
-				ci.slot = r * 32 + lane;
-				s_cls[base + __popc(m & ((1u << lane) - 1u))] = ci;
-			}
-			base += __popc(m);
-		}
-		if (lane == 0) {
-			s_ncls = base;
+		if (threadIdx.x == 0) {
+			s_ncls = n_vcls;
 		}
 	}
 	__syncthreads();
@@ -585,9 +545,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 		}
 		const ClassInfo &ci = s_cls[c];
 		ChunkArgs a;
-		a.rec = plan.rec;
-		a.sends = plan.sends;
-		a.list = plan.list + (size_t)ci.slot * g.max_voices;
+		a.rec = plan.rec + (size_t)slot_p * g.max_voices;
+		a.sends = plan.sends + (size_t)slot_p * g.max_voices;
+		a.list = plan_list(plan, slot_p, ci.slot, g.max_voices);
 		a.count = ci.count;
 		a.chunk = k;
 		a.cls_flags = ci.flags;
@@ -597,7 +557,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 			a.list += k;
 			a.count = 1;
 			a.chunk = 0;
-			const InstSends *own = &plan.sends[a.list[0].x];
+			const InstSends *own = &a.sends[a.list[0].x];
 			a.mask = own->mask;
 			a.n_send = own->n;
 		}
@@ -621,6 +581,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 				asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(bus + (size_t)i * 4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 			}
 		}
+	}	__syncthreads();
+	if (threadIdx.x == 0 && atomicAdd(&t.blk[BLK_Q_TICKET], 1) == (int)gridDim.x - 1) {
+		t.blk[BLK_Q_TICKET] = 0;
+		__threadfence();
+		*(volatile int32_t *)&t.blk[BLK_Q] = s_q + 1;
 	}
 }
 

@@ -46,6 +46,8 @@ PROTOTYPES = {
     "gas_effect_params_set": (C.c_int, [_vp, _i32, _vp, _vp]),
     "gas_mix_block": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "gas_mix_block_device": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "gas_step_device": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "gas_step_join_device": (C.c_int, [_vp]),
     "gas_process_frames": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32]),
     "gas_mix_channel": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32]),
     "gas_mix_block_stream": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
@@ -92,8 +94,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.gas_abi_version() != 2:
-        raise ImportError(f"libgas_b200.so has ABI version {lib.gas_abi_version()}, this binding expects 2")
+    if lib.gas_abi_version() != 3:
+        raise ImportError(f"libgas_b200.so has ABI version {lib.gas_abi_version()}, this binding expects 3")
     abi.check_layout(lib.gas_abi_sizeof, "libgas_b200.so")
     _lib = lib
     return lib

@@ -21,6 +21,12 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)
 
 
+class StepNext(C.Structure):
+    """gas_step_next (include/gas.h)"""
+    _fields_ = [("n_emitters", C.c_int32), ("d_emitters", C.c_void_p), ("n_voices", C.c_int32), ("d_voices", C.c_void_p),
+                ("src_rows", C.c_int32), ("frames", C.c_int32), ("d_bus_out", C.c_void_p), ("d_peaks", C.c_void_p)]
+
+
 class Mixer:
     def __init__(self, **config):
         """gas_create.  Keyword arguments override abi.config_defaults()."""
@@ -226,6 +232,22 @@ class Mixer:
         """gas_mix_block_device: asynchronous on the mix stream, everything device-resident."""
         self._ck(self._lib.gas_mix_block_device(self._ctx, int(n_voices), C.c_void_p(d_voices), C.c_void_p(d_src), int(src_rows),
                                                 int(src_row_stride), int(frames), C.c_void_p(d_bus_out), C.c_void_p(d_peaks)))
+
+    def step_device(self, d_src=0, src_row_stride=0, next=None):
+        """gas_step_device: streams the block planned by the previous call from d_src and prepares `next` in the same launch.
+        next: dict(n_voices, d_voices, src_rows, frames, d_bus_out[, d_peaks, n_emitters, d_emitters]) of device pointers, or None
+        to end the run."""
+        if next is None:
+            self._ck(self._lib.gas_step_device(self._ctx, C.c_void_p(d_src), int(src_row_stride), None))
+            return
+        nx = StepNext(int(next.get("n_emitters", 0)), C.c_void_p(next.get("d_emitters", 0) or None), int(next["n_voices"]),
+                      C.c_void_p(next["d_voices"]), int(next["src_rows"]), int(next["frames"]), C.c_void_p(next["d_bus_out"]),
+                      C.c_void_p(next.get("d_peaks", 0) or None))
+        self._ck(self._lib.gas_step_device(self._ctx, C.c_void_p(d_src or None), int(src_row_stride), C.byref(nx)))
+
+    def step_join_device(self):
+        """gas_step_join_device: the mix stream waits for the outstanding voice-parallel kernels of pipelined steps."""
+        self._ck(self._lib.gas_step_join_device(self._ctx))
 
     def process_frames(self, instance, voice, src):
         """gas_process_frames: the reference's process_frames virtual on one voice (audio_spatializer_3d.cpp:491-552,

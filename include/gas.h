@@ -51,7 +51,7 @@ extern "C" {
 #define GAS_MAX_EFFECTS 4        /* AudioEffectFilter instances per AudioSpatializerEffect chain */
 #define GAS_MAX_FILTER_STAGES 4  /* AudioEffectFilter FILTER_6DB..FILTER_24DB */
 #define GAS_MAX_BUSES 16         /* bus indices a context can mix into */
-#define GAS_ABI_VERSION 2
+#define GAS_ABI_VERSION 3
 
 typedef enum gas_status {
 	GAS_OK = 0,
@@ -345,6 +345,35 @@ GAS_API int gas_mix_block(gas_ctx *ctx, int32_t n_voices, const gas_voice *voice
 GAS_API int gas_mix_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices,
 		const gas_frame *d_src, int32_t src_rows, int32_t src_row_stride, int32_t frames,
 		gas_frame *d_bus_out, gas_frame *d_peaks);
+/* ---- pipelined form: one kernel launch per block, for callers that render blocks back to back -------------------------------
+ * No reference analogue in structure (the reference mixes when the audio driver asks), same results: gas_step_device streams the
+ * block that the PREVIOUS call planned into that block's bus buffers and, in the same launch and on the same SMs, does for the
+ * NEXT block what gas_gain_compute_device (calculate_spatialization + the bus-map push, with the resident listeners / areas of
+ * gas_listeners_set / gas_areas_set) and the planning part of gas_mix_block_device do: the latency-bound per-instance / per-voice
+ * work of block k + 1 hides behind the bandwidth-bound streaming of block k, and consecutive launches overlap (programmatic
+ * dependent launch) because block indices and plans live on the device.
+ *   d_src / src_row_stride  source rows of the block being streamed (ignored by the first call of a run, which only plans)
+ *   next                    the block to prepare: its emitters (n_emitters = 0 keeps the current parameters), voice list, source
+ *                           row count, frame count and output buffers (zeroed by this call, complete after the NEXT one);
+ *                           NULL ends the run (the planned block is streamed, nothing is prepared)
+ * next->d_bus_out / d_peaks must differ from the buffers of the block being streamed; reusing the buffers of the block before
+ * that is allowed but costs overlap (rotate over three or more).  Voices that need the voice-parallel kernel (filters, effect
+ * chains, peaks) are mixed by a launch on a side stream: a block's buffers are complete for work on the mix stream after
+ * gas_step_join_device (gas_sync, gas_mix_block* and the reduce calls join by themselves).  gas_mix_block* is refused
+ * (GAS_ERR_STATE) while a planned block is waiting.  Captured into graphs like the other device-resident calls: a replayed graph
+ * must then meet the device in the state it was captured in (a planned block waiting, or none). */
+typedef struct gas_step_next {
+	int32_t n_emitters;
+	const gas_emitter *d_emitters;
+	int32_t n_voices;
+	const gas_voice *d_voices;
+	int32_t src_rows;
+	int32_t frames;
+	gas_frame *d_bus_out;
+	gas_frame *d_peaks; /* optional */
+} gas_step_next;
+GAS_API int gas_step_device(gas_ctx *ctx, const gas_frame *d_src, int32_t src_row_stride, const gas_step_next *next);
+GAS_API int gas_step_join_device(gas_ctx *ctx);
 /* ---- the per-call virtuals, one voice per call (reference audio_spatializer.h:146,148; GDVIRTUAL mirror :103-112) --------
  * Same argument meaning as the reference: the instance's current SpatializerParameters and the voice's SpatializerPlaybackData
  * are the two Ref arguments (addressed by slot), out/src are caller-owned host arrays of `frames` AudioFrames, out is fully

@@ -36,7 +36,7 @@ def test_record_layouts_match(gas, orc):
     gas.abi.check_layout(lib.gas_abi_sizeof, "libgas_b200.so")
     gas.abi.check_layout(orc.load().orc_sizeof, "libgas_oracle.so")
     assert lib.gas_abi_sizeof(999) == 0
-    assert lib.gas_abi_version() == 2
+    assert lib.gas_abi_version() == 3
 
 
 def test_defaults_match_reference_headers(gas):
