@@ -45,6 +45,8 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 WORKLOAD = dict(voices=16384, frames=512, mix_rate=48000.0, speaker_mode=3, num_buses=2, area_fraction=0.25,
                 spat=dict(mix_channel_mode=1, unit_size=1.0, attenuation_filter_db=-80.0), r_min=10.0, r_max=120.0)
 N_SETS = 8  # distinct source / emitter sets rotated through: 8 x 64 MiB = 512 MiB >= 4 x L2
+NB = 4      # bus buffers in rotation
+CLASSIC = bool(os.environ.get("GAS_BENCH_CLASSIC"))  # experiments: one gas_mix_block_device + gas_gain_compute_device call per step
 
 
 def workload_name(w, filt="off"):
@@ -193,8 +195,10 @@ def bench_config(w, world, peer=True):
     V, F, C, B = w["voices"], w["frames"], w["speaker_mode"] + 1, w["num_buses"]
     return {"workload": workload_name(w), "voices_per_gpu": V, "frames": F, "channel_pairs": C, "buses": B,
             "l2": f"{N_SETS} distinct source sets of {V * F * 8 / 2**20:.0f} MiB rotated (> 4x L2)",
-            "launch": "CUDA-graph replay of gas_mix_block_device (block k) with gas_gain_compute_device (parameters of block "
-                      "k+1) beside it on the gain stream; up to 8 consecutive steps per graph launch",
+            "launch": ("CUDA-graph replay of gas_step_device: one kernel launch per step streams block k and computes gains + plan of "
+                       "block k+1 on its control warps; up to 8 consecutive steps per graph launch" if not CLASSIC else
+                       "CUDA-graph replay of gas_mix_block_device (block k) with gas_gain_compute_device (parameters of block "
+                       "k+1) beside it on the gain stream; up to 8 consecutive steps per graph launch"),
             "reduce": ("none (1 GPU)" if world == 1 else
                        "gas_reduce_bus_exchange_device inside the step graph, one block in flight on the exchange stream: every rank "
                        "adds its partial bus buffer into every rank's exchange buffer with vector reductions on peer pointers "
@@ -259,7 +263,9 @@ class DeviceWorkload:
                 self.d_src.append(torch.from_numpy(parity_src).to(dev))
             else:
                 self.d_src.append((torch.rand((V, F, 2), generator=g, device=dev, dtype=torch.float32) - 0.5) * 0.5)
-        self.d_bus = [torch.zeros((w["num_buses"], self.C, F, 2), device=dev, dtype=torch.float32) for _ in range(2)]
+        # bus buffers rotate over 4: the step kernel of block k zeroes the buffer of block k + 1 while block k - 1's may still be
+        # read by the exchange (N > 1) or added to by its voice-parallel kernel
+        self.d_bus = [torch.zeros((w["num_buses"], self.C, F, 2), device=dev, dtype=torch.float32) for _ in range(NB)]
         self.d_sum = [torch.zeros((w["num_buses"], self.C, F, 2), device=dev, dtype=torch.float32) for _ in range(2)]  # N > 1: reduced
         self.d_gate = torch.zeros((w["num_buses"], self.C, F, 2), device=dev, dtype=torch.float32)  # N > 1: start gate scratch
         setup_mixer(self.mixer, w, abi, self.emitters_host, self.listeners, self.areas)
@@ -282,30 +288,52 @@ class DeviceWorkload:
         """Pushes the last block and ends the two blocks still in flight."""
         if getattr(self, "peer_reduce", False):
             F = self.w["frames"]
-            self.mixer.reduce_bus_exchange_device(self.d_bus[k_last % 2].data_ptr(), self.d_sum[(k_last + 1) % 2].data_ptr(), F)
+            self.mixer.step_join_device()
+            self.mixer.reduce_bus_exchange_device(self.d_bus[k_last % NB].data_ptr(), self.d_sum[(k_last + 1) % 2].data_ptr(), F)
             self.mixer.reduce_bus_end_device(self.d_sum[k_last % 2].data_ptr(), F)
 
+    def next_block(self, k):
+        """What the step kernel of block k - 1 prepares: gains (emitter set of block k) and plan of block k."""
+        w = self.w
+        nx = dict(n_voices=w["voices"], d_voices=self.d_voices.data_ptr(), src_rows=w["voices"], frames=w["frames"],
+                  d_bus_out=self.d_bus[k % NB].data_ptr())
+        if not (os.environ.get("GAS_BENCH_NOGAIN") or getattr(self, "no_gain", False)):  # gains left out: experiments
+            nx.update(n_emitters=w["voices"], d_emitters=self.d_emitters[k % N_SETS].data_ptr())
+        return nx
+
+    def restart(self):
+        """Ends a pipelined run (streams the block still planned on the device) and plans block 0 again, so that step 0 can follow."""
+        if CLASSIC:
+            return
+        m, w = self.mixer, self.w
+        m.step_device(self.d_src[0].data_ptr(), w["frames"], next=None)
+        m.step_device(next=self.next_block(0))
+
     def step_device(self, k):
-        """One step = mix of block k (audio side) with, beside it, the gain computation for block k+1 (physics
-        side): the reference runs the two on different threads with a double-buffered parameter hand-off
-        (audio_spatializer.cpp:558-574); here they are the mix stream and the gain stream of the context."""
+        """One step = ONE launch of the step kernel: it streams block k into its bus buffers while its control warps compute,
+        for block k + 1, the gains (calculate_spatialization of every instance: the reference's physics thread) and the plan
+        (what process_frames / mix_channel and AudioServer decide per voice before their sample loops)."""
         m, w = self.mixer, self.w
         s = k % N_SETS
-        m.mix_block_device(w["voices"], self.d_voices.data_ptr(), self.d_src[s].data_ptr(), w["voices"], w["frames"], w["frames"],
-                           self.d_bus[k % 2].data_ptr())
+        if CLASSIC:
+            m.mix_block_device(w["voices"], self.d_voices.data_ptr(), self.d_src[s].data_ptr(), w["voices"], w["frames"], w["frames"],
+                               self.d_bus[k % NB].data_ptr())
+        else:
+            m.step_device(self.d_src[s].data_ptr(), w["frames"], next=self.next_block(k + 1))
         if getattr(self, "peer_reduce", False):
             # N > 1: sum of the per-GPU partial bus buffers over peer memory, inside the graph, one block in flight: while
             # block k mixes, the exchange stream pushes block k-1's partial sums to every rank and writes block k-2's
             # complete sum — the whole exchange (NVLink round trip, system-scope fences, rank skew) is off the critical path.
-            m.reduce_bus_exchange_device(self.d_bus[(k + 1) % 2].data_ptr(), self.d_sum[k % 2].data_ptr(), w["frames"])
-        if not (os.environ.get("GAS_BENCH_NOGAIN") or getattr(self, "no_gain", False)):  # K1 left out: experiments / K2-alone timing
+            m.reduce_bus_exchange_device(self.d_bus[(k - 1) % NB].data_ptr(), self.d_sum[k % 2].data_ptr(), w["frames"])
+        if CLASSIC and not (os.environ.get("GAS_BENCH_NOGAIN") or getattr(self, "no_gain", False)):
             m.gain_compute_device(w["voices"], self.d_emitters[(s + 1) % N_SETS].data_ptr())
-        return self.d_bus[k % 2]
+        return self.d_bus[k % NB]
 
     def capture_steps(self, chunk=1):
         """One CUDA graph per `chunk` consecutive steps (chunk divides N_SETS): graph g replays steps g*chunk .. g*chunk+chunk-1 of
         the source-set rotation.  Several steps per graph take the graph-to-graph launch gap off all but one step in `chunk`."""
         graphs = []
+        self.restart()
         for g in range(N_SETS // chunk):
             self.mixer.capture_begin()
             for j in range(chunk):
@@ -583,12 +611,14 @@ def k2_debug_dump(m, torch):
     fn.argtypes = [ctypes.c_void_p]
     ptr = fn(m._ctx)
     if ptr:
-        tl = torch.empty(148 * 16, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
-        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(tl.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(148 * 16 * 8), 3)
-        t = tl.cpu().numpy().reshape(148, 16).astype(np.float64)
+        tl = torch.empty(148 * 32, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(tl.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(148 * 32 * 8), 3)
+        t = tl.cpu().numpy().reshape(148, 32).astype(np.float64)
         t0 = t[:, 0][t[:, 0] > 0].min()
         names = {0: "start", 11: "table in smem", 1: "partition", 12: "first indices", 13: "stage 0 issued", 2: "first data", 3: "last data",
-                 9: "flush begins", 4: "flushed"}
+                 9: "flush begins", 4: "flushed", 16: "control: entry", 23: "gain: emitter loaded", 24: "gain: tables loaded", 25: "gain: attenuation done", 26: "gain: pan done",
+                 27: "gain: stores issued", 17: "control: gains done", 18: "control: barrier passed",
+                 19: "control: instances done", 20: "control: voices done", 21: "control: ticket", 22: "control: plan published"}
         for k, nm in names.items():
             v = (t[:, k][t[:, k] > 0] - t0) * 1e-3
             if v.size:
@@ -662,7 +692,8 @@ def gpu_arm(args):
             m.graph_launch(graphs[(k // chunk) % len(graphs)])
             if dist is not None and not peer and not os.environ.get("GAS_BENCH_NOREDUCE"):
                 with torch.cuda.stream(stream):
-                    dist.all_reduce(dw.d_bus[k % 2])  # sum of the per-GPU partial bus buffers (NCCL over NVLink)
+                    m.step_join_device()
+                    dist.all_reduce(dw.d_bus[k % NB])  # sum of the per-GPU partial bus buffers (NCCL over NVLink)
 
     def barrier():
         if dist is not None:
@@ -744,22 +775,29 @@ def gpu_arm(args):
     peak, peak_src = measured_hbm_peak()
     bytes_launch = algorithmic_bytes(V, F, C, B)
     k2_us = 1e3 * k2_ms / max(1, k2_n)
-    achieved = bytes_launch / (k2_us * 1e-6) / 1e9
+    step_us = 1e3 * ms / K
 
     def us(kind):
         return 1e3 * prof[kind][0] / max(1, prof[kind][1])
 
+    # The dominant kernel is the step kernel (one launch per step: streaming of block k + gains and plan of block k + 1 on its
+    # control warps).  Consecutive launches overlap (programmatic dependent launch), so its average launch duration over the
+    # timed region is the timed region divided by its launches; the isolated reading (event-record nodes around the kernel in
+    # a second, profiled capture, which serialise the launches) is reported beside it.
+    achieved = bytes_launch / (step_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "k_mix_stream (K2)", "us_per_launch": k2_us, "algorithmic_bytes_per_launch": bytes_launch,
-                "peak_source": peak_src, "timing": "CUDA event-record nodes around the kernel inside the replayed step graph",
-                "step_frac_of_hbm_peak": (bytes_launch / (ms * 1e-3 / K) / 1e9) / peak,
-                "event_pair_overhead_us": 1e3 * prof["none"][0] / max(1, prof["none"][1]),
-                "event_pair_note": "what an event-record pair with nothing between its records reads in the same graph; us_per_launch and "
-                                   "frac above are the raw readings and include it",
-                "alone": {"note": "same kernel in the same graph without K1 running beside it on the gain stream",
-                          "us_per_launch": 1e3 * prof_alone["mix_stream"][0] / max(1, prof_alone["mix_stream"][1]),
-                          "frac": bytes_launch / (1e3 * prof_alone["mix_stream"][0] / max(1, prof_alone["mix_stream"][1]) * 1e-6) / 1e9 / peak},
-                "other_kernels_us": {"gain_K1": us("gain"), "prologue": us("prologue"), "mix_voice_K3": us("mix_voice")}}
+                "kernel": "k_step (streaming of block k + gains and plan of block k+1)" if not CLASSIC else "k_step (streaming only)",
+                "us_per_launch": step_us, "algorithmic_bytes_per_launch": bytes_launch, "launches_in_timed_region": K,
+                "peak_source": peak_src,
+                "timing": "CUDA events on the mix stream around the timed region / launches of the kernel (launches overlap by "
+                          "programmatic dependent launch, so the per-launch average IS the step time)",
+                "step_frac_of_hbm_peak": achieved / peak,
+                "isolated": {"note": "same kernel between event-record nodes in a profiled capture of the same steps (the nodes serialise "
+                                     "the launches and read ~2.7 us by themselves: event_pair_overhead_us)",
+                             "us_per_launch": k2_us, "frac": bytes_launch / (k2_us * 1e-6) / 1e9 / peak,
+                             "event_pair_overhead_us": 1e3 * prof["none"][0] / max(1, prof["none"][1]) if prof["none"][1] else None,
+                             "without_gains_us_per_launch": 1e3 * prof_alone["mix_stream"][0] / max(1, prof_alone["mix_stream"][1])},
+                "other_kernels_us": {"gain_K1": us("gain"), "plan": us("prologue"), "mix_voice_K3": us("mix_voice")}}
     # DRAM traffic of the kernel comes from one `ncu --set full` capture (profiles/): valid only for the kernel source it was
     # taken from, so the file carries the hash of gas_mix_stream.cu and a stale file reports null instead of an old number
     traffic_file = os.path.join(ROOT, "profiles", "k2_traffic_bytes.json")
@@ -777,6 +815,9 @@ def gpu_arm(args):
             pass
 
     # ---- e2e: host buffers through the public API ---------------------------------------------------------------------
+    if not CLASSIC:
+        m.step_device(dw.d_src[0].data_ptr(), F, next=None)  # the pipelined run ends here: the block calls below plan for themselves
+        m.sync()
     ke = max(4, min(K, args.e2e_steps))
     pin_src = [torch.empty((V, F, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
     for t_ in pin_src:

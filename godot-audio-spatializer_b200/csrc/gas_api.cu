@@ -427,10 +427,11 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ctx->l2_bytes = prop.l2CacheSize;
 	refresh_globals(ctx);
 	{
-		// programmatic dependent launch of 1 = prologue, 2 = streaming kernel, 4 = voice-parallel kernel.  Default: the
-		// voice-parallel kernel, whose idle case (no filtered voice in the block) then costs no launch latency.
+		// programmatic dependent launch of 1 = planner kernel, 2 = step kernel of the block-call form, 4 = voice-parallel kernel of the
+		// block-call form, 8 = step kernel of the pipelined form.  Default: 4 (the idle case of the voice-parallel kernel — no filtered
+		// voice in the block — then costs no launch latency) and 8 (consecutive step kernels overlap: measured 37.5 -> 36.1 us per step).
 		const char *e = getenv("GAS_PDL");
-		ctx->pdl = e ? atoi(e) : 4;
+		ctx->pdl = e ? atoi(e) : 12;
 		// The voice-parallel kernel needs nothing the streaming kernel produces (both add into the bus buffers with
 		// reductions), so with GAS_K3_PARALLEL=1 it runs beside it on its own stream and K2 adds straight into the bus
 		// buffers (1 replica; more replicas are folded by the K3 launch, which then has to wait for K2).  Measured on
@@ -449,7 +450,7 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 		ctx->par_voice = false;
 		e = getenv("GAS_K2_DEBUG"); // the timeline buffer must exist before anything is captured into a graph
 		if (e && (atoi(e) & 8)) {
-			cudaMalloc((void **)&ctx->d_timeline, 256 * 16 * sizeof(unsigned long long));
+			cudaMalloc((void **)&ctx->d_timeline, 256 * 32 * sizeof(unsigned long long));
 		}
 		e = getenv("GAS_SKIP"); // experiments only: 1 = no prologue, 2 = no streaming kernel, 4 = no voice-parallel kernel
 		ctx->skip = e ? atoi(e) : 0;
@@ -472,6 +473,7 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->t.inst_cur, I);
 	ALLOC(ctx->t.inst_prev, 2 * I);
 	ALLOC(ctx->t.inst_mode, I);
+	ALLOC(ctx->t.inst_seq, I);
 	ALLOC(ctx->t.blk, (size_t)BLK_WORDS);
 	ctx->t.max_instances = (int32_t)I;
 	ALLOC(ctx->t.inst_fx, I);
@@ -504,6 +506,7 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->d_rep, (size_t)16 * GAS_MAX_BUSES * GAS_MAX_CHANNELS_PER_BUS * F);
 	ALLOC(ctx->d_emitters, I);
 	ALLOC(ctx->d_listeners, (size_t)GAS_MAX_LISTENERS);
+	ALLOC(ctx->d_listener_pre, (size_t)GAS_MAX_LISTENERS);
 	ALLOC(ctx->d_areas, (size_t)ctx->max_areas);
 	ALLOC(ctx->d_params_out, I);
 	ALLOC(ctx->d_ids, nscratch_ids);
@@ -577,7 +580,7 @@ void gas_destroy(gas_ctx *ctx) {
 		ctx->plan.overflow, ctx->plan.list, ctx->plan.k2_rows, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
 		ctx->d_peaks, ctx->d_rep, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
 		ctx->d_exchange, ctx->d_comm_seq, ctx->d_comm_ticket, ctx->t.vs_look, ctx->t.vs_life, ctx->t.inst_threshold, ctx->d_stage, ctx->d_voices_stage,
-		ctx->d_mixed, ctx->d_status, ctx->d_ids_mix, ctx->d_scratch_mix, ctx->plan.hdr };
+		ctx->d_mixed, ctx->d_status, ctx->d_ids_mix, ctx->d_scratch_mix, ctx->plan.hdr, ctx->d_listener_pre, ctx->t.inst_seq };
 	for (void *p : ptrs) {
 		if (p) {
 			cudaFree(p);
@@ -767,6 +770,7 @@ static int gain_common(gas_ctx *ctx, int32_t n, const gas_emitter *d_em, int32_t
 		}
 		if (n_listeners > 0) {
 			GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_listeners, listeners, n_listeners * sizeof(gas_listener), cudaMemcpyHostToDevice, ctx->s_gain));
+			GAS_CUDA(ctx, launch_listener_pre(ctx, n_listeners, ctx->s_gain));
 		}
 		ctx->n_listeners_res = n_listeners;
 	} else {
@@ -801,6 +805,7 @@ int gas_listeners_set(gas_ctx *ctx, int32_t n_listeners, const gas_listener *lis
 	}
 	if (n_listeners > 0) {
 		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_listeners, listeners, n_listeners * sizeof(gas_listener), cudaMemcpyHostToDevice, ctx->s_gain));
+		GAS_CUDA(ctx, launch_listener_pre(ctx, n_listeners, ctx->s_gain));
 	}
 	ctx->n_listeners_res = n_listeners;
 	return gain_side_end(ctx);
@@ -1496,6 +1501,12 @@ static int reduce_half(gas_ctx *ctx, gas_frame *d_bus, int32_t frames, bool begi
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_comm_done, 0));
 		ctx->comm_pending = false;
 	}
+	{
+		int st = join_voice_stream(ctx); // voice-parallel kernels of pipelined steps may still be adding to the buffer
+		if (st) {
+			return st;
+		}
+	}
 	if (begin && !end && ctx->reduce_open) {
 		return gas_fail(ctx, GAS_ERR_STATE, "%s: the previous block's gas_reduce_bus_end_device has not been called", who);
 	}
@@ -1531,7 +1542,14 @@ int gas_reduce_bus_exchange_device(gas_ctx *ctx, const gas_frame *d_partial, gas
 	if (ctx->comm_ranks <= 1) {
 		return gas_fail(ctx, GAS_ERR_STATE, "gas_reduce_bus_exchange_device: needs an opened exchange of at least 2 ranks");
 	}
-	if (ctx->mix_pending) { // the partial sums must be complete (also when they were mixed earlier in the same capture)
+	bool waited = false;
+	for (int i = 0; i < GAS_PLAN_DEPTH; i++) { // a block of a pipelined run: complete when its step kernel and its voice-parallel kernel are
+		if (ctx->block_inflight[i] && ctx->inflight_bus[i] == d_partial) {
+			GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comm, ctx->ev_block_done[i], 0));
+			waited = true;
+		}
+	}
+	if (!waited && ctx->mix_pending) { // the partial sums must be complete (also when they were mixed earlier in the same capture)
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comm, ctx->ev_mix_done, 0));
 	}
 	GAS_CUDA(ctx, launch_comm_exchange(ctx, d_partial, d_prev_sum, frames, ctx->s_comm));

@@ -21,7 +21,8 @@ using namespace gasgain;
 // NL lanes per emitter (8, 4, 2 or 1), see gain_emitter.
 template <int NL, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_gain(DevTables t, GlobalCfg g, int n, const gas_emitter *__restrict__ emitters,
-		int n_listeners, const gas_listener *__restrict__ listeners, const gas_area *__restrict__ areas, int n_areas, gas_params *__restrict__ out) {
+		int n_listeners, const gas_listener *__restrict__ listeners, const ListenerPre *__restrict__ pre, const gas_area *__restrict__ areas, int n_areas,
+		gas_params *__restrict__ out) {
 	const int i = (blockIdx.x * blockDim.x + threadIdx.x) / NL;
 	const int l = threadIdx.x & (NL - 1);
 	const int gbase = threadIdx.x & (32 - NL); // first lane of this emitter's group inside the warp
@@ -29,7 +30,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gain(DevTables t, GlobalCfg g
 	if (i >= n) {
 		return;
 	}
-	gain_emitter<NL>(t, g, i, l, gbase, gm, emitters, n_listeners, listeners, areas, n_areas, out);
+	gain_emitter<NL>(t, g, i, l, gbase, gm, emitters, n_listeners, listeners, pre, areas, n_areas, out);
+}
+
+__global__ void k_listener_pre(int n, const gas_listener *__restrict__ listeners, ListenerPre *__restrict__ pre) {
+	const int i = threadIdx.x;
+	if (i < n) {
+		listener_precompute(listeners[i], pre[i]);
+	}
 }
 
 __global__ void __launch_bounds__(128) k_params_set(DevTables t, GlobalCfg g, int n, const int32_t *__restrict__ ids, const gas_params *__restrict__ params) {
@@ -86,7 +94,7 @@ cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_list
 		shape = e ? atoi(e) : 0;
 	}
 #define GAS_K1_LAUNCH(NL_, T_, M_)                                                                                          \
-	k_gain<NL_, T_, M_><<<(int)(((long long)n * NL_ + T_ - 1) / T_), T_, 0, st>>>(ctx->t, ctx->g, n, d_em, n_listeners, d_l, d_areas, ctx->n_areas_res, d_out)
+	k_gain<NL_, T_, M_><<<(int)(((long long)n * NL_ + T_ - 1) / T_), T_, 0, st>>>(ctx->t, ctx->g, n, d_em, n_listeners, d_l, ctx->d_listener_pre, d_areas, ctx->n_areas_res, d_out)
 	switch (shape) {
 		case 1: GAS_K1_LAUNCH(8, 256, 4); break;
 		case 2: GAS_K1_LAUNCH(8, 64, 8); break;
@@ -97,6 +105,15 @@ cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_list
 		default: GAS_K1_LAUNCH(4, 64, 8); break;
 	}
 #undef GAS_K1_LAUNCH
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_listener_pre(gas_ctx *ctx, int n_listeners, cudaStream_t st) {
+	if (n_listeners <= 0) {
+		return cudaSuccess;
+	}
+	k_listener_pre<<<1, GAS_MAX_LISTENERS, 0, st>>>(n_listeners, ctx->d_listeners, ctx->d_listener_pre);
 	ctx->launches++;
 	return cudaGetLastError();
 }

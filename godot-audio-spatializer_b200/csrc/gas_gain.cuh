@@ -86,6 +86,20 @@ static __device__ __forceinline__ V3 xform(const Xf &t, V3 v) {
 	V3 r = bxform(t, v);
 	return V3{ r.x + t.o.x, r.y + t.o.y, r.z + t.o.z };
 }
+static __device__ __forceinline__ Xf load_xf12(const float *m) { // 9 basis floats (rows) + origin
+	Xf t;
+	t.m[0][0] = m[0]; t.m[0][1] = m[1]; t.m[0][2] = m[2];
+	t.m[1][0] = m[3]; t.m[1][1] = m[4]; t.m[1][2] = m[5];
+	t.m[2][0] = m[6]; t.m[2][1] = m[7]; t.m[2][2] = m[8];
+	t.o = V3{ m[9], m[10], m[11] };
+	return t;
+}
+static __device__ __forceinline__ void store_xf12(float *m, const Xf &t) {
+	m[0] = t.m[0][0]; m[1] = t.m[0][1]; m[2] = t.m[0][2];
+	m[3] = t.m[1][0]; m[4] = t.m[1][1]; m[5] = t.m[1][2];
+	m[6] = t.m[2][0]; m[7] = t.m[2][1]; m[8] = t.m[2][2];
+	m[9] = t.o.x; m[10] = t.o.y; m[11] = t.o.z;
+}
 static __device__ Xf load_xf(const gas_listener &l) {
 	Xf t;
 	for (int i = 0; i < 3; i++) {
@@ -136,7 +150,7 @@ static __device__ float attenuation_db(const gas_spatializer &s, float volume_db
 // reference audio_spatializer_3d.cpp:57-98 + :903-938.  Lane `l` of the emitter's NL-lane group (mask gm,
 // first lane gbase) owns speakers l, l + NL, ...; sums run in speaker order exactly like the reference loop.
 template <int NL>
-static __device__ void output_vol_surround(unsigned gm, int gbase, int l, const GlobalCfg &g, V3 src, float tightness, float out[4][2]) {
+static __device__ __forceinline__ void output_vol_surround(unsigned gm, int gbase, int l, const GlobalCfg &g, V3 src, float tightness, float out[4][2]) {
 	constexpr int S = 8 / NL; // speakers per lane
 	const int speaker_mode = g.speaker_mode;
 	const int count = speaker_mode == GAS_SPEAKER_SURROUND_31 ? 3 : (speaker_mode == GAS_SPEAKER_SURROUND_51 ? 5 : (speaker_mode == GAS_SPEAKER_SURROUND_71 ? 7 : 2));
@@ -192,7 +206,7 @@ static __device__ void output_vol_surround(unsigned gm, int gbase, int l, const 
 }
 
 // reference audio_spatializer_3d.cpp:103-110
-static __device__ void output_vol_stereo(V3 dir, float pan_strength, float out[4][2]) {
+static __device__ __noinline__ void output_vol_stereo(V3 dir, float pan_strength, float out[4][2]) {
 	double flatrad = sqrt((double)(dir.x * dir.x + dir.z * dir.z));
 	double g = (1.0 - (double)pan_strength) * (1.0 - (double)pan_strength);
 	g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
@@ -206,7 +220,7 @@ static __device__ void output_vol_stereo(V3 dir, float pan_strength, float out[4
 
 // reference audio_spatializer_3d.cpp:112-121
 template <int NL>
-static __device__ void output_vol(unsigned gm, int gbase, int l, const GlobalCfg &g, const gas_spatializer &s, V3 dir, float out[4][2]) {
+static __device__ __forceinline__ void output_vol(unsigned gm, int gbase, int l, const GlobalCfg &g, const gas_spatializer &s, V3 dir, float out[4][2]) {
 	if (g.speaker_mode == GAS_SPEAKER_MODE_STEREO) {
 		output_vol_stereo(dir, g.global_panning * s.panning_strength, out);
 	} else {
@@ -219,41 +233,78 @@ static __device__ void output_vol(unsigned gm, int gbase, int l, const GlobalCfg
 static __device__ __forceinline__ float lerpf(float a, float b, float w) { return a + (b - a) * w; }
 
 // reference audio_spatializer_3d.cpp:154-197
+// reference audio_spatializer_3d.cpp:154-191: the uniformity > 0 branch (rare: out of line)
+struct Vol8 {
+	float v[4][2];
+};
 template <int NL>
-static __device__ void reverb_vol(unsigned gm, int gbase, int l, const GlobalCfg &g, const gas_spatializer &s, const gas_emitter &e, const gas_area &a,
-		V3 listener_area_pos, const float direct[4][2], float rev[4][2]) {
+static __device__ __noinline__ Vol8 reverb_vol_uniform(unsigned gm, int gbase, int l, const GlobalCfg &g, int attenuation_model, float unit_size,
+		float panning_strength, float volume_db, float max_db, float uniformity, float area_send, V3 listener_area_pos, const Vol8 dir8) {
+	gas_spatializer s; // the three fields attenuation_db / output_vol read
+	s.attenuation_model = attenuation_model;
+	s.unit_size = unit_size;
+	s.panning_strength = panning_strength;
+	const int chan = g.channels;
+	float rev[4][2];
+	float direct[4][2];
+	for (int i = 0; i < 4; i++) {
+		rev[i][0] = rev[i][1] = 0.f;
+		direct[i][0] = dir8.v[i][0];
+		direct[i][1] = dir8.v[i][1];
+	}
+	float distance = len3(listener_area_pos);
+	float attenuation = db_to_linear_f(attenuation_db(s, volume_db, max_db, distance));
+	const float center_val[4] = { 0.5f, 0.25f, 0.16666f, 0.125f };
+	float cv = center_val[chan - 1];
+	if (attenuation < 1.0f) {
+		V3 rp = listener_area_pos;
+		rp.y = 0.f;
+		rp = norm3(rp);
+		output_vol<NL>(gm, gbase, l, g, s, rp, rev);
+		for (int i = 0; i < chan; i++) {
+			rev[i][0] = lerpf(rev[i][0], cv, attenuation);
+			rev[i][1] = lerpf(rev[i][1], cv, attenuation);
+		}
+	} else {
+		for (int i = 0; i < chan; i++) {
+			rev[i][0] = rev[i][1] = cv;
+		}
+	}
+	for (int i = 0; i < chan; i++) {
+		rev[i][0] = lerpf(direct[i][0], rev[i][0] * attenuation, uniformity);
+		rev[i][1] = lerpf(direct[i][1], rev[i][1] * attenuation, uniformity);
+		rev[i][0] *= area_send;
+		rev[i][1] *= area_send;
+	}
+	Vol8 out;
+	for (int i = 0; i < 4; i++) {
+		out.v[i][0] = rev[i][0];
+		out.v[i][1] = rev[i][1];
+	}
+	return out;
+}
+
+// reference audio_spatializer_3d.cpp:154-197
+template <int NL>
+static __device__ __forceinline__ void reverb_vol(unsigned gm, int gbase, int l, const GlobalCfg &g, const gas_spatializer &s, const gas_emitter &e,
+		const gas_area &a, V3 listener_area_pos, const float direct[4][2], float rev[4][2]) {
 	for (int i = 0; i < 4; i++) {
 		rev[i][0] = rev[i][1] = 0.f;
 	}
-	float uniformity = a.reverb_uniformity;
-	float area_send = a.reverb_amount;
-	int chan = g.channels;
-	if (uniformity > 0.0f) {
-		float distance = len3(listener_area_pos);
-		float attenuation = db_to_linear_f(attenuation_db(s, e.volume_db, e.max_db, distance));
-		const float center_val[4] = { 0.5f, 0.25f, 0.16666f, 0.125f };
-		float cv = center_val[chan - 1];
-		if (attenuation < 1.0f) {
-			V3 rp = listener_area_pos;
-			rp.y = 0.f;
-			rp = norm3(rp);
-			output_vol<NL>(gm, gbase, l, g, s, rp, rev);
-			for (int i = 0; i < chan; i++) {
-				rev[i][0] = lerpf(rev[i][0], cv, attenuation);
-				rev[i][1] = lerpf(rev[i][1], cv, attenuation);
-			}
-		} else {
-			for (int i = 0; i < chan; i++) {
-				rev[i][0] = rev[i][1] = cv;
-			}
+	if (a.reverb_uniformity > 0.0f) {
+		Vol8 d8;
+		for (int i = 0; i < 4; i++) {
+			d8.v[i][0] = direct[i][0];
+			d8.v[i][1] = direct[i][1];
 		}
-		for (int i = 0; i < chan; i++) {
-			rev[i][0] = lerpf(direct[i][0], rev[i][0] * attenuation, uniformity);
-			rev[i][1] = lerpf(direct[i][1], rev[i][1] * attenuation, uniformity);
-			rev[i][0] *= area_send;
-			rev[i][1] *= area_send;
+		const Vol8 r8 = reverb_vol_uniform<NL>(gm, gbase, l, g, s.attenuation_model, s.unit_size, s.panning_strength, e.volume_db, e.max_db,
+				a.reverb_uniformity, a.reverb_amount, listener_area_pos, d8);
+		for (int i = 0; i < 4; i++) {
+			rev[i][0] = r8.v[i][0];
+			rev[i][1] = r8.v[i][1];
 		}
 	} else {
+		const float area_send = a.reverb_amount;
 		for (int i = 0; i < 4; i++) {
 			rev[i][0] = direct[i][0] * area_send;
 			rev[i][1] = direct[i][1] * area_send;
@@ -299,7 +350,16 @@ static __device__ __forceinline__ bool inst_mix_channels(const DevTables &t, int
 }
 
 // set_spatializer_parameters + bus-map push (audio_spatializer.cpp:258-272)
-static __device__ void commit_params(const DevTables &t, int q, const gas_params &p) {
+static __device__ void commit_params(const DevTables &t, int q, const gas_params &p_in) {
+	// bus slots beyond n_bus carry nothing (the reference's arrays have exactly n_bus entries): stored as zeros, which is what
+	// gain_emitter relies on when it leaves slots it does not use untouched
+	gas_params p = p_in;
+	for (int b = p.n_bus < 0 ? 0 : p.n_bus; b < GAS_MAX_BUSES_PER_PLAYBACK; b++) {
+		p.bus[b] = 0;
+		for (int c = 0; c < GAS_MAX_CHANNELS_PER_BUS; c++) {
+			p.bus_volumes[b][c][0] = p.bus_volumes[b][c][1] = 0.f;
+		}
+	}
 	t.inst_params[q] = p;
 	if (p.update_parameters && t.inst_active[q]) {
 		push_bus_map(p, inst_mix_channels(t, q), t.inst_cur[q]);
@@ -319,15 +379,69 @@ static __device__ __forceinline__ float pick(const float v[4][2], int c, int x) 
 	return r;
 }
 
+// Per-listener part of calculate_spatialization (audio_spatializer_3d.cpp:335-342, :350-352, :408-409): the transforms
+// every emitter would derive from the listener again.
+static __device__ void listener_precompute(const gas_listener &L, ListenerPre &p) {
+	const Xf lt = load_xf(L);
+	Xf inv = lt;
+	orthonormalize(inv);
+	Xf on = inv;
+	affine_invert(inv);
+	Xf inv2 = lt;
+	affine_invert(inv2);
+	store_xf12(p.inv, inv);
+	store_xf12(p.inv2, inv2);
+	store_xf12(p.on, on);
+}
+
+// :378-385 (rare: out of line)
+static __device__ __noinline__ float emission_angle_db(float emission_angle, float emission_angle_filter_attenuation_db, V3 basis_z, V3 global_pos,
+		V3 listener_origin, float db_att) {
+	V3 listenertopos = sub3(global_pos, listener_origin);
+	float c = dot3(norm3(listenertopos), norm3(basis_z));
+	float ac = c < -1.0f ? (float)3.14159265358979323846 : (c > 1.0f ? 0.0f : (float)acos_d((double)c));
+	float angle = ac * (float)(180.0 / 3.14159265358979323846);
+	if (angle > emission_angle) {
+		db_att -= -emission_angle_filter_attenuation_db;
+	}
+	return db_att;
+}
+
+// :405-427 (rare: out of line)
+struct Pitch2 {
+	float scale, weight;
+};
+static __device__ __noinline__ Pitch2 doppler_listener(float pitch_scale, float speed_of_sound, V3 listener_velocity, const ListenerPre *pre, V3 linear_velocity,
+		V3 local_pos, float weight, Pitch2 acc) {
+	const Xf on = load_xf12(pre->on);
+	V3 local_velocity = bxform_inv(on, sub3(linear_velocity, listener_velocity));
+	if (!(local_velocity.x == 0.f && local_velocity.y == 0.f && local_velocity.z == 0.f)) {
+		float approaching = dot3(norm3(local_pos), norm3(local_velocity));
+		float velocity = len3(local_velocity);
+		float dps = pitch_scale * speed_of_sound / (speed_of_sound + velocity * approaching);
+		dps = (double)dps < 0.125 ? 0.125f : ((double)dps > 8.0 ? 8.0f : dps);
+		acc.scale += weight * (float)log2_d((double)dps);
+		acc.weight += weight;
+	}
+	return acc;
+}
+
 // NL lanes per emitter (8, 4 or 2).  The scalar chain is evaluated redundantly by the NL lanes; the SPCAP speaker gains
 // and the stores are dealt across them (lane l owns elements l, l + NL, ... of the [pair][side] tables).  Fewer lanes
 // = fewer, longer threads: slower on an empty GPU (the chain is latency-bound), but a smaller footprint beside the
 // mix kernels, which is what a step pays for (see launch_gain for the measured shapes).
 template <int NL>
 static __device__ __forceinline__ void gain_emitter(const DevTables &t, const GlobalCfg &g, int i, int l, int gbase, unsigned gm,
-		const gas_emitter *__restrict__ emitters, int n_listeners, const gas_listener *__restrict__ listeners, const gas_area *__restrict__ areas,
-		int n_areas, gas_params *__restrict__ out) {
+		const gas_emitter *__restrict__ emitters, int n_listeners, const gas_listener *__restrict__ listeners, const ListenerPre *__restrict__ pre,
+		const gas_area *__restrict__ areas, int n_areas, gas_params *__restrict__ out, int32_t *__restrict__ inst_seq = nullptr, int seq_val = 0,
+		unsigned long long *dbg = nullptr) {
 	constexpr int S = 8 / NL;
+#define GAS_GAIN_STAMP(k_)                                            \
+	if (dbg) {                                                        \
+		unsigned long long t_;                                        \
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));        \
+		dbg[k_] = t_;                                                 \
+	}
 	gas_emitter e = emitters[i];
 	// Device-resident emitter records are not seen by the host: a record that points outside the tables is skipped (its
 	// instance keeps its parameters), an area index outside the resident areas counts as "no area" — like the prologue
@@ -354,6 +468,10 @@ static __device__ __forceinline__ void gain_emitter(const DevTables &t, const Gl
 	s.doppler_tracking = sp->doppler_tracking;
 	s.doppler_speed_of_sound = sp->doppler_speed_of_sound;
 	const int q = e.instance;
+	// bus slots the instance's records hold at the moment: slots this computation leaves unused are cleared only if they were in use
+	// (parameters handed in through gas_params_set may carry up to six; calculate_spatialization produces at most two)
+	const int old_n_bus = t.inst_params[q].n_bus;
+	const int old_n_cur = t.inst_cur[q].n;
 	const bool was_further = t.inst_was_further[q] != 0;
 	const int q_active = t.inst_active[q];
 	const bool mix_channels = inst_mix_channels(t, q);
@@ -368,6 +486,7 @@ static __device__ __forceinline__ void gain_emitter(const DevTables &t, const Gl
 	prm.attenuation_filter_cutoff_hz = 5000.0f;
 	prm.update_parameters = 0;
 
+	GAS_GAIN_STAMP(23) // emitter record here
 	const V3 global_pos{ e.origin[0], e.origin[1], e.origin[2] };
 	V3 linear_velocity{ 0.f, 0.f, 0.f };
 	const bool doppler = s.doppler_tracking != GAS_DOPPLER_TRACKING_DISABLED;
@@ -385,18 +504,17 @@ static __device__ __forceinline__ void gain_emitter(const DevTables &t, const Gl
 
 	for (int li = 0; li < n_listeners; li++) { // :323
 		const gas_listener L = listeners[li];
-		const Xf lt = load_xf(L);
-		Xf inv = lt;
-		orthonormalize(inv);
-		affine_invert(inv);
+		// the listener's transforms (orthonormalised inverse, plain affine inverse, orthonormalised basis) are the same for
+		// every emitter: computed once per listener upload by k_listener_pre with the very code the reference runs per emitter
+		const Xf inv = load_xf12(pre[li].inv);
 		const V3 local_pos = xform(inv, global_pos); // :342
 		const float dist = len3(local_pos);          // :344
 		V3 listener_area_pos{ 0.f, 0.f, 0.f };
 		if (area_reverb_uniform) { // :350-353 (plain affine inverse, not orthonormalised)
-			Xf inv2 = lt;
-			affine_invert(inv2);
+			const Xf inv2 = load_xf12(pre[li].inv2);
 			listener_area_pos = xform(inv2, V3{ ap->closest_point[li][0], ap->closest_point[li][1], ap->closest_point[li][2] });
 		}
+		GAS_GAIN_STAMP(24) // tables + listener here
 		float multiplier = db_to_linear_f(attenuation_db(s, e.volume_db, e.max_db, dist)); // :359
 		if (s.max_distance > 0.f) { // :361-373
 			float total_max = s.max_distance;
@@ -416,17 +534,13 @@ static __device__ __forceinline__ void gain_emitter(const DevTables &t, const Gl
 		double mm = 1.0 < (double)multiplier ? 1.0 : (double)multiplier;
 		float db_att = (float)((1.0 - mm) * (double)s.attenuation_filter_db); // :376
 		if (s.emission_angle_enabled) { // :378-385
-			V3 listenertopos = sub3(global_pos, V3{ L.origin[0], L.origin[1], L.origin[2] });
-			float c = dot3(norm3(listenertopos), norm3(V3{ e.basis_z[0], e.basis_z[1], e.basis_z[2] }));
-			float ac = c < -1.0f ? (float)3.14159265358979323846 : (c > 1.0f ? 0.0f : (float)acos_d((double)c));
-			float angle = ac * (float)(180.0 / 3.14159265358979323846);
-			if (angle > s.emission_angle) {
-				db_att -= -s.emission_angle_filter_attenuation_db;
-			}
+			db_att = emission_angle_db(s.emission_angle, s.emission_angle_filter_attenuation_db, V3{ e.basis_z[0], e.basis_z[1], e.basis_z[2] }, global_pos,
+					V3{ L.origin[0], L.origin[1], L.origin[2] }, db_att);
 		}
 		prm.linear_attenuation = db_to_linear_f(db_att); // :387, last listener wins (Q6)
 		prm.attenuation_filter_cutoff_hz = s.attenuation_filter_cutoff_hz;
 
+		GAS_GAIN_STAMP(25) // attenuation + filter gain done
 		for (int c = 0; c < 4; c++) {
 			tmp_volume[c][0] = tmp_volume[c][1] = 0.f;
 		}
@@ -445,24 +559,18 @@ static __device__ __forceinline__ void gain_emitter(const DevTables &t, const Gl
 			}
 		}
 		if (doppler) { // :405-427
-			Xf on = lt;
-			orthonormalize(on);
-			V3 local_velocity = bxform_inv(on, sub3(linear_velocity, V3{ L.velocity[0], L.velocity[1], L.velocity[2] }));
-			if (!(local_velocity.x == 0.f && local_velocity.y == 0.f && local_velocity.z == 0.f)) {
-				float approaching = dot3(norm3(local_pos), norm3(local_velocity));
-				float velocity = len3(local_velocity);
-				float dps = e.pitch_scale * s.doppler_speed_of_sound / (s.doppler_speed_of_sound + velocity * approaching);
-				dps = (double)dps < 0.125 ? 0.125f : ((double)dps > 8.0 ? 8.0f : dps);
-				float weight = 0.f;
-				for (int c = 0; c < 4; c++) {
-					weight = weight > tmp_volume[c][0] ? weight : tmp_volume[c][0];
-					weight = weight > tmp_volume[c][1] ? weight : tmp_volume[c][1];
-				}
-				log_pitch_scale += weight * (float)log2_d((double)dps);
-				log_pitch_weight += weight;
+			float weight = 0.f;
+			for (int c = 0; c < 4; c++) {
+				weight = weight > tmp_volume[c][0] ? weight : tmp_volume[c][0];
+				weight = weight > tmp_volume[c][1] ? weight : tmp_volume[c][1];
 			}
+			const Pitch2 pa = doppler_listener(e.pitch_scale, s.doppler_speed_of_sound, V3{ L.velocity[0], L.velocity[1], L.velocity[2] }, &pre[li],
+					linear_velocity, local_pos, weight, Pitch2{ log_pitch_scale, log_pitch_weight });
+			log_pitch_scale = pa.scale;
+			log_pitch_weight = pa.weight;
 		}
 	}
+	GAS_GAIN_STAMP(26) // listeners done
 	if (log_pitch_weight > 0.f) { // :430-434
 		prm.pitch_scale = (float)pow_d(2.0, (double)(log_pitch_scale / log_pitch_weight));
 	} else {
@@ -516,7 +624,9 @@ static __device__ __forceinline__ void gain_emitter(const DevTables &t, const Gl
 			P->mix_volumes[el >> 1][el & 1] = mv[k];
 #pragma unroll
 			for (int b = 0; b < GAS_MAX_BUSES_PER_PLAYBACK; b++) {
-				P->bus_volumes[b][el >> 1][el & 1] = b == 0 ? bv0[k] : (b == 1 ? bv1[k] : 0.f);
+				if (b < 2 || pass == 1 || b < old_n_bus) {
+					P->bus_volumes[b][el >> 1][el & 1] = b == 0 ? bv0[k] : (b == 1 ? bv1[k] : 0.f);
+				}
 			}
 		}
 		if (l == 0) {
@@ -527,7 +637,9 @@ static __device__ __forceinline__ void gain_emitter(const DevTables &t, const Gl
 			P->n_bus = n_bus;
 #pragma unroll
 			for (int b = 0; b < GAS_MAX_BUSES_PER_PLAYBACK; b++) {
-				P->bus[b] = b == 0 ? bus0 : (b == 1 ? bus1 : 0);
+				if (b < 2 || pass == 1 || b < old_n_bus) {
+					P->bus[b] = b == 0 ? bus0 : (b == 1 ? bus1 : 0);
+				}
 			}
 		}
 	}
@@ -546,15 +658,27 @@ static __device__ __forceinline__ void gain_emitter(const DevTables &t, const Gl
 					const float bv = b == 0 ? bv0[k] : bv1[k];
 					w = mix_channels ? (mv[k] > 0.0f ? bv / mv[k] : 0.f) : mv[k];
 				}
-				d->vol[b][el >> 1][el & 1] = w;
+				if (b < 2 || b < old_n_cur) {
+					d->vol[b][el >> 1][el & 1] = w;
+				}
 			}
 		}
 		if (l == 0) {
 			d->n = n_bus;
 #pragma unroll
 			for (int b = 0; b < GAS_MAX_BUSES_PER_PLAYBACK; b++) {
-				d->bus[b] = b == 0 ? (n_bus > 0 ? bus0 : 0) : (b == 1 && n_bus > 1 ? bus1 : 0);
+				if (b < 2 || b < old_n_cur) {
+					d->bus[b] = b == 0 ? (n_bus > 0 ? bus0 : 0) : (b == 1 && n_bus > 1 ? bus1 : 0);
+				}
 			}
+		}
+	}
+	GAS_GAIN_STAMP(27) // stores issued
+	if (inst_seq) {
+		// in-kernel gains (step kernel): tell the planner of this block that the instance's parameters are in place
+		__syncwarp(gm);
+		if (l == 0) {
+			asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(inst_seq + q), "r"(seq_val) : "memory");
 		}
 	}
 }

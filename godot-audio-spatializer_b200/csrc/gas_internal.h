@@ -120,7 +120,7 @@ enum : int32_t {
 	BLK_S_TICKET = 24,
 	BLK_Q = 32,      // voice-parallel launches so far = index of the next block it mixes
 	BLK_Q_TICKET = 40,
-	BLK_BAR_CNT = 48, // grid barrier of the control warps (count, generation)
+	BLK_GAIN_DONE = 48, // control warps of the current step launch that have finished their gain tasks
 	BLK_BAR_GEN = 56,
 	BLK_WORDS = 64
 };
@@ -167,6 +167,8 @@ struct DevTables {
 	BusDetails *inst_cur;
 	BusDetails *inst_prev;   // [2][max_instances]: double-buffered by block parity (read [p], write [1-p])
 	int32_t *inst_mode;      // MODE_A/B/E | (effect_gain_binding + 1) << 8, latched at instantiate()
+	int32_t *inst_seq;       // [max_instances] block index + 1 of the last in-kernel gain computation (release store): lets the planner of
+	                         // that block start on a voice as soon as ITS instance's parameters are in place
 	int32_t *blk;            // [BLK_WORDS] device-side block counters and tickets (BLK_*)
 	int32_t max_instances;
 	gas_effect_chain *inst_fx;
@@ -179,6 +181,13 @@ struct DevTables {
 	float *inst_threshold;       // [max_instances] db_to_linear(playback_disable_threshold_db)
 	float threshold_default;     // db_to_linear(-80 dB), evaluated on the host like the reference does (audio_spatializer.cpp:465)
 	int32_t max_voices;
+};
+
+// what calculate_spatialization derives from a listener alone (computed once per listener upload)
+struct ListenerPre {
+	float inv[12];  // orthonormalised, then affine-inverted transform (basis rows + origin)
+	float inv2[12]; // plain affine inverse (reverb-area position)
+	float on[12];   // orthonormalised transform (doppler)
 };
 
 struct GlobalCfg {
@@ -242,6 +251,7 @@ struct gas_ctx {
 	int replicas = 8;           // GAS_K2_REPLICAS (1 = K2 adds straight into the bus buffers)
 	gas_emitter *d_emitters = nullptr;
 	gas_listener *d_listeners = nullptr;
+	ListenerPre *d_listener_pre = nullptr; // [GAS_MAX_LISTENERS] refreshed on the gain stream behind every listener upload
 	gas_area *d_areas = nullptr;
 	int32_t max_areas = 0;
 	gas_params *d_params_out = nullptr;
@@ -346,6 +356,7 @@ static inline cudaError_t gas_launch(void (*kernel)(KArgs...), dim3 grid, dim3 b
 // gas_gain.cu
 cudaError_t launch_gain(gas_ctx *ctx, int n, const gas_emitter *d_em, int n_listeners, const gas_listener *d_l,
 		const gas_area *d_areas, gas_params *d_out, cudaStream_t st);
+cudaError_t launch_listener_pre(gas_ctx *ctx, int n_listeners, cudaStream_t st);
 cudaError_t launch_params_set(gas_ctx *ctx, int n, const int32_t *d_ids, const gas_params *d_params, cudaStream_t st);
 cudaError_t launch_instance_start(gas_ctx *ctx, int n, const int32_t *d_ids, cudaStream_t st);
 // gas_prologue.cu

@@ -91,6 +91,7 @@ struct StepArgs {
 	const gas_emitter *emitters;
 	int n_listeners;
 	const gas_listener *listeners;
+	const ListenerPre *listener_pre;
 	const gas_area *areas;
 	int n_areas;
 };
@@ -129,6 +130,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
 			"l"(src), "r"(bytes), "r"(smem_u32(bar))
+			: "memory");
+}
+// ... with an L2 eviction policy: source rows are read exactly once, so they are marked evict-first and leave the small
+// tables the control warps walk (parameters, bus details, ramp state: ~15 MB) resident in L2 from step to step
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+			"l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
 			: "memory");
 }
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
@@ -533,26 +546,6 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 	}
 }
 
-// grid-wide barrier of the control groups (all CTAs of the launch are resident: one per SM)
-__device__ __forceinline__ void control_grid_barrier(int32_t *blk, int n_cta, int ctl_tid) {
-	__threadfence();
-	asm volatile("bar.sync 3, %0;" ::"n"(kControlThreads) : "memory");
-	if (ctl_tid == 0) {
-		const int gen = gasplan::ld_volatile(&blk[BLK_BAR_GEN]);
-		if (atomicAdd(&blk[BLK_BAR_CNT], 1) == n_cta - 1) {
-			blk[BLK_BAR_CNT] = 0;
-			__threadfence();
-			atomicAdd(&blk[BLK_BAR_GEN], 1);
-		} else {
-			while (gasplan::ld_volatile(&blk[BLK_BAR_GEN]) == gen) {
-				__nanosleep(64);
-			}
-		}
-		__threadfence();
-	}
-	asm volatile("bar.sync 3, %0;" ::"n"(kControlThreads) : "memory");
-}
-
 __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ StepArgs A) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
@@ -576,32 +569,45 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 			return;
 		}
 		const int ctl_tid = tid - kStreamThreads;
+		gasplan::PlanGroup G;
+		G.tl = (cf.debug & 8) && ctl_tid == 0 ? cf.timeline + blockIdx.x * 32 : nullptr;
+		gasplan::group_stamp(G, 16);
 		// the previous launch is complete after this (its streaming warps read the plan slot and the bus buffers that
 		// are rewritten here; its control warps wrote the tables that are read here)
 		GAS_GRID_DEP_WAIT();
+		int wait_total = 0;
 		if (A.n_emitters > 0) {
+			// Gains of the next block, two lanes per emitter.  No grid-wide barrier separates them from the plan: every instance
+			// carries a flag (block index + 1, release) that the planner of a voice waits for, and every control warp reports
+			// when its gain tasks are done, which releases the voices of instances that got no emitter this block.
+			const int b_next = gasplan::ld_volatile(&blk[BLK_P]);
 			const int pairs = kControlThreads / 2;
 			const int gbase = lane & 30;
 			const unsigned gm = 3u << gbase;
 			for (int e = blockIdx.x * pairs + (ctl_tid >> 1); e < A.n_emitters; e += gridDim.x * pairs) {
-				gasgain::gain_emitter<2>(A.p.t, g, e, ctl_tid & 1, gbase, gm, A.emitters, A.n_listeners, A.listeners, A.areas, A.n_areas, nullptr);
+				gasgain::gain_emitter<2>(A.p.t, g, e, ctl_tid & 1, gbase, gm, A.emitters, A.n_listeners, A.listeners, A.listener_pre, A.areas, A.n_areas,
+						nullptr, A.p.t.inst_seq, b_next + 1, G.tl);
 			}
-			// every instance's parameters are in place before any voice reads them
-			control_grid_barrier(blk, gridDim.x, ctl_tid);
+			__syncwarp();
+			if (lane == 0) {
+				asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(&blk[BLK_GAIN_DONE]) : "memory");
+			}
+			wait_total = (int)gridDim.x * kControlWarps;
+			gasplan::group_stamp(G, 17);
 		}
-		gasplan::PlanGroup G;
+		gasplan::group_stamp(G, 18);
 		G.tid = ctl_tid;
 		G.nthreads = kControlThreads;
 		G.cta = blockIdx.x;
 		G.n_cta = gridDim.x;
 		G.bar_id = 3;
-		gasplan::plan_block(G, s_plan, A.p);
+		gasplan::plan_block(G, s_plan, A.p, wait_total);
 		return;
 	}
 
 	// timeline (debug & 8): the first lane of the producer warp stamps the start-up, thread 0 the consumer side
-	unsigned long long *tlp = (cf.debug & 8) && tid == kConsumerThreads ? cf.timeline + blockIdx.x * 16 : nullptr;
-	unsigned long long *tl = (cf.debug & 8) && tid == 0 ? cf.timeline + blockIdx.x * 16 : nullptr;
+	unsigned long long *tlp = (cf.debug & 8) && tid == kConsumerThreads ? cf.timeline + blockIdx.x * 32 : nullptr;
+	unsigned long long *tl = (cf.debug & 8) && tid == 0 ? cf.timeline + blockIdx.x * 32 : nullptr;
 
 	// Start-up runs on the producer warp alone, with nothing but its own dependent loads in the way of the first
 	// copy: block index -> plan header (class table) -> partition -> first source-row indices -> copies.  The consumer
@@ -639,13 +645,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 		while (gasplan::ld_acquire(&hdr->seq) != k + 1) {
 			__nanosleep(100);
 		}
-		const int n_cls = __ldcg(&hdr->n_cls);
+		// Compact table of the streaming classes of this block, in slot order (identical in every CTA): one round of loads
+		// of the slot table and of this block's counts.
+		int n_cls = 0;
 		{
-			const int4 *srcw = reinterpret_cast<const int4 *>(hdr->cls);
-			int4 *dstw = reinterpret_cast<int4 *>(s_cls);
-			const int words = n_cls * (int)(sizeof(ClassInfo) / 16);
-			for (int i = lane; i < words; i += 32) {
-				dstw[i] = __ldcg(srcw + i);
+			constexpr int R = GAS_MAX_CLASSES / 32;
+			unsigned long long key[R], auxw[R];
+			int cnt[R];
+			const int32_t *counts = plan.cls_count + slot_p * GAS_MAX_CLASSES;
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				key[r] = __ldcg(plan.cls_key + r * 32 + lane);
+				auxw[r] = __ldcg(plan.cls_aux + r * 32 + lane);
+				cnt[r] = __ldcg(counts + r * 32 + lane);
+			}
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				const bool on = key[r] != 0ULL && (int)(key[r] & 3u) == PATH_STREAM && cnt[r] > 0;
+				const unsigned m = __ballot_sync(0xffffffffu, on);
+				if (on) {
+					ClassInfo ci = cls_decode(key[r], cnt[r]);
+					ci.slot = r * 32 + lane;
+					if (ci.flags & CLS_SCALED) {
+						ci.scale[0] = __uint_as_float((unsigned)(auxw[r] & 0xffffffffu));
+						ci.scale[1] = __uint_as_float((unsigned)(auxw[r] >> 32));
+					}
+					s_cls[n_cls + __popc(m & ((1u << lane) - 1u))] = ci;
+				}
+				n_cls += __popc(m);
 			}
 		}
 		__syncwarp();
@@ -675,6 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 		// ===== producer =====
 		int stage = 0;
 		uint32_t phase = 0;
+		const uint64_t pol_stream = l2_policy_evict_first();
 		const int2 *list = plan.list + (size_t)slot_p * GAS_MAX_CLASSES * maxv;
 		const float *rows = plan_rows(plan, k, 0, maxv);
 		// Source-row indices are fetched one warp-wide load (32 list positions = 32/vb units) at a time,
@@ -712,8 +740,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 			{
 				const int v = lane - (seq - cur.first_seq) * cf.vb; // this lane's voice inside the stage
 				if (v >= 0 && v < nv && !no_copy) {
-					bulk_g2s(sx + (size_t)v * row_bytes, A.src + (size_t)cur.val.y * cf.src_stride + (size_t)it.tile * cf.tile_frames, row_bytes,
-							&s_full[stage]);
+					bulk_g2s_hint(sx + (size_t)v * row_bytes, A.src + (size_t)cur.val.y * cf.src_stride + (size_t)it.tile * cf.tile_frames, row_bytes,
+							&s_full[stage], pol_stream);
 				}
 			}
 			if (tlp && seq < 2) {
@@ -833,9 +861,9 @@ cudaError_t launch_step(gas_ctx *ctx, const gas_frame *d_src, int src_stride, in
 	}
 	if (A.cf.debug & 8) {
 		if (!ctx->d_timeline) {
-			cudaMalloc((void **)&ctx->d_timeline, 256 * 16 * sizeof(unsigned long long));
+			cudaMalloc((void **)&ctx->d_timeline, 256 * 32 * sizeof(unsigned long long));
 		}
-		cudaMemsetAsync(ctx->d_timeline, 0, 256 * 16 * sizeof(unsigned long long), st);
+		cudaMemsetAsync(ctx->d_timeline, 0, 256 * 32 * sizeof(unsigned long long), st);
 		A.cf.timeline = ctx->d_timeline;
 	}
 	A.p.t = ctx->t;
@@ -857,6 +885,7 @@ cudaError_t launch_step(gas_ctx *ctx, const gas_frame *d_src, int src_stride, in
 		A.emitters = next->d_emitters;
 		A.n_listeners = ctx->n_listeners_res;
 		A.listeners = ctx->d_listeners;
+		A.listener_pre = ctx->d_listener_pre;
 		A.areas = ctx->d_areas;
 		A.n_areas = ctx->n_areas_res;
 	}

@@ -45,7 +45,15 @@ struct PlanGroup {
 	int nthreads; // multiple of 32, <= 2 * kTab
 	int cta, n_cta;
 	int bar_id;   // named barrier of the group
+	unsigned long long *tl; // experiments: globaltimer stamps of the group's first thread (nullptr normally)
 };
+static __device__ __forceinline__ void group_stamp(const PlanGroup &G, int slot) {
+	if (G.tl) {
+		unsigned long long t;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+		G.tl[slot] = t;
+	}
+}
 static __device__ __forceinline__ void group_sync(const PlanGroup &G) { asm volatile("bar.sync %0, %1;" ::"r"(G.bar_id), "r"(G.nthreads) : "memory"); }
 
 struct PlanArgs {
@@ -142,8 +150,36 @@ static __device__ __noinline__ void resolve_sends_wide(const BusDetails *__restr
 	}
 }
 
+// Coefficient preparation is long double-precision code that only voices of the voice-parallel path need: out of line, so
+// that the common path (streamed voices) does not have to be fetched around it.
+static __device__ __noinline__ void write_filter_target(VoiceRec *rec, float cutoff, float lin_att, float mix_rate) {
+	float target[5];
+	prepare_coefficients(GAS_FILTER_HIGHSHELF, cutoff, 1.0f, lin_att, 1, mix_rate, target); // audio_spatializer_3d.cpp:504-510
+#pragma unroll
+	for (int i = 0; i < 5; i++) {
+		rec->target[i] = target[i];
+	}
+}
+static __device__ __noinline__ void write_effect_coefficients(VoiceRec *rec, const gas_effect_chain *fx, int n_fx, int fx_binding, float lin_att,
+		float mix_rate, int x) {
+	for (int ei = x; ei < n_fx; ei += 2) { // effects x, x + 2 on this lane
+		gas_effect ef = fx->effects[ei];
+		if (fx_binding == ei) {
+			ef.gain = lin_att; // example _process_effects (gd_spatializer_instance.gd:125-127)
+		}
+		const int stages = ef.stages < 1 ? 1 : (ef.stages > GAS_MAX_FILTER_STAGES ? GAS_MAX_FILTER_STAGES : ef.stages);
+		float coef[5];
+		prepare_coefficients(ef.mode, ef.cutoff_hz, ef.resonance, ef.gain, stages, mix_rate, coef);
+		rec->fx_stages[ei] = stages;
+#pragma unroll
+		for (int i = 0; i < 5; i++) {
+			rec->fx_coef[ei][i] = coef[i];
+		}
+	}
+}
+
 // One pass of the voice part: the group's threads take nthreads / 2 consecutive voices starting at j0.
-static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, PlanSmem &S, const PlanArgs &a, int b, int j0) {
+static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, PlanSmem &S, const PlanArgs &a, int b, int j0, int wait_total) {
 	const DevTables &t = a.t;
 	const GlobalCfg &g = a.g;
 	const BlockPlan &plan = a.plan;
@@ -180,6 +216,13 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 	const bool valid = v.voice >= 0 && v.voice < maxv && v.instance >= 0 && v.instance < g.max_instances;
 	const int q = valid ? v.instance : 0;
 	const int vslot = valid ? v.voice : 0;
+	if (wait_total > 0 && valid) {
+		// fine-grained dependency instead of a grid-wide barrier between the gain tasks and the plan: normally the flag is already
+		// set (the same lanes computed this instance's gains a moment ago)
+		while (ld_acquire(&t.inst_seq[q]) != b + 1 && ld_acquire(&t.blk[BLK_GAIN_DONE]) < wait_total) {
+			__nanosleep(40);
+		}
+	}
 	const int v_active = t.inst_active[q];
 	const int imode = t.inst_mode[q];
 	const gas_params *prm = &t.inst_params[q];
@@ -221,24 +264,14 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 		}
 	}
 	float m_prev[4] = { 1.f, 1.f, 1.f, 1.f }, m_new[4] = { 1.f, 1.f, 1.f, 1.f }; // this side's mix_channel ramp per pair
-	float target[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
-	int n_fx = 0;
-	int fx_stage[2] = { 1, 1 };
-	float fx_coef[2][5];
-#pragma unroll
-	for (int e = 0; e < 2; e++) {
-#pragma unroll
-		for (int i = 0; i < 5; i++) {
-			fx_coef[e][i] = 0.f;
-		}
-	}
+	int n_fx = 0, fx_binding = -1;
 	bool shared = false, scaled = false, wide = false;
 	float sc1 = 0.f, sc2 = 0.f;
 	unsigned long long aux = CLS_AUX_NONE; // second word of the class identity
 
 	if (live) {
 		mode = imode & 0xff;
-		const int fx_binding = (imode >> 8) - 1;
+		fx_binding = (imode >> 8) - 1;
 		wide = cur_n > 2 || prev_n > 2;
 		if (!wide) {
 			// sends: every bus of the current details with the previous volume looked up by bus (absent => 0 => fade-in), then
@@ -370,26 +403,10 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 		}
 		if (filt) {
 			cflags |= CLS_FILT;
-			if (x == 0) {
-				prepare_coefficients(GAS_FILTER_HIGHSHELF, cutoff, 1.0f, lin_att, 1, g.mix_rate, target); // :504-510
-			}
 		}
 		if (mode == MODE_E) {
-			const gas_effect_chain *fx = &t.inst_fx[q];
-			n_fx = fx->n_effects;
+			n_fx = t.inst_fx[q].n_effects;
 			n_fx = n_fx < 0 ? 0 : (n_fx > GAS_MAX_EFFECTS ? GAS_MAX_EFFECTS : n_fx);
-#pragma unroll
-			for (int e = 0; e < 2; e++) { // effects x, x + 2 on this lane
-				const int ei = x + e * 2;
-				if (ei < n_fx) {
-					gas_effect ef = fx->effects[ei];
-					if (fx_binding == ei) {
-						ef.gain = lin_att; // example _process_effects (gd_spatializer_instance.gd:125-127)
-					}
-					fx_stage[e] = ef.stages < 1 ? 1 : (ef.stages > GAS_MAX_FILTER_STAGES ? GAS_MAX_FILTER_STAGES : ef.stages);
-					prepare_coefficients(ef.mode, ef.cutoff_hz, ef.resonance, ef.gain, fx_stage[e], g.mix_rate, fx_coef[e]);
-				}
-			}
 		}
 		const bool has_dsp = filt || (mode == MODE_E && n_fx > 0);
 		bool poison = false;
@@ -674,25 +691,16 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 				rec->src_row = v.src_row;
 				rec->flags = rflags;
 				rec->n_fx = n_fx;
-#pragma unroll
-				for (int i = 0; i < 5; i++) {
-					rec->target[i] = target[i];
+				if (cflags & CLS_FILT) {
+					write_filter_target(rec, cutoff, lin_att, g.mix_rate);
 				}
 				if (!wide) {
 					ps->n = n_send;
 					ps->mask = mask;
 				}
 			}
-#pragma unroll
-			for (int e = 0; e < 2; e++) {
-				const int ei = x + e * 2;
-				if (ei < n_fx) {
-					rec->fx_stages[ei] = fx_stage[e];
-#pragma unroll
-					for (int i = 0; i < 5; i++) {
-						rec->fx_coef[ei][i] = fx_coef[e][i];
-					}
-				}
+			if (n_fx > 0) {
+				write_effect_coefficients(rec, &t.inst_fx[q], n_fx, fx_binding, lin_att, g.mix_rate, x);
 			}
 			if (!wide) {
 #pragma unroll
@@ -713,9 +721,10 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 	}
 }
 
-// The whole plan of block b = blk[BLK_P] by n_cta cooperating groups.  `zero_first`: the bus buffers / peaks are zeroed
-// here (otherwise the caller has done it before a grid-wide barrier of its own).
-static __device__ __forceinline__ void plan_block(const PlanGroup &G, PlanSmem &S, const PlanArgs &a) {
+// The whole plan of block b = blk[BLK_P] by n_cta cooperating groups.  wait_total > 0: the gains of this block are being
+// computed by the control warps of this launch (step kernel): a voice waits until its instance's parameters are in place
+// (DevTables::inst_seq) or until all wait_total warps have reported (BLK_GAIN_DONE).
+static __device__ __forceinline__ void plan_block(const PlanGroup &G, PlanSmem &S, const PlanArgs &a, int wait_total) {
 	const DevTables &t = a.t;
 	const BlockPlan &plan = a.plan;
 	if (G.tid == 0) {
@@ -739,23 +748,63 @@ static __device__ __forceinline__ void plan_block(const PlanGroup &G, PlanSmem &
 		}
 	}
 
-	// ---- instance part: prev <- cur (2 lanes per instance) ---------------------------------------------------------
+	group_stamp(G, 19);
+	// ---- voice part, nthreads / 2 voices per CTA and pass -------------------------------------------------------------
+	const int vpc = G.nthreads >> 1;
+	const int per_pass = G.n_cta * vpc;
+	const int passes = (a.n_voices + per_pass - 1) / per_pass;
+	for (int p = 0; p < passes; p++) {
+		plan_voices_pass(G, S, a, b, (p * G.n_cta + G.cta) * vpc, wait_total);
+		group_sync(G); // the pass table is free again
+	}
+
+	group_stamp(G, 20);
+	// ---- instance part: prev <- cur (2 lanes per instance), after every instance's gains are in place -------------------------
 	{
+		if (wait_total > 0) {
+			while (ld_acquire(&t.blk[BLK_GAIN_DONE]) < wait_total) {
+				__nanosleep(40);
+			}
+		}
 		const BusDetails *curs = t.inst_cur;
 		BusDetails *prev_wr = t.inst_prev + (size_t)(parity ^ 1) * t.max_instances;
 		const int x = G.tid & 1;
 		for (int q = gtid >> 1; q < a.inst_hwm; q += gthreads >> 1) {
-			if (!t.inst_active[q]) {
-				continue;
-			}
+			// one round of loads: the first two buses (calculate_spatialization never produces more), the rest only if present
 			const BusDetails *cs = &curs[q];
 			BusDetails *pw = &prev_wr[q];
+			const int act = t.inst_active[q];
 			int cn = cs->n;
+			const int b0 = cs->bus[0], b1 = cs->bus[1];
+			float v0[4], v1[4];
+#pragma unroll
+			for (int c = 0; c < 4; c++) {
+				v0[c] = cs->vol[0][c][x];
+				v1[c] = cs->vol[1][c][x];
+			}
+			if (!act) {
+				continue;
+			}
 			cn = cn < 0 ? 0 : (cn > GAS_MAX_BUSES_PER_PLAYBACK ? GAS_MAX_BUSES_PER_PLAYBACK : cn);
 			if (x == 0) {
 				pw->n = cn;
+				if (cn > 0) {
+					pw->bus[0] = b0;
+				}
+				if (cn > 1) {
+					pw->bus[1] = b1;
+				}
 			}
-			for (int k = 0; k < cn; k++) {
+#pragma unroll
+			for (int c = 0; c < 4; c++) {
+				if (cn > 0) {
+					pw->vol[0][c][x] = v0[c];
+				}
+				if (cn > 1) {
+					pw->vol[1][c][x] = v1[c];
+				}
+			}
+			for (int k = 2; k < cn; k++) {
 				if (x == 0) {
 					pw->bus[k] = cs->bus[k];
 				}
@@ -766,38 +815,47 @@ static __device__ __forceinline__ void plan_block(const PlanGroup &G, PlanSmem &
 			}
 		}
 	}
-
-	// ---- voice part, nthreads / 2 voices per CTA and pass -------------------------------------------------------------
-	const int vpc = G.nthreads >> 1;
-	const int per_pass = G.n_cta * vpc;
-	const int passes = (a.n_voices + per_pass - 1) / per_pass;
-	for (int p = 0; p < passes; p++) {
-		plan_voices_pass(G, S, a, b, (p * G.n_cta + G.cta) * vpc);
-		group_sync(G); // the pass table is free again
+	group_stamp(G, 19);
+	// ---- finish: every warp reports (release: its lanes' stores first); the last one publishes the plan, then tidies up -------------
+	__syncwarp();
+	int last = 0;
+	if ((G.tid & 31) == 0) {
+		int old;
+		asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(&t.blk[BLK_P_TICKET]) : "memory");
+		last = old == G.n_cta * (G.nthreads >> 5) - 1;
 	}
-
-	// ---- finish: the last CTA completes and publishes the plan ----------------------------------------------------------
-	__threadfence();
-	group_sync(G);
-	if (G.tid == 0) {
-		S.ticket = atomicAdd(&t.blk[BLK_P_TICKET], 1);
-	}
-	group_sync(G);
-	if (S.ticket != G.n_cta - 1 || G.tid >= 32) {
+	last = __shfl_sync(0xffffffffu, last, 0);
+	group_stamp(G, 21);
+	if (!last) {
 		return;
 	}
-	__threadfence();
-	const int lane = G.tid;
+	const int lane = G.tid & 31;
 	PlanHdr *hdr = &plan.hdr[slot_p];
+	// Published: the class slots and this block's counts, lists and records are final.  The step kernel reads the slot table and
+	// the counts directly; what follows (compact table for the voice-parallel kernel, slot recycling, clearing the next counts,
+	// the block counter) is only needed by launches that start after this one has ended.
+	if (lane == 0) {
+		st_release(&hdr->seq, b + 1);
+	}
 	const int32_t *cnt_now = plan.cls_count + slot_p * GAS_MAX_CLASSES;
 	int32_t *cnt_next = plan.cls_count + ((b + 1) & (GAS_PLAN_DEPTH - 1)) * GAS_MAX_CLASSES;
 	int base_s = 0, base_v = 0;
-	for (int r = 0; r < GAS_MAX_CLASSES / 32; r++) {
+	constexpr int R = GAS_MAX_CLASSES / 32;
+	unsigned long long keys[R], auxs[R];
+	int counts[R], idles[R];
+#pragma unroll
+	for (int r = 0; r < R; r++) { // one round of loads
 		const int i = r * 32 + lane;
-		const unsigned long long key = __ldcg(plan.cls_key + i);
-		const unsigned long long auxw = __ldcg(plan.cls_aux + i);
-		const int count = __ldcg(cnt_now + i);
-		const int idle = __ldcg(plan.cls_idle + i);
+		keys[r] = __ldcg(plan.cls_key + i);
+		auxs[r] = __ldcg(plan.cls_aux + i);
+		counts[r] = __ldcg(cnt_now + i);
+		idles[r] = __ldcg(plan.cls_idle + i);
+	}
+#pragma unroll
+	for (int r = 0; r < R; r++) {
+		const int i = r * 32 + lane;
+		const unsigned long long key = keys[r], auxw = auxs[r];
+		const int count = counts[r], idle = idles[r];
 		const bool used = key != 0ULL && count > 0;
 		const bool on_s = used && (int)(key & 3u) == PATH_STREAM;
 		const bool on_v = used && (int)(key & 3u) == PATH_VOICE;
@@ -836,13 +894,10 @@ static __device__ __forceinline__ void plan_block(const PlanGroup &G, PlanSmem &
 		hdr->n_cls = base_s;
 		hdr->n_vcls = base_v;
 		t.blk[BLK_P_TICKET] = 0;
+		t.blk[BLK_GAIN_DONE] = 0;
 		*(volatile int32_t *)&t.blk[BLK_P] = b + 1;
 	}
-	__threadfence();
-	__syncwarp();
-	if (lane == 0) {
-		st_release(&hdr->seq, b + 1);
-	}
+	group_stamp(G, 22);
 }
 
 } // namespace gasplan

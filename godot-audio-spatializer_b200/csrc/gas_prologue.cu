@@ -18,8 +18,9 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(gasplan::PlanArgs a) {
 	G.cta = blockIdx.x;
 	G.n_cta = gridDim.x;
 	G.bar_id = 1;
+	G.tl = nullptr;
 	GAS_GRID_DEP_WAIT(); // programmatic dependent launch: the previous block's kernels are complete after this
-	gasplan::plan_block(G, S, a);
+	gasplan::plan_block(G, S, a, 0);
 }
 
 } // namespace

@@ -157,11 +157,11 @@ int main(int argc, char **argv) {
 	if (getenv("GAS_K2_DEBUG") && (atoi(getenv("GAS_K2_DEBUG")) & 8)) { // one eager block with the timeline on
 		CK(gas_mix_block_device(ctx, V, d_voices, d_src[0], V, F, F, d_bus, nullptr));
 		CK(gas_sync(ctx));
-		unsigned long long h[148 * 16];
+		unsigned long long h[148 * 32];
 		cudaMemcpy(h, gas_debug_timeline(ctx), sizeof(h), cudaMemcpyDeviceToHost);
 		unsigned long long t0 = ~0ULL;
 		for (int c = 0; c < 148; c++) {
-			if (h[c * 16] && h[c * 16] < t0) t0 = h[c * 16];
+			if (h[c * 32] && h[c * 32] < t0) t0 = h[c * 32];
 		}
 		const char *names[16] = { "start", "table+partition", "first data", "last data", "flushed", "", "", "before table loads", "table loaded", "flush begins", "partition again (dbg 4)", "table in smem", "first indices", "stage 0 issued", "stage 1 issued", "flush pass 1 (dbg 4)" };
 		for (int k = 0; k < 16; k++) {
@@ -169,8 +169,8 @@ int main(int argc, char **argv) {
 			double mn = 1e30, mx = 0, av = 0;
 			int n = 0;
 			for (int c = 0; c < 148; c++) {
-				if (!h[c * 16 + k]) continue;
-				const double d = (double)(h[c * 16 + k] - t0) * 1e-3;
+				if (!h[c * 32 + k]) continue;
+				const double d = (double)(h[c * 32 + k] - t0) * 1e-3;
 				mn = d < mn ? d : mn;
 				mx = d > mx ? d : mx;
 				av += d;
@@ -180,14 +180,14 @@ int main(int argc, char **argv) {
 		}
 		int umin = 1 << 30, umax = 0;
 		for (int c = 0; c < 148; c++) {
-			umin = (int)h[c * 16 + 5] < umin ? (int)h[c * 16 + 5] : umin;
-			umax = (int)h[c * 16 + 5] > umax ? (int)h[c * 16 + 5] : umax;
+			umin = (int)h[c * 32 + 5] < umin ? (int)h[c * 32 + 5] : umin;
+			umax = (int)h[c * 32 + 5] > umax ? (int)h[c * 32 + 5] : umax;
 		}
 		printf("  units per CTA: %d..%d\n", umin, umax);
 		if (getenv("GAS_K2_DUMP")) { // per CTA: SM id, units, first data, last data, flushed (us after the first CTA started)
 			for (int c = 0; c < 148; c++) {
-				printf("  cta %3d sm %3d units %2d  %6.2f %6.2f %6.2f %6.2f\n", c, (int)h[c * 16 + 6], (int)h[c * 16 + 5], (double)(h[c * 16 + 1] - t0) * 1e-3,
-						(double)(h[c * 16 + 2] - t0) * 1e-3, (double)(h[c * 16 + 3] - t0) * 1e-3, (double)(h[c * 16 + 4] - t0) * 1e-3);
+				printf("  cta %3d sm %3d units %2d  %6.2f %6.2f %6.2f %6.2f\n", c, (int)h[c * 32 + 6], (int)h[c * 32 + 5], (double)(h[c * 32 + 1] - t0) * 1e-3,
+						(double)(h[c * 32 + 2] - t0) * 1e-3, (double)(h[c * 32 + 3] - t0) * 1e-3, (double)(h[c * 32 + 4] - t0) * 1e-3);
 			}
 		}
 	}
