@@ -617,7 +617,8 @@ def k2_debug_dump(m, torch):
         t0 = t[:, 0][t[:, 0] > 0].min()
         names = {0: "start", 11: "table in smem", 1: "partition", 12: "first indices", 13: "stage 0 issued", 2: "first data", 3: "last data",
                  9: "flush begins", 4: "flushed", 16: "control: entry", 23: "gain: emitter loaded", 24: "gain: tables loaded", 25: "gain: attenuation done", 26: "gain: pan done",
-                 27: "gain: stores issued", 17: "control: gains done", 18: "control: barrier passed",
+                 27: "gain: stores issued", 17: "control: gains done", 28: "plan: pass table reset", 29: "plan: voice computed",
+                 30: "plan: registered in CTA table", 31: "plan: class ranges reserved", 18: "control: barrier passed",
                  19: "control: instances done", 20: "control: voices done", 21: "control: ticket", 22: "control: plan published"}
         for k, nm in names.items():
             v = (t[:, k][t[:, k] > 0] - t0) * 1e-3
@@ -908,8 +909,14 @@ def gpu_arm(args):
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        # orderly exit at N > 1: every rank leaves together, and interpreter teardown (tensors freed after the mixer's streams
+        # and the process group are gone) is skipped
         dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():

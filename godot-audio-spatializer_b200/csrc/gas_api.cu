@@ -255,9 +255,12 @@ int step_core(gas_ctx *ctx, const gas_frame *d_src, int src_stride, const StepNe
 	if (ctx->gain_pending) {
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
 	}
-	if (ctx->comm_pending) {
-		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_comm_done, 0));
-		ctx->comm_pending = false;
+	// an exchange still in flight matters only if it reads the buffer this call clears (next->d_bus) or streams into
+	for (int r = 0; r < GAS_PLAN_DEPTH; r++) {
+		if (ctx->comm_ring_valid[r] && ((next && ctx->comm_src[r] == next->d_bus) || (have && ctx->comm_src[r] == ctx->planned.bus))) {
+			GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_comm_ring[r], 0));
+			ctx->comm_ring_valid[r] = false;
+		}
 	}
 	constexpr int D = GAS_PLAN_DEPTH;
 	const int i = (int)(ctx->step_count % D), im1 = (int)((ctx->step_count + D - 1) % D), im2 = (int)((ctx->step_count + D - 2) % D);
@@ -545,6 +548,7 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	for (int i = 0; i < GAS_PLAN_DEPTH; i++) {
 		ok = ok && cudaEventCreateWithFlags(&ctx->ev_step_done[i], cudaEventDisableTiming) == cudaSuccess;
 		ok = ok && cudaEventCreateWithFlags(&ctx->ev_block_done[i], cudaEventDisableTiming) == cudaSuccess;
+		ok = ok && cudaEventCreateWithFlags(&ctx->ev_comm_ring[i], cudaEventDisableTiming) == cudaSuccess;
 	}
 	if (ok) {
 		ok = launch_defaults(ctx, ctx->s_gain) == cudaSuccess && cudaStreamSynchronize(ctx->s_gain) == cudaSuccess;
@@ -613,6 +617,9 @@ void gas_destroy(gas_ctx *ctx) {
 		}
 		if (ctx->ev_block_done[i]) {
 			cudaEventDestroy(ctx->ev_block_done[i]);
+		}
+		if (ctx->ev_comm_ring[i]) {
+			cudaEventDestroy(ctx->ev_comm_ring[i]);
 		}
 	}
 	if (ctx->s_comm) {
@@ -1296,6 +1303,7 @@ int gas_capture_begin(gas_ctx *ctx) {
 	ctx->step_done_valid = false;
 	for (int i = 0; i < GAS_PLAN_DEPTH; i++) {
 		ctx->block_inflight[i] = false;
+		ctx->comm_ring_valid[i] = false;
 	}
 	GAS_CUDA(ctx, cudaStreamBeginCapture(ctx->s_mix, cudaStreamCaptureModeThreadLocal));
 	// fork: the gain, exchange and voice streams join the capture
@@ -1338,6 +1346,7 @@ int gas_capture_end(gas_ctx *ctx, int32_t *out_graph) {
 	ctx->step_done_valid = false;
 	for (int i = 0; i < GAS_PLAN_DEPTH; i++) {
 		ctx->block_inflight[i] = false;
+		ctx->comm_ring_valid[i] = false;
 	}
 	cudaError_t e2 = cudaStreamEndCapture(ctx->s_mix, &graph);
 	const uint64_t kernels = ctx->launches - ctx->capture_launches0;
@@ -1555,6 +1564,15 @@ int gas_reduce_bus_exchange_device(gas_ctx *ctx, const gas_frame *d_partial, gas
 	GAS_CUDA(ctx, launch_comm_exchange(ctx, d_partial, d_prev_sum, frames, ctx->s_comm));
 	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done, ctx->s_comm));
 	ctx->comm_pending = true;
+	{
+		const int r = (int)(ctx->comm_count++ % GAS_PLAN_DEPTH);
+		if (ctx->comm_ring_valid[r]) { // four exchanges old: long done, but never dropped without an edge
+			GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_comm_ring[r], 0));
+		}
+		GAS_CUDA(ctx, cudaEventRecord(ctx->ev_comm_ring[r], ctx->s_comm));
+		ctx->comm_src[r] = d_partial;
+		ctx->comm_ring_valid[r] = true;
+	}
 	return GAS_OK;
 }
 

@@ -430,8 +430,9 @@ static __device__ __noinline__ Pitch2 doppler_listener(float pitch_scale, float 
 // and the stores are dealt across them (lane l owns elements l, l + NL, ... of the [pair][side] tables).  Fewer lanes
 // = fewer, longer threads: slower on an empty GPU (the chain is latency-bound), but a smaller footprint beside the
 // mix kernels, which is what a step pays for (see launch_gain for the measured shapes).
+// Returns the instance the emitter belongs to (-1: record skipped).
 template <int NL>
-static __device__ __forceinline__ void gain_emitter(const DevTables &t, const GlobalCfg &g, int i, int l, int gbase, unsigned gm,
+static __device__ __forceinline__ int gain_emitter(const DevTables &t, const GlobalCfg &g, int i, int l, int gbase, unsigned gm,
 		const gas_emitter *__restrict__ emitters, int n_listeners, const gas_listener *__restrict__ listeners, const ListenerPre *__restrict__ pre,
 		const gas_area *__restrict__ areas, int n_areas, gas_params *__restrict__ out, int32_t *__restrict__ inst_seq = nullptr, int seq_val = 0,
 		unsigned long long *dbg = nullptr) {
@@ -447,7 +448,7 @@ static __device__ __forceinline__ void gain_emitter(const DevTables &t, const Gl
 	// instance keeps its parameters), an area index outside the resident areas counts as "no area" — like the prologue
 	// does with voice records.  Uniform over the emitter's lanes, so the shuffles below stay converged.
 	if (e.instance < 0 || e.instance >= g.max_instances || e.spatializer < 0 || e.spatializer >= g.max_spatializers) {
-		return;
+		return -1;
 	}
 	if (e.area >= n_areas) {
 		e.area = -1;
@@ -681,6 +682,7 @@ static __device__ __forceinline__ void gain_emitter(const DevTables &t, const Gl
 			asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(inst_seq + q), "r"(seq_val) : "memory");
 		}
 	}
+	return q;
 }
 
 

@@ -237,6 +237,12 @@ struct gas_ctx {
 	bool block_inflight[GAS_PLAN_DEPTH] = {};
 	gas_frame *inflight_bus[GAS_PLAN_DEPTH] = {}, *inflight_peaks[GAS_PLAN_DEPTH] = {};
 	bool step_done_valid = false; // ev_step_done[(step_count - 1) % depth] has been recorded
+	// exchanges of a pipelined run still in flight on the exchange stream: a step only waits for the one that reads the buffer it is
+	// about to clear (two steps of slack when the caller rotates four bus buffers), not for the latest
+	cudaEvent_t ev_comm_ring[GAS_PLAN_DEPTH] = {};
+	const gas_frame *comm_src[GAS_PLAN_DEPTH] = {};
+	bool comm_ring_valid[GAS_PLAN_DEPTH] = {};
+	uint64_t comm_count = 0;
 	DevTables t{};
 	BlockPlan plan{};
 	// staging (device)

@@ -575,7 +575,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 		// the previous launch is complete after this (its streaming warps read the plan slot and the bus buffers that
 		// are rewritten here; its control warps wrote the tables that are read here)
 		GAS_GRID_DEP_WAIT();
-		int wait_total = 0;
+		int wait_total = 0, own_q = -1;
+		G.tid = ctl_tid;
+		G.nthreads = kControlThreads;
+		G.cta = blockIdx.x;
+		G.n_cta = gridDim.x;
+		G.bar_id = 3;
+		// this lane pair's first voice of the next block: fetched now, needed after the gain tasks
+		gas_voice v_pre{};
+		v_pre.voice = -1;
+		if (gasplan::plan_first_voice(G) < A.p.n_voices) {
+			v_pre = A.p.voices[gasplan::plan_first_voice(G)];
+		}
 		if (A.n_emitters > 0) {
 			// Gains of the next block, two lanes per emitter.  No grid-wide barrier separates them from the plan: every instance
 			// carries a flag (block index + 1, release) that the planner of a voice waits for, and every control warp reports
@@ -585,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 			const int gbase = lane & 30;
 			const unsigned gm = 3u << gbase;
 			for (int e = blockIdx.x * pairs + (ctl_tid >> 1); e < A.n_emitters; e += gridDim.x * pairs) {
-				gasgain::gain_emitter<2>(A.p.t, g, e, ctl_tid & 1, gbase, gm, A.emitters, A.n_listeners, A.listeners, A.listener_pre, A.areas, A.n_areas,
+				own_q = gasgain::gain_emitter<2>(A.p.t, g, e, ctl_tid & 1, gbase, gm, A.emitters, A.n_listeners, A.listeners, A.listener_pre, A.areas, A.n_areas,
 						nullptr, A.p.t.inst_seq, b_next + 1, G.tl);
 			}
 			__syncwarp();
@@ -596,12 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 			gasplan::group_stamp(G, 17);
 		}
 		gasplan::group_stamp(G, 18);
-		G.tid = ctl_tid;
-		G.nthreads = kControlThreads;
-		G.cta = blockIdx.x;
-		G.n_cta = gridDim.x;
-		G.bar_id = 3;
-		gasplan::plan_block(G, s_plan, A.p, wait_total);
+		gasplan::plan_block(G, s_plan, A.p, wait_total, own_q, &v_pre);
 		return;
 	}
 

@@ -179,7 +179,8 @@ static __device__ __noinline__ void write_effect_coefficients(VoiceRec *rec, con
 }
 
 // One pass of the voice part: the group's threads take nthreads / 2 consecutive voices starting at j0.
-static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, PlanSmem &S, const PlanArgs &a, int b, int j0, int wait_total) {
+static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, PlanSmem &S, const PlanArgs &a, int b, int j0, int wait_total, int own_q,
+		const gas_voice *pre) {
 	const DevTables &t = a.t;
 	const GlobalCfg &g = a.g;
 	const BlockPlan &plan = a.plan;
@@ -210,13 +211,15 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 	// ---- level 0 / level 1 loads -----------------------------------------------------------------------------------
 	gas_voice v{};
 	v.voice = -1;
-	if (j < a.n_voices) {
+	if (pre) {
+		v = *pre; // fetched by the caller before its gain tasks
+	} else if (j < a.n_voices) {
 		v = a.voices[j];
 	}
 	const bool valid = v.voice >= 0 && v.voice < maxv && v.instance >= 0 && v.instance < g.max_instances;
 	const int q = valid ? v.instance : 0;
 	const int vslot = valid ? v.voice : 0;
-	if (wait_total > 0 && valid) {
+	if (wait_total > 0 && valid && q != own_q) { // (own_q: this lane pair computed that instance's gains itself)
 		// fine-grained dependency instead of a grid-wide barrier between the gain tasks and the plan: normally the flag is already
 		// set (the same lanes computed this instance's gains a moment ago)
 		while (ld_acquire(&t.inst_seq[q]) != b + 1 && ld_acquire(&t.blk[BLK_GAIN_DONE]) < wait_total) {
@@ -245,6 +248,7 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 		vp_old[c] = vprev[c * 2 + x];
 	}
 	group_sync(G); // the pass table is reset
+	group_stamp(G, 28);
 
 	// ---- voice part ----------------------------------------------------------------------------------------
 	int path = PATH_NONE, mode = MODE_A, n_send = 0, n_group = 0;
@@ -553,6 +557,10 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 		}
 	}
 
+	if (G.tl) {
+		G.tl[8] = (unsigned long long)(__float_as_uint(mixv[0] + cur_vol[0][0] + prev_vol[0][0] + vp_old[0]) & 1u); // (forces the loads to have landed)
+	}
+	group_stamp(G, 29);
 	// ---- class lookup: once per class per CTA in shared memory, then one global atomic per class ------------
 	// A class is (key, aux).  The key of a scaled class carries a 20-bit hash of its aux word in its spare bits, so that
 	// the compare-and-swap that claims a slot sees (almost always) the whole identity; the aux words are compared once
@@ -593,6 +601,7 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 		gpos = atomicAdd(&cnt_now[generic_cid], 1);
 	}
 	group_sync(G);
+	group_stamp(G, 30);
 	if (G.tid < kTab && S.key[G.tid] != 0ULL && S.cnt[G.tid] > 0) {
 		// Slots are stable across blocks: in the steady state the class is already in the snapshot and the only
 		// global operation is the add that reserves this CTA's range of the class list.
@@ -643,6 +652,7 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 		S.cid[G.tid] = cid;
 	}
 	group_sync(G);
+	group_stamp(G, 31);
 	slot = __shfl_sync(gm, slot, lane & 30u);
 	lpos = __shfl_sync(gm, lpos, lane & 30u);
 	gpos = __shfl_sync(gm, gpos, lane & 30u);
@@ -724,7 +734,9 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 // The whole plan of block b = blk[BLK_P] by n_cta cooperating groups.  wait_total > 0: the gains of this block are being
 // computed by the control warps of this launch (step kernel): a voice waits until its instance's parameters are in place
 // (DevTables::inst_seq) or until all wait_total warps have reported (BLK_GAIN_DONE).
-static __device__ __forceinline__ void plan_block(const PlanGroup &G, PlanSmem &S, const PlanArgs &a, int wait_total) {
+static __device__ __forceinline__ int plan_first_voice(const PlanGroup &G) { return G.cta * (G.nthreads >> 1) + (G.tid >> 1); }
+static __device__ __forceinline__ void plan_block(const PlanGroup &G, PlanSmem &S, const PlanArgs &a, int wait_total, int own_q = -1,
+		const gas_voice *pre = nullptr) {
 	const DevTables &t = a.t;
 	const BlockPlan &plan = a.plan;
 	if (G.tid == 0) {
@@ -754,7 +766,7 @@ static __device__ __forceinline__ void plan_block(const PlanGroup &G, PlanSmem &
 	const int per_pass = G.n_cta * vpc;
 	const int passes = (a.n_voices + per_pass - 1) / per_pass;
 	for (int p = 0; p < passes; p++) {
-		plan_voices_pass(G, S, a, b, (p * G.n_cta + G.cta) * vpc, wait_total);
+		plan_voices_pass(G, S, a, b, (p * G.n_cta + G.cta) * vpc, wait_total, own_q, p == 0 ? pre : nullptr);
 		group_sync(G); // the pass table is free again
 	}
 

@@ -1,7 +1,7 @@
 #!/bin/bash
-# r02p: fine-grained gain->plan dependency, early publish, raw-table start-up: tests, timeline, bench
+# r02q: fine-grained gain->plan dependency, early publish, raw-table start-up: tests, timeline, bench
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
-O=gpurun_out/r02p; mkdir -p $O
+O=gpurun_out/r02q; mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q -x > $O/pytest_all.log 2>&1; echo "all exit $?" >> $O/runs.log
 B="python bench.py --no-cpu --no-configs --no-parity --steps 64 --warmup 8 --e2e-steps 4"
 GAS_K2_DEBUG=8 timeout 300 $B > $O/bench_tl.json 2> $O/bench_tl.err; echo "tl exit $?" >> $O/runs.log
