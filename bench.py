@@ -26,6 +26,7 @@ single-threaded object graph, not a batch mixer; headless Godot cannot be built 
 """
 import hashlib
 import argparse
+import math
 import json
 import os
 import sys
@@ -518,37 +519,56 @@ def measure_config(gas, torch, spec, device, peak_gbs, cpu_budget_s=2.5):
         d_em = [torch.from_numpy(e.view(np.uint8).copy()).to(dev) for e in ems]
         d_voices = torch.from_numpy(voices.view(np.uint8).copy()).to(dev)
         d_src = [(torch.rand((V, F, 2), device=dev) - 0.5) * 0.5 for _ in range(sets)]
-        d_bus = torch.zeros((B, C, F, 2), device=dev)
+        d_bus = [torch.zeros((B, C, F, 2), device=dev) for _ in range(NB)]
+        n_graphs = sets * NB // math.gcd(sets, NB)
+
+        def nxt(k):
+            return dict(n_emitters=V, d_emitters=d_em[k % sets].data_ptr(), n_voices=V, d_voices=d_voices.data_ptr(), src_rows=V, frames=F,
+                        d_bus_out=d_bus[k % NB].data_ptr())
 
         def capture():
             gs = []
-            for s_ in range(sets):
+            if CLASSIC:
+                for s_ in range(n_graphs):
+                    m.capture_begin()
+                    m.mix_block_device(V, d_voices.data_ptr(), d_src[s_ % sets].data_ptr(), V, F, F, d_bus[s_ % NB].data_ptr())
+                    m.gain_compute_device(V, d_em[(s_ + 1) % sets].data_ptr())
+                    gs.append(m.capture_end())
+                return gs
+            m.step_device(d_src[0].data_ptr(), F, next=None)  # ends a run in progress (nothing happens when none is)
+            m.step_device(next=nxt(0))
+            for s_ in range(n_graphs):
                 m.capture_begin()
-                m.mix_block_device(V, d_voices.data_ptr(), d_src[s_].data_ptr(), V, F, F, d_bus.data_ptr())
-                m.gain_compute_device(V, d_em[(s_ + 1) % sets].data_ptr())
+                m.step_device(d_src[s_ % sets].data_ptr(), F, next=nxt(s_ + 1))
                 gs.append(m.capture_end())
             return gs
 
         graphs = capture()
         stream = torch.cuda.ExternalStream(m.mix_stream, device=dev)
-        for k in range(max(8, sets)):
-            m.graph_launch(graphs[k % sets])
+        for k in range(2 * n_graphs):
+            m.graph_launch(graphs[k % n_graphs])
+        m.step_join_device()
         m.sync()
+        steps = (steps // n_graphs) * n_graphs
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record()
         for k in range(steps):
-            m.graph_launch(graphs[k % sets])
+            m.graph_launch(graphs[k % n_graphs])
+        m.step_join_device()
         with torch.cuda.stream(stream):
             e1.record()
         m.sync()
         us = 1e3 * e0.elapsed_time(e1) / steps
         m.profile_enable(True)
         pg = capture()
-        for k in range(16):
-            m.graph_launch(pg[k % sets])
+        for k in range(4 * n_graphs):
+            m.graph_launch(pg[k % n_graphs])
         prof = m.profile_read()
         m.profile_enable(False)
+        if not CLASSIC:
+            m.step_device(d_src[0].data_ptr(), F, next=None)
+        m.sync()
         del d_src
     # parity: two state-carrying blocks, full size, against the oracle (bounded: the largest corner is checked on a slice of time)
     parity = None
