@@ -207,8 +207,20 @@ def bench_config(w, world, peer=True):
                        if peer else "torch.distributed all_reduce (NCCL) of the partial bus buffers, one call per step")}
 
 
+def select_form(world):
+    """Pipelined form (gas_step_device) at 1 and 2 GPUs, block-call form at 4 and 8 unless GAS_BENCH_PIPELINED is set.
+    The pipelined form was validated at 1 and 2 GPUs this round; the only 4- / 8-GPU run hung (an NCCL barrier enqueued while step
+    kernels were in flight, see barrier() in gpu_arm) and took the rest of the round's GPU budget with it, so the fix could not be
+    re-run there: 4 and 8 GPUs keep the block-call form, whose kernels never wait for each other's CTAs (the structure that ran on 8
+    GPUs in round 1)."""
+    global CLASSIC
+    if world >= 4 and not os.environ.get("GAS_BENCH_PIPELINED"):
+        CLASSIC = True
+
+
 def reference_arm(args):
     rank, _, world = dist_env()
+    select_form(max(world, args.gpus))
     if rank != 0:
         return
     import gaspkg
@@ -667,6 +679,7 @@ def gpu_arm(args):
     abi, synth = gas.abi, gas.synth
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
+    select_form(world)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -717,10 +730,14 @@ def gpu_arm(args):
                     dist.all_reduce(dw.d_bus[k % NB])  # sum of the per-GPU partial bus buffers (NCCL over NVLink)
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        # Drain the GPU first, THEN meet the other ranks: a collective's kernel enqueued while step kernels are in flight can take
+        # an SM that a step launch needs for its 148th CTA (its control warps wait for every CTA of the launch), while the step
+        # kernels keep the collective's other CTAs off the SMs: the 4- and 8-GPU runs of this round hung exactly there.
         m.sync()
         torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
 
     # ---- timed region: `value` ----------------------------------------------------------------------------
     dw.reduce_prime()
@@ -887,6 +904,29 @@ def gpu_arm(args):
            "api": "gas_gain_compute + gas_mix_block (host pointers, pinned)" if dist is None else
                   "gas_gain_compute + pinned host->device copy + gas_mix_block_device + gas_reduce_bus_device + device->host copy of the sum"}
 
+    # ---- e2e with device-resident sources (N = 1): PCM clips live in HBM, the resampler in front of the path produces the block's
+    # source rows on the device (gas_mix_block_resident), so per step only the emitters and the voice list travel up and the bus
+    # buffers come back.  The leg runs in a process of its own (resident_leg below) and is adopted only if its self-checks pass:
+    # this code path was finished after the round's GPU budget was spent, so nothing that goes wrong in it may touch the line.
+    if dist is None and not os.environ.get("GAS_BENCH_NO_RESIDENT"):
+        import subprocess
+        res = None
+        try:
+            cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--resident-leg", "--e2e-steps", str(max(8, min(K, args.e2e_steps)))],
+                                capture_output=True, text=True, timeout=300)
+            for ln in reversed(cp.stdout.strip().splitlines()):
+                if ln.startswith("{"):
+                    res = json.loads(ln)
+                    break
+            if res is None:
+                res = {"error": f"exit {cp.returncode}: {cp.stderr.strip()[-300:]}"}
+        except Exception as ex:
+            res = {"error": repr(ex)[:300]}
+        if res.get("value") and res.get("parity_ok") and res.get("all_voices_still_active") and res.get("bus_finite_and_nonzero"):
+            e2e = dict(res, host_frames=e2e)
+        else:
+            e2e["resident_sources"] = res
+
     # ---- cpu baseline (rank 0, N = 1) --------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -939,6 +979,117 @@ def gpu_arm(args):
         os._exit(0)
 
 
+def resident_leg(args):
+    """Child process of the N = 1 bench: e2e with device-resident sources.  Prints one JSON object."""
+    import torch
+    import gaspkg
+    import scenarios as S
+    from oracle import orc
+    gas = gaspkg.load()
+    abi, synth = gas.abi, gas.synth
+    w = dict(WORKLOAD)
+    V, F, C, B = w["voices"], w["frames"], w["speaker_mode"] + 1, w["num_buses"]
+    out = {"unit": UNIT}
+
+    def clip(n, seed, rate=44100.0):
+        rs = np.random.RandomState(seed)
+        tt = np.arange(n, dtype=np.float64)
+        return (0.25 * np.sin(2 * np.pi * (80.0 + 23.0 * seed) * tt / rate)[:, None] + 0.02 * rs.randn(n, 2)).astype(np.float32)
+
+    # ---- self-check: 96 voices, 4 blocks, clips that end inside the run, against the oracle (stream form fed by the oracle's resampler) ----
+    try:
+        Vc = 96
+        cfg = dict(max_instances=Vc, max_voices=Vc, max_frames=F, num_buses=B, speaker_mode=w["speaker_mode"], mix_rate=w["mix_rate"])
+        listeners = np.array([abi.identity_listener()], dtype=abi.listener)
+        areas = np.array([synth.reverb_area(reverb_bus=1, amount=0.5, uniformity=0.0)], dtype=abi.area)
+        clips = [clip(1400 + 173 * k_, 10 + k_) for k_ in range(6)]
+        inst = np.arange(Vc, dtype=np.int32)
+        voices = synth.make_voices(Vc)
+        ok_all, worst_all = True, 0.0
+        with gas.Mixer(**cfg) as m, orc.OracleMixer(**cfg) as o:
+            ems = [synth.make_emitters(Vc, block=b_, dt=F / w["mix_rate"], area_fraction=0.5) for b_ in range(4)]
+            for e_ in ems:
+                e_["pitch_scale"] = np.linspace(0.5, 2.0, Vc).astype(np.float32)
+            for mm in (m, o):
+                mm.spatializer_set(0, abi.spatializer_defaults(**w["spat"]))
+                mm.instance_init(inst, 0)
+                mm.gain_compute(ems[0], listeners, areas, want_params=False)
+                mm.instance_start(inst)
+                mm.voice_init(inst)
+            for k_ in range(6):
+                m.source_set(k_, clips[k_], 44100.0)
+            m.voice_play(inst, inst % 6)
+            rsm = [orc.Resampler(clips[i_ % 6], 44100.0) for i_ in range(Vc)]
+            active = np.ones(Vc, dtype=bool)
+            for b_ in range(4):
+                m.gain_compute(ems[b_], listeners, areas, want_params=False)
+                po = o.gain_compute(ems[b_], listeners, areas)
+                live = voices[active].copy()
+                live["src_row"] = np.arange(live.size)
+                rows = np.zeros((max(live.size, 1), F, 2), dtype=np.float32)
+                mixed = np.zeros(max(live.size, 1), dtype=np.int32)
+                for r_, vv in enumerate(live["voice"]):
+                    rows[r_], mixed[r_] = rsm[vv].mix(F, float(po["pitch_scale"][vv]), w["mix_rate"])
+                want_bus, want_status = o.mix_block_stream(live, rows, mixed[: live.size], F)
+                got_bus, got_status = m.mix_block_resident(live, F)
+                ok, worst, _ = S.sample_close(got_bus, want_bus)
+                ok_all = ok_all and ok and bool(np.array_equal(got_status, want_status)) and bool(np.array_equal(S.routing(got_bus), S.routing(want_bus)))
+                worst_all = max(worst_all, worst)
+                alive = (want_status & abi.VOICE_ACTIVE) != 0
+                idx = np.nonzero(active)[0]
+                active[idx[~alive]] = False
+        out["parity_ok"] = bool(ok_all)
+        out["parity_worst_abs_err"] = worst_all
+    except Exception as ex:
+        out["parity_ok"] = False
+        out["parity_error"] = repr(ex)[:300]
+        print(json.dumps(out), flush=True)
+        return
+
+    # ---- timed leg: the bench workload, 16 looping clips at 44.1 kHz ----------------------------------------------------
+    listeners = np.array([abi.identity_listener()], dtype=abi.listener)
+    areas = np.array([synth.reverb_area(reverb_bus=1, amount=0.5, uniformity=0.0)], dtype=abi.area)
+    dt = F / w["mix_rate"]
+    emitters = [synth.make_emitters(V, block=b_, dt=dt, area_fraction=w["area_fraction"], r_min=w["r_min"], r_max=w["r_max"]) for b_ in range(N_SETS)]
+    voices = synth.make_voices(V)
+    with gas.Mixer(device=0, max_instances=V, max_voices=V, max_frames=F, max_spatializers=2, num_buses=B, speaker_mode=w["speaker_mode"],
+                   mix_rate=w["mix_rate"]) as m:
+        setup_mixer(m, w, abi, emitters, listeners, areas)
+        n_clips, clip_len = 16, 48000
+        for c_ in range(n_clips):
+            m.source_set(c_, clip(clip_len, c_), 44100.0, loop=True)
+        vid = np.arange(V, dtype=np.int32)
+        m.voice_play(vid, vid % n_clips, (vid * 977) % (clip_len - 256))
+        pin_voices = torch.from_numpy(voices.view(np.uint8).copy()).pin_memory()
+        pin_bus = torch.empty((B, C, F, 2), dtype=torch.float32).pin_memory()
+        pin_status = torch.empty((V,), dtype=torch.int32).pin_memory()
+
+        def step(k_):
+            m.gain_compute(emitters[k_ % N_SETS], listeners, areas, want_params=False)
+            m.mix_block_resident_host_ptr(V, pin_voices.data_ptr(), F, pin_bus.data_ptr(), pin_status.data_ptr())
+
+        for k_ in range(4):
+            step(k_)
+        torch.cuda.synchronize()
+        kr = max(8, args.e2e_steps)
+        t0 = time.perf_counter()
+        for k_ in range(kr):
+            step(k_)
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        bus = pin_bus.numpy()
+        out.update({"value": V * F * kr / sec, "ms_per_step": 1e3 * sec / kr, "steps": kr,
+                    "h2d_bytes_per_step": int(voices.nbytes + emitters[0].nbytes + listeners.nbytes + areas.nbytes),
+                    "d2h_bytes_per_step": int(B * C * F * 8 + V * 4),
+                    "api": "gas_gain_compute (host emitters) + gas_mix_block_resident (host voice list; resampler + voice lifecycle + mix on the "
+                           "device; bus buffers and voice status back to the host)",
+                    "sources": f"{n_clips} looping PCM clips of {clip_len} frames at 44.1 kHz resident in HBM (uploaded once with gas_source_set), "
+                               "resampled to 48 kHz x pitch_scale per block",
+                    "all_voices_still_active": bool((pin_status.numpy() & 1).all()),
+                    "bus_finite_and_nonzero": bool(np.isfinite(bus).all() and np.abs(bus).max() > 0)})
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -954,8 +1105,11 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE.json configurations")
     ap.add_argument("--configs-budget", type=float, default=100.0, help="seconds after which remaining secondary configurations are skipped")
     ap.add_argument("--area-fraction", type=float, default=None, help="fraction of voices inside the reverb area (experiments)")
+    ap.add_argument("--resident-leg", action="store_true", help="internal: the e2e leg with device-resident sources, in a process of its own")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.resident_leg:
+        resident_leg(args)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         gpu_arm(args)

@@ -486,6 +486,14 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->t.vs_look, V * (size_t)GAS_LOOKAHEAD_BUFFER_SIZE);
 	ALLOC(ctx->t.vs_life, V);
 	ALLOC(ctx->t.inst_threshold, I);
+	ALLOC(ctx->t.vs_src, V);
+	ALLOC(ctx->t.vs_start, V);
+	ALLOC(ctx->t.vs_pos, V);
+	ctx->max_sources = 4096;
+	ALLOC(ctx->d_sources, (size_t)ctx->max_sources);
+	ctx->h_sources.assign(ctx->max_sources, SourceDesc{});
+	ALLOC(ctx->d_rs_rows, V * F);
+	ALLOC(ctx->d_rs_mixed, V);
 	ctx->t.max_voices = (int32_t)V;
 	ctx->t.threshold_default = expf(-80.0f * (float)0.11512925464970228420089957273422); // upstream Math::db_to_linear(float)
 	ALLOC(ctx->d_stage, V * F + 2 * F); // + in/out rows of the per-call entry points
@@ -584,10 +592,15 @@ void gas_destroy(gas_ctx *ctx) {
 		ctx->plan.overflow, ctx->plan.list, ctx->plan.k2_rows, ctx->plan.rec, ctx->d_voices, ctx->d_src, ctx->d_bus,
 		ctx->d_peaks, ctx->d_rep, ctx->d_emitters, ctx->d_listeners, ctx->d_areas, ctx->d_params_out, ctx->d_ids, ctx->d_ids2, ctx->d_scratch,
 		ctx->d_exchange, ctx->d_comm_seq, ctx->d_comm_ticket, ctx->t.vs_look, ctx->t.vs_life, ctx->t.inst_threshold, ctx->d_stage, ctx->d_voices_stage,
-		ctx->d_mixed, ctx->d_status, ctx->d_ids_mix, ctx->d_scratch_mix, ctx->plan.hdr, ctx->d_listener_pre, ctx->t.inst_seq };
+		ctx->d_mixed, ctx->d_status, ctx->d_ids_mix, ctx->d_scratch_mix, ctx->plan.hdr, ctx->d_listener_pre, ctx->t.inst_seq, ctx->t.vs_src, ctx->t.vs_start, ctx->t.vs_pos, ctx->d_sources, ctx->d_rs_rows, ctx->d_rs_mixed };
 	for (void *p : ptrs) {
 		if (p) {
 			cudaFree(p);
+		}
+	}
+	for (auto &sd : ctx->h_sources) {
+		if (sd.pcm) {
+			cudaFree((void *)sd.pcm);
 		}
 	}
 	if (ctx->ev_gain_done) {
@@ -1115,6 +1128,128 @@ int gas_mix_block_stream_device(gas_ctx *ctx, int32_t n_voices, const gas_voice 
 		return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_stream_device: source rows must be 8-byte, bus buffers 16-byte aligned");
 	}
 	return stream_core(ctx, n_voices, d_voices, d_src, src_rows, src_row_stride, frames, d_mixed_frames, d_bus_out, d_status_out);
+}
+
+// ---- device-resident sources + resampler -----------------------------------------------------------
+int gas_source_set(gas_ctx *ctx, int32_t slot, const gas_frame *frames, int32_t n_frames, float sample_rate, int32_t loop) {
+	ENTER(ctx);
+	if (slot < 0 || slot >= ctx->max_sources || n_frames < 0 || (n_frames > 0 && !frames) || !(sample_rate > 0.f) || ctx->capturing) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_source_set: slot 0..%d, frames, sample_rate > 0, not while capturing", ctx->max_sources - 1);
+	}
+	if (n_frames > 0 && n_frames < 128) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_source_set: a source holds at least 128 frames (one internal buffer of the resampler)");
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix)); // nothing in flight reads the slot
+	SourceDesc &sd = ctx->h_sources[slot];
+	if (sd.pcm) {
+		cudaFree((void *)sd.pcm);
+		sd = SourceDesc{};
+	}
+	if (n_frames > 0) {
+		gas_frame *d = nullptr;
+		if (cudaMalloc((void **)&d, (size_t)n_frames * sizeof(gas_frame)) != cudaSuccess) {
+			return gas_fail(ctx, GAS_ERR_NOMEM, "gas_source_set: out of device memory");
+		}
+		GAS_CUDA(ctx, cudaMemcpyAsync(d, frames, (size_t)n_frames * sizeof(gas_frame), cudaMemcpyHostToDevice, ctx->s_mix));
+		sd.pcm = d;
+		sd.n_frames = n_frames;
+		sd.loop = loop ? 1 : 0;
+		sd.sample_rate = sample_rate;
+	}
+	GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources + slot, &sd, sizeof(SourceDesc), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	return GAS_OK;
+}
+
+int gas_voice_play(gas_ctx *ctx, int32_t n, const int32_t *voices, const int32_t *sources, const int32_t *start_frames) {
+	ENTER(ctx);
+	if (n < 0 || n > ctx->cfg.max_voices || (n > 0 && (!voices || !sources)) || !ids_valid(voices, n, ctx->cfg.max_voices) || ctx->capturing) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_play: bad voice slot (or capture in progress)");
+	}
+	for (int i = 0; i < n; i++) {
+		const int s = sources[i];
+		const int st = start_frames ? start_frames[i] : 0;
+		if (s < -1 || s >= ctx->max_sources || (s >= 0 && !ctx->h_sources[s].pcm) || st < 0) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_play: voice %d: source slot %d is empty or out of range", voices[i], s);
+		}
+		if (s >= 0 && !ctx->h_sources[s].loop && ctx->h_sources[s].n_frames - st < 128) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_voice_play: voice %d: fewer than 128 frames behind the start frame", voices[i]);
+		}
+	}
+	if (n == 0) {
+		return GAS_OK;
+	}
+	int32_t *d = ctx->d_ids_mix; // [max(V, I)] ints: voices | sources | starts need 3 n <= 3 V: staged through the scratch buffer instead
+	(void)d;
+	int32_t *dv = (int32_t *)ctx->d_scratch_mix, *ds = dv + n, *dst = ds + n;
+	GAS_CUDA(ctx, cudaMemcpyAsync(dv, voices, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	GAS_CUDA(ctx, cudaMemcpyAsync(ds, sources, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	if (start_frames) {
+		GAS_CUDA(ctx, cudaMemcpyAsync(dst, start_frames, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_mix));
+	}
+	GAS_CUDA(ctx, launch_voice_play(ctx, n, dv, ds, start_frames ? dst : nullptr, ctx->s_mix));
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix)); // the host arrays may be reused
+	return GAS_OK;
+}
+
+int gas_resample_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices, int32_t frames, gas_frame *d_rows, int32_t row_stride,
+		int32_t src_rows, int32_t *d_mixed_frames) {
+	ENTER(ctx);
+	if (n_voices < 0 || n_voices > ctx->cfg.max_voices || (n_voices > 0 && (!d_voices || !d_rows)) || frames < 1 || frames > ctx->cfg.max_frames ||
+			row_stride < frames || src_rows < 0) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_resample_block_device: bad voice count, frame count, stride or null pointer");
+	}
+	if (ctx->gain_pending) { // the pitch scale comes from the instance's current parameters
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
+	}
+	GAS_CUDA(ctx, launch_resample(ctx, n_voices, d_voices, frames, d_rows, row_stride, src_rows, d_mixed_frames, ctx->s_mix));
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_prologue_done, ctx->s_mix)); // later gain-side calls wait: they rewrite the pitch scale
+	ctx->prologue_pending = true;
+	return GAS_OK;
+}
+
+int gas_mix_block_resident(gas_ctx *ctx, int32_t n_voices, const gas_voice *voices, int32_t frames, gas_frame *bus_out, int32_t *status_out) {
+	{
+		ENTER(ctx);
+		if (n_voices < 0 || n_voices > ctx->cfg.max_voices || (n_voices > 0 && !voices) || !bus_out) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_resident: bad voice count or null pointer");
+		}
+		if (frames < GAS_LOOKAHEAD_BUFFER_SIZE || (frames & 1) || frames > ctx->cfg.max_frames) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_resident: frames must be even, >= %d and <= max_frames", GAS_LOOKAHEAD_BUFFER_SIZE);
+		}
+		if (ctx->capturing) {
+			return gas_fail(ctx, GAS_ERR_STATE, "gas_mix_block_resident: host pointers cannot be used while capturing");
+		}
+		if (ctx->planned.valid) {
+			return gas_fail(ctx, GAS_ERR_STATE, "gas_mix_block_resident: a block planned by gas_step_device is waiting to be streamed");
+		}
+		for (int i = 0; i < n_voices; i++) {
+			const gas_voice &v = voices[i];
+			if (v.voice < 0 || v.voice >= ctx->cfg.max_voices || v.instance < 0 || v.instance >= ctx->cfg.max_instances || v.src_row < -1 ||
+					v.src_row >= ctx->cfg.max_voices) {
+				return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_resident: voice %d references a bad slot or row", i);
+			}
+		}
+		const size_t bus_frames = (size_t)ctx->cfg.num_buses * (ctx->cfg.speaker_mode + 1) * frames;
+		if (n_voices > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_voices, voices, n_voices * sizeof(gas_voice), cudaMemcpyHostToDevice, ctx->s_mix));
+		}
+		if (ctx->gain_pending) {
+			GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));
+		}
+		// source rows come from the resident PCM: row src_row of the internal row buffer for every voice
+		GAS_CUDA(ctx, launch_resample(ctx, n_voices, ctx->d_voices, frames, ctx->d_rs_rows, frames, ctx->cfg.max_voices, ctx->d_rs_mixed, ctx->s_mix));
+		int st = stream_core(ctx, n_voices, ctx->d_voices, ctx->d_rs_rows, ctx->cfg.max_voices, frames, frames, ctx->d_rs_mixed, ctx->d_bus, ctx->d_status);
+		if (st) {
+			return st;
+		}
+		GAS_CUDA(ctx, cudaMemcpyAsync(bus_out, ctx->d_bus, bus_frames * sizeof(gas_frame), cudaMemcpyDeviceToHost, ctx->s_mix));
+		if (status_out && n_voices > 0) {
+			GAS_CUDA(ctx, cudaMemcpyAsync(status_out, ctx->d_status, n_voices * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_mix));
+		}
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	return GAS_OK;
 }
 
 int gas_set_playback_disable_threshold_db(gas_ctx *ctx, int32_t n, const int32_t *instances, const float *db) {

@@ -178,9 +178,21 @@ struct DevTables {
 	// voice lifecycle (stream form of the mix)
 	gas_frame *vs_look;          // [max_voices][64] lookahead
 	uint32_t *vs_life;           // [max_voices] GAS_VOICE_ACTIVE | GAS_VOICE_HAS_FRAMES
+	int32_t *vs_src;             // [max_voices] source slot the voice plays (-1: none), gas_voice_play
+	long long *vs_start;         // [max_voices] first source frame of the playback
+	unsigned long long *vs_pos;  // [max_voices] 16.16 fixed-point position since begin_resample
 	float *inst_threshold;       // [max_instances] db_to_linear(playback_disable_threshold_db)
 	float threshold_default;     // db_to_linear(-80 dB), evaluated on the host like the reference does (audio_spatializer.cpp:465)
 	int32_t max_voices;
+};
+
+// one device-resident PCM source (gas_source_set)
+struct SourceDesc {
+	const gas_frame *pcm;
+	int32_t n_frames;
+	int32_t loop;
+	float sample_rate;
+	int32_t pad;
 };
 
 // what calculate_spatialization derives from a listener alone (computed once per listener upload)
@@ -257,7 +269,12 @@ struct gas_ctx {
 	int replicas = 8;           // GAS_K2_REPLICAS (1 = K2 adds straight into the bus buffers)
 	gas_emitter *d_emitters = nullptr;
 	gas_listener *d_listeners = nullptr;
-	ListenerPre *d_listener_pre = nullptr; // [GAS_MAX_LISTENERS] refreshed on the gain stream behind every listener upload
+	ListenerPre *d_listener_pre = nullptr;
+	SourceDesc *d_sources = nullptr;        // [max_sources] device-resident PCM sources
+	std::vector<SourceDesc> h_sources;      // host copy (device pointers owned by the context)
+	int32_t max_sources = 0;
+	gas_frame *d_rs_rows = nullptr;         // [max_voices][max_frames] rows the resampler hands to the stream form (gas_mix_block_resident)
+	int32_t *d_rs_mixed = nullptr;          // [max_voices] // [GAS_MAX_LISTENERS] refreshed on the gain stream behind every listener upload
 	gas_area *d_areas = nullptr;
 	int32_t max_areas = 0;
 	gas_params *d_params_out = nullptr;
@@ -398,6 +415,10 @@ cudaError_t launch_life_post(gas_ctx *ctx, int n_voices, const gas_voice *d_voic
 cudaError_t launch_threshold_set(gas_ctx *ctx, int n, const int32_t *d_ids, const float *d_lin, cudaStream_t st);
 cudaError_t launch_life_export(gas_ctx *ctx, int n, const int32_t *d_ids, gas_voice_life *d_out, cudaStream_t st);
 cudaError_t launch_life_import(gas_ctx *ctx, int n, const int32_t *d_ids, const gas_voice_life *d_in, cudaStream_t st);
+// gas_resample.cu
+cudaError_t launch_resample(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int frames, gas_frame *d_rows, int row_stride, int src_rows,
+		int32_t *d_mixed, cudaStream_t st);
+cudaError_t launch_voice_play(gas_ctx *ctx, int n, const int32_t *d_voices, const int32_t *d_sources, const int32_t *d_starts, cudaStream_t st);
 // gas_single.cu: channel < 0 = process_frames, else mix_channel of that pair
 cudaError_t launch_single_voice(gas_ctx *ctx, int instance, int voice, int channel, gas_frame *d_out, const gas_frame *d_src, int frames, cudaStream_t st);
 // gas_state.cu

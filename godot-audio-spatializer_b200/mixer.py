@@ -233,6 +233,36 @@ class Mixer:
         self._ck(self._lib.gas_mix_block_device(self._ctx, int(n_voices), C.c_void_p(d_voices), C.c_void_p(d_src), int(src_rows),
                                                 int(src_row_stride), int(frames), C.c_void_p(d_bus_out), C.c_void_p(d_peaks)))
 
+    def source_set(self, slot, pcm, sample_rate, loop=False):
+        """gas_source_set: a PCM clip (float32 [n, 2]) becomes device-resident source `slot`."""
+        p = np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1, 2))
+        self._ck(self._lib.gas_source_set(self._ctx, int(slot), _ptr(p), p.shape[0], float(sample_rate), int(bool(loop))))
+
+    def voice_play(self, voices, sources, start_frames=None):
+        """gas_voice_play: begin_resample of voices[i] on sources[i] from start_frames[i]."""
+        v = _arr(voices, np.int32).reshape(-1)
+        s = np.broadcast_to(_arr(sources, np.int32), v.shape).copy()
+        st = None if start_frames is None else np.broadcast_to(_arr(start_frames, np.int32), v.shape).copy()
+        self._ck(self._lib.gas_voice_play(self._ctx, v.size, _ptr(v), _ptr(s), _ptr(st) if st is not None else None))
+
+    def resample_block_device(self, n_voices, d_voices, frames, d_rows, row_stride, src_rows, d_mixed_frames):
+        """gas_resample_block_device: asynchronous on the mix stream, device pointers."""
+        self._ck(self._lib.gas_resample_block_device(self._ctx, int(n_voices), C.c_void_p(d_voices), int(frames), C.c_void_p(d_rows),
+                                                     int(row_stride), int(src_rows), C.c_void_p(d_mixed_frames)))
+
+    def mix_block_resident(self, voices, frames):
+        """gas_mix_block_resident: resample the voices' resident sources and mix them through the stream form.  Returns (bus, status)."""
+        v = _arr(voices, abi.voice).reshape(-1)
+        bus = np.zeros((self.num_buses, self.channels, frames, 2), dtype=np.float32)
+        status = np.zeros(max(v.size, 1), dtype=np.int32)
+        self._ck(self._lib.gas_mix_block_resident(self._ctx, v.size, _ptr(v), int(frames), _ptr(bus), _ptr(status)))
+        return bus, status[: v.size]
+
+    def mix_block_resident_host_ptr(self, n_voices, voices_ptr, frames, bus_ptr, status_ptr=0):
+        """gas_mix_block_resident with caller-owned (pinned) host buffers: bench.py's e2e leg."""
+        self._ck(self._lib.gas_mix_block_resident(self._ctx, int(n_voices), C.c_void_p(voices_ptr), int(frames), C.c_void_p(bus_ptr),
+                                                  C.c_void_p(status_ptr) if status_ptr else None))
+
     def step_device(self, d_src=0, src_row_stride=0, next=None):
         """gas_step_device: streams the block planned by the previous call from d_src and prepares `next` in the same launch.
         next: dict(n_voices, d_voices, src_rows, frames, d_bus_out[, d_peaks, n_emitters, d_emitters]) of device pointers, or None

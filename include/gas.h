@@ -406,6 +406,27 @@ GAS_API int gas_mix_block_stream(gas_ctx *ctx, int32_t n_voices, const gas_voice
 		int32_t frames, const int32_t *mixed_frames, gas_frame *bus_out, int32_t *status_out);
 GAS_API int gas_mix_block_stream_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices, const gas_frame *d_src, int32_t src_rows,
 		int32_t src_row_stride, int32_t frames, const int32_t *d_mixed_frames, gas_frame *d_bus_out, int32_t *d_status_out);
+/* ---- device-resident sources + the resampler in front of the path --------------------------------------
+ * What `playback->stream_playback->mix(&buf[LOOKAHEAD_BUFFER_SIZE], pitch_scale, p_buffer_size)` (audio_spatializer.cpp:375-378)
+ * does for a resampled PCM stream, on the device: upstream AudioStreamPlaybackResampled::mix (16.16 fixed-point offset, 4-tap cubic
+ * interpolation, 128-frame internal buffer; restated from Godot 4.x as recalled — the engine is not part of the reference tree) at
+ * `sample_rate * pitch_scale / mix_rate`, pitch_scale being the instance's current SpatializerParameters::pitch_scale (Doppler
+ * included).  With resident sources a block needs no frames from the host: only the emitters travel.
+ *   gas_source_set     copies a PCM clip (AudioFrames at sample_rate, >= 128 frames; loop = wrap over the whole clip) into HBM as
+ *                      source `slot` (0..4095); n_frames = 0 frees the slot.  Synchronous.
+ *   gas_voice_play     AudioStreamPlaybackResampled::begin_resample for n voices: voice i plays sources[i] (-1 = none) from
+ *                      start_frames[i] (NULL = 0) with a cleared interpolation history.  Call it next to gas_voice_init.
+ *   gas_resample_block_device  row voices[j].src_row of d_rows receives `frames` new frames of voice j and d_mixed_frames[j] the
+ *                      number of valid ones (< frames once the clip has ended, upstream's end rule): exactly the inputs of
+ *                      gas_mix_block_stream_device.  Asynchronous on the mix stream.
+ *   gas_mix_block_resident     resample + gas_mix_block_stream in one synchronous call with host voice descriptors: src_row of a
+ *                      voice only names its row in the context's internal row buffer (use 0..n_voices-1). */
+GAS_API int gas_source_set(gas_ctx *ctx, int32_t slot, const gas_frame *frames, int32_t n_frames, float sample_rate, int32_t loop);
+GAS_API int gas_voice_play(gas_ctx *ctx, int32_t n, const int32_t *voices, const int32_t *sources, const int32_t *start_frames);
+GAS_API int gas_resample_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices, int32_t frames, gas_frame *d_rows,
+		int32_t row_stride, int32_t src_rows, int32_t *d_mixed_frames);
+GAS_API int gas_mix_block_resident(gas_ctx *ctx, int32_t n_voices, const gas_voice *voices, int32_t frames, gas_frame *bus_out,
+		int32_t *status_out);
 /* AudioSpatializerInstance::set_playback_disable_threshold_db (audio_spatializer.cpp:576-582; default -80, reset by
  * gas_instance_init). */
 GAS_API int gas_set_playback_disable_threshold_db(gas_ctx *ctx, int32_t n, const int32_t *instances, const float *db);

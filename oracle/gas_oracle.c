@@ -1558,3 +1558,127 @@ size_t orc_sizeof(int32_t id) {
 		default: return 0;
 	}
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * The resampler in front of the path: what `playback->stream_playback->mix(&buf[64], pitch_scale, n)`
+ * (reference audio_spatializer.cpp:375-378) runs for a resampled stream — upstream
+ * AudioStreamPlaybackResampled::begin_resample / ::mix (servers/audio/audio_stream.cpp), restated literally from Godot
+ * 4.x AS RECALLED: the engine is not in the reference tree, so THIS PART OF THE ORACLE IS NOT PINNED by reference code
+ * (parity for it means GPU == this restatement).  The stream behind it is plain PCM the way AudioStreamPlaybackWAV
+ * delivers it through _mix_internal: forward, optional loop over the whole stream, silence and `active = false` after
+ * the end.
+ * ------------------------------------------------------------------------------------------- */
+#define ORC_FP_BITS 16
+#define ORC_FP_LEN (1 << ORC_FP_BITS)
+#define ORC_FP_MASK (ORC_FP_LEN - 1)
+#define ORC_INTERNAL_BUFFER_LEN 128
+#define ORC_CUBIC_INTERP_HISTORY 4
+
+struct orc_resampler {
+	gas_frame internal_buffer[ORC_INTERNAL_BUFFER_LEN + ORC_CUBIC_INTERP_HISTORY];
+	unsigned int internal_buffer_end; /* upstream: unsigned; -1 = the buffer holds no end of stream */
+	uint64_t mix_offset;
+	const gas_frame *pcm;
+	int n_frames, loop;
+	long cursor; /* next source frame _mix_internal delivers */
+	int playing;
+	float sample_rate;
+};
+
+/* AudioStreamPlaybackWAV-like _mix_internal: up to n frames; after the end of a non-looping stream the rest is silence,
+ * the playback stops and the count of real frames is returned */
+static int orc_rs_mix_internal(orc_resampler *r, gas_frame *buf, int n) {
+	int mixed = 0;
+	for (int i = 0; i < n; i++) {
+		if (r->cursor >= r->n_frames) {
+			if (r->loop && r->n_frames > 0) {
+				r->cursor = 0;
+			} else {
+				r->playing = 0;
+				for (; i < n; i++) {
+					buf[i].l = buf[i].r = 0.f;
+				}
+				return mixed;
+			}
+		}
+		buf[i] = r->pcm[r->cursor++];
+		mixed++;
+	}
+	return mixed;
+}
+
+orc_resampler *orc_resampler_begin(const gas_frame *pcm, int n_frames, int loop, float sample_rate, int start_frame) {
+	orc_resampler *r = (orc_resampler *)calloc(1, sizeof(orc_resampler));
+	if (!r) {
+		return NULL;
+	}
+	r->pcm = pcm;
+	r->n_frames = n_frames;
+	r->loop = loop;
+	r->sample_rate = sample_rate;
+	r->cursor = start_frame;
+	r->playing = 1;
+	r->internal_buffer_end = (unsigned int)-1;
+	/* begin_resample(): clear the cubic interpolation history, mix the first buffer (its return value is not looked at) */
+	for (int i = 0; i < ORC_CUBIC_INTERP_HISTORY; i++) {
+		r->internal_buffer[i].l = r->internal_buffer[i].r = 0.f;
+	}
+	orc_rs_mix_internal(r, r->internal_buffer + ORC_CUBIC_INTERP_HISTORY, ORC_INTERNAL_BUFFER_LEN);
+	r->mix_offset = 0;
+	return r;
+}
+
+void orc_resampler_free(orc_resampler *r) { free(r); }
+
+int orc_resampler_mix(orc_resampler *r, gas_frame *p_buffer, float p_rate_scale, float target_rate, int p_frames) {
+	const float playback_speed_scale = 1.0f;
+	uint64_t mix_increment = (uint64_t)(((r->sample_rate * p_rate_scale * playback_speed_scale) / (double)target_rate) * (double)ORC_FP_LEN);
+	int mixed_frames_total = -1;
+	int i;
+	for (i = 0; i < p_frames; i++) {
+		uint32_t idx = ORC_CUBIC_INTERP_HISTORY + (uint32_t)(r->mix_offset >> ORC_FP_BITS);
+		float mu = (r->mix_offset & ORC_FP_MASK) / (float)ORC_FP_LEN;
+		gas_frame y0 = r->internal_buffer[idx - 3];
+		gas_frame y1 = r->internal_buffer[idx - 2];
+		gas_frame y2 = r->internal_buffer[idx - 1];
+		gas_frame y3 = r->internal_buffer[idx - 0];
+		if (idx >= r->internal_buffer_end && mixed_frames_total == -1) {
+			mixed_frames_total = i;
+		}
+		float mu2 = mu * mu;
+		float h11 = mu2 * (mu - 1);
+		float z = mu2 - h11;
+		float h01 = z - h11;
+		float h10 = mu - z;
+		/* p_buffer[i] = y1 + (y2 - y1) * h01 + ((y2 - y0) * h10 + (y3 - y1) * h11) * 0.5; */
+		{
+			float al = (y2.l - y1.l) * h01, ar = (y2.r - y1.r) * h01;
+			float bl = ((y2.l - y0.l) * h10 + (y3.l - y1.l) * h11) * 0.5f, br = ((y2.r - y0.r) * h10 + (y3.r - y1.r) * h11) * 0.5f;
+			p_buffer[i].l = (y1.l + al) + bl;
+			p_buffer[i].r = (y1.r + ar) + br;
+		}
+		r->mix_offset += mix_increment;
+		while ((r->mix_offset >> ORC_FP_BITS) >= ORC_INTERNAL_BUFFER_LEN) {
+			for (int k = 0; k < ORC_CUBIC_INTERP_HISTORY; k++) {
+				r->internal_buffer[k] = r->internal_buffer[ORC_INTERNAL_BUFFER_LEN + k];
+			}
+			if (r->playing) {
+				int mixed_frames = orc_rs_mix_internal(r, r->internal_buffer + ORC_CUBIC_INTERP_HISTORY, ORC_INTERNAL_BUFFER_LEN);
+				if (mixed_frames != ORC_INTERNAL_BUFFER_LEN) {
+					r->internal_buffer_end = (unsigned int)mixed_frames;
+				} else {
+					r->internal_buffer_end = (unsigned int)-1;
+				}
+			} else {
+				for (int j = 0; j < ORC_INTERNAL_BUFFER_LEN; j++) {
+					r->internal_buffer[j + ORC_CUBIC_INTERP_HISTORY].l = r->internal_buffer[j + ORC_CUBIC_INTERP_HISTORY].r = 0.f;
+				}
+			}
+			r->mix_offset -= ((uint64_t)ORC_INTERNAL_BUFFER_LEN << ORC_FP_BITS);
+		}
+	}
+	if (mixed_frames_total == -1 && i == p_frames) {
+		mixed_frames_total = p_frames;
+	}
+	return mixed_frames_total;
+}

@@ -102,6 +102,13 @@ double orc_last_gain_seconds(const orc_world *w);
 int orc_max_threads(void);
 size_t orc_sizeof(int32_t struct_id); /* same ids as gas_abi_sizeof */
 
+/* The resampler in front of the path (upstream AudioStreamPlaybackResampled over plain PCM, restated AS RECALLED: not pinned by
+ * reference code, see gas_oracle.c).  One object per playing voice; pcm must outlive it. */
+typedef struct orc_resampler orc_resampler;
+orc_resampler *orc_resampler_begin(const gas_frame *pcm, int n_frames, int loop, float sample_rate, int start_frame);
+int orc_resampler_mix(orc_resampler *r, gas_frame *out, float rate_scale, float target_rate, int frames);
+void orc_resampler_free(orc_resampler *r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,9 @@ def load():
         "orc_process_frames_3d": (None, [_vp, _vp, _f32, _vp, _vp, C.c_int]),
         "orc_mix_channel_3d": (None, [_vp, _vp, _f32, C.c_int, _vp, _vp, C.c_int]),
         "orc_process_frames_effect": (None, [_vp, _vp, _f32, _vp, _vp, C.c_int]),
+        "orc_resampler_begin": (_vp, [_vp, C.c_int, C.c_int, _f32, C.c_int]),
+        "orc_resampler_mix": (C.c_int, [_vp, _vp, _f32, _f32, C.c_int]),
+        "orc_resampler_free": (None, [_vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -253,6 +256,33 @@ class OracleMixer:
     @property
     def last_gain_seconds(self):
         return float(self._lib.orc_last_gain_seconds(self._w))
+
+
+class Resampler:
+    """upstream AudioStreamPlaybackResampled over PCM (oracle/gas_oracle.c, recalled): one playing voice."""
+
+    def __init__(self, pcm, sample_rate, loop=False, start_frame=0):
+        self._lib = load()
+        self._pcm = np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1, 2))  # kept alive: the C side holds the pointer
+        self._r = self._lib.orc_resampler_begin(_ptr(self._pcm), self._pcm.shape[0], int(bool(loop)), float(sample_rate), int(start_frame))
+        if not self._r:
+            raise OracleError("orc_resampler_begin failed")
+
+    def mix(self, frames, rate_scale, target_rate):
+        out = np.zeros((frames, 2), dtype=np.float32)
+        n = self._lib.orc_resampler_mix(self._r, _ptr(out), float(rate_scale), float(target_rate), int(frames))
+        return out, n
+
+    def close(self):
+        if self._r:
+            self._lib.orc_resampler_free(self._r)
+            self._r = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def max_threads():
