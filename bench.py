@@ -822,14 +822,17 @@ def gpu_arm(args):
     # control warps).  Consecutive launches overlap (programmatic dependent launch), so its average launch duration over the
     # timed region is the timed region divided by its launches; the isolated reading (event-record nodes around the kernel in
     # a second, profiled capture, which serialise the launches) is reported beside it.
-    achieved = bytes_launch / (step_us * 1e-6) / 1e9
+    # (block-call form: the step is four kernels, so the streaming kernel's own duration is the isolated reading)
+    launch_us = k2_us if CLASSIC else step_us
+    achieved = bytes_launch / (launch_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "k_step (streaming of block k + gains and plan of block k+1)" if not CLASSIC else "k_step (streaming only)",
-                "us_per_launch": step_us, "algorithmic_bytes_per_launch": bytes_launch, "launches_in_timed_region": K,
+                "kernel": "k_step (streaming of block k + gains and plan of block k+1)" if not CLASSIC else
+                          "k_step without control work (block-call form: gains, plan and streaming are separate kernels)",
+                "us_per_launch": launch_us, "algorithmic_bytes_per_launch": bytes_launch, "launches_in_timed_region": K,
                 "peak_source": peak_src,
                 "timing": "CUDA events on the mix stream around the timed region / launches of the kernel (launches overlap by "
                           "programmatic dependent launch, so the per-launch average IS the step time)",
-                "step_frac_of_hbm_peak": achieved / peak,
+                "step_frac_of_hbm_peak": bytes_launch / (step_us * 1e-6) / 1e9 / peak,
                 "isolated": {"note": "same kernel between event-record nodes in a profiled capture of the same steps (the nodes serialise "
                                      "the launches and read ~2.7 us by themselves: event_pair_overhead_us)",
                              "us_per_launch": k2_us, "frac": bytes_launch / (k2_us * 1e-6) / 1e9 / peak,
