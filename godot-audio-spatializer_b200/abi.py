@@ -51,6 +51,9 @@ voice_state = np.dtype([("prev_mix_volumes", f4, (MAX_CHANNELS_PER_BUS, 2)),
                         ("filter_processors", processor_state, (2 * MAX_CHANNELS_PER_BUS,)),
                         ("effect_history", f4, (MAX_EFFECTS, 2, MAX_FILTER_STAGES, 4))], align=True)
 voice_life = np.dtype([("lookahead", frame, (LOOKAHEAD_BUFFER_SIZE,)), ("flags", u4)], align=True)
+bus_desc = np.dtype([("volume_db", f4), ("mute", i4), ("solo", i4), ("send", i4)], align=True)  # gas_bus_desc
+step_next = np.dtype([("n_emitters", i4), ("d_emitters", np.uint64), ("n_voices", i4), ("d_voices", np.uint64), ("src_rows", i4), ("frames", i4),
+                      ("d_bus_out", np.uint64), ("d_peaks", np.uint64)], align=True)  # gas_step_next (pointers as 64-bit integers)
 VOICE_ACTIVE, VOICE_HAS_FRAMES = 1, 2
 STATUS_CLASS_OVERFLOW = 1
 config = np.dtype([("device", i4), ("max_instances", i4), ("max_voices", i4), ("max_frames", i4),
@@ -59,7 +62,7 @@ config = np.dtype([("device", i4), ("max_instances", i4), ("max_voices", i4), ("
 
 # gas_struct_id order (include/gas.h)
 STRUCT_IDS = [frame, effect, effect_chain, spatializer, listener, area, emitter, params, voice,
-              processor_state, voice_state, config, voice_life]
+              processor_state, voice_state, config, voice_life, bus_desc, step_next]
 
 
 def check_layout(sizeof_fn, who):

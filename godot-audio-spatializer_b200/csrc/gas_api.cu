@@ -344,6 +344,8 @@ size_t gas_abi_sizeof(int32_t id) {
 		case GAS_STRUCT_VOICE_STATE: return sizeof(gas_voice_state);
 		case GAS_STRUCT_CONFIG: return sizeof(gas_config);
 		case GAS_STRUCT_VOICE_LIFE: return sizeof(gas_voice_life);
+		case GAS_STRUCT_BUS_DESC: return sizeof(gas_bus_desc);
+		case GAS_STRUCT_STEP_NEXT: return sizeof(gas_step_next);
 		default: return 0;
 	}
 }
@@ -489,6 +491,10 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 	ALLOC(ctx->t.vs_src, V);
 	ALLOC(ctx->t.vs_start, V);
 	ALLOC(ctx->t.vs_pos, V);
+	for (int b = 0; b < GAS_MAX_BUSES; b++) {
+		ctx->bus_volume_lin[b] = 1.0f;
+		ctx->bus_send[b] = 0;
+	}
 	ctx->max_sources = 4096;
 	ALLOC(ctx->d_sources, (size_t)ctx->max_sources);
 	ctx->h_sources.assign(ctx->max_sources, SourceDesc{});
@@ -1128,6 +1134,62 @@ int gas_mix_block_stream_device(gas_ctx *ctx, int32_t n_voices, const gas_voice 
 		return gas_fail(ctx, GAS_ERR_INVALID, "gas_mix_block_stream_device: source rows must be 8-byte, bus buffers 16-byte aligned");
 	}
 	return stream_core(ctx, n_voices, d_voices, d_src, src_rows, src_row_stride, frames, d_mixed_frames, d_bus_out, d_status_out);
+}
+
+// ---- bus graph after the mix --------------------------------------------------------------------
+int gas_bus_layout_set(gas_ctx *ctx, int32_t n_buses, const gas_bus_desc *buses) {
+	ENTER(ctx);
+	if (n_buses != ctx->cfg.num_buses || !buses || ctx->capturing) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_bus_layout_set: one descriptor per bus of the context (%d), not while capturing", ctx->cfg.num_buses);
+	}
+	// upstream AudioServer::_mix_step: with any bus soloed, only soloed buses and the buses on their send chains are audible
+	bool solo_mode = false, soloed[GAS_MAX_BUSES] = {};
+	int send[GAS_MAX_BUSES] = {};
+	for (int b = 0; b < n_buses; b++) {
+		int t = buses[b].send;
+		send[b] = (b > 0 && t >= 0 && t < b) ? t : 0; // an invalid send (unknown bus, or one that is not to the left) goes to Master
+		solo_mode = solo_mode || buses[b].solo != 0;
+	}
+	if (solo_mode) {
+		for (int b = 0; b < n_buses; b++) {
+			if (buses[b].solo) {
+				int i = b;
+				soloed[i] = true;
+				while (i != 0) {
+					i = send[i];
+					soloed[i] = true;
+				}
+			}
+		}
+	}
+	for (int b = 0; b < n_buses; b++) {
+		float v = expf(buses[b].volume_db * (float)0.11512925464970228420089957273422); // Math::db_to_linear(float)
+		if (solo_mode ? !soloed[b] : buses[b].mute != 0) {
+			v = 0.0f;
+		}
+		ctx->bus_volume_lin[b] = v;
+		ctx->bus_send[b] = send[b];
+	}
+	return GAS_OK;
+}
+
+int gas_bus_graph_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames) {
+	ENTER(ctx);
+	if (!d_bus || frames < 2 || (frames & 1) || frames > ctx->cfg.max_frames || ((uintptr_t)d_bus & 15u)) {
+		return gas_fail(ctx, GAS_ERR_INVALID, "gas_bus_graph_device: bad buffer or frame count");
+	}
+	int st = join_voice_stream(ctx); // voice-parallel kernels of pipelined steps may still be adding to the buffers
+	if (st) {
+		return st;
+	}
+	if (ctx->comm_pending) {
+		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_comm_done, 0));
+		ctx->comm_pending = false;
+	}
+	GAS_CUDA(ctx, launch_bus_graph(ctx, d_bus, frames, ctx->s_mix));
+	GAS_CUDA(ctx, cudaEventRecord(ctx->ev_mix_done, ctx->s_mix));
+	ctx->mix_pending = true;
+	return GAS_OK;
 }
 
 // ---- device-resident sources + resampler -----------------------------------------------------------

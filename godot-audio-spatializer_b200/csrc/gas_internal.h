@@ -270,6 +270,8 @@ struct gas_ctx {
 	gas_emitter *d_emitters = nullptr;
 	gas_listener *d_listeners = nullptr;
 	ListenerPre *d_listener_pre = nullptr;
+	float bus_volume_lin[GAS_MAX_BUSES];    // bus graph (gas_bus_layout_set): linear volume per bus after mute / solo, 1 by default
+	int32_t bus_send[GAS_MAX_BUSES];        // send target per bus (0 = Master by default)
 	SourceDesc *d_sources = nullptr;        // [max_sources] device-resident PCM sources
 	std::vector<SourceDesc> h_sources;      // host copy (device pointers owned by the context)
 	int32_t max_sources = 0;
@@ -415,6 +417,8 @@ cudaError_t launch_life_post(gas_ctx *ctx, int n_voices, const gas_voice *d_voic
 cudaError_t launch_threshold_set(gas_ctx *ctx, int n, const int32_t *d_ids, const float *d_lin, cudaStream_t st);
 cudaError_t launch_life_export(gas_ctx *ctx, int n, const int32_t *d_ids, gas_voice_life *d_out, cudaStream_t st);
 cudaError_t launch_life_import(gas_ctx *ctx, int n, const int32_t *d_ids, const gas_voice_life *d_in, cudaStream_t st);
+// gas_bus.cu
+cudaError_t launch_bus_graph(gas_ctx *ctx, gas_frame *d_bus, int frames, cudaStream_t st);
 // gas_resample.cu
 cudaError_t launch_resample(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int frames, gas_frame *d_rows, int row_stride, int src_rows,
 		int32_t *d_mixed, cudaStream_t st);

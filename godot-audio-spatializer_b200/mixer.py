@@ -233,6 +233,20 @@ class Mixer:
         self._ck(self._lib.gas_mix_block_device(self._ctx, int(n_voices), C.c_void_p(d_voices), C.c_void_p(d_src), int(src_rows),
                                                 int(src_row_stride), int(frames), C.c_void_p(d_bus_out), C.c_void_p(d_peaks)))
 
+    def bus_layout_set(self, buses):
+        """gas_bus_layout_set: buses = list of dict(volume_db=0.0, mute=False, solo=False, send=0), one per bus of the context."""
+        d = np.zeros(len(buses), dtype=abi.bus_desc)
+        for i, b in enumerate(buses):
+            d[i]["volume_db"] = b.get("volume_db", 0.0)
+            d[i]["mute"] = int(bool(b.get("mute", False)))
+            d[i]["solo"] = int(bool(b.get("solo", False)))
+            d[i]["send"] = int(b.get("send", 0))
+        self._ck(self._lib.gas_bus_layout_set(self._ctx, d.size, _ptr(d)))
+
+    def bus_graph_device(self, d_bus, frames):
+        """gas_bus_graph_device: the bus graph in place on device-resident bus buffers, asynchronous on the mix stream."""
+        self._ck(self._lib.gas_bus_graph_device(self._ctx, C.c_void_p(d_bus), int(frames)))
+
     def source_set(self, slot, pcm, sample_rate, loop=False):
         """gas_source_set: a PCM clip (float32 [n, 2]) becomes device-resident source `slot`."""
         p = np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1, 2))

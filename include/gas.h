@@ -259,7 +259,9 @@ typedef enum gas_struct_id {
 	GAS_STRUCT_PROCESSOR_STATE = 9,
 	GAS_STRUCT_VOICE_STATE = 10,
 	GAS_STRUCT_CONFIG = 11,
-	GAS_STRUCT_VOICE_LIFE = 12
+	GAS_STRUCT_VOICE_LIFE = 12,
+	GAS_STRUCT_BUS_DESC = 13,
+	GAS_STRUCT_STEP_NEXT = 14
 } gas_struct_id;
 GAS_API size_t gas_abi_sizeof(int32_t struct_id);
 GAS_API void gas_config_defaults(gas_config *cfg);
@@ -410,6 +412,24 @@ GAS_API int gas_mix_block_stream(gas_ctx *ctx, int32_t n_voices, const gas_voice
 		int32_t frames, const int32_t *mixed_frames, gas_frame *bus_out, int32_t *status_out);
 GAS_API int gas_mix_block_stream_device(gas_ctx *ctx, int32_t n_voices, const gas_voice *d_voices, const gas_frame *d_src, int32_t src_rows,
 		int32_t src_row_stride, int32_t frames, const int32_t *d_mixed_frames, gas_frame *d_bus_out, int32_t *d_status_out);
+/* ---- the bus graph after the mix -------------------------------------------------------------------------
+ * What upstream AudioServer::_mix_step does with the bus buffers after every playback has been mixed into them (reference
+ * README.md:98-100 steps 3-5; the demo's default_bus_layout.tres sends its Reverb bus to Master): from the last bus to the first,
+ * each bus is scaled by its volume — 0 when muted, or, if any bus is soloed, when it is neither soloed nor on a soloed bus's send
+ * chain — and added to its send bus; bus 0 (Master) ends up holding what the audio driver gets.  Bus effects are not part of the
+ * library (a caller with effects on a bus runs them between two calls); restated from Godot 4.x as recalled.
+ *   gas_bus_layout_set    one descriptor per bus of the context (AudioBusLayout: volume_db, mute, solo, send as bus index; a send
+ *                         that is not to a bus on the left goes to Master, like upstream)
+ *   gas_bus_graph_device  d_bus [num_buses][channel_count][frames] in place, asynchronous on the mix stream; with sharded voices call
+ *                         it on the reduced sums */
+typedef struct gas_bus_desc {
+	float volume_db;
+	int32_t mute;
+	int32_t solo;
+	int32_t send;
+} gas_bus_desc;
+GAS_API int gas_bus_layout_set(gas_ctx *ctx, int32_t n_buses, const gas_bus_desc *buses);
+GAS_API int gas_bus_graph_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames);
 /* ---- device-resident sources + the resampler in front of the path --------------------------------------
  * What `playback->stream_playback->mix(&buf[LOOKAHEAD_BUFFER_SIZE], pitch_scale, p_buffer_size)` (audio_spatializer.cpp:375-378)
  * does for a resampled PCM stream, on the device: upstream AudioStreamPlaybackResampled::mix (16.16 fixed-point offset, 4-tap cubic

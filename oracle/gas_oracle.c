@@ -1555,6 +1555,8 @@ size_t orc_sizeof(int32_t id) {
 		case GAS_STRUCT_VOICE_STATE: return sizeof(gas_voice_state);
 		case GAS_STRUCT_CONFIG: return sizeof(gas_config);
 		case GAS_STRUCT_VOICE_LIFE: return sizeof(gas_voice_life);
+		case GAS_STRUCT_BUS_DESC: return sizeof(gas_bus_desc);
+		case GAS_STRUCT_STEP_NEXT: return sizeof(gas_step_next);
 		default: return 0;
 	}
 }
@@ -1681,4 +1683,59 @@ int orc_resampler_mix(orc_resampler *r, gas_frame *p_buffer, float p_rate_scale,
 		mixed_frames_total = p_frames;
 	}
 	return mixed_frames_total;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * The bus graph after the mix: upstream AudioServer::_mix_step from "process send" on, restated from
+ * Godot 4.x AS RECALLED (not pinned by reference code): buses from the last to the first; volume = db_to_linear(volume_db),
+ * 0 when muted (no bus soloed) or not on a soloed chain (some bus soloed); buf *= volume; send buffer += buf.
+ * bus: [n_buses][channels][frames] AudioFrames, in place.
+ * ------------------------------------------------------------------------------------------- */
+void orc_bus_graph(int n_buses, int channels, int frames, const float *volume_db, const int32_t *mute, const int32_t *solo, const int32_t *send_in,
+		gas_frame *bus) {
+	int send[GAS_MAX_BUSES] = { 0 }, soloed[GAS_MAX_BUSES] = { 0 };
+	int solo_mode = 0;
+	for (int b = 0; b < n_buses; b++) {
+		int t = send_in[b];
+		send[b] = (b > 0 && t >= 0 && t < b) ? t : 0; /* an invalid send goes to Master */
+		if (solo[b]) {
+			solo_mode = 1;
+		}
+	}
+	if (solo_mode) {
+		for (int b = 0; b < n_buses; b++) {
+			if (solo[b]) {
+				int i = b;
+				soloed[i] = 1;
+				while (i != 0) {
+					i = send[i];
+					soloed[i] = 1;
+				}
+			}
+		}
+	}
+	for (int b = n_buses - 1; b >= 0; b--) {
+		float volume = orc_db_to_linear_f(volume_db[b]);
+		if (solo_mode) {
+			if (!soloed[b]) {
+				volume = 0.0f;
+			}
+		} else if (mute[b]) {
+			volume = 0.0f;
+		}
+		for (int k = 0; k < channels; k++) {
+			gas_frame *buf = bus + ((size_t)b * channels + k) * frames;
+			for (int j = 0; j < frames; j++) {
+				buf[j].l *= volume;
+				buf[j].r *= volume;
+			}
+			if (b > 0) {
+				gas_frame *target = bus + ((size_t)send[b] * channels + k) * frames;
+				for (int j = 0; j < frames; j++) {
+					target[j].l += buf[j].l;
+					target[j].r += buf[j].r;
+				}
+			}
+		}
+	}
 }

@@ -102,6 +102,10 @@ double orc_last_gain_seconds(const orc_world *w);
 int orc_max_threads(void);
 size_t orc_sizeof(int32_t struct_id); /* same ids as gas_abi_sizeof */
 
+/* The bus graph after the mix (upstream AudioServer::_mix_step, restated AS RECALLED): volume / mute / solo / send routing in place. */
+void orc_bus_graph(int n_buses, int channels, int frames, const float *volume_db, const int32_t *mute, const int32_t *solo, const int32_t *send,
+		gas_frame *bus);
+
 /* The resampler in front of the path (upstream AudioStreamPlaybackResampled over plain PCM, restated AS RECALLED: not pinned by
  * reference code, see gas_oracle.c).  One object per playing voice; pcm must outlive it. */
 typedef struct orc_resampler orc_resampler;

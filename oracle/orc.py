@@ -75,6 +75,7 @@ def load():
         "orc_process_frames_3d": (None, [_vp, _vp, _f32, _vp, _vp, C.c_int]),
         "orc_mix_channel_3d": (None, [_vp, _vp, _f32, C.c_int, _vp, _vp, C.c_int]),
         "orc_process_frames_effect": (None, [_vp, _vp, _f32, _vp, _vp, C.c_int]),
+        "orc_bus_graph": (None, [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
         "orc_resampler_begin": (_vp, [_vp, C.c_int, C.c_int, _f32, C.c_int]),
         "orc_resampler_mix": (C.c_int, [_vp, _vp, _f32, _f32, C.c_int]),
         "orc_resampler_free": (None, [_vp]),
@@ -256,6 +257,20 @@ class OracleMixer:
     @property
     def last_gain_seconds(self):
         return float(self._lib.orc_last_gain_seconds(self._w))
+
+
+def bus_graph(bus, buses):
+    """upstream bus graph after the mix on bus [n_buses, channels, frames, 2] (a copy is returned); buses as for Mixer.bus_layout_set."""
+    lib = load()
+    out = np.ascontiguousarray(np.asarray(bus, dtype=np.float32)).copy()
+    nb, ch, fr = out.shape[:3]
+    vol = np.array([b.get("volume_db", 0.0) for b in buses], dtype=np.float32)
+    mute = np.array([int(bool(b.get("mute", False))) for b in buses], dtype=np.int32)
+    solo = np.array([int(bool(b.get("solo", False))) for b in buses], dtype=np.int32)
+    send = np.array([int(b.get("send", 0)) for b in buses], dtype=np.int32)
+    assert len(buses) == nb
+    lib.orc_bus_graph(nb, ch, fr, _ptr(vol), _ptr(mute), _ptr(solo), _ptr(send), _ptr(out))
+    return out
 
 
 class Resampler:
