@@ -1192,6 +1192,25 @@ int gas_bus_graph_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames) {
 	return GAS_OK;
 }
 
+int gas_bus_graph(gas_ctx *ctx, gas_frame *bus_inout, int32_t frames) {
+	{
+		ENTER(ctx);
+		if (!bus_inout || frames < 2 || (frames & 1) || frames > ctx->cfg.max_frames || ctx->capturing) {
+			return gas_fail(ctx, GAS_ERR_INVALID, "gas_bus_graph: bad buffer or frame count (or capture in progress)");
+		}
+		const size_t bytes = (size_t)ctx->cfg.num_buses * (ctx->cfg.speaker_mode + 1) * frames * sizeof(gas_frame);
+		int st = join_voice_stream(ctx);
+		if (st) {
+			return st;
+		}
+		GAS_CUDA(ctx, cudaMemcpyAsync(ctx->d_bus, bus_inout, bytes, cudaMemcpyHostToDevice, ctx->s_mix));
+		GAS_CUDA(ctx, launch_bus_graph(ctx, ctx->d_bus, frames, ctx->s_mix));
+		GAS_CUDA(ctx, cudaMemcpyAsync(bus_inout, ctx->d_bus, bytes, cudaMemcpyDeviceToHost, ctx->s_mix));
+	}
+	GAS_CUDA(ctx, cudaStreamSynchronize(ctx->s_mix));
+	return GAS_OK;
+}
+
 // ---- device-resident sources + resampler -----------------------------------------------------------
 int gas_source_set(gas_ctx *ctx, int32_t slot, const gas_frame *frames, int32_t n_frames, float sample_rate, int32_t loop) {
 	ENTER(ctx);

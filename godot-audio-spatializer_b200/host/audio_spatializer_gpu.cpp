@@ -549,6 +549,92 @@ bool BatchMixer::mix(int frames, const std::vector<const AudioFrame *> &sources,
 	return true;
 }
 
+bool BatchMixer::set_source(int slot, const AudioFrame *frames, int n_frames, float sample_rate, bool loop) {
+	GAS_FAIL_COND_V(!ctx, "no device context", false);
+	if (gas_source_set(ctx, slot, reinterpret_cast<const gas_frame *>(frames), n_frames, sample_rate, loop ? 1 : 0) != GAS_OK) {
+		set_last_error(gas_last_error(ctx));
+		return false;
+	}
+	return true;
+}
+
+bool BatchMixer::play_source(const Ref<SpatializerPlaybackData> &playback, int source_slot, int from_frame) {
+	GAS_FAIL_COND_V(!ctx, "no device context", false);
+	GAS_FAIL_COND_V(!playback || playback->voice_slot < 0, "Parameter \"p_playback\" is null.", false);
+	const int32_t v = playback->voice_slot, s = source_slot, f = from_frame;
+	if (gas_voice_play(ctx, 1, &v, &s, &f) != GAS_OK) {
+		set_last_error(gas_last_error(ctx));
+		return false;
+	}
+	return true;
+}
+
+bool BatchMixer::mix_resident(int frames, AudioFrame *bus_out, std::vector<Ref<SpatializerPlaybackData>> *finished) {
+	GAS_FAIL_COND_V(!ctx, "no device context", false);
+	std::vector<std::pair<Ref<AudioSpatializerInstance>, Ref<SpatializerPlaybackData>>> order;
+	std::vector<gas_voice> voices;
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		if (refuse_custom_dsp()) {
+			return false;
+		}
+		for (auto &ins : instances) {
+			if (!ins) {
+				continue;
+			}
+			for (auto &pb : ins->playbacks) {
+				gas_voice v;
+				v.voice = pb->voice_slot;
+				v.instance = ins->slot;
+				v.src_row = (int)voices.size(); // names the playback's row in the context's internal row buffer
+				v.flags = 0u;
+				voices.push_back(v);
+				order.emplace_back(ins, pb);
+			}
+		}
+		GAS_FAIL_COND_V(frames <= 0 || frames > cfg.max_frames || (frames & 1), "Condition \"p_frame_count != mix_buffer[ch].size()\" is true.", false);
+		std::vector<int32_t> status(voices.size() ? voices.size() : 1);
+		if (gas_mix_block_resident(ctx, (int)voices.size(), voices.data(), frames, reinterpret_cast<gas_frame *>(bus_out), status.data()) != GAS_OK) {
+			set_last_error(gas_last_error(ctx));
+			return false;
+		}
+		// _manage_playback_state (audio_spatializer.cpp:473-492): inactive playbacks leave the list
+		for (size_t i = 0; i < order.size(); i++) {
+			if (!(status[i] & GAS_VOICE_ACTIVE)) {
+				if (finished) {
+					finished->push_back(order[i].second);
+				}
+			} else {
+				order[i].second.reset();
+			}
+		}
+	}
+	for (auto &e : order) {
+		if (e.second) {
+			e.first->stop_playback_stream(e.second);
+		}
+	}
+	return true;
+}
+
+bool BatchMixer::set_bus_layout(const std::vector<gas_bus_desc> &layout) {
+	GAS_FAIL_COND_V(!ctx, "no device context", false);
+	if (gas_bus_layout_set(ctx, (int)layout.size(), layout.data()) != GAS_OK) {
+		set_last_error(gas_last_error(ctx));
+		return false;
+	}
+	return true;
+}
+
+bool BatchMixer::apply_bus_graph(int frames, AudioFrame *bus_inout) {
+	GAS_FAIL_COND_V(!ctx, "no device context", false);
+	if (gas_bus_graph(ctx, reinterpret_cast<gas_frame *>(bus_inout), frames) != GAS_OK) {
+		set_last_error(gas_last_error(ctx));
+		return false;
+	}
+	return true;
+}
+
 bool BatchMixer::voice_state(int voice_slot, gas_voice_state &out) {
 	int32_t v = voice_slot;
 	return ctx && gas_voice_state_export(ctx, 1, &v, &out) == GAS_OK;

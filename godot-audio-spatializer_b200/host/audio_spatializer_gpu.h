@@ -288,6 +288,17 @@ public:
 	// finished (optional) receives the playbacks dropped by this step.
 	bool mix_streams(int frames, const std::vector<const AudioFrame *> &sources, const std::vector<int> &counts, AudioFrame *bus_out,
 			std::vector<Ref<SpatializerPlaybackData>> *finished = nullptr);
+	// Device-resident PCM streams (gas_source_set / gas_voice_play / gas_mix_block_resident): an AudioStreamWAV-like clip is uploaded
+	// once; a playback started on it is resampled on the device (AudioStreamPlaybackResampled::mix at sample_rate x pitch_scale /
+	// mix_rate) and goes through the same lifecycle as mix_streams — no frames travel per block.  Every live playback must have
+	// been started with play_source before mix_resident is called.
+	bool set_source(int slot, const AudioFrame *frames, int n_frames, float sample_rate, bool loop);
+	bool play_source(const Ref<SpatializerPlaybackData> &playback, int source_slot, int from_frame = 0);
+	bool mix_resident(int frames, AudioFrame *bus_out, std::vector<Ref<SpatializerPlaybackData>> *finished = nullptr);
+	// AudioBusLayout: volume / mute / solo / send per bus (upstream AudioServer::_mix_step after the playbacks, README.md:98-100);
+	// apply_bus_graph runs that pass over host bus buffers [num_buses][channels][frames] in place.
+	bool set_bus_layout(const std::vector<gas_bus_desc> &layout);
+	bool apply_bus_graph(int frames, AudioFrame *bus_inout);
 	// the playbacks a mix() call expects sources for, in order (instances by slot, playbacks by start order)
 	std::vector<Ref<SpatializerPlaybackData>> playback_order() const;
 

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "gas_mix_block_stream_device": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "gas_bus_layout_set": (C.c_int, [_vp, _i32, _vp]),
     "gas_bus_graph_device": (C.c_int, [_vp, _vp, _i32]),
+    "gas_bus_graph": (C.c_int, [_vp, _vp, _i32]),
     "gas_source_set": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _i32]),
     "gas_voice_play": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "gas_resample_block_device": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp]),

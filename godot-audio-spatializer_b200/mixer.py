@@ -247,6 +247,12 @@ class Mixer:
         """gas_bus_graph_device: the bus graph in place on device-resident bus buffers, asynchronous on the mix stream."""
         self._ck(self._lib.gas_bus_graph_device(self._ctx, C.c_void_p(d_bus), int(frames)))
 
+    def bus_graph(self, bus):
+        """gas_bus_graph: the bus graph over host bus buffers [num_buses, channels, frames, 2]; returns the processed copy."""
+        b = np.ascontiguousarray(np.asarray(bus, dtype=np.float32)).copy()
+        self._ck(self._lib.gas_bus_graph(self._ctx, _ptr(b), int(b.shape[2])))
+        return b
+
     def source_set(self, slot, pcm, sample_rate, loop=False):
         """gas_source_set: a PCM clip (float32 [n, 2]) becomes device-resident source `slot`."""
         p = np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1, 2))

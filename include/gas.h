@@ -430,6 +430,8 @@ typedef struct gas_bus_desc {
 } gas_bus_desc;
 GAS_API int gas_bus_layout_set(gas_ctx *ctx, int32_t n_buses, const gas_bus_desc *buses);
 GAS_API int gas_bus_graph_device(gas_ctx *ctx, gas_frame *d_bus, int32_t frames);
+/* The same pass over host bus buffers (up, graph, down; synchronous). */
+GAS_API int gas_bus_graph(gas_ctx *ctx, gas_frame *bus_inout, int32_t frames);
 /* ---- device-resident sources + the resampler in front of the path --------------------------------------
  * What `playback->stream_playback->mix(&buf[LOOKAHEAD_BUFFER_SIZE], pitch_scale, p_buffer_size)` (audio_spatializer.cpp:375-378)
  * does for a resampled PCM stream, on the device: upstream AudioStreamPlaybackResampled::mix (16.16 fixed-point offset, 4-tap cubic

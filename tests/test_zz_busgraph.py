@@ -70,5 +70,6 @@ def test_cuda_bus_graph_matches_oracle_bit_for_bit(gas, orc, mode, B):
             m.bus_graph_device(d_bus.data_ptr(), F)
             m.sync()
             np.testing.assert_array_equal(d_bus.cpu().numpy(), orc.bus_graph(bus, lay))
+            np.testing.assert_array_equal(m.bus_graph(bus), orc.bus_graph(bus, lay))  # host-pointer form
         with pytest.raises(gas.GasError):
             m.bus_layout_set(layouts[0][:-1])  # one descriptor per bus of the context
