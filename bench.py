@@ -999,50 +999,52 @@ def resident_leg(args):
         tt = np.arange(n, dtype=np.float64)
         return (0.25 * np.sin(2 * np.pi * (80.0 + 23.0 * seed) * tt / rate)[:, None] + 0.02 * rs.randn(n, 2)).astype(np.float32)
 
-    # ---- self-check: 96 voices, 4 blocks, clips that end inside the run, against the oracle (stream form fed by the oracle's resampler) ----
+    # ---- self-check: 96 voices, 6 blocks, clips that end inside the run: the same calls on the CUDA mixer and on the oracle twin
+    # (upstream's resampler per voice + the stream form of the mix), compared block by block
     try:
-        Vc = 96
+        Vc, nblk = 96, 6
         cfg = dict(max_instances=Vc, max_voices=Vc, max_frames=F, num_buses=B, speaker_mode=w["speaker_mode"], mix_rate=w["mix_rate"])
         listeners = np.array([abi.identity_listener()], dtype=abi.listener)
         areas = np.array([synth.reverb_area(reverb_bus=1, amount=0.5, uniformity=0.0)], dtype=abi.area)
         clips = [clip(1400 + 173 * k_, 10 + k_) for k_ in range(6)]
         inst = np.arange(Vc, dtype=np.int32)
         voices = synth.make_voices(Vc)
-        ok_all, worst_all = True, 0.0
-        with gas.Mixer(**cfg) as m, orc.OracleMixer(**cfg) as o:
-            ems = [synth.make_emitters(Vc, block=b_, dt=F / w["mix_rate"], area_fraction=0.5) for b_ in range(4)]
-            for e_ in ems:
-                e_["pitch_scale"] = np.linspace(0.5, 2.0, Vc).astype(np.float32)
-            for mm in (m, o):
-                mm.spatializer_set(0, abi.spatializer_defaults(**w["spat"]))
-                mm.instance_init(inst, 0)
-                mm.gain_compute(ems[0], listeners, areas, want_params=False)
-                mm.instance_start(inst)
-                mm.voice_init(inst)
-            for k_ in range(6):
-                m.source_set(k_, clips[k_], 44100.0)
-            m.voice_play(inst, inst % 6)
-            rsm = [orc.Resampler(clips[i_ % 6], 44100.0) for i_ in range(Vc)]
-            active = np.ones(Vc, dtype=bool)
-            for b_ in range(4):
-                m.gain_compute(ems[b_], listeners, areas, want_params=False)
-                po = o.gain_compute(ems[b_], listeners, areas)
+        ems = [synth.make_emitters(Vc, block=b_, dt=F / w["mix_rate"], area_fraction=0.5) for b_ in range(nblk)]
+        for e_ in ems:
+            e_["pitch_scale"] = np.linspace(0.5, 2.0, Vc).astype(np.float32)
+
+        def play(mm):
+            mm.spatializer_set(0, abi.spatializer_defaults(**w["spat"]))
+            mm.instance_init(inst, 0)
+            mm.gain_compute(ems[0], listeners, areas, want_params=False)
+            mm.instance_start(inst)
+            mm.voice_init(inst)
+            for k_, c_ in enumerate(clips):
+                mm.source_set(k_, c_, 44100.0)
+            mm.voice_play(inst, inst % len(clips))
+            active, res = np.ones(Vc, dtype=bool), []
+            for b_ in range(nblk):
+                mm.gain_compute(ems[b_], listeners, areas, want_params=False)
                 live = voices[active].copy()
                 live["src_row"] = np.arange(live.size)
-                rows = np.zeros((max(live.size, 1), F, 2), dtype=np.float32)
-                mixed = np.zeros(max(live.size, 1), dtype=np.int32)
-                for r_, vv in enumerate(live["voice"]):
-                    rows[r_], mixed[r_] = rsm[vv].mix(F, float(po["pitch_scale"][vv]), w["mix_rate"])
-                want_bus, want_status = o.mix_block_stream(live, rows, mixed[: live.size], F)
-                got_bus, got_status = m.mix_block_resident(live, F)
-                ok, worst, _ = S.sample_close(got_bus, want_bus)
-                ok_all = ok_all and ok and bool(np.array_equal(got_status, want_status)) and bool(np.array_equal(S.routing(got_bus), S.routing(want_bus)))
-                worst_all = max(worst_all, worst)
-                alive = (want_status & abi.VOICE_ACTIVE) != 0
+                bus_, status_ = mm.mix_block_resident(live, F)
+                res.append((bus_, status_.copy()))
+                alive = (status_ & abi.VOICE_ACTIVE) != 0
                 idx = np.nonzero(active)[0]
                 active[idx[~alive]] = False
+            return res
+
+        with gas.Mixer(**cfg) as m, orc.OracleMixer(**cfg) as o:
+            got, want = play(m), play(o)
+        ok_all, worst_all = True, 0.0
+        for (gb, gs), (wb, ws) in zip(got, want):
+            same = gs.shape == ws.shape and bool(np.array_equal(gs, ws)) and gb.shape == wb.shape
+            ok, worst, _ = S.sample_close(gb, wb) if same else (False, float("inf"), 0)
+            ok_all = ok_all and same and ok and bool(np.array_equal(S.routing(gb), S.routing(wb)))
+            worst_all = max(worst_all, worst)
         out["parity_ok"] = bool(ok_all)
         out["parity_worst_abs_err"] = worst_all
+        out["parity_check"] = f"{Vc} voices x {nblk} blocks against the oracle twin (upstream resampler + stream form), clips ending inside the run"
     except Exception as ex:
         out["parity_ok"] = False
         out["parity_error"] = repr(ex)[:300]

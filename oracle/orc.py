@@ -234,6 +234,39 @@ class OracleMixer:
         self.last_peaks = peaks[: v.size]
         return bus, status[: v.size]
 
+    # ---- device-resident sources: the oracle twin of gas_source_set / gas_voice_play / gas_mix_block_resident -----------------
+    def source_set(self, slot, pcm, sample_rate, loop=False):
+        if not hasattr(self, "_sources"):
+            self._sources, self._players = {}, {}
+        self._sources[int(slot)] = (np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1, 2)), float(sample_rate), bool(loop))
+
+    def voice_play(self, voices, sources, start_frames=None):
+        v = _arr(voices, np.int32).reshape(-1)
+        s = np.broadcast_to(_arr(sources, np.int32), v.shape)
+        st = np.zeros(v.shape, dtype=np.int32) if start_frames is None else np.broadcast_to(_arr(start_frames, np.int32), v.shape)
+        for vi, si, fi in zip(v, s, st):
+            old = self._players.pop(int(vi), None)
+            if old is not None:
+                old.close()
+            if si >= 0:
+                pcm, rate, loop = self._sources[int(si)]
+                self._players[int(vi)] = Resampler(pcm, rate, loop=loop, start_frame=int(fi))
+
+    def mix_block_resident(self, voices, frames, threads=1):
+        """upstream's resampler per voice at the instance's current pitch_scale (audio_spatializer.cpp:375-378), then the stream form."""
+        v = _arr(voices, abi.voice).reshape(-1)
+        rows = np.zeros((max(v.size, 1), frames, 2), dtype=np.float32)
+        mixed = np.zeros(max(v.size, 1), dtype=np.int32)
+        inst = np.unique(v["instance"]) if v.size else np.zeros(0, dtype=np.int32)
+        pitch = dict(zip(inst.tolist(), self.params_get(inst)["pitch_scale"].tolist())) if inst.size else {}
+        vv = v.copy()
+        for i in range(v.size):
+            pl = self._players.get(int(v["voice"][i])) if hasattr(self, "_players") else None
+            if pl is not None and v["src_row"][i] >= 0:
+                rows[i], mixed[i] = pl.mix(frames, pitch[int(v["instance"][i])], float(self.config["mix_rate"]))
+            vv["src_row"][i] = i if v["src_row"][i] >= 0 else -1
+        return self.mix_block_stream(vv, rows, mixed[: v.size], frames, threads=threads)
+
     def set_playback_disable_threshold_db(self, instances, db):
         i = _arr(instances, np.int32)
         d = np.broadcast_to(_arr(db, np.float32), i.shape).copy()

@@ -148,51 +148,91 @@ def test_cuda_resampler_matches_oracle_bit_for_bit(gas, orc, loop):
             assert (mixed < F).any()  # the fast voices have run off the end of their clips by now
 
 
-@pytest.mark.gpu
-def test_resident_mix_equals_stream_form_fed_with_oracle_rows(gas, orc):
-    """gas_mix_block_resident (resample + lifecycle + mix on the device) against the oracle's stream form fed with the oracle
-    resampler's rows: bus buffers within tolerance, lifecycle status identical, until every clip has ended and its tail has died."""
-    V, F, blocks = 96, 512, 8
-    cfg = dict(max_instances=V, max_voices=V, max_frames=F, num_buses=2, speaker_mode=abi.SPEAKER_SURROUND_51, mix_rate=48000.0)
+def _resident_scene(V, F, blocks):
+    clips = [_clip(1500 + 211 * k, 10 + k) for k in range(6)]
+    ems = [synth.make_emitters(V, block=b, dt=F / 48000.0, area_fraction=0.5) for b in range(blocks)]
+    for e in ems:
+        e["pitch_scale"] = np.linspace(0.5, 2.0, V).astype(np.float32)  # AudioStreamPlayerSpatial::pitch_scale, passed through
+    return clips, ems
+
+
+def _play_resident(mm, V, F, blocks, clips, ems, rate=44100.0):
+    """The same calls on the CUDA Mixer and on the oracle: returns per-block (bus, status) and the voices alive before each block."""
     listeners = np.array([abi.identity_listener()], dtype=abi.listener)
     areas = np.array([synth.reverb_area(reverb_bus=1, amount=0.5)], dtype=abi.area)
-    clips = [_clip(1500 + 211 * k, 10 + k) for k in range(6)]
     inst = np.arange(V, dtype=np.int32)
     voices = synth.make_voices(V)
-    spat = abi.spatializer_defaults(mix_channel_mode=1, attenuation_filter_db=-18.0)
+    mm.spatializer_set(0, abi.spatializer_defaults(mix_channel_mode=1, attenuation_filter_db=-18.0))
+    mm.instance_init(inst, 0)
+    mm.gain_compute(ems[0], listeners, areas, want_params=False)
+    mm.instance_start(inst)
+    mm.voice_init(inst)
+    for k, c in enumerate(clips):
+        mm.source_set(k, c, rate)
+    mm.voice_play(inst, inst % len(clips))
+    active = np.ones(V, dtype=bool)
+    out = []
+    for b in range(blocks):
+        mm.gain_compute(ems[b], listeners, areas, want_params=False)
+        live = voices[active].copy()
+        live["src_row"] = np.arange(live.size)
+        bus, status = mm.mix_block_resident(live, F)
+        out.append((bus, status.copy(), active.copy()))
+        alive = (status & abi.VOICE_ACTIVE) != 0
+        idx = np.nonzero(active)[0]
+        active[idx[~alive]] = False
+    return out
+
+
+def test_oracle_resident_path_lifecycle(orc):
+    """The oracle twin of gas_mix_block_resident (upstream resampler per voice + stream form): clips end inside the run, voices keep
+    their filter tails for a while and are then deactivated; a 48 kHz clip at pitch 1 is the stream form fed with the clip itself,
+    two frames late."""
+    V, F, blocks = 24, 512, 8
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, num_buses=2, speaker_mode=abi.SPEAKER_SURROUND_51, mix_rate=48000.0)
+    clips, ems = _resident_scene(V, F, blocks)
+    with orc.OracleMixer(**cfg) as o:
+        res = _play_resident(o, V, F, blocks, clips, ems)
+    n_active = [int(r[2].sum()) for r in res]
+    assert n_active[0] == V and n_active[-1] < V and all(a >= b for a, b in zip(n_active, n_active[1:]))
+    assert all(np.isfinite(r[0]).all() for r in res) and np.abs(res[0][0]).max() > 0
+    # unit rate: rows = the clip delayed by two frames
+    for e in ems:
+        e["pitch_scale"] = 1.0
+    clip = _clip(4096, 3)
+    with orc.OracleMixer(**cfg) as a, orc.OracleMixer(**cfg) as b:
+        got = _play_resident(a, V, F, 2, [clip], ems, rate=48000.0)
+        listeners = np.array([abi.identity_listener()], dtype=abi.listener)
+        areas = np.array([synth.reverb_area(reverb_bus=1, amount=0.5)], dtype=abi.area)
+        inst = np.arange(V, dtype=np.int32)
+        b.spatializer_set(0, abi.spatializer_defaults(mix_channel_mode=1, attenuation_filter_db=-18.0))
+        b.instance_init(inst, 0)
+        b.gain_compute(ems[0], listeners, areas, want_params=False)
+        b.instance_start(inst)
+        b.voice_init(inst)
+        delayed = np.concatenate([np.zeros((2, 2), np.float32), clip])
+        for blk in range(2):
+            b.gain_compute(ems[blk], listeners, areas, want_params=False)
+            rows = np.broadcast_to(delayed[blk * F:(blk + 1) * F], (V, F, 2)).copy()
+            want_bus, want_status = b.mix_block_stream(synth.make_voices(V), rows, np.full(V, F, dtype=np.int32), F)
+            np.testing.assert_array_equal(got[blk][0], want_bus)
+            np.testing.assert_array_equal(got[blk][1], want_status)
+
+
+@pytest.mark.gpu
+def test_resident_mix_matches_the_oracle_twin(gas, orc):
+    """gas_mix_block_resident (resample + lifecycle + mix on the device) against the oracle twin, call for call: bus buffers within
+    tolerance, routing and lifecycle status identical, until clips have ended and their tails have died."""
+    V, F, blocks = 96, 512, 8
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, num_buses=2, speaker_mode=abi.SPEAKER_SURROUND_51, mix_rate=48000.0)
+    clips, ems = _resident_scene(V, F, blocks)
     with gas.Mixer(**cfg) as m, orc.OracleMixer(**cfg) as o:
-        for mm in (m, o):
-            mm.spatializer_set(0, spat)
-            mm.instance_init(inst, 0)
-        ems = [synth.make_emitters(V, block=b, dt=F / 48000.0, area_fraction=0.5) for b in range(blocks)]
-        for e in ems:
-            e["pitch_scale"] = np.linspace(0.5, 2.0, V).astype(np.float32)  # AudioStreamPlayerSpatial::pitch_scale, passed through
-        for mm in (m, o):
-            mm.gain_compute(ems[0], listeners, areas, want_params=False)
-            mm.instance_start(inst)
-            mm.voice_init(inst)
-        for k in range(6):
-            m.source_set(k, clips[k], 44100.0)
-        m.voice_play(inst, inst % 6)
-        rs = [orc.Resampler(clips[i % 6], 44100.0) for i in range(V)]
-        active = np.ones(V, dtype=bool)
-        for b in range(blocks):
-            pm = m.gain_compute(ems[b], listeners, areas)
-            po = o.gain_compute(ems[b], listeners, areas)
-            np.testing.assert_array_equal(pm["pitch_scale"], po["pitch_scale"])
-            live = voices[active].copy()
-            live["src_row"] = np.arange(live.size)
-            rows = np.zeros((max(live.size, 1), F, 2), dtype=np.float32)
-            mixed = np.zeros(max(live.size, 1), dtype=np.int32)
-            for r_, vv in enumerate(live["voice"]):
-                rows[r_], mixed[r_] = rs[vv].mix(F, float(po["pitch_scale"][vv]), 48000.0)
-            want_bus, want_status = o.mix_block_stream(live, rows, mixed[: live.size], F)
-            got_bus, got_status = m.mix_block_resident(live, F)
-            np.testing.assert_array_equal(got_status, want_status, err_msg=f"block {b}: lifecycle status")
-            assert np.array_equal(S.routing(got_bus), S.routing(want_bus)), f"block {b}: routing"
-            ok, worst, nbad = S.sample_close(got_bus, want_bus)
-            assert ok, f"block {b}: {nbad} samples out of tolerance (worst {worst:.3e})"
-            alive = (want_status & abi.VOICE_ACTIVE) != 0
-            idx = np.nonzero(active)[0]
-            active[idx[~alive]] = False
-        assert not active.all()  # clips ended and tails died inside the run
+        got = _play_resident(m, V, F, blocks, clips, ems)
+        want = _play_resident(o, V, F, blocks, clips, ems)
+    for b, ((gb, gs, ga), (wb, ws, wa)) in enumerate(zip(got, want)):
+        np.testing.assert_array_equal(ga, wa, err_msg=f"block {b}: live voices")
+        np.testing.assert_array_equal(gs, ws, err_msg=f"block {b}: lifecycle status")
+        assert np.array_equal(S.routing(gb), S.routing(wb)), f"block {b}: routing"
+        ok, worst, nbad = S.sample_close(gb, wb)
+        assert ok, f"block {b}: {nbad} samples out of tolerance (worst {worst:.3e})"
+    assert not want[-1][2].all()  # clips ended and tails died inside the run
