@@ -67,6 +67,7 @@ void spcap_constants(int speaker_mode, float dir[7][3], float eff[7]) {
 }
 
 void refresh_globals(gas_ctx *ctx) {
+	ctx->cfg_epoch++; // graphs captured under the old globals are refused from now on (gas_graph_launch)
 	ctx->g.speaker_mode = ctx->cfg.speaker_mode;
 	ctx->g.channels = ctx->cfg.speaker_mode + 1;
 	ctx->g.num_buses = ctx->cfg.num_buses;
@@ -153,7 +154,6 @@ int prof_drain(gas_ctx *ctx) {
 
 // Inside a capture the timing events become event-record nodes of the graph (cudaEventRecordExternal), so a
 // profiled graph reports each kernel's duration as it runs inside the replayed step.
-static gas_ctx::ProfPair g_graph_pair[GAS_KERNEL_KINDS];
 
 gas_ctx::ProfPair *prof_open(gas_ctx *ctx, int kind, cudaStream_t st = nullptr) {
 	st = st ? st : ctx->s_mix;
@@ -168,12 +168,12 @@ gas_ctx::ProfPair *prof_open(gas_ctx *ctx, int kind, cudaStream_t st = nullptr) 
 		}
 		ctx->gev_used[kind] = true;
 		ctx->capture_profiled = true;
-		g_graph_pair[kind].a = ctx->gev[kind][0];
-		g_graph_pair[kind].b = ctx->gev[kind][1];
-		g_graph_pair[kind].kind = kind;
-		g_graph_pair[kind].st = st;
-		cudaEventRecordWithFlags(g_graph_pair[kind].a, st, cudaEventRecordExternal);
-		return &g_graph_pair[kind];
+		ctx->graph_pair[kind].a = ctx->gev[kind][0];
+		ctx->graph_pair[kind].b = ctx->gev[kind][1];
+		ctx->graph_pair[kind].kind = kind;
+		ctx->graph_pair[kind].st = st;
+		cudaEventRecordWithFlags(ctx->graph_pair[kind].a, st, cudaEventRecordExternal);
+		return &ctx->graph_pair[kind];
 	}
 	if (ctx->prof_used >= 3072 && prof_drain(ctx) != GAS_OK) {
 		return nullptr;
@@ -1580,6 +1580,7 @@ int gas_capture_end(gas_ctx *ctx, int32_t *out_graph) {
 	}
 	g.kernels = kernels;
 	g.profiled = ctx->capture_profiled;
+	g.cfg_epoch = ctx->cfg_epoch;
 	ctx->graphs.push_back(g);
 	*out_graph = (int32_t)ctx->graphs.size() - 1;
 	return GAS_OK;
@@ -1589,6 +1590,10 @@ int gas_graph_launch(gas_ctx *ctx, int32_t graph) {
 	ENTER(ctx);
 	if (ctx->capturing || graph < 0 || graph >= (int32_t)ctx->graphs.size() || !ctx->graphs[graph].exec) {
 		return gas_fail(ctx, GAS_ERR_INVALID, "gas_graph_launch: bad graph id or capture in progress");
+	}
+	if (ctx->graphs[graph].cfg_epoch != ctx->cfg_epoch) {
+		return gas_fail(ctx, GAS_ERR_STATE, "gas_graph_launch: the graph was captured before gas_set_speaker_mode / gas_set_mix_rate / "
+				"gas_set_global_panning_strength changed the globals it has baked in: capture it again");
 	}
 	if (ctx->gain_pending) {
 		GAS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mix, ctx->ev_gain_done, 0));

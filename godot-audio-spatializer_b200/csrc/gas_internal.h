@@ -308,7 +308,9 @@ struct gas_ctx {
 		uint64_t kernels = 0;
 		bool profiled = false; // captured while per-kernel timing was on: carries event-record nodes around the kernels
 		int prof_blocks = 0;   // mix blocks in the graph (only the last block's events survive a launch)
+		uint64_t cfg_epoch = 0; // AudioServer globals the graph was captured under (speaker mode, mix rate, panning strength are baked in)
 	};
+	uint64_t cfg_epoch = 0; // bumped by gas_set_speaker_mode / gas_set_mix_rate / gas_set_global_panning_strength
 	std::vector<Graph> graphs;
 	// per-kernel timing
 	bool profiling = false;
@@ -318,6 +320,7 @@ struct gas_ctx {
 		cudaStream_t st;
 	};
 	std::vector<ProfPair> prof_pairs;
+	ProfPair graph_pair[GAS_KERNEL_KINDS] = {}; // the event pairs of a profiled capture
 	cudaEvent_t gev[GAS_KERNEL_KINDS][2] = {}; // event-record nodes of profiled graphs
 	bool gev_used[GAS_KERNEL_KINDS] = {};
 	bool capture_profiled = false;
