@@ -812,7 +812,7 @@ def gpu_arm(args):
     k2_ms, k2_n = prof["mix_stream"]
     peak, peak_src = measured_hbm_peak()
     bytes_launch = algorithmic_bytes(V, F, C, B)
-    k2_us = 1e3 * k2_ms / max(1, k2_n)
+    k2_us = max(1e3 * k2_ms / max(1, k2_n), 1e-6)
     step_us = 1e3 * ms / K
 
     def us(kind):
@@ -830,8 +830,9 @@ def gpu_arm(args):
                           "k_step without control work (block-call form: gains, plan and streaming are separate kernels)",
                 "us_per_launch": launch_us, "algorithmic_bytes_per_launch": bytes_launch, "launches_in_timed_region": K,
                 "peak_source": peak_src,
-                "timing": "CUDA events on the mix stream around the timed region / launches of the kernel (launches overlap by "
-                          "programmatic dependent launch, so the per-launch average IS the step time)",
+                "timing": ("CUDA events on the mix stream around the timed region / launches of the kernel (launches overlap by "
+                           "programmatic dependent launch, so the per-launch average IS the step time)" if not CLASSIC else
+                           "CUDA event-record nodes around the kernel inside a profiled capture of the same steps"),
                 "step_frac_of_hbm_peak": bytes_launch / (step_us * 1e-6) / 1e9 / peak,
                 "isolated": {"note": "same kernel between event-record nodes in a profiled capture of the same steps (the nodes serialise "
                                      "the launches and read ~2.7 us by themselves: event_pair_overhead_us)",
