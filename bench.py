@@ -343,11 +343,12 @@ class DeviceWorkload:
         return self.d_bus[k % NB]
 
     def capture_steps(self, chunk=1):
-        """One CUDA graph per `chunk` consecutive steps (chunk divides N_SETS): graph g replays steps g*chunk .. g*chunk+chunk-1 of
-        the source-set rotation.  Several steps per graph take the graph-to-graph launch gap off all but one step in `chunk`."""
+        """CUDA graphs of `chunk` consecutive steps each: graph g replays steps g*chunk .. g*chunk+chunk-1, and as many graphs are
+        captured as it takes to come back to step 0 of the rotation (sources and emitters rotate over N_SETS, bus buffers over NB).
+        Several steps per graph take the graph-to-graph hand-over off all but one step in `chunk`."""
         graphs = []
         self.restart()
-        for g in range(N_SETS // chunk):
+        for g in range(graphs_per_cycle(chunk)):
             self.mixer.capture_begin()
             for j in range(chunk):
                 self.step_device(g * chunk + j)
@@ -355,12 +356,23 @@ class DeviceWorkload:
         return graphs
 
 
+ROTATION = N_SETS  # steps after which sources (N_SETS), emitters (N_SETS), bus buffers (NB) and reduce buffers (2) all repeat
+assert ROTATION % NB == 0 and ROTATION % 2 == 0
+
+
+def graphs_per_cycle(chunk):
+    """Graphs of `chunk` steps needed before the rotation is back at step 0."""
+    return ROTATION // math.gcd(chunk, ROTATION)
+
+
 def steps_per_graph(K):
-    """Largest of 8, 4, 2, 1 that divides the timed step count (GAS_BENCH_CHUNK overrides)."""
+    """Largest of 8, 4, 2, 1 that divides the timed step count (GAS_BENCH_CHUNK overrides with any divisor up to 64: longer graphs
+    are supported by capture_steps but were not measured — a long graph's launch latency is exposed when it is the first of the
+    timed region)."""
     forced = os.environ.get("GAS_BENCH_CHUNK")
     if forced:
         c = int(forced)
-        if c in (1, 2, 4, 8) and K % c == 0:
+        if 1 <= c <= 64 and K % c == 0:
             return c
     for c in (8, 4, 2):
         if K % c == 0:
@@ -696,7 +708,7 @@ def gpu_arm(args):
     # rounded up to whole graphs
     K = args.steps
     chunk = steps_per_graph(K)
-    W = max(3, args.warmup, N_SETS)
+    W = max(3, args.warmup, N_SETS, graphs_per_cycle(chunk) * chunk)  # every graph is launched (uploaded) before the timed region
     W = ((W + chunk - 1) // chunk) * chunk
 
     parity_src = synth.make_sources(V, F, block=0, mix_rate=w["mix_rate"]) if (rank == 0 and not args.no_parity) else None
