@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """bench.py — mixed voice-frames/sec of the batched spatial mixer on N B200s (one process per GPU).
 
-One *step* = one pass of the hot path over one mix block of synthetic input on every rank:
-gain kernel (calculate_spatialization for every instance) -> prologue -> streaming / voice-parallel mix
-kernels -> (N > 1) sum of the per-GPU partial bus buffers.  Workload (BASELINE.json configs[2] shape,
-SURVEY.md §8d): AudioSpatializer3D, 16384 voices per GPU x 512-frame blocks at 48 kHz, 7.1 (4 channel
-pairs), mix_channel_mode on, two buses (Master + a reverb bus fed by the voices inside a reverb Area3D),
-attenuation filter inactive because the reference skips it below 0.001 linear gain
-(audio_spatializer_3d.cpp:568) — obtained with attenuation_filter_db = -80 and unit_size = 1, no override.
+One *step* = one pass of the hot path over one mix block of synthetic input on every rank: gains (calculate_spatialization for
+every instance), plan (what process_frames / mix_channel and AudioServer decide per voice before their sample loops), ramped
+mix of every voice into the bus buffers, and (N > 1) the sum of the per-GPU partial bus buffers.  At 1 and 2 GPUs a step is ONE
+launch of the step kernel (gas_step_device: it streams block k while its control warps compute gains and plan of block k + 1); at 4
+and 8 GPUs the block-call form (gas_mix_block_device + gas_gain_compute_device) is used, see select_form().  Workload (BASELINE.json
+configs[2] shape): AudioSpatializer3D, 16384 voices per GPU x 512-frame blocks at 48 kHz, 7.1 (4 channel pairs),
+mix_channel_mode on, two buses (Master + a reverb bus fed by the voices inside a reverb Area3D), attenuation filter inactive
+because the reference skips it below 0.001 linear gain (audio_spatializer_3d.cpp:568) — obtained with attenuation_filter_db = -80
+and unit_size = 1, no override.
 
-value      whole-job voice-frames/s, inputs resident in HBM, CUDA-graph replay of the device-resident
-           C-ABI calls, timed with CUDA events on the mix stream, max over ranks.
-e2e        same metric through gas_gain_compute + gas_mix_block with HOST (pinned) buffers: per step the
-           sources/voices/emitters go host->device and the bus buffers come back, inside the timed region.
-roofline   streaming mix kernel (K2): algorithmic bytes per launch / its mean duration (CUDA events around
-           every launch) vs the measured HBM copy peak in MEASURED_PEAKS.json.
-cpu_baseline  the CPU oracle (restated reference loop, oracle/) on the host cores, bounded sample.
+value      whole-job voice-frames/s, inputs resident in HBM, CUDA-graph replay of the device-resident C-ABI calls, timed with CUDA
+           events on the mix stream, max over ranks.
+e2e        same metric through the public API with HOST inputs.  With device-resident sources (gas_mix_block_resident: PCM clips in
+           HBM, resampler + voice lifecycle + mix on the device) only the emitters and the voice list go up per step and the bus
+           buffers come back; that leg runs in a child process and is adopted only if its own parity check against the oracle
+           passes.  Otherwise (and always as e2e.host_frames) gas_gain_compute + gas_mix_block with pinned host source frames:
+           68 MB up per step, PCIe-bound.
+roofline   the step kernel: algorithmic bytes per launch / its average launch duration over the timed region (launches overlap, so
+           that is the step time) vs the measured HBM copy peak in MEASURED_PEAKS.json; the isolated reading between event-record
+           nodes beside it.
+cpu_baseline  the CPU oracle (restated reference loop, oracle/, pinned by the reference's own sources in oracle/_ref) on the host
+           cores, bounded sample.
 
 configs    (N = 1) the other BASELINE.json configurations, time-boxed: us per block, voice-frames/s, fraction of the HBM
            and fp32 rooflines, CPU baseline and a full-size parity flag each.
