@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_comm_push(CommArgs a, const float4 *__r
 		const float4 v = partial[i];
 		for (int r = 0; r < a.n_ranks; r++) {
 			float *dst = reinterpret_cast<float *>(a.xbuf[r] + (size_t)par * a.xstride_f4 + i);
-			asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+			gas_red_add_v4(dst, v.x, v.y, v.z, v.w);
 		}
 	}
 	__syncthreads();
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_comm_push(CommArgs a, const float4 *__r
 			seq[0] = n + 1ULL;
 			__threadfence_system();
 			for (int r = 0; r < a.n_ranks; r++) {
-				asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(a.arrived[r]), "l"(1ULL) : "memory");
+				gas_red_release_sys_add_u64(a.arrived[r], 1ULL);
 			}
 		}
 	}
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_comm_finish(CommArgs a, float4 *__restr
 		const unsigned long long *flag = a.arrived[a.rank];
 		unsigned long long seen;
 		do {
-			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+			seen = gas_ld_acquire_sys_u64(flag);
 		} while (seen < want);
 		s_n = n;
 	}
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_comm_exchange(CommArgs a, const float4 
 			const unsigned long long *flag = a.arrived[a.rank];
 			unsigned long long seen;
 			do {
-				asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+				seen = gas_ld_acquire_sys_u64(flag);
 			} while (seen < want);
 		}
 		s_push = n_push;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) k_comm_exchange(CommArgs a, const float4 
 		const float4 v = partial[i];
 		for (int r = 0; r < a.n_ranks; r++) {
 			float *dst = reinterpret_cast<float *>(a.xbuf[r] + (size_t)par * a.xstride_f4 + i);
-			asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+			gas_red_add_v4(dst, v.x, v.y, v.z, v.w);
 		}
 	}
 	__syncthreads();
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_comm_exchange(CommArgs a, const float4 
 			}
 			__threadfence_system();
 			for (int r = 0; r < a.n_ranks; r++) {
-				asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(a.arrived[r]), "l"(1ULL) : "memory");
+				gas_red_release_sys_add_u64(a.arrived[r], 1ULL);
 			}
 		}
 	}

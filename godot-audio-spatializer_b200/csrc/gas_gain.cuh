@@ -439,9 +439,7 @@ static __device__ __forceinline__ int gain_emitter(const DevTables &t, const Glo
 	constexpr int S = 8 / NL;
 #define GAS_GAIN_STAMP(k_)                                            \
 	if (dbg) {                                                        \
-		unsigned long long t_;                                        \
-		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));        \
-		dbg[k_] = t_;                                                 \
+		dbg[k_] = gas_globaltimer();                                  \
 	}
 	gas_emitter e = emitters[i];
 	// Device-resident emitter records are not seen by the host: a record that points outside the tables is skipped (its
@@ -679,7 +677,7 @@ static __device__ __forceinline__ int gain_emitter(const DevTables &t, const Glo
 		// in-kernel gains (step kernel): tell the planner of this block that the instance's parameters are in place
 		__syncwarp(gm);
 		if (l == 0) {
-			asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(inst_seq + q), "r"(seq_val) : "memory");
+			gas_st_release_gpu_s32(inst_seq + q, seq_val);
 		}
 	}
 	return q;

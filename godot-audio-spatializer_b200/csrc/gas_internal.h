@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gas_ptx.cuh"
+
 #include <mutex>
 #include <string>
 #include <vector>
@@ -377,8 +379,7 @@ template <typename... KArgs, typename... Args>
 static inline cudaError_t gas_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
 	return gas_launch_ev(kernel, grid, block, smem, st, pdl, (cudaEvent_t) nullptr, args...);
 }
-#define GAS_GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
-#define GAS_GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+// (GAS_GRID_DEP_WAIT / GAS_GRID_DEP_LAUNCH: gas_ptx.cuh)
 
 // ---- kernel launchers (each returns cudaError_t from the launch) -----------------------------------
 // gas_gain.cu

@@ -44,10 +44,6 @@
 
 #include <stdlib.h>
 
-#ifndef GAS_USE_FFMA2
-#define GAS_USE_FFMA2 1
-#endif
-
 namespace {
 
 constexpr int kConsumerWarps = 8;
@@ -95,78 +91,6 @@ struct StepArgs {
 	const gas_area *areas;
 	int n_areas;
 };
-
-// ---- PTX helpers -------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long gtime() {
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	return t;
-}
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-	uint32_t ok = 0;
-	do {
-		asm volatile(
-				"{\n"
-				".reg .pred p;\n"
-				"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-				"selp.u32 %0, 1, 0, p;\n"
-				"}\n"
-				: "=r"(ok)
-				: "r"(smem_u32(bar)), "r"(parity)
-				: "memory");
-	} while (!ok);
-}
-// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-			"l"(src), "r"(bytes), "r"(smem_u32(bar))
-			: "memory");
-}
-// ... with an L2 eviction policy: source rows are read exactly once, so they are marked evict-first and leave the small
-// tables the control warps walk (parameters, bus details, ramp state: ~15 MB) resident in L2 from step to step
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-	uint64_t p;
-	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-	return p;
-}
-__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
-			"l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-			: "memory");
-}
-__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
-	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-// packed (L,R) FMA: a * b + c on both halves with one instruction (SASS: FFMA2)
-__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
-	float2 d;
-#if GAS_USE_FFMA2
-	asm("{\n"
-		".reg .b64 ra, rb, rc, rd;\n"
-		"mov.b64 ra, {%2, %3};\n"
-		"mov.b64 rb, {%4, %5};\n"
-		"mov.b64 rc, {%6, %7};\n"
-		"fma.rn.f32x2 rd, ra, rb, rc;\n"
-		"mov.b64 {%0, %1}, rd;\n"
-		"}\n"
-		: "=f"(d.x), "=f"(d.y)
-		: "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-#else
-	d.x = fmaf(a.x, b.x, c.x);
-	d.y = fmaf(a.y, b.y, c.y);
-#endif
-	return d;
-}
 
 // ---- unit iterator: (class, frame tile, voice batch), identical in every role ------------
 struct UnitIter {
@@ -427,12 +351,12 @@ __device__ __forceinline__ void voice_loop(float2 (&acc)[E][2], const unsigned c
 				const float2 a = make_float2(w[u][e].x, w[u][e].y);
 				float2 b0 = make_float2(w[u][e].z, w[u][e].w), b1 = b0;
 				if (QUAD) {
-					b0 = ffma2(qd[u][e], T0, b0);
-					b1 = ffma2(qd[u][e], T1, b1);
+					b0 = gas_ffma2(qd[u][e], T0, b0);
+					b1 = gas_ffma2(qd[u][e], T1, b1);
 				}
-				const float2 w0 = ffma2(b0, T0, a), w1 = ffma2(b1, T1, a);
-				acc[e][0] = ffma2(w0, x0, acc[e][0]);
-				acc[e][1] = ffma2(w1, x1, acc[e][1]);
+				const float2 w0 = gas_ffma2(b0, T0, a), w1 = gas_ffma2(b1, T1, a);
+				acc[e][0] = gas_ffma2(w0, x0, acc[e][0]);
+				acc[e][1] = gas_ffma2(w1, x1, acc[e][1]);
 			}
 		}
 	}
@@ -446,12 +370,12 @@ __device__ __forceinline__ void voice_loop(float2 (&acc)[E][2], const unsigned c
 			float2 b0 = make_float2(w.z, w.w), b1 = b0;
 			if (QUAD) {
 				const float2 qd = *reinterpret_cast<const float2 *>(wp + E * 16 + e * 8);
-				b0 = ffma2(qd, T0, b0);
-				b1 = ffma2(qd, T1, b1);
+				b0 = gas_ffma2(qd, T0, b0);
+				b1 = gas_ffma2(qd, T1, b1);
 			}
-			const float2 w0 = ffma2(b0, T0, a), w1 = ffma2(b1, T1, a);
-			acc[e][0] = ffma2(w0, x0, acc[e][0]);
-			acc[e][1] = ffma2(w1, x1, acc[e][1]);
+			const float2 w0 = gas_ffma2(b0, T0, a), w1 = gas_ffma2(b1, T1, a);
+			acc[e][0] = gas_ffma2(w0, x0, acc[e][0]);
+			acc[e][1] = gas_ffma2(w1, x1, acc[e][1]);
 		}
 	}
 }
@@ -483,9 +407,9 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		const int nv = min(cf.vb, ci.count - v0);
 		const unsigned char *sx = cc.smem + (size_t)cc.stage * cf.stage_bytes;
 		const unsigned char *sw = sx + cf.x_bytes;
-		mbar_wait(&cc.full[cc.stage], cc.phase);
+		gas_mbar_wait(&cc.full[cc.stage], cc.phase);
 		if (cc.tl && !cc.tl_first) { // (a register flag: reading the stamp back from global memory every stage cost 0.3 us per stage)
-			cc.tl[2] = gtime();
+			cc.tl[2] = gas_globaltimer();
 			cc.tl_first = true;
 		}
 		if (mine && !(cf.debug & 2)) {
@@ -499,7 +423,7 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		}
 		__syncwarp();
 		if (cc.lane == 0) {
-			mbar_arrive(&cc.empty[cc.stage]);
+			gas_mbar_arrive(&cc.empty[cc.stage]);
 		}
 		if (++cc.stage == cf.stages) {
 			cc.stage = 0;
@@ -508,14 +432,14 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 		unit_iter_next(it, cc.cls, cf);
 	} while (it.remaining > 0 && it.cid == cid && it.tile == tile);
 	if (cc.tl) {
-		cc.tl[3] = gtime();
+		cc.tl[3] = gas_globaltimer();
 	}
 	if ((cf.debug & 1) || !mine) {
 		return;
 	}
 	// ---- flush: bus[b][c][i] += the sums of this thread's two frames ------------------------------------------------
 	if (cc.tl) {
-		cc.tl[9] = gtime();
+		cc.tl[9] = gas_globaltimer();
 	}
 	if (ci.flags & (CLS_SHARED | CLS_SCALED)) {
 		// one row group fanned out to every bus of the mask: as it is (shared), or times the send's scale (scaled)
@@ -527,7 +451,7 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 			m &= m - 1;
 #pragma unroll
 			for (int c = 0; c < C; c++) {
-				red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, acc[c][0].x * sc, acc[c][0].y * sc, acc[c][1].x * sc, acc[c][1].y * sc);
+				gas_red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, acc[c][0].x * sc, acc[c][0].y * sc, acc[c][1].x * sc, acc[c][1].y * sc);
 			}
 			sc = nxt;
 			nxt = nxt2;
@@ -540,14 +464,14 @@ __device__ __forceinline__ void consumer_run(UnitIter &it, ConsumerCtx &cc, cons
 			rest &= rest - 1;
 #pragma unroll
 			for (int c = 0; c < C; c++) {
-				red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, acc[k * C + c][0].x, acc[k * C + c][0].y, acc[k * C + c][1].x, acc[k * C + c][1].y);
+				gas_red_add_v4(bus + ((size_t)(b * C + c) * F + frame0) * 2, acc[k * C + c][0].x, acc[k * C + c][0].y, acc[k * C + c][1].x, acc[k * C + c][1].y);
 			}
 		}
 	}
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ StepArgs A) {
-	extern __shared__ __align__(128) unsigned char smem[];
+	GAS_DYN_SMEM(unsigned char, 128, smem);
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ UnitIter s_it;
 	__shared__ __align__(8) uint64_t s_full[kMaxStages];
@@ -601,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 			}
 			__syncwarp();
 			if (lane == 0) {
-				asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(&blk[BLK_GAIN_DONE]) : "memory");
+				gas_red_release_gpu_add_s32(&blk[BLK_GAIN_DONE], 1);
 			}
 			wait_total = (int)gridDim.x * kControlWarps;
 			gasplan::group_stamp(G, 17);
@@ -622,10 +546,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 	int slot_p = 0, k = 0;
 	if (warp == kConsumerWarps) {
 		if (tlp) {
-			tlp[0] = gtime();
-			unsigned smid;
-			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-			tlp[6] = smid;
+			tlp[0] = gas_globaltimer();
+			tlp[6] = gas_smid();
 		}
 		// Which block: every CTA reads the launch counter, then takes a ticket; the CTA with the last ticket advances the
 		// counter, and only then lets the dependent launch go (a dependent launch starts once EVERY CTA of this one has
@@ -639,10 +561,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 				__threadfence();
 			}
 			for (int s = 0; s < cf.stages; s++) {
-				mbar_init(&s_full[s], 1);
-				mbar_init(&s_empty[s], kConsumerWarps);
+				gas_mbar_init(&s_full[s], 1);
+				gas_mbar_init(&s_empty[s], kConsumerWarps);
 			}
-			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			gas_mbar_init_fence();
 			GAS_GRID_DEP_LAUNCH();
 		}
 		slot_p = k & (GAS_PLAN_DEPTH - 1);
@@ -683,20 +605,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 		}
 		__syncwarp();
 		if (tlp) {
-			tlp[11] = gtime();
+			tlp[11] = gas_globaltimer();
 		}
 		unit_iter_init_warp(it, s_cls, n_cls, cf, C, blockIdx.x, gridDim.x, lane);
 		if (lane == 0) {
 			s_it = it;
 		}
 		__syncwarp();
-		asm volatile("bar.arrive 2, %0;" ::"n"(kStreamThreads) : "memory");
+		GAS_BAR_ARRIVE_IMM(2, kStreamThreads);
 		if (tlp) {
-			tlp[1] = gtime();
+			tlp[1] = gas_globaltimer();
 			tlp[5] = (unsigned long long)it.remaining;
 		}
 	} else {
-		asm volatile("bar.sync 2, %0;" ::"n"(kStreamThreads) : "memory");
+		GAS_BAR_SYNC_IMM(2, kStreamThreads);
 		it = s_it;
 	}
 	if (it.remaining <= 0) {
@@ -708,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 		// ===== producer =====
 		int stage = 0;
 		uint32_t phase = 0;
-		const uint64_t pol_stream = l2_policy_evict_first();
+		const uint64_t pol_stream = gas_l2_policy_evict_first();
 		const int2 *list = plan.list + (size_t)slot_p * GAS_MAX_CLASSES * maxv;
 		const float *rows = plan_rows(plan, k, 0, maxv);
 		// Source-row indices are fetched one warp-wide load (32 list positions = 32/vb units) at a time,
@@ -718,7 +640,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 		IdxBlock nxt = idx_block_load(pf, s_cls, cf, list, maxv, lane, cur.n_units);
 		int seq = 0;
 		if (tlp) {
-			tlp[12] = gtime() + (cur.val.y == -12345 ? 1ULL : 0ULL); // first indices have arrived
+			tlp[12] = gas_globaltimer() + (cur.val.y == -12345 ? 1ULL : 0ULL); // first indices have arrived
 		}
 		while (it.remaining > 0) {
 			if (seq >= cur.first_seq + cur.n_units) {
@@ -734,24 +656,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 			const uint32_t w_bytes = (uint32_t)(nv * nf * 4);
 			unsigned char *sx = ring + (size_t)stage * cf.stage_bytes;
 			unsigned char *sw = sx + cf.x_bytes;
-			mbar_wait(&s_empty[stage], phase ^ 1u);
+			gas_mbar_wait(&s_empty[stage], phase ^ 1u);
 			const bool no_copy = (cf.debug & 4) != 0; // experiment: arm the stage without copying anything into it
 			if (lane == 0) {
-				mbar_arrive_expect_tx(&s_full[stage], no_copy ? 0u : row_bytes * (uint32_t)nv + w_bytes);
+				gas_mbar_arrive_expect_tx(&s_full[stage], no_copy ? 0u : row_bytes * (uint32_t)nv + w_bytes);
 				if (!no_copy) {
-					bulk_g2s(sw, rows + (size_t)ci.slot * maxv * GAS_K2_ROW_FLOATS + (size_t)v0 * nf, w_bytes, &s_full[stage]);
+					gas_bulk_g2s(sw, rows + (size_t)ci.slot * maxv * GAS_K2_ROW_FLOATS + (size_t)v0 * nf, w_bytes, &s_full[stage]);
 				}
 			}
 			__syncwarp();
 			{
 				const int v = lane - (seq - cur.first_seq) * cf.vb; // this lane's voice inside the stage
 				if (v >= 0 && v < nv && !no_copy) {
-					bulk_g2s_hint(sx + (size_t)v * row_bytes, A.src + (size_t)cur.val.y * cf.src_stride + (size_t)it.tile * cf.tile_frames, row_bytes,
+					gas_bulk_g2s_hint(sx + (size_t)v * row_bytes, A.src + (size_t)cur.val.y * cf.src_stride + (size_t)it.tile * cf.tile_frames, row_bytes,
 							&s_full[stage], pol_stream);
 				}
 			}
 			if (tlp && seq < 2) {
-				tlp[13 + seq] = gtime(); // copies of the first / second stage issued
+				tlp[13 + seq] = gas_globaltimer(); // copies of the first / second stage issued
 			}
 			seq++;
 			if (++stage == cf.stages) {
@@ -796,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 #undef GAS_RUN
 		}
 		if (tl) {
-			tl[4] = gtime();
+			tl[4] = gas_globaltimer();
 		}
 	}
 }

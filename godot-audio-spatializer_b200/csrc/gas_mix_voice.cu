@@ -27,9 +27,9 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // add into the CTA's accumulation tile (explicit shared-space reduction: a generic-address atomicAdd on shared
 // memory is an order of magnitude slower) or, without a tile, into the bus buffers
-__device__ __forceinline__ void acc_add(float *bus, uint32_t tile_s, size_t o, float v) {
+__device__ __forceinline__ void acc_add(float *bus, gas_smem_addr tile_s, size_t o, float v) {
 	if (tile_s) {
-		asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(tile_s + (uint32_t)o * 4u), "f"(v) : "memory");
+		gas_red_shared_add_f32(tile_s + (gas_smem_addr)o * 4u, v);
 	} else {
 		atomicAdd(bus + o, v);
 	}
@@ -107,7 +107,7 @@ __device__ __forceinline__ void reduce_hi(float (&v)[N], int lane, int &base, bo
 // CTA's accumulation tile (or the bus buffers).
 template <int C, int NS>
 __device__ void voice_pass_b(const DevTables &t, const ChunkArgs &a, int send0, bool last_pass, const gas_frame *__restrict__ src,
-		int src_stride, int F, float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
+		int src_stride, int F, float *__restrict__ bus, gas_smem_addr tile, float2 *__restrict__ peaks) {
 	const int lane = threadIdx.x & 31;
 	const int g = lane >> 3, l = lane & 7, c = l >> 1, side = l & 1;
 	const int gbase = lane & 24;
@@ -232,7 +232,7 @@ __device__ void voice_pass_b(const DevTables &t, const ChunkArgs &a, int send0, 
 
 template <int C>
 __device__ void voice_chunk_b(const DevTables &t, const ChunkArgs &a, const gas_frame *__restrict__ src, int src_stride, int F,
-		float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
+		float *__restrict__ bus, gas_smem_addr tile, float2 *__restrict__ peaks) {
 	const int n = a.n_send;
 	if (n == 0) {
 		voice_pass_b<C, 1>(t, a, 0, true, src, src_stride, F, bus, tile, peaks); // state / peak only: every send test fails
@@ -259,7 +259,7 @@ struct Pow2Ceil8 {
 // summed with one transposing shuffle reduction over lane bits 4..1 (bit 0 is the side and is not reduced).
 template <int MODE, int C, int NS>
 __device__ void voice_pass_s(const DevTables &t, const ChunkArgs &a, int send0, bool emit, bool last_pass, const gas_frame *__restrict__ src,
-		int src_stride, int F, float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
+		int src_stride, int F, float *__restrict__ bus, gas_smem_addr tile, float2 *__restrict__ peaks) {
 	const int lane = threadIdx.x & 31;
 	const int side = lane & 1;
 	const int pos = a.chunk * 16 + (lane >> 1);
@@ -431,7 +431,7 @@ __device__ void voice_pass_s(const DevTables &t, const ChunkArgs &a, int send0, 
 
 template <int MODE, int C>
 __device__ void voice_chunk_s(const DevTables &t, const ChunkArgs &a, const gas_frame *__restrict__ src, int src_stride, int F,
-		float *__restrict__ bus, uint32_t tile, float2 *__restrict__ peaks) {
+		float *__restrict__ bus, gas_smem_addr tile, float2 *__restrict__ peaks) {
 	const int n = a.n_send;
 	if (n == 0) {
 		voice_pass_s<MODE, C, 1>(t, a, 0, false, true, src, src_stride, F, bus, tile, peaks);
@@ -460,7 +460,7 @@ template <int C>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t, GlobalCfg g, BlockPlan plan,
 		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks,
 		const float4 *__restrict__ rep, int bus_f4, int replicas, int tile_floats, int early_look) {
-	extern __shared__ __align__(16) float s_tile[];
+	GAS_DYN_SMEM(float, 16, s_tile);
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ int s_ncls;
 	GAS_GRID_DEP_LAUNCH();
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	__syncthreads();
 	// CTA-wide accumulation tile: the voices of all chunks this CTA visits are summed in shared memory and reach the
 	// bus buffers as one vector reduction per 16 bytes (instead of one scalar atomic per element per 32 voices)
-	const uint32_t tile = tile_floats > 0 ? (uint32_t)__cvta_generic_to_shared(s_tile) : 0u;
+	const gas_smem_addr tile = tile_floats > 0 ? gas_smem_u32(s_tile) : 0u;
 	bool cta_has_work = false;
 	{
 		int units = 0;
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 		for (int i = threadIdx.x; i < tile_floats / 4; i += blockDim.x) {
 			const float4 v = reinterpret_cast<const float4 *>(s_tile)[i];
 			if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
-				asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(bus + (size_t)i * 4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+				gas_red_add_v4(bus + (size_t)i * 4, v.x, v.y, v.z, v.w);
 			}
 		}
 	}	__syncthreads();

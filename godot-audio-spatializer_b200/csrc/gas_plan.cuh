@@ -49,12 +49,10 @@ struct PlanGroup {
 };
 static __device__ __forceinline__ void group_stamp(const PlanGroup &G, int slot) {
 	if (G.tl) {
-		unsigned long long t;
-		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-		G.tl[slot] = t;
+		G.tl[slot] = gas_globaltimer();
 	}
 }
-static __device__ __forceinline__ void group_sync(const PlanGroup &G) { asm volatile("bar.sync %0, %1;" ::"r"(G.bar_id), "r"(G.nthreads) : "memory"); }
+static __device__ __forceinline__ void group_sync(const PlanGroup &G) { gas_bar_sync(G.bar_id, G.nthreads); }
 
 struct PlanArgs {
 	DevTables t;
@@ -72,12 +70,8 @@ struct PlanArgs {
 
 static __device__ __forceinline__ int resolve_bus(const GlobalCfg &g, int bus) { return (bus >= 0 && bus < g.num_buses) ? bus : 0; }
 static __device__ __forceinline__ int ld_volatile(const int32_t *p) { return *(volatile const int32_t *)p; }
-static __device__ __forceinline__ void st_release(int32_t *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-static __device__ __forceinline__ int ld_acquire(const int32_t *p) {
-	int v;
-	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
+static __device__ __forceinline__ void st_release(int32_t *p, int v) { gas_st_release_gpu_s32(p, v); }
+static __device__ __forceinline__ int ld_acquire(const int32_t *p) { return gas_ld_acquire_gpu_s32(p); }
 
 // Sends of an instance with more than two buses on either side (custom parameters only: calculate_spatialization never
 // produces more than two): resolved straight into the voice's InstSends record in global memory, this lane's side.  Same
@@ -832,8 +826,7 @@ static __device__ __forceinline__ void plan_block(const PlanGroup &G, PlanSmem &
 	__syncwarp();
 	int last = 0;
 	if ((G.tid & 31) == 0) {
-		int old;
-		asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(&t.blk[BLK_P_TICKET]) : "memory");
+		const int old = gas_atom_add_acq_rel_gpu_s32(&t.blk[BLK_P_TICKET], 1);
 		last = old == G.n_cta * (G.nthreads >> 5) - 1;
 	}
 	last = __shfl_sync(0xffffffffu, last, 0);
