@@ -45,7 +45,6 @@ __global__ void __launch_bounds__(256) k_bus_graph(BusGraphArgs a, float4 *__res
 
 } // namespace
 
-#ifndef GAS_KERNEL_EMULATION // (tests/emu compiles the kernels above with g++ and runs them on the CPU)
 cudaError_t launch_bus_graph(gas_ctx *ctx, gas_frame *d_bus, int frames, cudaStream_t st) {
 	BusGraphArgs a{};
 	a.n_buses = ctx->g.num_buses;
@@ -60,4 +59,3 @@ cudaError_t launch_bus_graph(gas_ctx *ctx, gas_frame *d_bus, int frames, cudaStr
 	ctx->launches++;
 	return cudaGetLastError();
 }
-#endif

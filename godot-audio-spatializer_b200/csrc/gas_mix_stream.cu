@@ -553,6 +553,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_step(const __grid_constant__ St
 		// counter, and only then lets the dependent launch go (a dependent launch starts once EVERY CTA of this one has
 		// triggered, so all of its CTAs read the advanced counter and none of this launch's reads a value later than its own).
 		k = gasplan::ld_volatile(&blk[BLK_S]);
+		// (every lane keeps lane 0's reading: the warp loads before lane 0 takes the ticket, but nothing orders the OTHER lanes'
+		// loads before the counter's advance except convergent execution; the shuffle makes it explicit)
+		k = __shfl_sync(0xffffffffu, k, 0);
 		if (lane == 0) {
 			const int ticket = atomicAdd(&blk[BLK_S_TICKET], 1);
 			if (ticket == (int)gridDim.x - 1) {

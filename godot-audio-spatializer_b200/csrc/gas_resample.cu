@@ -125,7 +125,6 @@ __global__ void k_voice_play(DevTables t, int n, const int32_t *__restrict__ voi
 
 } // namespace
 
-#ifndef GAS_KERNEL_EMULATION // (tests/emu compiles the kernels above with g++ and runs them on the CPU)
 cudaError_t launch_resample(gas_ctx *ctx, int n_voices, const gas_voice *d_voices, int frames, gas_frame *d_rows, int row_stride, int src_rows,
 		int32_t *d_mixed, cudaStream_t st) {
 	if (n_voices <= 0) {
@@ -145,4 +144,3 @@ cudaError_t launch_voice_play(gas_ctx *ctx, int n, const int32_t *d_voices, cons
 	ctx->launches++;
 	return cudaGetLastError();
 }
-#endif
