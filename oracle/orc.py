@@ -210,6 +210,8 @@ class OracleMixer:
         bus = np.zeros((self.num_buses, self.channels, frames, 2), dtype=np.float32) if want_bus else None
         peaks = np.zeros((v.size, 2), dtype=np.float32) if want_peaks else None
         bus64 = np.zeros((self.num_buses, self.channels, frames, 2), dtype=np.float64) if shadow else None
+        if shadow:
+            threads = 1  # the float64 shadow is only computed by the single-threaded loop (orc_mix_block)
         self._ck(self._lib.orc_mix_block(self._w, v.size, _ptr(v), _ptr(s), rows, int(frames), _ptr(bus), _ptr(peaks), _ptr(bus64), int(threads)))
         self.last_bus64 = bus64
         return bus, peaks

@@ -1,0 +1,46 @@
+"""TEST INFRASTRUCTURE: runs a Python script of this repository (bench.py, tools/...) against the CPU emulation of the library.
+
+    python tests/emu/run_emulated.py bench.py --voices 512 --frames 128 --steps 16 --warmup 8 --no-configs
+
+The binding is pointed at tests/emu/_build/libgas_b200_emu.so, CUDA devices of torch are redirected to the CPU (torch_shim) and
+child processes the script starts with sys.executable go through this launcher too.  Nothing it prints is a measurement.
+"""
+import os
+import runpy
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+
+def install():
+    for p in (ROOT, os.path.join(ROOT, "tests"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import build_emu
+    import torch_shim
+    lib_path = build_emu.build()
+    import gaspkg
+    gaspkg.load()
+    from godot_audio_spatializer_b200 import lib as gas_lib
+    gas_lib.LIB_PATH = lib_path
+    gas_lib._lib = None
+    torch_shim.install()
+    real_run = subprocess.run
+
+    def run(cmd, *a, **k):
+        if isinstance(cmd, (list, tuple)) and len(cmd) >= 2 and cmd[0] == sys.executable and str(cmd[1]).endswith(".py"):
+            cmd = [sys.executable, os.path.abspath(__file__)] + list(cmd[1:])
+        return real_run(cmd, *a, **k)
+
+    subprocess.run = run
+
+
+if __name__ == "__main__":
+    if len(sys.argv) < 2:
+        sys.exit(__doc__)
+    install()
+    script = sys.argv[1]
+    sys.argv = sys.argv[1:]
+    runpy.run_path(script, run_name="__main__")
