@@ -935,8 +935,8 @@ def gpu_arm(args):
         import subprocess
         res = None
         try:
-            cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--resident-leg", "--e2e-steps", str(max(8, min(K, args.e2e_steps)))],
-                                capture_output=True, text=True, timeout=300)
+            cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--resident-leg", "--e2e-steps", str(max(8, min(K, args.e2e_steps))),
+                                 "--voices", str(args.voices), "--frames", str(args.frames)], capture_output=True, text=True, timeout=300)
             for ln in reversed(cp.stdout.strip().splitlines()):
                 if ln.startswith("{"):
                     res = json.loads(ln)
@@ -1011,6 +1011,10 @@ def resident_leg(args):
     gas = gaspkg.load()
     abi, synth = gas.abi, gas.synth
     w = dict(WORKLOAD)
+    if args.voices:
+        w["voices"] = args.voices
+    if args.frames:
+        w["frames"] = args.frames
     V, F, C, B = w["voices"], w["frames"], w["speaker_mode"] + 1, w["num_buses"]
     out = {"unit": UNIT}
 

@@ -15,6 +15,9 @@
 #include <cuda_runtime.h>
 
 #include <execinfo.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <map>
 #include <sched.h>
 #include <signal.h>
 #include <sys/mman.h>
@@ -576,8 +579,12 @@ cudaError_t cudaGetLastError() {
 	t_last_error = cudaSuccess;
 	return e;
 }
+static int emulated_devices() {
+	static const int n = std::max(1, std::min(8, env_int("GAS_EMU_DEVICES", 1)));
+	return n;
+}
 cudaError_t cudaGetDeviceCount(int *n) {
-	*n = 1;
+	*n = emulated_devices();
 	return cudaSuccess;
 }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
@@ -591,17 +598,42 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
 	p->sharedMemPerBlockOptin = 227 * 1024;
 	return cudaSuccess;
 }
-cudaError_t cudaSetDevice(int dev) { return dev == 0 ? cudaSuccess : fail(cudaErrorInvalidValue); }
+cudaError_t cudaSetDevice(int dev) { return dev >= 0 && dev < emulated_devices() ? cudaSuccess : fail(cudaErrorInvalidValue); }
 cudaError_t cudaDeviceSynchronize() { return unsafe_call("cudaDeviceSynchronize"); }
+// GAS_EMU_IPC=1 (several emulated ranks, one process each): device allocations are shared mappings of memory files, so that
+// cudaIpcGetMemHandle / cudaIpcOpenMemHandle can hand them to the other processes (through /proc/<pid>/fd/<fd>)
+struct SharedAlloc {
+	int fd;
+	size_t bytes;
+};
+static std::mutex g_alloc_mu;
+static std::map<void *, SharedAlloc> g_shared, g_opened;
+static bool ipc_mode() {
+	static const bool on = env_int("GAS_EMU_IPC", 0) != 0;
+	return on;
+}
 cudaError_t cudaMalloc(void **p, size_t bytes) {
 	if (cudaError_t e = unsafe_call("cudaMalloc")) {
 		return e;
 	}
 	void *q = nullptr;
-	// like device memory, allocations are not zeroed: fill with a pattern that shows up when read before it is written
-	if (posix_memalign(&q, 256, bytes ? bytes : 1) != 0) {
+	const size_t n = bytes ? bytes : 1;
+	if (ipc_mode()) {
+		const int fd = memfd_create("gas_emu_alloc", 0);
+		if (fd < 0 || ftruncate(fd, (off_t)n) != 0) {
+			return fail(cudaErrorMemoryAllocation);
+		}
+		q = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+		if (q == MAP_FAILED) {
+			close(fd);
+			return fail(cudaErrorMemoryAllocation);
+		}
+		std::lock_guard<std::mutex> lk(g_alloc_mu);
+		g_shared[q] = SharedAlloc{ fd, n };
+	} else if (posix_memalign(&q, 256, n) != 0) {
 		return fail(cudaErrorMemoryAllocation);
 	}
+	// like device memory, allocations are not zeroed: fill with a pattern that shows up when read before it is written
 	if (bytes <= ((size_t)64 << 20)) {
 		memset(q, 0xa5, bytes);
 	}
@@ -611,6 +643,16 @@ cudaError_t cudaMalloc(void **p, size_t bytes) {
 cudaError_t cudaFree(void *p) {
 	if (cudaError_t e = unsafe_call("cudaFree")) {
 		return e;
+	}
+	if (ipc_mode()) {
+		std::lock_guard<std::mutex> lk(g_alloc_mu);
+		auto it = g_shared.find(p);
+		if (it != g_shared.end()) {
+			munmap(p, it->second.bytes);
+			close(it->second.fd);
+			g_shared.erase(it);
+		}
+		return cudaSuccess;
 	}
 	free(p);
 	return cudaSuccess;
@@ -776,14 +818,50 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t st) {
 	}
 	return cudaSuccess;
 }
-// one process only: there are no peers to map
+struct IpcHandle {
+	int pid, fd;
+	unsigned long long bytes;
+};
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
 	memset(h, 0, sizeof(*h));
-	memcpy(h->reserved, &p, sizeof(p));
+	std::lock_guard<std::mutex> lk(g_alloc_mu);
+	auto it = g_shared.find(p);
+	if (it == g_shared.end()) {
+		return fail(cudaErrorNotSupported); // not in IPC mode (GAS_EMU_IPC=1), or not the base of an allocation
+	}
+	IpcHandle ih{ (int)getpid(), it->second.fd, it->second.bytes };
+	memcpy(h->reserved, &ih, sizeof(ih));
 	return cudaSuccess;
 }
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return fail(cudaErrorNotSupported); }
-cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+	IpcHandle ih;
+	memcpy(&ih, h.reserved, sizeof(ih));
+	char path[64];
+	snprintf(path, sizeof(path), "/proc/%d/fd/%d", ih.pid, ih.fd);
+	const int fd = open(path, O_RDWR);
+	if (fd < 0) {
+		return fail(cudaErrorInvalidValue);
+	}
+	void *q = mmap(nullptr, (size_t)ih.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	close(fd);
+	if (q == MAP_FAILED) {
+		return fail(cudaErrorMemoryAllocation);
+	}
+	std::lock_guard<std::mutex> lk(g_alloc_mu);
+	g_opened[q] = SharedAlloc{ -1, (size_t)ih.bytes };
+	*p = q;
+	return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void *p) {
+	std::lock_guard<std::mutex> lk(g_alloc_mu);
+	auto it = g_opened.find(p);
+	if (it == g_opened.end()) {
+		return fail(cudaErrorInvalidValue);
+	}
+	munmap(p, it->second.bytes);
+	g_opened.erase(it);
+	return cudaSuccess;
+}
 
 // ---- statistics for the tests ----------------------------------------------------------------------------------------------------
 extern "C" __attribute__((visibility("default"))) void gas_emu_stats(unsigned long long *grids, unsigned long long *ctas) {

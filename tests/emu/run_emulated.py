@@ -15,6 +15,11 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 
 
 def install():
+    # under torchrun: one emulated device per local rank, device allocations shareable between the rank processes
+    lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    if lws > 1:
+        os.environ.setdefault("GAS_EMU_DEVICES", str(lws))
+        os.environ.setdefault("GAS_EMU_IPC", "1")
     for p in (ROOT, os.path.join(ROOT, "tests"), HERE):
         if p not in sys.path:
             sys.path.insert(0, p)

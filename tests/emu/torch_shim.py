@@ -86,9 +86,30 @@ def install():
 
     torch.Generator = generator
     torch.Tensor.pin_memory = lambda self, *a, **k: self
+    # factory functions called with device="cuda" / "cuda:0"
+    def _cpu_device_kw(fn):
+        def wrapped(*a, **k):
+            d = k.get("device")
+            if isinstance(d, str) and d.startswith("cuda"):
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return wrapped
+
+    for name in ("tensor", "zeros", "ones", "empty", "full", "rand", "randn", "arange", "zeros_like", "empty_like"):
+        setattr(torch, name, _cpu_device_kw(getattr(torch, name)))
+    # several emulated ranks: the process group runs over gloo
+    import torch.distributed as dist
+    real_init = dist.init_process_group
+
+    def init_process_group(backend=None, *a, **k):
+        k.pop("device_id", None)
+        return real_init("gloo", *a, **k)
+
+    dist.init_process_group = init_process_group
     c = torch.cuda
     c.is_available = lambda: True
-    c.device_count = lambda: 1
+    import os
+    c.device_count = lambda: int(os.environ.get("GAS_EMU_DEVICES", "1"))
     c.synchronize = lambda *a, **k: None
     c.set_device = lambda *a, **k: None
     c.current_device = lambda: 0

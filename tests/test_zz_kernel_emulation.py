@@ -45,3 +45,70 @@ def test_smoke_runs_on_the_emulated_device():
             "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" % ROOT)
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "SMOKE_OK" in r.stdout, (r.stdout + r.stderr)[-4000:]
+
+
+def _emulated(cmd, timeout, ranks=1, port=29650):
+    env = dict(os.environ, GAS_EMU_DEADLOCK_S="120", GAS_EMU_SMS="4")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "GAS_EMU"):
+        env.pop(k, None)
+    launcher = os.path.join(HERE, "emu", "run_emulated.py")
+    if ranks > 1:
+        full = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}", "--master-addr", "127.0.0.1",
+                "--master-port", str(port), launcher] + cmd
+    else:
+        full = [sys.executable, launcher] + cmd
+    return subprocess.run(full, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def _bench_line(stdout):
+    import json
+    for ln in reversed(stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return None
+
+
+BENCH_SMALL = ["--voices", "512", "--frames", "128", "--steps", "20", "--warmup", "5", "--e2e-steps", "4", "--no-configs"]
+
+
+def test_bench_single_gpu_flow_on_the_emulated_device():
+    """bench.py end to end at N = 1 (a small workload): graphs of the pipelined step kernel, profiled captures, the e2e legs (the
+    resident-sources leg in its child process included), the CPU baseline, the full parity gate — every key of the JSON line."""
+    if not shutil.which(os.environ.get("CXX", "g++")):
+        pytest.skip("needs g++")
+    r = _emulated([os.path.join(ROOT, "bench.py")] + BENCH_SMALL, 900)
+    line = _bench_line(r.stdout)
+    assert r.returncode == 0 and line, (r.stdout + r.stderr)[-3000:]
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks",
+                "parity", "config"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 20 and line["gpu_launches"] == 40  # step kernel + voice-parallel kernel per step
+    for blk in ("block0", "block1"):
+        p = line["parity"][blk]
+        assert p["routing_exact"] and p["within_1e-5_rel_or_-110dBFS_of_f32_oracle"]
+        assert p["peak_abs_bus_sample"] > 0 and p["max_abs_err_gpu_vs_f64_shadow"] < 1e-5 * max(1.0, p["peak_abs_bus_sample"])
+    # the resident-sources leg passed its own oracle check and was adopted
+    assert line["e2e"].get("parity_ok") is True and "host_frames" in line["e2e"], line["e2e"]
+
+
+@pytest.mark.parametrize("ranks,form", [(2, "pipelined"), (4, "block-call")])
+def test_bench_multi_gpu_flow_on_emulated_ranks(ranks, form):
+    """bench.py under torchrun with emulated ranks (one process each, exchange buffers mapped between the processes): the step
+    graphs with the peer-memory exchange inside, the start gate, the drain, the N > 1 e2e leg and the reduced-sum parity gate."""
+    if not shutil.which(os.environ.get("CXX", "g++")):
+        pytest.skip("needs g++")
+    r = _emulated([os.path.join(ROOT, "bench.py"), "--gpus", str(ranks)] + BENCH_SMALL, 900, ranks=ranks, port=29650 + ranks)
+    line = _bench_line(r.stdout)
+    assert r.returncode == 0 and line, (r.stdout + r.stderr)[-3000:]
+    assert line["n_gpus"] == ranks
+    pm = line["parity"]["multi_gpu_reduced_sum"]
+    assert pm["ranks"] == ranks and pm["routing_exact"] and pm["reduced_sum_within_1e-5_rel_or_-110dBFS_of_f32_oracle"], pm
+    assert ("gas_step_device" in line["config"]["launch"]) == (form == "pipelined")
+
+
+def test_peer_memory_reduce_on_emulated_ranks():
+    """tools/check_multi_gpu.py (what tests/test_comm_gpu.py runs on real GPUs) with 4 emulated ranks."""
+    if not shutil.which(os.environ.get("CXX", "g++")):
+        pytest.skip("needs g++")
+    r = _emulated([os.path.join(ROOT, "tools", "check_multi_gpu.py")], 900, ranks=4, port=29661)
+    assert r.returncode == 0 and "multi-GPU check ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
