@@ -3,9 +3,11 @@
 
 One *step* = one pass of the hot path over one mix block of synthetic input on every rank: gains (calculate_spatialization for
 every instance), plan (what process_frames / mix_channel and AudioServer decide per voice before their sample loops), ramped
-mix of every voice into the bus buffers, and (N > 1) the sum of the per-GPU partial bus buffers.  At 1 and 2 GPUs a step is ONE
-launch of the step kernel (gas_step_device: it streams block k while its control warps compute gains and plan of block k + 1); at 4
-and 8 GPUs the block-call form (gas_mix_block_device + gas_gain_compute_device) is used, see select_form().  Workload (BASELINE.json
+mix of every voice into the bus buffers, and (N > 1) the sum of the per-GPU partial bus buffers.  A step is ONE launch of the step
+kernel (gas_step_device: it streams block k while its control warps compute gains and plan of block k + 1).  At 4 and 8 GPUs — where
+that form never completed a run on hardware this round — it is measured in a watchdog-guarded child process per rank
+(guarded_pipelined_attempt); if a child stops making progress all are killed and the ranks measure with the block-call form
+(gas_mix_block_device + gas_gain_compute_device) instead, see select_form().  Workload (BASELINE.json
 configs[2] shape): AudioSpatializer3D, 16384 voices per GPU x 512-frame blocks at 48 kHz, 7.1 (4 channel pairs),
 mix_channel_mode on, two buses (Master + a reverb bus fed by the voices inside a reverb Area3D), attenuation filter inactive
 because the reference skips it below 0.001 linear gain (audio_spatializer_3d.cpp:568) — obtained with attenuation_filter_db = -80
@@ -215,11 +217,12 @@ def bench_config(w, world, peer=True):
 
 
 def select_form(world):
-    """Pipelined form (gas_step_device) at 1 and 2 GPUs, block-call form at 4 and 8 unless GAS_BENCH_PIPELINED is set.
-    The pipelined form was validated at 1 and 2 GPUs this round; the only 4- / 8-GPU run hung (an NCCL barrier enqueued while step
-    kernels were in flight, see barrier() in gpu_arm) and took the rest of the round's GPU budget with it, so the fix could not be
-    re-run there: 4 and 8 GPUs keep the block-call form, whose kernels never wait for each other's CTAs (the structure that ran on 8
-    GPUs in round 1)."""
+    """Pipelined form (gas_step_device) at 1 and 2 GPUs.  At 4 and 8 GPUs main() first tries it in guarded child processes
+    (GAS_BENCH_PIPELINED set for them); the process that lands here without that variable is the fallback and uses the block-call
+    form, whose kernels never wait for each other's CTAs (the structure that ran on 8 GPUs in round 1).
+    Background: the pipelined form was validated on hardware at 1 and 2 GPUs; the only 4- / 8-GPU run of the round hung (an NCCL
+    barrier enqueued while step kernels were in flight, see barrier() in gpu_arm) and took the rest of the round's GPU budget with
+    it, so the fix has only run on the CPU emulation of the library (tests/emu, 4 and 8 emulated ranks) since."""
     global CLASSIC
     if world >= 4 and not os.environ.get("GAS_BENCH_PIPELINED"):
         CLASSIC = True
@@ -251,6 +254,119 @@ def reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 4 / 8 GPUs: the pipelined form under a watchdog
+# ---------------------------------------------------------------------------------------------------------------
+def heartbeat(what=""):
+    """Child of guarded_pipelined_attempt: tells the parent that the main thread is alive (one file per rank)."""
+    path = os.environ.get("GAS_BENCH_HB_FILE")
+    if path:
+        try:
+            with open(path, "w") as f:
+                f.write(f"{time.time():.3f} {what}\n")
+        except OSError:
+            pass
+    if path and os.environ.get("GAS_BENCH_TEST_HANG") == what and dist_env()[0] == 1:  # tests: rank 1's child stops here for good
+        time.sleep(3600)
+
+
+def guarded_pipelined_attempt(args, hb_timeout=None, total_timeout=None):
+    """Runs this very command once more in a child process per rank with the pipelined form forced (own rendezvous port), under a
+    watchdog: a rank whose child stops reporting progress kills it and says so, every other rank then kills its own.  True = all
+    children finished and rank 0 has printed the child's line; False = the caller measures with the block-call form instead.
+
+    Why: the pipelined form was validated on hardware at 1 and 2 GPUs only; its single 4- / 8-GPU run of the round hung (an NCCL
+    barrier enqueued behind in-flight step kernels, since fixed in barrier()) and the fix could not be re-run on hardware.  A hang
+    must cost the scaling run some time, never its data points."""
+    import subprocess
+    rank, _, world = dist_env()
+    hb_timeout = hb_timeout or float(os.environ.get("GAS_BENCH_HB_TIMEOUT", "120"))
+    total_timeout = total_timeout or float(os.environ.get("GAS_BENCH_ATTEMPT_TIMEOUT", "420"))
+    port = int(os.environ.get("MASTER_PORT", "29500"))
+    try:  # one directory per launch: the launcher's pid and start time (the ranks of one launch share both)
+        with open(f"/proc/{os.getppid()}/stat") as f:
+            born = f.read().rsplit(")", 1)[1].split()[19]
+    except Exception:
+        born = "0"
+    run_dir = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"gas_bench_{os.getppid()}_{born}_{port}")
+    os.makedirs(run_dir, exist_ok=True)
+    hb_file = os.path.join(run_dir, f"hb_{rank}")
+    out_file = os.path.join(run_dir, f"out_{rank}")
+    err_file = os.path.join(run_dir, f"err_{rank}")
+
+    def flag(r):
+        return os.path.join(run_dir, f"done_{r}")
+
+    env = dict(os.environ, MASTER_PORT=str(port + 53), GAS_BENCH_PIPELINED="1", GAS_BENCH_CHILD="1", GAS_BENCH_HB_FILE=hb_file)
+    env.pop("TORCHELASTIC_USE_AGENT_STORE", None)  # the children rendezvous on a store of their own (rank 0's child hosts it)
+    t0 = time.time()
+    with open(hb_file, "w") as f:
+        f.write(f"{t0:.3f} spawn\n")
+    ok, why = False, ""
+    with open(out_file, "w") as fo, open(err_file, "w") as fe:
+        child = subprocess.Popen([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, stdout=fo, stderr=fe)
+        while True:
+            rc = child.poll()
+            if rc is not None:
+                ok, why = rc == 0, f"exit {rc}"
+                break
+            now = time.time()
+            try:
+                last = os.path.getmtime(hb_file)
+                started = not open(hb_file).read().rstrip().endswith("spawn")
+            except OSError:
+                last, started = t0, False
+            limit = hb_timeout if started else 2 * hb_timeout  # the first import of torch on a fresh box can take a minute
+            others_failed = any(os.path.exists(flag(r)) and open(flag(r)).read().startswith("fail") for r in range(world) if r != rank)
+            if now - last > limit or now - t0 > total_timeout or others_failed:
+                why = "another rank gave up" if others_failed else f"no progress for {now - last:.0f} s (total {now - t0:.0f} s)"
+                child.kill()
+                try:
+                    child.wait(timeout=30)
+                except Exception:
+                    pass
+                break
+            time.sleep(0.5)
+    try:  # what the child said on stderr (NCCL's own log lines among it) belongs to this run's stderr
+        with open(err_file) as f:
+            sys.stderr.write(f.read()[-200000:])
+        sys.stderr.flush()
+    except OSError:
+        pass
+    with open(flag(rank) + ".tmp", "w") as f:
+        f.write(("ok " if ok else "fail ") + why + "\n")
+    os.replace(flag(rank) + ".tmp", flag(rank))
+    # every rank decides the same way: wait for all verdicts
+    t1 = time.time()
+    verdicts = {}
+    while len(verdicts) < world and time.time() - t1 < hb_timeout + 60:
+        for r in range(world):
+            if r not in verdicts and os.path.exists(flag(r)):
+                verdicts[r] = open(flag(r)).read().strip()
+        time.sleep(0.2)
+    all_ok = len(verdicts) == world and all(v.startswith("ok") for v in verdicts.values())
+    line = None
+    if rank == 0:
+        if all_ok:
+            try:
+                for ln in reversed(open(out_file).read().strip().splitlines()):
+                    if ln.startswith("{"):
+                        line = json.loads(ln)
+                        break
+            except Exception:
+                line = None
+            all_ok = line is not None
+            if not all_ok:  # (the other ranks cannot see this: they leave, rank 0 reports the failure instead of a number)
+                print(json.dumps({"error": "pipelined attempt finished without a result line", "n_gpus": world}), flush=True)
+                return True
+        if all_ok:
+            line["form"] = "pipelined (gas_step_device), measured in a watchdog-guarded child process per rank"
+            print(json.dumps(line), flush=True)
+        else:
+            print(f"[bench] pipelined attempt at {world} GPUs abandoned ({verdicts}); measuring with the block-call form", file=sys.stderr, flush=True)
+    return all_ok
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -697,6 +813,7 @@ def gpu_arm(args):
     gas = gaspkg.load()
     abi, synth = gas.abi, gas.synth
     rank, local_rank, world = dist_env()
+    heartbeat("imported")
     torch.cuda.set_device(local_rank)
     select_form(world)
     dist = None
@@ -719,8 +836,10 @@ def gpu_arm(args):
     W = ((W + chunk - 1) // chunk) * chunk
 
     parity_src = synth.make_sources(V, F, block=0, mix_rate=w["mix_rate"]) if (rank == 0 and not args.no_parity) else None
+    heartbeat("process group")
     dw = DeviceWorkload(gas, torch, w, local_rank, rank, parity_src)
     m = dw.mixer
+    heartbeat("workload resident")
     stream = torch.cuda.ExternalStream(m.mix_stream, device=torch.device("cuda", local_rank))
 
     parity = None
@@ -736,7 +855,9 @@ def gpu_arm(args):
     if dist is not None and not peer:
         chunk = 1  # the NCCL variant reduces between graph launches
         W = max(3, args.warmup, N_SETS)
+    heartbeat("exchange open")
     graphs = dw.capture_steps(chunk)
+    heartbeat("captured")
     sampler = ClockSampler(local_rank)  # NVML initialised here, outside the timed region
 
     def run_steps(k0, n):
@@ -763,6 +884,7 @@ def gpu_arm(args):
     run_steps(0, W)
     dw.reduce_drain(W - 1)
     barrier()
+    heartbeat("warm")
     sampler.start()
     if peer:
         # device-side start gate: an in-order reduce of a scratch buffer is one arrival round over peer memory, so every
@@ -782,6 +904,7 @@ def gpu_arm(args):
     with torch.cuda.stream(stream):
         ev2.record()
     barrier()
+    heartbeat("timed")
     t_wall1 = time.time()
     sampler.stop()
     sampler.join()
@@ -821,6 +944,7 @@ def gpu_arm(args):
     dw.no_gain = False
     m.profile_enable(False)
     barrier()
+    heartbeat("profiled")
     parity_multi = None
     if dist is not None and peer and not args.no_parity:
         parity_multi = parity_gate_multi(gas, torch, dist, w, local_rank, rank, world, abi, synth)
@@ -828,6 +952,7 @@ def gpu_arm(args):
         parity = parity_gate(gas, w, local_rank, abi, synth, parity_src, host_inputs)
         if parity_multi is not None:
             parity["multi_gpu_reduced_sum"] = parity_multi
+    heartbeat("parity")
     k2_ms, k2_n = prof["mix_stream"]
     peak, peak_src = measured_hbm_peak()
     bytes_launch = algorithmic_bytes(V, F, C, B)
@@ -913,6 +1038,7 @@ def gpu_arm(args):
     for k in range(3):
         e2e_step(k)
     barrier()
+    heartbeat("e2e warm")
     t0 = time.perf_counter()
     for k in range(ke):
         e2e_step(k)
@@ -981,6 +1107,7 @@ def gpu_arm(args):
             except Exception as ex:  # a secondary configuration must not take the headline line down with it
                 configs.append({"config": spec["name"], "error": repr(ex)[:300]})
 
+    heartbeat("e2e")
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -1141,6 +1268,11 @@ def main():
     elif args.impl == "reference":
         reference_arm(args)
     else:
+        _, _, world = dist_env()
+        if (world >= 4 and not os.environ.get("GAS_BENCH_CHILD") and not os.environ.get("GAS_BENCH_PIPELINED")
+                and not os.environ.get("GAS_BENCH_CLASSIC") and not os.environ.get("GAS_BENCH_NO_ATTEMPT")):
+            if guarded_pipelined_attempt(args):
+                return
         gpu_arm(args)
 
 

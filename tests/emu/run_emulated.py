@@ -32,14 +32,15 @@ def install():
     gas_lib.LIB_PATH = lib_path
     gas_lib._lib = None
     torch_shim.install()
-    real_run = subprocess.run
+    real_popen = subprocess.Popen
 
-    def run(cmd, *a, **k):
-        if isinstance(cmd, (list, tuple)) and len(cmd) >= 2 and cmd[0] == sys.executable and str(cmd[1]).endswith(".py"):
-            cmd = [sys.executable, os.path.abspath(__file__)] + list(cmd[1:])
-        return real_run(cmd, *a, **k)
+    class Popen(real_popen):  # children started with sys.executable run emulated too
+        def __init__(self, cmd, *a, **k):
+            if isinstance(cmd, (list, tuple)) and len(cmd) >= 2 and cmd[0] == sys.executable and str(cmd[1]).endswith(".py"):
+                cmd = [sys.executable, os.path.abspath(__file__)] + list(cmd[1:])
+            super().__init__(cmd, *a, **k)
 
-    subprocess.run = run
+    subprocess.Popen = Popen
 
 
 if __name__ == "__main__":

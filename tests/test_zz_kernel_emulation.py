@@ -47,8 +47,8 @@ def test_smoke_runs_on_the_emulated_device():
     assert r.returncode == 0 and "SMOKE_OK" in r.stdout, (r.stdout + r.stderr)[-4000:]
 
 
-def _emulated(cmd, timeout, ranks=1, port=29650):
-    env = dict(os.environ, GAS_EMU_DEADLOCK_S="120", GAS_EMU_SMS="4")
+def _emulated(cmd, timeout, ranks=1, port=29650, extra_env=None):
+    env = dict(os.environ, GAS_EMU_DEADLOCK_S="120", GAS_EMU_SMS="4", **(extra_env or {}))
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "GAS_EMU"):
         env.pop(k, None)
     launcher = os.path.join(HERE, "emu", "run_emulated.py")
@@ -91,19 +91,25 @@ def test_bench_single_gpu_flow_on_the_emulated_device():
     assert line["e2e"].get("parity_ok") is True and "host_frames" in line["e2e"], line["e2e"]
 
 
-@pytest.mark.parametrize("ranks,form", [(2, "pipelined"), (4, "block-call")])
-def test_bench_multi_gpu_flow_on_emulated_ranks(ranks, form):
+@pytest.mark.parametrize("ranks,hang,form", [(2, False, "pipelined"), (4, False, "pipelined"), (4, True, "block-call")])
+def test_bench_multi_gpu_flow_on_emulated_ranks(ranks, hang, form):
     """bench.py under torchrun with emulated ranks (one process each, exchange buffers mapped between the processes): the step
-    graphs with the peer-memory exchange inside, the start gate, the drain, the N > 1 e2e leg and the reduced-sum parity gate."""
+    graphs with the peer-memory exchange inside, the start gate, the drain, the N > 1 e2e leg and the reduced-sum parity gate.
+    At 4 ranks the pipelined form runs in watchdog-guarded child processes (bench.guarded_pipelined_attempt); with `hang` the
+    child of rank 1 stops after the warm-up, the watchdogs kill all children and the ranks measure with the block-call form."""
     if not shutil.which(os.environ.get("CXX", "g++")):
         pytest.skip("needs g++")
-    r = _emulated([os.path.join(ROOT, "bench.py"), "--gpus", str(ranks)] + BENCH_SMALL, 900, ranks=ranks, port=29650 + ranks)
+    extra = dict(GAS_BENCH_TEST_HANG="warm", GAS_BENCH_HB_TIMEOUT="15") if hang else {}
+    r = _emulated([os.path.join(ROOT, "bench.py"), "--gpus", str(ranks)] + BENCH_SMALL, 900, ranks=ranks, port=29650 + 3 * ranks + int(hang), extra_env=extra)
     line = _bench_line(r.stdout)
     assert r.returncode == 0 and line, (r.stdout + r.stderr)[-3000:]
     assert line["n_gpus"] == ranks
     pm = line["parity"]["multi_gpu_reduced_sum"]
     assert pm["ranks"] == ranks and pm["routing_exact"] and pm["reduced_sum_within_1e-5_rel_or_-110dBFS_of_f32_oracle"], pm
     assert ("gas_step_device" in line["config"]["launch"]) == (form == "pipelined")
+    if ranks >= 4:
+        assert ("form" in line) == (form == "pipelined")
+        assert ("abandoned" in r.stderr) == hang
 
 
 def test_peer_memory_reduce_on_emulated_ranks():
