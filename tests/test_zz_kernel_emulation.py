@@ -118,3 +118,15 @@ def test_peer_memory_reduce_on_emulated_ranks():
         pytest.skip("needs g++")
     r = _emulated([os.path.join(ROOT, "tools", "check_multi_gpu.py")], 900, ranks=4, port=29661)
     assert r.returncode == 0 and "multi-GPU check ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+@pytest.mark.parametrize("form", ["block-call", "pipelined"])
+def test_randomised_parity_campaign_on_the_emulated_device(form):
+    """tools/fuzz_parity.py: seeded random scenarios over every knob of the path (speaker modes, Mode A / B, effect chains, all
+    attenuation models, areas, overriding buses, two listeners, Doppler, polyphony, late starts, silent rows, peaks, odd block sizes),
+    CUDA sources on the emulated device against the oracle."""
+    if not shutil.which(os.environ.get("CXX", "g++")):
+        pytest.skip("needs g++")
+    cmd = [os.path.join(ROOT, "tools", "fuzz_parity.py"), "--cases", "80", "--seed", "11"] + (["--pipelined"] if form == "pipelined" else [])
+    r = _emulated(cmd, 900)
+    assert r.returncode == 0 and "80 / 80 cases match the oracle" in r.stdout, (r.stdout + r.stderr)[-3000:]
