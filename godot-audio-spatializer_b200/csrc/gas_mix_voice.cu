@@ -5,18 +5,18 @@
 // AudioFilterSW::Processor) or an AudioSpatializerEffect filter chain (reference
 // audio_spatializer_effect.cpp:33-77) — and voices that must report a block peak
 // (reference audio_spatializer.cpp:419-461) run here, serial in time with the filter state in registers for
-// the whole block.  The parallel axis is the *stream*, not the voice:
-//   Mode B   one lane per (voice, pair, side): the voice's 2C biquads run side by side, 4 voices per warp;
-//   Mode A / effect chains   one lane per (voice, side), 16 voices per warp.
-// After the per-stream work the AudioServer ramp (upstream _mix_step_for_channel) is applied per lane, the
-// voices of the warp are summed with shuffles and the result is added to a CTA-wide accumulation tile in
-// shared memory (the whole bus layout of the block, explicit red.shared); the CTA adds its tile to the bus
-// buffers once, with one vector reduction per 16 bytes.  The launch also folds the streaming kernel's partial
-// sums (replicas) into the bus buffers, so it runs every block.
-//
-// Sends are processed two at a time; a voice with more than two sends (bus transitions) is run in
-// several passes from the same initial state — every pass recomputes bit-identical samples, only the
-// last one stores state and peaks.
+// the whole block.  The parallel axis is the *stream*, not the voice.  Two forms:
+//   filter-tile path (Mode A and effect chains of the ordinary classes): the whole CTA works on a batch of voices; one
+//        lane per (voice, side) runs nothing but the biquads and hands the processed stream to a frame-parallel
+//        contraction through shared memory, 64 frames at a time (see "filter-tile path" below);
+//   per-warp path (Mode B: one lane per (voice, pair, side), 4 voices per warp; generic classes: one voice per warp):
+//        after the per-stream work the AudioServer ramp (upstream _mix_step_for_channel) is applied per lane, the
+//        voices of the warp are summed with shuffles and the result is added to the CTA's accumulation tile with
+//        explicit red.shared.  Sends are processed two at a time; a voice with more than two sends (bus transitions) is
+//        run in several passes from the same initial state — every pass recomputes bit-identical samples, only the last
+//        one stores state and peaks.
+// Both add into a CTA-wide accumulation tile in shared memory (the whole bus layout of the block); the CTA adds its tile to
+// the bus buffers once, with one vector reduction per 16 bytes.
 #include "gas_internal.h"
 
 namespace {
@@ -447,11 +447,374 @@ __device__ void voice_chunk_s(const DevTables &t, const ChunkArgs &a, const gas_
 	}
 }
 
-// units of a class: Mode B runs 4 voices per warp, Mode A / effect chains 16; the generic class (voices whose own class
-// found no slot) runs one voice per unit, because its voices do not share a send layout
+// ---- filter-tile path: Mode A and effect chains of the ordinary (non-generic) classes ------------------------------------
+// The recurrence and the cross-voice sum are two different shapes of work, so they get two different thread mappings inside
+// one CTA, handing over through shared memory, a tile of kFtFrames frames at a time:
+//   source tiles    the voices' rows of the NEXT tile are copied global -> shared memory asynchronously (cp.async, 16 bytes per
+//                   thread and copy) while the current tile is worked on: a tile of work (> 1 us) covers the DRAM latency,
+//                   which a register prefetch one 8-frame trip ahead (the per-warp form) does not.
+//   filter phase    one lane per (voice, side): nothing but the biquads (state in registers for the whole block) and the
+//                   block peak, in place on the tile in shared memory (x in, y out).  The lanes carry no ramps, no
+//                   cross-lane reduction and no atomics (the per-warp form above spends three quarters of its instructions on
+//                   those, inside the serial loop, and its red.shared.add.f32 compiles to a compare-and-swap loop).
+//   contraction     one thread per (frame, row group), all 256 threads: bus[b][c][i] += (p + t (n - p)) y_v[i] summed over the
+//                   voices of the unit, weights {p_L, p_R, n_L - p_L, n_R - p_R} staged once per unit, read as 16-byte broadcasts,
+//                   two packed FMAs (FFMA2) per (voice, row), accumulators in registers, added to the CTA's bus tile without
+//                   atomics (every (row, frame) has one owner).  The ramp is evaluated as p + t (n - p) instead of the
+//                   reference's n t + (1 - t) p: within 2 ulp of it, far inside the 1e-5 tolerance.
+// A unit is a batch of up to kFtVoices voices of one class; the batch size is chosen so that the units of a block just cover
+// the grid (the filter phase takes F serial steps however many lanes it has: more, smaller units are faster).
+constexpr int kFtVoices = 56;                              // voices per unit (2 lanes each in the filter phase): 16384 voices on 2 x 148 CTAs
+constexpr int kFtFrames = 64;                              // frames per tile
+constexpr int kFtYStride = kFtFrames * 2 + 4;              // floats per voice row of a tile (rows stay 16-byte aligned for the async copies;
+                                                           // +4: the (voice, side) lanes of a warp spread over the banks, two per bank)
+constexpr int kFtRows = 16;                                // weight rows (send x pair) of a class: 4 sends (2 current + 2 fading out) x 4 pairs
+constexpr int kFtYFloats = kFtVoices * kFtYStride;         // 7392 per tile buffer; two buffers: the tile being worked on and the next one in flight
+constexpr int kFtWFloats = kFtVoices * kFtRows * 4;        // 3584
+constexpr int kFtSmemBytes = (2 * kFtYFloats + kFtWFloats) * 4;
+constexpr int kFtFastStages = 4;                           // effect chains with up to this many biquads per side keep them in registers
+static_assert((kFtYFloats * 4) % 16 == 0 && (kFtYStride * 4) % 16 == 0, "tile rows are written and the weight tile behind them is read 16 bytes at a time");
+static_assert(kWarpsPerCta * 32 == 4 * kFtFrames, "contraction mapping: 4 row groups x kFtFrames frames");
+
+// (the planner sends voices with more than two buses on a side to the generic class, so an ordinary class has at most 4 sends;
+// anything wider than the weight tile stays on the per-warp path)
+template <int C>
+__device__ __forceinline__ bool ft_class(const ClassInfo &ci) {
+	return ci.mode != MODE_B && !(ci.flags & CLS_GENERIC) && ci.n_send * C <= kFtRows;
+}
+
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+	for (int s = 0; s < n; s++) {
+		m &= m - 1;
+	}
+	return m ? (__ffs(m) - 1) : 0;
+}
+
+// source frames [i0, i0 + kFtFrames) of the unit's voices -> tile buffer, asynchronously (silent voices: zeros)
+__device__ __forceinline__ void ft_prefetch(const gas_frame *__restrict__ src, int src_stride, const int2 *__restrict__ list, int nv, int i0, int F,
+		float *buf) {
+	const int chunks = min(kFtFrames, F - i0) >> 1; // 16-byte chunks (2 frames) per row; F is even
+	for (int idx = threadIdx.x; idx < nv * (kFtFrames / 2); idx += blockDim.x) {
+		const int v = idx / (kFtFrames / 2), ch = idx % (kFtFrames / 2);
+		if (ch < chunks) {
+			const int srow = list[v].y;
+			float *dst = buf + v * kFtYStride + ch * 4;
+			if (srow >= 0) {
+				gas_cp_async_16(dst, src + (size_t)srow * src_stride + i0 + ch * 2);
+			} else {
+				*reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+		}
+	}
+}
+
+// weights of the unit's voices, rows [0, nrows) -> shared memory
+template <int C>
+__device__ __forceinline__ void ft_stage_weights(const InstSends *__restrict__ sends, const int2 *__restrict__ list, int nv, int nrows, float4 *s_w) {
+	for (int idx = threadIdx.x; idx < nv * nrows; idx += blockDim.x) {
+		const int v = idx / nrows, r = idx % nrows;
+		const int s = r / C, c = r % C;
+		const InstSends *snd = &sends[list[v].x];
+		const float p0 = snd->vp[s][c][0], p1 = snd->vp[s][c][1];
+		const float n0 = snd->vn[s][c][0], n1 = snd->vn[s][c][1];
+		s_w[idx] = make_float4(p0, p1, n0 - p0, n1 - p1);
+	}
+}
+
+// rows [0, nrows) x frames [i0, i0 + kFtFrames) of the unit: sum over its voices, added to the bus tile / buffers
+template <int C>
+__device__ __forceinline__ void ft_contract(const float *s_y, const float4 *s_w, int nv, int nrows, const int (&rowoff)[kFtRows / 4], int i0, int F,
+		float *__restrict__ bus, float *s_tile) {
+	const int f = threadIdx.x & (kFtFrames - 1), rg = threadIdx.x / kFtFrames;
+	const int mine = (nrows - rg + 3) >> 2; // rows rg, rg + 4, ...
+	const int i = i0 + f;
+	if (mine <= 0 || i >= F) {
+		return;
+	}
+	constexpr int kMine = kFtRows / 4;
+	const float tt = (float)i / (float)F; // upstream _mix_step_for_channel: t = i / F
+	const float2 t2 = make_float2(tt, tt);
+	float2 acc[kMine];
+#pragma unroll
+	for (int q = 0; q < kMine; q++) {
+		acc[q] = make_float2(0.f, 0.f);
+	}
+	const float *yp = s_y + f * 2;
+	const float4 *wp = s_w + rg;
+#pragma unroll 4
+	for (int v = 0; v < nv; v++) {
+		const float2 y = *reinterpret_cast<const float2 *>(yp + v * kFtYStride);
+#pragma unroll
+		for (int q = 0; q < kMine; q++) {
+			if (q < mine) {
+				const float4 w4 = wp[v * nrows + q * 4];
+				const float2 w = gas_ffma2(t2, make_float2(w4.z, w4.w), make_float2(w4.x, w4.y));
+				acc[q] = gas_ffma2(w, y, acc[q]);
+			}
+		}
+	}
+#pragma unroll
+	for (int q = 0; q < kMine; q++) {
+		if (q < mine) {
+			const size_t o = (size_t)rowoff[q] + (size_t)i * 2;
+			if (s_tile) {
+				float2 *d = reinterpret_cast<float2 *>(s_tile + o); // one owner per (row, frame): no atomics
+				float2 cur = *d;
+				cur.x += acc[q].x;
+				cur.y += acc[q].y;
+				*d = cur;
+			} else {
+				atomicAdd(bus + o, acc[q].x);
+				atomicAdd(bus + o + 1, acc[q].y);
+			}
+		}
+	}
+}
+
+enum : int { FT_A = 0, FT_E_FAST = 1, FT_E_SLOW = 2, FT_COPY = 3 }; // FT_COPY: Mode A below the filter threshold (peaks only): y = x
+
+// One unit: voices list[0 .. nv) of class `ci`.  Every thread of the CTA takes part (the barriers are CTA-wide).
+template <int VAR, int C>
+__device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, const VoiceRec *__restrict__ recs, const InstSends *__restrict__ sends,
+		const int2 *__restrict__ list, int nv, const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float *s_tile,
+		float2 *__restrict__ peaks, float *s_y, float4 *s_w) {
+	const int vl = threadIdx.x >> 1, side = threadIdx.x & 1; // filter phase: lane = (voice, side)
+	const bool active = vl < nv;
+	const int j = active ? list[vl].x : 0;
+	const VoiceRec *rec = &recs[j];
+	const int voice = active ? rec->voice : 0;
+	const uint32_t flags = active ? rec->flags : 0u;
+	const bool filt = VAR == FT_A;
+
+	// FT_A: the interpolated high-shelf processor of this side (index 0 left, 1 right, reference audio_spatializer_3d.cpp:524-529)
+	gas_processor_state *ps = t.vs_proc + (size_t)voice * 8 + side;
+	gas_processor_state st{};
+	Biquad h{};
+	float cf[5] = {}, inc[5] = {};
+	if (VAR == FT_A) {
+		if (active && filt) {
+			st = *ps;
+		}
+		const bool clear = (flags >> 8) & 1u; // is_just_started => clear history (:518-521)
+		h.ha1 = clear ? 0.f : st.ha1;
+		h.ha2 = clear ? 0.f : st.ha2;
+		h.hb1 = clear ? 0.f : st.hb1;
+		h.hb2 = clear ? 0.f : st.hb2;
+		cf[0] = st.b0;
+		cf[1] = st.b1;
+		cf[2] = st.b2;
+		cf[3] = st.a1;
+		cf[4] = st.a2;
+#pragma unroll
+		for (int q = 0; q < 5; q++) {
+			inc[q] = ((active ? rec->target[q] : 0.f) - cf[q]) / (float)F; // update_coeffs(F)
+		}
+	}
+	// effect chains: cascaded constant-coefficient biquads (upstream AudioEffectFilter::process), histories
+	// [effect][side][stage]{ha1,ha2,hb1,hb2} in vs_fx
+	float *fxs = t.vs_fx + (size_t)voice * (GAS_MAX_EFFECTS * 2 * GAS_MAX_FILTER_STAGES * 4);
+	const int n_fx = ((VAR == FT_E_FAST || VAR == FT_E_SLOW) && active) ? rec->n_fx : 0;
+	// FT_E_FAST: the chain flattened to at most kFtFastStages biquads, coefficients and histories in registers
+	int n_slot = 0;
+	int e_of[kFtFastStages] = {}, q_of[kFtFastStages] = {};
+	float sc[kFtFastStages][5] = {}, sh[kFtFastStages][4] = {};
+	// FT_E_SLOW: any chain (dynamic shape: local memory)
+	float fxh[VAR == FT_E_SLOW ? GAS_MAX_EFFECTS : 1][VAR == FT_E_SLOW ? GAS_MAX_FILTER_STAGES : 1][4];
+	if (VAR == FT_E_FAST) {
+#pragma unroll
+		for (int e = 0; e < GAS_MAX_EFFECTS; e++) {
+			const int stages = e < n_fx ? rec->fx_stages[e] : 0;
+#pragma unroll
+			for (int q = 0; q < GAS_MAX_FILTER_STAGES; q++) {
+				const bool on = q < stages;
+#pragma unroll
+				for (int s = 0; s < kFtFastStages; s++) {
+					if (on && n_slot == s) {
+						e_of[s] = e;
+						q_of[s] = q;
+					}
+				}
+				n_slot += on ? 1 : 0;
+			}
+		}
+#pragma unroll
+		for (int s = 0; s < kFtFastStages; s++) {
+			if (s < n_slot) {
+#pragma unroll
+				for (int k = 0; k < 5; k++) {
+					sc[s][k] = rec->fx_coef[e_of[s]][k];
+				}
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					sh[s][k] = fxs[((e_of[s] * 2 + side) * GAS_MAX_FILTER_STAGES + q_of[s]) * 4 + k];
+				}
+			}
+		}
+	}
+	if (VAR == FT_E_SLOW) {
+		for (int e = 0; e < GAS_MAX_EFFECTS; e++) {
+			for (int q = 0; q < GAS_MAX_FILTER_STAGES; q++) {
+				for (int k = 0; k < 4; k++) {
+					fxh[VAR == FT_E_SLOW ? e : 0][VAR == FT_E_SLOW ? q : 0][k] = e < n_fx ? fxs[((e * 2 + side) * GAS_MAX_FILTER_STAGES + q) * 4 + k] : 0.f;
+				}
+			}
+		}
+	}
+
+	const int R = ci.n_send * C; // <= kFtRows (ft_class)
+	ft_stage_weights<C>(sends, list, nv, R, s_w); // visible to the contraction after the barrier behind the first filter phase
+
+	float pk = 0.f;
+	// one frame of this lane's stream: the biquads and the block peak (audio_spatializer.cpp:436-443, :453-460)
+	auto step = [&](float y) -> float {
+		if (VAR == FT_A) {
+			y = biquad_step(h, y, cf[0], cf[1], cf[2], cf[3], cf[4]);
+#pragma unroll
+			for (int q = 0; q < 5; q++) { // process_one_interp: coeffs += incr
+				cf[q] += inc[q];
+			}
+		} else if (VAR == FT_E_FAST) {
+#pragma unroll
+			for (int s = 0; s < kFtFastStages; s++) {
+				if (s < n_slot) {
+					const float pre = y;
+					y = y * sc[s][0] + sh[s][2] * sc[s][1] + sh[s][3] * sc[s][2] + sh[s][0] * sc[s][3] + sh[s][1] * sc[s][4];
+					sh[s][1] = sh[s][0];
+					sh[s][3] = sh[s][2];
+					sh[s][2] = pre;
+					sh[s][0] = y;
+				}
+			}
+		} else if (VAR == FT_E_SLOW) {
+			for (int e = 0; e < n_fx; e++) {
+				const float b0 = rec->fx_coef[e][0], b1 = rec->fx_coef[e][1], b2 = rec->fx_coef[e][2], a1 = rec->fx_coef[e][3], a2 = rec->fx_coef[e][4];
+				const int stages = rec->fx_stages[e];
+				for (int q = 0; q < stages; q++) {
+					float *hh = fxh[VAR == FT_E_SLOW ? e : 0][VAR == FT_E_SLOW ? q : 0];
+					const float pre = y;
+					y = y * b0 + hh[2] * b1 + hh[3] * b2 + hh[0] * a1 + hh[1] * a2;
+					hh[1] = hh[0];
+					hh[3] = hh[2];
+					hh[2] = pre;
+					hh[0] = y;
+				}
+			}
+		}
+		pk = fmaxf(pk, fabsf(y));
+		return y;
+	};
+	// contraction: this thread's rows rg, rg + 4, ... -> float offset of (bus, pair, frame 0) in the bus layout
+	int rowoff[kFtRows / 4];
+#pragma unroll
+	for (int q = 0; q < kFtRows / 4; q++) {
+		const int r = (int)threadIdx.x / kFtFrames + q * 4;
+		rowoff[q] = r < R ? (nth_set_bit(ci.mask, r / C) * C + r % C) * F * 2 : 0;
+	}
+	ft_prefetch(src, src_stride, list, nv, 0, F, s_y);
+	for (int i0 = 0, ti = 0; i0 < F; i0 += kFtFrames, ti++) {
+		float *buf = s_y + (ti & 1) * kFtYFloats;
+		gas_cp_async_wait_all(); // this thread's copies of the tile have landed ...
+		__syncthreads();         // ... and everybody else's; the other buffer (read by the previous contraction) is free
+		if (i0 + kFtFrames < F) {
+			ft_prefetch(src, src_stride, list, nv, i0 + kFtFrames, F, s_y + ((ti + 1) & 1) * kFtYFloats);
+		}
+		// ---- filter phase: in place on the tile ----
+		if (active) {
+			float *xr = buf + vl * kFtYStride + side;
+			for (int k0 = 0; k0 < kFtFrames && i0 + k0 < F; k0 += 8) {
+				if (i0 + k0 + 8 <= F) { // a whole trip inside the block: no per-frame bounds test between the recurrence steps
+					float xv[8];
+#pragma unroll
+					for (int k = 0; k < 8; k++) {
+						xv[k] = xr[(k0 + k) * 2];
+					}
+#pragma unroll
+					for (int k = 0; k < 8; k++) {
+						xr[(k0 + k) * 2] = step(xv[k]);
+					}
+				} else {
+					for (int k = 0; k < 8 && i0 + k0 + k < F; k++) {
+						xr[(k0 + k) * 2] = step(xr[(k0 + k) * 2]);
+					}
+				}
+			}
+		}
+		__syncthreads();
+		// ---- contraction ----
+		ft_contract<C>(buf, s_w, nv, R, rowoff, i0, F, bus, s_tile);
+	}
+	__syncthreads(); // the next unit's copies and weights overwrite what the last contraction read
+	if (active) {
+		if (VAR == FT_A && filt) {
+			st.b0 = cf[0];
+			st.b1 = cf[1];
+			st.b2 = cf[2];
+			st.a1 = cf[3];
+			st.a2 = cf[4];
+			st.ha1 = h.ha1;
+			st.ha2 = h.ha2;
+			st.hb1 = h.hb1;
+			st.hb2 = h.hb2;
+			*ps = st;
+		}
+		if (VAR == FT_E_FAST) {
+#pragma unroll
+			for (int s = 0; s < kFtFastStages; s++) {
+				if (s < n_slot) {
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						fxs[((e_of[s] * 2 + side) * GAS_MAX_FILTER_STAGES + q_of[s]) * 4 + k] = sh[s][k];
+					}
+				}
+			}
+		}
+		if (VAR == FT_E_SLOW) {
+			for (int e = 0; e < n_fx; e++) {
+				for (int q = 0; q < GAS_MAX_FILTER_STAGES; q++) {
+					for (int k = 0; k < 4; k++) {
+						fxs[((e * 2 + side) * GAS_MAX_FILTER_STAGES + q) * 4 + k] = fxh[VAR == FT_E_SLOW ? e : 0][VAR == FT_E_SLOW ? q : 0][k];
+					}
+				}
+			}
+		}
+		if ((flags & GAS_VOICE_WANT_PEAK) && peaks) {
+			reinterpret_cast<float *>(peaks + j)[side] = pk;
+		}
+	}
+}
+
+// biquads per side of the longest effect chain among voices list[0 .. nv) (CTA-uniform result; every thread calls it)
+__device__ int ft_max_stages(const VoiceRec *__restrict__ recs, const int2 *__restrict__ list, int nv, int *s_scratch) {
+	if (threadIdx.x == 0) {
+		*s_scratch = 0;
+	}
+	__syncthreads();
+	if ((int)threadIdx.x < nv) {
+		const VoiceRec *rec = &recs[list[threadIdx.x].x];
+		int total = 0;
+		for (int e = 0; e < rec->n_fx && e < GAS_MAX_EFFECTS; e++) {
+			total += rec->fx_stages[e];
+		}
+		if (total > kFtFastStages) {
+			atomicMax(s_scratch, total);
+		}
+	}
+	__syncthreads();
+	const int m = *s_scratch;
+	__syncthreads(); // the scratch word may be reset by the next unit
+	return m;
+}
+
+// units of a class on the per-warp path: Mode B runs 4 voices per warp; the generic class (voices whose own class found no
+// slot, or with more than two buses on a side) runs one voice per unit, because its voices do not share a send layout.
+// Mode A / effect-chain classes take the filter-tile path (a class too wide for its weight tile would run 16 voices per warp).
+template <int C>
 __device__ __forceinline__ int units_of(const ClassInfo &ci) {
 	if (ci.flags & CLS_GENERIC) {
 		return ci.count;
+	}
+	if (ft_class<C>(ci)) {
+		return 0;
 	}
 	return ci.mode == MODE_B ? (ci.count + 3) / 4 : (ci.count + 15) / 16;
 }
@@ -463,6 +826,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	GAS_DYN_SMEM(float, 16, s_tile);
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ int s_ncls;
+	__shared__ int s_ft_scratch;
 	GAS_GRID_DEP_LAUNCH();
 	// Programmatic dependent launch: this kernel may become resident while the streaming kernel (its stream predecessor)
 	// still runs.  What it reads first — the class table of the block — was written by the prologue, which completed
@@ -513,13 +877,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	// CTA-wide accumulation tile: the voices of all chunks this CTA visits are summed in shared memory and reach the
 	// bus buffers as one vector reduction per 16 bytes (instead of one scalar atomic per element per 32 voices)
 	const gas_smem_addr tile = tile_floats > 0 ? gas_smem_u32(s_tile) : 0u;
+	// filter-tile units (Mode A / effect chains): batches of `ft_vpu` voices, sized so that the block's units just cover the grid
+	float *s_y = s_tile + tile_floats;
+	float4 *s_w = reinterpret_cast<float4 *>(s_y + 2 * kFtYFloats);
+	int ft_vpu = 8, ft_units = 0;
+	{
+		int ft_voices = 0;
+		for (int c = 0; c < s_ncls; c++) {
+			ft_voices += ft_class<C>(s_cls[c]) ? s_cls[c].count : 0;
+		}
+		ft_vpu = (((ft_voices + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
+		ft_vpu = min(max(ft_vpu, 8), kFtVoices);
+		for (int c = 0; c < s_ncls; c++) {
+			ft_units += ft_class<C>(s_cls[c]) ? (s_cls[c].count + ft_vpu - 1) / ft_vpu : 0;
+		}
+	}
 	bool cta_has_work = false;
 	{
 		int units = 0;
 		for (int c = 0; c < s_ncls; c++) {
-			units += units_of(s_cls[c]);
+			units += units_of<C>(s_cls[c]);
 		}
-		cta_has_work = units > (int)blockIdx.x; // units are dealt round-robin to CTAs, then to the warps of a CTA
+		// both kinds of units are dealt round-robin to the CTAs (the per-warp ones then to the warps of a CTA)
+		cta_has_work = units > (int)blockIdx.x || ft_units > (int)blockIdx.x;
 	}
 	if (tile && cta_has_work) {
 		for (int i = threadIdx.x; i < tile_floats / 4; i += blockDim.x) {
@@ -527,17 +907,46 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 		}
 		__syncthreads();
 	}
+	// ---- filter-tile units: the whole CTA works on one unit at a time ----
+	for (int unit = (int)blockIdx.x; unit < ft_units; unit += (int)gridDim.x) {
+		int c = 0, k = unit;
+		for (; c < s_ncls; c++) {
+			const int n = ft_class<C>(s_cls[c]) ? (s_cls[c].count + ft_vpu - 1) / ft_vpu : 0;
+			if (k < n) {
+				break;
+			}
+			k -= n;
+		}
+		const ClassInfo &ci = s_cls[c];
+		const VoiceRec *recs = plan.rec + (size_t)slot_p * g.max_voices;
+		const InstSends *sends = plan.sends + (size_t)slot_p * g.max_voices;
+		const int2 *list = plan_list(plan, slot_p, ci.slot, g.max_voices) + k * ft_vpu;
+		const int nv = min(ft_vpu, ci.count - k * ft_vpu);
+		float *tile_p = tile_floats > 0 ? s_tile : nullptr;
+		if (ci.mode == MODE_A) {
+			if (ci.flags & CLS_FILT) {
+				ft_unit<FT_A, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+			} else {
+				ft_unit<FT_COPY, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+			}
+		} else if (ft_max_stages(recs, list, nv, &s_ft_scratch) <= kFtFastStages) {
+			ft_unit<FT_E_FAST, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+		} else {
+			ft_unit<FT_E_SLOW, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+		}
+	}
+	// ---- per-warp units (Mode B, generic classes) ----
 	const int my_warp = threadIdx.x >> 5;
-	// Units (32-voice chunks, or 4-voice chunks for the stream-parallel Mode B path) are numbered class by class and
+	// Units (4-voice chunks of the stream-parallel Mode B path, single voices of the generic classes) are numbered class by class and
 	// dealt round-robin to the CTAs, then to the warps of a CTA: this warp owns units b + grid * (w + 8 r), r = 0, 1, ...
 	int total_units = 0;
 	for (int c = 0; c < s_ncls; c++) {
-		total_units += units_of(s_cls[c]);
+		total_units += units_of<C>(s_cls[c]);
 	}
 	for (int unit = (int)blockIdx.x + (int)gridDim.x * my_warp; unit < total_units; unit += (int)gridDim.x * kWarpsPerCta) {
 		int c = 0, k = unit;
 		for (; c < s_ncls; c++) { // class and chunk of the unit: Mode B 4 voices per warp, Mode A / effect chains 16
-			const int chunks = units_of(s_cls[c]);
+			const int chunks = units_of<C>(s_cls[c]);
 			if (k < chunks) {
 				break;
 			}
@@ -606,12 +1015,15 @@ cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_strid
 	if ((size_t)tile_floats * sizeof(float) > (size_t)kMaxTileBytes) {
 		tile_floats = 0; // too many buses x frames for shared memory: scalar atomics straight into the bus buffers
 	}
-	const size_t smem = (size_t)tile_floats * sizeof(float);
+	const size_t smem = (size_t)tile_floats * sizeof(float) + kFtSmemBytes; // bus tile | y tile | weight tile
 	if (!ctx->k3_smem_attr_set) {
-		cudaFuncSetAttribute(k_mix_voice<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes);
-		cudaFuncSetAttribute(k_mix_voice<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes);
-		cudaFuncSetAttribute(k_mix_voice<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes);
-		cudaFuncSetAttribute(k_mix_voice<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes);
+		cudaError_t ea = cudaFuncSetAttribute(k_mix_voice<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes + kFtSmemBytes);
+		ea = ea != cudaSuccess ? ea : cudaFuncSetAttribute(k_mix_voice<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes + kFtSmemBytes);
+		ea = ea != cudaSuccess ? ea : cudaFuncSetAttribute(k_mix_voice<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes + kFtSmemBytes);
+		ea = ea != cudaSuccess ? ea : cudaFuncSetAttribute(k_mix_voice<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes + kFtSmemBytes);
+		if (ea != cudaSuccess) {
+			return ea;
+		}
 		ctx->k3_smem_attr_set = true;
 	}
 	cudaError_t e = cudaSuccess;

@@ -442,7 +442,26 @@ static __device__ __forceinline__ void plan_voices_pass(const PlanGroup &G, Plan
 			// weight polynomial per (send, pair, side): w(t) = A + B t + Cq t^2 with t = i/F, from
 			// (vn*t + (1-t)*vp) of the AudioServer ramp times (m_new*t + (1-t)*m_prev) of mix_channel.
 			bool streamed = false;
-			if (!has_dsp && !want_peak && n_send >= 1) {
+			// A silent source (the reference's zero-filled playback_buffer, audio_spatializer.cpp:405-408) contributes exactly nothing —
+			// unless one of its volumes is not finite (NaN pan gains): 0 * NaN is NaN and reaches the buses like any other
+			// sample.  Such a voice goes through the voice-parallel kernel, which multiplies the zeros out.
+			int silent_poison = 0;
+			if (v.src_row < 0) {
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+#pragma unroll
+					for (int c = 0; c < 4; c++) {
+						if (k < n_send && c < C) {
+							const float z = (s_vn[k][c] - s_vn[k][c]) + (s_vp[k][c] - s_vp[k][c]) + (m_new[c] - m_new[c]) + (m_prev[c] - m_prev[c]);
+							if (z != 0.f) { // x - x is 0 for every finite x
+								silent_poison = 1;
+							}
+						}
+					}
+				}
+				silent_poison |= __shfl_xor_sync(gm, silent_poison, 1);
+			}
+			if (!has_dsp && !want_peak && n_send >= 1 && !silent_poison) {
 				int q_any = 0, differs = 0;
 #pragma unroll
 				for (int k = 0; k < 4; k++) {

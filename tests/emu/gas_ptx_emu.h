@@ -70,6 +70,16 @@ static inline void gas_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint
 static inline uint64_t gas_l2_policy_evict_first() { return 0; }
 static inline void gas_bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t) { gas_bulk_g2s(dst, src, bytes, bar); }
 
+// ---- per-thread async copies (cp.async): executed at issue time; the source is never written while a copy is pending --------
+static inline void gas_cp_async_16(void *smem_dst, const void *gsrc) {
+	if ((((uintptr_t)smem_dst | (uintptr_t)gsrc) & 15u) != 0) { // a misaligned cp.async faults on the device
+		fprintf(stderr, "[emu] cp.async 16: misaligned copy (dst %p, src %p)\n", smem_dst, gsrc);
+		abort();
+	}
+	memcpy(smem_dst, gsrc, 16);
+}
+static inline void gas_cp_async_wait_all() {}
+
 // ---- named barriers ----------------------------------------------------------------------------------------------------
 static inline void gas_bar_sync(int id, int nthreads) { emu::bar_sync(id, nthreads); }
 #define GAS_BAR_SYNC_IMM(id_, n_) emu::bar_sync((id_), (n_))

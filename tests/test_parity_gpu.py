@@ -236,3 +236,96 @@ def test_class_table_overflow_falls_back_to_the_generic_class(gas, orc):
         assert np.array_equal(S.routing(bg), S.routing(bw)), f"block {b}: routing differs"
         ok, worst, nbad = S.sample_close(bg, bw)
         assert ok, f"block {b}: {nbad} samples out of tolerance, worst {worst:.3e}"
+
+
+def test_filter_tile_long_effect_chains(gas, orc):
+    """Filter-tile path of the voice-parallel kernel (gas_mix_voice.cu): chains of up to four biquads per side run out of
+    registers, longer ones (here 2 x 4 and 4 + 3 + 1 stages) out of local memory; both against the oracle, with peaks."""
+    for name, chain in (
+            ("3fx-fast", [dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=4000.0, resonance=1.0, gain=0.3, stages=1),
+                          dict(mode=abi.FILTER_LOWPASS, cutoff_hz=9000.0, resonance=0.7, gain=1.0, stages=2),
+                          dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=2500.0, resonance=0.9, gain=1.6, stages=1)]),
+            ("2x4-slow", [dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=4000.0, resonance=1.0, gain=0.5, stages=4),
+                          dict(mode=abi.FILTER_LOWPASS, cutoff_hz=11000.0, resonance=0.7, gain=1.0, stages=4)]),
+            ("431-slow", [dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=3000.0, resonance=1.0, gain=0.7, stages=4),
+                          dict(mode=abi.FILTER_LOWPASS, cutoff_hz=12000.0, resonance=0.7, gain=1.0, stages=3),
+                          dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=6000.0, resonance=0.8, gain=1.2, stages=1)])):
+        sc = S.default_scenario(name=f"ft-{name}", voices=53, frames=200, speaker_mode=abi.SPEAKER_SURROUND_51, num_buses=3,
+                                effect_chain=chain, effect_gain_binding=0, area=dict(reverb_bus=2, amount=0.4), area_fraction=0.5,
+                                blocks=3, want_peak_every=4)
+        got, want = _run_both(gas, orc, sc)
+        _check(got, want, sc)
+
+
+def test_filter_tile_many_units_ragged_frames(gas, orc):
+    """Filter-tile path, Mode A with the attenuation filter: enough voices that a CTA works through several units, a frame
+    count that is not a multiple of the 64-frame tile, silent rows, late starters and peaks."""
+    sc = S.default_scenario(name="ft-A-many", voices=1100, frames=200, speaker_mode=abi.SPEAKER_SURROUND_71,
+                            spat=dict(mix_channel_mode=0), area=dict(reverb_bus=1, amount=0.5, uniformity=0.4), area_fraction=0.3,
+                            blocks=3, start_late=1, silent_every=9, want_peak_every=6)
+    got, want = _run_both(gas, orc, sc)
+    _check(got, want, sc)
+
+
+def test_mode_a_filter_twelve_sends_generic_class(gas, orc):
+    """Mode A voices with the filter on whose six buses all change between blocks: six sends fade out while six fade in.  More
+    than two buses on a side take the generic class of the voice-parallel kernel (one voice per unit, sends two at a time, six
+    passes from the same filter state), next to ordinary classes on the filter-tile path in the same launch."""
+    V, F = 70, 256
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, max_spatializers=2, num_buses=16, speaker_mode=abi.SPEAKER_SURROUND_71,
+               mix_rate=48000.0)
+    rng = np.random.default_rng(11)
+    inst = np.arange(V, dtype=np.int32)
+
+    def params(block):
+        p = np.zeros(V, dtype=abi.params)
+        p["pitch_scale"] = 1.0
+        p["update_parameters"] = 1
+        p["linear_attenuation"] = 0.4          # >= 0.001: the high-shelf runs (audio_spatializer_3d.cpp:503)
+        p["attenuation_filter_cutoff_hz"] = 5000.0
+        p["mix_volumes"] = rng.uniform(0.2, 1.0, (V, 4, 2)).astype(np.float32)
+        p["n_bus"] = 6
+        for i in range(V):
+            first = (1 + 6 * (block % 2)) if i % 2 == 0 else 1 + (block + i) % 9
+            p["bus"][i] = np.arange(first, first + 6)
+            p["bus_volumes"][i] = rng.uniform(0.1, 0.9, (6, 4, 2)).astype(np.float32)
+        return p
+
+    ps = [params(b) for b in range(4)]
+    voices = S.synth.make_voices(V)
+    srcs = [S.synth.make_sources(V, F, block=b) for b in range(4)]
+    out = []
+    for mk in (lambda: gas.Mixer(**cfg), lambda: orc.OracleMixer(**cfg)):
+        with mk() as m:
+            m.spatializer_set(0, abi.spatializer_defaults(mix_channel_mode=0))
+            m.instance_init(inst, 0)
+            m.params_set(inst, ps[0])
+            m.instance_start(inst)
+            m.voice_init(inst)
+            blocks = []
+            for b in range(4):
+                m.params_set(inst, ps[b])
+                blocks.append(m.mix_block(voices, srcs[b], F, want_peaks=False)[0])
+            out.append(blocks)
+    for b, (bg, bw) in enumerate(zip(*out)):
+        assert np.array_equal(S.routing(bg), S.routing(bw)), f"block {b}: routing differs"
+        ok, worst, nbad = S.sample_close(bg, bw)
+        assert ok, f"block {b}: {nbad} samples out of tolerance, worst {worst:.3e}"
+    assert (S.routing(out[1][1]).reshape(16, -1).any(axis=1).sum()) >= 12, "scenario did not reach twelve sends"
+
+
+@pytest.mark.parametrize("mode", ["A", "B"])
+def test_q1_nan_gains_of_a_silent_voice_still_reach_the_buses(gas, orc, mode):
+    """SURVEY Q1 meets the silent tail: a voice without source frames (the reference's zero-filled playback_buffer,
+    audio_spatializer.cpp:405-408) whose pan gains are NaN still poisons its buses, 0 * NaN being NaN.  Found by
+    tools/fuzz_parity.py (seed 7, case 196): the planner used to drop every silent unfiltered voice."""
+    sc = S.default_scenario(name=f"q1-silent-{mode}", voices=64, speaker_mode=abi.SPEAKER_SURROUND_51, blocks=2, silent_every=2,
+                            spat=dict(mix_channel_mode=MODES[mode], panning_strength=1.5), force_filter_off=True,
+                            area=dict(reverb_bus=1, amount=0.3, uniformity=1.0), area_fraction=0.5)
+    got, want = _run_both(gas, orc, sc)
+    silent = (S.synth.make_voices(64)["voice"] % 2) == 1
+    nan_voice = np.isnan(want["params"][0]["mix_volumes"]).any(axis=(1, 2))
+    assert (nan_voice & silent).any(), "scenario has no silent voice with NaN gains"
+    for b in range(len(want["bus"])):
+        assert np.array_equal(np.isnan(got["bus"][b]), np.isnan(want["bus"][b])), f"block {b}: NaN pattern differs"
+    _check(got, want, sc, state=False)
