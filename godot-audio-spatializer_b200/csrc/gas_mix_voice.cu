@@ -471,7 +471,7 @@ constexpr int kFtYStride = kFtFrames * 2 + 4;              // floats per voice r
 constexpr int kFtRows = 16;                                // weight rows (send x pair) of a class: 4 sends (2 current + 2 fading out) x 4 pairs
 constexpr int kFtYFloats = kFtVoices * kFtYStride;         // 7392 per tile buffer; two buffers: the tile being worked on and the next one in flight
 constexpr int kFtWFloats = kFtVoices * kFtRows * 4;        // 3584
-constexpr int kFtSmemBytes = (2 * kFtYFloats + kFtWFloats) * 4;
+constexpr int kFtSmemBytes = (2 * kFtYFloats + kFtWFloats + kFtFrames) * 4; // tile buffers | weight tile | t of the tile's frames
 constexpr int kFtFastStages = 4;                           // effect chains with up to this many biquads per side keep them in registers
 static_assert((kFtYFloats * 4) % 16 == 0 && (kFtYStride * 4) % 16 == 0, "tile rows are written and the weight tile behind them is read 16 bytes at a time");
 static_assert(kWarpsPerCta * 32 == 4 * kFtFrames, "contraction mapping: 4 row groups x kFtFrames frames");
@@ -480,7 +480,12 @@ static_assert(kWarpsPerCta * 32 == 4 * kFtFrames, "contraction mapping: 4 row gr
 // anything wider than the weight tile stays on the per-warp path)
 template <int C>
 __device__ __forceinline__ bool ft_class(const ClassInfo &ci) {
-	return ci.mode != MODE_B && !(ci.flags & CLS_GENERIC) && ci.n_send * C <= kFtRows;
+	return !(ci.flags & CLS_GENERIC) && ci.n_send * C <= kFtRows;
+}
+// voices per unit of a class, given the block's stream budget per unit (Mode B: C streams per voice and side)
+template <int C>
+__device__ __forceinline__ int ft_vpu_of(const ClassInfo &ci, int budget) {
+	return ci.mode == MODE_B ? max(1, min(28, budget / C)) : budget;
 }
 
 __device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
@@ -522,7 +527,8 @@ __device__ __forceinline__ void ft_stage_weights(const InstSends *__restrict__ s
 }
 
 // rows [0, nrows) x frames [i0, i0 + kFtFrames) of the unit: sum over its voices, added to the bus tile / buffers
-template <int C>
+// PER_PAIR (Mode B): the voice's C pairs are C streams of their own, row (send, pair) sums stream pair of every voice.
+template <int C, bool PER_PAIR>
 __device__ __forceinline__ void ft_contract(const float *s_y, const float4 *s_w, int nv, int nrows, const int (&rowoff)[kFtRows / 4], int i0, int F,
 		float *__restrict__ bus, float *s_tile) {
 	const int f = threadIdx.x & (kFtFrames - 1), rg = threadIdx.x / kFtFrames;
@@ -541,15 +547,35 @@ __device__ __forceinline__ void ft_contract(const float *s_y, const float4 *s_w,
 	}
 	const float *yp = s_y + f * 2;
 	const float4 *wp = s_w + rg;
+	if (!PER_PAIR) {
 #pragma unroll 4
-	for (int v = 0; v < nv; v++) {
-		const float2 y = *reinterpret_cast<const float2 *>(yp + v * kFtYStride);
+		for (int v = 0; v < nv; v++) {
+			const float2 y = *reinterpret_cast<const float2 *>(yp + v * kFtYStride);
+#pragma unroll
+			for (int q = 0; q < kMine; q++) {
+				if (q < mine) {
+					const float4 w4 = wp[v * nrows + q * 4];
+					const float2 w = gas_ffma2(t2, make_float2(w4.z, w4.w), make_float2(w4.x, w4.y));
+					acc[q] = gas_ffma2(w, y, acc[q]);
+				}
+			}
+		}
+	} else {
+		int ycol[kMine]; // pair of row rg + 4 q = stream of the voice it sums
 #pragma unroll
 		for (int q = 0; q < kMine; q++) {
-			if (q < mine) {
-				const float4 w4 = wp[v * nrows + q * 4];
-				const float2 w = gas_ffma2(t2, make_float2(w4.z, w4.w), make_float2(w4.x, w4.y));
-				acc[q] = gas_ffma2(w, y, acc[q]);
+			ycol[q] = ((rg + q * 4) % C) * kFtYStride;
+		}
+#pragma unroll 2
+		for (int v = 0; v < nv; v++) {
+#pragma unroll
+			for (int q = 0; q < kMine; q++) {
+				if (q < mine) {
+					const float2 y = *reinterpret_cast<const float2 *>(yp + v * (C * kFtYStride) + ycol[q]);
+					const float4 w4 = wp[v * nrows + q * 4];
+					const float2 w = gas_ffma2(t2, make_float2(w4.z, w4.w), make_float2(w4.x, w4.y));
+					acc[q] = gas_ffma2(w, y, acc[q]);
+				}
 			}
 		}
 	}
@@ -741,7 +767,7 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 		}
 		__syncthreads();
 		// ---- contraction ----
-		ft_contract<C>(buf, s_w, nv, R, rowoff, i0, F, bus, s_tile);
+		ft_contract<C, false>(buf, s_w, nv, R, rowoff, i0, F, bus, s_tile);
 	}
 	__syncthreads(); // the next unit's copies and weights overwrite what the last contraction read
 	if (active) {
@@ -780,6 +806,137 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 		if ((flags & GAS_VOICE_WANT_PEAK) && peaks) {
 			reinterpret_cast<float *>(peaks + j)[side] = pk;
 		}
+	}
+}
+
+
+// Mode B unit (with or without the attenuation filter: up to 2C biquads per voice): one lane per (voice, pair, side) stream.
+// The voices' source rows arrive in two small x tiles (this tile and the next one in flight); every stream applies the
+// mix_channel ramp (reference audio_spatializer_3d.cpp:591-593) and its interpolated high-shelf (:594-595) and writes its own row
+// of the y tile; the contraction then sums, for every (send, pair) row, stream `pair` of every voice under the AudioServer ramp.
+constexpr int kFtVoicesB = 28; // x tiles: the second tile buffer, halved (ft_vpu_of)
+static_assert(kFtVoicesB * kFtYStride * 2 <= kFtYFloats, "two x tiles share one tile buffer");
+
+template <int C, bool FILT>
+__device__ __noinline__ void ft_unit_b(const DevTables &t, const ClassInfo &ci, const VoiceRec *__restrict__ recs, const InstSends *__restrict__ sends,
+		const int2 *__restrict__ list, int nv, const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float *s_tile,
+		float2 *__restrict__ peaks, float *s_y, float4 *s_w, float *s_t) {
+	constexpr int kPer = 2 * C; // lanes per voice
+	const int vl = (int)threadIdx.x / kPer, rem = (int)threadIdx.x % kPer, c = rem >> 1, side = rem & 1;
+	const bool active = vl < nv;
+	const int j = active ? list[vl].x : 0;
+	const VoiceRec *rec = &recs[j];
+	const int voice = active ? rec->voice : 0;
+	const uint32_t flags = active ? rec->flags : 0u;
+	const float m_prev = active ? rec->m_prev[c][side] : 0.f;
+	const float m_new = active ? rec->m_new[c][side] : 0.f;
+	constexpr bool filt = FILT; // CLS_FILT of the class: a template parameter keeps the test out of the recurrence
+	gas_processor_state *ps = t.vs_proc + (size_t)voice * 8 + rem; // processor index pair * 2 + (left ? 0 : 1)
+	gas_processor_state st{};
+	if (active && filt) {
+		st = *ps;
+	}
+	const bool clear = (flags >> (8 + c)) & 1u; // is_just_started => clear history (:583-586)
+	Biquad h;
+	h.ha1 = clear ? 0.f : st.ha1;
+	h.ha2 = clear ? 0.f : st.ha2;
+	h.hb1 = clear ? 0.f : st.hb1;
+	h.hb2 = clear ? 0.f : st.hb2;
+	float cf[5] = { st.b0, st.b1, st.b2, st.a1, st.a2 }, inc[5];
+#pragma unroll
+	for (int q = 0; q < 5; q++) { // update_coeffs(F): per-sample increment towards the target
+		inc[q] = ((active ? rec->target[q] : 0.f) - cf[q]) / (float)F;
+	}
+	const int R = ci.n_send * C; // <= kFtRows (ft_class)
+	ft_stage_weights<C>(sends, list, nv, R, s_w);
+	int rowoff[kFtRows / 4];
+#pragma unroll
+	for (int q = 0; q < kFtRows / 4; q++) {
+		const int r = (int)threadIdx.x / kFtFrames + q * 4;
+		rowoff[q] = r < R ? (nth_set_bit(ci.mask, r / C) * C + r % C) * F * 2 : 0;
+	}
+	float pk = 0.f;
+	float *ybuf = s_y, *xbuf = s_y + kFtYFloats; // y tile: nv * C stream rows; x tiles: 2 x nv voice rows
+	auto step = [&](float x, float tt) -> float {
+		const float omt = 1.0f - tt;
+		const float vol = m_new * tt + omt * m_prev; // :592
+		float y = vol * x;                            // :593
+		if (filt) {
+			y = biquad_step(h, y, cf[0], cf[1], cf[2], cf[3], cf[4]); // :594-595
+#pragma unroll
+			for (int q = 0; q < 5; q++) { // process_one_interp: coeffs += incr
+				cf[q] += inc[q];
+			}
+		}
+		pk = fmaxf(pk, fabsf(y));
+		return y;
+	};
+	ft_prefetch(src, src_stride, list, nv, 0, F, xbuf);
+	for (int i0 = 0, ti = 0; i0 < F; i0 += kFtFrames, ti++) {
+		const float *xb = xbuf + (ti & 1) * (kFtVoicesB * kFtYStride);
+		gas_cp_async_wait_all();
+		if ((int)threadIdx.x < kFtFrames) {
+			s_t[threadIdx.x] = (float)(i0 + (int)threadIdx.x) / (float)F; // t of the tile's frames (:591), once per frame instead of once per stream
+		}
+		__syncthreads();
+		if (i0 + kFtFrames < F) {
+			ft_prefetch(src, src_stride, list, nv, i0 + kFtFrames, F, xbuf + ((ti + 1) & 1) * (kFtVoicesB * kFtYStride));
+		}
+		// ---- filter phase ----
+		if (active) {
+			const float *xr = xb + vl * kFtYStride + side;
+			float *yr = ybuf + (vl * C + c) * kFtYStride + side;
+			for (int k0 = 0; k0 < kFtFrames && i0 + k0 < F; k0 += 8) {
+				if (i0 + k0 + 8 <= F) {
+					float xv[8], tv[8];
+#pragma unroll
+					for (int k = 0; k < 8; k++) {
+						xv[k] = xr[(k0 + k) * 2];
+						tv[k] = s_t[k0 + k];
+					}
+#pragma unroll
+					for (int k = 0; k < 8; k++) {
+						yr[(k0 + k) * 2] = step(xv[k], tv[k]);
+					}
+				} else {
+					for (int k = 0; k < 8 && i0 + k0 + k < F; k++) {
+						yr[(k0 + k) * 2] = step(xr[(k0 + k) * 2], s_t[k0 + k]);
+					}
+				}
+			}
+		}
+		__syncthreads();
+		// ---- contraction ----
+		ft_contract<C, true>(ybuf, s_w, nv, R, rowoff, i0, F, bus, s_tile);
+	}
+	__syncthreads();
+	if (active && filt) {
+		st.b0 = cf[0];
+		st.b1 = cf[1];
+		st.b2 = cf[2];
+		st.a1 = cf[3];
+		st.a2 = cf[4];
+		st.ha1 = h.ha1;
+		st.ha2 = h.ha2;
+		st.hb1 = h.hb1;
+		st.hb2 = h.hb2;
+		*ps = st;
+	}
+	// block peak: max over the voice's pairs, per side (audio_spatializer.cpp:436-443), handed over through the (free) y tile
+	if (peaks) {
+		if (active) {
+			ybuf[(vl * C + c) * kFtYStride + side] = pk;
+		}
+		__syncthreads();
+		if (active && c == 0 && (flags & GAS_VOICE_WANT_PEAK)) {
+			float m = 0.f;
+#pragma unroll
+			for (int cc = 0; cc < C; cc++) {
+				m = fmaxf(m, ybuf[(vl * C + cc) * kFtYStride + side]);
+			}
+			reinterpret_cast<float *>(peaks + j)[side] = m;
+		}
+		__syncthreads();
 	}
 }
 
@@ -880,16 +1037,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	// filter-tile units (Mode A / effect chains): batches of `ft_vpu` voices, sized so that the block's units just cover the grid
 	float *s_y = s_tile + tile_floats;
 	float4 *s_w = reinterpret_cast<float4 *>(s_y + 2 * kFtYFloats);
-	int ft_vpu = 8, ft_units = 0;
+	float *s_t = reinterpret_cast<float *>(s_w + kFtWFloats / 4);
+	int ft_budget = 8, ft_units = 0;
 	{
-		int ft_voices = 0;
+		int ft_streams = 0; // per side
 		for (int c = 0; c < s_ncls; c++) {
-			ft_voices += ft_class<C>(s_cls[c]) ? s_cls[c].count : 0;
+			ft_streams += ft_class<C>(s_cls[c]) ? s_cls[c].count * (s_cls[c].mode == MODE_B ? C : 1) : 0;
 		}
-		ft_vpu = (((ft_voices + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
-		ft_vpu = min(max(ft_vpu, 8), kFtVoices);
+		ft_budget = (((ft_streams + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
+		ft_budget = min(max(ft_budget, 8), kFtVoices);
 		for (int c = 0; c < s_ncls; c++) {
-			ft_units += ft_class<C>(s_cls[c]) ? (s_cls[c].count + ft_vpu - 1) / ft_vpu : 0;
+			const int vpu = ft_vpu_of<C>(s_cls[c], ft_budget);
+			ft_units += ft_class<C>(s_cls[c]) ? (s_cls[c].count + vpu - 1) / vpu : 0;
 		}
 	}
 	bool cta_has_work = false;
@@ -911,19 +1070,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	for (int unit = (int)blockIdx.x; unit < ft_units; unit += (int)gridDim.x) {
 		int c = 0, k = unit;
 		for (; c < s_ncls; c++) {
-			const int n = ft_class<C>(s_cls[c]) ? (s_cls[c].count + ft_vpu - 1) / ft_vpu : 0;
+			const int vpu = ft_vpu_of<C>(s_cls[c], ft_budget);
+			const int n = ft_class<C>(s_cls[c]) ? (s_cls[c].count + vpu - 1) / vpu : 0;
 			if (k < n) {
 				break;
 			}
 			k -= n;
 		}
 		const ClassInfo &ci = s_cls[c];
+		const int ft_vpu = ft_vpu_of<C>(ci, ft_budget);
 		const VoiceRec *recs = plan.rec + (size_t)slot_p * g.max_voices;
 		const InstSends *sends = plan.sends + (size_t)slot_p * g.max_voices;
 		const int2 *list = plan_list(plan, slot_p, ci.slot, g.max_voices) + k * ft_vpu;
 		const int nv = min(ft_vpu, ci.count - k * ft_vpu);
 		float *tile_p = tile_floats > 0 ? s_tile : nullptr;
-		if (ci.mode == MODE_A) {
+		if (ci.mode == MODE_B) {
+			if (ci.flags & CLS_FILT) {
+				ft_unit_b<C, true>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w, s_t);
+			} else {
+				ft_unit_b<C, false>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w, s_t);
+			}
+		} else if (ci.mode == MODE_A) {
 			if (ci.flags & CLS_FILT) {
 				ft_unit<FT_A, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
 			} else {
@@ -1024,6 +1191,12 @@ cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_strid
 		if (ea != cudaSuccess) {
 			return ea;
 		}
+		// two CTAs of ~115 KB per SM need (nearly) the whole shared-memory carve-out; a hint, so its status does not matter
+		cudaFuncSetAttribute(k_mix_voice<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(k_mix_voice<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(k_mix_voice<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(k_mix_voice<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		(void)cudaGetLastError();
 		ctx->k3_smem_attr_set = true;
 	}
 	cudaError_t e = cudaSuccess;

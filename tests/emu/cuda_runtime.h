@@ -309,7 +309,8 @@ enum { cudaStreamNonBlocking = 1 };
 enum { cudaEventDefault = 0, cudaEventDisableTiming = 2 };
 enum { cudaEventRecordDefault = 0, cudaEventRecordExternal = 1 };
 enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+enum { cudaSharedmemCarveoutMaxShared = 100 };
 enum { cudaIpcMemLazyEnablePeerAccess = 1 };
 struct cudaIpcMemHandle_t {
 	char reserved[64];

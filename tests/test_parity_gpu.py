@@ -329,3 +329,14 @@ def test_q1_nan_gains_of_a_silent_voice_still_reach_the_buses(gas, orc, mode):
     for b in range(len(want["bus"])):
         assert np.array_equal(np.isnan(got["bus"][b]), np.isnan(want["bus"][b])), f"block {b}: NaN pattern differs"
     _check(got, want, sc, state=False)
+
+
+@pytest.mark.parametrize("speakers", ["stereo", "3.1", "5.1", "7.1"])
+def test_filter_tile_mode_b_many_units_ragged_frames(gas, orc, speakers):
+    """Filter-tile path, Mode B with the attenuation filter (2C biquads per voice): several units per CTA, a frame count that is
+    not a multiple of the 64-frame tile, two buses, silent rows, late starters and peaks (max over the voice's pairs)."""
+    sc = S.default_scenario(name=f"ft-B-many-{speakers}", voices=420, frames=200, speaker_mode=SPEAKERS[speakers],
+                            spat=dict(mix_channel_mode=1), area=dict(reverb_bus=1, amount=0.5, uniformity=0.4), area_fraction=0.3,
+                            blocks=3, start_late=1, silent_every=9, want_peak_every=5)
+    got, want = _run_both(gas, orc, sc)
+    _check(got, want, sc)
