@@ -597,7 +597,11 @@ __device__ __forceinline__ void ft_contract(const float *s_y, const float4 *s_w,
 	}
 }
 
-enum : int { FT_A = 0, FT_E_FAST = 1, FT_E_SLOW = 2, FT_COPY = 3 }; // FT_COPY: Mode A below the filter threshold (peaks only): y = x
+// FT_COPY: Mode A below the filter threshold (peaks only): y = x.  FT_E_FAST1 / 2 / (4): effect chains whose longest member in the
+// unit has 1 / 2 / up to 4 biquads per side (the slots beyond a lane's own chain are predicated off, so fewer slots = fewer issue slots)
+enum : int { FT_A = 0, FT_E_FAST = 1, FT_E_SLOW = 2, FT_COPY = 3, FT_E_FAST1 = 4, FT_E_FAST2 = 5 };
+__host__ __device__ constexpr bool ft_is_fast(int var) { return var == FT_E_FAST || var == FT_E_FAST1 || var == FT_E_FAST2; }
+__host__ __device__ constexpr int ft_slots(int var) { return var == FT_E_FAST1 ? 1 : (var == FT_E_FAST2 ? 2 : kFtFastStages); }
 
 // One unit: voices list[0 .. nv) of class `ci`.  Every thread of the CTA takes part (the barriers are CTA-wide).
 template <int VAR, int C>
@@ -639,14 +643,15 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 	// effect chains: cascaded constant-coefficient biquads (upstream AudioEffectFilter::process), histories
 	// [effect][side][stage]{ha1,ha2,hb1,hb2} in vs_fx
 	float *fxs = t.vs_fx + (size_t)voice * (GAS_MAX_EFFECTS * 2 * GAS_MAX_FILTER_STAGES * 4);
-	const int n_fx = ((VAR == FT_E_FAST || VAR == FT_E_SLOW) && active) ? rec->n_fx : 0;
+	const int n_fx = ((ft_is_fast(VAR) || VAR == FT_E_SLOW) && active) ? rec->n_fx : 0;
+	constexpr int kSlots = ft_slots(VAR);
 	// FT_E_FAST: the chain flattened to at most kFtFastStages biquads, coefficients and histories in registers
 	int n_slot = 0;
-	int e_of[kFtFastStages] = {}, q_of[kFtFastStages] = {};
-	float sc[kFtFastStages][5] = {}, sh[kFtFastStages][4] = {};
+	int e_of[kSlots] = {}, q_of[kSlots] = {};
+	float sc[kSlots][5] = {}, sh[kSlots][4] = {};
 	// FT_E_SLOW: any chain (dynamic shape: local memory)
 	float fxh[VAR == FT_E_SLOW ? GAS_MAX_EFFECTS : 1][VAR == FT_E_SLOW ? GAS_MAX_FILTER_STAGES : 1][4];
-	if (VAR == FT_E_FAST) {
+	if (ft_is_fast(VAR)) {
 #pragma unroll
 		for (int e = 0; e < GAS_MAX_EFFECTS; e++) {
 			const int stages = e < n_fx ? rec->fx_stages[e] : 0;
@@ -654,7 +659,7 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 			for (int q = 0; q < GAS_MAX_FILTER_STAGES; q++) {
 				const bool on = q < stages;
 #pragma unroll
-				for (int s = 0; s < kFtFastStages; s++) {
+				for (int s = 0; s < kSlots; s++) {
 					if (on && n_slot == s) {
 						e_of[s] = e;
 						q_of[s] = q;
@@ -664,7 +669,7 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 			}
 		}
 #pragma unroll
-		for (int s = 0; s < kFtFastStages; s++) {
+		for (int s = 0; s < kSlots; s++) {
 			if (s < n_slot) {
 #pragma unroll
 				for (int k = 0; k < 5; k++) {
@@ -699,9 +704,9 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 			for (int q = 0; q < 5; q++) { // process_one_interp: coeffs += incr
 				cf[q] += inc[q];
 			}
-		} else if (VAR == FT_E_FAST) {
+		} else if (ft_is_fast(VAR)) {
 #pragma unroll
-			for (int s = 0; s < kFtFastStages; s++) {
+			for (int s = 0; s < kSlots; s++) {
 				if (s < n_slot) {
 					const float pre = y;
 					y = y * sc[s][0] + sh[s][2] * sc[s][1] + sh[s][3] * sc[s][2] + sh[s][0] * sc[s][3] + sh[s][1] * sc[s][4];
@@ -783,9 +788,9 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 			st.hb2 = h.hb2;
 			*ps = st;
 		}
-		if (VAR == FT_E_FAST) {
+		if (ft_is_fast(VAR)) {
 #pragma unroll
-			for (int s = 0; s < kFtFastStages; s++) {
+			for (int s = 0; s < kSlots; s++) {
 				if (s < n_slot) {
 #pragma unroll
 					for (int k = 0; k < 4; k++) {
@@ -952,9 +957,7 @@ __device__ int ft_max_stages(const VoiceRec *__restrict__ recs, const int2 *__re
 		for (int e = 0; e < rec->n_fx && e < GAS_MAX_EFFECTS; e++) {
 			total += rec->fx_stages[e];
 		}
-		if (total > kFtFastStages) {
-			atomicMax(s_scratch, total);
-		}
+		atomicMax(s_scratch, total);
 	}
 	__syncthreads();
 	const int m = *s_scratch;
@@ -1096,10 +1099,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 			} else {
 				ft_unit<FT_COPY, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
 			}
-		} else if (ft_max_stages(recs, list, nv, &s_ft_scratch) <= kFtFastStages) {
-			ft_unit<FT_E_FAST, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
 		} else {
-			ft_unit<FT_E_SLOW, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+			const int longest = ft_max_stages(recs, list, nv, &s_ft_scratch);
+			if (longest <= 1) {
+				ft_unit<FT_E_FAST1, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+			} else if (longest == 2) {
+				ft_unit<FT_E_FAST2, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+			} else if (longest <= kFtFastStages) {
+				ft_unit<FT_E_FAST, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+			} else {
+				ft_unit<FT_E_SLOW, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+			}
 		}
 	}
 	// ---- per-warp units (Mode B, generic classes) ----
