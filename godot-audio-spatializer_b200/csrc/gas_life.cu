@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(256) k_life_stage(DevTables t, int n_voices, c
 		}
 		return;
 	}
-	o.flags |= GAS_VOICE_WANT_PEAK; // the reference tracks the peak of every voice (:419); it is read when has_frames is clear
+	// The reference tracks the block peak of every voice (:419) but reads it only once has_frames is clear (:464): only the voices that
+	// end in this block or are already in their tail ask for one.  Everything else keeps the streaming path.
 	if (life & 2u) {
 		const bool has_row = v.src_row >= 0 && v.src_row < src_rows;
 		int mixed = has_row ? mixed_frames[warp] : 0;
@@ -99,10 +100,12 @@ __global__ void __launch_bounds__(256) k_life_stage(DevTables t, int n_voices, c
 			}
 		} else {
 			life &= ~2u; // no more frames to mix (:397)
+			o.flags |= GAS_VOICE_WANT_PEAK;
 		}
 		o.src_row = warp;
 	} else {
 		o.src_row = -1; // zero-filled playback buffer (:405-408)
+		o.flags |= GAS_VOICE_WANT_PEAK;
 	}
 	if (lane == 0) {
 		t.vs_life[v.voice] = life;
