@@ -40,7 +40,7 @@ def run_stream(mixer, sc, threshold_db=-80.0, keep_alive=False):
     V, F, vpi = sc["voices"], sc["frames"], sc["vpi"]
     n_inst = (V + vpi - 1) // vpi
     inst = np.arange(n_inst, dtype=np.int32)
-    spat = abi.spatializer_defaults(mix_channel_mode=int(sc["mode_b"]))
+    spat = abi.spatializer_defaults(mix_channel_mode=int(sc["mode_b"]), **sc.get("spat", {}))
     mixer.spatializer_set(0, spat)
     mixer.instance_init(inst, 0)
     if threshold_db != -80.0:
@@ -182,5 +182,58 @@ def test_cuda_lifecycle_matches_oracle(gas, orc, mode_b, filt):
     for b in range(sc["blocks"]):
         assert np.array_equal(got["status"][b], want["status"][b]), f"block {b}: voice status differs"
         assert np.array_equal(S.routing(got["bus"][b]), S.routing(want["bus"][b])), f"block {b}: routing differs"
+        ok, worst, nbad = S.sample_close(got["bus"][b], want["bus"][b])
+        assert ok, f"block {b}: {nbad} samples out of tolerance, worst {worst:.3e}"
+
+
+def _nan_aware_bits_equal(a, b):
+    """Bit for bit where both are numbers, NaN where either is (the payload of a NaN depends on operand order)."""
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
+
+
+def nan_tail_scenario(mode_b):
+    """SURVEY Q1 meets Q16: un-normalised directions into SPCAP with a non-integer tightness give NaN pan gains to some voices
+    (audio_spatializer_3d.cpp:930); their streams end inside the run, so they go through the end fade and a zero-input tail block:
+    0 x NaN is NaN, the bus stays poisoned for that block too, and the NaN samples never raise the peak (`l > peak.left` is false,
+    audio_spatializer.cpp:436), so the voice is dropped after its first tail block."""
+    sc = lifecycle_scenario(mode_b=mode_b, filt=False, voices=24, vpi=1, blocks=8)
+    sc["spat"] = dict(panning_strength=1.5)
+    return sc
+
+
+@pytest.mark.parametrize("mode_b", [False, True])
+def test_oracle_nan_gain_tails_match_reference_code(orc, mode_b):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built and /root/reference not present")
+    sc = nan_tail_scenario(mode_b)
+    cfg = dict(max_instances=sc["voices"], max_voices=2 * sc["voices"], max_frames=sc["frames"], max_spatializers=2, num_buses=2,
+               speaker_mode=sc["speaker_mode"], mix_rate=48000.0)
+    with orc.OracleMixer(**cfg) as o, ref.RefMixer(**cfg) as r:
+        want = run_stream(o, sc)
+        got = run_stream(r, sc, keep_alive=True)
+    poisoned_tail = False
+    for b in range(sc["blocks"]):
+        assert np.array_equal(got["status"][b] & 1, want["status"][b] & 1), f"block {b}: active flags differ"
+        assert _nan_aware_bits_equal(got["bus"][b], want["bus"][b]), f"block {b}: bus differs"
+        tails = (want["status"][b - 1] & 3) == 1 if b else np.zeros(sc["voices"], dtype=bool)  # active without frames when the block began
+        poisoned_tail = poisoned_tail or (bool(tails.any()) and bool(np.isnan(want["bus"][b]).any()))
+    assert poisoned_tail, "the scenario never mixed a zero-input tail while the bus was NaN"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode_b", [False, True])
+def test_cuda_nan_gain_tails_match_oracle(gas, orc, mode_b):
+    sc = nan_tail_scenario(mode_b)
+    cfg = dict(max_instances=sc["voices"], max_voices=sc["voices"], max_frames=sc["frames"], max_spatializers=2, num_buses=2,
+               speaker_mode=sc["speaker_mode"], mix_rate=48000.0)
+    with orc.OracleMixer(**cfg) as o, gas.Mixer(**cfg) as m:
+        want = run_stream(o, sc)
+        got = run_stream(m, sc)
+    for b in range(sc["blocks"]):
+        assert np.array_equal(got["status"][b], want["status"][b]), f"block {b}: voice status differs"
+        assert np.array_equal(np.isnan(got["bus"][b]), np.isnan(want["bus"][b])), f"block {b}: NaN pattern differs"
         ok, worst, nbad = S.sample_close(got["bus"][b], want["bus"][b])
         assert ok, f"block {b}: {nbad} samples out of tolerance, worst {worst:.3e}"
