@@ -451,6 +451,8 @@ int gas_create(const gas_config *cfg, gas_ctx **out) {
 		ctx->gain_after_stream = !(e && atoi(e) == 0);
 		e = getenv("GAS_K2_SCALED");
 		ctx->scaled_classes = !(e && atoi(e) == 0);
+		e = getenv("GAS_K3_LEGACY"); // experiments: the round-1 per-warp form of the voice-parallel kernel for every class
+		ctx->k3_legacy = e && atoi(e) != 0;
 		ctx->replicas = 1; // the step kernel adds straight into the bus buffers (8 replicas + fold measured no faster)
 		ctx->par_voice = false;
 		e = getenv("GAS_K2_DEBUG"); // the timeline buffer must exist before anything is captured into a graph

@@ -234,6 +234,7 @@ struct gas_ctx {
 	cudaEvent_t ev_stream_started = nullptr; // programmatic event of the last streaming kernel launch
 	bool stream_started_pending = false;
 	bool scaled_classes = true; // GAS_K2_SCALED=0 turns the scaled-send classes off (experiments)
+	bool k3_legacy = false;     // GAS_K3_LEGACY=1: the voice-parallel kernel keeps every class on its per-warp path (A/B against the filter-tile path)
 	cudaEvent_t ev_gain_done = nullptr, ev_prologue_done = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_mix_done = nullptr, ev_comm_done = nullptr, ev_join2 = nullptr;
 	bool mix_pending = false, comm_pending = false;
 	bool reduce_open = false; // gas_reduce_bus_begin_device without its _end yet

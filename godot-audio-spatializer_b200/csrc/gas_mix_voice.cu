@@ -479,8 +479,8 @@ static_assert(kWarpsPerCta * 32 == 4 * kFtFrames, "contraction mapping: 4 row gr
 // (the planner sends voices with more than two buses on a side to the generic class, so an ordinary class has at most 4 sends;
 // anything wider than the weight tile stays on the per-warp path)
 template <int C>
-__device__ __forceinline__ bool ft_class(const ClassInfo &ci) {
-	return !(ci.flags & CLS_GENERIC) && ci.n_send * C <= kFtRows;
+__device__ __forceinline__ bool ft_class(const ClassInfo &ci, int ft_on) {
+	return ft_on && !(ci.flags & CLS_GENERIC) && ci.n_send * C <= kFtRows;
 }
 // voices per unit of a class, given the block's stream budget per unit (Mode B: C streams per voice and side)
 template <int C>
@@ -969,11 +969,11 @@ __device__ int ft_max_stages(const VoiceRec *__restrict__ recs, const int2 *__re
 // slot, or with more than two buses on a side) runs one voice per unit, because its voices do not share a send layout.
 // Mode A / effect-chain classes take the filter-tile path (a class too wide for its weight tile would run 16 voices per warp).
 template <int C>
-__device__ __forceinline__ int units_of(const ClassInfo &ci) {
+__device__ __forceinline__ int units_of(const ClassInfo &ci, int ft_on) {
 	if (ci.flags & CLS_GENERIC) {
 		return ci.count;
 	}
-	if (ft_class<C>(ci)) {
+	if (ft_class<C>(ci, ft_on)) {
 		return 0;
 	}
 	return ci.mode == MODE_B ? (ci.count + 3) / 4 : (ci.count + 15) / 16;
@@ -982,7 +982,7 @@ __device__ __forceinline__ int units_of(const ClassInfo &ci) {
 template <int C>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t, GlobalCfg g, BlockPlan plan,
 		const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float2 *__restrict__ peaks,
-		const float4 *__restrict__ rep, int bus_f4, int replicas, int tile_floats, int early_look) {
+		const float4 *__restrict__ rep, int bus_f4, int replicas, int tile_floats, int early_look, int ft_on) {
 	GAS_DYN_SMEM(float, 16, s_tile);
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ int s_ncls;
@@ -1045,20 +1045,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	{
 		int ft_streams = 0; // per side
 		for (int c = 0; c < s_ncls; c++) {
-			ft_streams += ft_class<C>(s_cls[c]) ? s_cls[c].count * (s_cls[c].mode == MODE_B ? C : 1) : 0;
+			ft_streams += ft_class<C>(s_cls[c], ft_on) ? s_cls[c].count * (s_cls[c].mode == MODE_B ? C : 1) : 0;
 		}
 		ft_budget = (((ft_streams + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
 		ft_budget = min(max(ft_budget, 8), kFtVoices);
 		for (int c = 0; c < s_ncls; c++) {
 			const int vpu = ft_vpu_of<C>(s_cls[c], ft_budget);
-			ft_units += ft_class<C>(s_cls[c]) ? (s_cls[c].count + vpu - 1) / vpu : 0;
+			ft_units += ft_class<C>(s_cls[c], ft_on) ? (s_cls[c].count + vpu - 1) / vpu : 0;
 		}
 	}
 	bool cta_has_work = false;
 	{
 		int units = 0;
 		for (int c = 0; c < s_ncls; c++) {
-			units += units_of<C>(s_cls[c]);
+			units += units_of<C>(s_cls[c], ft_on);
 		}
 		// both kinds of units are dealt round-robin to the CTAs (the per-warp ones then to the warps of a CTA)
 		cta_has_work = units > (int)blockIdx.x || ft_units > (int)blockIdx.x;
@@ -1074,7 +1074,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 		int c = 0, k = unit;
 		for (; c < s_ncls; c++) {
 			const int vpu = ft_vpu_of<C>(s_cls[c], ft_budget);
-			const int n = ft_class<C>(s_cls[c]) ? (s_cls[c].count + vpu - 1) / vpu : 0;
+			const int n = ft_class<C>(s_cls[c], ft_on) ? (s_cls[c].count + vpu - 1) / vpu : 0;
 			if (k < n) {
 				break;
 			}
@@ -1118,12 +1118,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	// dealt round-robin to the CTAs, then to the warps of a CTA: this warp owns units b + grid * (w + 8 r), r = 0, 1, ...
 	int total_units = 0;
 	for (int c = 0; c < s_ncls; c++) {
-		total_units += units_of<C>(s_cls[c]);
+		total_units += units_of<C>(s_cls[c], ft_on);
 	}
 	for (int unit = (int)blockIdx.x + (int)gridDim.x * my_warp; unit < total_units; unit += (int)gridDim.x * kWarpsPerCta) {
 		int c = 0, k = unit;
 		for (; c < s_ncls; c++) { // class and chunk of the unit: Mode B 4 voices per warp, Mode A / effect chains 16
-			const int chunks = units_of<C>(s_cls[c]);
+			const int chunks = units_of<C>(s_cls[c], ft_on);
 			if (k < chunks) {
 				break;
 			}
@@ -1212,16 +1212,16 @@ cudaError_t launch_mix_voice(gas_ctx *ctx, const gas_frame *d_src, int src_strid
 	cudaError_t e = cudaSuccess;
 	switch (ctx->g.channels) {
 		case 1:
-			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look);
+			e = gas_launch(k_mix_voice<1>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look, ctx->k3_legacy ? 0 : 1);
 			break;
 		case 2:
-			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look);
+			e = gas_launch(k_mix_voice<2>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look, ctx->k3_legacy ? 0 : 1);
 			break;
 		case 3:
-			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look);
+			e = gas_launch(k_mix_voice<3>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look, ctx->k3_legacy ? 0 : 1);
 			break;
 		default:
-			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look);
+			e = gas_launch(k_mix_voice<4>, dim3(grid), dim3(threads), smem, st, pdl, ctx->t, ctx->g, ctx->plan, d_src, src_stride, frames, (float *)d_bus, (float2 *)d_peaks, (const float4 *)ctx->d_rep, bus_f4, ctx->replicas, tile_floats, early_look, ctx->k3_legacy ? 0 : 1);
 			break;
 	}
 	ctx->launches++;
