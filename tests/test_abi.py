@@ -78,3 +78,32 @@ def test_product_does_not_reference_the_oracle():
                 text = open(os.path.join(d, f), errors="ignore").read()
                 assert "gas_oracle" not in text and "orc_" not in text and "from oracle" not in text and "import oracle" not in text, os.path.join(d, f)
                 assert "libgas_ref" not in text and "godot_lite" not in text and "ref_harness" not in text, os.path.join(d, f)
+
+
+def test_library_is_sm100a_and_uses_the_async_engines():
+    """The built library carries sm_100a SASS only, and its hot kernels use what DESIGN.md says they use: 1-D bulk copies (UBLKCP,
+    the TMA engine) and packed FFMA2 in the step kernel, per-thread async copies (LDGSTS) and FFMA2 in the voice-parallel kernel.
+    Static evidence (cuobjdump); needs no GPU."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    lib = os.path.join(ROOT, "godot-audio-spatializer_b200", "libgas_b200.so")
+    if not (os.path.exists(cuobjdump) and os.path.exists(lib)):
+        pytest.skip("cuobjdump or the built library is not available")
+    elf = subprocess.run([cuobjdump, "-lelf", lib], capture_output=True, text=True).stdout
+    archs = {ln.split(".")[-2] for ln in elf.splitlines() if ln.strip().endswith(".cubin")}
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True).stdout
+    per_fn, name = {}, None
+    for ln in sass.splitlines():
+        if "Function :" in ln:
+            name = ln.split("Function :")[1].strip()
+            per_fn[name] = []
+        elif name and "/*" in ln:
+            per_fn[name].append(ln)
+
+    def count(fn_substr, op):
+        return sum(sum(op in ln for ln in body) for fn, body in per_fn.items() if fn_substr in fn)
+
+    assert count("6k_stepE", "UBLKCP") > 0 and count("6k_stepE", "FFMA2") > 0
+    assert count("k_mix_voiceILi4E", "LDGSTS") > 0 and count("k_mix_voiceILi4E", "FFMA2") > 0
