@@ -340,3 +340,43 @@ def test_filter_tile_mode_b_many_units_ragged_frames(gas, orc, speakers):
                             blocks=3, start_late=1, silent_every=9, want_peak_every=5)
     got, want = _run_both(gas, orc, sc)
     _check(got, want, sc)
+
+
+def test_mixed_spatializers_in_one_block(gas, orc):
+    """Four AudioSpatializer resources in one context — 3D Mode A and Mode B with the attenuation filter, an effect chain, and an
+    unfiltered Mode B one (streaming kernel) — instances dealt round-robin to them: every kind of class meets in the same launch of the
+    voice-parallel kernel (filter-tile units of three different forms dealt to the same CTAs) beside the streaming kernel."""
+    V, F, blocks = 333, 320, 3
+    mode = abi.SPEAKER_SURROUND_51
+    cfg = dict(max_instances=V, max_voices=V, max_frames=F, max_spatializers=4, num_buses=3, speaker_mode=mode, mix_rate=48000.0)
+    inst = np.arange(V, dtype=np.int32)
+    listeners = np.array([abi.identity_listener(), S.synth.rotated_listener()], dtype=abi.listener)
+    areas = np.array([S.synth.reverb_area(n_listeners=2, reverb_bus=2, amount=0.4, uniformity=0.5)], dtype=abi.area)
+    fx = S.make_spatializer(S.default_scenario(effect_chain=[dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=3500.0, resonance=1.0, gain=0.4, stages=2),
+                                                             dict(mode=abi.FILTER_LOWPASS, cutoff_hz=9000.0, resonance=0.7, gain=1.0, stages=1)],
+                                               effect_gain_binding=0))
+    spats = [abi.spatializer_defaults(mix_channel_mode=0), abi.spatializer_defaults(mix_channel_mode=1), fx,
+             abi.spatializer_defaults(mix_channel_mode=1, attenuation_filter_db=0.0)]
+    voices = S.synth.make_voices(V)
+    voices["flags"][::7] |= abi.VOICE_WANT_PEAK
+    out = []
+    for mk in (lambda: gas.Mixer(**cfg), lambda: orc.OracleMixer(**cfg)):
+        with mk() as m:
+            for k, sp in enumerate(spats):
+                m.spatializer_set(k, sp)
+            m.instance_init(inst, inst % len(spats))
+            res = []
+            for b in range(blocks):
+                em = S.synth.make_emitters(V, block=b, dt=F / 48000.0, area_fraction=0.4)
+                m.gain_compute(em, listeners, areas, want_params=False)
+                if b == 0:
+                    m.instance_start(inst)
+                    m.voice_init(inst)
+                res.append(m.mix_block(voices, S.synth.make_sources(V, F, block=b), F, want_peaks=True))
+            out.append(res)
+    for b, ((bg, pg), (bw, pw)) in enumerate(zip(*out)):
+        assert np.array_equal(S.routing(bg), S.routing(bw)), f"block {b}: routing differs"
+        ok, worst, nbad = S.sample_close(bg, bw)
+        assert ok, f"block {b}: {nbad} samples out of tolerance, worst {worst:.3e}"
+        ok, worst, nbad = S.sample_close(pg[::7], pw[::7])
+        assert ok, f"block {b}: peaks differ (worst {worst:.3e})"
