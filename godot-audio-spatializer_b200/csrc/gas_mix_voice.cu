@@ -526,23 +526,19 @@ __device__ __forceinline__ void ft_stage_weights(const InstSends *__restrict__ s
 	}
 }
 
-// rows [0, nrows) x frames [i0, i0 + kFtFrames) of the unit: sum over its voices, added to the bus tile / buffers
-// PER_PAIR (Mode B): the voice's C pairs are C streams of their own, row (send, pair) sums stream pair of every voice.
-template <int C, bool PER_PAIR>
-__device__ __forceinline__ void ft_contract(const float *s_y, const float4 *s_w, int nv, int nrows, const int (&rowoff)[kFtRows / 4], int i0, int F,
+// rows [0, nrows) x frames [i0, i0 + kFtFrames) of the unit: sum over its voices, added to the bus tile / buffers.
+// A thread owns frame i0 + (tid % 64) of rows rg, rg + 4, ... (rg = tid / 64): N of them, a template parameter so that the loop over
+// the voices carries exactly N weight loads and 2 N packed FMAs (the row count is uniform over the warp).
+// PER_PAIR (Mode B): the voice's C pairs are C streams of their own, row (send, pair) sums stream `pair` of every voice.
+template <int C, bool PER_PAIR, int N>
+__device__ __forceinline__ void ft_contract_n(const float *s_y, const float4 *s_w, int nv, int nrows, const int (&rowoff)[kFtRows / 4], int i, int F,
 		float *__restrict__ bus, float *s_tile) {
 	const int f = threadIdx.x & (kFtFrames - 1), rg = threadIdx.x / kFtFrames;
-	const int mine = (nrows - rg + 3) >> 2; // rows rg, rg + 4, ...
-	const int i = i0 + f;
-	if (mine <= 0 || i >= F) {
-		return;
-	}
-	constexpr int kMine = kFtRows / 4;
 	const float tt = (float)i / (float)F; // upstream _mix_step_for_channel: t = i / F
 	const float2 t2 = make_float2(tt, tt);
-	float2 acc[kMine];
+	float2 acc[N];
 #pragma unroll
-	for (int q = 0; q < kMine; q++) {
+	for (int q = 0; q < N; q++) {
 		acc[q] = make_float2(0.f, 0.f);
 	}
 	const float *yp = s_y + f * 2;
@@ -552,48 +548,70 @@ __device__ __forceinline__ void ft_contract(const float *s_y, const float4 *s_w,
 		for (int v = 0; v < nv; v++) {
 			const float2 y = *reinterpret_cast<const float2 *>(yp + v * kFtYStride);
 #pragma unroll
-			for (int q = 0; q < kMine; q++) {
-				if (q < mine) {
-					const float4 w4 = wp[v * nrows + q * 4];
-					const float2 w = gas_ffma2(t2, make_float2(w4.z, w4.w), make_float2(w4.x, w4.y));
-					acc[q] = gas_ffma2(w, y, acc[q]);
-				}
+			for (int q = 0; q < N; q++) {
+				const float4 w4 = wp[v * nrows + q * 4];
+				const float2 w = gas_ffma2(t2, make_float2(w4.z, w4.w), make_float2(w4.x, w4.y));
+				acc[q] = gas_ffma2(w, y, acc[q]);
 			}
 		}
 	} else {
-		int ycol[kMine]; // pair of row rg + 4 q = stream of the voice it sums
+		int ycol[N]; // pair of row rg + 4 q = stream of the voice it sums
 #pragma unroll
-		for (int q = 0; q < kMine; q++) {
+		for (int q = 0; q < N; q++) {
 			ycol[q] = ((rg + q * 4) % C) * kFtYStride;
 		}
-#pragma unroll 2
+#pragma unroll 4
 		for (int v = 0; v < nv; v++) {
 #pragma unroll
-			for (int q = 0; q < kMine; q++) {
-				if (q < mine) {
-					const float2 y = *reinterpret_cast<const float2 *>(yp + v * (C * kFtYStride) + ycol[q]);
-					const float4 w4 = wp[v * nrows + q * 4];
-					const float2 w = gas_ffma2(t2, make_float2(w4.z, w4.w), make_float2(w4.x, w4.y));
-					acc[q] = gas_ffma2(w, y, acc[q]);
-				}
+			for (int q = 0; q < N; q++) {
+				const float2 y = *reinterpret_cast<const float2 *>(yp + v * (C * kFtYStride) + ycol[q]);
+				const float4 w4 = wp[v * nrows + q * 4];
+				const float2 w = gas_ffma2(t2, make_float2(w4.z, w4.w), make_float2(w4.x, w4.y));
+				acc[q] = gas_ffma2(w, y, acc[q]);
 			}
 		}
 	}
 #pragma unroll
-	for (int q = 0; q < kMine; q++) {
-		if (q < mine) {
-			const size_t o = (size_t)rowoff[q] + (size_t)i * 2;
-			if (s_tile) {
-				float2 *d = reinterpret_cast<float2 *>(s_tile + o); // one owner per (row, frame): no atomics
-				float2 cur = *d;
-				cur.x += acc[q].x;
-				cur.y += acc[q].y;
-				*d = cur;
-			} else {
-				atomicAdd(bus + o, acc[q].x);
-				atomicAdd(bus + o + 1, acc[q].y);
-			}
+	for (int q = 0; q < N; q++) {
+		const size_t o = (size_t)rowoff[q] + (size_t)i * 2;
+		if (s_tile) {
+			float2 *d = reinterpret_cast<float2 *>(s_tile + o); // one owner per (row, frame): no atomics
+			float2 cur = *d;
+			cur.x += acc[q].x;
+			cur.y += acc[q].y;
+			*d = cur;
+		} else {
+			atomicAdd(bus + o, acc[q].x);
+			atomicAdd(bus + o + 1, acc[q].y);
 		}
+	}
+}
+
+template <int C, bool PER_PAIR>
+__device__ __forceinline__ void ft_contract(const float *s_y, const float4 *s_w, int nv, int nrows, const int (&rowoff)[kFtRows / 4], int i0, int F,
+		float *__restrict__ bus, float *s_tile) {
+	const int f = threadIdx.x & (kFtFrames - 1), rg = threadIdx.x / kFtFrames;
+	const int mine = (nrows - rg + 3) >> 2; // rows rg, rg + 4, ...: 0 .. kFtRows / 4
+	const int i = i0 + f;
+	if (i >= F) {
+		return;
+	}
+	static_assert(kFtRows / 4 == 4, "one case per row count");
+	switch (mine) {
+		case 1:
+			ft_contract_n<C, PER_PAIR, 1>(s_y, s_w, nv, nrows, rowoff, i, F, bus, s_tile);
+			break;
+		case 2:
+			ft_contract_n<C, PER_PAIR, 2>(s_y, s_w, nv, nrows, rowoff, i, F, bus, s_tile);
+			break;
+		case 3:
+			ft_contract_n<C, PER_PAIR, 3>(s_y, s_w, nv, nrows, rowoff, i, F, bus, s_tile);
+			break;
+		case 4:
+			ft_contract_n<C, PER_PAIR, 4>(s_y, s_w, nv, nrows, rowoff, i, F, bus, s_tile);
+			break;
+		default:
+			break; // no row of this thread's group in the class
 	}
 }
 
