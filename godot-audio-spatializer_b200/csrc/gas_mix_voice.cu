@@ -626,6 +626,9 @@ template <int VAR, int C>
 __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, const VoiceRec *__restrict__ recs, const InstSends *__restrict__ sends,
 		const int2 *__restrict__ list, int nv, const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float *s_tile,
 		float2 *__restrict__ peaks, float *s_y, float4 *s_w) {
+	// the first source tile is requested before anything else: its DRAM round trip runs beside the dependent loads of the set-up
+	// (list -> voice record -> processor state, list -> sends -> weight tile)
+	ft_prefetch(src, src_stride, list, nv, 0, F, s_y);
 	const int vl = threadIdx.x >> 1, side = threadIdx.x & 1; // filter phase: lane = (voice, side)
 	const bool active = vl < nv;
 	const int j = active ? list[vl].x : 0;
@@ -759,7 +762,6 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 		const int r = (int)threadIdx.x / kFtFrames + q * 4;
 		rowoff[q] = r < R ? (nth_set_bit(ci.mask, r / C) * C + r % C) * F * 2 : 0;
 	}
-	ft_prefetch(src, src_stride, list, nv, 0, F, s_y);
 	for (int i0 = 0, ti = 0; i0 < F; i0 += kFtFrames, ti++) {
 		float *buf = s_y + (ti & 1) * kFtYFloats;
 		gas_cp_async_wait_all(); // this thread's copies of the tile have landed ...
@@ -845,6 +847,7 @@ __device__ __noinline__ void ft_unit_b(const DevTables &t, const ClassInfo &ci, 
 		const int2 *__restrict__ list, int nv, const gas_frame *__restrict__ src, int src_stride, int F, float *__restrict__ bus, float *s_tile,
 		float2 *__restrict__ peaks, float *s_y, float4 *s_w, float *s_t) {
 	constexpr int kPer = 2 * C; // lanes per voice
+	ft_prefetch(src, src_stride, list, nv, 0, F, s_y + kFtYFloats); // first x tile: requested before the set-up's dependent loads
 	const int vl = (int)threadIdx.x / kPer, rem = (int)threadIdx.x % kPer, c = rem >> 1, side = rem & 1;
 	const bool active = vl < nv;
 	const int j = active ? list[vl].x : 0;
@@ -894,7 +897,6 @@ __device__ __noinline__ void ft_unit_b(const DevTables &t, const ClassInfo &ci, 
 		pk = fmaxf(pk, fabsf(y));
 		return y;
 	};
-	ft_prefetch(src, src_stride, list, nv, 0, F, xbuf);
 	for (int i0 = 0, ti = 0; i0 < F; i0 += kFtFrames, ti++) {
 		const float *xb = xbuf + (ti & 1) * (kFtVoicesB * kFtYStride);
 		gas_cp_async_wait_all();
