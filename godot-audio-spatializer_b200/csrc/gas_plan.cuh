@@ -786,15 +786,18 @@ static __device__ __forceinline__ void plan_block(const PlanGroup &G, PlanSmem &
 	group_stamp(G, 20);
 	// ---- instance part: prev <- cur (2 lanes per instance), after every instance's gains are in place -------------------------
 	{
-		if (wait_total > 0) {
-			while (ld_acquire(&t.blk[BLK_GAIN_DONE]) < wait_total) {
-				__nanosleep(40);
-			}
-		}
 		const BusDetails *curs = t.inst_cur;
 		BusDetails *prev_wr = t.inst_prev + (size_t)(parity ^ 1) * t.max_instances;
 		const int x = G.tid & 1;
 		for (int q = gtid >> 1; q < a.inst_hwm; q += gthreads >> 1) {
+			if (wait_total > 0 && q != own_q) {
+				// this block's gains of instance q are in place (its flag), or no gain task of the launch is outstanding at all (an
+				// instance without an emitter in this block).  Per instance instead of one wait for every warp of the launch: when
+				// instance, emitter and voice indices coincide (q == own_q, the common layout) a CTA waits for no other CTA at all.
+				while (ld_acquire(&t.inst_seq[q]) != b + 1 && ld_acquire(&t.blk[BLK_GAIN_DONE]) < wait_total) {
+					__nanosleep(40);
+				}
+			}
 			// one round of loads: the first two buses (calculate_spatialization never produces more), the rest only if present
 			const BusDetails *cs = &curs[q];
 			BusDetails *pw = &prev_wr[q];

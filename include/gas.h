@@ -364,10 +364,13 @@ GAS_API int gas_mix_block_device(gas_ctx *ctx, int32_t n_voices, const gas_voice
  * gas_step_join_device (gas_sync, gas_mix_block* and the reduce calls join by themselves).  gas_mix_block* is refused
  * (GAS_ERR_STATE) while a planned block is waiting.  Captured into graphs like the other device-resident calls: a replayed graph
  * must then meet the device in the state it was captured in (a planned block waiting, or none).
- * Residency: a step launch takes one whole SM per CTA and its control warps wait for every CTA of the launch.  While a pipelined run is
- * in flight no kernel that spin-waits on other GPUs (an NCCL collective, a hand-written barrier) may be enqueued on this GPU from
- * another stream: it can take an SM the launch needs and wait for peers whose own SMs are held the same way.  Synchronise (gas_sync)
- * before such a call; the library's own exchange (gas_reduce_bus_exchange_device) is ordered so that it cannot close that cycle. */
+ * Residency: a step launch takes one whole SM per CTA.  Its control warps wait for the gains of an instance only where a voice or an
+ * instance is planned by another lane pair than the one that computed its gains: with emitter i, instance i and voice i at the same
+ * index (the layout bench.py uses) no CTA waits for another one, otherwise CTAs of a launch wait for each other and the launch needs
+ * all of them resident.  So: while a pipelined run is in flight do not enqueue, from another stream of this GPU, a kernel that
+ * spin-waits on other GPUs (an NCCL collective, a hand-written barrier) — it can take an SM the launch needs and wait for peers whose
+ * own SMs are held the same way.  Synchronise (gas_sync) before such a call; the library's own exchange
+ * (gas_reduce_bus_exchange_device) is ordered so that it cannot close that cycle. */
 typedef struct gas_step_next {
 	int32_t n_emitters;
 	const gas_emitter *d_emitters;
