@@ -617,6 +617,9 @@ EXTRA_CONFIGS = [
     dict(name="configs[2] with the attenuation filter ON, Mode A (process_frames: 2 biquads per voice-frame)", voices=16384, frames=512,
          speaker_mode=3, num_buses=2, kind="A-filter", n_send=1.25,
          sc=dict(spat=dict(mix_channel_mode=0), area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25)),
+    dict(name="configs[2] with the attenuation filter ON, Mode B (mix_channel: 8 biquads per voice-frame)", voices=16384, frames=512,
+         speaker_mode=3, num_buses=2, kind="B-filter", n_send=1.25,
+         sc=dict(spat=dict(mix_channel_mode=1), area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25), steps=48),
     dict(name="configs[4] corner: 256 voices x 128-frame blocks, stereo, filter off", voices=256, frames=128, speaker_mode=0, num_buses=2,
          kind="stream", n_send=1.25, sc=dict(spat=dict(mix_channel_mode=1, unit_size=1.0, attenuation_filter_db=-80.0),
                                              area=dict(reverb_bus=1, amount=0.5), area_fraction=0.25, r_min=10.0)),
@@ -1259,7 +1262,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE.json configurations")
-    ap.add_argument("--configs-budget", type=float, default=100.0, help="seconds after which remaining secondary configurations are skipped")
+    ap.add_argument("--configs-budget", type=float, default=130.0, help="seconds after which remaining secondary configurations are skipped")
     ap.add_argument("--area-fraction", type=float, default=None, help="fraction of voices inside the reverb area (experiments)")
     ap.add_argument("--resident-leg", action="store_true", help="internal: the e2e leg with device-resident sources, in a process of its own")
     args = ap.parse_args()
