@@ -617,9 +617,14 @@ __device__ __forceinline__ void ft_contract(const float *s_y, const float4 *s_w,
 
 // FT_COPY: Mode A below the filter threshold (peaks only): y = x.  FT_E_FAST1 / 2 / (4): effect chains whose longest member in the
 // unit has 1 / 2 / up to 4 biquads per side (the slots beyond a lane's own chain are predicated off, so fewer slots = fewer issue slots)
-enum : int { FT_A = 0, FT_E_FAST = 1, FT_E_SLOW = 2, FT_COPY = 3, FT_E_FAST1 = 4, FT_E_FAST2 = 5 };
-__host__ __device__ constexpr bool ft_is_fast(int var) { return var == FT_E_FAST || var == FT_E_FAST1 || var == FT_E_FAST2; }
-__host__ __device__ constexpr int ft_slots(int var) { return var == FT_E_FAST1 ? 1 : (var == FT_E_FAST2 ? 2 : kFtFastStages); }
+// FT_E_U1 / U2 / U4: every voice of the unit has exactly 1 / 2 / 4 biquads per side (the usual case: one chain per spatializer), so the
+// slots carry no predicate at all.
+enum : int { FT_A = 0, FT_E_FAST = 1, FT_E_SLOW = 2, FT_COPY = 3, FT_E_FAST1 = 4, FT_E_FAST2 = 5, FT_E_U1 = 6, FT_E_U2 = 7, FT_E_U4 = 8 };
+__host__ __device__ constexpr bool ft_uniform(int var) { return var == FT_E_U1 || var == FT_E_U2 || var == FT_E_U4; }
+__host__ __device__ constexpr bool ft_is_fast(int var) { return var == FT_E_FAST || var == FT_E_FAST1 || var == FT_E_FAST2 || ft_uniform(var); }
+__host__ __device__ constexpr int ft_slots(int var) {
+	return (var == FT_E_FAST1 || var == FT_E_U1) ? 1 : ((var == FT_E_FAST2 || var == FT_E_U2) ? 2 : kFtFastStages);
+}
 
 // One unit: voices list[0 .. nv) of class `ci`.  Every thread of the CTA takes part (the barriers are CTA-wide).
 template <int VAR, int C>
@@ -728,7 +733,7 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 		} else if (ft_is_fast(VAR)) {
 #pragma unroll
 			for (int s = 0; s < kSlots; s++) {
-				if (s < n_slot) {
+				if (ft_uniform(VAR) || s < n_slot) {
 					const float pre = y;
 					y = y * sc[s][0] + sh[s][2] * sc[s][1] + sh[s][3] * sc[s][2] + sh[s][0] * sc[s][3] + sh[s][1] * sc[s][4];
 					sh[s][1] = sh[s][0];
@@ -772,22 +777,34 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 		// ---- filter phase: in place on the tile ----
 		if (active) {
 			float *xr = buf + vl * kFtYStride + side;
-			for (int k0 = 0; k0 < kFtFrames && i0 + k0 < F; k0 += 8) {
-				if (i0 + k0 + 8 <= F) { // a whole trip inside the block: no per-frame bounds test between the recurrence steps
-					float xv[8];
+			// whole 8-frame trips of the tile: no per-frame bounds test between the recurrence steps, and the next trip's frames are
+			// read from shared memory while this trip's recurrence runs
+			const int n_frames = min(kFtFrames, F - i0);
+			const int trips = n_frames >> 3;
+			float xv[8], xq[8];
 #pragma unroll
-					for (int k = 0; k < 8; k++) {
-						xv[k] = xr[(k0 + k) * 2];
-					}
+			for (int k = 0; k < 8; k++) {
+				xv[k] = trips > 0 ? xr[k * 2] : 0.f;
+			}
+#pragma unroll 2
+			for (int tr = 0; tr < trips; tr++) {
+				const int k0 = tr * 8;
+				const bool more = tr + 1 < trips;
 #pragma unroll
-					for (int k = 0; k < 8; k++) {
-						xr[(k0 + k) * 2] = step(xv[k]);
-					}
-				} else {
-					for (int k = 0; k < 8 && i0 + k0 + k < F; k++) {
-						xr[(k0 + k) * 2] = step(xr[(k0 + k) * 2]);
-					}
+				for (int k = 0; k < 8; k++) {
+					xq[k] = more ? xr[(k0 + 8 + k) * 2] : 0.f;
 				}
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					xr[(k0 + k) * 2] = step(xv[k]);
+				}
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					xv[k] = xq[k];
+				}
+			}
+			for (int k = trips * 8; k < n_frames; k++) { // the block's last frames when F is not a multiple of 8
+				xr[k * 2] = step(xr[k * 2]);
 			}
 		}
 		__syncthreads();
@@ -911,23 +928,34 @@ __device__ __noinline__ void ft_unit_b(const DevTables &t, const ClassInfo &ci, 
 		if (active) {
 			const float *xr = xb + vl * kFtYStride + side;
 			float *yr = ybuf + (vl * C + c) * kFtYStride + side;
-			for (int k0 = 0; k0 < kFtFrames && i0 + k0 < F; k0 += 8) {
-				if (i0 + k0 + 8 <= F) {
-					float xv[8], tv[8];
+			const int n_frames = min(kFtFrames, F - i0);
+			const int trips = n_frames >> 3;
+			float xv[8], xq[8];
 #pragma unroll
-					for (int k = 0; k < 8; k++) {
-						xv[k] = xr[(k0 + k) * 2];
-						tv[k] = s_t[k0 + k];
-					}
+			for (int k = 0; k < 8; k++) {
+				xv[k] = trips > 0 ? xr[k * 2] : 0.f;
+			}
+#pragma unroll 2
+			for (int tr = 0; tr < trips; tr++) {
+				const int k0 = tr * 8;
+				const bool more = tr + 1 < trips;
+				float tv[8];
 #pragma unroll
-					for (int k = 0; k < 8; k++) {
-						yr[(k0 + k) * 2] = step(xv[k], tv[k]);
-					}
-				} else {
-					for (int k = 0; k < 8 && i0 + k0 + k < F; k++) {
-						yr[(k0 + k) * 2] = step(xr[(k0 + k) * 2], s_t[k0 + k]);
-					}
+				for (int k = 0; k < 8; k++) {
+					xq[k] = more ? xr[(k0 + 8 + k) * 2] : 0.f;
+					tv[k] = s_t[k0 + k];
 				}
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					yr[(k0 + k) * 2] = step(xv[k], tv[k]);
+				}
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					xv[k] = xq[k];
+				}
+			}
+			for (int k = trips * 8; k < n_frames; k++) {
+				yr[k * 2] = step(xr[k * 2], s_t[k]);
 			}
 		}
 		__syncthreads();
@@ -966,9 +994,10 @@ __device__ __noinline__ void ft_unit_b(const DevTables &t, const ClassInfo &ci, 
 }
 
 // biquads per side of the longest effect chain among voices list[0 .. nv) (CTA-uniform result; every thread calls it)
-__device__ int ft_max_stages(const VoiceRec *__restrict__ recs, const int2 *__restrict__ list, int nv, int *s_scratch) {
+__device__ int ft_max_stages(const VoiceRec *__restrict__ recs, const int2 *__restrict__ list, int nv, int *s_scratch, bool *all_equal) {
 	if (threadIdx.x == 0) {
-		*s_scratch = 0;
+		s_scratch[0] = 0;
+		s_scratch[1] = 1 << 20;
 	}
 	__syncthreads();
 	if ((int)threadIdx.x < nv) {
@@ -977,11 +1006,13 @@ __device__ int ft_max_stages(const VoiceRec *__restrict__ recs, const int2 *__re
 		for (int e = 0; e < rec->n_fx && e < GAS_MAX_EFFECTS; e++) {
 			total += rec->fx_stages[e];
 		}
-		atomicMax(s_scratch, total);
+		atomicMax(&s_scratch[0], total);
+		atomicMin(&s_scratch[1], total);
 	}
 	__syncthreads();
-	const int m = *s_scratch;
-	__syncthreads(); // the scratch word may be reset by the next unit
+	const int m = s_scratch[0];
+	*all_equal = s_scratch[1] == m;
+	__syncthreads(); // the scratch words may be reset by the next unit
 	return m;
 }
 
@@ -1006,7 +1037,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 	GAS_DYN_SMEM(float, 16, s_tile);
 	__shared__ ClassInfo s_cls[GAS_MAX_CLASSES];
 	__shared__ int s_ncls;
-	__shared__ int s_ft_scratch;
+	__shared__ int s_ft_scratch[2];
 	GAS_GRID_DEP_LAUNCH();
 	// Programmatic dependent launch: this kernel may become resident while the streaming kernel (its stream predecessor)
 	// still runs.  What it reads first — the class table of the block — was written by the prologue, which completed
@@ -1120,8 +1151,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_mix_voice(DevTables t,
 				ft_unit<FT_COPY, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
 			}
 		} else {
-			const int longest = ft_max_stages(recs, list, nv, &s_ft_scratch);
-			if (longest <= 1) {
+			bool same = false;
+			const int longest = ft_max_stages(recs, list, nv, s_ft_scratch, &same);
+			if (same && longest == 1) {
+				ft_unit<FT_E_U1, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+			} else if (same && longest == 2) {
+				ft_unit<FT_E_U2, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+			} else if (same && longest == 4) {
+				ft_unit<FT_E_U4, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
+			} else if (longest <= 1) {
 				ft_unit<FT_E_FAST1, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
 			} else if (longest == 2) {
 				ft_unit<FT_E_FAST2, C>(t, ci, recs, sends, list, nv, src, src_stride, F, bus, tile_p, peaks, s_y, s_w);
