@@ -90,7 +90,7 @@ def check(got, want, sc):
         if not np.array_equal(S.routing(bg), S.routing(bw)):
             return f"block {b}: routing differs"
         with np.errstate(invalid="ignore"):
-            if np.nanmax(np.abs(np.where(np.isfinite(bw), bw, 0.0))) > 1e4:
+            if np.nanmax(np.abs(np.where(np.isfinite(bw), bw, 0.0))) > 50.0:  # (stable scenarios stay below ~10: the amplitude is scaled to the voice count)
                 # the reference's own recurrence diverges here (a filter driven outside its stable range): every rounding difference
                 # is amplified without bound from now on, so only what came before is comparable
                 return None
