@@ -480,7 +480,7 @@ static_assert(kWarpsPerCta * 32 == 4 * kFtFrames, "contraction mapping: 4 row gr
 // anything wider than the weight tile stays on the per-warp path)
 template <int C>
 __device__ __forceinline__ bool ft_class(const ClassInfo &ci, int ft_on) {
-	return ft_on && !(ci.flags & CLS_GENERIC) && ci.n_send * C <= kFtRows;
+	return ft_on && !(ci.flags & CLS_GENERIC) && ci.n_send <= 4 && ci.n_send * C <= kFtRows;
 }
 // voices per unit of a class, given the block's stream budget per unit (Mode B: C streams per voice and side)
 template <int C>
@@ -612,6 +612,63 @@ __device__ __forceinline__ void ft_contract(const float *s_y, const float4 *s_w,
 			break;
 		default:
 			break; // no row of this thread's group in the class
+	}
+}
+
+// Mode A / effect chains: every row of the class sums the SAME stream y_v, so four thread groups that own different rows would each
+// read the whole y tile (shared-memory bandwidth, not issue slots, is what the contraction runs out of).  Here the four groups
+// split the VOICES instead (group g: voices g, g + 4, ...) and every thread carries all NS * C rows of its frame: the y tile is
+// read once.  The four partial sums of a (row, frame) meet in the bus tile one group after the other, a barrier apart.  Every
+// thread of the CTA calls this (it contains barriers).
+template <int C, int NS>
+__device__ __forceinline__ void ft_contract_split(const float *s_y, const float4 *s_w, int nv, const int (&busoff)[4], int i0, int F,
+		float *__restrict__ bus, float *s_tile) {
+	constexpr int R = NS * C;
+	const int f = threadIdx.x & (kFtFrames - 1), g = threadIdx.x / kFtFrames;
+	const int i = i0 + f;
+	const bool in_block = i < F;
+	float2 acc[R];
+#pragma unroll
+	for (int r = 0; r < R; r++) {
+		acc[r] = make_float2(0.f, 0.f);
+	}
+	if (in_block) {
+		const float tt = (float)i / (float)F; // upstream _mix_step_for_channel: t = i / F
+		const float2 t2 = make_float2(tt, tt);
+		const float *yp = s_y + f * 2;
+#pragma unroll 2
+		for (int v = g; v < nv; v += 4) {
+			const float2 y = *reinterpret_cast<const float2 *>(yp + v * kFtYStride);
+			const float4 *wp = s_w + v * R;
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				const float4 w4 = wp[r];
+				const float2 w = gas_ffma2(t2, make_float2(w4.z, w4.w), make_float2(w4.x, w4.y));
+				acc[r] = gas_ffma2(w, y, acc[r]);
+			}
+		}
+	}
+#pragma unroll
+	for (int ph = 0; ph < 4; ph++) {
+		if (ph == g && in_block) {
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				const size_t o = (size_t)busoff[r / C] + ((size_t)(r % C) * F + i) * 2;
+				if (s_tile) {
+					float2 *d = reinterpret_cast<float2 *>(s_tile + o); // this group's turn: one owner per (row, frame)
+					float2 cur = *d;
+					cur.x += acc[r].x;
+					cur.y += acc[r].y;
+					*d = cur;
+				} else {
+					atomicAdd(bus + o, acc[r].x);
+					atomicAdd(bus + o + 1, acc[r].y);
+				}
+			}
+		}
+		if (ph < 3) {
+			__syncthreads();
+		}
 	}
 }
 
@@ -760,12 +817,11 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 		pk = fmaxf(pk, fabsf(y));
 		return y;
 	};
-	// contraction: this thread's rows rg, rg + 4, ... -> float offset of (bus, pair, frame 0) in the bus layout
-	int rowoff[kFtRows / 4];
+	// contraction: float offset of (bus of send s, pair 0, frame 0) in the bus layout
+	int busoff[4];
 #pragma unroll
-	for (int q = 0; q < kFtRows / 4; q++) {
-		const int r = (int)threadIdx.x / kFtFrames + q * 4;
-		rowoff[q] = r < R ? (nth_set_bit(ci.mask, r / C) * C + r % C) * F * 2 : 0;
+	for (int q = 0; q < 4; q++) {
+		busoff[q] = q < ci.n_send ? nth_set_bit(ci.mask, q) * C * F * 2 : 0;
 	}
 	for (int i0 = 0, ti = 0; i0 < F; i0 += kFtFrames, ti++) {
 		float *buf = s_y + (ti & 1) * kFtYFloats;
@@ -809,7 +865,22 @@ __device__ __noinline__ void ft_unit(const DevTables &t, const ClassInfo &ci, co
 		}
 		__syncthreads();
 		// ---- contraction ----
-		ft_contract<C, false>(buf, s_w, nv, R, rowoff, i0, F, bus, s_tile);
+		switch (ci.n_send) { // (0: nothing to add, the block only advances state / peaks)
+			case 1:
+				ft_contract_split<C, 1>(buf, s_w, nv, busoff, i0, F, bus, s_tile);
+				break;
+			case 2:
+				ft_contract_split<C, 2>(buf, s_w, nv, busoff, i0, F, bus, s_tile);
+				break;
+			case 3:
+				ft_contract_split<C, 3>(buf, s_w, nv, busoff, i0, F, bus, s_tile);
+				break;
+			case 4:
+				ft_contract_split<C, 4>(buf, s_w, nv, busoff, i0, F, bus, s_tile);
+				break;
+			default:
+				break;
+		}
 	}
 	__syncthreads(); // the next unit's copies and weights overwrite what the last contraction read
 	if (active) {
