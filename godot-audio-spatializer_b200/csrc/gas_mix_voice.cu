@@ -466,14 +466,15 @@ __device__ void voice_chunk_s(const DevTables &t, const ChunkArgs &a, const gas_
 // the grid (the filter phase takes F serial steps however many lanes it has: more, smaller units are faster).
 constexpr int kFtVoices = 56;                              // voices per unit (2 lanes each in the filter phase): 16384 voices on 2 x 148 CTAs
 constexpr int kFtFrames = 64;                              // frames per tile
-constexpr int kFtYStride = kFtFrames * 2 + 4;              // floats per voice row of a tile (rows stay 16-byte aligned for the async copies;
-                                                           // +4: the (voice, side) lanes of a warp spread over the banks, two per bank)
+constexpr int kFtYStride = kFtFrames * 2 + 2;              // floats per voice row of a tile: +2 puts the 32 (voice, side) lanes of a warp on 32
+                                                           // different banks in the filter phase (rows are then 8-byte aligned only, hence
+                                                           // the 8-byte async copies)
 constexpr int kFtRows = 16;                                // weight rows (send x pair) of a class: 4 sends (2 current + 2 fading out) x 4 pairs
-constexpr int kFtYFloats = kFtVoices * kFtYStride;         // 7392 per tile buffer; two buffers: the tile being worked on and the next one in flight
+constexpr int kFtYFloats = kFtVoices * kFtYStride;         // 7280 per tile buffer; two buffers: the tile being worked on and the next one in flight
 constexpr int kFtWFloats = kFtVoices * kFtRows * 4;        // 3584
 constexpr int kFtSmemBytes = (2 * kFtYFloats + kFtWFloats + kFtFrames) * 4; // tile buffers | weight tile | t of the tile's frames
 constexpr int kFtFastStages = 4;                           // effect chains with up to this many biquads per side keep them in registers
-static_assert((kFtYFloats * 4) % 16 == 0 && (kFtYStride * 4) % 16 == 0, "tile rows are written and the weight tile behind them is read 16 bytes at a time");
+static_assert((kFtYFloats * 4) % 16 == 0 && (kFtYStride * 4) % 8 == 0, "tile rows are written 8 bytes, the weight tile behind them is read 16 bytes at a time");
 static_assert(kWarpsPerCta * 32 == 4 * kFtFrames, "contraction mapping: 4 row groups x kFtFrames frames");
 
 // (the planner sends voices with more than two buses on a side to the generic class, so an ordinary class has at most 4 sends;
@@ -495,19 +496,20 @@ __device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
 	return m ? (__ffs(m) - 1) : 0;
 }
 
-// source frames [i0, i0 + kFtFrames) of the unit's voices -> tile buffer, asynchronously (silent voices: zeros)
+// source frames [i0, i0 + kFtFrames) of the unit's voices -> tile buffer, asynchronously, one frame (8 bytes) per copy: consecutive
+// threads take consecutive frames of a row (silent voices: zeros)
 __device__ __forceinline__ void ft_prefetch(const gas_frame *__restrict__ src, int src_stride, const int2 *__restrict__ list, int nv, int i0, int F,
 		float *buf) {
-	const int chunks = min(kFtFrames, F - i0) >> 1; // 16-byte chunks (2 frames) per row; F is even
-	for (int idx = threadIdx.x; idx < nv * (kFtFrames / 2); idx += blockDim.x) {
-		const int v = idx / (kFtFrames / 2), ch = idx % (kFtFrames / 2);
-		if (ch < chunks) {
+	const int n_frames = min(kFtFrames, F - i0);
+	for (int idx = threadIdx.x; idx < nv * kFtFrames; idx += blockDim.x) {
+		const int v = idx / kFtFrames, fr = idx % kFtFrames;
+		if (fr < n_frames) {
 			const int srow = list[v].y;
-			float *dst = buf + v * kFtYStride + ch * 4;
+			float *dst = buf + v * kFtYStride + fr * 2;
 			if (srow >= 0) {
-				gas_cp_async_16(dst, src + (size_t)srow * src_stride + i0 + ch * 2);
+				gas_cp_async_8(dst, src + (size_t)srow * src_stride + i0 + fr);
 			} else {
-				*reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+				*reinterpret_cast<float2 *>(dst) = make_float2(0.f, 0.f);
 			}
 		}
 	}

@@ -74,9 +74,12 @@ static __device__ __forceinline__ void gas_bulk_g2s_hint(void *dst, const void *
 			: "memory");
 }
 
-// ---- per-thread async copies global -> shared (SASS: LDGSTS), 16 bytes each, L1 bypassed ------------------------------------
+// ---- per-thread async copies global -> shared (SASS: LDGSTS) ---------------------------------------------------------------
 static __device__ __forceinline__ void gas_cp_async_16(void *smem_dst, const void *gsrc) {
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gas_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+static __device__ __forceinline__ void gas_cp_async_8(void *smem_dst, const void *gsrc) { // (8-byte copies exist in the .ca form only)
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(gas_smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 // all of this thread's async copies so far have landed in shared memory (visible to the thread; a barrier publishes them to the CTA)
 static __device__ __forceinline__ void gas_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }

@@ -78,6 +78,13 @@ static inline void gas_cp_async_16(void *smem_dst, const void *gsrc) {
 	}
 	memcpy(smem_dst, gsrc, 16);
 }
+static inline void gas_cp_async_8(void *smem_dst, const void *gsrc) {
+	if ((((uintptr_t)smem_dst | (uintptr_t)gsrc) & 7u) != 0) {
+		fprintf(stderr, "[emu] cp.async 8: misaligned copy (dst %p, src %p)\n", smem_dst, gsrc);
+		abort();
+	}
+	memcpy(smem_dst, gsrc, 8);
+}
 static inline void gas_cp_async_wait_all() {}
 
 // ---- named barriers ----------------------------------------------------------------------------------------------------
