@@ -380,3 +380,16 @@ def test_mixed_spatializers_in_one_block(gas, orc):
         assert ok, f"block {b}: {nbad} samples out of tolerance, worst {worst:.3e}"
         ok, worst, nbad = S.sample_close(pg[::7], pw[::7])
         assert ok, f"block {b}: peaks differ (worst {worst:.3e})"
+
+
+@pytest.mark.parametrize("kind", ["A", "B", "E"])
+def test_filter_tile_without_a_bus_tile(gas, orc, kind):
+    """2048-frame blocks on three 7.1 buses: the bus layout (192 KiB) does not fit the CTA's shared-memory tile, so the voice-parallel
+    kernel adds its contraction results straight into the bus buffers."""
+    kw = dict(A=dict(spat=dict(mix_channel_mode=0)), B=dict(spat=dict(mix_channel_mode=1)),
+              E=dict(effect_chain=[dict(mode=abi.FILTER_HIGHSHELF, cutoff_hz=4000.0, resonance=1.0, gain=0.3, stages=2)],
+                     effect_gain_binding=0))[kind]
+    sc = S.default_scenario(name=f"ft-notile-{kind}", voices=70, frames=2048, speaker_mode=abi.SPEAKER_SURROUND_71, num_buses=3, blocks=2,
+                            area=dict(reverb_bus=1, amount=0.5, uniformity=0.3), area_fraction=0.5, want_peak_every=3, **kw)
+    got, want = _run_both(gas, orc, sc)
+    _check(got, want, sc)
