@@ -447,23 +447,26 @@ __device__ void voice_chunk_s(const DevTables &t, const ChunkArgs &a, const gas_
 	}
 }
 
-// ---- filter-tile path: Mode A and effect chains of the ordinary (non-generic) classes ------------------------------------
+// ---- filter-tile path: the ordinary (non-generic) classes of every mode -----------------------------------------------------
 // The recurrence and the cross-voice sum are two different shapes of work, so they get two different thread mappings inside
 // one CTA, handing over through shared memory, a tile of kFtFrames frames at a time:
-//   source tiles    the voices' rows of the NEXT tile are copied global -> shared memory asynchronously (cp.async, 16 bytes per
+//   source tiles    the voices' rows of the NEXT tile are copied global -> shared memory asynchronously (cp.async, one frame per
 //                   thread and copy) while the current tile is worked on: a tile of work (> 1 us) covers the DRAM latency,
 //                   which a register prefetch one 8-frame trip ahead (the per-warp form) does not.
-//   filter phase    one lane per (voice, side): nothing but the biquads (state in registers for the whole block) and the
-//                   block peak, in place on the tile in shared memory (x in, y out).  The lanes carry no ramps, no
-//                   cross-lane reduction and no atomics (the per-warp form above spends three quarters of its instructions on
-//                   those, inside the serial loop, and its red.shared.add.f32 compiles to a compare-and-swap loop).
-//   contraction     one thread per (frame, row group), all 256 threads: bus[b][c][i] += (p + t (n - p)) y_v[i] summed over the
-//                   voices of the unit, weights {p_L, p_R, n_L - p_L, n_R - p_R} staged once per unit, read as 16-byte broadcasts,
-//                   two packed FMAs (FFMA2) per (voice, row), accumulators in registers, added to the CTA's bus tile without
-//                   atomics (every (row, frame) has one owner).  The ramp is evaluated as p + t (n - p) instead of the
-//                   reference's n t + (1 - t) p: within 2 ulp of it, far inside the 1e-5 tolerance.
-// A unit is a batch of up to kFtVoices voices of one class; the batch size is chosen so that the units of a block just cover
-// the grid (the filter phase takes F serial steps however many lanes it has: more, smaller units are faster).
+//   filter phase    one lane per stream — (voice, side) in Mode A and effect chains, (voice, pair, side) in Mode B: nothing but
+//                   the biquads (state in registers for the whole block), the Mode B mix_channel ramp and the block peak, on the
+//                   tile in shared memory (Mode A / effects: in place; Mode B: from the x tile into the stream's own row of the
+//                   y tile).  The lanes carry no bus ramps, no cross-lane reduction and no atomics (the per-warp form above spends
+//                   three quarters of its instructions on those, inside the serial loop, and its red.shared.add.f32 compiles to a
+//                   compare-and-swap loop).
+//   contraction     all 256 threads: bus[b][c][i] += (p + t (n - p)) y[i] summed over the voices of the unit, weights
+//                   {p_L, p_R, n_L - p_L, n_R - p_R} staged once per unit, read as 16-byte broadcasts, two packed FMAs (FFMA2) per
+//                   (voice, row), accumulators in registers, added to the CTA's bus tile without atomics.  Mode B: a thread owns
+//                   (frame, row group); Mode A / effects: the thread groups split the voices (ft_contract_split).  The ramp is
+//                   evaluated as p + t (n - p) instead of the reference's n t + (1 - t) p: within 2 ulp of it, far inside the
+//                   1e-5 tolerance.
+// A unit is a batch of voices of one class (up to kFtVoices streams per side); the batch size is chosen so that the units of a
+// block just cover the grid (the filter phase takes F serial steps however many lanes it has: more, smaller units are faster).
 constexpr int kFtVoices = 56;                              // voices per unit (2 lanes each in the filter phase): 16384 voices on 2 x 148 CTAs
 constexpr int kFtFrames = 64;                              // frames per tile
 constexpr int kFtYStride = kFtFrames * 2 + 2;              // floats per voice row of a tile: +2 puts the 32 (voice, side) lanes of a warp on 32
@@ -475,7 +478,7 @@ constexpr int kFtWFloats = kFtVoices * kFtRows * 4;        // 3584
 constexpr int kFtSmemBytes = (2 * kFtYFloats + kFtWFloats + kFtFrames) * 4; // tile buffers | weight tile | t of the tile's frames
 constexpr int kFtFastStages = 4;                           // effect chains with up to this many biquads per side keep them in registers
 static_assert((kFtYFloats * 4) % 16 == 0 && (kFtYStride * 4) % 8 == 0, "tile rows are written 8 bytes, the weight tile behind them is read 16 bytes at a time");
-static_assert(kWarpsPerCta * 32 == 4 * kFtFrames, "contraction mapping: 4 row groups x kFtFrames frames");
+static_assert(kWarpsPerCta * 32 == 4 * kFtFrames, "contraction mapping: 4 thread groups (row groups / voice groups) x kFtFrames frames");
 
 // (the planner sends voices with more than two buses on a side to the generic class, so an ordinary class has at most 4 sends;
 // anything wider than the weight tile stays on the per-warp path)
